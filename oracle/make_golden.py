@@ -1,0 +1,243 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference functions.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden
+
+The reference has no tests or golden vectors of its own, so
+parity is pinned by recording what its functions return on seeded inputs.
+Inputs are stored next to the outputs, so the fixtures do not depend on RNG
+reproducibility across machines.  Environment at generation time is recorded
+in tests/golden/MANIFEST.json.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def softmax_slab(gen, P, C, spatial, scale):
+    return torch.softmax(scale * torch.randn(P, C, *spatial, generator=gen), dim=1)
+
+
+def uncertainty_cases(ref):
+    gen = torch.Generator().manual_seed(20260101)
+    cases = {}
+    specs = [
+        # name, P, C, spatial, logit scale
+        ("cfg1_toy2d", 10, 2, (16, 32), 2.0),
+        ("cfg2_lidc3d", 5, 2, (8, 8, 8), 2.0),
+        ("cfg3_gta", 10, 19, (8, 16), 2.0),
+        ("cfg3_gta_peaked", 10, 19, (8, 16), 8.0),
+        ("cfg4_diffusion", 32, 2, (16, 16), 2.0),
+        ("cfg4_diffusion_peaked", 32, 2, (16, 16), 12.0),
+        ("cfg5_sweep", 16, 19, (8, 16), 3.0),
+        ("p17_c3", 17, 3, (8, 16), 2.0),
+        ("p18_c3", 18, 3, (8, 16), 2.0),
+        ("p33_c4", 33, 4, (8, 8), 2.0),
+        ("p2_c7_odd", 2, 7, (5, 13), 2.0),
+    ]
+    for name, P, C, spatial, scale in specs:
+        cases[name] = softmax_slab(gen, P, C, spatial, scale)
+
+    # edge vectors
+    P, C, S = 6, 4, (4, 16)
+    onehot = torch.zeros(P, C, *S)
+    idx = torch.randint(0, C, (P, *S), generator=gen)
+    onehot.scatter_(1, idx.unsqueeze(1), 1.0)
+    cases["edge_onehot_ties"] = onehot  # --discretize: one-hot members, tied means
+    same = softmax_slab(gen, 1, C, S, 2.0).repeat(P, 1, 1, 1)
+    cases["edge_identical_members"] = same  # EU ~ 0, slightly negative allowed
+    zeros = torch.zeros(P, C, *S)
+    cases["edge_zeros"] = zeros
+    mixed = softmax_slab(gen, P, C, S, 4.0)
+    mixed[0, 0, 0, :4] = float("nan")
+    mixed[1, 1, 1, :4] = -0.25
+    mixed[2, 2, 2, :4] = 0.0
+    mixed[3, 3, 3, :4] = 1e-42  # subnormal
+    mixed[4, 0, 3, 8:12] = 1.0
+    cases["edge_nan_neg_zero_subnormal"] = mixed
+    near1 = torch.full((P, 2, *S), 0.0)
+    eps = torch.logspace(-8, -1, S[0] * S[1]).reshape(S)
+    near1[:, 0] = 1.0 - eps
+    near1[:, 1] = eps
+    near1[1::2, 0] = (1.0 - 0.5 * eps)
+    near1[1::2, 1] = 0.5 * eps
+    cases["edge_near_one"] = near1  # confident pixels: log accuracy near p = 1
+    out = {}
+    for name, x in cases.items():
+        with torch.no_grad():
+            u = ref.calculate_uncertainty(x)
+        m = torch.mean(x, dim=0)
+        out[f"{name}/x"] = x.numpy()
+        out[f"{name}/TU"] = u["TU"].numpy()
+        out[f"{name}/AU"] = u["AU"].numpy()
+        out[f"{name}/EU"] = u["EU"].numpy()
+        out[f"{name}/mean"] = m.numpy()
+        out[f"{name}/label"] = m.argmax(dim=0).numpy().astype(np.uint8)
+    # P == 1 -> one-minus-MSR (test_2D.py:1006-1007)
+    x1 = softmax_slab(gen, 1, 5, (8, 16), 3.0)
+    out["msr_p1/x"] = x1.numpy()
+    out["msr_p1/pred_entropy"] = ref.calculate_one_minus_msr(x1.squeeze(0))["pred_entropy"].numpy()
+    out["msr_p1/label"] = x1[0].argmax(dim=0).numpy().astype(np.uint8)
+    return out
+
+
+def aggregation_cases(ref):
+    rng = np.random.default_rng(7)
+    out = {}
+    img2d = (rng.random((40, 56)) ** 3).astype(np.float32)
+    img3d = (rng.random((14, 16, 18)) ** 3).astype(np.float32)
+    plateau = np.zeros((32, 32), np.float32)
+    plateau[5:20, 7:25] = 0.5  # many boxes tie for the max -> first-isclose rule
+    for name, img in (("img2d", img2d), ("img3d", img3d), ("plateau", plateau)):
+        out[f"{name}/image"] = img
+        out[f"{name}/image_level_mean"] = np.float64(ref.image_level_aggregation(img)["max_score"])
+        out[f"{name}/image_level_sum"] = np.float64(ref.image_level_aggregation(img, mean=False)["max_score"])
+        for ps in (10, 4):
+            r = ref.patch_level_aggregation(img, ps)
+            out[f"{name}/patch{ps}_score"] = np.float64(r["max_score"])
+            out[f"{name}/patch{ps}_bbox"] = np.asarray(r["bounding_box"], dtype=np.int64)
+            r = ref.patch_level_aggregation(img, ps, mean=True)
+            out[f"{name}/patch{ps}_mean_score"] = np.float64(r["max_score"])
+        for tname, t in (("mid", float(np.quantile(img, 0.9))), ("above_max", float(img.max()) + 1.0),
+                         ("zero", 0.0)):
+            r = ref.threshold_aggregation(img, threshold=t)
+            out[f"{name}/thr_{tname}_t"] = np.float64(t)
+            out[f"{name}/thr_{tname}_score"] = np.float64(r["max_score"])
+            r = ref.threshold_aggregation(img, threshold=t, mean=False)
+            out[f"{name}/thr_{tname}_sum"] = np.float64(r["max_score"])
+    # area / border on label maps
+    lab2d = (rng.random((24, 40)) > 0.7).astype(np.uint8) * rng.integers(1, 19, (24, 40)).astype(np.uint8)
+    lab3d = (rng.random((6, 10, 12)) > 0.5).astype(np.uint8)
+    empty = np.zeros((8, 8), np.uint8)
+    for name, lab in (("lab2d", lab2d), ("lab3d", lab3d), ("empty", empty)):
+        out[f"{name}/label"] = lab
+        out[f"{name}/area"] = np.float64(ref.compute_area(lab))
+        out[f"{name}/border"] = np.float64(ref.compute_border(lab))
+        out[f"{name}/norm_area"] = np.float64(ref.normalize_uncertainty_sum(img2d, ref.compute_area(lab)))
+    return out
+
+
+def calibration_cases(ref):
+    rng = np.random.default_rng(11)
+    out = {}
+    H, W, R = 24, 32, 4
+    specs = {
+        "lidc_like": dict(n_cls=2, ignore=None, a=3.5, b=-1.25),
+        "gta_like_ignore": dict(n_cls=19, ignore=255, a=6.0, b=-2.0),
+        "steep": dict(n_cls=2, ignore=None, a=900.0, b=-300.0),  # many edges collapse onto few floats
+        "negative_a": dict(n_cls=2, ignore=None, a=-2.0, b=0.5),
+        "all_correct": dict(n_cls=1, ignore=None, a=3.5, b=-1.25),  # single-class quirk Q8
+    }
+    for name, s in specs.items():
+        pred = rng.integers(0, s["n_cls"], (H, W)).astype(np.uint8)
+        refs = np.stack([np.where(rng.random((H, W)) < 0.8, pred, rng.integers(0, max(s["n_cls"], 2), (H, W)))
+                         for _ in range(R)]).astype(np.uint8)
+        if name == "all_correct":
+            refs = np.stack([pred] * R)
+        if s["ignore"] is not None:
+            refs[rng.random(refs.shape) < 0.05] = s["ignore"]
+        unc = (rng.random((H, W)) ** 2 * 0.69).astype(np.float32)
+        unc[0, :4] = 0.0
+        with tempfile.TemporaryDirectory() as td:
+            pf = os.path.join(td, "platt_scale_params.json")
+            with open(pf, "w") as f:
+                json.dump({"TU": {"a": s["a"], "b": s["b"]}}, f)
+            # the body of calibration_error (ace.py:484-515), calling the reference pieces
+            n_gt = refs.shape[0]
+            pred_rep = np.repeat(pred[np.newaxis, :], n_gt, 0)
+            unc_rep = np.repeat(unc[np.newaxis, :], n_gt, 0)
+            correct = (refs == pred_rep).astype(int)
+            if s["ignore"] is not None:
+                keep = refs != s["ignore"]
+                conf = ref.platt_scale_confid(-unc_rep[keep], platt_scale_file=pf, uncertainty="TU")
+                cv = correct[keep]
+            else:
+                conf = ref.platt_scale_confid(-unc_rep.flatten(), platt_scale_file=pf, uncertainty="TU")
+                cv = correct.flatten()
+        acc = ref.GlobalCalibAccumulator()
+        acc.accumulate(cv, conf)
+        out[f"{name}/refs"] = refs
+        out[f"{name}/pred"] = pred
+        out[f"{name}/unc"] = unc
+        out[f"{name}/a"] = np.float64(s["a"])
+        out[f"{name}/b"] = np.float64(s["b"])
+        out[f"{name}/ignore"] = np.int64(-999 if s["ignore"] is None else s["ignore"])
+        out[f"{name}/conf"] = conf
+        out[f"{name}/correct"] = cv.astype(np.uint8)
+        out[f"{name}/ace"] = np.float64(ref.calc_ace(cv, conf))
+        out[f"{name}/ece"] = np.float64(ref.calc_ece(cv, conf))
+        out[f"{name}/g_bin_sums"] = acc.bin_sums
+        out[f"{name}/g_bin_true"] = acc.bin_true
+        out[f"{name}/g_bin_total"] = acc.bin_total
+        out[f"{name}/gace"] = np.float64(acc.compute_ace())
+        out[f"{name}/gece"] = np.float64(acc.compute_ece())
+    return out
+
+
+def ncc_aurc_cases(ref):
+    rng = np.random.default_rng(13)
+    out = {}
+    H, W, R = 32, 32, 4
+    refs = (rng.random((R, H, W)) < np.linspace(0.1, 0.9, W)[None, None, :]).astype(np.uint8)
+    pred = (rng.random((H, W)) * 0.69).astype(np.float32)
+    gt_map = np.var(refs, axis=0)  # experiment_dataloader.py:283
+    out["ncc/refs"] = refs
+    out["ncc/pred"] = pred
+    out["ncc/gt_map"] = gt_map
+    out["ncc/value"] = np.float64(ref.compute_ncc(gt_map, pred))
+    out["ncc/self"] = np.float64(ref.compute_ncc(pred, pred))
+    out["ncc/const_gt"] = np.float64(ref.compute_ncc(np.zeros((H, W)), pred))
+    out["ncc/const_pred"] = np.float64(ref.compute_ncc(gt_map, np.full((H, W), 0.25, np.float32)))
+    n = 300
+    risks = rng.random(n)
+    confids = -rng.random(n)
+    out["aurc/risks"] = risks
+    out["aurc/confids"] = confids
+    out["aurc/aurc"] = np.float64(ref.aurc(risks, confids))
+    out["aurc/eaurc"] = np.float64(ref.eaurc(risks, confids))
+    cov, sel, w = ref.rc_curve_stats(risks, confids)
+    out["aurc/coverages"] = np.asarray(cov, np.float64)
+    out["aurc/selective_risks"] = np.asarray(sel, np.float64)
+    out["aurc/weights"] = np.asarray(w, np.float64)
+    return out
+
+
+def main():
+    assert ref_shim.available(), "needs /root/reference"
+    ref = ref_shim.load()
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(1)  # thread-count independent reduction rows (see oracle.cascade_sum_f32)
+    for fname, builder in (("uncertainty.npz", uncertainty_cases), ("aggregation.npz", aggregation_cases),
+                           ("calibration.npz", calibration_cases), ("ncc_aurc.npz", ncc_aurc_cases)):
+        data = builder(ref)
+        np.savez_compressed(os.path.join(GOLDEN, fname), **data)
+        print(fname, len(data), "arrays", os.path.getsize(os.path.join(GOLDEN, fname)), "bytes")
+    import scipy
+    import sklearn
+    manifest = {
+        "generator": "oracle/make_golden.py",
+        "reference": "JakobLC/DiffUncertainty @ /root/reference (unmodified functions via oracle/ref_shim.py)",
+        "torch": torch.__version__, "numpy": np.__version__, "scipy": scipy.__version__,
+        "sklearn": sklearn.__version__, "torch_threads": torch.get_num_threads(),
+    }
+    with open(os.path.join(GOLDEN, "MANIFEST.json"), "w") as f:
+        json.dump(manifest, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,484 @@
+"""CPU oracle for the ValUES per-pixel uncertainty hot path.
+
+TEST INFRASTRUCTURE ONLY.  This module restates, on the CPU with torch/NumPy,
+the algorithm of the reference (JakobLC/DiffUncertainty) for the one path this
+repository accelerates.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it;
+the product package ``diffuncertainty_b200`` never does (it fails loudly when
+the CUDA library is missing instead of falling back to anything here).
+
+Parity pinning: every function below is checked in ``tests/test_oracle.py``
+against (a) the committed fixtures in ``tests/golden/`` that were produced by
+importing the *unmodified* reference functions (``oracle/make_golden.py`` via
+``oracle/ref_shim.py``) and (b), when ``/root/reference`` is mounted, the
+reference functions themselves on fresh seeded inputs.
+
+All ``file:line`` citations are relative to the reference repository root.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+N_CALIB_BINS = 20  # evaluation/metrics/ace.py:334,417
+
+
+# --------------------------------------------------------------------------
+# mean over the member axis (uncertainty_modeling/test_2D.py:971,
+# unc_mod_utils/test_utils.py:835,854)
+# --------------------------------------------------------------------------
+def cascade_sum_f32(x: np.ndarray) -> np.ndarray:
+    """fp32 sum over axis 0 in the exact order torch's CPU kernel uses.
+
+    ``torch.mean(t, dim=0)`` (test_2D.py:971, test_utils.py:835) reduces an
+    outer dimension with ATen's cascade sum: members are added sequentially
+    into a level-0 accumulator that starts at zero; every ``2**k`` members
+    (k = max(4, ceil(log2 P) // 4), i.e. 16 for P <= 2**19) the level-0 value
+    is added into level 1 and reset, level 1 is flushed into level 2 every
+    ``2**(2k)`` members, and so on for 4 levels; the leftover members go to
+    level 0 and the levels are finally added 0 <- 1 <- 2 <- 3.
+    Probed bit-exact against torch 2.11 for P in 2..600 (tests/test_oracle.py).
+
+    torch deviates from this order only for the last ``numel % 32`` elements of
+    a contiguous reduction row (its SIMD remainder loop adds 4 interleaved
+    partial sums, see ``interleaved_tail_sum_f32``); the canonical order below
+    is what the CUDA kernel reproduces.
+    """
+    x = np.asarray(x, dtype=np.float32)
+    n = x.shape[0]
+    k = max(4, (math.ceil(math.log2(n)) if n > 1 else 0) // 4)
+    step = 1 << k
+    level = [np.zeros(x.shape[1:], dtype=np.float32) for _ in range(4)]
+    i = 0
+    while i + step <= n:
+        for _ in range(step):
+            level[0] = level[0] + x[i]
+            i += 1
+        for j in range(1, 4):
+            level[j] = level[j] + level[j - 1]
+            level[j - 1] = np.zeros_like(level[0])
+            if i & ((step - 1) << (j * k)):
+                break
+    while i < n:
+        level[0] = level[0] + x[i]
+        i += 1
+    for j in range(1, 4):
+        level[0] = level[0] + level[j]
+    return level[0]
+
+
+def interleaved_tail_sum_f32(x: np.ndarray) -> np.ndarray:
+    """The order torch uses for the SIMD remainder columns of an outer sum:
+    four partial cascade sums over members 0,4,8.. / 1,5,9.. / 2.. / 3..,
+    leftovers added to partial 0, then partials added 0 <- 1 <- 2 <- 3."""
+    x = np.asarray(x, dtype=np.float32)
+    n = x.shape[0]
+    q = n // 4
+    if q > 0:
+        parts = cascade_sum_f32(x[: 4 * q].reshape(q, 4, *x.shape[1:]))
+    else:
+        parts = np.zeros((4,) + x.shape[1:], dtype=np.float32)
+    acc = parts[0]
+    for i in range(4 * q, n):
+        acc = acc + x[i]
+    for j in range(1, 4):
+        acc = acc + parts[j]
+    return acc
+
+
+def mean_members_f32(x: np.ndarray) -> np.ndarray:
+    """``torch.mean(x, dim=0)`` in canonical order: cascade sum, then a true
+    fp32 division by P (not a multiply by the reciprocal)."""
+    x = np.asarray(x, dtype=np.float32)
+    return cascade_sum_f32(x) / np.float32(x.shape[0])
+
+
+def argmax_first_nan_max(m: np.ndarray) -> np.ndarray:
+    """``torch.argmax(dim=0)`` semantics (test_2D.py:817,871): first maximal
+    index, a NaN compares as the maximum (first NaN wins)."""
+    m = np.asarray(m)
+    nan = np.isnan(m)
+    has_nan = nan.any(axis=0)
+    first_nan = np.argmax(nan, axis=0)
+    plain = np.argmax(np.where(nan, -np.inf, m), axis=0)
+    return np.where(has_nan, first_nan, plain).astype(np.int64)
+
+
+def mean_and_label(image_preds: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The reference's own ops for one image (test_2D.py:969-971, :871):
+    mean over members with torch, argmax over classes, cast as save_prediction
+    does (test_2D.py:817-818)."""
+    mean_softmax = torch.mean(image_preds, dim=0)
+    label = mean_softmax.argmax(dim=0)
+    return mean_softmax, label.to(torch.uint8)
+
+
+# --------------------------------------------------------------------------
+# C2 uncertainty measures (unc_mod_utils/test_utils.py:833-864)
+# --------------------------------------------------------------------------
+def _neg_plogp_sum(stack: torch.Tensor, out_shape, device) -> torch.Tensor:
+    """-sum_c p_c log p_c for a (C, *S) stack the way test_utils.py:836-841 /
+    :848-852 do it: class by class in fp32, NaN products skipped (p == 0,
+    p < 0 and NaN contribute nothing), sign flipped at the end."""
+    acc = torch.zeros(*out_shape, device=device)
+    for c in range(stack.shape[0]):
+        term = stack[c] * torch.log(stack[c])
+        keep = ~torch.isnan(term)
+        acc[keep] += term[keep]
+    acc *= -1
+    return acc
+
+
+def calculate_uncertainty(softmax_preds: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Restates test_utils.py:833-859.  (P, C, *S) -> TU, AU, EU of shape S,
+    always fp32 (the accumulators are default-dtype zeros, :836,843-847)."""
+    spatial = softmax_preds.shape[2:]
+    dev = softmax_preds.device
+    mean_softmax = torch.mean(softmax_preds, dim=0)  # :835
+    total = _neg_plogp_sum(mean_softmax, spatial, mean_softmax.device)  # :836-841
+    per_member = torch.zeros(softmax_preds.shape[0], *spatial, device=dev)  # :843-845
+    for p in range(softmax_preds.shape[0]):  # :846-853
+        per_member[p] = _neg_plogp_sum(softmax_preds[p], spatial, dev)
+    aleatoric = torch.mean(per_member, dim=0)  # :854
+    return {"TU": total, "AU": aleatoric, "EU": total - aleatoric}  # :855-858
+
+
+def calculate_one_minus_msr(softmax_pred: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """test_utils.py:862-864: 1 - max_c p_c for a single member, key "pred_entropy"."""
+    return {"pred_entropy": 1 - softmax_pred.max(dim=0)[0]}
+
+
+def process_image(image_preds: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """The per-image body of ``Tester.process_output`` restricted to the hot
+    path (test_2D.py:969-971, :1004-1007, :817): mean, label, uncertainty."""
+    mean_softmax, label = mean_and_label(image_preds)
+    if image_preds.shape[0] > 1:
+        unc = calculate_uncertainty(image_preds)
+    else:
+        unc = calculate_one_minus_msr(image_preds.squeeze(0))
+    out = dict(unc)
+    out["mean"] = mean_softmax
+    out["label"] = label
+    return out
+
+
+# --------------------------------------------------------------------------
+# C3 aggregation (evaluation/uncertainty_aggregation/aggregate_uncertainties.py)
+# --------------------------------------------------------------------------
+def image_level_aggregation(image: np.ndarray, mean: bool = True) -> Dict[str, float]:
+    """aggregate_uncertainties.py:37-39."""
+    total = np.sum(image)
+    return {"max_score": float(total / image.size) if mean else float(total)}
+
+
+def patch_level_aggregation(image: np.ndarray, patch_size, mean: bool = False) -> Dict[str, object]:
+    """aggregate_uncertainties.py:16-34.  Box sum by ``scipy.signal.convolve``
+    with a float64 ones kernel ("valid"), max, and the box whose corner is the
+    first entry -- per axis, as ``np.where`` orders them -- that is
+    ``np.isclose`` to the max.  Note the reference takes ``indices[0]`` of each
+    axis' index array separately, which is the row-major first hit."""
+    from scipy.signal import convolve
+
+    if isinstance(patch_size, int):
+        patch_size = image.ndim * [patch_size]
+    box = convolve(image, np.ones(patch_size), mode="valid")
+    if mean:
+        box = box / np.prod(patch_size)
+    peak = np.max(box)
+    hits = np.where(np.isclose(box, peak))
+    corner = [int(axis_hits[0]) for axis_hits in hits]
+    return {
+        "max_score": float(peak),
+        "bounding_box": [(c, c + int(k)) for c, k in zip(corner, patch_size)],
+    }
+
+
+def box_sum_direct_f64(image: np.ndarray, patch_size: Sequence[int]) -> np.ndarray:
+    """Direct (non-FFT) float64 "valid" box sum via an integral image; what
+    the CUDA kernel computes.  Differs from the FFT path by ~1e-13 relative."""
+    acc = np.asarray(image, dtype=np.float64)
+    for axis, k in enumerate(patch_size):
+        c = np.cumsum(acc, axis=axis)
+        pad_shape = list(c.shape)
+        pad_shape[axis] = 1
+        c = np.concatenate([np.zeros(pad_shape), c], axis=axis)
+        hi = [slice(None)] * acc.ndim
+        lo = [slice(None)] * acc.ndim
+        hi[axis] = slice(k, None)
+        lo[axis] = slice(0, c.shape[axis] - k)
+        acc = c[tuple(hi)] - c[tuple(lo)]
+    return acc
+
+
+def threshold_aggregation(image: np.ndarray, threshold: float, mean: bool = True) -> Dict[str, object]:
+    """aggregate_uncertainties.py:124-130 (threshold given explicitly): sum and
+    count of the pixels >= t; the mean only when the count is positive,
+    otherwise the (zero) sum is returned."""
+    sel = image >= threshold
+    total = image[sel].sum()
+    count = sel.sum()
+    if mean and count > 0:
+        return {"max_score": total / count, "threshold": threshold}
+    return {"max_score": total, "threshold": threshold}
+
+
+def normalized_sum(image: np.ndarray, divisor: float) -> float:
+    """aggregate_uncertainties.py:70-74: sum / divisor, un-normalised when the
+    divisor is <= 0."""
+    total = float(np.sum(image))
+    return total if divisor <= 0 else total / divisor
+
+
+def compute_area(mask: np.ndarray) -> float:
+    """prediction_shape_stats.py:10-12."""
+    return float(np.count_nonzero(np.asarray(mask) > 0))
+
+
+def compute_border(mask: np.ndarray) -> float:
+    """prediction_shape_stats.py:15-30: per axis, count adjacent pairs whose
+    labels differ; summed over axes."""
+    mask = np.asarray(mask)
+    if mask.size == 0:
+        return 0.0
+    total = 0
+    for axis in range(mask.ndim):
+        if mask.shape[axis] < 2:
+            continue
+        a = np.take(mask, range(0, mask.shape[axis] - 1), axis=axis)
+        b = np.take(mask, range(1, mask.shape[axis]), axis=axis)
+        total += int(np.count_nonzero(a != b))
+    return float(total)
+
+
+# --------------------------------------------------------------------------
+# calibration (evaluation/metrics/ace.py)
+# --------------------------------------------------------------------------
+def platt_scale_confid(uncalib_confid: np.ndarray, a: float, b: float) -> np.ndarray:
+    """ace.py:325-329 with the JSON lookup already done: 1 / (1 + exp(x a + b)),
+    x = -uncertainty; a, b are Python floats so float32 input stays float32."""
+    return 1 / (1 + np.exp(uncalib_confid * a + b))
+
+
+def calib_bin_edges() -> np.ndarray:
+    """ace.py:350: 21 float64 edges over [0, 1 + 1e-8]."""
+    return np.linspace(0.0, 1.0 + 1e-8, N_CALIB_BINS + 1)
+
+
+def _binarize_like_sklearn(correct: np.ndarray) -> np.ndarray:
+    """ace.py:343-348: ``label_binarize(y, classes=unique(y))[:, 0]``.
+    Two classes -> indicator of the larger one; a single class (all correct or
+    all wrong) -> all zeros; more than two -> ValueError."""
+    labels = np.unique(correct)
+    if len(labels) > 2:
+        raise ValueError(f"Only binary classification is supported. Provided labels {labels}.")
+    if len(labels) < 2:
+        return np.zeros(correct.shape[0], dtype=np.int64)
+    return (correct == labels[1]).astype(np.int64)
+
+
+def calib_histogram(correct: np.ndarray, calib_confids: np.ndarray, binarize: bool = True):
+    """The three ``np.bincount`` arrays of ace.py:352-356 (per image, with the
+    single-class quirk) or ace.py:431-437 (``binarize=False``, the global
+    accumulator).  Returns (bin_sums f64[21], bin_true f64[21], bin_total i64[21])."""
+    conf = np.clip(np.ravel(calib_confids), 0, 1)
+    y = np.ravel(correct)
+    y = _binarize_like_sklearn(y) if binarize else y.astype(np.float64)
+    edges = calib_bin_edges()
+    ids = np.digitize(conf, edges) - 1
+    n = len(edges)
+    return (
+        np.bincount(ids, weights=conf, minlength=n),
+        np.bincount(ids, weights=y, minlength=n),
+        np.bincount(ids, minlength=n),
+    )
+
+
+def ace_ece_from_histogram(bin_sums, bin_true, bin_total) -> Tuple[float, float]:
+    """ace.py:357-375 (and :439-460): ACE = mean |acc - conf| over non-empty
+    bins, ECE = the same weighted by the bin's share of samples.  NaN when
+    there are no samples (ace.py:443-444,453-454)."""
+    bin_total = np.asarray(bin_total)
+    filled = bin_total != 0
+    n_filled = int(filled.sum())
+    if n_filled == 0:
+        return float("nan"), float("nan")
+    acc = np.asarray(bin_true, dtype=np.float64)[filled] / bin_total[filled]
+    conf = np.asarray(bin_sums, dtype=np.float64)[filled] / bin_total[filled]
+    gap = np.abs(acc - conf)
+    share = bin_total[filled] / bin_total.sum()
+    return float((1 / n_filled) * np.sum(gap)), float(np.sum(gap * share))
+
+
+def calc_ace(correct, calib_confids) -> float:
+    """ace.py:368-370."""
+    return ace_ece_from_histogram(*calib_histogram(correct, calib_confids))[0]
+
+
+def calc_ece(correct, calib_confids) -> float:
+    """ace.py:373-375."""
+    return ace_ece_from_histogram(*calib_histogram(correct, calib_confids))[1]
+
+
+class GlobalCalibAccumulator:
+    """ace.py:409-460: dataset-level running histogram (no single-class quirk)."""
+
+    def __init__(self) -> None:
+        n = N_CALIB_BINS + 1
+        self.bin_sums = np.zeros(n, dtype=np.float64)
+        self.bin_true = np.zeros(n, dtype=np.float64)
+        self.bin_total = np.zeros(n, dtype=np.int64)
+
+    def accumulate(self, correct, calib_confids) -> None:
+        s, t, n = calib_histogram(correct, calib_confids, binarize=False)
+        self.bin_sums += s
+        self.bin_true += t
+        self.bin_total += n
+
+    def compute_ace(self) -> float:
+        return ace_ece_from_histogram(self.bin_sums, self.bin_true, self.bin_total)[0]
+
+    def compute_ece(self) -> float:
+        return ace_ece_from_histogram(self.bin_sums, self.bin_true, self.bin_total)[1]
+
+
+def calibration_inputs(refs: np.ndarray, pred: np.ndarray, unc: np.ndarray, a: float, b: float,
+                       ignore_value=None) -> Tuple[np.ndarray, np.ndarray]:
+    """The per-image preparation in ``calibration_error`` (ace.py:484-515):
+    rater-wise ``correct = (ref == pred)``, optional ignore mask on the
+    references, Platt-scaled confidence of ``-unc``."""
+    n_gt = refs.shape[0]
+    pred_rep = np.repeat(pred[np.newaxis], n_gt, 0)
+    unc_rep = np.repeat(unc[np.newaxis], n_gt, 0)
+    correct = (refs == pred_rep).astype(int)
+    if ignore_value is not None:
+        keep = refs != ignore_value
+        return correct[keep], platt_scale_confid(-unc_rep[keep], a, b)
+    return correct.flatten(), platt_scale_confid(-unc_rep.flatten(), a, b)
+
+
+# --------------------------------------------------------------------------
+# ambiguity: NCC (evaluation/metrics/ncc.py:9-28, experiment_dataloader.py:283)
+# --------------------------------------------------------------------------
+def rater_variance_map(refs: np.ndarray) -> np.ndarray:
+    """experiment_dataloader.py:283: ``np.var(reference_segs, axis=0)`` (ddof=0)."""
+    return np.var(refs, axis=0)
+
+
+def compute_ncc(gt_unc_map: np.ndarray, pred_unc_map: np.ndarray):
+    """ncc.py:17-28: covariance sum over (n * sigma_gt * sigma_pred) with the
+    sigmas taken with ddof=1; 0.0 if either sigma is exactly 0."""
+    g = gt_unc_map - np.mean(gt_unc_map)
+    p = pred_unc_map - np.mean(pred_unc_map)
+    s_g = np.std(gt_unc_map, ddof=1)
+    s_p = np.std(pred_unc_map, ddof=1)
+    if s_g == 0 or s_p == 0:
+        return 0.0
+    # same operation order (and result dtype) as ncc.py:27
+    return (1 / (np.size(gt_unc_map) * s_g * s_p)) * np.sum(np.multiply(g, p))
+
+
+# --------------------------------------------------------------------------
+# failure detection inputs: binary Dice (test_2D.py:873-899) and AURC
+# (evaluation/metrics/aurc.py:14-67)
+# --------------------------------------------------------------------------
+def binary_dice_counts(label: np.ndarray, gt: np.ndarray, ignore_index: int):
+    """Integer TP / |pred| / |gt| per rater on valid pixels (test_2D.py:878-886)."""
+    valid = gt != ignore_index
+    pred_pos = (label[np.newaxis] == 1) & valid
+    gt_pos = (gt == 1) & valid
+    axes = tuple(range(1, gt.ndim))
+    return (pred_pos & gt_pos).sum(axis=axes), pred_pos.sum(axis=axes), gt_pos.sum(axis=axes)
+
+
+def binary_dice_from_counts(tp, pred_sum, gt_sum) -> float:
+    """test_2D.py:884-899 in fp32: both empty -> 1, exactly one empty -> 0,
+    else 2TP / (2TP + FP + FN); mean over raters."""
+    tp = np.asarray(tp, dtype=np.float32)
+    ps = np.asarray(pred_sum, dtype=np.float32)
+    gs = np.asarray(gt_sum, dtype=np.float32)
+    denom = 2 * tp + (ps - tp) + (gs - tp)
+    dice = np.zeros_like(denom)
+    dice[(ps == 0) & (gs == 0)] = 1.0
+    regular = (ps != 0) & (gs != 0) & (denom > 0)
+    dice[regular] = (2 * tp[regular]) / denom[regular]
+    return float(dice.mean())
+
+
+def rc_curve_stats(risks: np.ndarray, confids: np.ndarray):
+    """aurc.py:14-51: selective-risk curve; a point is emitted only where the
+    sorted confidence changes (and at i == 0)."""
+    risks = np.asarray(risks)
+    confids = np.asarray(confids)
+    assert risks.ndim == 1 and confids.ndim == 1 and len(risks) == len(confids)
+    n = len(risks)
+    order = np.argsort(confids)
+    remaining = n
+    err = sum(risks[order])
+    coverages: List[float] = [remaining / n]
+    sel_risks: List[float] = [err / n]
+    weights: List[float] = []
+    pending = 0
+    for i in range(n - 1):
+        remaining -= 1
+        err = err - risks[order[i]]
+        pending += 1
+        if i == 0 or confids[order[i]] != confids[order[i - 1]]:
+            coverages.append(remaining / n)
+            sel_risks.append(err / (n - 1 - i))
+            weights.append(pending / n)
+            pending = 0
+    if pending > 0:
+        coverages.append(0)
+        sel_risks.append(sel_risks[-1])
+        weights.append(pending / n)
+    return coverages, sel_risks, weights
+
+
+def aurc(risks: np.ndarray, confids: np.ndarray) -> float:
+    """aurc.py:54-58: trapezoid over the emitted points."""
+    _, r, w = rc_curve_stats(risks, confids)
+    return sum((r[i] + r[i + 1]) * 0.5 * w[i] for i in range(len(w)))
+
+
+def eaurc(risks: np.ndarray, confids: np.ndarray) -> float:
+    """aurc.py:61-67: AURC minus the AURC of the risk-sorted oracle."""
+    n = len(risks)
+    best = np.sort(risks).cumsum() / np.arange(1, n + 1)
+    return aurc(risks, confids) - best.sum() / n
+
+
+# --------------------------------------------------------------------------
+# the reference's per-image call sequence, as timed by bench.py's CPU legs
+# 
+# --------------------------------------------------------------------------
+def reference_pipeline_image(image_preds: torch.Tensor, gt: np.ndarray | None = None, *,
+                             thresholds: Sequence[float] | None = None, patch_size: int | None = None,
+                             platt: Sequence[Tuple[float, float]] | None = None,
+                             ignore_value=None, ncc: bool = False) -> Dict[str, object]:
+    """mean + argmax + calculate_uncertainty, then the aggregations / metric
+    inputs the way the reference evaluates them, map by map on the CPU."""
+    out = process_image(image_preds)
+    label = out["label"].numpy()
+    res: Dict[str, object] = {"label": label}
+    names = ("TU", "AU", "EU") if "TU" in out else ("pred_entropy",)
+    for k, name in enumerate(names):
+        m = out[name].numpy()
+        res[name] = m
+        res[f"{name}/image"] = image_level_aggregation(m)["max_score"]
+        if thresholds is not None:
+            res[f"{name}/threshold"] = threshold_aggregation(m, thresholds[k])["max_score"]
+        if patch_size is not None:
+            res[f"{name}/patch"] = patch_level_aggregation(m, patch_size)
+        if gt is not None and platt is not None:
+            correct, conf = calibration_inputs(gt, label, m, platt[k][0], platt[k][1], ignore_value)
+            res[f"{name}/ace"] = calc_ace(correct, conf)
+            res[f"{name}/ece"] = calc_ece(correct, conf)
+            res[f"{name}/hist"] = calib_histogram(correct, conf, binarize=False)
+        if gt is not None and ncc:
+            res[f"{name}/ncc"] = compute_ncc(rater_variance_map(gt), m)
+    res["area"] = compute_area(label)
+    res["border"] = compute_border(label)
+    return res

@@ -1,0 +1,176 @@
+"""Pin oracle/oracle.py (the CPU restatement) against the golden vectors that
+were recorded from the unmodified reference, and -- when /root/reference is
+mounted -- against the reference functions themselves on fresh inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle, ref_shim
+from conftest import case_names
+
+RTOL = 1e-5  # north_star: floating-point maps and scores within 1e-5 relative
+
+
+def same_bits(a, b):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and a.tobytes() == b.tobytes()
+
+
+def test_uncertainty_matches_golden_bitwise(golden_unc):
+    torch.set_num_threads(1)
+    for name in case_names(golden_unc):
+        x = torch.from_numpy(golden_unc[f"{name}/x"])
+        if name == "msr_p1":
+            got = oracle.calculate_one_minus_msr(x.squeeze(0))["pred_entropy"].numpy()
+            assert same_bits(got, golden_unc[f"{name}/pred_entropy"])
+            continue
+        got = oracle.calculate_uncertainty(x)
+        for key in ("TU", "AU", "EU"):
+            assert got[key].dtype == torch.float32
+            assert same_bits(got[key].numpy(), golden_unc[f"{name}/{key}"]), (name, key)
+        mean, label = oracle.mean_and_label(x)
+        assert same_bits(label.numpy(), golden_unc[f"{name}/label"]), name
+
+
+def test_canonical_mean_matches_torch_outside_simd_tail(golden_unc):
+    """cascade_sum_f32 is bit-identical to torch.mean except in the last
+    numel % 32 elements of the reduction row, where torch uses the interleaved
+    order; there it must equal interleaved_tail_sum_f32."""
+    for name in case_names(golden_unc):
+        if name == "msr_p1":
+            continue
+        x = golden_unc[f"{name}/x"]
+        ref = golden_unc[f"{name}/mean"].reshape(-1)
+        P = x.shape[0]
+        flat = x.reshape(P, -1)
+        canon = (oracle.cascade_sum_f32(flat) / np.float32(P))
+        tail = (oracle.interleaved_tail_sum_f32(flat) / np.float32(P))
+        n = flat.shape[1]
+        body = (n // 32) * 32
+        cb, rb = canon.view(np.uint32), ref.view(np.uint32)
+        nan_ok = np.isnan(canon) & np.isnan(ref)
+        assert np.all((cb[:body] == rb[:body]) | nan_ok[:body]), name
+        tb = tail.view(np.uint32)
+        assert np.all((tb[body:] == rb[body:]) | nan_ok[body:]), name
+
+
+@pytest.mark.parametrize("P", [2, 5, 10, 16, 17, 18, 31, 32, 33, 48, 100, 255, 256, 257, 300])
+def test_cascade_sum_vs_torch_live(P):
+    torch.manual_seed(P)
+    torch.set_num_threads(1)
+    x = torch.softmax(2 * torch.randn(P, 4, 8, 16), dim=1)  # 512 elements: no SIMD tail
+    ref = torch.mean(x, dim=0).numpy()
+    assert same_bits(oracle.mean_members_f32(x.numpy()), ref)
+    xb = torch.softmax(2 * torch.randn(P, 3, 4, 8, 16), dim=2)[:, 1]  # strided per-image view
+    assert same_bits(oracle.mean_members_f32(xb.numpy()), torch.mean(xb, dim=0).numpy())
+
+
+def test_argmax_rule():
+    m = np.array([[0.5, np.nan, 0.2, 1.0], [0.5, 0.1, np.nan, 1.0], [0.1, np.nan, 0.9, 1.0]], np.float32)
+    ref = torch.from_numpy(m).argmax(dim=0).numpy()
+    assert np.array_equal(oracle.argmax_first_nan_max(m), ref)
+    assert ref.tolist() == [0, 0, 1, 0]
+
+
+def test_aggregation_matches_golden(golden_agg):
+    for name in ("img2d", "img3d", "plateau"):
+        img = golden_agg[f"{name}/image"]
+        assert oracle.image_level_aggregation(img)["max_score"] == golden_agg[f"{name}/image_level_mean"]
+        assert oracle.image_level_aggregation(img, mean=False)["max_score"] == golden_agg[f"{name}/image_level_sum"]
+        for ps in (10, 4):
+            r = oracle.patch_level_aggregation(img, ps)
+            assert r["max_score"] == golden_agg[f"{name}/patch{ps}_score"]
+            assert np.array_equal(np.asarray(r["bounding_box"]), golden_agg[f"{name}/patch{ps}_bbox"])
+            assert oracle.patch_level_aggregation(img, ps, mean=True)["max_score"] == \
+                golden_agg[f"{name}/patch{ps}_mean_score"]
+            direct = oracle.box_sum_direct_f64(img, img.ndim * [ps])
+            # scipy runs the FFT in float32 for float32 images: ~5e-8 relative noise
+            np.testing.assert_allclose(direct.max(), golden_agg[f"{name}/patch{ps}_score"], rtol=1e-6)
+        for t in ("mid", "above_max", "zero"):
+            thr = float(golden_agg[f"{name}/thr_{t}_t"])
+            assert float(oracle.threshold_aggregation(img, thr)["max_score"]) == golden_agg[f"{name}/thr_{t}_score"]
+            assert float(oracle.threshold_aggregation(img, thr, mean=False)["max_score"]) == \
+                golden_agg[f"{name}/thr_{t}_sum"]
+    for name in ("lab2d", "lab3d", "empty"):
+        lab = golden_agg[f"{name}/label"]
+        assert oracle.compute_area(lab) == golden_agg[f"{name}/area"]
+        assert oracle.compute_border(lab) == golden_agg[f"{name}/border"]
+        assert oracle.normalized_sum(golden_agg["img2d/image"], oracle.compute_area(lab)) == \
+            golden_agg[f"{name}/norm_area"]
+
+
+def test_calibration_matches_golden(golden_calib):
+    for name in case_names(golden_calib):
+        g = {k.split("/", 1)[1]: v for k, v in golden_calib.items() if k.startswith(name + "/")}
+        ignore = None if int(g["ignore"]) == -999 else int(g["ignore"])
+        correct, conf = oracle.calibration_inputs(g["refs"], g["pred"], g["unc"], float(g["a"]), float(g["b"]), ignore)
+        assert conf.dtype == np.float32
+        assert same_bits(conf, g["conf"]), name
+        assert np.array_equal(correct.astype(np.uint8), g["correct"])
+        assert oracle.calc_ace(correct, conf) == g["ace"], name
+        assert oracle.calc_ece(correct, conf) == g["ece"], name
+        acc = oracle.GlobalCalibAccumulator()
+        acc.accumulate(correct, conf)
+        assert np.array_equal(acc.bin_total, g["g_bin_total"])
+        assert np.array_equal(acc.bin_true, g["g_bin_true"])
+        assert np.array_equal(acc.bin_sums, g["g_bin_sums"])
+        assert acc.compute_ace() == g["gace"] and acc.compute_ece() == g["gece"]
+    # quirk Q8: an all-correct image is scored as if nothing were correct
+    g = golden_calib
+    assert g["all_correct/correct"].min() == 1
+    s, t, n = oracle.calib_histogram(g["all_correct/correct"], g["all_correct/conf"], binarize=True)
+    assert t.sum() == 0 and n.sum() == g["all_correct/correct"].size
+    assert n[20] == 0 and len(n) == 21  # Q7: 21 slots, the last always empty
+
+
+def test_ncc_aurc_match_golden(golden_ncc_aurc):
+    g = golden_ncc_aurc
+    assert np.array_equal(oracle.rater_variance_map(g["ncc/refs"]), g["ncc/gt_map"])
+    assert oracle.compute_ncc(g["ncc/gt_map"], g["ncc/pred"]) == g["ncc/value"]
+    assert oracle.compute_ncc(g["ncc/pred"], g["ncc/pred"]) == g["ncc/self"]
+    n = g["ncc/pred"].size
+    np.testing.assert_allclose(g["ncc/self"], (n - 1) / n, rtol=1e-6)  # quirk Q10
+    assert oracle.compute_ncc(np.zeros_like(g["ncc/gt_map"]), g["ncc/pred"]) == 0.0 == g["ncc/const_gt"]
+    assert oracle.compute_ncc(g["ncc/gt_map"], np.full(g["ncc/pred"].shape, 0.25, np.float32)) == g["ncc/const_pred"]
+    assert oracle.aurc(g["aurc/risks"], g["aurc/confids"]) == g["aurc/aurc"]
+    assert oracle.eaurc(g["aurc/risks"], g["aurc/confids"]) == g["aurc/eaurc"]
+    cov, sel, w = oracle.rc_curve_stats(g["aurc/risks"], g["aurc/confids"])
+    assert np.array_equal(np.asarray(sel), g["aurc/selective_risks"])
+    assert np.array_equal(np.asarray(w), g["aurc/weights"])
+
+
+def test_binary_dice_rule():
+    label = np.array([[1, 1, 0, 0]], np.uint8)
+    gt = np.array([[[1, 0, 0, 0]], [[0, 0, 0, 0]], [[1, 1, 255, 0]]], np.int64)
+    tp, ps, gs = oracle.binary_dice_counts(label, gt, 255)
+    assert tp.tolist() == [1, 0, 2] and ps.tolist() == [2, 2, 2] and gs.tolist() == [1, 0, 2]
+    assert oracle.binary_dice_from_counts(tp, ps, gs) == pytest.approx((2 / 3 + 0 + 1) / 3, rel=1e-6)
+    assert oracle.binary_dice_from_counts([0], [0], [0]) == 1.0
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted (GPU box)")
+def test_oracle_vs_live_reference():
+    ref = ref_shim.load()
+    torch.manual_seed(5)
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(5)
+    for P, C, S in ((10, 2, (32, 32)), (5, 2, (8, 8, 16)), (16, 19, (8, 32)), (33, 3, (16, 16))):
+        x = torch.softmax(6 * torch.randn(P, C, *S), dim=1)
+        a, b = ref.calculate_uncertainty(x), oracle.calculate_uncertainty(x)
+        for k in ("TU", "AU", "EU"):
+            assert same_bits(a[k].numpy(), b[k].numpy())
+    img = rng.random((48, 64)).astype(np.float32)
+    assert ref.patch_level_aggregation(img, 10) == oracle.patch_level_aggregation(img, 10)
+    assert ref.image_level_aggregation(img) == oracle.image_level_aggregation(img)
+    ra, rb = ref.threshold_aggregation(img, threshold=0.5), oracle.threshold_aggregation(img, 0.5)
+    assert float(ra["max_score"]) == float(rb["max_score"])
+    correct = rng.integers(0, 2, 5000)
+    conf = rng.random(5000).astype(np.float32)
+    assert ref.calc_ace(correct, conf) == oracle.calc_ace(correct, conf)
+    assert ref.calc_ece(correct, conf) == oracle.calc_ece(correct, conf)
+    lab = rng.integers(0, 3, (20, 30)).astype(np.uint8)
+    assert ref.compute_border(lab) == oracle.compute_border(lab)
+    risks, confids = rng.random(100), rng.random(100)
+    assert ref.aurc(risks, confids) == oracle.aurc(risks, confids)
+    assert ref.eaurc(risks, confids) == oracle.eaurc(risks, confids)
