@@ -1,0 +1,75 @@
+"""Build libvalunc.so in-tree with nvcc for sm_100a (no JIT cache, no pip).
+
+    python -m diffuncertainty_b200.build [--force] [--verbose]
+
+The shared library lands in diffuncertainty_b200/lib/ so it travels with the
+repository snapshot to the GPU box.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIBDIR = os.path.join(PKG, "lib")
+OBJDIR = os.path.join(LIBDIR, "obj")
+LIB = os.path.join(LIBDIR, "libvalunc.so")
+SOURCES = ["abi.cu", "k1_fused.cu", "k2_spatial.cu", "k3_map_stats.cu", "synth.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-O3", "-std=c++17", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+]
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    names = sorted(os.listdir(CSRC)) + ["../../include/valunc.h"]
+    for n in names:
+        p = os.path.join(CSRC, n)
+        if os.path.isfile(p):
+            h.update(n.encode())
+            with open(p, "rb") as f:
+                h.update(f.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJDIR, exist_ok=True)
+    stamp = os.path.join(LIBDIR, "build.stamp")
+    digest = _digest()
+    if not force and os.path.isfile(LIB) and os.path.isfile(stamp) and open(stamp).read().strip() == digest:
+        return LIB
+    extra = ["-Xptxas", "-v"] if verbose else []
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        cmd = [NVCC, *FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose:
+            sys.stderr.write(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,244 @@
+"""Calibration (ECE / ACE) on the GPU behind the reference's call surface
+(evaluation/metrics/ace.py:325-460).
+
+Bin membership must be bit-exact with ``np.digitize(platt(-u), linspace(0, 1+1e-8, 21))``
+although the device's ``expf`` differs from NumPy's by an ulp or two.  The map
+u -> conf is monotone, so the 19 interior edges are pulled back to thresholds on
+u on the host -- evaluating the reference's float32 expression with NumPy itself
+-- and the kernels compare u with those thresholds (``PlattEdges``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+N_BINS = 20
+
+
+def bin_edges() -> np.ndarray:
+    """ace.py:350: np.linspace(0, 1 + 1e-8, 21) (float64)."""
+    return np.linspace(0.0, 1.0 + 1e-8, N_BINS + 1)
+
+
+def _platt_f32(u: np.ndarray, a: float, b: float) -> np.ndarray:
+    """ace.py:329 applied to x = -u, float32 in / float32 out exactly as the
+    reference evaluates it (a, b are Python floats)."""
+    with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+        return 1 / (1 + np.exp((-u) * a + b))
+
+
+def _ord(f: np.ndarray) -> np.ndarray:
+    """order-preserving float32 -> uint32 key"""
+    u = f.view(np.uint32).astype(np.uint64)
+    return np.where(u & 0x80000000, (~u) & 0xFFFFFFFF, u | 0x80000000).astype(np.uint64)
+
+
+def _unord(o: np.ndarray) -> np.ndarray:
+    o = o.astype(np.uint64)
+    u = np.where(o & 0x80000000, o & 0x7FFFFFFF, (~o) & 0xFFFFFFFF).astype(np.uint32)
+    return u.view(np.float32)
+
+
+@dataclass
+class PlattEdges:
+    """Thresholds on the uncertainty value that reproduce the reference's bins."""
+    a: float
+    b: float
+    edge_u: np.ndarray  # float32[19]; NaN = this edge is never reached
+    mode: int           # 0 decreasing (a < 0), 1 increasing, 2 identity
+
+    def as_struct(self) -> _lib.Calib:
+        c = _lib.Calib()
+        c.a, c.b, c.mode = float(np.float32(self.a)), float(np.float32(self.b)), int(self.mode)
+        for k in range(_lib.N_EDGES):
+            c.edge_u[k] = float(self.edge_u[k])
+        return c
+
+    def bin_of(self, u: np.ndarray) -> np.ndarray:
+        """Host mirror of the device binning rule (used in tests)."""
+        u = np.asarray(u, np.float32)
+        with np.errstate(invalid="ignore"):
+            if self.mode == 0:
+                hit = u[..., None] <= self.edge_u
+            else:
+                hit = u[..., None] >= self.edge_u
+        b = hit.sum(-1)
+        return np.where(np.isnan(u), N_BINS, b)
+
+
+def platt_edges(a: float, b: float) -> PlattEdges:
+    """Invert conf(u) = 1/(1+exp(-u*a+b)) (float32, NumPy's exp) on the 19
+    interior bin edges by bisection over float32 bit patterns, vectorised over
+    the edges.  increasing (a >= 0): smallest u with conf(u) >= edge;
+    decreasing: largest such u.  The result is made monotone in k."""
+    a32 = np.float32(a)
+    increasing = bool(a32 >= 0)
+    edges = bin_edges()[1:N_BINS]
+    lo = np.full(19, _ord(np.array([-np.inf], np.float32))[0], np.uint64)
+    hi = np.full(19, _ord(np.array([np.inf], np.float32))[0], np.uint64)
+
+    def ok(keys):
+        conf = _platt_f32(_unord(keys), float(a), float(b)).astype(np.float64)
+        return conf >= edges
+
+    if increasing:
+        reach = ok(hi)
+        for _ in range(34):
+            mid = lo + (hi - lo) // 2
+            good = ok(mid)
+            hi = np.where(good, mid, hi)
+            lo = np.where(good, lo, np.minimum(mid + 1, hi))
+        thr = _unord(hi).copy()
+        thr[~reach] = np.nan
+        fin = ~np.isnan(thr)
+        thr[fin] = np.maximum.accumulate(thr[fin])
+    else:
+        reach = ok(lo)
+        for _ in range(34):
+            mid = lo + (hi - lo + 1) // 2
+            good = ok(mid)
+            lo = np.where(good, mid, lo)
+            hi = np.where(good, hi, np.maximum(mid - 1, lo))
+        thr = _unord(lo).copy()
+        thr[~reach] = np.nan
+        fin = ~np.isnan(thr)
+        thr[fin] = np.minimum.accumulate(thr[fin])
+    return PlattEdges(a=float(a), b=float(b), edge_u=thr.astype(np.float32), mode=1 if increasing else 0)
+
+
+def identity_edges() -> PlattEdges:
+    """Edges for maps that already hold confidences: the smallest float32 that
+    is >= each float64 edge, so ``conf >= edge`` has the same truth value."""
+    e64 = bin_edges()[1:N_BINS]
+    e32 = e64.astype(np.float32)
+    e32 = np.where(e32.astype(np.float64) < e64, np.nextafter(e32, np.float32(np.inf)), e32).astype(np.float32)
+    return PlattEdges(a=0.0, b=0.0, edge_u=e32, mode=2)
+
+
+def load_platt_params(platt_scale_file, uncertainty: str) -> Tuple[float, float]:
+    """The JSON lookup of ace.py:326-328."""
+    with open(platt_scale_file) as f:
+        params = json.load(f)[uncertainty]
+    return float(params["a"]), float(params["b"])
+
+
+# ---------------------------------------------------------------------------
+# host finalisation in float64 (ace.py:357-375, 439-460)
+# ---------------------------------------------------------------------------
+def ace_ece_from_histogram(bin_sums, bin_true, bin_total) -> Tuple[float, float]:
+    bin_total = np.asarray(bin_total)
+    filled = bin_total != 0
+    n = int(filled.sum())
+    if n == 0:
+        return float("nan"), float("nan")
+    acc = np.asarray(bin_true, np.float64)[filled] / bin_total[filled]
+    conf = np.asarray(bin_sums, np.float64)[filled] / bin_total[filled]
+    gap = np.abs(acc - conf)
+    return float((1 / n) * np.sum(gap)), float(np.sum(gap * (bin_total[filled] / bin_total.sum())))
+
+
+def per_image_ace_ece(bin_sums, bin_true, bin_total) -> Tuple[float, float]:
+    """calc_ace / calc_ece of ONE image from its histogram, including the
+    single-class rule of ace.py:343-348: when every sample is correct (or every
+    sample is wrong) sklearn's label_binarize yields all zeros."""
+    bin_true = np.asarray(bin_true, np.float64)
+    tot = np.asarray(bin_total).sum()
+    if bin_true.sum() == tot or bin_true.sum() == 0:
+        bin_true = np.zeros_like(bin_true)
+    return ace_ece_from_histogram(bin_sums, bin_true, bin_total)
+
+
+def _device_histogram(correct, calib_confids):
+    """(correct, conf) arrays -> 21-slot histogram on the GPU (ace.py:352-356)."""
+    _lib.require_device()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    conf = torch.as_tensor(np.ascontiguousarray(np.asarray(calib_confids, dtype=np.float32)).ravel()) \
+        if not isinstance(calib_confids, torch.Tensor) else calib_confids.reshape(-1).float()
+    corr = torch.as_tensor(np.ascontiguousarray(np.asarray(correct)).ravel()) \
+        if not isinstance(correct, torch.Tensor) else correct.reshape(-1)
+    if conf.numel() != corr.numel():
+        raise ValueError("correct and calib_confids must have the same number of elements")
+    conf = conf.to(dev, non_blocking=True).contiguous()
+    corr = corr.to(dev, non_blocking=True)
+    corr = corr.to(torch.uint8 if corr.dtype in (torch.bool, torch.uint8, torch.int8) else torch.int64).contiguous()
+    n = conf.numel()
+    sf = torch.zeros((1, _lib.F64["COLS"]), dtype=torch.float64, device=dev)
+    si = torch.zeros((1, _lib.I64["COLS"]), dtype=torch.int64, device=dev)
+    if n:
+        ones = torch.ones(n, dtype=torch.uint8, device=dev)  # "label" 1 so that correct == label <=> correct == 1
+        a = _lib.MapStatsArgs()
+        a.struct_size = C.sizeof(_lib.MapStatsArgs)
+        a.stat_flags = _lib.STAT_CALIB
+        a.B, a.V = 1, n
+        a.maps[0] = conf.data_ptr()
+        a.labels = ones.data_ptr()
+        a.gt.data = corr.data_ptr()
+        a.gt.dtype = _lib.GT_U8 if corr.dtype == torch.uint8 else _lib.GT_I64
+        a.gt.R = 1
+        a.gt.stride_b, a.gt.stride_r, a.gt.stride_v = n, n, 1
+        ident = identity_edges().as_struct()
+        for k in range(3):
+            a.calib[k] = ident
+        a.stats_f64, a.stats_i64 = sf.data_ptr(), si.data_ptr()
+        # only map 0 is present; the kernel skips NULL maps
+        _lib.check(lib.vu_map_stats(C.byref(a), _lib.current_stream_ptr()), "vu_map_stats")
+    f = sf.cpu().numpy()[0]
+    i = si.cpu().numpy()[0]
+    F, I = _lib.F64, _lib.I64
+    return (f[F["BIN_SUMS"]:F["BIN_SUMS"] + 21].copy(), i[I["BIN_TRUE"]:I["BIN_TRUE"] + 21].astype(np.float64),
+            i[I["BIN_TOTAL"]:I["BIN_TOTAL"] + 21].copy())
+
+
+def _check_binary(correct) -> None:
+    vals = torch.unique(correct) if isinstance(correct, torch.Tensor) else np.unique(correct)
+    if len(vals) > 2:
+        # ace.py:339-342
+        raise ValueError(f"Only binary classification is supported. Provided labels {vals}.")
+
+
+def calc_ace(correct, calib_confids) -> float:
+    """Drop-in for ace.py:368-370 (histogram on the GPU, finalisation in float64)."""
+    _check_binary(correct)
+    return per_image_ace_ece(*_device_histogram(correct, calib_confids))[0]
+
+
+def calc_ece(correct, calib_confids) -> float:
+    """Drop-in for ace.py:373-375."""
+    _check_binary(correct)
+    return per_image_ace_ece(*_device_histogram(correct, calib_confids))[1]
+
+
+class GlobalCalibAccumulator:
+    """Drop-in for ace.py:409-460.  ``accumulate`` takes per-pixel arrays like the
+    reference; ``accumulate_histogram`` takes what the fused pass already produced."""
+
+    N_BINS = N_BINS
+
+    def __init__(self) -> None:
+        n = self.N_BINS + 1
+        self.bin_sums = np.zeros(n, dtype=np.float64)
+        self.bin_true = np.zeros(n, dtype=np.float64)
+        self.bin_total = np.zeros(n, dtype=np.int64)
+
+    def accumulate(self, correct, calib_confids) -> None:
+        s, t, n = _device_histogram(correct, calib_confids)
+        self.accumulate_histogram(s, t, n)
+
+    def accumulate_histogram(self, bin_sums, bin_true, bin_total) -> None:
+        self.bin_sums += np.asarray(bin_sums, np.float64)
+        self.bin_true += np.asarray(bin_true, np.float64)
+        self.bin_total += np.asarray(bin_total, np.int64)
+
+    def compute_ace(self) -> float:
+        return ace_ece_from_histogram(self.bin_sums, self.bin_true, self.bin_total)[0]
+
+    def compute_ece(self) -> float:
+        return ace_ece_from_histogram(self.bin_sums, self.bin_true, self.bin_total)[1]

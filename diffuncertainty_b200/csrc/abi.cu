@@ -1,0 +1,265 @@
+// extern "C" boundary of libvalunc.so (see include/valunc.h).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "vu_common.cuh"
+#include "vu_host.h"
+
+namespace vu {
+
+static thread_local char g_err[512] = "";
+static std::mutex g_mu;
+static std::map<std::string, long long> g_options;
+static std::map<std::string, long long> g_counters;
+
+int set_error(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+int set_cuda_error(const char* where) {
+    cudaError_t e = cudaGetLastError();
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return VU_ERR_CUDA;
+}
+int check_launch(const char* kernel) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e == cudaSuccess) return VU_OK;
+    return set_cuda_error(kernel);
+}
+void count_launch(const char* kernel) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_counters["launches"] += 1;
+    g_counters[std::string("launches.") + kernel] += 1;
+}
+long long get_option(const char* key, long long dflt) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_options.find(key);
+    return it == g_options.end() ? dflt : it->second;
+}
+int device_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!cached[dev]) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+    return cached[dev] > 0 ? cached[dev] : 148;
+}
+
+static int fill_stat_params(StatParams& st, uint32_t flags, int n_unc, long long V, const vu_gt& gt,
+                            const float* thr, const vu_calib* calib, const uint8_t* lut, const double* ncc_gt_map,
+                            double* f64, int64_t* i64) {
+    memset(&st, 0, sizeof(st));
+    st.flags = flags;
+    st.n_unc = n_unc;
+    st.V = V;
+    if (flags == 0) return VU_OK;
+    if (!f64 || !i64) return set_error(VU_ERR_BAD_ARG, "stat_flags set but stats_f64 / stats_i64 is NULL");
+    const uint32_t known = VU_STAT_IMAGE_SUM | VU_STAT_THRESHOLD | VU_STAT_AREA | VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC;
+    if (flags & ~known) return set_error(VU_ERR_BAD_ARG, "unknown stat flag");
+    const bool needs_gt = (flags & (VU_STAT_DICE | VU_STAT_CALIB)) || ((flags & VU_STAT_NCC) && !ncc_gt_map);
+    if (needs_gt) {
+        if (!gt.data) return set_error(VU_ERR_BAD_ARG, "DICE / CALIB / NCC statistics need ground truth");
+        if (gt.R < 1 || gt.R > VU_MAX_RATERS) return set_error(VU_ERR_UNSUPPORTED, "gt.R must be 1..8");
+        if (gt.dtype != VU_GT_U8 && gt.dtype != VU_GT_I64) return set_error(VU_ERR_BAD_ARG, "gt.dtype");
+    }
+    if (gt.data) {
+        st.gt.data = gt.data; st.gt.dtype = gt.dtype; st.gt.R = gt.R;
+        st.gt.sb = gt.stride_b; st.gt.sr = gt.stride_r; st.gt.sv = gt.stride_v;
+        st.gt.has_ignore = gt.has_ignore; st.gt.ignore = gt.ignore_index;
+    }
+    for (int k = 0; k < VU_N_UNC; ++k) {
+        st.thr[k] = thr[k];
+        st.calib[k].a = calib[k].a;
+        st.calib[k].b = calib[k].b;
+        const int mode = calib[k].mode;
+        if ((flags & VU_STAT_CALIB) && (mode < 0 || mode > 2)) return set_error(VU_ERR_BAD_ARG, "vu_calib.mode");
+        st.calib[k].increasing = mode != VU_CALIB_PLATT_DEC;
+        st.calib[k].identity = mode == VU_CALIB_IDENTITY;
+        for (int e = 0; e < 32; ++e) {
+            float t = e < VU_N_EDGES ? calib[k].edge_u[e] : NAN;
+            st.calib[k].edge[e] = st.calib[k].increasing ? t : -t;
+        }
+    }
+    st.lut = lut;
+    st.ncc_gt_map = ncc_gt_map;
+    st.f64 = f64;
+    st.i64 = reinterpret_cast<long long*>(i64);
+    return VU_OK;
+}
+
+}  // namespace vu
+
+using namespace vu;
+
+extern "C" {
+
+int vu_abi_version(void) { return VU_ABI_VERSION; }
+
+const char* vu_build_info(void) {
+    return "libvalunc sm_100a (compute_100a) nvcc " VU_STR(__CUDACC_VER_MAJOR__) "." VU_STR(__CUDACC_VER_MINOR__)
+           " built " __DATE__;
+}
+
+const char* vu_last_error(void) { return g_err; }
+
+int vu_device_check(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return set_error(VU_ERR_NO_DEVICE, "no CUDA device"); }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return set_error(VU_ERR_NO_DEVICE, "libvalunc needs an sm_100 (B200) device");
+    return VU_OK;
+}
+
+int vu_struct_size(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(vu_fused_args);
+        case 1: return (int)sizeof(vu_map_stats_args);
+        case 2: return (int)sizeof(vu_calib);
+        default: return -1;
+    }
+}
+
+int vu_fused_pass(const vu_fused_args* a, void* stream) {
+    if (!a) return set_error(VU_ERR_BAD_ARG, "args is NULL");
+    if (a->struct_size != sizeof(vu_fused_args)) return set_error(VU_ERR_BAD_ARG, "vu_fused_args.struct_size mismatch");
+    const vu_slab& s = a->slab;
+    if (!s.data) return set_error(VU_ERR_BAD_ARG, "slab.data is NULL");
+    if (s.P < 1 || s.B < 0 || s.C < 1 || s.V < 0) return set_error(VU_ERR_BAD_ARG, "slab sizes must be positive");
+    if (s.C > 256) return set_error(VU_ERR_UNSUPPORTED, "C > 256 (labels are uint8)");
+    if (s.B == 0 || s.V == 0) return VU_OK;  // empty batch: nothing to do
+    StatParams st;
+    const int n_unc = s.P > 1 ? VU_N_UNC : 1;
+    int rc = fill_stat_params(st, a->stat_flags, n_unc, s.V, a->gt, a->threshold, a->calib, a->calib_label_lut, nullptr,
+                              a->stats_f64, a->stats_i64);
+    if (rc != VU_OK) return rc;
+    return launch_k1(a, st, (cudaStream_t)stream);
+}
+
+int vu_map_stats(const vu_map_stats_args* a, void* stream) {
+    if (!a) return set_error(VU_ERR_BAD_ARG, "args is NULL");
+    if (a->struct_size != sizeof(vu_map_stats_args)) return set_error(VU_ERR_BAD_ARG, "vu_map_stats_args.struct_size mismatch");
+    if (a->B < 0 || a->V < 0) return set_error(VU_ERR_BAD_ARG, "negative size");
+    if (a->B == 0 || a->V == 0 || a->stat_flags == 0) return VU_OK;
+    if ((a->stat_flags & (VU_STAT_AREA | VU_STAT_DICE | VU_STAT_CALIB)) && !a->labels)
+        return set_error(VU_ERR_BAD_ARG, "AREA / DICE / CALIB need labels");
+    StatParams st;
+    int rc = fill_stat_params(st, a->stat_flags, VU_N_UNC, a->V, a->gt, a->threshold, a->calib, a->calib_label_lut,
+                              a->ncc_gt_map, a->stats_f64, a->stats_i64);
+    if (rc != VU_OK) return rc;
+    return launch_map_stats(a, st, (cudaStream_t)stream);
+}
+
+int vu_patch_max(const float* maps, int64_t B, int64_t d0, int64_t d1, int64_t d2, int32_t k0, int32_t k1, int32_t k2,
+                 int32_t mean, double* out_max, int64_t* out_first, void* stream) {
+    if (!maps || !out_max || !out_first) return set_error(VU_ERR_BAD_ARG, "NULL pointer");
+    if (B < 0 || d0 < 1 || d1 < 1 || d2 < 1 || k0 < 1 || k1 < 1 || k2 < 1) return set_error(VU_ERR_BAD_ARG, "bad size");
+    if (k0 > d0 || k1 > d1 || k2 > d2) return set_error(VU_ERR_BAD_ARG, "patch larger than the map (\"valid\" output is empty)");
+    if (B == 0) return VU_OK;
+    return launch_patch_max(maps, B, d0, d1, d2, k0, k1, k2, mean, out_max, reinterpret_cast<long long*>(out_first),
+                            (cudaStream_t)stream);
+}
+
+int vu_border_count(const uint8_t* labels, int64_t B, int64_t d0, int64_t d1, int64_t d2, int64_t* stats_i64, void* stream) {
+    if (!labels || !stats_i64) return set_error(VU_ERR_BAD_ARG, "NULL pointer");
+    if (B < 0 || d0 < 1 || d1 < 1 || d2 < 1) return set_error(VU_ERR_BAD_ARG, "bad size");
+    if (B == 0) return VU_OK;
+    return launch_border(labels, B, d0, d1, d2, reinterpret_cast<long long*>(stats_i64), (cudaStream_t)stream);
+}
+
+// --- host: invert the Platt map on the bin edges (ace.py:329, 350) ------------
+// float32 evaluation of 1 / (1 + exp(x*a + b)), x = -u, exactly as NumPy does it
+// for a float32 array and Python-float a, b (NEP 50: a, b are cast to float32).
+// expf here is the host libm's; the *counts* the kernels produce are exact with
+// respect to whatever conf() is used to build the edges, so the Python layer
+// rebuilds the edges with NumPy's own exp (diffuncertainty_b200/calibration.py)
+// and only falls back to this helper for C callers.
+static float platt_host(float u, float a, float b) {
+    volatile float z = (-u) * a;
+    z = z + b;
+    volatile float e = expf(z);
+    volatile float d = 1.0f + e;
+    return 1.0f / d;
+}
+static inline uint32_t f2o(float f) {  // order-preserving float -> uint32
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static inline float o2f(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+int vu_platt_invert_edges_host(double a, double b, vu_calib* calib) {
+    if (!calib) return set_error(VU_ERR_BAD_ARG, "calib is NULL");
+    const float af = (float)a, bf = (float)b;
+    calib->a = af;
+    calib->b = bf;
+    calib->mode = af >= 0.0f ? VU_CALIB_PLATT_INC : VU_CALIB_PLATT_DEC;
+    const bool increasing = calib->mode == VU_CALIB_PLATT_INC;
+    const uint32_t lo_all = f2o(-INFINITY), hi_all = f2o(INFINITY);
+    for (int k = 0; k < VU_N_EDGES; ++k) {
+        const double edge = (1.0 + 1e-8) * (double)(k + 1) / 20.0;
+        // smallest u (increasing) / largest u (decreasing) with conf(u) >= edge
+        uint32_t lo = lo_all, hi = hi_all;
+        auto ok = [&](uint32_t o) { float c = platt_host(o2f(o), af, bf); return (double)c >= edge; };
+        if (increasing) {
+            if (!ok(hi)) { calib->edge_u[k] = NAN; continue; }
+            while (lo < hi) { uint32_t mid = lo + (hi - lo) / 2; if (ok(mid)) hi = mid; else lo = mid + 1; }
+            calib->edge_u[k] = o2f(lo);
+        } else {
+            if (!ok(lo)) { calib->edge_u[k] = NAN; continue; }
+            while (lo < hi) { uint32_t mid = lo + (hi - lo + 1) / 2; if (ok(mid)) lo = mid; else hi = mid - 1; }
+            calib->edge_u[k] = o2f(lo);
+        }
+    }
+    return VU_OK;
+}
+
+int vu_synth_slab(float* out, int64_t P, int64_t B, int64_t C, int64_t V, uint64_t seed, int64_t first_image, float scale,
+                  void* stream) {
+    if (!out) return set_error(VU_ERR_BAD_ARG, "out is NULL");
+    if (P < 1 || B < 0 || C < 1 || V < 0 || C > 256) return set_error(VU_ERR_BAD_ARG, "bad size");
+    if (B == 0 || V == 0) return VU_OK;
+    return launch_synth_slab(out, P, B, C, V, seed, first_image, scale, (cudaStream_t)stream);
+}
+
+int vu_synth_gt(uint8_t* out, const float* slab, int64_t P, int64_t B, int64_t C, int64_t V, int32_t R, uint64_t seed,
+                int64_t first_image, float flip, float ignore_frac, int32_t ignore_value, void* stream) {
+    if (!out || !slab) return set_error(VU_ERR_BAD_ARG, "NULL pointer");
+    if (P < 1 || B < 0 || C < 1 || V < 0 || R < 1 || R > VU_MAX_RATERS) return set_error(VU_ERR_BAD_ARG, "bad size");
+    if (B == 0 || V == 0) return VU_OK;
+    return launch_synth_gt(out, slab, P, B, C, V, R, seed, first_image, flip, ignore_frac, ignore_value, (cudaStream_t)stream);
+}
+
+int vu_set_option(const char* key, int64_t value) {
+    if (!key) return set_error(VU_ERR_BAD_ARG, "key is NULL");
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_options[key] = value;
+    return VU_OK;
+}
+
+int64_t vu_get_counter(const char* key) {
+    if (!key) return -1;
+    if (strcmp(key, "k1_num_variants") == 0) return num_fast_variants();
+    if (strncmp(key, "k1_variant.", 11) == 0) {  // "k1_variant.<i>.<field 0..6>"
+        int i = 0, f = 0;
+        if (sscanf(key + 11, "%d.%d", &i, &f) != 2 || f < 0 || f > 6) return -1;
+        int d[7];
+        if (describe_fast_variant(i, d) != 0) return -1;
+        return d[f];
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_counters.find(key);
+    return it == g_counters.end() ? 0 : it->second;
+}
+
+}  // extern "C"

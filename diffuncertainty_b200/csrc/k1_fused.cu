@@ -1,0 +1,407 @@
+// K1: the fused streaming pass over the (P, B, C, V) probability slab.
+//
+// One read of HBM per element produces, per voxel: the member mean (torch's
+// cascade order, bit-exact), its argmax label, TU / AU / EU, and -- when
+// requested -- the per-image reductions behind image/threshold aggregation,
+// area, Dice counts, the 20-bin calibration histograms and the NCC sums.
+//
+// Reference semantics: uncertainty_modeling/test_2D.py:969-971 (slice + mean),
+// :871 (argmax), unc_mod_utils/test_utils.py:833-864 (uncertainty measures),
+// evaluation/uncertainty_aggregation/aggregate_uncertainties.py:37-39,124-125,
+// evaluation/metrics/ace.py:350-356, evaluation/metrics/ncc.py:17-27.
+#include "vu_common.cuh"
+#include "vu_host.h"
+
+namespace vu {
+
+struct K1Params {
+    const float* x;
+    long long P, B, C, V;
+    long long sp, sb, sc, sv;
+    float* tu;
+    float* au;
+    float* eu;
+    uint8_t* lab;
+    long long tiles_per_img, total_tiles;
+    StatParams st;
+};
+
+// ---------------------------------------------------------------------------
+// Fast kernel: C compile-time, one thread owns VEC consecutive voxels and walks
+// the members in order (that is what makes the mean bit-exact), G members per
+// load stage, optionally double-buffered in registers.
+//   LEVELS = 1: P <= 17 (plain sequential sum == torch's cascade)
+//   LEVELS = 2: P <= 271 (level-0 accumulator folded into level 1 every 16)
+// Requires stride_v == 1 and VEC-element alignment of every row start.
+// ---------------------------------------------------------------------------
+template <int C, int VEC, int LEVELS, int THREADS, int MINB, int G, bool DB, bool STATS>
+__global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__ K1Params prm) {
+    constexpr int WARPS = THREADS / 32;
+    __shared__ CtaStats<STATS ? WARPS : 1> cs_store;
+    CtaStats<WARPS>& cs = reinterpret_cast<CtaStats<WARPS>&>(cs_store);
+    constexpr bool do_stats = STATS;
+    if (do_stats) cs.init(prm.st);
+
+    const long long P = prm.P, V = prm.V;
+    const float Pf = (float)P;
+    const long long t0 = prm.total_tiles * (long long)blockIdx.x / gridDim.x;
+    const long long t1 = prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x;
+    long long cur_b = -1;
+
+    for (long long tile = t0; tile < t1; ++tile) {
+        const long long b = tile / prm.tiles_per_img;
+        const long long vt = tile - b * prm.tiles_per_img;
+        const long long v = vt * (long long)(THREADS * VEC) + (long long)threadIdx.x * VEC;
+        if (do_stats && b != cur_b) {
+            if (cur_b >= 0) cs.flush(prm.st, cur_b);
+            cur_b = b;
+        }
+        const bool active = v < V;
+        float u[VU_N_UNC][VEC];
+        int label[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { u[0][k] = u[1][k] = u[2][k] = 0.f; label[k] = 0; }
+
+        if (active) {
+            float m0[C][VEC], a0[VEC];
+            float m1[LEVELS > 1 ? C : 1][VEC], a1[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                a0[k] = 0.f; a1[k] = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) m0[c][k] = 0.f;
+#pragma unroll
+                for (int c = 0; c < (LEVELS > 1 ? C : 1); ++c) m1[c][k] = 0.f;
+            }
+            const float* row0 = prm.x + b * prm.sb + v;
+
+            auto load_stage = [&](float (&x)[G][C][VEC], long long p0) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    if (G == 1 || p0 + g < P) {
+                        const float* r = row0 + (p0 + g) * prm.sp;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) VecLoad<VEC>::load(r + c * prm.sc, x[g][c]);
+                    }
+                }
+            };
+            auto consume_stage = [&](const float (&x)[G][C][VEC], long long p0) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    if (G == 1 || p0 + g < P) {
+                        float h[VEC];
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) h[k] = 0.f;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+#pragma unroll
+                            for (int k = 0; k < VEC; ++k) {
+                                m0[c][k] += x[g][c][k];
+                                h[k] += plog2p(x[g][c][k]);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) a0[k] += h[k];
+                        if (LEVELS > 1 && (((p0 + g) & 15) == 15)) {
+#pragma unroll
+                            for (int k = 0; k < VEC; ++k) {
+                                a1[k] += a0[k]; a0[k] = 0.f;
+#pragma unroll
+                                for (int c = 0; c < (LEVELS > 1 ? C : 1); ++c) { m1[c][k] += m0[c][k]; m0[c][k] = 0.f; }
+                            }
+                        }
+                    }
+                }
+            };
+
+            if (DB) {
+                float xa[G][C][VEC], xb[G][C][VEC];
+                load_stage(xa, 0);
+                for (long long p = 0; p < P; p += 2 * G) {
+                    if (p + G < P) load_stage(xb, p + G);
+                    consume_stage(xa, p);
+                    if (p + 2 * G < P) load_stage(xa, p + 2 * G);
+                    if (p + G < P) consume_stage(xb, p + G);
+                }
+            } else {
+                float xa[G][C][VEC];
+                for (long long p = 0; p < P; p += G) {
+                    load_stage(xa, p);
+                    consume_stage(xa, p);
+                }
+            }
+
+            // epilogue: mean (true division, test_2D.py:971), label, TU, AU, EU
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                float best = 0.f, tu2 = 0.f;
+                int idx = 0;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float s = (LEVELS > 1) ? (m0[c][k] + m1[c][k]) : m0[c][k];
+                    const float mean = s / Pf;
+                    if (c == 0) { best = mean; idx = 0; } else argmax_step(mean, c, best, idx);
+                    tu2 += plog2p(mean);
+                }
+                const float asum = (LEVELS > 1) ? (a0[k] + a1[k]) : a0[k];
+                const float tu = -(tu2 * kLn2);
+                const float au = (-(asum * kLn2)) / Pf;
+                u[0][k] = tu; u[1][k] = au; u[2][k] = tu - au;
+                label[k] = idx;
+            }
+            const long long o = b * V + v;
+            if (prm.tu) VecLoad<VEC>::store(prm.tu + o, u[0]);
+            if (prm.au) VecLoad<VEC>::store(prm.au + o, u[1]);
+            if (prm.eu) VecLoad<VEC>::store(prm.eu + o, u[2]);
+            if (prm.lab) VecLoad<VEC>::store_u8(prm.lab + o, label);
+        }
+
+        if (do_stats) stats_tile<VEC, WARPS>(prm.st, cs, active, b, v, u, label);
+    }
+    if (do_stats && cur_b >= 0) cs.flush(prm.st, cur_b);
+}
+
+// ---------------------------------------------------------------------------
+// Generic kernel: any C <= 256, any strides / alignment, any P up to the
+// shared-memory limit, all four cascade levels.  Class-outer order: the mean of
+// one class is finished in registers before the next class starts; the
+// per-member entropies accumulate in shared memory (h[p][thread]).
+// Also serves P == 1 (calculate_one_minus_msr, test_utils.py:862-864).
+// ---------------------------------------------------------------------------
+struct Cascade {
+    float a[4];
+    __device__ __forceinline__ void reset() { a[0] = a[1] = a[2] = a[3] = 0.f; }
+    // i = index of the member being added, n_full = members covered by whole
+    // chunks, k = log2(chunk)
+    __device__ __forceinline__ void add(float x, long long i, long long n_full, int k) {
+        a[0] += x;
+        const long long done = i + 1;
+        const long long mask = (1LL << k) - 1;
+        if (i < n_full && (done & mask) == 0) {
+#pragma unroll
+            for (int j = 1; j < 4; ++j) {
+                a[j] += a[j - 1];
+                a[j - 1] = 0.f;
+                if (done & (mask << (j * k))) break;
+            }
+        }
+    }
+    __device__ __forceinline__ float total() const { return ((a[0] + a[1]) + a[2]) + a[3]; }
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1Params prm, int level_k) {
+    constexpr int WARPS = THREADS / 32;
+    __shared__ CtaStats<WARPS> cs;
+    extern __shared__ float h_smem[];  // [P][THREADS]
+    const bool do_stats = prm.st.flags != 0;
+    if (do_stats) cs.init(prm.st);
+
+    const long long P = prm.P, V = prm.V;
+    const int C = (int)prm.C;
+    const float Pf = (float)P;
+    const long long n_full = (P >> level_k) << level_k;
+    const long long t0 = prm.total_tiles * (long long)blockIdx.x / gridDim.x;
+    const long long t1 = prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x;
+    long long cur_b = -1;
+    float* h = h_smem + threadIdx.x;
+
+    for (long long tile = t0; tile < t1; ++tile) {
+        const long long b = tile / prm.tiles_per_img;
+        const long long vt = tile - b * prm.tiles_per_img;
+        const long long v = vt * (long long)THREADS + threadIdx.x;
+        if (do_stats && b != cur_b) {
+            if (cur_b >= 0) cs.flush(prm.st, cur_b);
+            cur_b = b;
+        }
+        const bool active = v < V;
+        float u[VU_N_UNC] = {0.f, 0.f, 0.f};
+        int label = 0;
+        if (active) {
+            const float* base = prm.x + b * prm.sb + v * prm.sv;
+            if (P > 1)
+                for (long long p = 0; p < P; ++p) h[p * THREADS] = 0.f;
+            float best = 0.f, tu2 = 0.f;
+            for (int c = 0; c < C; ++c) {
+                Cascade cas;
+                cas.reset();
+                const float* pc = base + (long long)c * prm.sc;
+                for (long long p = 0; p < P; ++p) {
+                    const float x = ldg_stream(pc + p * prm.sp);
+                    cas.add(x, p, n_full, level_k);
+                    if (P > 1) h[p * THREADS] += plog2p(x);
+                }
+                const float mean = cas.total() / Pf;
+                if (c == 0) { best = mean; label = 0; } else argmax_step(mean, c, best, label);
+                tu2 += plog2p(mean);
+            }
+            const long long o = b * V + v;
+            if (P > 1) {
+                Cascade cas;
+                cas.reset();
+                for (long long p = 0; p < P; ++p) cas.add(h[p * THREADS], p, n_full, level_k);
+                const float tu = -(tu2 * kLn2);
+                const float au = (-(cas.total() * kLn2)) / Pf;
+                u[0] = tu; u[1] = au; u[2] = tu - au;
+                if (prm.tu) __stcs(prm.tu + o, u[0]);
+                if (prm.au) __stcs(prm.au + o, u[1]);
+                if (prm.eu) __stcs(prm.eu + o, u[2]);
+            } else {
+                u[0] = 1.0f - best;  // test_utils.py:863-864
+                if (prm.tu) __stcs(prm.tu + o, u[0]);
+            }
+            if (prm.lab) prm.lab[o] = (uint8_t)label;
+        }
+        if (do_stats) {
+            const float u1[VU_N_UNC][1] = {{u[0]}, {u[1]}, {u[2]}};
+            const int l1[1] = {label};
+            stats_tile<1, WARPS>(prm.st, cs, active, b, v, u1, l1);
+        }
+    }
+    if (do_stats && cur_b >= 0) cs.flush(prm.st, cur_b);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef void (*K1Kernel)(const K1Params);
+struct FastVariant {
+    int C, VEC, LEVELS, THREADS, MINB, G, DB;
+    K1Kernel fn;        // maps + labels only
+    K1Kernel fn_stats;  // with the per-image statistics phase
+};
+
+#define VU_VARIANT(C, VEC, LEVELS, THREADS, MINB, G, DB)                                   \
+    { C, VEC, LEVELS, THREADS, MINB, G, DB,                                                \
+      (K1Kernel)k1_fast<C, VEC, LEVELS, THREADS, MINB, G, DB, false>,                      \
+      (K1Kernel)k1_fast<C, VEC, LEVELS, THREADS, MINB, G, DB, true> }
+
+// First entry matching (C, LEVELS, alignment) wins unless the "k1_variant"
+// option selects another by index (used by the tuning sweep, bench/sweep_k1.py).
+static const FastVariant kFast[] = {
+    // ---- C = 2 (LIDC-like, toy): few loads per member -> group members
+    VU_VARIANT(2, 4, 1, 256, 2, 4, true),    // 0
+    VU_VARIANT(2, 4, 2, 256, 2, 4, true),    // 1
+    VU_VARIANT(2, 4, 1, 256, 2, 8, false),   // 2
+    VU_VARIANT(2, 4, 2, 256, 2, 8, false),   // 3
+    VU_VARIANT(2, 4, 1, 128, 4, 4, true),    // 4
+    VU_VARIANT(2, 4, 2, 128, 4, 4, true),    // 5
+    VU_VARIANT(2, 2, 1, 256, 2, 8, true),    // 6
+    VU_VARIANT(2, 2, 2, 256, 2, 8, true),    // 7
+    VU_VARIANT(2, 1, 1, 256, 2, 8, true),    // 8  (unaligned V)
+    VU_VARIANT(2, 1, 2, 256, 2, 8, true),    // 9
+    // ---- C = 19 (Cityscapes / GTA): 19 independent loads per member
+    VU_VARIANT(19, 2, 1, 256, 2, 1, false),  // 10
+    VU_VARIANT(19, 2, 2, 256, 1, 1, false),  // 11
+    VU_VARIANT(19, 4, 1, 256, 1, 1, false),  // 12
+    VU_VARIANT(19, 4, 1, 128, 2, 1, false),  // 13
+    VU_VARIANT(19, 2, 1, 256, 1, 1, true),   // 14
+    VU_VARIANT(19, 2, 1, 128, 4, 1, false),  // 15
+    VU_VARIANT(19, 1, 1, 256, 3, 1, false),  // 16
+    VU_VARIANT(19, 1, 2, 256, 2, 1, false),  // 17
+    VU_VARIANT(19, 1, 1, 256, 2, 1, true),   // 18
+    // ---- small C
+    VU_VARIANT(3, 4, 1, 256, 2, 2, true),    // 19
+    VU_VARIANT(3, 4, 2, 256, 2, 2, true),    // 20
+    VU_VARIANT(3, 1, 1, 256, 2, 4, true),    // 21
+    VU_VARIANT(3, 1, 2, 256, 2, 4, true),    // 22
+    VU_VARIANT(4, 4, 1, 256, 2, 2, true),    // 23
+    VU_VARIANT(4, 4, 2, 256, 2, 2, true),    // 24
+    VU_VARIANT(4, 1, 1, 256, 2, 4, true),    // 25
+    VU_VARIANT(4, 1, 2, 256, 2, 4, true),    // 26
+};
+static const int kNumFast = (int)(sizeof(kFast) / sizeof(kFast[0]));
+
+static bool aligned_for(const vu_fused_args* a, int vec) {
+    if (vec == 1) return true;
+    const vu_slab& s = a->slab;
+    const uintptr_t bytes = (uintptr_t)vec * 4;
+    auto ok = [&](const void* p) { return p == nullptr || ((uintptr_t)p % bytes) == 0; };
+    if (!ok(s.data) || !ok(a->tu) || !ok(a->au) || !ok(a->eu)) return false;
+    if (a->labels && ((uintptr_t)a->labels % vec) != 0) return false;
+    if (s.V % vec || s.stride_p % vec || s.stride_b % vec || s.stride_c % vec) return false;
+    return true;
+}
+
+static int level_power_for(long long P) {
+    // ATen cascade_sum: max(4, ceil(log2 P) / 4)
+    int lg = 0;
+    while ((1LL << lg) < P) ++lg;
+    return lg / 4 > 4 ? lg / 4 : 4;
+}
+
+int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream) {
+    const vu_slab& s = a->slab;
+    K1Params prm;
+    prm.x = s.data;
+    prm.P = s.P; prm.B = s.B; prm.C = s.C; prm.V = s.V;
+    prm.sp = s.stride_p; prm.sb = s.stride_b; prm.sc = s.stride_c; prm.sv = s.stride_v;
+    prm.tu = a->tu; prm.au = a->au; prm.eu = a->eu; prm.lab = a->labels;
+    prm.st = st;
+
+    const int sms = device_sm_count();
+    const long long forced = get_option("k1_variant", -1);
+    const int need_levels = s.P <= 17 ? 1 : (s.P <= 271 ? 2 : 3);
+
+    const FastVariant* pick = nullptr;
+    if (s.stride_v == 1 && s.P >= 2 && need_levels <= 2 && forced != -2) {
+        if (forced >= 0 && forced < kNumFast) {
+            const FastVariant& f = kFast[forced];
+            if (f.C == s.C && f.LEVELS >= need_levels && aligned_for(a, f.VEC)) pick = &f;
+            else return set_error(VU_ERR_UNSUPPORTED, "k1_variant does not fit this slab");
+        } else {
+            for (int i = 0; i < kNumFast && !pick; ++i) {
+                const FastVariant& f = kFast[i];
+                if (f.C == s.C && f.LEVELS == need_levels && aligned_for(a, f.VEC)) pick = &f;
+            }
+        }
+    }
+
+    if (pick) {
+        const long long tile_vox = (long long)pick->THREADS * pick->VEC;
+        prm.tiles_per_img = (s.V + tile_vox - 1) / tile_vox;
+        prm.total_tiles = prm.tiles_per_img * s.B;
+        K1Kernel fn = st.flags ? pick->fn_stats : pick->fn;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pick->THREADS, 0) != cudaSuccess || occ < 1)
+            return set_cuda_error("occupancy query (k1_fast)");
+        long long grid = (long long)sms * occ;
+        if (grid > prm.total_tiles) grid = prm.total_tiles;
+        fn<<<(unsigned)grid, pick->THREADS, 0, stream>>>(prm);
+        count_launch("k1_fast");
+        return check_launch("k1_fast");
+    }
+
+    // generic path
+    constexpr int T = 64;
+    const size_t max_dyn = 160 * 1024;
+    size_t dyn = (size_t)(s.P > 1 ? s.P : 0) * T * sizeof(float);
+    if (dyn > max_dyn) return set_error(VU_ERR_UNSUPPORTED, "P too large for the generic kernel (P*256 B of shared memory)");
+    if (s.P > (1LL << 19)) return set_error(VU_ERR_UNSUPPORTED, "P > 2^19");
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k1_generic<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(k1_generic)");
+        attr_set = true;
+    }
+    prm.tiles_per_img = (s.V + T - 1) / T;
+    prm.total_tiles = prm.tiles_per_img * s.B;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_generic<T>, T, dyn) != cudaSuccess || occ < 1)
+        return set_cuda_error("occupancy query (k1_generic)");
+    long long grid = (long long)sms * occ;
+    if (grid > prm.total_tiles) grid = prm.total_tiles;
+    k1_generic<T><<<(unsigned)grid, T, dyn, stream>>>(prm, level_power_for(s.P));
+    count_launch("k1_generic");
+    return check_launch("k1_generic");
+}
+
+int num_fast_variants() { return kNumFast; }
+int describe_fast_variant(int i, int* out7) {
+    if (i < 0 || i >= kNumFast) return -1;
+    const FastVariant& f = kFast[i];
+    out7[0] = f.C; out7[1] = f.VEC; out7[2] = f.LEVELS; out7[3] = f.THREADS; out7[4] = f.MINB; out7[5] = f.G; out7[6] = f.DB;
+    return 0;
+}
+
+}  // namespace vu

@@ -1,0 +1,34 @@
+// Host-side plumbing shared by the translation units of libvalunc.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "valunc.h"
+
+#define VU_STR2(x) #x
+#define VU_STR(x) VU_STR2(x)
+
+namespace vu {
+struct StatParams;
+
+int set_error(int code, const char* msg);        // records msg, returns code
+int set_cuda_error(const char* where);           // records cudaGetLastError text, returns VU_ERR_CUDA
+int check_launch(const char* kernel);            // cudaPeekAtLastError after a launch
+void count_launch(const char* kernel);           // launch counters for bench.py ("gpu_launches")
+long long get_option(const char* key, long long dflt);
+int device_sm_count();
+
+int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream);
+int num_fast_variants();
+int describe_fast_variant(int i, int* out7);
+int launch_map_stats(const vu_map_stats_args* a, const StatParams& st, cudaStream_t stream);
+int launch_patch_max(const float* maps, long long B, long long d0, long long d1, long long d2, int k0, int k1, int k2,
+                     int mean, double* out_max, long long* out_first, cudaStream_t stream);
+int launch_border(const uint8_t* labels, long long B, long long d0, long long d1, long long d2, long long* stats_i64,
+                  cudaStream_t stream);
+int launch_synth_slab(float* out, long long P, long long B, long long C, long long V, uint64_t seed,
+                      long long first_image, float scale, cudaStream_t stream);
+int launch_synth_gt(uint8_t* out, const float* slab, long long P, long long B, long long C, long long V, int R,
+                    uint64_t seed, long long first_image, float flip, float ignore_frac, int ignore_value,
+                    cudaStream_t stream);
+}  // namespace vu

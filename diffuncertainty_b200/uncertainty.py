@@ -1,0 +1,247 @@
+"""C2 uncertainty measures on the GPU, behind the reference's call surface.
+
+``calculate_uncertainty`` / ``calculate_one_minus_msr`` are drop-ins for
+uncertainty_modeling/unc_mod_utils/test_utils.py:833-864 (same argument, same
+dict keys, fp32 maps on the input's device).  ``fused_pass`` is the batch form
+that replaces the per-image loop of ``Tester.process_output``
+(uncertainty_modeling/test_2D.py:968-1041): one launch for the whole
+``softmax_pred`` of shape (P, B, C, *S), strided views accepted as they are.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F64, I64
+
+UNC_KEYS = ("TU", "AU", "EU")
+
+
+def _spatial_strides_flat(t: torch.Tensor, first_spatial_dim: int) -> Optional[int]:
+    """Element stride of the flattened spatial index, or None if the spatial
+    dims cannot be addressed as one strided run (then a copy is unavoidable)."""
+    shape, stride = t.shape[first_spatial_dim:], t.stride()[first_spatial_dim:]
+    dims = [(n, s) for n, s in zip(shape, stride) if n != 1]
+    if not dims:
+        return 1
+    for (n0, s0), (n1, s1) in zip(dims[:-1], dims[1:]):
+        if s0 != n1 * s1:
+            return None
+    return dims[-1][1]
+
+
+def _check_slab(x: torch.Tensor, what: str) -> None:
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"{what} must be a torch.Tensor, got {type(x)}")
+    if not x.is_cuda:
+        raise _lib.ValuncError(f"{what} must live on a CUDA device (no CPU fallback in diffuncertainty_b200)")
+
+
+@dataclass
+class GroundTruth:
+    """batch["seg"] handed alongside the slab (test_2D.py:1122-1124): (B, R, *S)
+    int64 or uint8, optional ignore value (ace.py:492-499, test_2D.py:880)."""
+    seg: torch.Tensor
+    ignore_index: Optional[int] = None
+
+
+@dataclass
+class FusedResult:
+    """Outputs of one fused pass over a batch."""
+    maps: Dict[str, torch.Tensor]        # "TU","AU","EU" (or "pred_entropy") -> (B, *S) fp32
+    labels: Optional[torch.Tensor]       # (B, *S) uint8
+    stats_f64: Optional[torch.Tensor]    # (B, 80) float64, see valunc.h
+    stats_i64: Optional[torch.Tensor]    # (B, 156) int64
+    n_voxels: int
+    n_raters: int
+    stat_flags: int
+
+    # -- per-image scores, all computed on the host in float64 from the rows --
+    def _rows(self):
+        if self.stats_f64 is None:
+            raise ValueError("this pass was run without statistics (stats=0)")
+        return self.stats_f64.cpu().numpy(), self.stats_i64.cpu().numpy()
+
+    def image_level(self, mean: bool = True) -> np.ndarray:
+        """(B, 3) image_level_aggregation scores (aggregate_uncertainties.py:37-39)."""
+        f, _ = self._rows()
+        s = f[:, F64["SUM"]:F64["SUM"] + 3]
+        return s / self.n_voxels if mean else s
+
+    def threshold_level(self, mean: bool = True) -> np.ndarray:
+        """(B, 3) threshold_aggregation scores (aggregate_uncertainties.py:124-130):
+        mean over the pixels >= t, or the (zero) sum when none qualifies."""
+        f, i = self._rows()
+        s = f[:, F64["THR_SUM"]:F64["THR_SUM"] + 3]
+        n = i[:, I64["THR_COUNT"]:I64["THR_COUNT"] + 3]
+        if not mean:
+            return s
+        return np.where(n > 0, s / np.maximum(n, 1), s)
+
+    def area(self) -> np.ndarray:
+        return self._rows()[1][:, I64["AREA"]].astype(np.float64)
+
+    def border(self) -> np.ndarray:
+        return self._rows()[1][:, I64["BORDER"]].astype(np.float64)
+
+    def dice_counts(self):
+        """(tp, pred_sum, gt_sum), each (B, R) int64 (test_2D.py:878-886)."""
+        _, i = self._rows()
+        R = self.n_raters
+        return (i[:, I64["DICE_TP"]:I64["DICE_TP"] + R], i[:, I64["DICE_PRED"]:I64["DICE_PRED"] + R],
+                i[:, I64["DICE_GT"]:I64["DICE_GT"] + R])
+
+    def calib_histograms(self):
+        """(bin_sums f64, bin_true i64, bin_total i64), each (B, 3, 21) (ace.py:352-356)."""
+        f, i = self._rows()
+        B = f.shape[0]
+        return (f[:, F64["BIN_SUMS"]:F64["BIN_SUMS"] + 63].reshape(B, 3, 21),
+                i[:, I64["BIN_TRUE"]:I64["BIN_TRUE"] + 63].reshape(B, 3, 21),
+                i[:, I64["BIN_TOTAL"]:I64["BIN_TOTAL"] + 63].reshape(B, 3, 21))
+
+    def ncc_sums(self):
+        f, _ = self._rows()
+        return dict(g=f[:, F64["NCC_G"]], gg=f[:, F64["NCC_GG"]], u=f[:, F64["NCC_U"]:F64["NCC_U"] + 3],
+                    uu=f[:, F64["NCC_UU"]:F64["NCC_UU"] + 3], gu=f[:, F64["NCC_GU"]:F64["NCC_GU"] + 3])
+
+
+def _fill_gt(gt_struct: _lib.Gt, gt: Optional[GroundTruth], B: int, spatial) -> Optional[torch.Tensor]:
+    if gt is None:
+        gt_struct.data = None
+        return None
+    seg = gt.seg
+    _check_slab(seg, "gt.seg")
+    if seg.dim() == 1 + len(spatial):  # (B, *S) -> (B, 1, *S) as test_2D.py:1123-1124 does
+        seg = seg.unsqueeze(1)
+    if seg.shape[0] != B or tuple(seg.shape[2:]) != tuple(spatial):
+        # ace.py:79-80 asserts the same contract
+        raise AssertionError(f"gt must have shape (B, R, *spatial) = ({B}, R, {tuple(spatial)}), got {tuple(seg.shape)}")
+    if seg.dtype == torch.uint8:
+        gt_struct.dtype = _lib.GT_U8
+    elif seg.dtype == torch.int64:
+        gt_struct.dtype = _lib.GT_I64
+    else:
+        raise TypeError(f"gt dtype must be uint8 or int64, got {seg.dtype}")
+    sv = _spatial_strides_flat(seg, 2)
+    if sv is None:
+        seg = seg.contiguous()
+        sv = 1
+    gt_struct.data = seg.data_ptr()
+    gt_struct.R = seg.shape[1]
+    gt_struct.stride_b, gt_struct.stride_r, gt_struct.stride_v = seg.stride(0), seg.stride(1), sv
+    gt_struct.has_ignore = 0 if gt.ignore_index is None else 1
+    gt_struct.ignore_index = 0 if gt.ignore_index is None else int(gt.ignore_index)
+    return seg  # keep alive
+
+
+def fused_pass(softmax_pred: torch.Tensor, gt: Optional[GroundTruth] = None, *, stats: int = 0,
+               thresholds: Optional[Sequence[float]] = None, calib=None, label_lut: Optional[torch.Tensor] = None,
+               want_maps: bool = True, want_labels: bool = True,
+               stats_out: Optional[tuple] = None) -> FusedResult:
+    """One launch over ``softmax_pred`` of shape (P, B, C, *S) (test_2D.py:1277).
+
+    stats      : OR of _lib.STAT_* flags
+    thresholds : three floats (TU, AU, EU) for STAT_THRESHOLD
+    calib      : three ``calibration.PlattEdges`` for STAT_CALIB
+    stats_out  : optional (stats_f64, stats_i64) device tensors to accumulate
+                 into (rows = images of this batch)
+    """
+    _check_slab(softmax_pred, "softmax_pred")
+    if softmax_pred.dim() < 4:
+        raise ValueError(f"softmax_pred must be (P, B, C, *spatial), got shape {tuple(softmax_pred.shape)}")
+    if softmax_pred.dtype != torch.float32:
+        # the reference computes fp32 maps whatever the input dtype (test_utils.py:836);
+        # the kernels read fp32 only, so other dtypes are upcast once here
+        softmax_pred = softmax_pred.float()
+    _lib.require_device()
+    lib = _lib.load()
+    P, B, Cn = softmax_pred.shape[:3]
+    spatial = tuple(softmax_pred.shape[3:])
+    V = int(np.prod(spatial)) if spatial else 1
+    sv = _spatial_strides_flat(softmax_pred, 3)
+    if sv is None:
+        softmax_pred = softmax_pred.contiguous()
+        sv = 1
+    dev = softmax_pred.device
+    a = _lib.FusedArgs()
+    a.struct_size = C.sizeof(_lib.FusedArgs)
+    a.stat_flags = int(stats)
+    a.slab.data = softmax_pred.data_ptr()
+    a.slab.P, a.slab.B, a.slab.C, a.slab.V = P, B, Cn, V
+    a.slab.stride_p, a.slab.stride_b, a.slab.stride_c = softmax_pred.stride(0), softmax_pred.stride(1), softmax_pred.stride(2)
+    a.slab.stride_v = sv
+
+    maps: Dict[str, torch.Tensor] = {}
+    with torch.cuda.device(dev):
+        if want_maps:
+            names = UNC_KEYS if P > 1 else ("pred_entropy",)
+            for name in names:
+                maps[name] = torch.empty((B,) + spatial, dtype=torch.float32, device=dev)
+            a.tu = maps[names[0]].data_ptr()
+            if P > 1:
+                a.au, a.eu = maps["AU"].data_ptr(), maps["EU"].data_ptr()
+        labels = torch.empty((B,) + spatial, dtype=torch.uint8, device=dev) if want_labels else None
+        a.labels = labels.data_ptr() if labels is not None else None
+        keep = _fill_gt(a.gt, gt, B, spatial)
+        if thresholds is not None:
+            for k in range(3):
+                a.threshold[k] = float(thresholds[k])
+        elif stats & _lib.STAT_THRESHOLD:
+            # aggregate_uncertainties.py:112-115 raises a bare Exception in this situation
+            raise Exception("A threshold needs to be provided for threshold aggregation!")
+        if calib is not None:
+            for k in range(min(3, len(calib))):
+                a.calib[k] = calib[k].as_struct()
+        elif stats & _lib.STAT_CALIB:
+            raise ValueError("STAT_CALIB needs `calib` (three PlattEdges)")
+        if label_lut is not None:
+            if label_lut.dtype != torch.uint8 or label_lut.numel() != 256 or not label_lut.is_cuda:
+                raise ValueError("label_lut must be a CUDA uint8 tensor with 256 entries")
+            a.calib_label_lut = label_lut.data_ptr()
+        sf = si = None
+        if stats:
+            if stats_out is not None:
+                sf, si = stats_out
+                if sf.shape != (B, F64["COLS"]) or si.shape != (B, I64["COLS"]) or sf.dtype != torch.float64 \
+                        or si.dtype != torch.int64 or not sf.is_contiguous() or not si.is_contiguous():
+                    raise ValueError("stats_out must be contiguous (B, 80) float64 and (B, 156) int64 tensors")
+            else:
+                sf = torch.zeros((B, F64["COLS"]), dtype=torch.float64, device=dev)
+                si = torch.zeros((B, I64["COLS"]), dtype=torch.int64, device=dev)
+            a.stats_f64, a.stats_i64 = sf.data_ptr(), si.data_ptr()
+        _lib.check(lib.vu_fused_pass(C.byref(a), _lib.current_stream_ptr()), "vu_fused_pass")
+    del keep
+    return FusedResult(maps=maps, labels=labels, stats_f64=sf, stats_i64=si, n_voxels=V,
+                       n_raters=int(a.gt.R) if gt is not None else 0, stat_flags=int(stats))
+
+
+def calculate_uncertainty(softmax_preds: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Drop-in for test_utils.py:833-859: (P, C, *S) -> {"TU","AU","EU"} of shape S."""
+    _check_slab(softmax_preds, "softmax_preds")
+    if softmax_preds.dim() < 2:
+        raise ValueError("softmax_preds must be (P, C, *spatial)")
+    if softmax_preds.shape[0] == 1:
+        # the reference only reaches this function with P > 1 (test_2D.py:1004-1007); its
+        # formulas give TU = AU = H(p), EU = 0 for one member, which is what two identical
+        # members produce: present the member twice through a stride-0 view (no copy)
+        softmax_preds = softmax_preds.expand(2, *softmax_preds.shape[1:])
+    res = fused_pass(softmax_preds.unsqueeze(1), want_labels=False)
+    return {k: res.maps[k][0] for k in UNC_KEYS}
+
+
+def calculate_one_minus_msr(softmax_pred: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Drop-in for test_utils.py:862-864: (C, *S) -> {"pred_entropy": 1 - max_c p}."""
+    _check_slab(softmax_pred, "softmax_pred")
+    res = fused_pass(softmax_pred.unsqueeze(0).unsqueeze(0), want_labels=False)
+    return {"pred_entropy": res.maps["pred_entropy"][0]}
+
+
+def mean_argmax_labels(softmax_pred: torch.Tensor) -> torch.Tensor:
+    """argmax over classes of the member mean for a whole batch (test_2D.py:971, 871,
+    815-818): (P, B, C, *S) -> (B, *S) uint8."""
+    return fused_pass(softmax_pred, want_maps=False).labels

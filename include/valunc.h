@@ -1,0 +1,234 @@
+/*
+ * valunc.h -- C ABI of libvalunc.so: the B200 (sm_100a) implementation of the
+ * ValUES per-pixel uncertainty hot path (C2 measures + C3 aggregation +
+ * calibration / ambiguity / failure-detection inputs).
+ *
+ * The reference (JakobLC/DiffUncertainty) is pure Python and has no FFI layer;
+ * these entry points are what a binding for its hot path would call.  Each one
+ * cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - strides are in ELEMENTS, not bytes; the slab is never copied or made
+ *     contiguous (the per-image view softmax_pred[:, i] of test_2D.py:969 is
+ *     strided);
+ *   - functions only enqueue work on `stream` (a cudaStream_t passed as
+ *     void*); they never synchronise, allocate or free caller memory;
+ *   - statistics outputs ACCUMULATE (+=) so one buffer can span many calls;
+ *     the caller zeroes them;
+ *   - return value: VU_OK or a negative vu_status; nothing throws.
+ */
+#ifndef VALUNC_H
+#define VALUNC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VU_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VU_API __attribute__((visibility("default")))
+#else
+#define VU_API
+#endif
+
+typedef enum vu_status {
+    VU_OK = 0,
+    VU_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, bad enum     */
+    VU_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels handle         */
+    VU_ERR_CUDA = -3,         /* a CUDA runtime call failed (see vu_last_error)*/
+    VU_ERR_NO_DEVICE = -4     /* no sm_100 device visible                      */
+} vu_status;
+
+#define VU_N_UNC 3        /* TU, AU, EU in this order everywhere               */
+#define VU_N_BINS 21      /* ace.py:350-356: 20 bins, arrays of length 21      */
+#define VU_N_EDGES 19     /* interior edges of np.linspace(0, 1+1e-8, 21)      */
+#define VU_MAX_RATERS 8   /* R: LIDC 4, GTA 5         */
+#define VU_MAX_CLASSES 255 /* labels are uint8 (test_2D.py:818)                */
+
+/* ground-truth element types handed over by the data loader
+ * (batch["seg"].long(), test_2D.py:1122-1124, or uint8 PNG decodes) */
+#define VU_GT_U8 0
+#define VU_GT_I64 1
+
+/* which per-image statistics vu_fused_pass / vu_map_stats accumulate */
+#define VU_STAT_IMAGE_SUM 0x01u /* aggregate_uncertainties.py:37-39           */
+#define VU_STAT_THRESHOLD 0x02u /* aggregate_uncertainties.py:124-125         */
+#define VU_STAT_AREA 0x04u      /* prediction_shape_stats.py:10-12            */
+#define VU_STAT_DICE 0x08u      /* test_2D.py:878-886 (needs gt)              */
+#define VU_STAT_CALIB 0x10u     /* ace.py:350-356, 431-437 (needs gt)         */
+#define VU_STAT_NCC 0x20u       /* ncc.py:17-27 + experiment_dataloader.py:283*/
+
+/* ---- layout of one row of the per-image statistics buffers --------------- */
+/* double row (VU_F64_COLS doubles per image)                                 */
+#define VU_F64_SUM 0       /* [3]  sum of TU, AU, EU                          */
+#define VU_F64_THR_SUM 3   /* [3]  sum of map[map >= t]                       */
+#define VU_F64_NCC_G 6     /* [1]  sum g      (g = rater variance map)        */
+#define VU_F64_NCC_GG 7    /* [1]  sum g*g                                    */
+#define VU_F64_NCC_U 8     /* [3]  sum u                                      */
+#define VU_F64_NCC_UU 11   /* [3]  sum u*u                                    */
+#define VU_F64_NCC_GU 14   /* [3]  sum g*u                                    */
+#define VU_F64_BIN_SUMS 17 /* [3][21] sum of Platt confidences per bin        */
+#define VU_F64_COLS 80
+/* int64 row (VU_I64_COLS int64 per image)                                    */
+#define VU_I64_THR_COUNT 0   /* [3]  #(map >= t)                              */
+#define VU_I64_AREA 3        /* [1]  #(label > 0)                             */
+#define VU_I64_BORDER 4      /* [1]  neighbour-differs count (vu_border_count)*/
+#define VU_I64_NVOX 5        /* [1]  voxels seen                              */
+#define VU_I64_BIN_TOTAL 6   /* [3][21] samples per bin                       */
+#define VU_I64_BIN_TRUE 69   /* [3][21] correct samples per bin               */
+#define VU_I64_DICE_TP 132   /* [8]  per rater: pred==1 & gt==1 & valid       */
+#define VU_I64_DICE_PRED 140 /* [8]  per rater: pred==1 & valid               */
+#define VU_I64_DICE_GT 148   /* [8]  per rater: gt==1 & valid                 */
+#define VU_I64_COLS 156
+
+/* The stacked probabilities "softmax_pred" of test_2D.py:1277, shape
+ * (P, B, C, V) with V = H*W(*D) flattened; any strides.                      */
+typedef struct vu_slab {
+    const float* data;
+    int64_t P, B, C, V;
+    int64_t stride_p, stride_b, stride_c, stride_v;
+} vu_slab;
+
+/* batch["seg"]: (B, R, V) reference segmentations (test_2D.py:1122-1124).    */
+typedef struct vu_gt {
+    const void* data; /* NULL: no ground truth                                */
+    int32_t dtype;    /* VU_GT_U8 or VU_GT_I64                                */
+    int32_t R;        /* raters, 1..VU_MAX_RATERS                             */
+    int64_t stride_b, stride_r, stride_v;
+    int32_t has_ignore;
+    int64_t ignore_index; /* ace.py:492-499 ignore_value / test_2D.py:880     */
+} vu_gt;
+
+/* Platt-scaled calibration binning (ace.py:325-329, 350-352) for one
+ * uncertainty type.  conf(u) = 1 / (1 + exp(-u*a + b)) in float32.  The bin
+ * of a voxel is decided by comparing u with `edge_u` -- the 19 interior bin
+ * edges pulled back through conf() on the host with the reference's own
+ * float32 expression (vu_platt_invert_edges_host), so counts do not depend on
+ * the device's expf.  A NaN edge never matches; NaN u goes to slot 20 as
+ * np.digitize does.                                                          */
+#define VU_CALIB_PLATT_DEC 0 /* a < 0: conf falls with u, bin = #{k: u <= edge_u[k]} */
+#define VU_CALIB_PLATT_INC 1 /* a >= 0: conf rises with u, bin = #{k: u >= edge_u[k]} */
+#define VU_CALIB_IDENTITY 2  /* the map already holds confidences (calc_ace(correct,
+                                conf) drop-in): conf = clip(u, 0, 1), edge_u[k] = the
+                                smallest float32 >= the float64 edge                  */
+typedef struct vu_calib {
+    float a, b;
+    float edge_u[VU_N_EDGES];
+    int32_t mode;
+} vu_calib;
+
+typedef struct vu_fused_args {
+    uint32_t struct_size; /* sizeof(vu_fused_args), ABI check                 */
+    uint32_t stat_flags;  /* VU_STAT_* or 0                                   */
+    vu_slab slab;
+    /* maps, each (B, V) contiguous fp32; NULL = do not store.
+     * P >= 2: TU / AU / EU of test_utils.py:833-859.
+     * P == 1: `tu` receives 1 - max softmax ("pred_entropy",
+     *         test_utils.py:862-864); au / eu are not written.               */
+    float* tu;
+    float* au;
+    float* eu;
+    /* argmax of the member mean, (B, V) uint8 (test_2D.py:871, 815-818)      */
+    uint8_t* labels;
+    vu_gt gt;
+    float threshold[VU_N_UNC];   /* VU_STAT_THRESHOLD                         */
+    vu_calib calib[VU_N_UNC];    /* VU_STAT_CALIB                             */
+    /* optional label lookup applied to the predicted label before it is
+     * compared with the references in VU_STAT_CALIB (quirk Q14: LIDC PNGs
+     * store foreground as 255).  NULL = compare class ids.  256 entries.     */
+    const uint8_t* calib_label_lut;
+    double* stats_f64;  /* (B, VU_F64_COLS), accumulated; NULL iff flags == 0 */
+    int64_t* stats_i64; /* (B, VU_I64_COLS), accumulated                      */
+} vu_fused_args;
+
+/* ABI / build info ---------------------------------------------------------- */
+VU_API int vu_abi_version(void);
+VU_API const char* vu_build_info(void); /* "sm_100a nvcc 12.9 ..."                   */
+VU_API const char* vu_last_error(void); /* text of the last CUDA error on this thread*/
+VU_API int vu_device_check(void);       /* VU_OK if the current device is sm_100     */
+VU_API int vu_struct_size(int which);   /* 0 vu_fused_args, 1 vu_map_stats_args, 2 vu_calib:
+                                    lets a binding verify its struct layout   */
+
+/* The fused streaming pass.  Replaces, for a whole batch in one launch:
+ *   mean over members        test_2D.py:971
+ *   argmax label             test_2D.py:871, 815-818
+ *   calculate_uncertainty    unc_mod_utils/test_utils.py:833-859
+ *   calculate_one_minus_msr  unc_mod_utils/test_utils.py:862-864 (P == 1)
+ * and, per stat_flags, the reductions of
+ *   image_level_aggregation / threshold_aggregation
+ *                            aggregate_uncertainties.py:37-39, 124-125
+ *   _compute_area            prediction_shape_stats.py:10-12
+ *   binary Dice counts       test_2D.py:878-886
+ *   calib histograms         ace.py:350-356, 431-437
+ *   NCC sums                 ncc.py:17-27
+ * reading the slab exactly once.                                             */
+VU_API int vu_fused_pass(const vu_fused_args* args, void* stream);
+
+/* Same reductions on maps / labels that already exist in device memory (the
+ * reference's file-based evaluation, evaluation/eval_experiments.py:348-355,
+ * works on stored maps).  maps[k] may be NULL to skip a type.  `labels` is
+ * needed for AREA / DICE / CALIB.                                            */
+typedef struct vu_map_stats_args {
+    uint32_t struct_size;
+    uint32_t stat_flags;
+    int64_t B, V;
+    const float* maps[VU_N_UNC]; /* each (B, V) contiguous                    */
+    const uint8_t* labels;       /* (B, V)                                    */
+    vu_gt gt;
+    float threshold[VU_N_UNC];
+    vu_calib calib[VU_N_UNC];
+    const uint8_t* calib_label_lut;
+    const double* ncc_gt_map; /* optional (B, V) float64 ready-made GT map
+                                 (evaluation/utils/gta.py:15-35); NULL = use
+                                 the variance of the gt raters               */
+    double* stats_f64;
+    int64_t* stats_i64;
+} vu_map_stats_args;
+VU_API int vu_map_stats(const vu_map_stats_args* args, void* stream);
+
+/* patch_level_aggregation (aggregate_uncertainties.py:16-34) for B maps of
+ * shape (d0, d1, d2) (2-D maps: d0 = 1) with box (k0, k1, k2) ("valid").
+ * out_max[b]   = max box sum (float64)
+ * out_first[b] = row-major linear index, in the (d0-k0+1, d1-k1+1, d2-k2+1)
+ *                output grid, of the first box with np.isclose(sum, max)
+ *                (rtol 1e-5, atol 1e-8).
+ * mean != 0 divides the sums by k0*k1*k2 first (patch_level_aggregation's
+ * mean=True).  Four small launches on `stream`, no scratch memory.           */
+VU_API int vu_patch_max(const float* maps, int64_t B, int64_t d0, int64_t d1, int64_t d2,
+                 int32_t k0, int32_t k1, int32_t k2, int32_t mean,
+                 double* out_max, int64_t* out_first, void* stream);
+
+/* _compute_border (prediction_shape_stats.py:15-30) on (B, d0, d1, d2) uint8
+ * label maps; adds into stats_i64[b][VU_I64_BORDER] (row stride VU_I64_COLS) */
+VU_API int vu_border_count(const uint8_t* labels, int64_t B, int64_t d0, int64_t d1, int64_t d2,
+                    int64_t* stats_i64, void* stream);
+
+/* Host helper: pull the 19 interior edges of np.linspace(0, 1+1e-8, 21) back
+ * through the reference's float32 Platt expression (ace.py:329) by bisection
+ * over float32 bit patterns.  Fills calib->edge_u / increasing from a, b.    */
+VU_API int vu_platt_invert_edges_host(double a, double b, vu_calib* calib);
+
+/* Deterministic synthetic slab for benchmarks and smoke tests:
+ * softmax(scale * N(0,1)) over C, from a counter-based RNG keyed by
+ * (seed, first_image + b, p, c, v) so every GPU count sees the same images.
+ * Writes a contiguous (P, B, C, V) slab.                                     */
+VU_API int vu_synth_slab(float* out, int64_t P, int64_t B, int64_t C, int64_t V,
+                  uint64_t seed, int64_t first_image, float scale, void* stream);
+/* synthetic (B, R, V) uint8 references: label of member 0 with `flip` of the
+ * voxels re-drawn uniformly and `ignore_frac` set to ignore_value.           */
+VU_API int vu_synth_gt(uint8_t* out, const float* slab, int64_t P, int64_t B, int64_t C, int64_t V,
+                int32_t R, uint64_t seed, int64_t first_image, float flip, float ignore_frac,
+                int32_t ignore_value, void* stream);
+
+/* tuning / introspection used by bench.py and the variant sweep */
+VU_API int vu_set_option(const char* key, int64_t value); /* e.g. "k1_variant"       */
+VU_API int64_t vu_get_counter(const char* key);           /* e.g. "launches"         */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VALUNC_H */

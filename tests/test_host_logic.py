@@ -1,0 +1,85 @@
+"""Host-side logic of the product package against the oracle / golden vectors.
+Runs without a GPU."""
+import numpy as np
+import pytest
+
+from diffuncertainty_b200 import aurc as vaurc
+from diffuncertainty_b200 import calibration, ncc as vncc
+from oracle import oracle
+from conftest import case_names
+
+
+def test_platt_edges_reproduce_np_digitize(golden_calib):
+    rng = np.random.default_rng(3)
+    for name in case_names(golden_calib):
+        a, b = float(golden_calib[f"{name}/a"]), float(golden_calib[f"{name}/b"])
+        pe = calibration.platt_edges(a, b)
+        u = np.concatenate([golden_calib[f"{name}/unc"].ravel(), (rng.random(20000) ** 3 * 3).astype(np.float32),
+                            np.array([0.0, 1e-30, 0.6931472, 3.0, 1e10], np.float32)])
+        fin = pe.edge_u[~np.isnan(pe.edge_u)]
+        near = np.concatenate([np.nextafter(fin, np.float32(-np.inf)), fin, np.nextafter(fin, np.float32(np.inf))])
+        u = np.concatenate([u, near.astype(np.float32)])
+        conf = oracle.platt_scale_confid(-u, a, b)
+        assert conf.dtype == np.float32
+        want = np.digitize(np.clip(conf, 0, 1), oracle.calib_bin_edges()) - 1
+        assert np.array_equal(pe.bin_of(u), want), name
+
+
+def test_identity_edges():
+    pe = calibration.identity_edges()
+    rng = np.random.default_rng(0)
+    conf = np.concatenate([rng.random(50000).astype(np.float32), np.array([0, 1, 0.05, 0.1, 0.95], np.float32),
+                           pe.edge_u, np.nextafter(pe.edge_u, np.float32(0))])
+    want = np.digitize(conf, oracle.calib_bin_edges()) - 1
+    assert np.array_equal(pe.bin_of(conf), want)
+
+
+def test_ace_ece_finalisers_match_oracle(golden_calib):
+    for name in case_names(golden_calib):
+        correct, conf = golden_calib[f"{name}/correct"], golden_calib[f"{name}/conf"]
+        s, t, n = oracle.calib_histogram(correct, conf, binarize=False)
+        ace, ece = calibration.per_image_ace_ece(s, t, n)
+        assert ace == golden_calib[f"{name}/ace"], name
+        assert ece == golden_calib[f"{name}/ece"], name
+        g = calibration.GlobalCalibAccumulator()
+        g.accumulate_histogram(s, t, n)
+        assert g.compute_ace() == golden_calib[f"{name}/gace"]
+        assert g.compute_ece() == golden_calib[f"{name}/gece"]
+    assert np.isnan(calibration.GlobalCalibAccumulator().compute_ace())
+
+
+def test_ncc_from_sums(golden_ncc_aurc):
+    g = golden_ncc_aurc["ncc/gt_map"].astype(np.float64).ravel()
+    u = golden_ncc_aurc["ncc/pred"].astype(np.float64).ravel()
+    got = vncc.ncc_from_sums(g.size, g.sum(), (g * g).sum(), u.sum(), (u * u).sum(), (g * u).sum())
+    np.testing.assert_allclose(got, golden_ncc_aurc["ncc/value"], rtol=1e-6)  # the reference centres the float32 map in float32
+    assert vncc.ncc_from_sums(g.size, 0.0, 0.0, u.sum(), (u * u).sum(), 0.0) == 0.0
+    c = np.full(u.size, 0.3, np.float32).astype(np.float64)
+    assert vncc.ncc_from_sums(c.size, g.sum(), (g * g).sum(), c.sum(), (c * c).sum(), (g * c).sum()) == 0.0
+    self_ncc = vncc.ncc_from_sums(u.size, u.sum(), (u * u).sum(), u.sum(), (u * u).sum(), (u * u).sum())
+    np.testing.assert_allclose(self_ncc, (u.size - 1) / u.size, rtol=1e-9)
+
+
+def test_aurc_matches_golden_and_oracle(golden_ncc_aurc):
+    r, c = golden_ncc_aurc["aurc/risks"], golden_ncc_aurc["aurc/confids"]
+    np.testing.assert_allclose(vaurc.aurc(r, c), golden_ncc_aurc["aurc/aurc"], rtol=1e-12)
+    np.testing.assert_allclose(vaurc.eaurc(r, c), golden_ncc_aurc["aurc/eaurc"], rtol=1e-10)
+    cov, sel, w = vaurc.rc_curve_stats(r, c)
+    np.testing.assert_allclose(sel, golden_ncc_aurc["aurc/selective_risks"], rtol=1e-12)
+    np.testing.assert_allclose(w, golden_ncc_aurc["aurc/weights"], rtol=1e-12)
+    # tied confidences: points only on value changes (sorted stably here, so feed sorted ties)
+    rng = np.random.default_rng(1)
+    for n in (2, 3, 17, 100):
+        c2 = np.sort(np.round(rng.random(n), 1))
+        r2 = rng.random(n)
+        np.testing.assert_allclose(vaurc.aurc(r2, c2), oracle.aurc(r2, c2), rtol=1e-12)
+    assert vaurc.aurc(np.array([0.3]), np.array([0.1])) == oracle.aurc(np.array([0.3]), np.array([0.1]))
+
+
+def test_dice_from_counts():
+    tp = np.array([[1, 0, 2], [0, 0, 0]])
+    ps = np.array([[2, 2, 2], [0, 0, 5]])
+    gs = np.array([[1, 0, 2], [0, 3, 0]])
+    got = vaurc.binary_dice_from_counts(tp, ps, gs)
+    want = [oracle.binary_dice_from_counts(tp[i], ps[i], gs[i]) for i in range(2)]
+    np.testing.assert_allclose(got, want, rtol=1e-7)
