@@ -1,0 +1,13 @@
+"""diffuncertainty_b200 -- the ValUES per-pixel uncertainty hot path on B200.
+
+Hand-written sm_100a CUDA (libvalunc.so, C ABI in include/valunc.h) behind the
+Python call surface of JakobLC/DiffUncertainty's
+``uncertainty_modeling/unc_mod_utils/test_utils.py`` (C2 measures),
+``evaluation/uncertainty_aggregation`` (C3 aggregation) and
+``evaluation/metrics`` (ECE/ACE, NCC, AURC inputs).  There is no CPU fallback.
+"""
+from . import _lib  # noqa: F401
+from .uncertainty import (FusedResult, GroundTruth, calculate_one_minus_msr, calculate_uncertainty, fused_pass,  # noqa: F401
+                          mean_argmax_labels)
+
+__version__ = "0.1.0"

@@ -90,7 +90,7 @@ __device__ __forceinline__ float plog2p(float p) {
     t = fmaf(t, f, kLog2e);
     const float near_one = t * f;
     const float l = (fabsf(f) < (1.0f / 64.0f)) ? near_one : lg;
-    const float term = p * l;
+    const float term = __fmul_rn(p, l);  // never contracted into the caller's add: all kernels agree bitwise
     return (p >= FLT_MIN) ? term : 0.0f;
 }
 

@@ -1,0 +1,387 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the
+golden vectors recorded from the unmodified reference.
+
+Tolerances (BASELINE.json north_star):
+  * labels, areas, borders, Dice counts, bin counts, threshold counts: bit-exact
+  * TU, AU, scores, bin_sums, NCC: |d| <= RTOL * |ref| (+ ATOL for values that
+    are ~0 in the reference: subnormal probabilities are flushed on the device)
+  * EU = TU - AU cancels, so |d| <= RTOL * max(|TU|, |AU|)
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import case_names
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+ATOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def vu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import diffuncertainty_b200 as pkg
+    from diffuncertainty_b200 import _lib
+    _lib.require_device()
+    return pkg
+
+
+def assert_maps_close(got, ref, name=""):
+    """got / ref: dicts with TU, AU, EU numpy arrays."""
+    tu, au = ref["TU"].astype(np.float64), ref["AU"].astype(np.float64)
+    for key in ("TU", "AU"):
+        r = ref[key].astype(np.float64)
+        g = got[key].astype(np.float64)
+        fin = np.isfinite(r)
+        assert np.array_equal(np.isfinite(g), fin), (name, key, "finite pattern")
+        assert np.array_equal(g[~fin], r[~fin], equal_nan=True), (name, key)
+        err = np.abs(g[fin] - r[fin])
+        tol = RTOL * np.abs(r[fin]) + ATOL
+        assert np.all(err <= tol), (name, key, float((err / np.maximum(np.abs(r[fin]), 1e-30)).max()))
+    fin = np.isfinite(tu) & np.isfinite(au)
+    err = np.abs(got["EU"].astype(np.float64)[fin] - ref["EU"].astype(np.float64)[fin])
+    tol = RTOL * np.maximum(np.abs(tu[fin]), np.abs(au[fin])) + ATOL
+    assert np.all(err <= tol), (name, "EU", float(err.max()))
+
+
+def oracle_image(x_cpu):
+    from oracle import oracle
+    torch.set_num_threads(1)
+    u = oracle.calculate_uncertainty(x_cpu)
+    mean = oracle.mean_members_f32(x_cpu.numpy())
+    label = oracle.argmax_first_nan_max(mean).astype(np.uint8)
+    return {k: v.numpy() for k, v in u.items()}, label
+
+
+# --------------------------------------------------------------------------
+# golden vectors recorded from the reference
+# --------------------------------------------------------------------------
+def test_golden_uncertainty_maps_and_labels(vu, golden_unc):
+    for name in case_names(golden_unc):
+        x = torch.from_numpy(golden_unc[f"{name}/x"]).cuda()
+        if name == "msr_p1":
+            got = vu.calculate_one_minus_msr(x.squeeze(0))["pred_entropy"].cpu().numpy()
+            np.testing.assert_allclose(got, golden_unc[f"{name}/pred_entropy"], rtol=1e-6, atol=1e-7)
+            res = vu.fused_pass(x.unsqueeze(1))
+            assert np.array_equal(res.labels[0].cpu().numpy(), golden_unc[f"{name}/label"])
+            continue
+        got = {k: v.cpu().numpy() for k, v in vu.calculate_uncertainty(x).items()}
+        for k in got:
+            assert got[k].dtype == np.float32 and got[k].shape == x.shape[2:]
+        ref = {k: golden_unc[f"{name}/{k}"] for k in ("TU", "AU", "EU")}
+        assert_maps_close(got, ref, name)
+        res = vu.fused_pass(x.unsqueeze(1))
+        lab = res.labels[0].cpu().numpy()
+        # the reference's torch.mean uses an interleaved order in its SIMD tail (last numel % 32
+        # elements, see oracle.cascade_sum_f32); labels there can only differ on 1-ulp ties
+        from oracle import oracle
+        canon = oracle.argmax_first_nan_max(oracle.mean_members_f32(golden_unc[f"{name}/x"])).astype(np.uint8)
+        assert np.array_equal(lab, canon), name
+        n = lab.size * x.shape[1]
+        body = (n // 32) * 32 // x.shape[1]
+        assert np.array_equal(lab.ravel()[: max(body - 32, 0)], golden_unc[f"{name}/label"].ravel()[: max(body - 32, 0)]), name
+
+
+def test_plogp_accuracy_dense_sweep(vu):
+    """-p log p against float64 over 30 decades and densely next to p = 1."""
+    p = np.concatenate([np.logspace(-37, 0, 40000), 1 - np.logspace(-8, -0.31, 40000), np.linspace(0.4, 1.0, 40000),
+                        1 + np.logspace(-7, 0, 4000)]).astype(np.float32)
+    n = p.size
+    x = torch.zeros(2, 1, 2, n)
+    x[:, 0, 0] = torch.from_numpy(p)
+    res = vu.fused_pass(x.cuda())
+    tu = res.maps["TU"][0].cpu().numpy().astype(np.float64)
+    p64 = p.astype(np.float64)
+    want = -p64 * np.log(p64)
+    err = np.abs(tu - want)
+    # relative to the term itself, except right at p = 1 where the term vanishes
+    assert np.all(err <= 2e-6 * np.abs(want) + 1e-9 * np.abs(p64 - 1) + 1e-37), float((err / np.maximum(np.abs(want), 1e-30)).max())
+
+
+# --------------------------------------------------------------------------
+# seeded random slabs against the oracle: shapes of all BASELINE configs (reduced)
+# --------------------------------------------------------------------------
+CASES = [
+    # P, B, C, spatial, scale
+    (10, 3, 2, (32, 32), 2.0),      # cfg1
+    (5, 2, 2, (8, 16, 16), 2.0),    # cfg2 (3-D)
+    (10, 1, 19, (16, 64), 6.0),     # cfg3
+    (32, 2, 2, (32, 32), 10.0),     # cfg4, peaked
+    (16, 2, 19, (8, 64), 3.0),      # cfg5
+    (17, 1, 2, (16, 32), 2.0), (18, 1, 2, (16, 32), 2.0), (33, 1, 19, (4, 32), 2.0),
+    (2, 1, 3, (8, 16), 2.0), (7, 2, 4, (8, 16), 2.0), (48, 1, 4, (8, 16), 4.0),
+    (6, 1, 5, (8, 16), 2.0), (3, 1, 21, (4, 16), 2.0),           # generic kernel (C not specialised)
+    (10, 2, 2, (7, 9), 2.0), (10, 1, 19, (5, 13), 2.0), (20, 1, 3, (3, 11), 2.0),   # unaligned V
+    (272, 1, 2, (4, 16), 2.0), (300, 1, 3, (2, 16), 2.0),        # three cascade levels -> generic
+]
+
+
+@pytest.mark.parametrize("P,B,C,spatial,scale", CASES)
+def test_random_slabs_vs_oracle(vu, P, B, C, spatial, scale):
+    g = torch.Generator().manual_seed(P * 1000 + C * 10 + len(spatial))
+    x = torch.softmax(scale * torch.randn(P, B, C, *spatial, generator=g), dim=2)
+    res = vu.fused_pass(x.cuda())
+    for b in range(B):
+        ref, label = oracle_image(x[:, b])
+        got = {k: res.maps[k][b].cpu().numpy() for k in ("TU", "AU", "EU")}
+        assert_maps_close(got, ref, f"P{P} C{C} b{b}")
+        assert np.array_equal(res.labels[b].cpu().numpy(), label.reshape(spatial))
+        # create_TU.py:46-55 invariant: TU == AU + EU up to an ulp
+        np.testing.assert_allclose(got["AU"] + got["EU"], got["TU"], rtol=3e-7, atol=1e-7)
+
+
+def test_strided_views_are_read_in_place(vu):
+    g = torch.Generator().manual_seed(9)
+    big = torch.softmax(2 * torch.randn(6, 5, 2, 16, 48, generator=g), dim=2).cuda()
+    views = {
+        "image slice (test_2D.py:969)": big[:, 2:3],
+        "every other image": big[:, ::2],
+        "cropped columns (stride_v=1, rows not contiguous -> copy)": big[..., 8:40],
+        "class-last memory layout": big.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3),
+        "column step 2 (stride_v = 2)": big[..., ::2] if False else big[:, :, :, 0:1, ::2],
+    }
+    for name, v in views.items():
+        res = vu.fused_pass(v)
+        ref = vu.fused_pass(v.contiguous())
+        for k in ("TU", "AU", "EU"):
+            assert torch.equal(res.maps[k], ref.maps[k]), name
+        assert torch.equal(res.labels, ref.labels), name
+        rr, label = oracle_image(v[:, 0].cpu())
+        assert_maps_close({k: res.maps[k][0].cpu().numpy() for k in ("TU", "AU", "EU")}, rr, name)
+
+
+def test_input_contract(vu):
+    with pytest.raises(Exception):
+        vu.calculate_uncertainty(torch.rand(3, 2, 4, 4))  # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        vu.fused_pass(torch.rand(3, 2, 4, device="cuda"))
+    empty = vu.fused_pass(torch.rand(3, 0, 2, 4, 4, device="cuda"))
+    assert empty.labels.shape == (0, 4, 4)
+    x = torch.softmax(torch.randn(4, 2, 8, 8, dtype=torch.float64), 1).cuda()
+    out = vu.calculate_uncertainty(x)  # fp64 in -> fp32 out (test_utils.py:836)
+    assert out["TU"].dtype == torch.float32
+    one = torch.softmax(torch.randn(1, 3, 8, 8), 1)
+    from oracle import oracle
+    ref = oracle.calculate_uncertainty(one)
+    got = vu.calculate_uncertainty(one.cuda())
+    np.testing.assert_allclose(got["TU"].cpu().numpy(), ref["TU"].numpy(), rtol=RTOL)
+    assert float(got["EU"].abs().max()) <= 1e-6
+
+
+# --------------------------------------------------------------------------
+# fused per-image statistics
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("P,B,C,spatial,R,ignore,dtype", [
+    (5, 3, 2, (8, 16, 16), 4, None, torch.uint8),       # cfg2-like
+    (10, 2, 19, (16, 64), 5, 255, torch.uint8),         # cfg3-like with ignore
+    (32, 3, 2, (32, 32), 4, None, torch.int64),         # cfg4-like, int64 gt as the loader hands it
+    (16, 2, 19, (8, 64), 1, 255, torch.int64),          # cfg5-like
+    (6, 2, 5, (9, 7), 3, -1, torch.int64),              # generic kernel, unaligned, ignore -1
+])
+def test_fused_statistics_vs_oracle(vu, P, B, C, spatial, R, ignore, dtype):
+    from diffuncertainty_b200 import _lib, aurc as vaurc, calibration, ncc as vncc
+    from oracle import oracle
+    g = torch.Generator().manual_seed(P + C + R)
+    x = torch.softmax(4 * torch.randn(P, B, C, *spatial, generator=g), dim=2)
+    member0 = x[0].argmax(dim=1)
+    noise = torch.randint(0, C, (B, R, *spatial), generator=g)
+    gt = torch.where(torch.rand(B, R, *spatial, generator=g) < 0.75, member0.unsqueeze(1).expand(B, R, *spatial), noise)
+    if ignore is not None:
+        gt = torch.where(torch.rand(B, R, *spatial, generator=g) < 0.05, torch.full_like(gt, ignore), gt)
+    gt = gt.to(dtype) if dtype == torch.int64 else (gt % 256).to(torch.uint8)
+    ign = None if ignore is None else (ignore if dtype == torch.int64 else ignore % 256)
+    platt = [(3.5, -1.25), (6.0, -2.0), (40.0, -0.5)]
+    thr = [0.2, 0.15, 0.01]
+    flags = (_lib.STAT_IMAGE_SUM | _lib.STAT_THRESHOLD | _lib.STAT_AREA | _lib.STAT_DICE | _lib.STAT_CALIB | _lib.STAT_NCC)
+    res = vu.fused_pass(x.cuda(), vu.GroundTruth(gt.cuda(), ign), stats=flags, thresholds=thr,
+                        calib=[calibration.platt_edges(a, b) for a, b in platt])
+    img_mean, thr_score = res.image_level(), res.threshold_level()
+    tp, ps, gs = res.dice_counts()
+    bs, bt, bn = res.calib_histograms()
+    for b in range(B):
+        _, label = oracle_image(x[:, b])
+        label = label.reshape(spatial)
+        assert np.array_equal(res.labels[b].cpu().numpy(), label)
+        gnp = gt[b].numpy()
+        assert res.area()[b] == oracle.compute_area(label)
+        otp, ops, ogs = oracle.binary_dice_counts(label, gnp, -12345 if ign is None else ign)
+        assert np.array_equal(tp[b], otp) and np.array_equal(ps[b], ops) and np.array_equal(gs[b], ogs)
+        np.testing.assert_allclose(vaurc.binary_dice_from_counts(tp[b], ps[b], gs[b]),
+                                   oracle.binary_dice_from_counts(otp, ops, ogs), rtol=1e-6)
+        for k, name in enumerate(("TU", "AU", "EU")):
+            m = res.maps[name][b].cpu().numpy()  # OUR map: counts must be exact given the map
+            np.testing.assert_allclose(img_mean[b, k], oracle.image_level_aggregation(m)["max_score"], rtol=RTOL, atol=1e-9)
+            o = oracle.threshold_aggregation(m, np.float32(thr[k]))
+            np.testing.assert_allclose(thr_score[b, k], float(o["max_score"]), rtol=RTOL)
+            assert int(res.stats_i64[b, _lib.I64["THR_COUNT"] + k]) == int((m >= np.float32(thr[k])).sum())
+            correct, conf = oracle.calibration_inputs(gnp, label, m, platt[k][0], platt[k][1], ign)
+            s, t, n = oracle.calib_histogram(correct, conf, binarize=False)
+            assert np.array_equal(bn[b, k], n), (name, "bin_total")
+            assert np.array_equal(bt[b, k], t.astype(np.int64)), (name, "bin_true")
+            np.testing.assert_allclose(bs[b, k], s, rtol=RTOL, atol=1e-9)
+            ace, ece = calibration.per_image_ace_ece(bs[b, k], bt[b, k], bn[b, k])
+            np.testing.assert_allclose(ace, oracle.calc_ace(correct, conf), rtol=RTOL, atol=1e-9)
+            np.testing.assert_allclose(ece, oracle.calc_ece(correct, conf), rtol=RTOL, atol=1e-9)
+            want_ncc = oracle.compute_ncc(oracle.rater_variance_map(gnp), m)
+            np.testing.assert_allclose(vncc.ncc_from_result(res, k)[b], want_ncc, rtol=1e-4, atol=1e-7)
+
+
+def test_statistics_accumulate_across_calls(vu):
+    from diffuncertainty_b200 import _lib
+    x = torch.softmax(torch.randn(4, 2, 2, 16, 16), 2).cuda()
+    once = vu.fused_pass(x, stats=_lib.STAT_IMAGE_SUM | _lib.STAT_AREA)
+    sf = torch.zeros_like(once.stats_f64)
+    si = torch.zeros_like(once.stats_i64)
+    for _ in range(3):
+        vu.fused_pass(x, stats=_lib.STAT_IMAGE_SUM | _lib.STAT_AREA, stats_out=(sf, si))
+    assert torch.equal(si, 3 * once.stats_i64)
+    torch.testing.assert_close(sf, 3 * once.stats_f64, rtol=1e-12, atol=0)
+
+
+# --------------------------------------------------------------------------
+# aggregation / calibration / NCC drop-ins against the golden vectors
+# --------------------------------------------------------------------------
+def test_golden_aggregations(vu, golden_agg):
+    from diffuncertainty_b200 import aggregation as agg
+    for name in ("img2d", "img3d", "plateau"):
+        img = golden_agg[f"{name}/image"]
+        np.testing.assert_allclose(agg.image_level_aggregation(img)["max_score"], golden_agg[f"{name}/image_level_mean"], rtol=RTOL)
+        np.testing.assert_allclose(agg.image_level_aggregation(img, mean=False)["max_score"], golden_agg[f"{name}/image_level_sum"], rtol=RTOL)
+        for ps in (10, 4):
+            r = agg.patch_level_aggregation(img, ps)
+            np.testing.assert_allclose(r["max_score"], golden_agg[f"{name}/patch{ps}_score"], rtol=RTOL)
+            assert np.array_equal(np.asarray(r["bounding_box"]), golden_agg[f"{name}/patch{ps}_bbox"]), (name, ps)
+            r = agg.patch_level_aggregation(torch.from_numpy(img).cuda(), ps, mean=True, image_id="x", unc_type="TU")
+            np.testing.assert_allclose(r["max_score"], golden_agg[f"{name}/patch{ps}_mean_score"], rtol=RTOL)
+        for t in ("mid", "above_max", "zero"):
+            thr = float(golden_agg[f"{name}/thr_{t}_t"])
+            np.testing.assert_allclose(float(agg.threshold_aggregation(img, threshold=thr)["max_score"]),
+                                       golden_agg[f"{name}/thr_{t}_score"], rtol=RTOL)
+            np.testing.assert_allclose(float(agg.threshold_aggregation(img, threshold=thr, mean=False)["max_score"]),
+                                       golden_agg[f"{name}/thr_{t}_sum"], rtol=RTOL)
+    for name in ("lab2d", "lab3d", "empty"):
+        lab = golden_agg[f"{name}/label"]
+        area, border = agg.prediction_shape_stats(lab)
+        assert area == golden_agg[f"{name}/area"] and border == golden_agg[f"{name}/border"], name
+        np.testing.assert_allclose(agg._normalize_uncertainty_sum(golden_agg["img2d/image"], area),
+                                   golden_agg[f"{name}/norm_area"], rtol=RTOL)
+    with pytest.raises(Exception):
+        agg.threshold_aggregation(golden_agg["img2d/image"])
+
+
+def test_golden_calibration(vu, golden_calib):
+    from diffuncertainty_b200 import _lib, calibration
+    from diffuncertainty_b200.uncertainty import GroundTruth
+    import ctypes as C
+    for name in case_names(golden_calib):
+        g = {k.split("/", 1)[1]: v for k, v in golden_calib.items() if k.startswith(name + "/")}
+        # (1) drop-in signature: per-pixel correct / confidence arrays
+        np.testing.assert_allclose(calibration.calc_ace(g["correct"], g["conf"]), g["ace"], rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(calibration.calc_ece(g["correct"], g["conf"]), g["ece"], rtol=RTOL, atol=1e-12)
+        acc = calibration.GlobalCalibAccumulator()
+        acc.accumulate(g["correct"], g["conf"])
+        assert np.array_equal(acc.bin_total, g["g_bin_total"]), name
+        assert np.array_equal(acc.bin_true, g["g_bin_true"]), name
+        np.testing.assert_allclose(acc.bin_sums, g["g_bin_sums"], rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(acc.compute_ace(), g["gace"], rtol=RTOL)
+        np.testing.assert_allclose(acc.compute_ece(), g["gece"], rtol=RTOL)
+        # (2) from the raw maps: refs, predicted labels, uncertainty map and Platt parameters
+        lib = _lib.load()
+        unc = torch.from_numpy(g["unc"]).cuda().contiguous()
+        pred = torch.from_numpy(g["pred"]).cuda().contiguous()
+        refs = torch.from_numpy(g["refs"]).cuda().contiguous()
+        sf = torch.zeros((1, _lib.F64["COLS"]), dtype=torch.float64, device="cuda")
+        si = torch.zeros((1, _lib.I64["COLS"]), dtype=torch.int64, device="cuda")
+        a = _lib.MapStatsArgs()
+        a.struct_size = C.sizeof(_lib.MapStatsArgs)
+        a.stat_flags = _lib.STAT_CALIB
+        a.B, a.V = 1, unc.numel()
+        a.maps[0] = unc.data_ptr()
+        a.labels = pred.data_ptr()
+        a.gt.data, a.gt.dtype, a.gt.R = refs.data_ptr(), _lib.GT_U8, refs.shape[0]
+        a.gt.stride_b, a.gt.stride_r, a.gt.stride_v = refs.numel(), unc.numel(), 1
+        ign = int(g["ignore"])
+        a.gt.has_ignore, a.gt.ignore_index = (0, 0) if ign == -999 else (1, ign)
+        pe = calibration.platt_edges(float(g["a"]), float(g["b"])).as_struct()
+        for k in range(3):
+            a.calib[k] = pe
+        a.stats_f64, a.stats_i64 = sf.data_ptr(), si.data_ptr()
+        _lib.check(lib.vu_map_stats(C.byref(a), _lib.current_stream_ptr()), "vu_map_stats")
+        i = si.cpu().numpy()[0]
+        f = sf.cpu().numpy()[0]
+        assert np.array_equal(i[_lib.I64["BIN_TOTAL"]:_lib.I64["BIN_TOTAL"] + 21], g["g_bin_total"]), name
+        assert np.array_equal(i[_lib.I64["BIN_TRUE"]:_lib.I64["BIN_TRUE"] + 21], g["g_bin_true"].astype(np.int64)), name
+        np.testing.assert_allclose(f[_lib.F64["BIN_SUMS"]:_lib.F64["BIN_SUMS"] + 21], g["g_bin_sums"], rtol=RTOL, atol=1e-12)
+    with pytest.raises(ValueError):
+        calibration.calc_ace(np.array([0, 1, 2]), np.array([0.1, 0.2, 0.3], np.float32))
+
+
+def test_golden_ncc(vu, golden_ncc_aurc):
+    from diffuncertainty_b200 import ncc as vncc
+    g = golden_ncc_aurc
+    np.testing.assert_allclose(vncc.compute_ncc(g["ncc/gt_map"], g["ncc/pred"]), g["ncc/value"], rtol=RTOL)
+    np.testing.assert_allclose(vncc.compute_ncc(g["ncc/pred"], g["ncc/pred"]), g["ncc/self"], rtol=RTOL)
+    assert vncc.compute_ncc(np.zeros_like(g["ncc/gt_map"]), g["ncc/pred"]) == 0.0
+    assert vncc.compute_ncc(g["ncc/gt_map"], np.full(g["ncc/pred"].shape, 0.25, np.float32)) == 0.0
+
+
+# --------------------------------------------------------------------------
+# full BASELINE sizes: size-independent properties
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("P,B,C,spatial", [
+    (10, 4, 2, (256, 256)), (5, 4, 2, (64, 64, 64)), (10, 1, 19, (1024, 2048)), (32, 8, 2, (128, 128)),
+    (16, 2, 19, (512, 1024)),
+])
+def test_full_size_properties(vu, P, B, C, spatial):
+    from diffuncertainty_b200 import _lib, synth
+    x = synth.synth_slab(P, B, C, spatial, seed=1, scale=3.0)
+    torch.testing.assert_close(x.sum(dim=2), torch.ones_like(x[:, :, 0]), rtol=0, atol=1e-5)
+    res = vu.fused_pass(x, stats=_lib.STAT_IMAGE_SUM | _lib.STAT_AREA)
+    tu, au, eu = (res.maps[k] for k in ("TU", "AU", "EU"))
+    assert float(tu.max()) <= np.log(C) * (1 + 1e-6) and float(au.min()) >= 0.0
+    assert float(eu.min()) >= -2e-6  # Jensen: EU >= 0 up to rounding
+    torch.testing.assert_close(au + eu, tu, rtol=3e-7, atol=1e-7)
+    # image-level sums are the sums of the maps; area is the count of non-zero labels
+    np.testing.assert_allclose(res.image_level(mean=False)[:, 0], tu.double().flatten(1).sum(1).cpu().numpy(), rtol=1e-9)
+    assert np.array_equal(res.area(), (res.labels > 0).flatten(1).sum(1).cpu().numpy())
+    # voxel-permutation equivariance: the result of a voxel does not depend on its position / tile
+    perm = torch.randperm(x[0, 0, 0].numel(), device="cuda")
+    xp = x.flatten(3)[..., perm].contiguous()
+    rp = vu.fused_pass(xp)
+    assert torch.equal(rp.maps["TU"], tu.flatten(1)[:, perm]) and torch.equal(rp.labels, res.labels.flatten(1)[:, perm])
+    # one image checked voxel by voxel against the oracle on a 64k-voxel window
+    flat = x.flatten(3)[:, 0, :, : 1 << 16].cpu()
+    ref, label = oracle_image(flat)
+    got = {k: res.maps[k].flatten(1)[0, : 1 << 16].cpu().numpy() for k in ("TU", "AU", "EU")}
+    assert_maps_close(got, ref, "full-size window")
+    assert np.array_equal(res.labels.flatten(1)[0, : 1 << 16].cpu().numpy(), label)
+
+
+def test_all_fast_variants_agree(vu):
+    """Every tuning variant of the fast kernel must give bit-identical maps."""
+    from diffuncertainty_b200 import _lib, synth
+    n = _lib.get_counter("k1_num_variants")
+    assert n > 0
+    try:
+        for C, P in ((2, 10), (2, 32), (19, 10), (19, 32), (3, 7), (4, 20)):
+            x = synth.synth_slab(P, 2, C, (64, 128), seed=3, scale=4.0)
+            _lib.set_option("k1_variant", -2)  # generic kernel as the baseline
+            base = vu.fused_pass(x)
+            levels = 1 if P <= 17 else 2
+            tested = 0
+            for i in range(n):
+                d = [_lib.get_counter(f"k1_variant.{i}.{f}") for f in range(7)]
+                if d[0] != C or d[2] < levels:
+                    continue
+                _lib.set_option("k1_variant", i)
+                r = vu.fused_pass(x)
+                for k in ("TU", "AU", "EU"):
+                    assert torch.equal(r.maps[k], base.maps[k]), (i, d, k)
+                assert torch.equal(r.labels, base.labels), (i, d)
+                tested += 1
+            assert tested >= 2
+    finally:
+        _lib.set_option("k1_variant", -1)
