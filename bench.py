@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Headline benchmark: sample-voxels/s of the fused uncertainty + aggregation +
+calibration pass on BASELINE.json's sharded-sweep shape (configs[4]: N=16 members,
+C=19 classes, 512x1024 images, dataset-level ECE/ACE histograms), per GPU and
+aggregated over the GPUs of one box, next to the reference's CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over one resident batch of synthetic images:
+one vu_fused_pass launch (maps, labels, per-image sums / threshold / area / Dice
+counts / calibration histograms) plus, on N > 1 GPUs, the all-reduce of the packed
+dataset-level partials.  Inputs (10 GB per GPU) are far larger than L2, so no
+flush is needed between steps.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sample_voxels_per_s"
+UNIT = "sample-voxels/s"
+WORKLOAD = dict(P=16, C=19, spatial=(512, 1024), R=1, ignore_index=255, scale=3.0, flip=0.2, ignore_frac=0.02,
+                thresholds=(0.3, 0.2, 0.02), platt=((3.5, -1.25), (6.0, -2.0), (40.0, -0.5)))
+PEAKS_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def workload_name(images_per_step: int) -> str:
+    return ("cfg5 sharded sweep: N=16 members, C=19, 512x1024, R=1 uint8 refs with 2% ignore(255); maps+labels+"
+            f"image/threshold/area/Dice/ECE-ACE histograms; {images_per_step} images per GPU per step")
+
+
+def algorithmic_bytes_per_voxel(P, C, R, gt_bytes=1):
+    """slab read + TU/AU/EU fp32 + uint8 label + references."""
+    return 4 * P * C + 12 + 1 + R * gt_bytes
+
+
+# ---------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path (oracle port)
+# ---------------------------------------------------------------------------
+def make_cpu_image(seed: int):
+    import numpy as np
+    import torch
+    w = WORKLOAD
+    g = torch.Generator().manual_seed(seed)
+    x = torch.softmax(w["scale"] * torch.randn(w["P"], w["C"], *w["spatial"], generator=g), dim=1)
+    lab0 = x[0].argmax(0).numpy()
+    rng = np.random.default_rng(seed)
+    gt = np.where(rng.random((w["R"],) + w["spatial"]) < w["flip"], rng.integers(0, w["C"], (w["R"],) + w["spatial"]), lab0[None])
+    gt = np.where(rng.random(gt.shape) < w["ignore_frac"], w["ignore_index"], gt).astype(np.uint8)
+    return x, gt
+
+
+def reference_step(x, gt, acc):
+    """One image through the reference's call sequence for this workload:
+    mean + argmax + calculate_uncertainty, image-level and threshold aggregation, area / border,
+    binary Dice counts, per-image ACE / ECE and the dataset accumulator."""
+    from oracle import oracle
+    w = WORKLOAD
+    res = oracle.reference_pipeline_image(x, gt, thresholds=w["thresholds"], platt=w["platt"], ignore_value=w["ignore_index"])
+    oracle.binary_dice_counts(res["label"], gt, w["ignore_index"])
+    for k, name in enumerate(("TU", "AU", "EU")):
+        s, t, n = res[f"{name}/hist"]
+        acc[k].bin_sums += s
+        acc[k].bin_true += t
+        acc[k].bin_total += n
+    return res
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import oracle
+    w = WORKLOAD
+    V = w["spatial"][0] * w["spatial"][1]
+    x, gt = make_cpu_image(0)
+    acc = [oracle.GlobalCalibAccumulator() for _ in range(3)]
+    for _ in range(args.warmup):
+        reference_step(x, gt, acc)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        reference_step(x, gt, acc)
+    dt = time.perf_counter() - t0
+    value = w["P"] * V * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = f"1 image of the workload per step ({args.steps} timed steps), oracle port of the reference's per-image CPU call sequence"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(1), "timing": "host wall clock, inputs resident in host memory"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline_leg(n_images: int):
+    import torch
+    from oracle import oracle
+    w = WORKLOAD
+    V = w["spatial"][0] * w["spatial"][1]
+    x, gt = make_cpu_image(0)
+    acc = [oracle.GlobalCalibAccumulator() for _ in range(3)]
+    reference_step(x, gt, acc)  # warm-up (allocator, thread pool)
+    t0 = time.perf_counter()
+    for _ in range(n_images):
+        reference_step(x, gt, acc)
+    dt = time.perf_counter() - t0
+    return {"value": w["P"] * V * n_images / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_images} images of the workload ({dt:.1f} s), oracle port of the reference's per-image CPU call sequence",
+            "host_cpus": os.cpu_count()}
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback. Use --impl reference for the CPU arm.")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import diffuncertainty_b200 as vu
+    from diffuncertainty_b200 import _lib, calibration, synth
+    from diffuncertainty_b200.host_pipeline import HostPipeline
+    from diffuncertainty_b200.sweep import exchange, pack_partials
+    from diffuncertainty_b200._lib import F64, I64
+
+    w = WORKLOAD
+    P, C, S, R = w["P"], w["C"], w["spatial"], w["R"]
+    V = S[0] * S[1]
+    B = args.images_per_step
+    flags = _lib.STAT_IMAGE_SUM | _lib.STAT_THRESHOLD | _lib.STAT_AREA | _lib.STAT_DICE | _lib.STAT_CALIB
+    calib = [calibration.platt_edges(a, b) for a, b in w["platt"]]
+
+    # resident inputs: every rank owns its own block of images (weak scaling)
+    x = synth.synth_slab(P, B, C, S, seed=1234, first_image=rank * B, scale=w["scale"])
+    gt_t = synth.synth_gt(x, R, seed=1234, first_image=rank * B, flip=w["flip"], ignore_frac=w["ignore_frac"],
+                          ignore_value=w["ignore_index"])
+    gt = vu.GroundTruth(gt_t, w["ignore_index"])
+    maps = {k: torch.empty((B,) + S, dtype=torch.float32, device=dev) for k in ("TU", "AU", "EU")}
+    labels = torch.empty((B,) + S, dtype=torch.uint8, device=dev)
+    rows_f = torch.zeros((B, F64["COLS"]), dtype=torch.float64, device=dev)
+    rows_i = torch.zeros((B, I64["COLS"]), dtype=torch.int64, device=dev)
+    k1_events = []
+
+    def step(timed: bool):
+        rows_f.zero_()
+        rows_i.zero_()
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        vu.fused_pass(x, gt, stats=flags, thresholds=w["thresholds"], calib=calib, stats_out=(rows_f, rows_i),
+                      maps_out=maps, labels_out=labels)
+        if timed:
+            e1.record()
+            k1_events.append((e0, e1))
+        if world > 1:
+            ibuf, fbuf = pack_partials(rows_f, rows_i, rank * B, world * B)
+            exchange(ibuf, fbuf)
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    fence()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = _lib.get_counter("launches")
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    start.record()
+    for _ in range(args.steps):
+        step(True)
+    end.record()
+    fence()
+    launches = _lib.get_counter("launches") - launches0
+    ms_total = start.elapsed_time(end)
+    k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / max(1, len(k1_events))
+    # keep the GPU busy a little longer so that the 100 ms clock sampler sees it under this load
+    if rank == 0:
+        t_end = time.time() + 1.0
+        while time.time() < t_end:
+            step(False)
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total, k1_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, k1_ms = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    value = P * V * B * world / (ms_per_step * 1e-3)
+
+    # ---- end to end: host buffers through the public host API, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        Be = args.e2e_images
+        pipe = HostPipeline(P, C, S, Be, R=R, gt_dtype=torch.uint8, chunk_images=1, n_buffers=3, stats=flags,
+                            thresholds=w["thresholds"], platt=w["platt"], ignore_index=w["ignore_index"], device=dev)
+        xh = torch.empty((P, Be, C) + S, dtype=torch.float32).pin_memory()
+        gh = torch.empty((Be, R) + S, dtype=torch.uint8).pin_memory()
+        xh.copy_(x[:, :Be])
+        gh.copy_(gt_t[:Be])
+        torch.cuda.synchronize()
+        r0 = pipe.run(xh, gh)  # warm-up
+        if rank == 0:  # the host path must reproduce the resident path bit for bit
+            assert torch.equal(r0.labels, labels[:Be].cpu()) and torch.equal(r0.maps["TU"], maps["TU"][:Be].cpu())
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            r0 = pipe.run(xh, gh)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        e2e = {"value": P * V * Be * world * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": r0.h2d_bytes,
+               "d2h_bytes_per_step": r0.d2h_bytes, "images_per_step": Be, "steps": args.e2e_steps,
+               "api": "diffuncertainty_b200.host_pipeline.HostPipeline.run (pinned host slab -> host maps, labels, statistics rows)"}
+        del pipe, xh, gh
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = PEAKS_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+    bpv = algorithmic_bytes_per_voxel(P, C, R)
+    achieved = bpv * V * B / (k1_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch_at_images", {}).get(str(B))
+            if traffic is None and tj.get("dram_bytes_per_voxel") is not None:
+                traffic = tj["dram_bytes_per_voxel"] * V * B
+        except Exception:
+            traffic = None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(B), "parallelism": f"images sharded over {world} GPU(s), one int64 + one float64 all-reduce of packed partials per step" if world > 1 else "1 GPU",
+                       "l2": "inputs (10.2 GB per GPU at 16 images) are larger than L2; no flush between steps",
+                       "bytes_per_voxel": bpv},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k1_fast (vu_fused_pass)", "kernel_ms": k1_ms, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bpv * V * B},
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg(args.cpu_images)
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images-per-step", type=int, default=16)
+    ap.add_argument("--e2e-images", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-images", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

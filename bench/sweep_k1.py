@@ -43,6 +43,8 @@ def main():
     ap.add_argument("--configs", default="1,2,3,4,5")
     ap.add_argument("--out", default=None)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--flags", type=lambda v: int(v, 0), default=None, help="explicit VU_STAT_* mask (implies --stats)")
+    ap.add_argument("--variants", default=None, help="comma-separated variant indices to time")
     args = ap.parse_args()
     n_var = _lib.get_counter("k1_num_variants")
     variants = [[_lib.get_counter(f"k1_variant.{i}.{f}") for f in range(7)] for i in range(n_var)]
@@ -55,11 +57,17 @@ def main():
         V = x[0, 0, 0].numel()
         gt = None
         flags = 0
+        if args.flags is not None:
+            args.stats = True
         if args.stats:
             flags = _lib.STAT_IMAGE_SUM | _lib.STAT_THRESHOLD | _lib.STAT_AREA
             if R:
                 gt = vu.GroundTruth(synth.synth_gt(x, R, seed=cid, flip=0.2, ignore_frac=0.02), 255)
                 flags |= _lib.STAT_DICE | _lib.STAT_CALIB | _lib.STAT_NCC
+            if args.flags is not None:
+                flags = args.flags
+                if not R and flags & (_lib.STAT_DICE | _lib.STAT_CALIB | _lib.STAT_NCC):
+                    gt = vu.GroundTruth(synth.synth_gt(x, 1, seed=cid, flip=0.2, ignore_frac=0.02), 255)
         bytes_per_voxel = 4 * P * C + 13 + (R if args.stats else 0)
         total_bytes = bytes_per_voxel * V * B
         levels = 1 if P <= 17 else 2
@@ -68,6 +76,8 @@ def main():
         # preallocate outputs once: time the kernel, not the allocator
         for i, d in enumerate(variants):
             if d[0] != C or d[2] != levels:
+                continue
+            if args.variants is not None and str(i) not in args.variants.split(","):
                 continue
             _lib.set_option("k1_variant", i)
 
@@ -84,7 +94,7 @@ def main():
             row = dict(cfg=cid, variant=i, desc=dict(zip(("C", "VEC", "LEVELS", "THREADS", "MINB", "G", "DB"), d)),
                        ms=ms, gbs=gbs, gsv_per_s=svps, stats=bool(args.stats))
             results.append(row)
-            print(f"cfg{cid} stats={int(args.stats)} var {i:2d} VEC={d[1]} T={d[3]} MINB={d[4]} G={d[5]} DB={d[6]}: "
+            print(f"cfg{cid} flags={flags:#04x} var {i:2d} VEC={d[1]} T={d[3]} MINB={d[4]} G={d[5]} DB={d[6]}: "
                   f"{ms:8.3f} ms  {gbs:7.1f} GB/s  {svps:7.1f} Gsv/s", flush=True)
         _lib.set_option("k1_variant", -1)
         del x, gt

@@ -50,12 +50,23 @@ int device_sm_count() {
     return cached[dev] > 0 ? cached[dev] : 148;
 }
 
-static int fill_stat_params(StatParams& st, uint32_t flags, int n_unc, long long V, const vu_gt& gt,
+// largest power of two <= 4 such that `align` consecutive references can be fetched with one vector load
+static int gt_alignment(const vu_gt& gt, long long V) {
+    if (gt.stride_v != 1) return 1;
+    const long long esz = gt.dtype == VU_GT_U8 ? 1 : 8;
+    for (int a = 4; a > 1; a >>= 1) {
+        const long long bytes = a * esz > 16 ? 16 : a * esz;
+        if ((uintptr_t)gt.data % bytes == 0 && gt.stride_b % a == 0 && gt.stride_r % a == 0 && V % a == 0) return a;
+    }
+    return 1;
+}
+
+static int fill_stat_params(StatParams& st, uint32_t flags, unsigned unc_mask, long long V, const vu_gt& gt,
                             const float* thr, const vu_calib* calib, const uint8_t* lut, const double* ncc_gt_map,
                             double* f64, int64_t* i64) {
     memset(&st, 0, sizeof(st));
     st.flags = flags;
-    st.n_unc = n_unc;
+    st.unc_mask = unc_mask;
     st.V = V;
     if (flags == 0) return VU_OK;
     if (!f64 || !i64) return set_error(VU_ERR_BAD_ARG, "stat_flags set but stats_f64 / stats_i64 is NULL");
@@ -71,6 +82,7 @@ static int fill_stat_params(StatParams& st, uint32_t flags, int n_unc, long long
         st.gt.data = gt.data; st.gt.dtype = gt.dtype; st.gt.R = gt.R;
         st.gt.sb = gt.stride_b; st.gt.sr = gt.stride_r; st.gt.sv = gt.stride_v;
         st.gt.has_ignore = gt.has_ignore; st.gt.ignore = gt.ignore_index;
+        st.gt.align = gt_alignment(gt, V);
     }
     for (int k = 0; k < VU_N_UNC; ++k) {
         st.thr[k] = thr[k];
@@ -80,10 +92,7 @@ static int fill_stat_params(StatParams& st, uint32_t flags, int n_unc, long long
         if ((flags & VU_STAT_CALIB) && (mode < 0 || mode > 2)) return set_error(VU_ERR_BAD_ARG, "vu_calib.mode");
         st.calib[k].increasing = mode != VU_CALIB_PLATT_DEC;
         st.calib[k].identity = mode == VU_CALIB_IDENTITY;
-        for (int e = 0; e < 32; ++e) {
-            float t = e < VU_N_EDGES ? calib[k].edge_u[e] : NAN;
-            st.calib[k].edge[e] = st.calib[k].increasing ? t : -t;
-        }
+        for (int e = 0; e < VU_N_EDGES; ++e) st.calib[k].edge[e] = st.calib[k].increasing ? calib[k].edge_u[e] : -calib[k].edge_u[e];
     }
     st.lut = lut;
     st.ncc_gt_map = ncc_gt_map;
@@ -129,13 +138,13 @@ int vu_fused_pass(const vu_fused_args* a, void* stream) {
     if (!a) return set_error(VU_ERR_BAD_ARG, "args is NULL");
     if (a->struct_size != sizeof(vu_fused_args)) return set_error(VU_ERR_BAD_ARG, "vu_fused_args.struct_size mismatch");
     const vu_slab& s = a->slab;
-    if (!s.data) return set_error(VU_ERR_BAD_ARG, "slab.data is NULL");
     if (s.P < 1 || s.B < 0 || s.C < 1 || s.V < 0) return set_error(VU_ERR_BAD_ARG, "slab sizes must be positive");
     if (s.C > 256) return set_error(VU_ERR_UNSUPPORTED, "C > 256 (labels are uint8)");
-    if (s.B == 0 || s.V == 0) return VU_OK;  // empty batch: nothing to do
+    if (s.B == 0 || s.V == 0) return VU_OK;  // empty batch: nothing to do (its data pointer may be NULL)
+    if (!s.data) return set_error(VU_ERR_BAD_ARG, "slab.data is NULL");
     StatParams st;
-    const int n_unc = s.P > 1 ? VU_N_UNC : 1;
-    int rc = fill_stat_params(st, a->stat_flags, n_unc, s.V, a->gt, a->threshold, a->calib, a->calib_label_lut, nullptr,
+    const unsigned unc_mask = s.P > 1 ? 7u : 1u;
+    int rc = fill_stat_params(st, a->stat_flags, unc_mask, s.V, a->gt, a->threshold, a->calib, a->calib_label_lut, nullptr,
                               a->stats_f64, a->stats_i64);
     if (rc != VU_OK) return rc;
     return launch_k1(a, st, (cudaStream_t)stream);
@@ -149,7 +158,9 @@ int vu_map_stats(const vu_map_stats_args* a, void* stream) {
     if ((a->stat_flags & (VU_STAT_AREA | VU_STAT_DICE | VU_STAT_CALIB)) && !a->labels)
         return set_error(VU_ERR_BAD_ARG, "AREA / DICE / CALIB need labels");
     StatParams st;
-    int rc = fill_stat_params(st, a->stat_flags, VU_N_UNC, a->V, a->gt, a->threshold, a->calib, a->calib_label_lut,
+    unsigned unc_mask = 0;
+    for (int k = 0; k < VU_N_UNC; ++k) unc_mask |= a->maps[k] ? (1u << k) : 0u;
+    int rc = fill_stat_params(st, a->stat_flags, unc_mask, a->V, a->gt, a->threshold, a->calib, a->calib_label_lut,
                               a->ncc_gt_map, a->stats_f64, a->stats_i64);
     if (rc != VU_OK) return rc;
     return launch_map_stats(a, st, (cudaStream_t)stream);

@@ -14,6 +14,8 @@
 
 namespace vu {
 
+extern __shared__ __align__(16) unsigned char vu_dyn_smem[];
+
 struct K1Params {
     const float* x;
     long long P, B, C, V;
@@ -36,26 +38,23 @@ struct K1Params {
 // ---------------------------------------------------------------------------
 template <int C, int VEC, int LEVELS, int THREADS, int MINB, int G, bool DB, bool STATS>
 __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__ K1Params prm) {
-    constexpr int WARPS = THREADS / 32;
-    __shared__ CtaStats<STATS ? WARPS : 1> cs_store;
-    CtaStats<WARPS>& cs = reinterpret_cast<CtaStats<WARPS>&>(cs_store);
     constexpr bool do_stats = STATS;
-    if (do_stats) cs.init(prm.st);
+    constexpr long long kTileVox = (long long)THREADS * VEC;
+    StatsCursor<THREADS> cursor;
+    if (do_stats) stats_init<THREADS>(prm.st, vu_dyn_smem);
 
     const long long P = prm.P, V = prm.V;
     const float Pf = (float)P;
-    const long long t0 = prm.total_tiles * (long long)blockIdx.x / gridDim.x;
-    const long long t1 = prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x;
-    long long cur_b = -1;
+    // consecutive tiles per CTA (total_tiles < 2^31 is checked on the host): (b, vt) advance incrementally
+    const int t0 = (int)(prm.total_tiles * (long long)blockIdx.x / gridDim.x);
+    const int t1 = (int)(prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x);
+    const int tpi = (int)prm.tiles_per_img;
+    int b = t0 / tpi, vt = t0 - b * tpi - 1;
 
-    for (long long tile = t0; tile < t1; ++tile) {
-        const long long b = tile / prm.tiles_per_img;
-        const long long vt = tile - b * prm.tiles_per_img;
-        const long long v = vt * (long long)(THREADS * VEC) + (long long)threadIdx.x * VEC;
-        if (do_stats && b != cur_b) {
-            if (cur_b >= 0) cs.flush(prm.st, cur_b);
-            cur_b = b;
-        }
+    for (int tile = t0; tile < t1; ++tile) {
+        if (++vt == tpi) { vt = 0; ++b; }
+        const long long v = (long long)vt * kTileVox + (long long)threadIdx.x * VEC;
+        if (do_stats) cursor.enter(prm.st, vu_dyn_smem, b, vt, kTileVox);
         const bool active = v < V;
         float u[VU_N_UNC][VEC];
         int label[VEC];
@@ -73,7 +72,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < (LEVELS > 1 ? C : 1); ++c) m1[c][k] = 0.f;
             }
-            const float* row0 = prm.x + b * prm.sb + v;
+            const float* row0 = prm.x + (long long)b * prm.sb + v;
 
             auto load_stage = [&](float (&x)[G][C][VEC], long long p0) {
 #pragma unroll
@@ -149,16 +148,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__
                 u[0][k] = tu; u[1][k] = au; u[2][k] = tu - au;
                 label[k] = idx;
             }
-            const long long o = b * V + v;
+            const long long o = (long long)b * V + v;
             if (prm.tu) VecLoad<VEC>::store(prm.tu + o, u[0]);
             if (prm.au) VecLoad<VEC>::store(prm.au + o, u[1]);
             if (prm.eu) VecLoad<VEC>::store(prm.eu + o, u[2]);
             if (prm.lab) VecLoad<VEC>::store_u8(prm.lab + o, label);
         }
 
-        if (do_stats) stats_tile<VEC, WARPS>(prm.st, cs, active, b, v, u, label);
+        if (do_stats) stats_tile<VEC, THREADS>(prm.st, vu_dyn_smem, active, b, v, u, label);
     }
-    if (do_stats && cur_b >= 0) cs.flush(prm.st, cur_b);
+    if (do_stats && t1 > t0) cursor.finish(prm.st, vu_dyn_smem, vt, kTileVox);
 }
 
 // ---------------------------------------------------------------------------
@@ -191,34 +190,31 @@ struct Cascade {
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1Params prm, int level_k) {
-    constexpr int WARPS = THREADS / 32;
-    __shared__ CtaStats<WARPS> cs;
-    extern __shared__ float h_smem[];  // [P][THREADS]
+    float* h_smem = reinterpret_cast<float*>(vu_dyn_smem);  // [P][THREADS] (P > 1), then the statistics state
+    void* st_smem = vu_dyn_smem + (prm.P > 1 ? (size_t)prm.P * THREADS * sizeof(float) : 0);
     const bool do_stats = prm.st.flags != 0;
-    if (do_stats) cs.init(prm.st);
+    StatsCursor<THREADS> cursor;
+    if (do_stats) stats_init<THREADS>(prm.st, st_smem);
 
     const long long P = prm.P, V = prm.V;
     const int C = (int)prm.C;
     const float Pf = (float)P;
     const long long n_full = (P >> level_k) << level_k;
-    const long long t0 = prm.total_tiles * (long long)blockIdx.x / gridDim.x;
-    const long long t1 = prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x;
-    long long cur_b = -1;
+    const int t0 = (int)(prm.total_tiles * (long long)blockIdx.x / gridDim.x);
+    const int t1 = (int)(prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x);
+    const int tpi = (int)prm.tiles_per_img;
+    int b = t0 / tpi, vt = t0 - b * tpi - 1;
     float* h = h_smem + threadIdx.x;
 
-    for (long long tile = t0; tile < t1; ++tile) {
-        const long long b = tile / prm.tiles_per_img;
-        const long long vt = tile - b * prm.tiles_per_img;
-        const long long v = vt * (long long)THREADS + threadIdx.x;
-        if (do_stats && b != cur_b) {
-            if (cur_b >= 0) cs.flush(prm.st, cur_b);
-            cur_b = b;
-        }
+    for (int tile = t0; tile < t1; ++tile) {
+        if (++vt == tpi) { vt = 0; ++b; }
+        const long long v = (long long)vt * THREADS + threadIdx.x;
+        if (do_stats) cursor.enter(prm.st, st_smem, b, vt, THREADS);
         const bool active = v < V;
         float u[VU_N_UNC] = {0.f, 0.f, 0.f};
         int label = 0;
         if (active) {
-            const float* base = prm.x + b * prm.sb + v * prm.sv;
+            const float* base = prm.x + (long long)b * prm.sb + v * prm.sv;
             if (P > 1)
                 for (long long p = 0; p < P; ++p) h[p * THREADS] = 0.f;
             float best = 0.f, tu2 = 0.f;
@@ -235,7 +231,7 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
                 if (c == 0) { best = mean; label = 0; } else argmax_step(mean, c, best, label);
                 tu2 += plog2p(mean);
             }
-            const long long o = b * V + v;
+            const long long o = (long long)b * V + v;
             if (P > 1) {
                 Cascade cas;
                 cas.reset();
@@ -255,10 +251,10 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
         if (do_stats) {
             const float u1[VU_N_UNC][1] = {{u[0]}, {u[1]}, {u[2]}};
             const int l1[1] = {label};
-            stats_tile<1, WARPS>(prm.st, cs, active, b, v, u1, l1);
+            stats_tile<1, THREADS>(prm.st, st_smem, active, b, v, u1, l1);
         }
     }
-    if (do_stats && cur_b >= 0) cs.flush(prm.st, cur_b);
+    if (do_stats && t1 > t0) cursor.finish(prm.st, st_smem, vt, THREADS);
 }
 
 // ---------------------------------------------------------------------------
@@ -267,12 +263,13 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
 typedef void (*K1Kernel)(const K1Params);
 struct FastVariant {
     int C, VEC, LEVELS, THREADS, MINB, G, DB;
+    int use;            // automatic selection: 0 = maps-only launches, 1 = launches with statistics, 2 = both, -1 = never
     K1Kernel fn;        // maps + labels only
     K1Kernel fn_stats;  // with the per-image statistics phase
 };
 
-#define VU_VARIANT(C, VEC, LEVELS, THREADS, MINB, G, DB)                                   \
-    { C, VEC, LEVELS, THREADS, MINB, G, DB,                                                \
+#define VU_VARIANT(C, VEC, LEVELS, THREADS, MINB, G, DB, USE)                              \
+    { C, VEC, LEVELS, THREADS, MINB, G, DB, USE,                                           \
       (K1Kernel)k1_fast<C, VEC, LEVELS, THREADS, MINB, G, DB, false>,                      \
       (K1Kernel)k1_fast<C, VEC, LEVELS, THREADS, MINB, G, DB, true> }
 
@@ -280,35 +277,33 @@ struct FastVariant {
 // option selects another by index (used by the tuning sweep, bench/sweep_k1.py).
 static const FastVariant kFast[] = {
     // ---- C = 2 (LIDC-like, toy): few loads per member -> group members
-    VU_VARIANT(2, 4, 1, 256, 2, 4, true),    // 0
-    VU_VARIANT(2, 4, 2, 256, 2, 4, true),    // 1
-    VU_VARIANT(2, 4, 1, 256, 2, 8, false),   // 2
-    VU_VARIANT(2, 4, 2, 256, 2, 8, false),   // 3
-    VU_VARIANT(2, 4, 1, 128, 4, 4, true),    // 4
-    VU_VARIANT(2, 4, 2, 128, 4, 4, true),    // 5
-    VU_VARIANT(2, 2, 1, 256, 2, 8, true),    // 6
-    VU_VARIANT(2, 2, 2, 256, 2, 8, true),    // 7
-    VU_VARIANT(2, 1, 1, 256, 2, 8, true),    // 8  (unaligned V)
-    VU_VARIANT(2, 1, 2, 256, 2, 8, true),    // 9
+    VU_VARIANT(2, 4, 1, 256, 2, 8, false, 0),   // 0
+    VU_VARIANT(2, 4, 2, 256, 2, 8, false, 0),   // 1
+    VU_VARIANT(2, 4, 1, 256, 2, 4, false, 1),   // 2
+    VU_VARIANT(2, 4, 2, 256, 2, 4, false, 1),   // 3
+    VU_VARIANT(2, 4, 1, 256, 2, 4, true, -1),   // 4
+    VU_VARIANT(2, 4, 2, 256, 2, 4, true, -1),   // 5
+    VU_VARIANT(2, 2, 1, 256, 2, 8, false, 2),   // 6
+    VU_VARIANT(2, 2, 2, 256, 2, 8, false, 2),   // 7
+    VU_VARIANT(2, 1, 1, 256, 2, 8, false, 2),   // 8  (unaligned V)
+    VU_VARIANT(2, 1, 2, 256, 2, 8, false, 2),   // 9
     // ---- C = 19 (Cityscapes / GTA): 19 independent loads per member
-    VU_VARIANT(19, 2, 1, 256, 2, 1, false),  // 10
-    VU_VARIANT(19, 2, 2, 256, 1, 1, false),  // 11
-    VU_VARIANT(19, 4, 1, 256, 1, 1, false),  // 12
-    VU_VARIANT(19, 4, 1, 128, 2, 1, false),  // 13
-    VU_VARIANT(19, 2, 1, 256, 1, 1, true),   // 14
-    VU_VARIANT(19, 2, 1, 128, 4, 1, false),  // 15
-    VU_VARIANT(19, 1, 1, 256, 3, 1, false),  // 16
-    VU_VARIANT(19, 1, 2, 256, 2, 1, false),  // 17
-    VU_VARIANT(19, 1, 1, 256, 2, 1, true),   // 18
+    VU_VARIANT(19, 1, 1, 256, 3, 1, false, 2),  // 10
+    VU_VARIANT(19, 1, 2, 256, 2, 1, false, 2),  // 11
+    VU_VARIANT(19, 2, 1, 256, 2, 1, false, -1), // 12
+    VU_VARIANT(19, 2, 2, 256, 1, 1, false, -1), // 13
+    VU_VARIANT(19, 1, 1, 256, 4, 1, false, -1), // 14
+    VU_VARIANT(19, 1, 1, 128, 6, 1, false, -1), // 15
+    VU_VARIANT(19, 1, 2, 256, 3, 1, false, -1), // 16
     // ---- small C
-    VU_VARIANT(3, 4, 1, 256, 2, 2, true),    // 19
-    VU_VARIANT(3, 4, 2, 256, 2, 2, true),    // 20
-    VU_VARIANT(3, 1, 1, 256, 2, 4, true),    // 21
-    VU_VARIANT(3, 1, 2, 256, 2, 4, true),    // 22
-    VU_VARIANT(4, 4, 1, 256, 2, 2, true),    // 23
-    VU_VARIANT(4, 4, 2, 256, 2, 2, true),    // 24
-    VU_VARIANT(4, 1, 1, 256, 2, 4, true),    // 25
-    VU_VARIANT(4, 1, 2, 256, 2, 4, true),    // 26
+    VU_VARIANT(3, 4, 1, 256, 2, 2, true, 2),    // 17
+    VU_VARIANT(3, 4, 2, 256, 2, 2, true, 2),    // 18
+    VU_VARIANT(3, 1, 1, 256, 2, 4, true, 2),    // 19
+    VU_VARIANT(3, 1, 2, 256, 2, 4, true, 2),    // 20
+    VU_VARIANT(4, 4, 1, 256, 2, 2, true, 2),    // 21
+    VU_VARIANT(4, 4, 2, 256, 2, 2, true, 2),    // 22
+    VU_VARIANT(4, 1, 1, 256, 2, 4, true, 2),    // 23
+    VU_VARIANT(4, 1, 2, 256, 2, 4, true, 2),    // 24
 };
 static const int kNumFast = (int)(sizeof(kFast) / sizeof(kFast[0]));
 
@@ -352,7 +347,8 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
         } else {
             for (int i = 0; i < kNumFast && !pick; ++i) {
                 const FastVariant& f = kFast[i];
-                if (f.C == s.C && f.LEVELS == need_levels && aligned_for(a, f.VEC)) pick = &f;
+                const bool use_ok = f.use == 2 || f.use == (st.flags ? 1 : 0);
+                if (use_ok && f.C == s.C && f.LEVELS == need_levels && aligned_for(a, f.VEC)) pick = &f;
             }
         }
     }
@@ -361,13 +357,17 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
         const long long tile_vox = (long long)pick->THREADS * pick->VEC;
         prm.tiles_per_img = (s.V + tile_vox - 1) / tile_vox;
         prm.total_tiles = prm.tiles_per_img * s.B;
+        if (prm.total_tiles >= (1LL << 31)) return set_error(VU_ERR_UNSUPPORTED, "more than 2^31 tiles in one launch; split the batch");
         K1Kernel fn = st.flags ? pick->fn_stats : pick->fn;
+        const size_t dyn = stats_smem_bytes(st.flags, st.gt.R, pick->THREADS);
+        if (dyn > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(k1_fast)");
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pick->THREADS, 0) != cudaSuccess || occ < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pick->THREADS, dyn) != cudaSuccess || occ < 1)
             return set_cuda_error("occupancy query (k1_fast)");
         long long grid = (long long)sms * occ;
         if (grid > prm.total_tiles) grid = prm.total_tiles;
-        fn<<<(unsigned)grid, pick->THREADS, 0, stream>>>(prm);
+        fn<<<(unsigned)grid, pick->THREADS, dyn, stream>>>(prm);
         count_launch("k1_fast");
         return check_launch("k1_fast");
     }
@@ -375,7 +375,7 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     // generic path
     constexpr int T = 64;
     const size_t max_dyn = 160 * 1024;
-    size_t dyn = (size_t)(s.P > 1 ? s.P : 0) * T * sizeof(float);
+    size_t dyn = (size_t)(s.P > 1 ? s.P : 0) * T * sizeof(float) + stats_smem_bytes(st.flags, st.gt.R, T);
     if (dyn > max_dyn) return set_error(VU_ERR_UNSUPPORTED, "P too large for the generic kernel (P*256 B of shared memory)");
     if (s.P > (1LL << 19)) return set_error(VU_ERR_UNSUPPORTED, "P > 2^19");
     static bool attr_set = false;
@@ -386,6 +386,7 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     }
     prm.tiles_per_img = (s.V + T - 1) / T;
     prm.total_tiles = prm.tiles_per_img * s.B;
+    if (prm.total_tiles >= (1LL << 31)) return set_error(VU_ERR_UNSUPPORTED, "more than 2^31 tiles in one launch; split the batch");
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_generic<T>, T, dyn) != cudaSuccess || occ < 1)
         return set_cuda_error("occupancy query (k1_generic)");

@@ -5,6 +5,8 @@
 
 namespace vu {
 
+extern __shared__ __align__(16) unsigned char vu_dyn_smem[];
+
 struct K3Params {
     const float* maps[VU_N_UNC];
     const uint8_t* labels;
@@ -12,56 +14,72 @@ struct K3Params {
     StatParams st;
 };
 
-constexpr int kK3Threads = 256, kK3PerThread = 4;
+constexpr int kK3Threads = 256;
 
+// VEC = 4: V % 4 == 0 and every pointer 16-byte (labels 4-byte) aligned; VEC = 1 otherwise.
+template <int VEC>
 __global__ void __launch_bounds__(kK3Threads) k3_map_stats(const __grid_constant__ K3Params prm) {
-    constexpr int WARPS = kK3Threads / 32;
-    __shared__ CtaStats<WARPS> cs;
-    cs.init(prm.st);
-    const long long t0 = prm.total_tiles * (long long)blockIdx.x / gridDim.x;
-    const long long t1 = prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x;
-    long long cur_b = -1;
-    for (long long tile = t0; tile < t1; ++tile) {
-        const long long b = tile / prm.tiles_per_img;
-        const long long vt = tile - b * prm.tiles_per_img;
-        if (b != cur_b) {
-            if (cur_b >= 0) cs.flush(prm.st, cur_b);
-            cur_b = b;
-        }
-        TileAcc acc;
-        acc.clear();
-#pragma unroll 1
-        for (int j = 0; j < kK3PerThread; ++j) {
-            const long long v = (vt * kK3PerThread + j) * kK3Threads + threadIdx.x;
-            const bool active = v < prm.V;
-            float u[VU_N_UNC] = {0.f, 0.f, 0.f};
-            int label = 0;
-            if (active) {
-                const long long o = b * prm.V + v;
+    constexpr long long kTileVox = (long long)kK3Threads * VEC;
+    StatsCursor<kK3Threads> cursor;
+    stats_init<kK3Threads>(prm.st, vu_dyn_smem);
+    const int t0 = (int)(prm.total_tiles * (long long)blockIdx.x / gridDim.x);
+    const int t1 = (int)(prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x);
+    const int tpi = (int)prm.tiles_per_img;
+    int b = t0 / tpi, vt = t0 - b * tpi - 1;
+    for (int tile = t0; tile < t1; ++tile) {
+        if (++vt == tpi) { vt = 0; ++b; }
+        cursor.enter(prm.st, vu_dyn_smem, b, vt, kTileVox);
+        const long long v = (long long)vt * kTileVox + (long long)threadIdx.x * VEC;
+        const bool active = v < prm.V;
+        float u[VU_N_UNC][VEC];
+        int label[VEC];
 #pragma unroll
-                for (int k = 0; k < VU_N_UNC; ++k)
-                    if (prm.maps[k]) u[k] = __ldg(prm.maps[k] + o);
-                if (prm.labels) label = __ldg(prm.labels + o);
+        for (int j = 0; j < VEC; ++j) { u[0][j] = u[1][j] = u[2][j] = 0.f; label[j] = 0; }
+        if (active) {
+            const long long o = (long long)b * prm.V + v;
+#pragma unroll
+            for (int k = 0; k < VU_N_UNC; ++k)
+                if (prm.maps[k]) VecLoad<VEC>::load(prm.maps[k] + o, u[k]);
+            if (prm.labels) {
+                if (VEC == 4) {
+                    const unsigned w = __ldg(reinterpret_cast<const unsigned*>(prm.labels + o));
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) label[j] = (int)((w >> (8 * j)) & 0xffu);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) label[j] = (int)__ldg(prm.labels + o + j);
+                }
             }
-            stats_voxel<WARPS>(prm.st, cs, acc, active, b, v, u, label);
         }
-        stats_tile_end<WARPS>(prm.st, cs, acc);
+        stats_tile<VEC, kK3Threads>(prm.st, vu_dyn_smem, active, b, v, u, label);
     }
-    if (cur_b >= 0) cs.flush(prm.st, cur_b);
+    if (t1 > t0) cursor.finish(prm.st, vu_dyn_smem, vt, kTileVox);
 }
 
 int launch_map_stats(const vu_map_stats_args* a, const StatParams& st, cudaStream_t stream) {
     K3Params prm;
-    for (int k = 0; k < VU_N_UNC; ++k) prm.maps[k] = a->maps[k];
+    bool vec4 = (a->V % 4) == 0 && ((uintptr_t)a->labels % 4) == 0;
+    for (int k = 0; k < VU_N_UNC; ++k) {
+        prm.maps[k] = a->maps[k];
+        vec4 = vec4 && ((uintptr_t)a->maps[k] % 16) == 0;
+    }
     prm.labels = a->labels;
     prm.B = a->B; prm.V = a->V;
-    const long long tile_vox = (long long)kK3Threads * kK3PerThread;
+    const long long tile_vox = (long long)kK3Threads * (vec4 ? 4 : 1);
     prm.tiles_per_img = (a->V + tile_vox - 1) / tile_vox;
     prm.total_tiles = prm.tiles_per_img * a->B;
+    if (prm.total_tiles >= (1LL << 31)) return set_error(VU_ERR_UNSUPPORTED, "more than 2^31 tiles in one launch; split the batch");
     prm.st = st;
-    long long grid = (long long)device_sm_count() * 4;
+    void (*fn)(const K3Params) = vec4 ? k3_map_stats<4> : k3_map_stats<1>;
+    const size_t dyn = stats_smem_bytes(st.flags, st.gt.R, kK3Threads);
+    if (dyn > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+        return set_cuda_error("cudaFuncSetAttribute(k3_map_stats)");
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kK3Threads, dyn) != cudaSuccess || occ < 1)
+        return set_cuda_error("occupancy query (k3_map_stats)");
+    long long grid = (long long)device_sm_count() * occ;
     if (grid > prm.total_tiles) grid = prm.total_tiles;
-    k3_map_stats<<<(unsigned)grid, kK3Threads, 0, stream>>>(prm);
+    fn<<<(unsigned)grid, kK3Threads, dyn, stream>>>(prm);
     count_launch("k3_map_stats");
     return check_launch("k3_map_stats");
 }

@@ -4,6 +4,8 @@
 #include <float.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "valunc.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -76,20 +78,23 @@ struct VecLoad<1> {
 // ---- p * log2(p) with the reference's skip rule ---------------------------
 // test_utils.py:838-840 / 849-851 drop every NaN product, i.e. the term is
 // p*log(p) for p > 0 and 0 for p == 0, p < 0 and NaN.  One MUFU.LG2 per
-// element; its absolute error (2^-22 on [0.5, 2]) is too large next to p = 1
-// (confident pixels: the term is ~ -(1-p)), so within |p-1| < 1/64 the log is
-// taken from a 4-term log1p series instead (relative error < 2e-8).
+// element; its absolute error (~2^-23.5 on [0.5, 2], measured on B200) is too
+// large next to p = 1 (confident pixels: the term is ~ -(1-p)), so within
+// |p-1| < 1/16 log2(p) = f * q(f), f = p - 1, with q the degree-4 near-minimax
+// fit of log2(1+f)/f on [-1/16, 1/16] (relative error of p*log2(p) < 1.8e-7
+// over every float in the window; outside it MUFU.LG2 stays below 1e-6).
 // Subnormal p (< FLT_MIN) is treated as 0: its true term is < 1.1e-36.
 // Result is in log2 units; callers multiply the class sum by ln 2 once.
 __device__ __forceinline__ float plog2p(float p) {
     float lg;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(p));
     const float f = p - 1.0f;
-    float t = fmaf(f, -0.25f * kLog2e, kLog2e / 3.0f);
-    t = fmaf(t, f, -0.5f * kLog2e);
-    t = fmaf(t, f, kLog2e);
+    float t = fmaf(f, 0.28995341062545776f, -0.36185145378112793f);
+    t = fmaf(t, f, 0.4808957874774933f);
+    t = fmaf(t, f, -0.721346378326416f);
+    t = fmaf(t, f, 1.4426950216293335f);
     const float near_one = t * f;
-    const float l = (fabsf(f) < (1.0f / 64.0f)) ? near_one : lg;
+    const float l = (fabsf(f) < (1.0f / 16.0f)) ? near_one : lg;
     const float term = __fmul_rn(p, l);  // never contracted into the caller's add: all kernels agree bitwise
     return (p >= FLT_MIN) ? term : 0.0f;
 }
@@ -117,23 +122,55 @@ struct GtView {
     long long sb, sr, sv;
     int has_ignore;
     long long ignore;
-    __device__ __forceinline__ long long at(long long b, int r, long long v) const {
-        const long long off = b * sb + (long long)r * sr + v * sv;
-        return dtype == VU_GT_U8 ? (long long)__ldg(reinterpret_cast<const uint8_t*>(data) + off)
-                                 : __ldg(reinterpret_cast<const long long*>(data) + off);
-    }
+    int align;  // largest power of two <= 4 such that VEC = align voxels can be fetched with one vector load
 };
+
+template <typename T>
+__device__ __forceinline__ T ldg_gt(const T* p) { return __ldg(p); }
+
+// references of `VEC` consecutive voxels of rater r (values widened to int for uint8, kept 64-bit for int64)
+template <int VEC>
+__device__ __forceinline__ void load_gt(const GtView& gt, long long b, int r, long long v, int (&g)[VEC], uint8_t) {
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(gt.data) + b * gt.sb + (long long)r * gt.sr;
+    if (VEC == 4 && gt.align >= 4) {
+        const unsigned w = __ldg(reinterpret_cast<const unsigned*>(base + v));
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) g[k] = (int)((w >> (8 * k)) & 0xffu);
+    } else if (VEC == 2 && gt.align >= 2) {
+        const unsigned short w = __ldg(reinterpret_cast<const unsigned short*>(base + v));
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) g[k] = (int)((w >> (8 * k)) & 0xffu);
+    } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) g[k] = (int)__ldg(base + (v + k) * gt.sv);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void load_gt(const GtView& gt, long long b, int r, long long v, long long (&g)[VEC], long long) {
+    const long long* base = reinterpret_cast<const long long*>(gt.data) + b * gt.sb + (long long)r * gt.sr;
+    if (VEC >= 2 && gt.align >= 2) {
+#pragma unroll
+        for (int k = 0; k < VEC; k += 2) {
+            const longlong2 w = __ldg(reinterpret_cast<const longlong2*>(base + v + k));
+            g[k] = w.x;
+            if (k + 1 < VEC) g[k + 1] = w.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) g[k] = __ldg(base + (v + k) * gt.sv);
+    }
+}
 
 struct CalibDev {
     float a, b;
-    float edge[32];  // [0..18] real edges (sign-flipped when decreasing), rest NaN
+    float edge[VU_N_EDGES];  // thresholds on u (sign-flipped when conf falls with u); NaN = never reached
     int increasing;
     int identity;  // the map already is the confidence
 };
 
 struct StatParams {
     unsigned flags;
-    int n_unc;  // 3 (TU/AU/EU) or 1 (pred_entropy when P == 1)
+    unsigned unc_mask;  // bit k set: uncertainty type k is present (TU/AU/EU; bit 0 only when P == 1)
     long long V;
     GtView gt;
     float thr[VU_N_UNC];
@@ -144,246 +181,378 @@ struct StatParams {
     long long* i64;
 };
 
-// ---- per-CTA statistics state ------------------------------------------------
-// One slot per warp: lane 0 of the warp is the only writer between barriers,
-// so no shared-memory atomics are needed.  flush() folds the slots and issues
-// one global atomic per non-zero column.
-struct WarpSlot {
-    double f[VU_F64_COLS];
-    long long i[VU_I64_COLS];
-};
+// ---- per-CTA statistics state (dynamic shared memory) ---------------------------
+// Every thread owns one private column of float64 / packed-integer accumulators
+// ("slots", layout [slot][thread]: conflict-free, no atomics, no shuffles while
+// streaming).  The calibration histograms are one CTA-wide copy with 32 replicas,
+// one per lane ([unc][bin][lane]: a warp's 32 adds never share an address or a
+// bank, whatever the bins are), updated with native 32-bit shared-memory atomic
+// adds (warps share the replicas).  flush() folds
+// everything into the image's row of the global statistics buffers with one
+// atomic per non-zero column; it runs when a CTA moves on to another image.
+//
+// float64 slots                       packed-integer slots (uint64)
+//   0..2   sum of u_k                   0      #(u_k >= t_k), 3 x 21 bit
+//   3..5   sum of u_k over u_k >= t_k   1      #(label > 0)
+//   6..8   sum of conf in bin 0         2+r    rater r: tp | pred << 21 | gt << 42
+//   9      sum g        10  sum g*g
+//   11..13 sum u_k^2    14..16  sum g*u_k
+enum { FS_SUM = 0, FS_THR = 3, FS_BIN0 = 6, FS_G = 9, FS_GG = 10, FS_UU = 11, FS_GU = 14, FS_MAX = 17 };
+enum { IS_THRCNT = 0, IS_AREA = 1, IS_DICE = 2, IS_MAX = 2 + VU_MAX_RATERS };
+constexpr int kPackBits = 21;
+constexpr unsigned long long kPackMask = (1ull << kPackBits) - 1;
+constexpr long long kMaxTilesPerFlush = 1LL << 13;  // bounds every packed / 32-bit counter between two flushes
+constexpr int kQBits = 24;                           // fixed point of (conf - bin * 0.05): |q| < 2^20, x n_valid <= 8
+constexpr int kQSplit = 12;                          // q is accumulated as (q >> 12, q & 0xfff) in two 32-bit words
+constexpr int kEdgePad = 24;                         // E[0] = NaN, E[1..19] = edges, E[20..23] = NaN
 
-template <int WARPS>
-struct CtaStats {
-    WarpSlot slot[WARPS];
-    float edges[VU_N_UNC][32];
+// histogram words: [4 planes: total, true, q_hi, q_lo][VU_N_UNC][VU_N_BINS][32 lanes] int32
+constexpr int kHistPlane = VU_N_UNC * VU_N_BINS * 32;
+constexpr int kHistWords = 4 * kHistPlane;
 
-    __device__ void init(const StatParams& sp) {
-        for (int t = threadIdx.x; t < WARPS * VU_F64_COLS; t += blockDim.x) slot[t / VU_F64_COLS].f[t % VU_F64_COLS] = 0.0;
-        for (int t = threadIdx.x; t < WARPS * VU_I64_COLS; t += blockDim.x) slot[t / VU_I64_COLS].i[t % VU_I64_COLS] = 0;
-        for (int t = threadIdx.x; t < VU_N_UNC * 32; t += blockDim.x) edges[t / 32][t % 32] = sp.calib[t / 32].edge[t % 32];
-        __syncthreads();
-    }
-    // add this CTA's partials into image row b and clear them
-    __device__ void flush(const StatParams& sp, long long b) {
-        __syncthreads();
-        for (int c = threadIdx.x; c < VU_F64_COLS; c += blockDim.x) {
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) { s += slot[w].f[c]; slot[w].f[c] = 0.0; }
-            if (s != 0.0) atomicAdd(sp.f64 + b * VU_F64_COLS + c, s);
-        }
-        for (int c = threadIdx.x; c < VU_I64_COLS; c += blockDim.x) {
-            long long s = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) { s += slot[w].i[c]; slot[w].i[c] = 0; }
-            if (s != 0) atomicAdd(reinterpret_cast<unsigned long long*>(sp.i64 + b * VU_I64_COLS + c), (unsigned long long)s);
-        }
-        __syncthreads();
-    }
-};
-
-// Per-thread partials for the voxels a thread owns inside one tile.
-struct TileAcc {
-    double sum[VU_N_UNC], thr_sum[VU_N_UNC];
-    double g, gg, u[VU_N_UNC], uu[VU_N_UNC], gu[VU_N_UNC];
-    int thr_cnt[VU_N_UNC];
-    int area, nvox;
-    int tp[VU_MAX_RATERS], ps[VU_MAX_RATERS], gs[VU_MAX_RATERS];
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int k = 0; k < VU_N_UNC; ++k) { sum[k] = thr_sum[k] = u[k] = uu[k] = gu[k] = 0.0; thr_cnt[k] = 0; }
-        g = gg = 0.0;
-        area = nvox = 0;
-#pragma unroll
-        for (int r = 0; r < VU_MAX_RATERS; ++r) tp[r] = ps[r] = gs[r] = 0;
-    }
-};
-
-// bin = number of interior edges e_k with conf(u) >= e_k, decided on u itself
-// (see vu_calib in valunc.h).  edges[] is padded to 32 with NaN (never true).
-__device__ __forceinline__ int calib_bin(const float* edges, int increasing, float u) {
-    if (u != u) return VU_N_BINS - 1;  // np.digitize puts NaN past the last edge
-    const float uu = increasing ? u : -u;
-    int pos = 0;
-#pragma unroll
-    for (int step = 16; step > 0; step >>= 1) pos += (uu >= edges[pos + step - 1]) ? step : 0;
-    return pos;
+__host__ __device__ inline int stats_num_fslots(unsigned flags) {
+    return (flags & VU_STAT_NCC) ? FS_MAX : ((flags & VU_STAT_CALIB) ? FS_G : FS_BIN0);
+}
+__host__ __device__ inline int stats_num_islots(unsigned flags, int R) { return (flags & VU_STAT_DICE) ? IS_DICE + R : IS_DICE; }
+__host__ __device__ inline size_t stats_smem_bytes(unsigned flags, int R, int threads) {
+    if (!flags) return 0;
+    size_t n = (size_t)(stats_num_fslots(flags) + stats_num_islots(flags, R)) * threads * 8;
+    if (flags & VU_STAT_CALIB) n += (size_t)kHistWords * sizeof(int) + (size_t)VU_N_UNC * kEdgePad * sizeof(float);
+    return n;
 }
 
-// ace.py:329 in float32: 1 / (1 + exp((-u) * a + b)); ace.py:333 clips to [0, 1]
+template <int THREADS>
+struct StatsLayout {
+    double* fs;
+    unsigned long long* is;
+    int* hist;
+    float* E;
+    int nF, nI;
+    __device__ __forceinline__ StatsLayout(const StatParams& sp, void* smem) {
+        nF = stats_num_fslots(sp.flags);
+        nI = stats_num_islots(sp.flags, sp.gt.R);
+        fs = reinterpret_cast<double*>(smem);
+        is = reinterpret_cast<unsigned long long*>(fs + (size_t)nF * THREADS);
+        hist = reinterpret_cast<int*>(is + (size_t)nI * THREADS);
+        E = reinterpret_cast<float*>(hist + kHistWords);
+    }
+};
+
+template <int THREADS>
+__device__ __noinline__ void stats_init(const StatParams& sp, void* smem) {
+    StatsLayout<THREADS> L(sp, smem);
+    for (int t = threadIdx.x; t < (L.nF + L.nI) * THREADS; t += THREADS) reinterpret_cast<unsigned long long*>(smem)[t] = 0ull;
+    if (sp.flags & VU_STAT_CALIB) {
+        for (int t = threadIdx.x; t < kHistWords; t += THREADS) L.hist[t] = 0;
+        for (int t = threadIdx.x; t < VU_N_UNC * kEdgePad; t += THREADS) {
+            const int k = t / kEdgePad, e = t % kEdgePad;
+            L.E[t] = (e >= 1 && e <= VU_N_EDGES) ? sp.calib[k].edge[e - 1] : __int_as_float(0x7fc00000);
+        }
+    }
+    __syncthreads();
+}
+
+// Add this CTA's partials into image row b and clear them.  nvox = voxels of image b
+// the CTA went through since the last flush.  Called by every thread of the CTA.
+template <int THREADS>
+__device__ __noinline__ void stats_flush(const StatParams& sp, void* smem, long long b, long long nvox) {
+    __syncthreads();
+    StatsLayout<THREADS> L(sp, smem);
+    constexpr int WARPS = THREADS / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned flags = sp.flags;
+    double* frow = sp.f64 + b * VU_F64_COLS;
+    unsigned long long* irow = reinterpret_cast<unsigned long long*>(sp.i64 + b * VU_I64_COLS);
+    for (int q = warp; q < L.nF; q += WARPS) {
+        double s = 0.0;
+        for (int i = lane; i < THREADS; i += 32) { s += L.fs[q * THREADS + i]; L.fs[q * THREADS + i] = 0.0; }
+        s = warp_sum(s);
+        if (lane == 0 && s != 0.0) {
+            if (q < FS_THR) {
+                if (flags & VU_STAT_IMAGE_SUM) atomicAdd(frow + VU_F64_SUM + q, s);
+                if (flags & VU_STAT_NCC) atomicAdd(frow + VU_F64_NCC_U + q, s);
+            } else if (q < FS_BIN0) atomicAdd(frow + VU_F64_THR_SUM + (q - FS_THR), s);
+            else if (q < FS_G) atomicAdd(frow + VU_F64_BIN_SUMS + (q - FS_BIN0) * VU_N_BINS, s);
+            else if (q == FS_G) atomicAdd(frow + VU_F64_NCC_G, s);
+            else if (q == FS_GG) atomicAdd(frow + VU_F64_NCC_GG, s);
+            else if (q < FS_GU) atomicAdd(frow + VU_F64_NCC_UU + (q - FS_UU), s);
+            else atomicAdd(frow + VU_F64_NCC_GU + (q - FS_GU), s);
+        }
+    }
+    for (int q = warp; q < L.nI; q += WARPS) {
+        unsigned long long f0 = 0, f1 = 0, f2 = 0;
+        for (int i = lane; i < THREADS; i += 32) {
+            const unsigned long long w = L.is[q * THREADS + i];
+            L.is[q * THREADS + i] = 0ull;
+            if (q == IS_AREA) f0 += w;
+            else { f0 += w & kPackMask; f1 += (w >> kPackBits) & kPackMask; f2 += w >> (2 * kPackBits); }
+        }
+        f0 = (unsigned long long)warp_sum((double)f0);  // exact: every partial is far below 2^53
+        f1 = (unsigned long long)warp_sum((double)f1);
+        f2 = (unsigned long long)warp_sum((double)f2);
+        if (lane == 0) {
+            if (q == IS_THRCNT) {
+                if (f0) atomicAdd(irow + VU_I64_THR_COUNT + 0, f0);
+                if (f1) atomicAdd(irow + VU_I64_THR_COUNT + 1, f1);
+                if (f2) atomicAdd(irow + VU_I64_THR_COUNT + 2, f2);
+            } else if (q == IS_AREA) {
+                if (f0) atomicAdd(irow + VU_I64_AREA, f0);
+            } else {
+                const int r = q - IS_DICE;
+                if (f0) atomicAdd(irow + VU_I64_DICE_TP + r, f0);
+                if (f1) atomicAdd(irow + VU_I64_DICE_PRED + r, f1);
+                if (f2) atomicAdd(irow + VU_I64_DICE_GT + r, f2);
+            }
+        }
+    }
+    if (flags & VU_STAT_CALIB) {
+        for (int t = threadIdx.x; t < VU_N_UNC * VU_N_BINS; t += THREADS) {
+            const int k = t / VU_N_BINS, bin = t % VU_N_BINS;
+            long long tot = 0, tru = 0, q = 0;
+            int* h = L.hist + t * 32;
+            for (int i = 0; i < 32; ++i) {
+                const int r = (i + threadIdx.x) & 31;  // skewed: the threads of a warp read different banks
+                tot += h[r]; tru += h[kHistPlane + r];
+                q += (long long)h[2 * kHistPlane + r] * (1 << kQSplit) + h[3 * kHistPlane + r];
+                h[r] = 0; h[kHistPlane + r] = 0; h[2 * kHistPlane + r] = 0; h[3 * kHistPlane + r] = 0;
+            }
+            if (tot) {
+                atomicAdd(irow + VU_I64_BIN_TOTAL + t, (unsigned long long)tot);
+                if (tru) atomicAdd(irow + VU_I64_BIN_TRUE + t, (unsigned long long)tru);
+                // bin 0 is summed in floating point by the threads (slots FS_BIN0); slot 20 only ever holds NaN
+                // confidences (np.digitize sends NaN past the last edge), whose sum is NaN
+                if (bin == VU_N_BINS - 1) atomicAdd(frow + VU_F64_BIN_SUMS + t, (double)__int_as_float(0x7fc00000));
+                else if (bin > 0)
+                    atomicAdd(frow + VU_F64_BIN_SUMS + t,
+                              (double)tot * (double)((float)bin * 0.05f) + (double)q * (1.0 / (double)(1 << kQBits)));
+            }
+        }
+    }
+    if (threadIdx.x == 0 && nvox) atomicAdd(irow + VU_I64_NVOX, (unsigned long long)nvox);
+    __syncthreads();
+}
+
+// Tracks which image a CTA is working on and flushes when it moves on.  All members are CTA-uniform.
+template <int THREADS>
+struct StatsCursor {
+    int cur_b, vt_begin;
+    __device__ __forceinline__ StatsCursor() : cur_b(-1), vt_begin(0) {}
+    // top of every tile: tile index vt inside image b, tile_vox voxels per tile
+    __device__ __forceinline__ void enter(const StatParams& sp, void* smem, int b, int vt, long long tile_vox) {
+        if (b != cur_b || vt - vt_begin >= (int)kMaxTilesPerFlush) {
+            if (cur_b >= 0) {
+                const long long end = (b != cur_b) ? sp.V : (long long)vt * tile_vox;
+                stats_flush<THREADS>(sp, smem, cur_b, end - (long long)vt_begin * tile_vox);
+            }
+            cur_b = b;
+            vt_begin = vt;
+        }
+    }
+    // after the last tile (vt = its index inside the image)
+    __device__ __forceinline__ void finish(const StatParams& sp, void* smem, int last_vt, long long tile_vox) {
+        if (cur_b >= 0) {
+            long long end = (long long)(last_vt + 1) * tile_vox;
+            end = end > sp.V ? sp.V : end;
+            stats_flush<THREADS>(sp, smem, cur_b, end - (long long)vt_begin * tile_vox);
+        }
+    }
+};
+
+// ace.py:329 in float32: 1 / (1 + exp((-u) * a + b)); ace.py:333 clips to [0, 1].  Bins are decided on u
+// itself (calib_bin), so this value only feeds the floating bin_sums: fast exp / reciprocal are enough.
 __device__ __forceinline__ float platt_conf(float u, float a, float b, int identity) {
-    if (identity) return (u != u) ? u : fminf(fmaxf(u, 0.0f), 1.0f);
-    const float z = __fadd_rn(__fmul_rn(-u, a), b);
-    const float c = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(z)));
-    if (c != c) return c;  // np.clip keeps NaN
+    if (identity) return fminf(fmaxf(u, 0.0f), 1.0f);
+    const float z = fmaf(-u, a, b);
+    const float c = __fdividef(1.0f, 1.0f + __expf(z));
     return fminf(fmaxf(c, 0.0f), 1.0f);
 }
 
-// Statistics of ONE voxel per lane.  Must be called by all 32 lanes of the warp
-// (lanes past the end of the image pass active = false).
-template <int WARPS>
-__device__ __forceinline__ void stats_voxel(const StatParams& sp, CtaStats<WARPS>& cs, TileAcc& acc, bool active,
-                                            long long b, long long v, const float (&u)[VU_N_UNC], int label) {
-    const unsigned flags = sp.flags;
-    const int lane = threadIdx.x & 31;
-    WarpSlot& slot = cs.slot[threadIdx.x >> 5];
-    if (active) {
-        acc.nvox += 1;
-        if (flags & VU_STAT_IMAGE_SUM) {
+// bin = number of interior edges e_k with conf(u) >= e_k, decided on u itself
+// (see vu_calib in valunc.h).  The device confidence is within a few ulp of the
+// reference's, so floor(conf * 20) is at most one bin off; the two neighbouring
+// thresholds on u settle it exactly.  E is padded with NaN (compares false).
+__device__ __forceinline__ int calib_bin(const float* E, int increasing, float u, float conf) {
+    const float uu = increasing ? u : -u;
+    int k0 = __float2int_rd(conf * 20.0f);
+    k0 = k0 > 19 ? 19 : (k0 < 0 ? 0 : k0);
+    const float e_lo = E[k0], e_hi = E[k0 + 1];  // E[j] = interior edge j-1, i.e. the lower edge of bin j
+    return k0 + (uu >= e_hi ? 1 : 0) - (uu < e_lo ? 1 : 0);
+}
+
+// The whole statistics phase for the VEC voxels a thread owns in one tile.  Must
+// be called by every thread of the CTA (threads past the end of the image pass
+// active = false).  Kept out of line so its registers do not inflate the
+// streaming loop of the calling kernel.
+template <int VEC> struct FVec;
+template <> struct FVec<4> { typedef float4 type; };
+template <> struct FVec<2> { typedef float2 type; };
+template <> struct FVec<1> { typedef float type; };
+__device__ __forceinline__ float4 fvec_pack(const float (&x)[4]) { return make_float4(x[0], x[1], x[2], x[3]); }
+__device__ __forceinline__ float2 fvec_pack(const float (&x)[2]) { return make_float2(x[0], x[1]); }
+__device__ __forceinline__ float fvec_pack(const float (&x)[1]) { return x[0]; }
+__device__ __forceinline__ void fvec_unpack(float4 v, float (&x)[4]) { x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+__device__ __forceinline__ void fvec_unpack(float2 v, float (&x)[2]) { x[0] = v.x; x[1] = v.y; }
+__device__ __forceinline__ void fvec_unpack(float v, float (&x)[1]) { x[0] = v; }
+
+// (arguments travel in registers: the three maps as built-in vectors, the VEC labels packed into one word)
+template <int VEC, int THREADS, typename GT>
+__device__ __noinline__ void stats_tile_t(const StatParams& sp, void* smem, bool active, long long b, long long v,
+                                          typename FVec<VEC>::type u0, typename FVec<VEC>::type u1,
+                                          typename FVec<VEC>::type u2, unsigned labels_packed) {
+    StatsLayout<THREADS> cs(sp, smem);
+    float u[VU_N_UNC][VEC];
+    int label[VEC];
+    fvec_unpack(u0, u[0]);
+    fvec_unpack(u1, u[1]);
+    fvec_unpack(u2, u[2]);
 #pragma unroll
-            for (int k = 0; k < VU_N_UNC; ++k)
-                if (k < sp.n_unc) acc.sum[k] += (double)u[k];
-        }
-        if (flags & VU_STAT_THRESHOLD) {
+    for (int j = 0; j < VEC; ++j) label[j] = (int)((labels_packed >> (8 * j)) & 0xffu);
+    using G = typename std::conditional<sizeof(GT) == 1, int, long long>::type;
+    using GAcc = typename std::conditional<sizeof(GT) == 1, int, double>::type;
+    const unsigned flags = sp.flags, mask = sp.unc_mask;
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    if (active && (flags & (VU_STAT_IMAGE_SUM | VU_STAT_NCC))) {
 #pragma unroll
-            for (int k = 0; k < VU_N_UNC; ++k)
-                if (k < sp.n_unc && u[k] >= sp.thr[k]) { acc.thr_sum[k] += (double)u[k]; acc.thr_cnt[k] += 1; }
-        }
-        if (flags & VU_STAT_AREA) acc.area += (label > 0);
+        for (int k = 0; k < VU_N_UNC; ++k)
+            if ((mask >> k) & 1) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) s += u[k][j];
+                cs.fs[(FS_SUM + k) * THREADS + tid] += (double)s;
+            }
+    }
+    if (active && (flags & VU_STAT_THRESHOLD)) {
+        unsigned long long packed = 0;
+#pragma unroll
+        for (int k = 0; k < VU_N_UNC; ++k)
+            if ((mask >> k) & 1) {
+                float s = 0.f;
+                int n = 0;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const bool hit = u[k][j] >= sp.thr[k];
+                    s += hit ? u[k][j] : 0.f;
+                    n += hit;
+                }
+                if (n) cs.fs[(FS_THR + k) * THREADS + tid] += (double)s;
+                packed |= (unsigned long long)n << (k * kPackBits);
+            }
+        if (packed) cs.is[IS_THRCNT * THREADS + tid] += packed;
+    }
+    if (active && (flags & VU_STAT_AREA)) {
+        int n = 0;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) n += (label[j] > 0);
+        if (n) cs.is[IS_AREA * THREADS + tid] += (unsigned long long)n;
     }
     if (!(flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC))) return;
 
-    int n_valid = 0, n_correct = 0;
-    double gmean = 0.0, gsq = 0.0;
+    int n_valid[VEC], n_correct[VEC];
+    GAcc gsum[VEC], gsq[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { n_valid[j] = 0; n_correct[j] = 0; gsum[j] = 0; gsq[j] = 0; }
     const int R = sp.gt.data ? sp.gt.R : 0;
     if (active && R > 0) {
-        const int cmp_label = sp.lut ? (int)__ldg(sp.lut + label) : label;
+        G cmp[VEC];
 #pragma unroll
-        for (int r = 0; r < VU_MAX_RATERS; ++r) {
-            if (r < R) {
-                const long long g = sp.gt.at(b, r, v);
-                const bool valid = !(sp.gt.has_ignore && g == sp.gt.ignore);
-                if (flags & VU_STAT_DICE) {  // test_2D.py:878-886
-                    const bool pp = (label == 1) && valid, gp = (g == 1) && valid;
-                    acc.tp[r] += (pp && gp);
-                    acc.ps[r] += pp;
-                    acc.gs[r] += gp;
-                }
-                n_valid += valid;                             // ace.py:492-499
-                n_correct += (valid && g == (long long)cmp_label);  // ace.py:488
-                gmean += (double)g;
-                gsq += (double)g * (double)g;
+        for (int j = 0; j < VEC; ++j) cmp[j] = (G)(sp.lut ? (int)__ldg(sp.lut + label[j]) : label[j]);
+        const bool has_ign = sp.gt.has_ignore != 0;
+        const G ign = (G)sp.gt.ignore;
+#pragma unroll 1
+        for (int r = 0; r < R; ++r) {
+            G g[VEC];
+            load_gt<VEC>(sp.gt, b, r, v, g, GT());
+            int tp = 0, ps = 0, gs = 0;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const bool valid = !(has_ign && g[j] == ign);     // ace.py:492-499, test_2D.py:880
+                const bool pp = (label[j] == 1) && valid, gp = (g[j] == (G)1) && valid;  // test_2D.py:878-886
+                tp += (pp && gp); ps += pp; gs += gp;
+                n_valid[j] += valid;
+                n_correct[j] += (valid && g[j] == cmp[j]);       // ace.py:488
+                gsum[j] += (GAcc)g[j];
+                gsq[j] += (GAcc)g[j] * (GAcc)g[j];
             }
+            if ((flags & VU_STAT_DICE) && (tp | ps | gs))
+                cs.is[(IS_DICE + r) * THREADS + tid] +=
+                    (unsigned long long)tp | ((unsigned long long)ps << kPackBits) | ((unsigned long long)gs << (2 * kPackBits));
         }
     }
-    if (flags & VU_STAT_NCC) {
-        if (active) {
+    if (active && (flags & VU_STAT_NCC)) {
+        double sg = 0.0, sgg = 0.0, suu[VU_N_UNC] = {0.0, 0.0, 0.0}, sgu[VU_N_UNC] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
             double g;
             if (sp.ncc_gt_map) {
-                g = sp.ncc_gt_map[b * sp.V + v];
+                g = sp.ncc_gt_map[b * sp.V + v + j];
             } else {
-                // np.var(refs, axis=0), ddof = 0 (experiment_dataloader.py:283)
-                const double mu = gmean / (double)R;
-                g = gsq / (double)R - mu * mu;
+                // np.var(refs, axis=0), ddof = 0 (experiment_dataloader.py:283): (R*sum g^2 - (sum g)^2) / R^2
+                const double rr = (double)R;
+                g = ((double)gsq[j] * rr - (double)gsum[j] * (double)gsum[j]) / (rr * rr);
                 g = g < 0.0 ? 0.0 : g;
             }
-            acc.g += g;
-            acc.gg += g * g;
+            sg += g;
+            sgg += g * g;
 #pragma unroll
             for (int k = 0; k < VU_N_UNC; ++k)
-                if (k < sp.n_unc) {
-                    const double x = (double)u[k];
-                    acc.u[k] += x; acc.uu[k] += x * x; acc.gu[k] += g * x;
+                if ((mask >> k) & 1) {
+                    const double x = (double)u[k][j];
+                    suu[k] += x * x;
+                    sgu[k] += g * x;
                 }
         }
+        cs.fs[FS_G * THREADS + tid] += sg;
+        cs.fs[FS_GG * THREADS + tid] += sgg;
+#pragma unroll
+        for (int k = 0; k < VU_N_UNC; ++k)
+            if ((mask >> k) & 1) {
+                cs.fs[(FS_UU + k) * THREADS + tid] += suu[k];
+                cs.fs[(FS_GU + k) * THREADS + tid] += sgu[k];
+            }
     }
     if (flags & VU_STAT_CALIB) {
 #pragma unroll
         for (int k = 0; k < VU_N_UNC; ++k) {
-            if (k >= sp.n_unc) break;
-            int bin = -1;
-            double w = 0.0;
-            if (active && n_valid > 0) {
-                bin = calib_bin(cs.edges[k], sp.calib[k].increasing, u[k]);
-                w = (double)platt_conf(u[k], sp.calib[k].a, sp.calib[k].b, sp.calib[k].identity) * (double)n_valid;
-            }
-            // one round per distinct bin present in the warp (neighbouring
-            // voxels mostly share a bin, so this is 1-2 rounds)
-            unsigned todo = __ballot_sync(kFull, bin >= 0);
-            while (todo) {
-                const int leader = __ffs(todo) - 1;
-                const int bsel = __shfl_sync(kFull, bin, leader);
-                const bool mine = (bin == bsel);
-                const int tot = warp_sum(mine ? n_valid : 0);
-                const int tru = warp_sum(mine ? n_correct : 0);
-                const double sw = warp_sum(mine ? w : 0.0);
-                if (lane == 0) {
-                    slot.i[VU_I64_BIN_TOTAL + k * VU_N_BINS + bsel] += tot;
-                    slot.i[VU_I64_BIN_TRUE + k * VU_N_BINS + bsel] += tru;
-                    slot.f[VU_F64_BIN_SUMS + k * VU_N_BINS + bsel] += sw;
+            if (!((mask >> k) & 1)) continue;
+            float bin0 = 0.f;
+            const CalibDev& cal = sp.calib[k];
+            const float* E = cs.E + k * kEdgePad;
+            int* hk = cs.hist + k * (VU_N_BINS * 32) + lane;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const int nv = n_valid[j];
+                if (active && nv > 0) {
+                    const float x = u[k][j];
+                    int bin = VU_N_BINS - 1, q = 0;  // np.digitize puts NaN past the last edge
+                    if (x == x) {
+                        const float conf = platt_conf(x, cal.a, cal.b, cal.identity);
+                        bin = calib_bin(E, cal.increasing, x, conf);
+                        q = __float2int_rn((conf - (float)bin * 0.05f) * (float)(1 << kQBits)) * nv;
+                        bin0 += bin == 0 ? conf * (float)nv : 0.f;
+                    }
+                    int* h = hk + bin * 32;
+                    atomicAdd(h, nv);
+                    if (n_correct[j]) atomicAdd(h + kHistPlane, n_correct[j]);
+                    atomicAdd(h + 2 * kHistPlane, q >> kQSplit);
+                    atomicAdd(h + 3 * kHistPlane, q & ((1 << kQSplit) - 1));
                 }
-                todo &= ~__ballot_sync(kFull, mine);
             }
+            if (bin0 != 0.f) cs.fs[(FS_BIN0 + k) * THREADS + tid] += (double)bin0;
         }
     }
 }
 
-// Fold a thread's tile partials into its warp slot.  All 32 lanes call it.
-template <int WARPS>
-__device__ __forceinline__ void stats_tile_end(const StatParams& sp, CtaStats<WARPS>& cs, TileAcc& acc) {
-    const unsigned flags = sp.flags;
-    const int lane = threadIdx.x & 31;
-    WarpSlot& slot = cs.slot[threadIdx.x >> 5];
-    {
-        const int n = warp_sum(acc.nvox);
-        if (lane == 0) slot.i[VU_I64_NVOX] += n;
-    }
-    if (flags & VU_STAT_IMAGE_SUM) {
+template <int VEC, int THREADS>
+__device__ __forceinline__ void stats_tile(const StatParams& sp, void* smem, bool active, long long b, long long v,
+                                           const float (&u)[VU_N_UNC][VEC], const int (&label)[VEC]) {
+    unsigned lp = 0;
 #pragma unroll
-        for (int k = 0; k < VU_N_UNC; ++k) {
-            const double s = warp_sum(acc.sum[k]);
-            if (lane == 0) slot.f[VU_F64_SUM + k] += s;
-        }
-    }
-    if (flags & VU_STAT_THRESHOLD) {
-#pragma unroll
-        for (int k = 0; k < VU_N_UNC; ++k) {
-            const double s = warp_sum(acc.thr_sum[k]);
-            const int n = warp_sum(acc.thr_cnt[k]);
-            if (lane == 0) { slot.f[VU_F64_THR_SUM + k] += s; slot.i[VU_I64_THR_COUNT + k] += n; }
-        }
-    }
-    if (flags & VU_STAT_AREA) {
-        const int n = warp_sum(acc.area);
-        if (lane == 0) slot.i[VU_I64_AREA] += n;
-    }
-    if (flags & VU_STAT_DICE) {
-#pragma unroll
-        for (int r = 0; r < VU_MAX_RATERS; ++r) {
-            if (r < sp.gt.R) {
-                const int a = warp_sum(acc.tp[r]), p = warp_sum(acc.ps[r]), g = warp_sum(acc.gs[r]);
-                if (lane == 0) { slot.i[VU_I64_DICE_TP + r] += a; slot.i[VU_I64_DICE_PRED + r] += p; slot.i[VU_I64_DICE_GT + r] += g; }
-            }
-        }
-    }
-    if (flags & VU_STAT_NCC) {
-        const double g = warp_sum(acc.g), gg = warp_sum(acc.gg);
-        if (lane == 0) { slot.f[VU_F64_NCC_G] += g; slot.f[VU_F64_NCC_GG] += gg; }
-#pragma unroll
-        for (int k = 0; k < VU_N_UNC; ++k) {
-            const double a = warp_sum(acc.u[k]), c = warp_sum(acc.uu[k]), d = warp_sum(acc.gu[k]);
-            if (lane == 0) { slot.f[VU_F64_NCC_U + k] += a; slot.f[VU_F64_NCC_UU + k] += c; slot.f[VU_F64_NCC_GU + k] += d; }
-        }
-    }
-    acc.clear();
-}
-
-
-// The whole statistics phase for the VEC voxels a thread owns in one tile.
-// Kept out of line so its register needs (double accumulators) do not inflate
-// the streaming loop of the calling kernel.
-template <int VEC, int WARPS>
-__device__ __noinline__ void stats_tile(const StatParams& sp, CtaStats<WARPS>& cs, bool active, long long b, long long v,
-                                        const float (&u)[VU_N_UNC][VEC], const int (&label)[VEC]) {
-    TileAcc acc;
-    acc.clear();
-#pragma unroll 1
-    for (int k = 0; k < VEC; ++k) {
-        const float uk[VU_N_UNC] = {u[0][k], u[1][k], u[2][k]};
-        stats_voxel<WARPS>(sp, cs, acc, active, b, v + k, uk, label[k]);
-    }
-    stats_tile_end<WARPS>(sp, cs, acc);
+    for (int j = 0; j < VEC; ++j) lp |= (unsigned)(label[j] & 0xff) << (8 * j);
+    if (sp.gt.dtype == VU_GT_I64)
+        stats_tile_t<VEC, THREADS, long long>(sp, smem, active, b, v, fvec_pack(u[0]), fvec_pack(u[1]), fvec_pack(u[2]), lp);
+    else
+        stats_tile_t<VEC, THREADS, uint8_t>(sp, smem, active, b, v, fvec_pack(u[0]), fvec_pack(u[1]), fvec_pack(u[2]), lp);
 }
 
 }  // namespace vu

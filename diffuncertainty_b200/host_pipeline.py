@@ -1,0 +1,117 @@
+"""The fused pass for slabs that live in HOST memory.
+
+The reference's evaluation side works on arrays it loaded from disk
+(evaluation/uncertainty_aggregation/aggregate_uncertainties.py:140-142,
+evaluation/experiment_dataloader.py:305-312), and ``calculate_uncertainty``
+(unc_mod_utils/test_utils.py:833) accepts CPU tensors.  This is the equivalent
+entry: the caller hands pinned host buffers, the pipeline streams them through
+the device in image chunks -- host->device copy of chunk i+1, kernel on chunk i
+and device->host copy of the maps of chunk i-1 overlap on three streams -- and
+returns host results.  All arithmetic still happens in libvalunc's kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, calibration
+from ._lib import F64, I64
+from .uncertainty import UNC_KEYS, GroundTruth, fused_pass
+
+
+@dataclass
+class HostResult:
+    maps: Dict[str, torch.Tensor]      # pinned host fp32 (B, *S)
+    labels: torch.Tensor               # pinned host uint8 (B, *S)
+    stats_f64: Optional[np.ndarray]    # (B, 80)
+    stats_i64: Optional[np.ndarray]    # (B, 156)
+    h2d_bytes: int
+    d2h_bytes: int
+
+
+class HostPipeline:
+    def __init__(self, P: int, C: int, spatial: Sequence[int], batch: int, R: int = 0, gt_dtype=torch.uint8,
+                 chunk_images: int = 1, n_buffers: int = 3, stats: int = 0, thresholds: Optional[Sequence[float]] = None,
+                 platt=None, ignore_index: Optional[int] = None, device=None):
+        _lib.require_device()
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.P, self.C, self.spatial, self.B, self.R = P, C, tuple(spatial), batch, R
+        self.chunk = max(1, min(chunk_images, batch))
+        self.nb = n_buffers
+        self.stats, self.thresholds, self.ignore_index = stats, thresholds, ignore_index
+        self.calib = [calibration.platt_edges(a, b) for a, b in platt] if (platt is not None and stats & _lib.STAT_CALIB) else None
+        S = self.spatial
+        with torch.cuda.device(self.dev):
+            self.d_slab = [torch.empty((P, self.chunk, C) + S, dtype=torch.float32, device=self.dev) for _ in range(n_buffers)]
+            self.d_gt = [torch.empty((self.chunk, R) + S, dtype=gt_dtype, device=self.dev) for _ in range(n_buffers)] if R else None
+            self.d_maps = [{k: torch.empty((self.chunk,) + S, dtype=torch.float32, device=self.dev) for k in UNC_KEYS}
+                           for _ in range(n_buffers)]
+            self.d_labels = [torch.empty((self.chunk,) + S, dtype=torch.uint8, device=self.dev) for _ in range(n_buffers)]
+            self.rows_f = torch.zeros((batch, F64["COLS"]), dtype=torch.float64, device=self.dev)
+            self.rows_i = torch.zeros((batch, I64["COLS"]), dtype=torch.int64, device=self.dev)
+            self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self.h_maps = {k: torch.empty((batch,) + S, dtype=torch.float32).pin_memory() for k in UNC_KEYS}
+        self.h_labels = torch.empty((batch,) + S, dtype=torch.uint8).pin_memory()
+        self.h_rows_f = torch.empty((batch, F64["COLS"]), dtype=torch.float64).pin_memory()
+        self.h_rows_i = torch.empty((batch, I64["COLS"]), dtype=torch.int64).pin_memory()
+
+    def run(self, x_host: torch.Tensor, gt_host: Optional[torch.Tensor] = None) -> HostResult:
+        """x_host: (P, B, C, *S) float32 host tensor (pinned for full speed); gt_host: (B, R, *S)."""
+        P, B, nb, ch = self.P, self.B, self.nb, self.chunk
+        if tuple(x_host.shape) != (P, B, self.C) + self.spatial or x_host.dtype != torch.float32 or x_host.is_cuda:
+            raise ValueError("x_host must be a float32 host tensor of shape (P, B, C, *spatial)")
+        if self.R and (gt_host is None or tuple(gt_host.shape) != (B, self.R) + self.spatial):
+            raise ValueError("gt_host must have shape (B, R, *spatial)")
+        h2d = d2h = 0
+        ev_in = [torch.cuda.Event() for _ in range(nb)]
+        ev_run = [torch.cuda.Event() for _ in range(nb)]
+        ev_out = [None] * nb
+        n_chunks = (B + ch - 1) // ch
+        with torch.cuda.device(self.dev):
+            if self.stats:
+                with torch.cuda.stream(self.s_run):
+                    self.rows_f.zero_()
+                    self.rows_i.zero_()
+            for i in range(n_chunks):
+                s, e = i * ch, min(B, (i + 1) * ch)
+                n, j = e - s, i % nb
+                with torch.cuda.stream(self.s_in):
+                    self.s_in.wait_event(ev_run[j]) if i >= nb else None   # buffer j is free once its kernel ran
+                    for p in range(P):                                      # each source run is contiguous
+                        self.d_slab[j][p, :n].copy_(x_host[p, s:e], non_blocking=True)
+                    h2d += x_host[:, s:e].numel() * 4
+                    if self.R:
+                        self.d_gt[j][:n].copy_(gt_host[s:e], non_blocking=True)
+                        h2d += gt_host[s:e].numel() * gt_host.element_size()
+                    ev_in[j].record(self.s_in)
+                with torch.cuda.stream(self.s_run):
+                    self.s_run.wait_event(ev_in[j])
+                    if ev_out[j] is not None:
+                        self.s_run.wait_event(ev_out[j])                    # maps of the previous user of buffer j left
+                    maps_out = {k: v[:n] for k, v in self.d_maps[j].items()}
+                    fused_pass(self.d_slab[j][:, :n], GroundTruth(self.d_gt[j][:n], self.ignore_index) if self.R else None,
+                               stats=self.stats, thresholds=self.thresholds, calib=self.calib,
+                               stats_out=(self.rows_f[s:e], self.rows_i[s:e]) if self.stats else None,
+                               maps_out=maps_out, labels_out=self.d_labels[j][:n])
+                    ev_run[j].record(self.s_run)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(ev_run[j])
+                    for k in UNC_KEYS:
+                        self.h_maps[k][s:e].copy_(self.d_maps[j][k][:n], non_blocking=True)
+                    self.h_labels[s:e].copy_(self.d_labels[j][:n], non_blocking=True)
+                    d2h += n * int(np.prod(self.spatial)) * 13
+                    ev_out[j] = torch.cuda.Event()
+                    ev_out[j].record(self.s_out)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_stream(self.s_run)
+                if self.stats:
+                    self.h_rows_f.copy_(self.rows_f, non_blocking=True)
+                    self.h_rows_i.copy_(self.rows_i, non_blocking=True)
+                    d2h += self.rows_f.numel() * 8 + self.rows_i.numel() * 8
+            self.s_out.synchronize()
+        return HostResult(maps=self.h_maps, labels=self.h_labels,
+                          stats_f64=self.h_rows_f.numpy() if self.stats else None,
+                          stats_i64=self.h_rows_i.numpy() if self.stats else None, h2d_bytes=h2d, d2h_bytes=d2h)

@@ -142,7 +142,8 @@ def _fill_gt(gt_struct: _lib.Gt, gt: Optional[GroundTruth], B: int, spatial) -> 
 def fused_pass(softmax_pred: torch.Tensor, gt: Optional[GroundTruth] = None, *, stats: int = 0,
                thresholds: Optional[Sequence[float]] = None, calib=None, label_lut: Optional[torch.Tensor] = None,
                want_maps: bool = True, want_labels: bool = True,
-               stats_out: Optional[tuple] = None) -> FusedResult:
+               stats_out: Optional[tuple] = None, maps_out: Optional[Dict[str, torch.Tensor]] = None,
+               labels_out: Optional[torch.Tensor] = None) -> FusedResult:
     """One launch over ``softmax_pred`` of shape (P, B, C, *S) (test_2D.py:1277).
 
     stats      : OR of _lib.STAT_* flags
@@ -150,6 +151,8 @@ def fused_pass(softmax_pred: torch.Tensor, gt: Optional[GroundTruth] = None, *, 
     calib      : three ``calibration.PlattEdges`` for STAT_CALIB
     stats_out  : optional (stats_f64, stats_i64) device tensors to accumulate
                  into (rows = images of this batch)
+    maps_out   : optional preallocated contiguous fp32 (B, *S) tensors keyed "TU","AU","EU"
+                 (or "pred_entropy" when P == 1); labels_out: preallocated uint8 (B, *S)
     """
     _check_slab(softmax_pred, "softmax_pred")
     if softmax_pred.dim() < 4:
@@ -181,11 +184,25 @@ def fused_pass(softmax_pred: torch.Tensor, gt: Optional[GroundTruth] = None, *, 
         if want_maps:
             names = UNC_KEYS if P > 1 else ("pred_entropy",)
             for name in names:
-                maps[name] = torch.empty((B,) + spatial, dtype=torch.float32, device=dev)
+                if maps_out is not None:
+                    m = maps_out[name]
+                    if m.shape != (B,) + spatial or m.dtype != torch.float32 or not m.is_contiguous() or m.device != dev:
+                        raise ValueError(f"maps_out[{name!r}] must be a contiguous float32 {(B,) + spatial} tensor on {dev}")
+                    maps[name] = m
+                else:
+                    maps[name] = torch.empty((B,) + spatial, dtype=torch.float32, device=dev)
             a.tu = maps[names[0]].data_ptr()
             if P > 1:
                 a.au, a.eu = maps["AU"].data_ptr(), maps["EU"].data_ptr()
-        labels = torch.empty((B,) + spatial, dtype=torch.uint8, device=dev) if want_labels else None
+        labels = None
+        if want_labels:
+            if labels_out is not None:
+                if labels_out.shape != (B,) + spatial or labels_out.dtype != torch.uint8 or not labels_out.is_contiguous() \
+                        or labels_out.device != dev:
+                    raise ValueError(f"labels_out must be a contiguous uint8 {(B,) + spatial} tensor on {dev}")
+                labels = labels_out
+            else:
+                labels = torch.empty((B,) + spatial, dtype=torch.uint8, device=dev)
         a.labels = labels.data_ptr() if labels is not None else None
         keep = _fill_gt(a.gt, gt, B, spatial)
         if thresholds is not None:
