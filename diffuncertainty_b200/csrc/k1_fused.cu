@@ -31,15 +31,40 @@ struct K1Params {
 // ---------------------------------------------------------------------------
 // Fast kernel: C compile-time, one thread owns VEC consecutive voxels and walks
 // the members in order (that is what makes the mean bit-exact), G members per
-// load stage, optionally double-buffered in registers.
+// load stage.
 //   LEVELS = 1: P <= 17 (plain sequential sum == torch's cascade)
 //   LEVELS = 2: P <= 271 (level-0 accumulator folded into level 1 every 16)
+// The E = C * VEC values of one member are handled as E/2 packed fp32 pairs
+// (FADD2 / FFMA2): pairs of neighbouring voxels for VEC = 2, 4, pairs of classes
+// for VEC = 1 (with one scalar leftover when C is odd).  The entropy of a member
+// is accumulated class by class with one fma per term in every variant, so all
+// variants and the generic kernel produce bit-identical maps.
 // Requires stride_v == 1 and VEC-element alignment of every row start.
 // ---------------------------------------------------------------------------
-template <int C, int VEC, int LEVELS, int THREADS, int MINB, int G, bool DB, bool STATS>
+template <int VEC>
+struct PairLoad;
+template <>
+struct PairLoad<4> {  // 16 bytes -> two pairs
+    __device__ __forceinline__ static void load(const float* p, f32x2* x) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(x[0]), "=l"(x[1]) : "l"(p));
+    }
+};
+template <>
+struct PairLoad<2> {
+    __device__ __forceinline__ static void load(const float* p, f32x2* x) {
+        asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(x[0]) : "l"(p));
+    }
+};
+
+template <int C, int VEC, int LEVELS, int THREADS, int MINB, int G, bool STATS>
 __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__ K1Params prm) {
     constexpr bool do_stats = STATS;
     constexpr long long kTileVox = (long long)THREADS * VEC;
+    constexpr int E = C * VEC;       // values of one member owned by a thread, flattened [class][voxel]
+    constexpr int NP = E / 2;        // packed pairs
+    constexpr bool ODD = (E & 1);    // VEC == 1 and C odd: the last class is handled in scalar code
+    constexpr int NH = VEC >= 2 ? VEC / 2 : 1;
+    constexpr int NP1 = LEVELS > 1 ? NP : 1;
     StatsCursor<THREADS> cursor;
     if (do_stats) stats_init<THREADS>(prm.st, vu_dyn_smem);
 
@@ -62,89 +87,116 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__
         for (int k = 0; k < VEC; ++k) { u[0][k] = u[1][k] = u[2][k] = 0.f; label[k] = 0; }
 
         if (active) {
-            float m0[C][VEC], a0[VEC];
-            float m1[LEVELS > 1 ? C : 1][VEC], a1[VEC];
+            if (do_stats) stats_prefetch_gt<VEC>(prm.st, b, v);
+            f32x2 m0[NP > 0 ? NP : 1], m1[NP1 > 0 ? NP1 : 1];  // member sums, cascade level 0 / 1
+            float m0s = 0.f, m1s = 0.f;                          // scalar leftover class (ODD)
+            f32x2 a0[NH], a1[NH];                                // entropy sums (VEC >= 2: packed over voxels)
+            float a0s = 0.f, a1s = 0.f;                          // entropy sums (VEC == 1)
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                a0[k] = 0.f; a1[k] = 0.f;
+            for (int j = 0; j < NP; ++j) m0[j] = 0ull;
 #pragma unroll
-                for (int c = 0; c < C; ++c) m0[c][k] = 0.f;
+            for (int j = 0; j < NP1; ++j) m1[j] = 0ull;
 #pragma unroll
-                for (int c = 0; c < (LEVELS > 1 ? C : 1); ++c) m1[c][k] = 0.f;
-            }
+            for (int q = 0; q < NH; ++q) { a0[q] = 0ull; a1[q] = 0ull; }
             const float* row0 = prm.x + (long long)b * prm.sb + v;
 
-            auto load_stage = [&](float (&x)[G][C][VEC], long long p0) {
+            f32x2 xp[G][NP > 0 ? NP : 1];
+            float xs[G];
+            for (long long p0 = 0; p0 < P; p0 += G) {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     if (G == 1 || p0 + g < P) {
                         const float* r = row0 + (p0 + g) * prm.sp;
+                        if constexpr (VEC >= 2) {
 #pragma unroll
-                        for (int c = 0; c < C; ++c) VecLoad<VEC>::load(r + c * prm.sc, x[g][c]);
+                            for (int c = 0; c < C; ++c) PairLoad<VEC >= 2 ? VEC : 2>::load(r + c * prm.sc, &xp[g][c * NH]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < NP; ++j) xp[g][j] = pk2(ldg_stream(r + (2 * j) * prm.sc), ldg_stream(r + (2 * j + 1) * prm.sc));
+                            if constexpr (ODD) xs[g] = ldg_stream(r + (C - 1) * prm.sc);
+                        }
                     }
                 }
-            };
-            auto consume_stage = [&](const float (&x)[G][C][VEC], long long p0) {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     if (G == 1 || p0 + g < P) {
-                        float h[VEC];
+                        if constexpr (VEC >= 2) {
+                            f32x2 h[NH];
 #pragma unroll
-                        for (int k = 0; k < VEC; ++k) h[k] = 0.f;
+                            for (int q = 0; q < NH; ++q) h[q] = 0ull;
 #pragma unroll
-                        for (int c = 0; c < C; ++c) {
+                            for (int c = 0; c < C; ++c) {
 #pragma unroll
-                            for (int k = 0; k < VEC; ++k) {
-                                m0[c][k] += x[g][c][k];
-                                h[k] += plog2p(x[g][c][k]);
+                                for (int q = 0; q < NH; ++q) {
+                                    const f32x2 X = xp[g][c * NH + q];
+                                    m0[c * NH + q] = add2(m0[c * NH + q], X);
+                                    f32x2 PC, L;
+                                    plog2p_parts2(X, PC, L);
+                                    h[q] = fma2(PC, L, h[q]);
+                                }
                             }
-                        }
 #pragma unroll
-                        for (int k = 0; k < VEC; ++k) a0[k] += h[k];
+                            for (int q = 0; q < NH; ++q) a0[q] = add2(a0[q], h[q]);
+                        } else {
+                            float h = 0.f;
+#pragma unroll
+                            for (int j = 0; j < NP; ++j) {
+                                const f32x2 X = xp[g][j];
+                                m0[j] = add2(m0[j], X);
+                                f32x2 PC, L;
+                                plog2p_parts2(X, PC, L);
+                                float pc0, pc1, l0, l1;
+                                upk2(PC, pc0, pc1);
+                                upk2(L, l0, l1);
+                                h = __fmaf_rn(pc0, l0, h);
+                                h = __fmaf_rn(pc1, l1, h);
+                            }
+                            if constexpr (ODD) { m0s = __fadd_rn(m0s, xs[g]); h = plog2p_acc(h, xs[g]); }
+                            a0s = __fadd_rn(a0s, h);
+                        }
                         if (LEVELS > 1 && (((p0 + g) & 15) == 15)) {
 #pragma unroll
-                            for (int k = 0; k < VEC; ++k) {
-                                a1[k] += a0[k]; a0[k] = 0.f;
+                            for (int j = 0; j < NP1; ++j) { m1[j] = add2(m1[j], m0[j]); m0[j] = 0ull; }
 #pragma unroll
-                                for (int c = 0; c < (LEVELS > 1 ? C : 1); ++c) { m1[c][k] += m0[c][k]; m0[c][k] = 0.f; }
-                            }
+                            for (int q = 0; q < NH; ++q) { a1[q] = add2(a1[q], a0[q]); a0[q] = 0ull; }
+                            m1s = __fadd_rn(m1s, m0s); m0s = 0.f;
+                            a1s = __fadd_rn(a1s, a0s); a0s = 0.f;
                         }
                     }
-                }
-            };
-
-            if (DB) {
-                float xa[G][C][VEC], xb[G][C][VEC];
-                load_stage(xa, 0);
-                for (long long p = 0; p < P; p += 2 * G) {
-                    if (p + G < P) load_stage(xb, p + G);
-                    consume_stage(xa, p);
-                    if (p + 2 * G < P) load_stage(xa, p + 2 * G);
-                    if (p + G < P) consume_stage(xb, p + G);
-                }
-            } else {
-                float xa[G][C][VEC];
-                for (long long p = 0; p < P; p += G) {
-                    load_stage(xa, p);
-                    consume_stage(xa, p);
                 }
             }
 
             // epilogue: mean (true division, test_2D.py:971), label, TU, AU, EU
+            float mean[C][VEC], asum[VEC];
+#pragma unroll
+            for (int e = 0; e < NP; ++e) {
+                const f32x2 S = (LEVELS > 1) ? add2(m0[e], m1[e]) : m0[e];
+                float s0, s1;
+                upk2(S, s0, s1);
+                mean[(2 * e) / VEC][(2 * e) % VEC] = __fdiv_rn(s0, Pf);
+                mean[(2 * e + 1) / VEC][(2 * e + 1) % VEC] = __fdiv_rn(s1, Pf);
+            }
+            if constexpr (ODD) mean[C - 1][0] = __fdiv_rn((LEVELS > 1) ? __fadd_rn(m0s, m1s) : m0s, Pf);
+            if constexpr (VEC >= 2) {
+#pragma unroll
+                for (int q = 0; q < NH; ++q) {
+                    const f32x2 A = (LEVELS > 1) ? add2(a0[q], a1[q]) : a0[q];
+                    upk2(A, asum[2 * q], asum[(2 * q + 1) % VEC]);
+                }
+            } else {
+                asum[0] = (LEVELS > 1) ? __fadd_rn(a0s, a1s) : a0s;
+            }
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-                float best = 0.f, tu2 = 0.f;
+                float best = mean[0][k], tu2 = 0.f;
                 int idx = 0;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const float s = (LEVELS > 1) ? (m0[c][k] + m1[c][k]) : m0[c][k];
-                    const float mean = s / Pf;
-                    if (c == 0) { best = mean; idx = 0; } else argmax_step(mean, c, best, idx);
-                    tu2 += plog2p(mean);
+                    if (c > 0) argmax_step(mean[c][k], c, best, idx);
+                    tu2 = plog2p_acc(tu2, mean[c][k]);
                 }
-                const float asum = (LEVELS > 1) ? (a0[k] + a1[k]) : a0[k];
                 const float tu = -(tu2 * kLn2);
-                const float au = (-(asum * kLn2)) / Pf;
+                const float au = (-(asum[k] * kLn2)) / Pf;
                 u[0][k] = tu; u[1][k] = au; u[2][k] = tu - au;
                 label[k] = idx;
             }
@@ -225,11 +277,11 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
                 for (long long p = 0; p < P; ++p) {
                     const float x = ldg_stream(pc + p * prm.sp);
                     cas.add(x, p, n_full, level_k);
-                    if (P > 1) h[p * THREADS] += plog2p(x);
+                    if (P > 1) h[p * THREADS] = plog2p_acc(h[p * THREADS], x);
                 }
-                const float mean = cas.total() / Pf;
+                const float mean = __fdiv_rn(cas.total(), Pf);
                 if (c == 0) { best = mean; label = 0; } else argmax_step(mean, c, best, label);
-                tu2 += plog2p(mean);
+                tu2 = plog2p_acc(tu2, mean);
             }
             const long long o = (long long)b * V + v;
             if (P > 1) {
@@ -270,40 +322,41 @@ struct FastVariant {
 
 #define VU_VARIANT(C, VEC, LEVELS, THREADS, MINB, G, DB, USE)                              \
     { C, VEC, LEVELS, THREADS, MINB, G, DB, USE,                                           \
-      (K1Kernel)k1_fast<C, VEC, LEVELS, THREADS, MINB, G, DB, false>,                      \
-      (K1Kernel)k1_fast<C, VEC, LEVELS, THREADS, MINB, G, DB, true> }
+      (K1Kernel)k1_fast<C, VEC, LEVELS, THREADS, MINB, G, false>,                          \
+      (K1Kernel)k1_fast<C, VEC, LEVELS, THREADS, MINB, G, true> }
 
 // First entry matching (C, LEVELS, alignment) wins unless the "k1_variant"
 // option selects another by index (used by the tuning sweep, bench/sweep_k1.py).
 static const FastVariant kFast[] = {
     // ---- C = 2 (LIDC-like, toy): few loads per member -> group members
-    VU_VARIANT(2, 4, 1, 256, 2, 8, false, 0),   // 0
-    VU_VARIANT(2, 4, 2, 256, 2, 8, false, 0),   // 1
-    VU_VARIANT(2, 4, 1, 256, 2, 4, false, 1),   // 2
-    VU_VARIANT(2, 4, 2, 256, 2, 4, false, 1),   // 3
-    VU_VARIANT(2, 4, 1, 256, 2, 4, true, -1),   // 4
-    VU_VARIANT(2, 4, 2, 256, 2, 4, true, -1),   // 5
-    VU_VARIANT(2, 2, 1, 256, 2, 8, false, 2),   // 6
-    VU_VARIANT(2, 2, 2, 256, 2, 8, false, 2),   // 7
-    VU_VARIANT(2, 1, 1, 256, 2, 8, false, 2),   // 8  (unaligned V)
-    VU_VARIANT(2, 1, 2, 256, 2, 8, false, 2),   // 9
+    VU_VARIANT(2, 4, 1, 256, 2, 8, 0, 0),    // 0
+    VU_VARIANT(2, 4, 2, 256, 2, 8, 0, 0),    // 1
+    VU_VARIANT(2, 4, 1, 256, 2, 4, 0, 1),    // 2
+    VU_VARIANT(2, 4, 2, 256, 2, 4, 0, 1),    // 3
+    VU_VARIANT(2, 4, 1, 256, 3, 4, 0, -1),   // 4
+    VU_VARIANT(2, 4, 2, 256, 3, 4, 0, -1),   // 5
+    VU_VARIANT(2, 2, 1, 256, 2, 8, 0, 2),    // 6
+    VU_VARIANT(2, 2, 2, 256, 2, 8, 0, 2),    // 7
+    VU_VARIANT(2, 1, 1, 256, 2, 8, 0, 2),    // 8  (unaligned V)
+    VU_VARIANT(2, 1, 2, 256, 2, 8, 0, 2),    // 9
     // ---- C = 19 (Cityscapes / GTA): 19 independent loads per member
-    VU_VARIANT(19, 1, 1, 256, 3, 1, false, 2),  // 10
-    VU_VARIANT(19, 1, 2, 256, 2, 1, false, 2),  // 11
-    VU_VARIANT(19, 2, 1, 256, 2, 1, false, -1), // 12
-    VU_VARIANT(19, 2, 2, 256, 1, 1, false, -1), // 13
-    VU_VARIANT(19, 1, 1, 256, 4, 1, false, -1), // 14
-    VU_VARIANT(19, 1, 1, 128, 6, 1, false, -1), // 15
-    VU_VARIANT(19, 1, 2, 256, 3, 1, false, -1), // 16
+    VU_VARIANT(19, 1, 1, 256, 3, 1, 0, 2),   // 10
+    VU_VARIANT(19, 1, 2, 256, 2, 1, 0, 2),   // 11
+    VU_VARIANT(19, 2, 1, 256, 2, 1, 0, -1),  // 12
+    VU_VARIANT(19, 2, 2, 256, 1, 1, 0, -1),  // 13
+    VU_VARIANT(19, 1, 1, 256, 4, 1, 0, -1),  // 14
+    VU_VARIANT(19, 4, 1, 128, 2, 1, 0, -1),  // 15
+    VU_VARIANT(19, 1, 2, 256, 3, 1, 0, -1),  // 16
+    VU_VARIANT(19, 2, 1, 128, 4, 1, 0, -1),  // 17
     // ---- small C
-    VU_VARIANT(3, 4, 1, 256, 2, 2, true, 2),    // 17
-    VU_VARIANT(3, 4, 2, 256, 2, 2, true, 2),    // 18
-    VU_VARIANT(3, 1, 1, 256, 2, 4, true, 2),    // 19
-    VU_VARIANT(3, 1, 2, 256, 2, 4, true, 2),    // 20
-    VU_VARIANT(4, 4, 1, 256, 2, 2, true, 2),    // 21
-    VU_VARIANT(4, 4, 2, 256, 2, 2, true, 2),    // 22
-    VU_VARIANT(4, 1, 1, 256, 2, 4, true, 2),    // 23
-    VU_VARIANT(4, 1, 2, 256, 2, 4, true, 2),    // 24
+    VU_VARIANT(3, 4, 1, 256, 2, 2, 0, 2),    // 18
+    VU_VARIANT(3, 4, 2, 256, 2, 2, 0, 2),    // 19
+    VU_VARIANT(3, 1, 1, 256, 2, 4, 0, 2),    // 20
+    VU_VARIANT(3, 1, 2, 256, 2, 4, 0, 2),    // 21
+    VU_VARIANT(4, 4, 1, 256, 2, 2, 0, 2),    // 22
+    VU_VARIANT(4, 4, 2, 256, 2, 2, 0, 2),    // 23
+    VU_VARIANT(4, 1, 1, 256, 2, 4, 0, 2),    // 24
+    VU_VARIANT(4, 1, 2, 256, 2, 4, 0, 2),    // 25
 };
 static const int kNumFast = (int)(sizeof(kFast) / sizeof(kFast[0]));
 

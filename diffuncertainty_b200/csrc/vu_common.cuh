@@ -75,28 +75,63 @@ struct VecLoad<1> {
     __device__ __forceinline__ static void store_u8(uint8_t* p, const int (&l)[1]) { *p = (uint8_t)l[0]; }
 };
 
+// ---- packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE fp32 lanes per instruction) -------------
+// The streaming loop is bound by instruction issue as much as by HBM, so every elementwise step that can
+// be done on two voxels (or two classes) at once is.  Each lane rounds exactly like the scalar op.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 // ---- p * log2(p) with the reference's skip rule ---------------------------
 // test_utils.py:838-840 / 849-851 drop every NaN product, i.e. the term is
-// p*log(p) for p > 0 and 0 for p == 0, p < 0 and NaN.  One MUFU.LG2 per
-// element; its absolute error (~2^-23.5 on [0.5, 2], measured on B200) is too
-// large next to p = 1 (confident pixels: the term is ~ -(1-p)), so within
-// |p-1| < 1/16 log2(p) = f * q(f), f = p - 1, with q the degree-4 near-minimax
-// fit of log2(1+f)/f on [-1/16, 1/16] (relative error of p*log2(p) < 1.8e-7
-// over every float in the window; outside it MUFU.LG2 stays below 1e-6).
-// Subnormal p (< FLT_MIN) is treated as 0: its true term is < 1.1e-36.
+// p*log(p) for p > 0 and 0 for p == 0, p < 0 and NaN (+inf is kept).  The term is
+// formed as  max(p, 0) * L(p)  with  L(p) = log2(max(p, FLT_MIN)):
+//   p <= 0, NaN  -> 0 * (-126) = 0          (fmaxf returns the non-NaN operand)
+//   subnormal p  -> p * (-126): off by < 2e-37 from the true term
+//   +inf         -> inf
+// L is one MUFU.LG2, whose absolute error (~2^-23.5 on [0.5, 2], measured on B200)
+// is too large next to p = 1 (confident pixels: the term is ~ -(1-p)); within
+// |p-1| < 1/16, L = f * q(f), f = p - 1, q = degree-3 near-minimax fit of
+// log2(1+f)/f on [-1/16, 1/16].  Relative error of the term: < 6e-7 inside the
+// window (checked over every float in it), < 1e-6 outside.
 // Result is in log2 units; callers multiply the class sum by ln 2 once.
-__device__ __forceinline__ float plog2p(float p) {
+constexpr float kQ0 = 1.4426945447921753f, kQ1 = -0.7213456630706787f, kQ2 = 0.48202842473983765f, kQ3 = -0.36208757758140564f;
+constexpr float kNearOne = 1.0f / 16.0f;
+
+__device__ __forceinline__ float lg2_clamped(float p) {
     float lg;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(p));
-    const float f = p - 1.0f;
-    float t = fmaf(f, 0.28995341062545776f, -0.36185145378112793f);
-    t = fmaf(t, f, 0.4808957874774933f);
-    t = fmaf(t, f, -0.721346378326416f);
-    t = fmaf(t, f, 1.4426950216293335f);
-    const float near_one = t * f;
-    const float l = (fabsf(f) < (1.0f / 16.0f)) ? near_one : lg;
-    const float term = __fmul_rn(p, l);  // never contracted into the caller's add: all kernels agree bitwise
-    return (p >= FLT_MIN) ? term : 0.0f;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(fmaxf(p, FLT_MIN)));
+    return lg;
+}
+// scalar: h + max(p,0) * L(p), one fused multiply-add (all kernels use this same operation order)
+__device__ __forceinline__ float plog2p_acc(float h, float p) {
+    const float lg = lg2_clamped(p);
+    const float f = __fadd_rn(p, -1.0f);
+    float t = __fmaf_rn(f, kQ3, kQ2);
+    t = __fmaf_rn(t, f, kQ1);
+    t = __fmaf_rn(t, f, kQ0);
+    const float near_one = __fmul_rn(t, f);
+    const float l = (fabsf(f) < kNearOne) ? near_one : lg;
+    return __fmaf_rn(fmaxf(p, 0.0f), l, h);
+}
+// two elements at once: returns (max(p,0), L(p)) for both, the polynomial evaluated with packed ops
+__device__ __forceinline__ void plog2p_parts2(f32x2 P, f32x2& PC, f32x2& L) {
+    float p0, p1;
+    upk2(P, p0, p1);
+    const float lg0 = lg2_clamped(p0), lg1 = lg2_clamped(p1);
+    const f32x2 F = add2(P, pk2(-1.0f, -1.0f));
+    f32x2 T = fma2(F, pk2(kQ3, kQ3), pk2(kQ2, kQ2));
+    T = fma2(T, F, pk2(kQ1, kQ1));
+    T = fma2(T, F, pk2(kQ0, kQ0));
+    const f32x2 N = mul2(T, F);
+    float f0, f1, n0, n1;
+    upk2(F, f0, f1);
+    upk2(N, n0, n1);
+    L = pk2((fabsf(f0) < kNearOne) ? n0 : lg0, (fabsf(f1) < kNearOne) ? n1 : lg1);
+    PC = pk2(fmaxf(p0, 0.0f), fmaxf(p1, 0.0f));
 }
 
 // torch.argmax tie rule (test_2D.py:817,871): first maximal index, NaN is max.
@@ -184,40 +219,45 @@ struct StatParams {
 // ---- per-CTA statistics state (dynamic shared memory) ---------------------------
 // Every thread owns one private column of float64 / packed-integer accumulators
 // ("slots", layout [slot][thread]: conflict-free, no atomics, no shuffles while
-// streaming).  The calibration histograms are one CTA-wide copy with 32 replicas,
-// one per lane ([unc][bin][lane]: a warp's 32 adds never share an address or a
-// bank, whatever the bins are), updated with native 32-bit shared-memory atomic
-// adds (warps share the replicas).  flush() folds
-// everything into the image's row of the global statistics buffers with one
-// atomic per non-zero column; it runs when a CTA moves on to another image.
+// streaming).  The calibration histograms are private to a warp and replicated
+// 16 times ([unc][bin][lane & 15], one 64-bit word each): the two half-warps
+// update them one after the other with plain load / add / store -- inside a
+// half-warp every lane has its own replica, so there are no conflicts whatever
+// the bins are, and no atomics (a shared-memory atomic costs ~64 cycles per warp
+// on this part).  flush() folds everything into the image's row of the global
+// statistics buffers with one atomic per non-zero column; it runs when a CTA
+// moves on to another image, and at least every kMaxTilesPerFlush tiles so that
+// the packed counters cannot overflow.
 //
 // float64 slots                       packed-integer slots (uint64)
 //   0..2   sum of u_k                   0      #(u_k >= t_k), 3 x 21 bit
 //   3..5   sum of u_k over u_k >= t_k   1      #(label > 0)
-//   6..8   sum of conf in bin 0         2+r    rater r: tp | pred << 21 | gt << 42
-//   9      sum g        10  sum g*g
+//   6..8   sum of conf in bin 0         2, 3   samples / correct samples with NaN u_k (bin slot 20), 3 x 21 bit
+//   9      sum g        10  sum g*g     4+r    rater r: tp | pred << 21 | gt << 42
 //   11..13 sum u_k^2    14..16  sum g*u_k
+// histogram word (bins 0..19): x = samples | correct << 16,  y = sum of q * n_valid,
+//   q = round((conf - bin * 0.05) * 2^21)   (bin 0 is also summed in floating point, slots 6..8)
 enum { FS_SUM = 0, FS_THR = 3, FS_BIN0 = 6, FS_G = 9, FS_GG = 10, FS_UU = 11, FS_GU = 14, FS_MAX = 17 };
-enum { IS_THRCNT = 0, IS_AREA = 1, IS_DICE = 2, IS_MAX = 2 + VU_MAX_RATERS };
+enum { IS_THRCNT = 0, IS_AREA = 1, IS_NANTOT = 2, IS_NANTRU = 3, IS_DICE = 4, IS_MAX = 4 + VU_MAX_RATERS };
 constexpr int kPackBits = 21;
 constexpr unsigned long long kPackMask = (1ull << kPackBits) - 1;
-constexpr long long kMaxTilesPerFlush = 1LL << 13;  // bounds every packed / 32-bit counter between two flushes
-constexpr int kQBits = 24;                           // fixed point of (conf - bin * 0.05): |q| < 2^20, x n_valid <= 8
-constexpr int kQSplit = 12;                          // q is accumulated as (q >> 12, q & 0xfff) in two 32-bit words
-constexpr int kEdgePad = 24;                         // E[0] = NaN, E[1..19] = edges, E[20..23] = NaN
-
-// histogram words: [4 planes: total, true, q_hi, q_lo][VU_N_UNC][VU_N_BINS][32 lanes] int32
-constexpr int kHistPlane = VU_N_UNC * VU_N_BINS * 32;
-constexpr int kHistWords = 4 * kHistPlane;
+constexpr int kMaxTilesPerFlush = 256;  // x VEC <= 4 voxels x 2 lanes per replica x n_valid <= 8: 16-bit counts and 32-bit q sums hold
+constexpr int kQBits = 21;
+constexpr int kHistBins = VU_N_BINS - 1;  // 20 real bins; slot 20 (NaN) is counted in the integer slots
+constexpr int kHistRep = 16;
+constexpr int kHistWordsPerWarp = VU_N_UNC * kHistBins * kHistRep;  // uint2 words
+constexpr int kEdgePad = 24;  // E[0] = NaN, E[1..19] = edges, E[20..23] = NaN
 
 __host__ __device__ inline int stats_num_fslots(unsigned flags) {
     return (flags & VU_STAT_NCC) ? FS_MAX : ((flags & VU_STAT_CALIB) ? FS_G : FS_BIN0);
 }
-__host__ __device__ inline int stats_num_islots(unsigned flags, int R) { return (flags & VU_STAT_DICE) ? IS_DICE + R : IS_DICE; }
+__host__ __device__ inline int stats_num_islots(unsigned flags, int R) {
+    return (flags & VU_STAT_DICE) ? IS_DICE + R : ((flags & VU_STAT_CALIB) ? IS_DICE : IS_NANTOT);
+}
 __host__ __device__ inline size_t stats_smem_bytes(unsigned flags, int R, int threads) {
     if (!flags) return 0;
     size_t n = (size_t)(stats_num_fslots(flags) + stats_num_islots(flags, R)) * threads * 8;
-    if (flags & VU_STAT_CALIB) n += (size_t)kHistWords * sizeof(int) + (size_t)VU_N_UNC * kEdgePad * sizeof(float);
+    if (flags & VU_STAT_CALIB) n += (size_t)(threads / 32) * kHistWordsPerWarp * sizeof(uint2) + (size_t)VU_N_UNC * kEdgePad * sizeof(float);
     return n;
 }
 
@@ -225,7 +265,7 @@ template <int THREADS>
 struct StatsLayout {
     double* fs;
     unsigned long long* is;
-    int* hist;
+    uint2* hist;  // [warp][unc][bin][replica]
     float* E;
     int nF, nI;
     __device__ __forceinline__ StatsLayout(const StatParams& sp, void* smem) {
@@ -233,8 +273,8 @@ struct StatsLayout {
         nI = stats_num_islots(sp.flags, sp.gt.R);
         fs = reinterpret_cast<double*>(smem);
         is = reinterpret_cast<unsigned long long*>(fs + (size_t)nF * THREADS);
-        hist = reinterpret_cast<int*>(is + (size_t)nI * THREADS);
-        E = reinterpret_cast<float*>(hist + kHistWords);
+        hist = reinterpret_cast<uint2*>(is + (size_t)nI * THREADS);
+        E = reinterpret_cast<float*>(hist + (THREADS / 32) * kHistWordsPerWarp);
     }
 };
 
@@ -243,7 +283,7 @@ __device__ __noinline__ void stats_init(const StatParams& sp, void* smem) {
     StatsLayout<THREADS> L(sp, smem);
     for (int t = threadIdx.x; t < (L.nF + L.nI) * THREADS; t += THREADS) reinterpret_cast<unsigned long long*>(smem)[t] = 0ull;
     if (sp.flags & VU_STAT_CALIB) {
-        for (int t = threadIdx.x; t < kHistWords; t += THREADS) L.hist[t] = 0;
+        for (int t = threadIdx.x; t < (THREADS / 32) * kHistWordsPerWarp; t += THREADS) L.hist[t] = make_uint2(0u, 0u);
         for (int t = threadIdx.x; t < VU_N_UNC * kEdgePad; t += THREADS) {
             const int k = t / kEdgePad, e = t % kEdgePad;
             L.E[t] = (e >= 1 && e <= VU_N_EDGES) ? sp.calib[k].edge[e - 1] : __int_as_float(0x7fc00000);
@@ -297,6 +337,15 @@ __device__ __noinline__ void stats_flush(const StatParams& sp, void* smem, long 
                 if (f2) atomicAdd(irow + VU_I64_THR_COUNT + 2, f2);
             } else if (q == IS_AREA) {
                 if (f0) atomicAdd(irow + VU_I64_AREA, f0);
+            } else if (q == IS_NANTOT || q == IS_NANTRU) {
+                // np.digitize sends NaN confidences past the last edge: slot 20, whose sum of confidences is NaN
+                const int col = (q == IS_NANTOT ? VU_I64_BIN_TOTAL : VU_I64_BIN_TRUE) + (VU_N_BINS - 1);
+                const unsigned long long f[3] = {f0, f1, f2};
+                for (int k = 0; k < VU_N_UNC; ++k)
+                    if (f[k]) {
+                        atomicAdd(irow + col + k * VU_N_BINS, f[k]);
+                        if (q == IS_NANTOT) atomicAdd(frow + VU_F64_BIN_SUMS + k * VU_N_BINS + (VU_N_BINS - 1), (double)__int_as_float(0x7fc00000));
+                    }
             } else {
                 const int r = q - IS_DICE;
                 if (f0) atomicAdd(irow + VU_I64_DICE_TP + r, f0);
@@ -306,24 +355,38 @@ __device__ __noinline__ void stats_flush(const StatParams& sp, void* smem, long 
         }
     }
     if (flags & VU_STAT_CALIB) {
-        for (int t = threadIdx.x; t < VU_N_UNC * VU_N_BINS; t += THREADS) {
-            const int k = t / VU_N_BINS, bin = t % VU_N_BINS;
+        // 4 adjacent threads fold one (unc, bin): each takes a quarter of its WARPS x 16 replica words
+        constexpr int kItems = VU_N_UNC * kHistBins * 4;
+        constexpr int kPer = WARPS * kHistRep / 4;
+        for (int base = 0; base < ((kItems + THREADS - 1) / THREADS) * THREADS; base += THREADS) {
+            const int item = base + threadIdx.x;
+            const int pair = item >> 2, part = item & 3;
             long long tot = 0, tru = 0, q = 0;
-            int* h = L.hist + t * 32;
-            for (int i = 0; i < 32; ++i) {
-                const int r = (i + threadIdx.x) & 31;  // skewed: the threads of a warp read different banks
-                tot += h[r]; tru += h[kHistPlane + r];
-                q += (long long)h[2 * kHistPlane + r] * (1 << kQSplit) + h[3 * kHistPlane + r];
-                h[r] = 0; h[kHistPlane + r] = 0; h[2 * kHistPlane + r] = 0; h[3 * kHistPlane + r] = 0;
+            if (pair < VU_N_UNC * kHistBins) {
+                for (int i = 0; i < kPer; ++i) {
+                    const int e = part * kPer + i;
+                    const int w = e / kHistRep, rep = (e + pair) & (kHistRep - 1);  // skewed: neighbours read different banks
+                    uint2* h = L.hist + w * kHistWordsPerWarp + pair * kHistRep + rep;
+                    const uint2 v = *h;
+                    *h = make_uint2(0u, 0u);
+                    tot += v.x & 0xffffu;
+                    tru += v.x >> 16;
+                    q += (int)v.y;
+                }
             }
-            if (tot) {
-                atomicAdd(irow + VU_I64_BIN_TOTAL + t, (unsigned long long)tot);
-                if (tru) atomicAdd(irow + VU_I64_BIN_TRUE + t, (unsigned long long)tru);
-                // bin 0 is summed in floating point by the threads (slots FS_BIN0); slot 20 only ever holds NaN
-                // confidences (np.digitize sends NaN past the last edge), whose sum is NaN
-                if (bin == VU_N_BINS - 1) atomicAdd(frow + VU_F64_BIN_SUMS + t, (double)__int_as_float(0x7fc00000));
-                else if (bin > 0)
-                    atomicAdd(frow + VU_F64_BIN_SUMS + t,
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                tot += __shfl_xor_sync(kFull, tot, o);
+                tru += __shfl_xor_sync(kFull, tru, o);
+                q += __shfl_xor_sync(kFull, q, o);
+            }
+            if (part == 0 && pair < VU_N_UNC * kHistBins && tot) {
+                const int k = pair / kHistBins, bin = pair % kHistBins;
+                const int col = k * VU_N_BINS + bin;
+                atomicAdd(irow + VU_I64_BIN_TOTAL + col, (unsigned long long)tot);
+                if (tru) atomicAdd(irow + VU_I64_BIN_TRUE + col, (unsigned long long)tru);
+                if (bin > 0)  // bin 0 is summed in floating point by the threads (slots FS_BIN0)
+                    atomicAdd(frow + VU_F64_BIN_SUMS + col,
                               (double)tot * (double)((float)bin * 0.05f) + (double)q * (1.0 / (double)(1 << kQBits)));
             }
         }
@@ -339,7 +402,7 @@ struct StatsCursor {
     __device__ __forceinline__ StatsCursor() : cur_b(-1), vt_begin(0) {}
     // top of every tile: tile index vt inside image b, tile_vox voxels per tile
     __device__ __forceinline__ void enter(const StatParams& sp, void* smem, int b, int vt, long long tile_vox) {
-        if (b != cur_b || vt - vt_begin >= (int)kMaxTilesPerFlush) {
+        if (b != cur_b || vt - vt_begin >= kMaxTilesPerFlush) {
             if (cur_b >= 0) {
                 const long long end = (b != cur_b) ? sp.V : (long long)vt * tile_vox;
                 stats_flush<THREADS>(sp, smem, cur_b, end - (long long)vt_begin * tile_vox);
@@ -357,6 +420,16 @@ struct StatsCursor {
         }
     }
 };
+
+// Pull the references of a tile towards the SM while the slab is still streaming (L1 is otherwise unused:
+// the slab is read with no-allocate loads), so that the statistics phase does not wait on HBM.
+template <int VEC>
+__device__ __forceinline__ void stats_prefetch_gt(const StatParams& sp, long long b, long long v) {
+    if (!(sp.flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC)) || !sp.gt.data) return;
+    const long long esz = sp.gt.dtype == VU_GT_U8 ? 1 : 8;
+    const char* base = reinterpret_cast<const char*>(sp.gt.data) + (b * sp.gt.sb + v * sp.gt.sv) * esz;
+    for (int r = 0; r < sp.gt.R; ++r) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (long long)r * sp.gt.sr * esz));
+}
 
 // ace.py:329 in float32: 1 / (1 + exp((-u) * a + b)); ace.py:333 clips to [0, 1].  Bins are decided on u
 // itself (calib_bin), so this value only feeds the floating bin_sums: fast exp / reciprocal are enough.
@@ -379,10 +452,6 @@ __device__ __forceinline__ int calib_bin(const float* E, int increasing, float u
     return k0 + (uu >= e_hi ? 1 : 0) - (uu < e_lo ? 1 : 0);
 }
 
-// The whole statistics phase for the VEC voxels a thread owns in one tile.  Must
-// be called by every thread of the CTA (threads past the end of the image pass
-// active = false).  Kept out of line so its registers do not inflate the
-// streaming loop of the calling kernel.
 template <int VEC> struct FVec;
 template <> struct FVec<4> { typedef float4 type; };
 template <> struct FVec<2> { typedef float2 type; };
@@ -394,11 +463,18 @@ __device__ __forceinline__ void fvec_unpack(float4 v, float (&x)[4]) { x[0] = v.
 __device__ __forceinline__ void fvec_unpack(float2 v, float (&x)[2]) { x[0] = v.x; x[1] = v.y; }
 __device__ __forceinline__ void fvec_unpack(float v, float (&x)[1]) { x[0] = v; }
 
-// (arguments travel in registers: the three maps as built-in vectors, the VEC labels packed into one word)
+// The whole statistics phase for the VEC voxels a thread owns in one tile.  Must
+// be called by every thread of the CTA (threads past the end of the image pass
+// active = false).  Kept out of line so its registers do not inflate the
+// streaming loop of the calling kernel; arguments travel in registers (the three
+// maps as built-in vectors, the VEC labels packed into one word).
 template <int VEC, int THREADS, typename GT>
 __device__ __noinline__ void stats_tile_t(const StatParams& sp, void* smem, bool active, long long b, long long v,
                                           typename FVec<VEC>::type u0, typename FVec<VEC>::type u1,
                                           typename FVec<VEC>::type u2, unsigned labels_packed) {
+    using G = typename std::conditional<sizeof(GT) == 1, int, long long>::type;
+    using GAcc = typename std::conditional<sizeof(GT) == 1, int, double>::type;
+    constexpr int RB = sizeof(GT) == 1 ? 4 : (VEC == 4 ? 1 : 2);  // raters fetched together
     StatsLayout<THREADS> cs(sp, smem);
     float u[VU_N_UNC][VEC];
     int label[VEC];
@@ -407,8 +483,6 @@ __device__ __noinline__ void stats_tile_t(const StatParams& sp, void* smem, bool
     fvec_unpack(u2, u[2]);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) label[j] = (int)((labels_packed >> (8 * j)) & 0xffu);
-    using G = typename std::conditional<sizeof(GT) == 1, int, long long>::type;
-    using GAcc = typename std::conditional<sizeof(GT) == 1, int, double>::type;
     const unsigned flags = sp.flags, mask = sp.unc_mask;
     const int tid = threadIdx.x, lane = tid & 31;
 
@@ -460,23 +534,30 @@ __device__ __noinline__ void stats_tile_t(const StatParams& sp, void* smem, bool
         const bool has_ign = sp.gt.has_ignore != 0;
         const G ign = (G)sp.gt.ignore;
 #pragma unroll 1
-        for (int r = 0; r < R; ++r) {
-            G g[VEC];
-            load_gt<VEC>(sp.gt, b, r, v, g, GT());
-            int tp = 0, ps = 0, gs = 0;
+        for (int r0 = 0; r0 < R; r0 += RB) {
+            G g[RB][VEC];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const bool valid = !(has_ign && g[j] == ign);     // ace.py:492-499, test_2D.py:880
-                const bool pp = (label[j] == 1) && valid, gp = (g[j] == (G)1) && valid;  // test_2D.py:878-886
-                tp += (pp && gp); ps += pp; gs += gp;
-                n_valid[j] += valid;
-                n_correct[j] += (valid && g[j] == cmp[j]);       // ace.py:488
-                gsum[j] += (GAcc)g[j];
-                gsq[j] += (GAcc)g[j] * (GAcc)g[j];
+            for (int i = 0; i < RB; ++i)
+                if (r0 + i < R) load_gt<VEC>(sp.gt, b, r0 + i, v, g[i], GT());
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                if (r0 + i >= R) break;
+                int tp = 0, ps = 0, gs = 0;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const G gj = g[i][j];
+                    const bool valid = !(has_ign && gj == ign);                              // ace.py:492-499, test_2D.py:880
+                    const bool pp = (label[j] == 1) && valid, gp = (gj == (G)1) && valid;  // test_2D.py:878-886
+                    tp += (pp && gp); ps += pp; gs += gp;
+                    n_valid[j] += valid;
+                    n_correct[j] += (valid && gj == cmp[j]);                                 // ace.py:488
+                    gsum[j] += (GAcc)gj;
+                    gsq[j] += (GAcc)gj * (GAcc)gj;
+                }
+                if ((flags & VU_STAT_DICE) && (tp | ps | gs))
+                    cs.is[(IS_DICE + r0 + i) * THREADS + tid] +=
+                        (unsigned long long)tp | ((unsigned long long)ps << kPackBits) | ((unsigned long long)gs << (2 * kPackBits));
             }
-            if ((flags & VU_STAT_DICE) && (tp | ps | gs))
-                cs.is[(IS_DICE + r) * THREADS + tid] +=
-                    (unsigned long long)tp | ((unsigned long long)ps << kPackBits) | ((unsigned long long)gs << (2 * kPackBits));
         }
     }
     if (active && (flags & VU_STAT_NCC)) {
@@ -511,35 +592,45 @@ __device__ __noinline__ void stats_tile_t(const StatParams& sp, void* smem, bool
                 cs.fs[(FS_GU + k) * THREADS + tid] += sgu[k];
             }
     }
-    if (flags & VU_STAT_CALIB) {
+    if (flags & VU_STAT_CALIB) {  // every lane of the warp walks through here: the half-warp phases are warp-synchronous
+        uint2* hw = cs.hist + (tid >> 5) * kHistWordsPerWarp + (lane & (kHistRep - 1));
+        const bool upper = lane >= kHistRep;
+        unsigned long long nan_tot = 0, nan_tru = 0;
 #pragma unroll
         for (int k = 0; k < VU_N_UNC; ++k) {
             if (!((mask >> k) & 1)) continue;
             float bin0 = 0.f;
             const CalibDev& cal = sp.calib[k];
             const float* E = cs.E + k * kEdgePad;
-            int* hk = cs.hist + k * (VU_N_BINS * 32) + lane;
+            uint2* hk = hw + k * (kHistBins * kHistRep);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 const int nv = n_valid[j];
-                if (active && nv > 0) {
+                bool hit = active && nv > 0;
+                int bin = 0, q = 0;
+                if (hit) {
                     const float x = u[k][j];
-                    int bin = VU_N_BINS - 1, q = 0;  // np.digitize puts NaN past the last edge
-                    if (x == x) {
+                    if (x != x) {
+                        hit = false;
+                        nan_tot += (unsigned long long)nv << (k * kPackBits);
+                        nan_tru += (unsigned long long)n_correct[j] << (k * kPackBits);
+                    } else {
                         const float conf = platt_conf(x, cal.a, cal.b, cal.identity);
                         bin = calib_bin(E, cal.increasing, x, conf);
                         q = __float2int_rn((conf - (float)bin * 0.05f) * (float)(1 << kQBits)) * nv;
                         bin0 += bin == 0 ? conf * (float)nv : 0.f;
                     }
-                    int* h = hk + bin * 32;
-                    atomicAdd(h, nv);
-                    if (n_correct[j]) atomicAdd(h + kHistPlane, n_correct[j]);
-                    atomicAdd(h + 2 * kHistPlane, q >> kQSplit);
-                    atomicAdd(h + 3 * kHistPlane, q & ((1 << kQSplit) - 1));
                 }
+                const unsigned inc = (unsigned)nv | ((unsigned)n_correct[j] << 16);
+                uint2* h = hk + bin * kHistRep;
+                if (hit && !upper) { uint2 w = *h; w.x += inc; w.y += (unsigned)q; *h = w; }
+                __syncwarp();
+                if (hit && upper) { uint2 w = *h; w.x += inc; w.y += (unsigned)q; *h = w; }
+                __syncwarp();
             }
             if (bin0 != 0.f) cs.fs[(FS_BIN0 + k) * THREADS + tid] += (double)bin0;
         }
+        if (nan_tot) { cs.is[IS_NANTOT * THREADS + tid] += nan_tot; cs.is[IS_NANTRU * THREADS + tid] += nan_tru; }
     }
 }
 
