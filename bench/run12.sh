@@ -1,0 +1,2 @@
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -30 > gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log
+timeout 600 python bench/sweep_tma.py --stages 0 --flags 0x0,0x07,0x1f,0x3f > gpurun_out/sweep_tma.log 2>&1; cat gpurun_out/sweep_tma.log

@@ -261,6 +261,7 @@ int vu_set_option(const char* key, int64_t value) {
 int64_t vu_get_counter(const char* key) {
     if (!key) return -1;
     if (strcmp(key, "k1_num_variants") == 0) return num_fast_variants();
+    if (strcmp(key, "k1_num_tma_variants") == 0) return num_tma_variants();
     if (strncmp(key, "k1_variant.", 11) == 0) {  // "k1_variant.<i>.<field 0..6>"
         int i = 0, f = 0;
         if (sscanf(key + 11, "%d.%d", &i, &f) != 2 || f < 0 || f > 6) return -1;

@@ -9,7 +9,7 @@
 // :871 (argmax), unc_mod_utils/test_utils.py:833-864 (uncertainty measures),
 // evaluation/uncertainty_aggregation/aggregate_uncertainties.py:37-39,124-125,
 // evaluation/metrics/ace.py:350-356, evaluation/metrics/ncc.py:17-27.
-#include "vu_common.cuh"
+#include "k1_core.cuh"
 #include "vu_host.h"
 
 namespace vu {
@@ -55,16 +55,19 @@ struct PairLoad<2> {
         asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(x[0]) : "l"(p));
     }
 };
+template <>
+struct PairLoad<1> {  // never called (VEC == 1 pairs classes from scalar loads); keeps the dead branch well-formed
+    __device__ __forceinline__ static void load(const float*, f32x2*) {}
+};
 
 template <int C, int VEC, int LEVELS, int THREADS, int MINB, int G, bool STATS>
 __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__ K1Params prm) {
     constexpr bool do_stats = STATS;
     constexpr long long kTileVox = (long long)THREADS * VEC;
-    constexpr int E = C * VEC;       // values of one member owned by a thread, flattened [class][voxel]
-    constexpr int NP = E / 2;        // packed pairs
-    constexpr bool ODD = (E & 1);    // VEC == 1 and C odd: the last class is handled in scalar code
-    constexpr int NH = VEC >= 2 ? VEC / 2 : 1;
-    constexpr int NP1 = LEVELS > 1 ? NP : 1;
+    using Acc = VoxelAcc<C, VEC, LEVELS>;
+    constexpr int NP = Acc::NP, NH = Acc::NH;
+    constexpr bool ODD = Acc::ODD;
+    constexpr int PF = (C * VEC >= 16) ? 1 : (16 / (C * VEC));  // members of the next tile prefetched into L2
     StatsCursor<THREADS> cursor;
     if (do_stats) stats_init<THREADS>(prm.st, vu_dyn_smem);
 
@@ -88,28 +91,21 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__
 
         if (active) {
             if (do_stats) stats_prefetch_gt<VEC>(prm.st, b, v);
-            f32x2 m0[NP > 0 ? NP : 1], m1[NP1 > 0 ? NP1 : 1];  // member sums, cascade level 0 / 1
-            float m0s = 0.f, m1s = 0.f;                          // scalar leftover class (ODD)
-            f32x2 a0[NH], a1[NH];                                // entropy sums (VEC >= 2: packed over voxels)
-            float a0s = 0.f, a1s = 0.f;                          // entropy sums (VEC == 1)
-#pragma unroll
-            for (int j = 0; j < NP; ++j) m0[j] = 0ull;
-#pragma unroll
-            for (int j = 0; j < NP1; ++j) m1[j] = 0ull;
-#pragma unroll
-            for (int q = 0; q < NH; ++q) { a0[q] = 0ull; a1[q] = 0ull; }
+            Acc acc;
+            acc.init();
             const float* row0 = prm.x + (long long)b * prm.sb + v;
 
-            f32x2 xp[G][NP > 0 ? NP : 1];
+            f32x2 xp[G][NP];
             float xs[G];
             for (long long p0 = 0; p0 < P; p0 += G) {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
+                    xs[g] = 0.f;
                     if (G == 1 || p0 + g < P) {
                         const float* r = row0 + (p0 + g) * prm.sp;
                         if constexpr (VEC >= 2) {
 #pragma unroll
-                            for (int c = 0; c < C; ++c) PairLoad<VEC >= 2 ? VEC : 2>::load(r + c * prm.sc, &xp[g][c * NH]);
+                            for (int c = 0; c < C; ++c) PairLoad<VEC>::load(r + c * prm.sc, &xp[g][c * NH]);
                         } else {
 #pragma unroll
                             for (int j = 0; j < NP; ++j) xp[g][j] = pk2(ldg_stream(r + (2 * j) * prm.sc), ldg_stream(r + (2 * j + 1) * prm.sc));
@@ -118,88 +114,27 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__
                     }
                 }
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    if (G == 1 || p0 + g < P) {
-                        if constexpr (VEC >= 2) {
-                            f32x2 h[NH];
+                for (int g = 0; g < G; ++g)
+                    if (G == 1 || p0 + g < P) acc.add_member(xp[g], xs[g], p0 + g);
+            }
+
+            // Pull the first members of the CTA's next tile into L2 while this tile's epilogue and statistics
+            // run: no loads of this warp are in flight during those phases otherwise.
+            if (PF > 0 && tile + 1 < t1) {
+                const bool wrap = (vt + 1 == tpi);
+                const long long nv = wrap ? (long long)threadIdx.x * VEC : v + kTileVox;
+                if (nv < V) {
+                    const float* nrow = prm.x + (long long)(wrap ? b + 1 : b) * prm.sb + nv;
 #pragma unroll
-                            for (int q = 0; q < NH; ++q) h[q] = 0ull;
+                    for (int g = 0; g < PF; ++g)
+                        if (g < P) {
 #pragma unroll
-                            for (int c = 0; c < C; ++c) {
-#pragma unroll
-                                for (int q = 0; q < NH; ++q) {
-                                    const f32x2 X = xp[g][c * NH + q];
-                                    m0[c * NH + q] = add2(m0[c * NH + q], X);
-                                    f32x2 PC, L;
-                                    plog2p_parts2(X, PC, L);
-                                    h[q] = fma2(PC, L, h[q]);
-                                }
-                            }
-#pragma unroll
-                            for (int q = 0; q < NH; ++q) a0[q] = add2(a0[q], h[q]);
-                        } else {
-                            float h = 0.f;
-#pragma unroll
-                            for (int j = 0; j < NP; ++j) {
-                                const f32x2 X = xp[g][j];
-                                m0[j] = add2(m0[j], X);
-                                f32x2 PC, L;
-                                plog2p_parts2(X, PC, L);
-                                float pc0, pc1, l0, l1;
-                                upk2(PC, pc0, pc1);
-                                upk2(L, l0, l1);
-                                h = __fmaf_rn(pc0, l0, h);
-                                h = __fmaf_rn(pc1, l1, h);
-                            }
-                            if constexpr (ODD) { m0s = __fadd_rn(m0s, xs[g]); h = plog2p_acc(h, xs[g]); }
-                            a0s = __fadd_rn(a0s, h);
+                            for (int c = 0; c < C; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + g * prm.sp + c * prm.sc));
                         }
-                        if (LEVELS > 1 && (((p0 + g) & 15) == 15)) {
-#pragma unroll
-                            for (int j = 0; j < NP1; ++j) { m1[j] = add2(m1[j], m0[j]); m0[j] = 0ull; }
-#pragma unroll
-                            for (int q = 0; q < NH; ++q) { a1[q] = add2(a1[q], a0[q]); a0[q] = 0ull; }
-                            m1s = __fadd_rn(m1s, m0s); m0s = 0.f;
-                            a1s = __fadd_rn(a1s, a0s); a0s = 0.f;
-                        }
-                    }
                 }
             }
 
-            // epilogue: mean (true division, test_2D.py:971), label, TU, AU, EU
-            float mean[C][VEC], asum[VEC];
-#pragma unroll
-            for (int e = 0; e < NP; ++e) {
-                const f32x2 S = (LEVELS > 1) ? add2(m0[e], m1[e]) : m0[e];
-                float s0, s1;
-                upk2(S, s0, s1);
-                mean[(2 * e) / VEC][(2 * e) % VEC] = __fdiv_rn(s0, Pf);
-                mean[(2 * e + 1) / VEC][(2 * e + 1) % VEC] = __fdiv_rn(s1, Pf);
-            }
-            if constexpr (ODD) mean[C - 1][0] = __fdiv_rn((LEVELS > 1) ? __fadd_rn(m0s, m1s) : m0s, Pf);
-            if constexpr (VEC >= 2) {
-#pragma unroll
-                for (int q = 0; q < NH; ++q) {
-                    const f32x2 A = (LEVELS > 1) ? add2(a0[q], a1[q]) : a0[q];
-                    upk2(A, asum[2 * q], asum[(2 * q + 1) % VEC]);
-                }
-            } else {
-                asum[0] = (LEVELS > 1) ? __fadd_rn(a0s, a1s) : a0s;
-            }
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                float best = mean[0][k], tu2 = 0.f;
-                int idx = 0;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    if (c > 0) argmax_step(mean[c][k], c, best, idx);
-                    tu2 = plog2p_acc(tu2, mean[c][k]);
-                }
-                const float tu = -(tu2 * kLn2);
-                const float au = (-(asum[k] * kLn2)) / Pf;
-                u[0][k] = tu; u[1][k] = au; u[2][k] = tu - au;
-                label[k] = idx;
-            }
+            acc.finish(Pf, u, label);
             const long long o = (long long)b * V + v;
             if (prm.tu) VecLoad<VEC>::store(prm.tu + o, u[0]);
             if (prm.au) VecLoad<VEC>::store(prm.au + o, u[1]);
@@ -329,34 +264,31 @@ struct FastVariant {
 // option selects another by index (used by the tuning sweep, bench/sweep_k1.py).
 static const FastVariant kFast[] = {
     // ---- C = 2 (LIDC-like, toy): few loads per member -> group members
-    VU_VARIANT(2, 4, 1, 256, 2, 8, 0, 0),    // 0
-    VU_VARIANT(2, 4, 2, 256, 2, 8, 0, 0),    // 1
+    VU_VARIANT(2, 4, 1, 256, 3, 4, 0, 0),    // 0
+    VU_VARIANT(2, 4, 2, 256, 3, 4, 0, 0),    // 1
     VU_VARIANT(2, 4, 1, 256, 2, 4, 0, 1),    // 2
     VU_VARIANT(2, 4, 2, 256, 2, 4, 0, 1),    // 3
-    VU_VARIANT(2, 4, 1, 256, 3, 4, 0, -1),   // 4
-    VU_VARIANT(2, 4, 2, 256, 3, 4, 0, -1),   // 5
+    VU_VARIANT(2, 4, 1, 256, 2, 8, 0, -1),   // 4
+    VU_VARIANT(2, 4, 2, 256, 2, 8, 0, -1),   // 5
     VU_VARIANT(2, 2, 1, 256, 2, 8, 0, 2),    // 6
     VU_VARIANT(2, 2, 2, 256, 2, 8, 0, 2),    // 7
     VU_VARIANT(2, 1, 1, 256, 2, 8, 0, 2),    // 8  (unaligned V)
     VU_VARIANT(2, 1, 2, 256, 2, 8, 0, 2),    // 9
     // ---- C = 19 (Cityscapes / GTA): 19 independent loads per member
-    VU_VARIANT(19, 1, 1, 256, 3, 1, 0, 2),   // 10
-    VU_VARIANT(19, 1, 2, 256, 2, 1, 0, 2),   // 11
-    VU_VARIANT(19, 2, 1, 256, 2, 1, 0, -1),  // 12
-    VU_VARIANT(19, 2, 2, 256, 1, 1, 0, -1),  // 13
-    VU_VARIANT(19, 1, 1, 256, 4, 1, 0, -1),  // 14
-    VU_VARIANT(19, 4, 1, 128, 2, 1, 0, -1),  // 15
-    VU_VARIANT(19, 1, 2, 256, 3, 1, 0, -1),  // 16
-    VU_VARIANT(19, 2, 1, 128, 4, 1, 0, -1),  // 17
+    VU_VARIANT(19, 2, 1, 256, 2, 1, 0, 2),   // 10
+    VU_VARIANT(19, 2, 2, 256, 1, 1, 0, 2),   // 11
+    VU_VARIANT(19, 1, 1, 256, 3, 1, 0, 2),   // 12 (unaligned V)
+    VU_VARIANT(19, 1, 2, 256, 2, 1, 0, 2),   // 13
+    VU_VARIANT(19, 2, 1, 128, 4, 1, 0, -1),  // 14
     // ---- small C
-    VU_VARIANT(3, 4, 1, 256, 2, 2, 0, 2),    // 18
-    VU_VARIANT(3, 4, 2, 256, 2, 2, 0, 2),    // 19
-    VU_VARIANT(3, 1, 1, 256, 2, 4, 0, 2),    // 20
-    VU_VARIANT(3, 1, 2, 256, 2, 4, 0, 2),    // 21
-    VU_VARIANT(4, 4, 1, 256, 2, 2, 0, 2),    // 22
-    VU_VARIANT(4, 4, 2, 256, 2, 2, 0, 2),    // 23
-    VU_VARIANT(4, 1, 1, 256, 2, 4, 0, 2),    // 24
-    VU_VARIANT(4, 1, 2, 256, 2, 4, 0, 2),    // 25
+    VU_VARIANT(3, 4, 1, 256, 2, 2, 0, 2),    // 15
+    VU_VARIANT(3, 4, 2, 256, 2, 2, 0, 2),    // 16
+    VU_VARIANT(3, 1, 1, 256, 2, 4, 0, 2),    // 17
+    VU_VARIANT(3, 1, 2, 256, 2, 4, 0, 2),    // 18
+    VU_VARIANT(4, 4, 1, 256, 2, 2, 0, 2),    // 19
+    VU_VARIANT(4, 4, 2, 256, 2, 2, 0, 2),    // 20
+    VU_VARIANT(4, 1, 1, 256, 2, 4, 0, 2),    // 21
+    VU_VARIANT(4, 1, 2, 256, 2, 4, 0, 2),    // 22
 };
 static const int kNumFast = (int)(sizeof(kFast) / sizeof(kFast[0]));
 
@@ -389,6 +321,13 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
 
     const int sms = device_sm_count();
     const long long forced = get_option("k1_variant", -1);
+    // preferred path: the TMA-pipelined kernel (k1_tma.cu); "k1_path" = 1 keeps to the register-streaming
+    // kernels, 2 insists on TMA
+    if (forced == -1) {
+        const int rc = launch_k1_tma(a, st, stream);
+        if (rc <= 0) return rc;
+        if (get_option("k1_path", 0) == 2) return set_error(VU_ERR_UNSUPPORTED, "slab not eligible for the TMA path");
+    }
     const int need_levels = s.P <= 17 ? 1 : (s.P <= 271 ? 2 : 3);
 
     const FastVariant* pick = nullptr;

@@ -226,7 +226,7 @@ struct StatParams {
 // the bins are, and no atomics (a shared-memory atomic costs ~64 cycles per warp
 // on this part).  flush() folds everything into the image's row of the global
 // statistics buffers with one atomic per non-zero column; it runs when a CTA
-// moves on to another image, and at least every kMaxTilesPerFlush tiles so that
+// moves on to another image, and at least every kMaxVoxPerFlush voxels per thread so that
 // the packed counters cannot overflow.
 //
 // float64 slots                       packed-integer slots (uint64)
@@ -241,7 +241,8 @@ enum { FS_SUM = 0, FS_THR = 3, FS_BIN0 = 6, FS_G = 9, FS_GG = 10, FS_UU = 11, FS
 enum { IS_THRCNT = 0, IS_AREA = 1, IS_NANTOT = 2, IS_NANTRU = 3, IS_DICE = 4, IS_MAX = 4 + VU_MAX_RATERS };
 constexpr int kPackBits = 21;
 constexpr unsigned long long kPackMask = (1ull << kPackBits) - 1;
-constexpr int kMaxTilesPerFlush = 256;  // x VEC <= 4 voxels x 2 lanes per replica x n_valid <= 8: 16-bit counts and 32-bit q sums hold
+constexpr int kMaxVoxPerFlush = 1024;   // voxels per thread between flushes: x 2 lanes per replica x n_valid <= 8 keeps the
+                                        // 16-bit counts (<= 16384) and the 32-bit q sums (< 2^31) from overflowing
 constexpr int kQBits = 21;
 constexpr int kHistBins = VU_N_BINS - 1;  // 20 real bins; slot 20 (NaN) is counted in the integer slots
 constexpr int kHistRep = 16;
@@ -278,28 +279,36 @@ struct StatsLayout {
     }
 };
 
-template <int THREADS>
+// CTA-wide barrier over the THREADS statistics threads: the whole CTA (BAR == 0) or named barrier BAR for
+// kernels whose CTA holds other warps as well (the TMA producer warp)
+template <int THREADS, int BAR>
+__device__ __forceinline__ void stats_sync() {
+    if (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(THREADS) : "memory");
+}
+
+template <int THREADS, int BAR = 0, int TID0 = 0>
 __device__ __noinline__ void stats_init(const StatParams& sp, void* smem) {
     StatsLayout<THREADS> L(sp, smem);
-    for (int t = threadIdx.x; t < (L.nF + L.nI) * THREADS; t += THREADS) reinterpret_cast<unsigned long long*>(smem)[t] = 0ull;
+    for (int t = ((int)threadIdx.x - TID0); t < (L.nF + L.nI) * THREADS; t += THREADS) reinterpret_cast<unsigned long long*>(smem)[t] = 0ull;
     if (sp.flags & VU_STAT_CALIB) {
-        for (int t = threadIdx.x; t < (THREADS / 32) * kHistWordsPerWarp; t += THREADS) L.hist[t] = make_uint2(0u, 0u);
-        for (int t = threadIdx.x; t < VU_N_UNC * kEdgePad; t += THREADS) {
+        for (int t = ((int)threadIdx.x - TID0); t < (THREADS / 32) * kHistWordsPerWarp; t += THREADS) L.hist[t] = make_uint2(0u, 0u);
+        for (int t = ((int)threadIdx.x - TID0); t < VU_N_UNC * kEdgePad; t += THREADS) {
             const int k = t / kEdgePad, e = t % kEdgePad;
             L.E[t] = (e >= 1 && e <= VU_N_EDGES) ? sp.calib[k].edge[e - 1] : __int_as_float(0x7fc00000);
         }
     }
-    __syncthreads();
+    stats_sync<THREADS, BAR>();
 }
 
 // Add this CTA's partials into image row b and clear them.  nvox = voxels of image b
 // the CTA went through since the last flush.  Called by every thread of the CTA.
-template <int THREADS>
+template <int THREADS, int BAR = 0, int TID0 = 0>
 __device__ __noinline__ void stats_flush(const StatParams& sp, void* smem, long long b, long long nvox) {
-    __syncthreads();
+    stats_sync<THREADS, BAR>();
     StatsLayout<THREADS> L(sp, smem);
     constexpr int WARPS = THREADS / 32;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = ((int)threadIdx.x - TID0) >> 5, lane = ((int)threadIdx.x - TID0) & 31;
     const unsigned flags = sp.flags;
     double* frow = sp.f64 + b * VU_F64_COLS;
     unsigned long long* irow = reinterpret_cast<unsigned long long*>(sp.i64 + b * VU_I64_COLS);
@@ -359,7 +368,7 @@ __device__ __noinline__ void stats_flush(const StatParams& sp, void* smem, long 
         constexpr int kItems = VU_N_UNC * kHistBins * 4;
         constexpr int kPer = WARPS * kHistRep / 4;
         for (int base = 0; base < ((kItems + THREADS - 1) / THREADS) * THREADS; base += THREADS) {
-            const int item = base + threadIdx.x;
+            const int item = base + ((int)threadIdx.x - TID0);
             const int pair = item >> 2, part = item & 3;
             long long tot = 0, tru = 0, q = 0;
             if (pair < VU_N_UNC * kHistBins) {
@@ -391,8 +400,8 @@ __device__ __noinline__ void stats_flush(const StatParams& sp, void* smem, long 
             }
         }
     }
-    if (threadIdx.x == 0 && nvox) atomicAdd(irow + VU_I64_NVOX, (unsigned long long)nvox);
-    __syncthreads();
+    if (((int)threadIdx.x - TID0) == 0 && nvox) atomicAdd(irow + VU_I64_NVOX, (unsigned long long)nvox);
+    stats_sync<THREADS, BAR>();
 }
 
 // Tracks which image a CTA is working on and flushes when it moves on.  All members are CTA-uniform.
@@ -401,22 +410,24 @@ struct StatsCursor {
     int cur_b, vt_begin;
     __device__ __forceinline__ StatsCursor() : cur_b(-1), vt_begin(0) {}
     // top of every tile: tile index vt inside image b, tile_vox voxels per tile
+    template <int BAR = 0, int TID0 = 0>
     __device__ __forceinline__ void enter(const StatParams& sp, void* smem, int b, int vt, long long tile_vox) {
-        if (b != cur_b || vt - vt_begin >= kMaxTilesPerFlush) {
+        if (b != cur_b || (long long)(vt - vt_begin) * (tile_vox / THREADS) >= kMaxVoxPerFlush) {
             if (cur_b >= 0) {
                 const long long end = (b != cur_b) ? sp.V : (long long)vt * tile_vox;
-                stats_flush<THREADS>(sp, smem, cur_b, end - (long long)vt_begin * tile_vox);
+                stats_flush<THREADS, BAR, TID0>(sp, smem, cur_b, end - (long long)vt_begin * tile_vox);
             }
             cur_b = b;
             vt_begin = vt;
         }
     }
     // after the last tile (vt = its index inside the image)
+    template <int BAR = 0, int TID0 = 0>
     __device__ __forceinline__ void finish(const StatParams& sp, void* smem, int last_vt, long long tile_vox) {
         if (cur_b >= 0) {
             long long end = (long long)(last_vt + 1) * tile_vox;
             end = end > sp.V ? sp.V : end;
-            stats_flush<THREADS>(sp, smem, cur_b, end - (long long)vt_begin * tile_vox);
+            stats_flush<THREADS, BAR, TID0>(sp, smem, cur_b, end - (long long)vt_begin * tile_vox);
         }
     }
 };
@@ -468,8 +479,11 @@ __device__ __forceinline__ void fvec_unpack(float v, float (&x)[1]) { x[0] = v; 
 // active = false).  Kept out of line so its registers do not inflate the
 // streaming loop of the calling kernel; arguments travel in registers (the three
 // maps as built-in vectors, the VEC labels packed into one word).
-template <int VEC, int THREADS, typename GT>
-__device__ __noinline__ void stats_tile_t(const StatParams& sp, void* smem, bool active, long long b, long long v,
+#ifndef VU_STATS_INLINE
+#define VU_STATS_INLINE __forceinline__
+#endif
+template <int VEC, int THREADS, typename GT, int TID0 = 0>
+__device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, bool active, long long b, long long v,
                                           typename FVec<VEC>::type u0, typename FVec<VEC>::type u1,
                                           typename FVec<VEC>::type u2, unsigned labels_packed) {
     using G = typename std::conditional<sizeof(GT) == 1, int, long long>::type;
@@ -484,7 +498,7 @@ __device__ __noinline__ void stats_tile_t(const StatParams& sp, void* smem, bool
 #pragma unroll
     for (int j = 0; j < VEC; ++j) label[j] = (int)((labels_packed >> (8 * j)) & 0xffu);
     const unsigned flags = sp.flags, mask = sp.unc_mask;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = (int)threadIdx.x - TID0, lane = tid & 31;
 
     if (active && (flags & (VU_STAT_IMAGE_SUM | VU_STAT_NCC))) {
 #pragma unroll
@@ -634,16 +648,16 @@ __device__ __noinline__ void stats_tile_t(const StatParams& sp, void* smem, bool
     }
 }
 
-template <int VEC, int THREADS>
+template <int VEC, int THREADS, int TID0 = 0>
 __device__ __forceinline__ void stats_tile(const StatParams& sp, void* smem, bool active, long long b, long long v,
                                            const float (&u)[VU_N_UNC][VEC], const int (&label)[VEC]) {
     unsigned lp = 0;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) lp |= (unsigned)(label[j] & 0xff) << (8 * j);
     if (sp.gt.dtype == VU_GT_I64)
-        stats_tile_t<VEC, THREADS, long long>(sp, smem, active, b, v, fvec_pack(u[0]), fvec_pack(u[1]), fvec_pack(u[2]), lp);
+        stats_tile_t<VEC, THREADS, long long, TID0>(sp, smem, active, b, v, fvec_pack(u[0]), fvec_pack(u[1]), fvec_pack(u[2]), lp);
     else
-        stats_tile_t<VEC, THREADS, uint8_t>(sp, smem, active, b, v, fvec_pack(u[0]), fvec_pack(u[1]), fvec_pack(u[2]), lp);
+        stats_tile_t<VEC, THREADS, uint8_t, TID0>(sp, smem, active, b, v, fvec_pack(u[0]), fvec_pack(u[1]), fvec_pack(u[2]), lp);
 }
 
 }  // namespace vu
