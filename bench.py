@@ -219,7 +219,7 @@ def run_ours(args):
     rows_i = torch.zeros((B, I64["COLS"]), dtype=torch.int64, device=dev)
     k1_events = []
 
-    def step(timed: bool):
+    def step(timed: bool, collective: bool = True):
         rows_f.zero_()
         rows_i.zero_()
         if timed:
@@ -230,7 +230,7 @@ def run_ours(args):
         if timed:
             e1.record()
             k1_events.append((e0, e1))
-        if world > 1:
+        if world > 1 and collective:
             ibuf, fbuf = pack_partials(rows_f, rows_i, rank * B, world * B)
             exchange(ibuf, fbuf)
 
@@ -248,6 +248,7 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.3)
     launches0 = _lib.get_counter("launches")
+    tma0 = _lib.get_counter("launches.k1_tma")
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
     start.record()
@@ -256,13 +257,16 @@ def run_ours(args):
     end.record()
     fence()
     launches = _lib.get_counter("launches") - launches0
+    kernel_name = ("k1_tma (vu_fused_pass, TMA-pipelined, producer / consumer / statistics warps)"
+                   if _lib.get_counter("launches.k1_tma") - tma0 == launches else "k1_fast (vu_fused_pass, register-streaming)")
     ms_total = start.elapsed_time(end)
     k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / max(1, len(k1_events))
-    # keep the GPU busy a little longer so that the 100 ms clock sampler sees it under this load
+    # keep the GPU busy a little longer so that the 100 ms clock sampler sees it under this load (rank 0 only, so
+    # without the collective: the other ranks are not taking part)
     if rank == 0:
         t_end = time.time() + 1.0
         while time.time() < t_end:
-            step(False)
+            step(False, collective=False)
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -331,7 +335,7 @@ def run_ours(args):
                        "l2": "inputs (10.2 GB per GPU at 16 images) are larger than L2; no flush between steps",
                        "bytes_per_voxel": bpv},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k1_fast (vu_fused_pass)", "kernel_ms": k1_ms, "peak_source": peak_src,
+                         "traffic": traffic, "kernel": kernel_name, "kernel_ms": k1_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bpv * V * B},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e}
     if world == 1 and not args.no_cpu_baseline:
@@ -354,7 +358,7 @@ def main():
     ap.add_argument("--images-per-step", type=int, default=16)
     ap.add_argument("--e2e-images", type=int, default=2)
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-images", type=int, default=4)
+    ap.add_argument("--cpu-images", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

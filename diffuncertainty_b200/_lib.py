@@ -14,10 +14,11 @@ LIB_PATH = os.path.join(PKG, "lib", "libvalunc.so")
 
 VU_OK = 0
 VU_ERR_BAD_ARG, VU_ERR_UNSUPPORTED, VU_ERR_CUDA, VU_ERR_NO_DEVICE = -1, -2, -3, -4
-VU_ABI_VERSION = 1
+VU_ABI_VERSION = 2
 N_UNC, N_BINS, N_EDGES, MAX_RATERS = 3, 21, 19, 8
 GT_U8, GT_I64 = 0, 1
-STAT_IMAGE_SUM, STAT_THRESHOLD, STAT_AREA, STAT_DICE, STAT_CALIB, STAT_NCC = 1, 2, 4, 8, 16, 32
+STAT_IMAGE_SUM, STAT_THRESHOLD, STAT_AREA, STAT_DICE, STAT_CALIB, STAT_NCC, STAT_PLATT_FIT = 1, 2, 4, 8, 16, 32, 64
+N_PLATT_BINS = 256
 STAT_ALL_NO_GT = STAT_IMAGE_SUM | STAT_THRESHOLD | STAT_AREA
 
 # column layout of the per-image rows (keep in sync with valunc.h; checked in tests/test_abi.py)
@@ -41,18 +42,24 @@ class Calib(C.Structure):
     _fields_ = [("a", C.c_float), ("b", C.c_float), ("edge_u", C.c_float * N_EDGES), ("mode", C.c_int32)]
 
 
+class PlattFit(C.Structure):
+    _fields_ = [("edge_u", C.c_float * (N_PLATT_BINS + 1))]
+
+
 class FusedArgs(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("stat_flags", C.c_uint32), ("slab", Slab),
                 ("tu", C.c_void_p), ("au", C.c_void_p), ("eu", C.c_void_p), ("labels", C.c_void_p),
                 ("gt", Gt), ("threshold", C.c_float * N_UNC), ("calib", Calib * N_UNC),
-                ("calib_label_lut", C.c_void_p), ("stats_f64", C.c_void_p), ("stats_i64", C.c_void_p)]
+                ("calib_label_lut", C.c_void_p), ("stats_f64", C.c_void_p), ("stats_i64", C.c_void_p),
+                ("platt_fit", C.POINTER(PlattFit)), ("platt_i64", C.c_void_p), ("platt_f64", C.c_void_p)]
 
 
 class MapStatsArgs(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("stat_flags", C.c_uint32), ("B", C.c_int64), ("V", C.c_int64),
                 ("maps", C.c_void_p * N_UNC), ("labels", C.c_void_p), ("gt", Gt),
                 ("threshold", C.c_float * N_UNC), ("calib", Calib * N_UNC), ("calib_label_lut", C.c_void_p),
-                ("ncc_gt_map", C.c_void_p), ("stats_f64", C.c_void_p), ("stats_i64", C.c_void_p)]
+                ("ncc_gt_map", C.c_void_p), ("stats_f64", C.c_void_p), ("stats_i64", C.c_void_p),
+                ("platt_fit", C.POINTER(PlattFit)), ("platt_i64", C.c_void_p), ("platt_f64", C.c_void_p)]
 
 
 EXPORTS = {
@@ -67,6 +74,7 @@ EXPORTS = {
                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vu_border_count": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "vu_platt_invert_edges_host": (C.c_int, [C.c_double, C.c_double, C.POINTER(Calib)]),
+    "vu_platt_fit_edges_host": (C.c_int, [C.POINTER(PlattFit)]),
     "vu_synth_slab": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int64,
                                 C.c_float, C.c_void_p]),
     "vu_synth_gt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
@@ -105,6 +113,10 @@ def load():
                     f"libvalunc.so is not built and could not be built ({exc}); run "
                     "`python -m diffuncertainty_b200.build`. There is no CPU fallback.") from exc
             path = LIB_PATH
+        try:
+            import torch  # noqa: F401  (brings libcudart.so.12 into the process: libvalunc shares torch's CUDA runtime)
+        except ImportError:
+            pass
         lib = C.CDLL(path)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(lib, name)  # AttributeError here = header / library drift
@@ -113,7 +125,7 @@ def load():
         if lib.vu_abi_version() != VU_ABI_VERSION:
             raise ValuncError("libvalunc ABI version mismatch; rebuild with python -m diffuncertainty_b200.build --force")
         if lib.vu_struct_size(0) != C.sizeof(FusedArgs) or lib.vu_struct_size(1) != C.sizeof(MapStatsArgs) \
-                or lib.vu_struct_size(2) != C.sizeof(Calib):
+                or lib.vu_struct_size(2) != C.sizeof(Calib) or lib.vu_struct_size(3) != C.sizeof(PlattFit):
             raise ValuncError("ctypes struct layout differs from valunc.h")
         _lib = lib
         return lib

@@ -62,7 +62,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    # the CUDA runtime is linked SHARED: inside a PyTorch process the library must use the same runtime instance as
+    # torch (one notion of the current device and of the streams torch hands over); a private static runtime
+    # launches on device 0 whatever torch.cuda.current_device() is.  libcudart.so.12 is already in the process
+    # when torch is imported; the rpath covers stand-alone C users.
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared",
+           "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr}")

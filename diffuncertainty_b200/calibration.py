@@ -242,3 +242,136 @@ class GlobalCalibAccumulator:
 
     def compute_ece(self) -> float:
         return ace_ece_from_histogram(self.bin_sums, self.bin_true, self.bin_total)[1]
+
+
+# ---------------------------------------------------------------------------
+# Platt-scaling fit on the validation split (ace.py:14-285)
+# ---------------------------------------------------------------------------
+N_PLATT_BINS = _lib.N_PLATT_BINS
+
+
+def platt_fit_bin_edges(n_bins: int = N_PLATT_BINS) -> np.ndarray:
+    """ace.py:31: the float64 edges np.logspace(-12, 2, n_bins + 1)."""
+    return np.logspace(-12, 2, num=n_bins + 1, dtype=np.float64)
+
+
+def platt_fit_struct() -> _lib.PlattFit:
+    """Edges rounded up to float32 (same truth value as NumPy's float64 comparison of a float32 sample)."""
+    e64 = platt_fit_bin_edges()
+    e32 = e64.astype(np.float32)
+    e32 = np.where(e32.astype(np.float64) < e64, np.nextafter(e32, np.float32(np.inf)), e32).astype(np.float32)
+    pf = _lib.PlattFit()
+    for k in range(N_PLATT_BINS + 1):
+        pf.edge_u[k] = float(e32[k])
+    return pf
+
+
+class PlattFitAccumulator:
+    """Dataset-level buffers of the compressed Platt-fit data (ace.py:58-137): per uncertainty type and bin the
+    number of samples, of correct samples, and the sum of uncertainties.  Lives on the device; fused passes and
+    vu_map_stats launches with STAT_PLATT_FIT accumulate into it."""
+
+    def __init__(self, device=None) -> None:
+        _lib.require_device()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.counts = torch.zeros((3, N_PLATT_BINS, 2), dtype=torch.int64, device=self.device)
+        self.sums = torch.zeros((3, N_PLATT_BINS), dtype=torch.float64, device=self.device)
+        self.edges = platt_fit_struct()
+
+    def accumulate_maps(self, reference_segs, pred_seg, unc_maps, ignore_value=None) -> None:
+        """One image from stored maps: reference_segs (R, *S), pred_seg (*S), unc_maps: up to three (*S) float maps
+        (TU, AU, EU order; None to skip one)."""
+        lib = _lib.load()
+        refs = torch.as_tensor(np.ascontiguousarray(reference_segs)) if not isinstance(reference_segs, torch.Tensor) else reference_segs
+        pred = torch.as_tensor(np.ascontiguousarray(pred_seg)) if not isinstance(pred_seg, torch.Tensor) else pred_seg
+        if refs.dim() != pred.dim() + 1 or tuple(refs.shape[1:]) != tuple(pred.shape):
+            # ace.py:79-80
+            raise AssertionError(f"Reference segs should have shape (n_raters, *pred_seg.shape). found {tuple(refs.shape)} vs {tuple(pred.shape)}")
+        refs = refs.to(self.device)
+        refs = refs.to(torch.uint8 if refs.dtype in (torch.uint8, torch.bool) else torch.int64).contiguous()
+        pred = pred.to(self.device).to(torch.uint8).contiguous()
+        V = pred.numel()
+        maps = []
+        for m in list(unc_maps) + [None] * (3 - len(unc_maps)):
+            if m is None:
+                maps.append(None)
+                continue
+            t = torch.as_tensor(np.ascontiguousarray(m)) if not isinstance(m, torch.Tensor) else m
+            if t.numel() != V:
+                raise ValueError("uncertainty map and prediction must have the same number of elements")
+            maps.append(t.to(self.device).float().contiguous())
+        if V == 0:
+            return
+        sf = torch.zeros((1, _lib.F64["COLS"]), dtype=torch.float64, device=self.device)
+        si = torch.zeros((1, _lib.I64["COLS"]), dtype=torch.int64, device=self.device)
+        a = _lib.MapStatsArgs()
+        a.struct_size = C.sizeof(_lib.MapStatsArgs)
+        a.stat_flags = _lib.STAT_PLATT_FIT
+        a.B, a.V = 1, V
+        for k, m in enumerate(maps):
+            a.maps[k] = m.data_ptr() if m is not None else None
+        a.labels = pred.data_ptr()
+        a.gt.data = refs.data_ptr()
+        a.gt.dtype = _lib.GT_U8 if refs.dtype == torch.uint8 else _lib.GT_I64
+        a.gt.R = refs.shape[0]
+        a.gt.stride_b, a.gt.stride_r, a.gt.stride_v = refs.numel(), V, 1
+        a.gt.has_ignore = 0 if ignore_value is None else 1
+        a.gt.ignore_index = 0 if ignore_value is None else int(ignore_value)
+        a.stats_f64, a.stats_i64 = sf.data_ptr(), si.data_ptr()
+        a.platt_fit = C.pointer(self.edges)
+        a.platt_i64, a.platt_f64 = self.counts.data_ptr(), self.sums.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.vu_map_stats(C.byref(a), _lib.current_stream_ptr()), "vu_map_stats")
+
+    def histograms(self):
+        """(total, pos, neg, sum_unc), each (3, 256), on the host."""
+        c = self.counts.cpu().numpy()
+        return c[..., 0], c[..., 1], c[..., 0] - c[..., 1], self.sums.cpu().numpy()
+
+    def fit(self, unc_index: int) -> Tuple[float, float]:
+        total, pos, neg, sums = self.histograms()
+        return platt_fit_from_histogram(total[unc_index], pos[unc_index], neg[unc_index], sums[unc_index])
+
+
+def platt_fit_from_histogram(total, pos, neg, sum_unc) -> Tuple[float, float]:
+    """ace.py:146-178: at most two weighted samples per non-empty bin at F = -(mean uncertainty of the bin), fitted with
+    sklearn's Platt routine (the <= 512-point fit stays on the host); (0, 0) without samples."""
+    total = np.asarray(total)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mean_unc = np.divide(sum_unc, total, out=np.zeros(len(total), np.float64), where=total > 0)
+    F, y, w = [], [], []
+    for b in range(len(total)):
+        if total[b] == 0:
+            continue
+        if pos[b] > 0:
+            F.append(-mean_unc[b]); y.append(1); w.append(int(pos[b]))
+        if neg[b] > 0:
+            F.append(-mean_unc[b]); y.append(0); w.append(int(neg[b]))
+    if not F:
+        return 0.0, 0.0
+    from sklearn.calibration import _sigmoid_calibration
+    a, b = _sigmoid_calibration(np.asarray(F, np.float64), np.asarray(y, np.float64), sample_weight=np.asarray(w, np.float64))
+    return float(a), float(b)
+
+
+def platt_scale_params(val_exp_dataloader, ignore_value=None, n_bins: int = 256, plot: bool = False):
+    """Drop-in for ace.py:14-285 (without the diagnostic plots): bins every validation image on the GPU, fits (a, b) per
+    uncertainty type on the host and writes platt_scale_params.json next to the experiment like the reference."""
+    if n_bins != N_PLATT_BINS:
+        raise NotImplementedError("the GPU path bins on the reference's default grid of 256 bins")
+    unc_types = list(val_exp_dataloader.exp_version.unc_types)
+    params = {}
+    for unc_type in unc_types:  # one accumulator per type: the reference loops types outermost as well
+        acc = PlattFitAccumulator()
+        for image_id in val_exp_dataloader.image_ids:
+            refs = np.asarray(val_exp_dataloader.get_reference_segs(image_id))
+            pred = np.asarray(val_exp_dataloader.get_mean_pred_seg(image_id))
+            unc = np.asarray(val_exp_dataloader.get_unc_map(image_id, unc_type))
+            if pred.shape != unc.shape:  # 2d unc map is loaded in shape (W, H) (ace.py:76-78)
+                unc = np.swapaxes(unc, 0, 1)
+            acc.accumulate_maps(refs, pred, [unc], ignore_value)
+        a, b = acc.fit(0)
+        params[unc_type] = {"a": float(a), "b": float(b)}
+    with open(val_exp_dataloader.exp_version.exp_path / "platt_scale_params.json", "w") as f:
+        json.dump(params, f, indent=2)
+    return params

@@ -63,16 +63,28 @@ static int gt_alignment(const vu_gt& gt, long long V) {
 
 static int fill_stat_params(StatParams& st, uint32_t flags, unsigned unc_mask, long long V, const vu_gt& gt,
                             const float* thr, const vu_calib* calib, const uint8_t* lut, const double* ncc_gt_map,
-                            double* f64, int64_t* i64) {
+                            double* f64, int64_t* i64, const vu_platt_fit* platt_fit, int64_t* platt_i64, double* platt_f64) {
     memset(&st, 0, sizeof(st));
     st.flags = flags;
     st.unc_mask = unc_mask;
     st.V = V;
     if (flags == 0) return VU_OK;
     if (!f64 || !i64) return set_error(VU_ERR_BAD_ARG, "stat_flags set but stats_f64 / stats_i64 is NULL");
-    const uint32_t known = VU_STAT_IMAGE_SUM | VU_STAT_THRESHOLD | VU_STAT_AREA | VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC;
+    const uint32_t known = VU_STAT_IMAGE_SUM | VU_STAT_THRESHOLD | VU_STAT_AREA | VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC |
+                           VU_STAT_PLATT_FIT;
     if (flags & ~known) return set_error(VU_ERR_BAD_ARG, "unknown stat flag");
-    const bool needs_gt = (flags & (VU_STAT_DICE | VU_STAT_CALIB)) || ((flags & VU_STAT_NCC) && !ncc_gt_map);
+    const bool needs_gt = (flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_PLATT_FIT)) || ((flags & VU_STAT_NCC) && !ncc_gt_map);
+    if (flags & VU_STAT_PLATT_FIT) {
+        if (!platt_fit || !platt_i64 || !platt_f64)
+            return set_error(VU_ERR_BAD_ARG, "VU_STAT_PLATT_FIT needs platt_fit, platt_i64 and platt_f64");
+        for (int k = 0; k <= VU_N_PLATT_BINS; ++k) {
+            st.platt_edge[k] = platt_fit->edge_u[k];
+            if (!(st.platt_edge[k] > 0.0f) || (k && !(st.platt_edge[k] > st.platt_edge[k - 1])))
+                return set_error(VU_ERR_BAD_ARG, "vu_platt_fit.edge_u must be positive and increasing");
+        }
+        st.platt_i64 = reinterpret_cast<long long*>(platt_i64);
+        st.platt_f64 = platt_f64;
+    }
     if (needs_gt) {
         if (!gt.data) return set_error(VU_ERR_BAD_ARG, "DICE / CALIB / NCC statistics need ground truth");
         if (gt.R < 1 || gt.R > VU_MAX_RATERS) return set_error(VU_ERR_UNSUPPORTED, "gt.R must be 1..8");
@@ -130,6 +142,7 @@ int vu_struct_size(int which) {
         case 0: return (int)sizeof(vu_fused_args);
         case 1: return (int)sizeof(vu_map_stats_args);
         case 2: return (int)sizeof(vu_calib);
+        case 3: return (int)sizeof(vu_platt_fit);
         default: return -1;
     }
 }
@@ -145,7 +158,7 @@ int vu_fused_pass(const vu_fused_args* a, void* stream) {
     StatParams st;
     const unsigned unc_mask = s.P > 1 ? 7u : 1u;
     int rc = fill_stat_params(st, a->stat_flags, unc_mask, s.V, a->gt, a->threshold, a->calib, a->calib_label_lut, nullptr,
-                              a->stats_f64, a->stats_i64);
+                              a->stats_f64, a->stats_i64, a->platt_fit, a->platt_i64, a->platt_f64);
     if (rc != VU_OK) return rc;
     return launch_k1(a, st, (cudaStream_t)stream);
 }
@@ -161,7 +174,7 @@ int vu_map_stats(const vu_map_stats_args* a, void* stream) {
     unsigned unc_mask = 0;
     for (int k = 0; k < VU_N_UNC; ++k) unc_mask |= a->maps[k] ? (1u << k) : 0u;
     int rc = fill_stat_params(st, a->stat_flags, unc_mask, a->V, a->gt, a->threshold, a->calib, a->calib_label_lut,
-                              a->ncc_gt_map, a->stats_f64, a->stats_i64);
+                              a->ncc_gt_map, a->stats_f64, a->stats_i64, a->platt_fit, a->platt_i64, a->platt_f64);
     if (rc != VU_OK) return rc;
     return launch_map_stats(a, st, (cudaStream_t)stream);
 }
@@ -231,6 +244,17 @@ int vu_platt_invert_edges_host(double a, double b, vu_calib* calib) {
             while (lo < hi) { uint32_t mid = lo + (hi - lo + 1) / 2; if (ok(mid)) lo = mid; else hi = mid - 1; }
             calib->edge_u[k] = o2f(lo);
         }
+    }
+    return VU_OK;
+}
+
+int vu_platt_fit_edges_host(vu_platt_fit* out) {
+    if (!out) return set_error(VU_ERR_BAD_ARG, "out is NULL");
+    for (int k = 0; k <= VU_N_PLATT_BINS; ++k) {
+        const double e = pow(10.0, -12.0 + 14.0 * (double)k / (double)VU_N_PLATT_BINS);  // np.logspace(-12, 2, 257)
+        float f = (float)e;
+        if ((double)f < e) f = nextafterf(f, INFINITY);
+        out->edge_u[k] = f;
     }
     return VU_OK;
 }

@@ -10,6 +10,19 @@
 
 namespace vu {
 
+// s / P for a member count P (2 <= P <= 271, rP = RN(1 / P)), bit-identical to the IEEE division that
+// torch.mean performs (test_2D.py:971): q = RN(s * rP) followed by one residual correction.  Verified exhaustively
+// against __fdiv_rn over all 2^24 mantissas of two binades for every P (bench/diag_div.cu: 0 mismatches; the
+// uncorrected product differs 1.2e9 times).  Division is exponent-invariant away from under / overflow; outside
+// [1e-30, 1e30] (and for NaN / inf) the IEEE divide is taken.
+__device__ __forceinline__ float div_by_count(float s, float Pf, float rP) {
+    float q = __fmul_rn(s, rP);
+    const float a = fabsf(s);
+    if (a > 1e-30f && a < 1e30f) q = __fmaf_rn(__fmaf_rn(-q, Pf, s), rP, q);
+    else if (s != 0.0f) q = __fdiv_rn(s, Pf);
+    return q;
+}
+
 // One thread owns VEC consecutive voxels.  The E = C * VEC values of one member are handled as E/2 packed
 // fp32 pairs (FADD2 / FFMA2), flattened [class][voxel]: pairs of neighbouring voxels for VEC = 2, 4, pairs
 // of classes for VEC = 1 (with one scalar leftover when C is odd).  The entropy of a member is accumulated
@@ -119,35 +132,56 @@ struct VoxelAcc {
 
     // mean (true division, test_2D.py:971), label, TU, AU, EU of the VEC voxels
     __device__ __forceinline__ void finish(float Pf, float (&u)[VU_N_UNC][VEC], int (&label)[VEC]) const {
-        float mean[C][VEC], asum[VEC];
+        const bool fast_div = Pf <= 271.0f;
+        const float rP = __frcp_rn(Pf);
+        auto mean_of = [&](float s) { return fast_div ? div_by_count(s, Pf, rP) : __fdiv_rn(s, Pf); };
+        float mean[C][VEC], asum[VEC], tu2[VEC];
+        f32x2 T[NH];  // TU sums (VEC >= 2: packed over voxels, like the member entropies)
+#pragma unroll
+        for (int q = 0; q < NH; ++q) T[q] = 0ull;
+        float ts = 0.f;
 #pragma unroll
         for (int e = 0; e < NP; ++e) {
             const f32x2 S = (LEVELS > 1) ? add2(m0[e], m1[e < NP1 ? e : 0]) : m0[e];
             float s0, s1;
             upk2(S, s0, s1);
-            mean[(2 * e) / VEC][(2 * e) % VEC] = __fdiv_rn(s0, Pf);
-            mean[(2 * e + 1) / VEC][(2 * e + 1) % VEC] = __fdiv_rn(s1, Pf);
+            const float q0 = mean_of(s0), q1 = mean_of(s1);
+            mean[(2 * e) / VEC][(2 * e) % VEC] = q0;
+            mean[(2 * e + 1) / VEC][(2 * e + 1) % VEC] = q1;
+            f32x2 PC, L;
+            plog2p_parts2(pk2(q0, q1), PC, L);
+            if constexpr (VEC >= 2) {
+                T[e % NH] = fma2(PC, L, T[e % NH]);  // pair e = (class e / NH, voxels 2 (e % NH), +1): class order per voxel
+            } else {
+                float pc0, pc1, l0, l1;
+                upk2(PC, pc0, pc1);
+                upk2(L, l0, l1);
+                ts = __fmaf_rn(pc0, l0, ts);
+                ts = __fmaf_rn(pc1, l1, ts);
+            }
         }
-        if constexpr (ODD) mean[C - 1][0] = __fdiv_rn((LEVELS > 1) ? __fadd_rn(m0s, m1s) : m0s, Pf);
+        if constexpr (ODD) {
+            mean[C - 1][0] = mean_of((LEVELS > 1) ? __fadd_rn(m0s, m1s) : m0s);
+            ts = plog2p_acc(ts, mean[C - 1][0]);
+        }
         if constexpr (VEC >= 2) {
 #pragma unroll
             for (int q = 0; q < NH; ++q) {
                 const f32x2 A = (LEVELS > 1) ? add2(a0[q], a1[q]) : a0[q];
                 upk2(A, asum[2 * q], asum[2 * q + 1]);
+                upk2(T[q], tu2[2 * q], tu2[2 * q + 1]);
             }
         } else {
             asum[0] = (LEVELS > 1) ? __fadd_rn(a0s, a1s) : a0s;
+            tu2[0] = ts;
         }
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            float best = mean[0][k], tu2 = 0.f;
+            float best = mean[0][k];
             int idx = 0;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                if (c > 0) argmax_step(mean[c][k], c, best, idx);
-                tu2 = plog2p_acc(tu2, mean[c][k]);
-            }
-            const float tu = -(tu2 * kLn2);
+            for (int c = 1; c < C; ++c) argmax_step(mean[c][k], c, best, idx);
+            const float tu = -(tu2[k] * kLn2);
             const float au = (-(asum[k] * kLn2)) / Pf;
             u[0][k] = tu; u[1][k] = au; u[2][k] = tu - au;
             label[k] = idx;

@@ -64,6 +64,27 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
 }
+constexpr int kStatThreads = 96;   // 3 statistics warps: with the producer warp they fill one 128-thread group
+constexpr int kStatVec = 4;        // voxels per statistics thread and pass
+
+// same, for warps that are ahead of the pipeline (producer, statistics): sleep between probes instead of
+// burning issue slots the consumer warps need
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(100);
+    }
+}
 // global -> shared bulk copy, completion counted in bytes on an mbarrier; read-once data: evict-first in L2
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar, unsigned long long policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
@@ -71,8 +92,53 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  : "memory");
 }
 
-constexpr int kStatThreads = 96;   // 3 statistics warps: with the producer warp they fill one 128-thread group
-constexpr int kStatVec = 4;        // voxels per statistics thread and pass
+
+// The tile loop of the statistics warps: pick (TU, AU, EU, label) of each tile up from the hand-off buffer the consumers
+// filled and run the statistics phase on kStatVec voxels per thread and pass.
+template <int TV, int TID0, unsigned FL>
+__device__ __forceinline__ void stat_warps_loop(const StatParams& st, void* st_smem, const unsigned char* hand, unsigned hand_bytes,
+                                                unsigned hfull0, unsigned hempty0, int t0, int t1, int tpi, long long V) {
+    constexpr int kRep = 32;
+    constexpr int kPasses = (TV + kStatThreads * kStatVec - 1) / (kStatThreads * kStatVec);
+    const int s = (int)threadIdx.x - TID0;
+    StatsCursor<kStatThreads> cursor;
+    stats_init<kStatThreads, 2, TID0, kRep>(st, st_smem);
+    int b = t0 / tpi, vt = t0 - b * tpi - 1;
+    for (int tile = t0; tile < t1; ++tile) {
+        if (++vt == tpi) { vt = 0; ++b; }
+        cursor.template enter<2, TID0, kRep>(st, st_smem, b, vt, TV);
+        const int buf = (tile - t0) & 1;
+        const unsigned par = ((tile - t0) >> 1) & 1;
+        const long long v0 = (long long)vt * TV;
+#pragma unroll 1
+        for (int pass = 0; pass < kPasses; ++pass) {
+            const int q = (pass * kStatThreads + s) * kStatVec;
+            if (q < TV && v0 + q < V) stats_prefetch_gt<kStatVec>(st, b, v0 + q);
+        }
+        mbar_wait_relaxed(hfull0 + 8 * buf, par);  // the consumers have written this tile's maps and labels
+        const unsigned char* hb = hand + (size_t)buf * hand_bytes;
+#pragma unroll 1
+        for (int pass = 0; pass < kPasses; ++pass) {
+            const int q = (pass * kStatThreads + s) * kStatVec;  // first voxel of this thread inside the tile
+            const bool in_tile = q < TV;                         // (the last pass may overhang the tile)
+            float u[VU_N_UNC][kStatVec];
+            int label[kStatVec];
+#pragma unroll
+            for (int k = 0; k < VU_N_UNC; ++k) {
+                const float4 w = in_tile ? *reinterpret_cast<const float4*>(hb + ((size_t)k * TV + q) * sizeof(float))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                u[k][0] = w.x; u[k][1] = w.y; u[k][2] = w.z; u[k][3] = w.w;
+            }
+            const unsigned lw = in_tile ? *reinterpret_cast<const unsigned*>(hb + (size_t)12 * TV + q) : 0u;
+#pragma unroll
+            for (int j = 0; j < kStatVec; ++j) label[j] = (int)((lw >> (8 * j)) & 0xffu);
+            stats_tile<kStatVec, kStatThreads, TID0, kRep, FL>(st, st_smem, in_tile && v0 + q < V, b, v0 + q, u, label);
+        }
+        __syncwarp();
+        if ((s & 31) == 0) mbar_arrive(hempty0 + 8 * buf);  // this warp is done with the hand-off buffer
+    }
+    if (t1 > t0) cursor.template finish<2, TID0, kRep>(st, st_smem, vt, TV);
+}
 
 // C classes, VEC voxels per consumer thread, CT consumer threads.
 // NCH == 1: a stage holds G whole members (G x C rows).  NCH == 2 (G == 1, VEC >= 2): a stage holds half a
@@ -141,7 +207,7 @@ __global__ void __launch_bounds__(CT + 32 + kStatThreads, 1) k1_tma(const __grid
                     p0 = fi >> 1; c0 = (fi & 1) * CH;
                     nrows = (fi & 1) ? (C - CH) : CH;
                 }
-                mbar_wait(empty0 + 8 * stage, phase ^ 1);  // slot free (the first pass falls through)
+                mbar_wait_relaxed(empty0 + 8 * stage, phase ^ 1);  // slot free (the first pass falls through)
                 if (lane == 0) mbar_arrive_expect_tx(full0 + 8 * stage, (unsigned)nrows * row_bytes);
                 __syncwarp();
                 const unsigned dst0 = smem_u32(ring) + (unsigned)stage * kStageBytes;
@@ -159,45 +225,17 @@ __global__ void __launch_bounds__(CT + 32 + kStatThreads, 1) k1_tma(const __grid
 
     if (STATS && tid >= kStat0) {
         // ------------------------------ statistics warps ------------------------------------------------
-        const int s = tid - kStat0;
-        StatsCursor<kStatThreads> cursor;
-        stats_init<kStatThreads, 2, kStat0>(prm.st, st_smem);
-        int b = t0 / tpi, vt = t0 - b * tpi - 1;
-        for (int tile = t0; tile < t1; ++tile) {
-            if (++vt == tpi) { vt = 0; ++b; }
-            cursor.template enter<2, kStat0>(prm.st, st_smem, b, vt, TV);
-            const int buf = (tile - t0) & 1;
-            const unsigned par = ((tile - t0) >> 1) & 1;
-            const long long v0 = (long long)vt * TV;
-            constexpr int kPasses = (TV + kStatThreads * kStatVec - 1) / (kStatThreads * kStatVec);
-#pragma unroll 1
-            for (int pass = 0; pass < kPasses; ++pass) {
-                const int q = (pass * kStatThreads + s) * kStatVec;
-                if (q < TV && v0 + q < V) stats_prefetch_gt<kStatVec>(prm.st, b, v0 + q);
-            }
-            mbar_wait(hfull0 + 8 * buf, par);  // the consumers have written this tile's maps and labels
-            const unsigned char* hb = hand + (size_t)buf * kHandBytes;
-#pragma unroll 1
-            for (int pass = 0; pass < kPasses; ++pass) {
-                const int q = (pass * kStatThreads + s) * kStatVec;  // first voxel of this thread inside the tile
-                const bool in_tile = q < TV;                         // (the last pass may overhang the tile)
-                float u[VU_N_UNC][kStatVec];
-                int label[kStatVec];
-#pragma unroll
-                for (int k = 0; k < VU_N_UNC; ++k) {
-                    const float4 w = in_tile ? *reinterpret_cast<const float4*>(hb + ((size_t)k * TV + q) * sizeof(float))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                    u[k][0] = w.x; u[k][1] = w.y; u[k][2] = w.z; u[k][3] = w.w;
-                }
-                const unsigned lw = in_tile ? *reinterpret_cast<const unsigned*>(hb + (size_t)12 * TV + q) : 0u;
-#pragma unroll
-                for (int j = 0; j < kStatVec; ++j) label[j] = (int)((lw >> (8 * j)) & 0xffu);
-                stats_tile<kStatVec, kStatThreads, kStat0>(prm.st, st_smem, in_tile && v0 + q < V, b, v0 + q, u, label);
-            }
-            __syncwarp();
-            if ((s & 31) == 0) mbar_arrive(hempty0 + 8 * buf);  // this warp is done with the hand-off buffer
-        }
-        if (t1 > t0) cursor.template finish<2, kStat0>(prm.st, st_smem, vt, TV);
+        // common masks get a compile-time specialisation of the statistics phase (no flag tests, no dead code)
+        const StatParams& st = prm.st;
+        const bool plain = st.unc_mask == 7u && st.lut == nullptr && st.gt.dtype == VU_GT_U8;
+        auto run = [&](auto fl_tag) {
+            constexpr unsigned FL = decltype(fl_tag)::value;
+            stat_warps_loop<TV, kStat0, FL>(st, st_smem, hand, kHandBytes, hfull0, hempty0, t0, t1, tpi, V);
+        };
+        if (plain && st.flags == 0x1fu) run(std::integral_constant<unsigned, 0x1fu>());
+        else if (plain && st.flags == 0x3fu) run(std::integral_constant<unsigned, 0x3fu>());
+        else if (st.unc_mask == 7u && st.flags == 0x07u) run(std::integral_constant<unsigned, 0x07u>());
+        else run(std::integral_constant<unsigned, kRuntimeFlags>());
         return;
     }
 
@@ -353,10 +391,12 @@ int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t str
             if (kTma[i].C == s.C && kTma[i].LEVELS == need_levels) pick = &kTma[i];
     }
     if (!pick) return 1;
-    // With few classes the statistics phase outweighs the streaming arithmetic; three statistics warps cannot
-    // keep up with sixteen consumer warps there, so those launches stay on the register-streaming kernel, where
-    // every warp does both (measured r01: cfg2 / cfg4 with reference-based statistics 2-3x faster that way).
-    if (forced < 0 && st.flags && s.C * s.P < 128) return 1;
+    // With few classes the reference-based statistics outweigh the streaming arithmetic; three statistics warps
+    // cannot keep up with sixteen consumer warps there, so those launches stay on the register-streaming kernel,
+    // where every warp does both (measured r01: cfg2 / cfg4 with Dice + calibration statistics 1.3-2.2x faster
+    // that way; without reference-based statistics the TMA form wins everywhere).
+    const unsigned heavy = VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC | VU_STAT_PLATT_FIT;
+    if (forced < 0 && get_option("k1_path", 0) != 2 && (st.flags & heavy) && s.C * s.P < 128) return 1;
     const int vec = pick->VEC;
     auto ok = [&](const void* p, uintptr_t al) { return p == nullptr || ((uintptr_t)p % al) == 0; };
     if (!ok(a->tu, 4 * vec) || !ok(a->au, 4 * vec) || !ok(a->eu, 4 * vec) || !ok(a->labels, vec) || s.V % vec) return 1;
@@ -374,7 +414,7 @@ int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t str
 
     const int rows = pick->NCH == 1 ? pick->G * pick->C : (pick->C + 1) / 2;
     const size_t stage_bytes = (size_t)rows * tile_vox * sizeof(float);
-    const size_t stats_bytes = stats_smem_bytes(st.flags, st.gt.R, kStatThreads);
+    const size_t stats_bytes = stats_smem_bytes(st.flags, st.gt.R, kStatThreads, 32);
     const size_t hand_bytes = st.flags ? 2 * 13 * (size_t)tile_vox : 0;
     const size_t budget = 227 * 1024;
     const size_t fixed = 256 /* barriers */ + 256 /* alignment slack */ + stats_bytes + hand_bytes;

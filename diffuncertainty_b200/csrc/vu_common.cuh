@@ -214,6 +214,10 @@ struct StatParams {
     const double* ncc_gt_map;
     double* f64;
     long long* i64;
+    // VU_STAT_PLATT_FIT (dataset-level outputs)
+    long long* platt_i64;
+    double* platt_f64;
+    float platt_edge[VU_N_PLATT_BINS + 1];  // smallest float32 >= edge k of np.logspace(-12, 2, 257)
 };
 
 // ---- per-CTA statistics state (dynamic shared memory) ---------------------------
@@ -245,9 +249,17 @@ constexpr int kMaxVoxPerFlush = 1024;   // voxels per thread between flushes: x 
                                         // 16-bit counts (<= 16384) and the 32-bit q sums (< 2^31) from overflowing
 constexpr int kQBits = 21;
 constexpr int kHistBins = VU_N_BINS - 1;  // 20 real bins; slot 20 (NaN) is counted in the integer slots
-constexpr int kHistRep = 16;
-constexpr int kHistWordsPerWarp = VU_N_UNC * kHistBins * kHistRep;  // uint2 words
+// histogram replicas per warp: 16 (two half-warp phases; the register-streaming kernels, 8 warps per CTA) or 32 (one
+// replica per lane, no phases; the three statistics warps of the TMA kernel)
+constexpr unsigned kRuntimeFlags = 0xffffffffu;  // template value: statistics mask read from StatParams at run time
 constexpr int kEdgePad = 24;  // E[0] = NaN, E[1..19] = edges, E[20..23] = NaN
+
+// Platt-fit data: one CTA-wide histogram [unc][bin][samples, correct, q_hi, q_lo] of int32 updated with native shared
+// atomics (768 bins are too many to replicate per lane), plus the edge table T[0..256] (padded) and 1 / edge
+constexpr int kPlattWords = VU_N_UNC * VU_N_PLATT_BINS * 4;
+constexpr int kPlattTab = 264;
+constexpr int kPlattQBits = 20;  // q = round((u / edge_bin - 1) * 2^20), |q| <= 2^21 after clamping
+constexpr int kPlattQSplit = 12;
 
 __host__ __device__ inline int stats_num_fslots(unsigned flags) {
     return (flags & VU_STAT_NCC) ? FS_MAX : ((flags & VU_STAT_CALIB) ? FS_G : FS_BIN0);
@@ -255,19 +267,24 @@ __host__ __device__ inline int stats_num_fslots(unsigned flags) {
 __host__ __device__ inline int stats_num_islots(unsigned flags, int R) {
     return (flags & VU_STAT_DICE) ? IS_DICE + R : ((flags & VU_STAT_CALIB) ? IS_DICE : IS_NANTOT);
 }
-__host__ __device__ inline size_t stats_smem_bytes(unsigned flags, int R, int threads) {
+__host__ __device__ inline size_t stats_smem_bytes(unsigned flags, int R, int threads, int rep = 16) {
     if (!flags) return 0;
     size_t n = (size_t)(stats_num_fslots(flags) + stats_num_islots(flags, R)) * threads * 8;
-    if (flags & VU_STAT_CALIB) n += (size_t)(threads / 32) * kHistWordsPerWarp * sizeof(uint2) + (size_t)VU_N_UNC * kEdgePad * sizeof(float);
+    if (flags & VU_STAT_CALIB)
+        n += (size_t)(threads / 32) * (VU_N_UNC * kHistBins * rep) * sizeof(uint2) + (size_t)VU_N_UNC * kEdgePad * sizeof(float);
+    if (flags & VU_STAT_PLATT_FIT) n += (size_t)kPlattWords * sizeof(int) + (size_t)kPlattTab * 2 * sizeof(float);
     return n;
 }
 
-template <int THREADS>
+template <int THREADS, int REP = 16>
 struct StatsLayout {
+    static constexpr int kHistWordsPerWarp = VU_N_UNC * kHistBins * REP;  // uint2 words
     double* fs;
     unsigned long long* is;
     uint2* hist;  // [warp][unc][bin][replica]
     float* E;
+    int* phist;   // Platt-fit data [unc][bin][4]
+    float* pT;    // [kPlattTab] edges, then [kPlattTab] reciprocals
     int nF, nI;
     __device__ __forceinline__ StatsLayout(const StatParams& sp, void* smem) {
         nF = stats_num_fslots(sp.flags);
@@ -275,7 +292,9 @@ struct StatsLayout {
         fs = reinterpret_cast<double*>(smem);
         is = reinterpret_cast<unsigned long long*>(fs + (size_t)nF * THREADS);
         hist = reinterpret_cast<uint2*>(is + (size_t)nI * THREADS);
-        E = reinterpret_cast<float*>(hist + (THREADS / 32) * kHistWordsPerWarp);
+        E = reinterpret_cast<float*>(hist + ((sp.flags & VU_STAT_CALIB) ? (THREADS / 32) * kHistWordsPerWarp : 0));
+        phist = reinterpret_cast<int*>(E + ((sp.flags & VU_STAT_CALIB) ? VU_N_UNC * kEdgePad : 0));
+        pT = reinterpret_cast<float*>(phist + kPlattWords);
     }
 };
 
@@ -287,9 +306,10 @@ __device__ __forceinline__ void stats_sync() {
     else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(THREADS) : "memory");
 }
 
-template <int THREADS, int BAR = 0, int TID0 = 0>
+template <int THREADS, int BAR = 0, int TID0 = 0, int REP = 16>
 __device__ __noinline__ void stats_init(const StatParams& sp, void* smem) {
-    StatsLayout<THREADS> L(sp, smem);
+    StatsLayout<THREADS, REP> L(sp, smem);
+    constexpr int kHistWordsPerWarp = StatsLayout<THREADS, REP>::kHistWordsPerWarp;
     for (int t = ((int)threadIdx.x - TID0); t < (L.nF + L.nI) * THREADS; t += THREADS) reinterpret_cast<unsigned long long*>(smem)[t] = 0ull;
     if (sp.flags & VU_STAT_CALIB) {
         for (int t = ((int)threadIdx.x - TID0); t < (THREADS / 32) * kHistWordsPerWarp; t += THREADS) L.hist[t] = make_uint2(0u, 0u);
@@ -298,15 +318,25 @@ __device__ __noinline__ void stats_init(const StatParams& sp, void* smem) {
             L.E[t] = (e >= 1 && e <= VU_N_EDGES) ? sp.calib[k].edge[e - 1] : __int_as_float(0x7fc00000);
         }
     }
+    if (sp.flags & VU_STAT_PLATT_FIT) {
+        for (int t = ((int)threadIdx.x - TID0); t < kPlattWords; t += THREADS) L.phist[t] = 0;
+        for (int t = ((int)threadIdx.x - TID0); t < kPlattTab; t += THREADS) {
+            const float e = t <= VU_N_PLATT_BINS ? sp.platt_edge[t] : __int_as_float(0x7fc00000);
+            L.pT[t] = e;
+            L.pT[kPlattTab + t] = t < VU_N_PLATT_BINS ? 1.0f / e : 0.f;
+        }
+    }
     stats_sync<THREADS, BAR>();
 }
 
 // Add this CTA's partials into image row b and clear them.  nvox = voxels of image b
 // the CTA went through since the last flush.  Called by every thread of the CTA.
-template <int THREADS, int BAR = 0, int TID0 = 0>
+template <int THREADS, int BAR = 0, int TID0 = 0, int REP = 16>
 __device__ __noinline__ void stats_flush(const StatParams& sp, void* smem, long long b, long long nvox) {
     stats_sync<THREADS, BAR>();
-    StatsLayout<THREADS> L(sp, smem);
+    StatsLayout<THREADS, REP> L(sp, smem);
+    constexpr int kHistRep = REP;
+    constexpr int kHistWordsPerWarp = StatsLayout<THREADS, REP>::kHistWordsPerWarp;
     constexpr int WARPS = THREADS / 32;
     const int warp = ((int)threadIdx.x - TID0) >> 5, lane = ((int)threadIdx.x - TID0) & 31;
     const unsigned flags = sp.flags;
@@ -400,6 +430,21 @@ __device__ __noinline__ void stats_flush(const StatParams& sp, void* smem, long 
             }
         }
     }
+    if (flags & VU_STAT_PLATT_FIT) {  // dataset-level: not tied to the image row
+        for (int t = ((int)threadIdx.x - TID0); t < VU_N_UNC * VU_N_PLATT_BINS; t += THREADS) {
+            int* h = L.phist + t * 4;
+            const int tot = h[0], pos = h[1];
+            if (tot) {
+                const long long q = (long long)h[2] * (1 << kPlattQSplit) + h[3];
+                const int bin = t % VU_N_PLATT_BINS;
+                atomicAdd(reinterpret_cast<unsigned long long*>(sp.platt_i64) + 2 * t, (unsigned long long)tot);
+                if (pos) atomicAdd(reinterpret_cast<unsigned long long*>(sp.platt_i64) + 2 * t + 1, (unsigned long long)pos);
+                // sum of u over the bin = edge * (count + sum((u / edge - 1)))
+                atomicAdd(sp.platt_f64 + t, (double)L.pT[bin] * ((double)tot + (double)q * (1.0 / (double)(1 << kPlattQBits))));
+                h[0] = 0; h[1] = 0; h[2] = 0; h[3] = 0;
+            }
+        }
+    }
     if (((int)threadIdx.x - TID0) == 0 && nvox) atomicAdd(irow + VU_I64_NVOX, (unsigned long long)nvox);
     stats_sync<THREADS, BAR>();
 }
@@ -410,24 +455,24 @@ struct StatsCursor {
     int cur_b, vt_begin;
     __device__ __forceinline__ StatsCursor() : cur_b(-1), vt_begin(0) {}
     // top of every tile: tile index vt inside image b, tile_vox voxels per tile
-    template <int BAR = 0, int TID0 = 0>
+    template <int BAR = 0, int TID0 = 0, int REP = 16>
     __device__ __forceinline__ void enter(const StatParams& sp, void* smem, int b, int vt, long long tile_vox) {
         if (b != cur_b || (long long)(vt - vt_begin) * (tile_vox / THREADS) >= kMaxVoxPerFlush) {
             if (cur_b >= 0) {
                 const long long end = (b != cur_b) ? sp.V : (long long)vt * tile_vox;
-                stats_flush<THREADS, BAR, TID0>(sp, smem, cur_b, end - (long long)vt_begin * tile_vox);
+                stats_flush<THREADS, BAR, TID0, REP>(sp, smem, cur_b, end - (long long)vt_begin * tile_vox);
             }
             cur_b = b;
             vt_begin = vt;
         }
     }
     // after the last tile (vt = its index inside the image)
-    template <int BAR = 0, int TID0 = 0>
+    template <int BAR = 0, int TID0 = 0, int REP = 16>
     __device__ __forceinline__ void finish(const StatParams& sp, void* smem, int last_vt, long long tile_vox) {
         if (cur_b >= 0) {
             long long end = (long long)(last_vt + 1) * tile_vox;
             end = end > sp.V ? sp.V : end;
-            stats_flush<THREADS, BAR, TID0>(sp, smem, cur_b, end - (long long)vt_begin * tile_vox);
+            stats_flush<THREADS, BAR, TID0, REP>(sp, smem, cur_b, end - (long long)vt_begin * tile_vox);
         }
     }
 };
@@ -436,7 +481,7 @@ struct StatsCursor {
 // the slab is read with no-allocate loads), so that the statistics phase does not wait on HBM.
 template <int VEC>
 __device__ __forceinline__ void stats_prefetch_gt(const StatParams& sp, long long b, long long v) {
-    if (!(sp.flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC)) || !sp.gt.data) return;
+    if (!(sp.flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC | VU_STAT_PLATT_FIT)) || !sp.gt.data) return;
     const long long esz = sp.gt.dtype == VU_GT_U8 ? 1 : 8;
     const char* base = reinterpret_cast<const char*>(sp.gt.data) + (b * sp.gt.sb + v * sp.gt.sv) * esz;
     for (int r = 0; r < sp.gt.R; ++r) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (long long)r * sp.gt.sr * esz));
@@ -482,14 +527,18 @@ __device__ __forceinline__ void fvec_unpack(float v, float (&x)[1]) { x[0] = v; 
 #ifndef VU_STATS_INLINE
 #define VU_STATS_INLINE __forceinline__
 #endif
-template <int VEC, int THREADS, typename GT, int TID0 = 0>
+// FL: the statistics mask as a compile-time constant (the caller guarantees sp.flags == FL, all three uncertainty
+// types present and no label LUT), or kRuntimeFlags.  REP: histogram replicas per warp (16 or 32).
+template <int VEC, int THREADS, typename GT, int TID0 = 0, int REP = 16, unsigned FL = kRuntimeFlags>
 __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, bool active, long long b, long long v,
                                           typename FVec<VEC>::type u0, typename FVec<VEC>::type u1,
                                           typename FVec<VEC>::type u2, unsigned labels_packed) {
     using G = typename std::conditional<sizeof(GT) == 1, int, long long>::type;
     using GAcc = typename std::conditional<sizeof(GT) == 1, int, double>::type;
     constexpr int RB = sizeof(GT) == 1 ? 4 : (VEC == 4 ? 1 : 2);  // raters fetched together
-    StatsLayout<THREADS> cs(sp, smem);
+    StatsLayout<THREADS, REP> cs(sp, smem);
+    constexpr int kHistRep = REP;
+    constexpr int kHistWordsPerWarp = StatsLayout<THREADS, REP>::kHistWordsPerWarp;
     float u[VU_N_UNC][VEC];
     int label[VEC];
     fvec_unpack(u0, u[0]);
@@ -497,7 +546,8 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
     fvec_unpack(u2, u[2]);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) label[j] = (int)((labels_packed >> (8 * j)) & 0xffu);
-    const unsigned flags = sp.flags, mask = sp.unc_mask;
+    const unsigned flags = (FL == kRuntimeFlags) ? sp.flags : FL, mask = (FL == kRuntimeFlags) ? sp.unc_mask : 7u;
+    const uint8_t* lut = (FL == kRuntimeFlags) ? sp.lut : nullptr;
     const int tid = (int)threadIdx.x - TID0, lane = tid & 31;
 
     if (active && (flags & (VU_STAT_IMAGE_SUM | VU_STAT_NCC))) {
@@ -534,7 +584,7 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
         for (int j = 0; j < VEC; ++j) n += (label[j] > 0);
         if (n) cs.is[IS_AREA * THREADS + tid] += (unsigned long long)n;
     }
-    if (!(flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC))) return;
+    if (!(flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC | VU_STAT_PLATT_FIT))) return;
 
     int n_valid[VEC], n_correct[VEC];
     GAcc gsum[VEC], gsq[VEC];
@@ -544,7 +594,7 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
     if (active && R > 0) {
         G cmp[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) cmp[j] = (G)(sp.lut ? (int)__ldg(sp.lut + label[j]) : label[j]);
+        for (int j = 0; j < VEC; ++j) cmp[j] = (G)(lut ? (int)__ldg(lut + label[j]) : label[j]);
         const bool has_ign = sp.gt.has_ignore != 0;
         const G ign = (G)sp.gt.ignore;
 #pragma unroll 1
@@ -606,9 +656,39 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
                 cs.fs[(FS_GU + k) * THREADS + tid] += sgu[k];
             }
     }
-    if (flags & VU_STAT_CALIB) {  // every lane of the warp walks through here: the half-warp phases are warp-synchronous
+    if (flags & VU_STAT_PLATT_FIT) {
+#pragma unroll
+        for (int k = 0; k < VU_N_UNC; ++k) {
+            if (!((mask >> k) & 1)) continue;
+            int* hk = cs.phist + k * (VU_N_PLATT_BINS * 4);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const int nv = n_valid[j];
+                if (active && nv > 0) {
+                    const float x = u[k][j];
+                    // candidate bin from log10(u), settled exactly by the two neighbouring edges (ace.py:117-126)
+                    float lg;
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(x));
+                    int b0 = __float2int_rd(fmaf(lg, 0.30102999566f * (256.0f / 14.0f), 12.0f * 256.0f / 14.0f));
+                    b0 = b0 < 0 ? 0 : (b0 > VU_N_PLATT_BINS - 1 ? VU_N_PLATT_BINS - 1 : b0);
+                    int bin = b0 + (x >= cs.pT[b0 + 1] ? 1 : 0) - (x < cs.pT[b0] ? 1 : 0);
+                    bin = bin < 0 ? 0 : (bin > VU_N_PLATT_BINS - 1 ? VU_N_PLATT_BINS - 1 : bin);
+                    bin = (x != x) ? VU_N_PLATT_BINS - 1 : bin;  // np.digitize sends NaN past the last edge
+                    float rel = fmaf(x, cs.pT[kPlattTab + bin], -1.0f);
+                    rel = fminf(fmaxf(rel, -1.0f), 2.0f);  // out-of-range values are clamped into the end bins (NaN -> -1)
+                    const int q = __float2int_rn(rel * (float)(1 << kPlattQBits)) * nv;
+                    int* h = hk + bin * 4;
+                    atomicAdd(h, nv);
+                    if (n_correct[j]) atomicAdd(h + 1, n_correct[j]);
+                    atomicAdd(h + 2, q >> kPlattQSplit);
+                    atomicAdd(h + 3, q & ((1 << kPlattQSplit) - 1));
+                }
+            }
+        }
+    }
+    if (flags & VU_STAT_CALIB) {  // every lane of the warp walks through here (the half-warp phases are warp-synchronous)
         uint2* hw = cs.hist + (tid >> 5) * kHistWordsPerWarp + (lane & (kHistRep - 1));
-        const bool upper = lane >= kHistRep;
+        const bool upper = lane >= kHistRep;  // REP == 32: never
         unsigned long long nan_tot = 0, nan_tru = 0;
 #pragma unroll
         for (int k = 0; k < VU_N_UNC; ++k) {
@@ -620,27 +700,34 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 const int nv = n_valid[j];
-                bool hit = active && nv > 0;
-                int bin = 0, q = 0;
-                if (hit) {
-                    const float x = u[k][j];
-                    if (x != x) {
-                        hit = false;
-                        nan_tot += (unsigned long long)nv << (k * kPackBits);
-                        nan_tru += (unsigned long long)n_correct[j] << (k * kPackBits);
-                    } else {
-                        const float conf = platt_conf(x, cal.a, cal.b, cal.identity);
-                        bin = calib_bin(E, cal.increasing, x, conf);
-                        q = __float2int_rn((conf - (float)bin * 0.05f) * (float)(1 << kQBits)) * nv;
-                        bin0 += bin == 0 ? conf * (float)nv : 0.f;
-                    }
+                const float x = u[k][j];
+                const bool is_nan = x != x;
+                const bool sample = active && nv > 0;
+                const bool hit = sample && !is_nan;
+                // computed unconditionally (garbage for lanes that do not hit, which add nothing)
+                const float conf = platt_conf(x, cal.a, cal.b, cal.identity);
+                int bin = calib_bin(E, cal.increasing, x, conf);
+                bin = hit ? bin : 0;
+                const int q = __float2int_rn((conf - (float)bin * 0.05f) * (float)(1 << kQBits)) * nv;
+                bin0 += (hit && bin == 0) ? conf * (float)nv : 0.f;
+                if (sample && is_nan) {  // np.digitize puts NaN past the last edge: slot 20, counted in the integer slots
+                    nan_tot += (unsigned long long)nv << (k * kPackBits);
+                    nan_tru += (unsigned long long)n_correct[j] << (k * kPackBits);
                 }
-                const unsigned inc = (unsigned)nv | ((unsigned)n_correct[j] << 16);
+                const unsigned inc = hit ? ((unsigned)nv | ((unsigned)n_correct[j] << 16)) : 0u;
+                const unsigned qq = hit ? (unsigned)q : 0u;
                 uint2* h = hk + bin * kHistRep;
-                if (hit && !upper) { uint2 w = *h; w.x += inc; w.y += (unsigned)q; *h = w; }
-                __syncwarp();
-                if (hit && upper) { uint2 w = *h; w.x += inc; w.y += (unsigned)q; *h = w; }
-                __syncwarp();
+                if (kHistRep == 32) {
+                    // one replica per lane: plain read-modify-write, lanes that do not hit add zero to bin 0
+                    uint2 w = *h;
+                    w.x += inc; w.y += qq;
+                    *h = w;
+                } else {
+                    if (!upper) { uint2 w = *h; w.x += inc; w.y += qq; *h = w; }
+                    __syncwarp();
+                    if (upper) { uint2 w = *h; w.x += inc; w.y += qq; *h = w; }
+                    __syncwarp();
+                }
             }
             if (bin0 != 0.f) cs.fs[(FS_BIN0 + k) * THREADS + tid] += (double)bin0;
         }
@@ -648,16 +735,16 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
     }
 }
 
-template <int VEC, int THREADS, int TID0 = 0>
+template <int VEC, int THREADS, int TID0 = 0, int REP = 16, unsigned FL = kRuntimeFlags>
 __device__ __forceinline__ void stats_tile(const StatParams& sp, void* smem, bool active, long long b, long long v,
                                            const float (&u)[VU_N_UNC][VEC], const int (&label)[VEC]) {
     unsigned lp = 0;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) lp |= (unsigned)(label[j] & 0xff) << (8 * j);
     if (sp.gt.dtype == VU_GT_I64)
-        stats_tile_t<VEC, THREADS, long long, TID0>(sp, smem, active, b, v, fvec_pack(u[0]), fvec_pack(u[1]), fvec_pack(u[2]), lp);
+        stats_tile_t<VEC, THREADS, long long, TID0, REP, FL>(sp, smem, active, b, v, fvec_pack(u[0]), fvec_pack(u[1]), fvec_pack(u[2]), lp);
     else
-        stats_tile_t<VEC, THREADS, uint8_t, TID0>(sp, smem, active, b, v, fvec_pack(u[0]), fvec_pack(u[1]), fvec_pack(u[2]), lp);
+        stats_tile_t<VEC, THREADS, uint8_t, TID0, REP, FL>(sp, smem, active, b, v, fvec_pack(u[0]), fvec_pack(u[1]), fvec_pack(u[2]), lp);
 }
 
 }  // namespace vu

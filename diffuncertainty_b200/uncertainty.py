@@ -143,7 +143,7 @@ def fused_pass(softmax_pred: torch.Tensor, gt: Optional[GroundTruth] = None, *, 
                thresholds: Optional[Sequence[float]] = None, calib=None, label_lut: Optional[torch.Tensor] = None,
                want_maps: bool = True, want_labels: bool = True,
                stats_out: Optional[tuple] = None, maps_out: Optional[Dict[str, torch.Tensor]] = None,
-               labels_out: Optional[torch.Tensor] = None) -> FusedResult:
+               labels_out: Optional[torch.Tensor] = None, platt_fit=None) -> FusedResult:
     """One launch over ``softmax_pred`` of shape (P, B, C, *S) (test_2D.py:1277).
 
     stats      : OR of _lib.STAT_* flags
@@ -151,6 +151,7 @@ def fused_pass(softmax_pred: torch.Tensor, gt: Optional[GroundTruth] = None, *, 
     calib      : three ``calibration.PlattEdges`` for STAT_CALIB
     stats_out  : optional (stats_f64, stats_i64) device tensors to accumulate
                  into (rows = images of this batch)
+    platt_fit  : a ``calibration.PlattFitAccumulator`` for STAT_PLATT_FIT (dataset-level buffers)
     maps_out   : optional preallocated contiguous fp32 (B, *S) tensors keyed "TU","AU","EU"
                  (or "pred_entropy" when P == 1); labels_out: preallocated uint8 (B, *S)
     """
@@ -220,6 +221,11 @@ def fused_pass(softmax_pred: torch.Tensor, gt: Optional[GroundTruth] = None, *, 
             if label_lut.dtype != torch.uint8 or label_lut.numel() != 256 or not label_lut.is_cuda:
                 raise ValueError("label_lut must be a CUDA uint8 tensor with 256 entries")
             a.calib_label_lut = label_lut.data_ptr()
+        if stats & _lib.STAT_PLATT_FIT:
+            if platt_fit is None:
+                raise ValueError("STAT_PLATT_FIT needs `platt_fit` (a calibration.PlattFitAccumulator)")
+            a.platt_fit = C.pointer(platt_fit.edges)
+            a.platt_i64, a.platt_f64 = platt_fit.counts.data_ptr(), platt_fit.sums.data_ptr()
         sf = si = None
         if stats:
             if stats_out is not None:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VU_ABI_VERSION 1
+#define VU_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VU_API __attribute__((visibility("default")))
@@ -61,6 +61,11 @@ typedef enum vu_status {
 #define VU_STAT_DICE 0x08u      /* test_2D.py:878-886 (needs gt)              */
 #define VU_STAT_CALIB 0x10u     /* ace.py:350-356, 431-437 (needs gt)         */
 #define VU_STAT_NCC 0x20u       /* ncc.py:17-27 + experiment_dataloader.py:283*/
+#define VU_STAT_PLATT_FIT 0x40u /* ace.py:117-136: the 256-bin data the Platt fit is
+                                   run on (validation split; needs gt).  Dataset
+                                   level: accumulates into platt_i64 / platt_f64,
+                                   not into the per-image rows                   */
+#define VU_N_PLATT_BINS 256     /* ace.py:17,31: np.logspace(-12, 2, 257) edges  */
 
 /* ---- layout of one row of the per-image statistics buffers --------------- */
 /* double row (VU_F64_COLS doubles per image)                                 */
@@ -121,6 +126,15 @@ typedef struct vu_calib {
     int32_t mode;
 } vu_calib;
 
+/* Binning of the Platt-fit data (ace.py:31,117-126): sample u falls into bin
+ * #{k : u >= edge_k} - 1, clamped to [0, 255] (NaN -> 255).  edge_u[k] is the
+ * smallest float32 >= the float64 edge k, so the float32 comparison has the
+ * truth value of NumPy's float64 one.  Fill with vu_platt_fit_edges_host, or
+ * from np.logspace itself for bit-exact parity with NumPy's pow.              */
+typedef struct vu_platt_fit {
+    float edge_u[VU_N_PLATT_BINS + 1];
+} vu_platt_fit;
+
 typedef struct vu_fused_args {
     uint32_t struct_size; /* sizeof(vu_fused_args), ABI check                 */
     uint32_t stat_flags;  /* VU_STAT_* or 0                                   */
@@ -143,6 +157,12 @@ typedef struct vu_fused_args {
     const uint8_t* calib_label_lut;
     double* stats_f64;  /* (B, VU_F64_COLS), accumulated; NULL iff flags == 0 */
     int64_t* stats_i64; /* (B, VU_I64_COLS), accumulated                      */
+    /* VU_STAT_PLATT_FIT: dataset-level outputs, accumulated
+     *   platt_i64 (3, 256, 2): samples, correct samples per uncertainty type and bin
+     *   platt_f64 (3, 256)   : sum of the uncertainties of the samples              */
+    const vu_platt_fit* platt_fit; /* HOST pointer; read during the call      */
+    int64_t* platt_i64;
+    double* platt_f64;
 } vu_fused_args;
 
 /* ABI / build info ---------------------------------------------------------- */
@@ -150,7 +170,7 @@ VU_API int vu_abi_version(void);
 VU_API const char* vu_build_info(void); /* "sm_100a nvcc 12.9 ..."                   */
 VU_API const char* vu_last_error(void); /* text of the last CUDA error on this thread*/
 VU_API int vu_device_check(void);       /* VU_OK if the current device is sm_100     */
-VU_API int vu_struct_size(int which);   /* 0 vu_fused_args, 1 vu_map_stats_args, 2 vu_calib:
+VU_API int vu_struct_size(int which);   /* 0 vu_fused_args, 1 vu_map_stats_args, 2 vu_calib, 3 vu_platt_fit:
                                     lets a binding verify its struct layout   */
 
 /* The fused streaming pass.  Replaces, for a whole batch in one launch:
@@ -187,6 +207,9 @@ typedef struct vu_map_stats_args {
                                  the variance of the gt raters               */
     double* stats_f64;
     int64_t* stats_i64;
+    const vu_platt_fit* platt_fit; /* HOST pointer (VU_STAT_PLATT_FIT)        */
+    int64_t* platt_i64;            /* (3, 256, 2), accumulated                */
+    double* platt_f64;             /* (3, 256), accumulated                   */
 } vu_map_stats_args;
 VU_API int vu_map_stats(const vu_map_stats_args* args, void* stream);
 
@@ -211,6 +234,8 @@ VU_API int vu_border_count(const uint8_t* labels, int64_t B, int64_t d0, int64_t
  * through the reference's float32 Platt expression (ace.py:329) by bisection
  * over float32 bit patterns.  Fills calib->edge_u / increasing from a, b.    */
 VU_API int vu_platt_invert_edges_host(double a, double b, vu_calib* calib);
+/* Host helper: the 257 edges 10^(-12 + 14 k / 256) rounded up to float32.     */
+VU_API int vu_platt_fit_edges_host(vu_platt_fit* out);
 
 /* Deterministic synthetic slab for benchmarks and smoke tests:
  * softmax(scale * N(0,1)) over C, from a counter-based RNG keyed by

@@ -217,13 +217,79 @@ def ncc_aurc_cases(ref):
     return out
 
 
+def platt_fit_cases(ref):
+    """The reference's platt_scale_params (ace.py:14-285) run unmodified on a small in-memory validation set; its call to
+    sklearn's fit is observed (not replaced) to record the compressed per-bin samples it builds."""
+    import pathlib
+    import types
+    rng = np.random.default_rng(17)
+    out = {}
+    specs = {"lidc_like": dict(n_cls=2, ignore=None, R=4, n_img=3), "gta_like_ignore": dict(n_cls=19, ignore=255, R=2, n_img=2)}
+    H, W = 24, 40
+    for name, s in specs.items():
+        images = []
+        for i in range(s["n_img"]):
+            pred = rng.integers(0, s["n_cls"], (H, W)).astype(np.uint8)
+            maps = {}
+            for unc in ("TU", "AU", "EU"):
+                m = (10.0 ** rng.uniform(-9, -0.2, (H, W))).astype(np.float32)
+                m[0, :5] = 0.0            # below the first edge: clamped into bin 0
+                m[1, :3] = 150.0          # above the last edge: clamped into bin 255
+                m[2, 0] = np.float32(1e-12)
+                maps[unc] = m
+            wrong = rng.random((s["R"], H, W)) < np.clip(maps["TU"] * 3, 0.02, 0.9)[None]
+            refs = np.where(wrong, rng.integers(0, max(s["n_cls"], 2), (s["R"], H, W)), pred[None]).astype(np.uint8)
+            if s["ignore"] is not None:
+                refs[rng.random(refs.shape) < 0.05] = s["ignore"]
+            images.append((refs, pred, maps))
+        captured = {}
+        real_calib = ref.ace_module.calib
+
+        def spy(F, y, sample_weight=None, _store=captured, _real=real_calib):
+            _store.setdefault("calls", []).append((np.array(F), np.array(y), np.array(sample_weight)))
+            return _real(F, y, sample_weight=sample_weight)
+
+        with tempfile.TemporaryDirectory() as td:
+            loader = types.SimpleNamespace(
+                exp_version=types.SimpleNamespace(unc_types=["TU", "AU", "EU"], exp_path=pathlib.Path(td)),
+                image_ids=list(range(s["n_img"])),
+                get_reference_segs=lambda i: images[i][0], get_mean_pred_seg=lambda i: images[i][1],
+                get_unc_map=lambda i, unc: images[i][2][unc])
+            ref.ace_module.calib = spy
+            try:
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    ref.platt_scale_params(loader, ignore_value=s["ignore"])
+            finally:
+                ref.ace_module.calib = real_calib
+            with open(os.path.join(td, "platt_scale_params.json")) as f:
+                params = json.load(f)
+        out[f"{name}/n_img"] = np.int64(s["n_img"])
+        out[f"{name}/ignore"] = np.int64(-999 if s["ignore"] is None else s["ignore"])
+        for i, (refs, pred, maps) in enumerate(images):
+            out[f"{name}/refs{i}"] = refs
+            out[f"{name}/pred{i}"] = pred
+            for unc in ("TU", "AU", "EU"):
+                out[f"{name}/{unc}{i}"] = maps[unc]
+        for k, unc in enumerate(("TU", "AU", "EU")):
+            F, y, w = captured["calls"][k]
+            out[f"{name}/{unc}_F"] = F
+            out[f"{name}/{unc}_y"] = y
+            out[f"{name}/{unc}_w"] = w
+            out[f"{name}/{unc}_a"] = np.float64(params[unc]["a"])
+            out[f"{name}/{unc}_b"] = np.float64(params[unc]["b"])
+    return out
+
+
 def main():
     assert ref_shim.available(), "needs /root/reference"
     ref = ref_shim.load()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(1)  # thread-count independent reduction rows (see oracle.cascade_sum_f32)
     for fname, builder in (("uncertainty.npz", uncertainty_cases), ("aggregation.npz", aggregation_cases),
-                           ("calibration.npz", calibration_cases), ("ncc_aurc.npz", ncc_aurc_cases)):
+                           ("calibration.npz", calibration_cases), ("ncc_aurc.npz", ncc_aurc_cases),
+                           ("platt_fit.npz", platt_fit_cases)):
         data = builder(ref)
         np.savez_compressed(os.path.join(GOLDEN, fname), **data)
         print(fname, len(data), "arrays", os.path.getsize(os.path.join(GOLDEN, fname)), "bytes")

@@ -360,6 +360,72 @@ def calibration_inputs(refs: np.ndarray, pred: np.ndarray, unc: np.ndarray, a: f
 
 
 # --------------------------------------------------------------------------
+# Platt-scaling fit on the validation split (evaluation/metrics/ace.py:14-285)
+# --------------------------------------------------------------------------
+N_PLATT_BINS = 256  # ace.py:17
+
+
+def platt_fit_bin_edges(n_bins: int = N_PLATT_BINS) -> np.ndarray:
+    """ace.py:31: 257 float64 edges, log-spaced over [1e-12, 1e2]."""
+    return np.logspace(-12, 2, num=n_bins + 1, dtype=np.float64)
+
+
+def platt_fit_histogram(refs: np.ndarray, pred: np.ndarray, unc: np.ndarray, ignore_value=None, n_bins: int = N_PLATT_BINS):
+    """One image's contribution to the compressed fit data (ace.py:80-137): every valid (rater, pixel)
+    pair is binned by the magnitude of its uncertainty (``np.digitize`` on the log-spaced edges, values
+    outside clamped to the end bins); per bin the sample count, the correct / wrong counts and the sum of
+    uncertainties.  Returns (total i64, pos i64, neg i64, sum_unc f64), each of length n_bins."""
+    refs = np.asarray(refs)
+    pred = np.asarray(pred)
+    correct = refs == pred[None, ...]
+    valid = (refs != ignore_value) if ignore_value is not None else np.ones(refs.shape, dtype=bool)
+    u = np.broadcast_to(unc[None, ...], refs.shape)[valid].ravel()
+    c = correct[valid].ravel().astype(np.int8)
+    total = np.zeros(n_bins, np.int64)
+    pos = np.zeros(n_bins, np.int64)
+    neg = np.zeros(n_bins, np.int64)
+    sums = np.zeros(n_bins, np.float64)
+    if u.size == 0:
+        return total, pos, neg, sums
+    idx = np.digitize(u, platt_fit_bin_edges(n_bins)) - 1
+    idx[idx < 0] = 0
+    idx[idx >= n_bins] = n_bins - 1
+    sums += np.bincount(idx, weights=u, minlength=n_bins)
+    total += np.bincount(idx, minlength=n_bins)
+    pos += np.bincount(idx[c == 1], minlength=n_bins)
+    neg += np.bincount(idx[c == 0], minlength=n_bins)
+    return total, pos, neg, sums
+
+
+def platt_fit_samples(total, pos, neg, sum_unc):
+    """ace.py:150-169: at most two weighted samples per non-empty bin, at F = -(mean uncertainty of the bin)."""
+    total = np.asarray(total)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mean_unc = np.divide(sum_unc, total, out=np.zeros_like(np.asarray(sum_unc, np.float64)), where=total > 0)
+    F: List[float] = []
+    y: List[int] = []
+    w: List[int] = []
+    for b in range(len(total)):
+        if total[b] == 0:
+            continue
+        if pos[b] > 0:
+            F.append(-mean_unc[b]); y.append(1); w.append(int(pos[b]))
+        if neg[b] > 0:
+            F.append(-mean_unc[b]); y.append(0); w.append(int(neg[b]))
+    return np.asarray(F, np.float64), np.asarray(y, np.float64), np.asarray(w, np.float64)
+
+
+def platt_fit(total, pos, neg, sum_unc) -> Tuple[float, float]:
+    """ace.py:171-178: sklearn's Platt fit on the compressed data; (0, 0) when there are no samples."""
+    from sklearn.calibration import _sigmoid_calibration
+    F, y, w = platt_fit_samples(total, pos, neg, sum_unc)
+    if len(F) == 0:
+        return 0.0, 0.0
+    a, b = _sigmoid_calibration(F, y, sample_weight=w)
+    return float(a), float(b)
+
+
+# --------------------------------------------------------------------------
 # ambiguity: NCC (evaluation/metrics/ncc.py:9-28, experiment_dataloader.py:283)
 # --------------------------------------------------------------------------
 def rater_variance_map(refs: np.ndarray) -> np.ndarray:

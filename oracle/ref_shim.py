@@ -73,6 +73,8 @@ def load() -> types.SimpleNamespace:
         normalize_uncertainty_sum=agg._normalize_uncertainty_sum,
         compute_area=shp._compute_area,
         compute_border=shp._compute_border,
+        platt_scale_params=ace.platt_scale_params,
+        ace_module=ace,
         platt_scale_confid=ace.platt_scale_confid,
         calib_stats=ace.calib_stats,
         calc_ace=ace.calc_ace,

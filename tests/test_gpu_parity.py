@@ -385,3 +385,135 @@ def test_all_fast_variants_agree(vu):
             assert tested >= 2
     finally:
         _lib.set_option("k1_variant", -1)
+
+
+def test_tma_variants_agree_with_the_other_kernels(vu):
+    """The TMA-pipelined kernel (producer / consumer / statistics warps) must give bit-identical maps and labels, exact
+    integer statistics and matching float statistics for every variant, ring depth, partial tiles and both GT dtypes."""
+    from diffuncertainty_b200 import _lib, calibration, synth
+    n = _lib.get_counter("k1_num_tma_variants")
+    assert n >= 4
+    platt = [calibration.platt_edges(a, b) for a, b in ((3.5, -1.25), (6.0, -2.0), (40.0, -0.5))]
+    thr = [0.3, 0.2, 0.02]
+    try:
+        for C, P, spatial, R in ((2, 10, (96, 1000), 4), (2, 32, (64, 132), 2), (19, 10, (40, 500), 5), (19, 20, (33, 128), 1),
+                                 (3, 7, (64, 128), 2), (4, 20, (64, 128), 1)):
+            x = synth.synth_slab(P, 3, C, spatial, seed=11, scale=5.0)
+            gt8 = synth.synth_gt(x, R, seed=11, flip=0.3, ignore_frac=0.05, ignore_value=255)
+            for gt_t, ign in ((gt8, 255), (gt8.long(), 255)):
+                gt = vu.GroundTruth(gt_t, ign)
+                _lib.set_option("k1_path", 1)        # register-streaming / generic kernels as the baseline
+                _lib.set_option("k1_variant", -2)
+                base = vu.fused_pass(x)
+                _lib.set_option("k1_variant", -1)
+                tested = 0
+                for i in range(n):
+                    for stages in (0, 2):
+                        for flags in (0, 0x07, 0x1f, 0x3f):
+                            _lib.set_option("k1_path", 1)
+                            ref = vu.fused_pass(x, gt if flags & 0x38 else None, stats=flags, thresholds=thr, calib=platt if flags & 0x10 else None)
+                            _lib.set_option("k1_path", 2)
+                            _lib.set_option("k1_tma_variant", i)
+                            _lib.set_option("k1_tma_stages", stages)
+                            try:
+                                r = vu.fused_pass(x, gt if flags & 0x38 else None, stats=flags, thresholds=thr, calib=platt if flags & 0x10 else None)
+                            except NotImplementedError:
+                                break  # variant is for another class count / cascade depth
+                            for k in ("TU", "AU", "EU"):
+                                assert torch.equal(r.maps[k], base.maps[k]), (C, P, i, stages, flags, k)
+                            assert torch.equal(r.labels, base.labels), (C, P, i, stages, flags)
+                            if flags:
+                                assert torch.equal(r.stats_i64, ref.stats_i64), (C, P, i, stages, flags)
+                                torch.testing.assert_close(r.stats_f64, ref.stats_f64, rtol=1e-6, atol=1e-9)
+                            tested += 1
+                assert tested >= 8, (C, P, tested)
+    finally:
+        _lib.set_option("k1_path", 0)
+        _lib.set_option("k1_variant", -1)
+        _lib.set_option("k1_tma_variant", -1)
+        _lib.set_option("k1_tma_stages", 0)
+
+
+def test_every_visible_device(vu):
+    """The library shares torch's CUDA runtime: a slab on cuda:1 must be processed on cuda:1."""
+    from diffuncertainty_b200 import _lib, synth
+    if torch.cuda.device_count() < 2:
+        pytest.skip("single-GPU box")
+    x0 = synth.synth_slab(6, 2, 19, (64, 128), seed=5, scale=3.0, device="cuda:0")
+    want = vu.fused_pass(x0, stats=_lib.STAT_IMAGE_SUM)
+    for d in range(1, torch.cuda.device_count()):
+        with torch.cuda.device(d):
+            xd = x0.to(f"cuda:{d}")
+            got = vu.fused_pass(xd, stats=_lib.STAT_IMAGE_SUM)
+            assert got.maps["TU"].device.index == d
+            assert torch.equal(got.maps["TU"].cpu(), want.maps["TU"].cpu()) and torch.equal(got.labels.cpu(), want.labels.cpu())
+            torch.testing.assert_close(got.stats_f64.cpu(), want.stats_f64.cpu(), rtol=1e-12, atol=0)
+
+
+def test_golden_platt_fit(vu):
+    """The 256-bin Platt-fit data (ace.py:14-285) from stored maps (vu_map_stats) and fused into the streaming pass:
+    counts bit-exact, per-bin sums and the fitted (a, b) within tolerance of what the unmodified reference produced."""
+    import os
+    from conftest import GOLDEN_DIR
+    from diffuncertainty_b200 import _lib, calibration
+    from oracle import oracle
+    with np.load(os.path.join(GOLDEN_DIR, "platt_fit.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    for name in case_names(g):
+        ign = int(g[f"{name}/ignore"])
+        ign = None if ign == -999 else ign
+        n_img = int(g[f"{name}/n_img"])
+        acc = calibration.PlattFitAccumulator()
+        want = [[np.zeros(256, np.int64), np.zeros(256, np.int64), np.zeros(256, np.int64), np.zeros(256)] for _ in range(3)]
+        for i in range(n_img):
+            maps = [g[f"{name}/{u}{i}"] for u in ("TU", "AU", "EU")]
+            acc.accumulate_maps(g[f"{name}/refs{i}"], g[f"{name}/pred{i}"], maps, ign)
+            for k in range(3):
+                for dst, src in zip(want[k], oracle.platt_fit_histogram(g[f"{name}/refs{i}"], g[f"{name}/pred{i}"], maps[k], ign)):
+                    dst += src
+        total, pos, neg, sums = acc.histograms()
+        for k, u in enumerate(("TU", "AU", "EU")):
+            assert np.array_equal(total[k], want[k][0]) and np.array_equal(pos[k], want[k][1]) and np.array_equal(neg[k], want[k][2]), (name, u)
+            inside = slice(1, 255)  # the clamped end bins hold out-of-range values whose sum is not representable in the bin's fixed point
+            np.testing.assert_allclose(sums[k][inside], want[k][3][inside], rtol=2e-6, atol=1e-30)
+            a, b = acc.fit(k)
+            np.testing.assert_allclose([a, b], [g[f"{name}/{u}_a"], g[f"{name}/{u}_b"]], rtol=2e-4)
+
+    # drop-in signature on an in-memory loader
+    import pathlib, tempfile, types, json
+    name = "lidc_like"
+    n_img = int(g[f"{name}/n_img"])
+    with tempfile.TemporaryDirectory() as td:
+        loader = types.SimpleNamespace(
+            exp_version=types.SimpleNamespace(unc_types=["TU", "AU", "EU"], exp_path=pathlib.Path(td)), image_ids=list(range(n_img)),
+            get_reference_segs=lambda i: g[f"{name}/refs{i}"], get_mean_pred_seg=lambda i: g[f"{name}/pred{i}"],
+            get_unc_map=lambda i, unc: g[f"{name}/{unc}{i}"])
+        params = calibration.platt_scale_params(loader, ignore_value=None)
+        assert json.load(open(pathlib.Path(td) / "platt_scale_params.json")) == params
+    for u in ("TU", "AU", "EU"):
+        np.testing.assert_allclose([params[u]["a"], params[u]["b"]], [g[f"{name}/{u}_a"], g[f"{name}/{u}_b"]], rtol=2e-4)
+
+
+def test_platt_fit_fused_equals_stored_maps(vu):
+    """STAT_PLATT_FIT fused into the streaming pass (both K1 forms) == the same statistic from the maps it wrote."""
+    from diffuncertainty_b200 import _lib, calibration, synth
+    try:
+        for C, P, spatial, R in ((19, 10, (40, 500), 2), (2, 10, (64, 512), 4)):
+            x = synth.synth_slab(P, 2, C, spatial, seed=3, scale=6.0)
+            gt = synth.synth_gt(x, R, seed=3, flip=0.3, ignore_frac=0.05, ignore_value=255)
+            ref = None
+            for path in (1, 2):
+                _lib.set_option("k1_path", path)
+                acc = calibration.PlattFitAccumulator()
+                res = vu.fused_pass(x, vu.GroundTruth(gt, 255), stats=_lib.STAT_PLATT_FIT | _lib.STAT_AREA, platt_fit=acc)
+                stored = calibration.PlattFitAccumulator()
+                for b in range(2):
+                    stored.accumulate_maps(gt[b], res.labels[b], [res.maps[k][b] for k in ("TU", "AU", "EU")], 255)
+                for got, want in zip(acc.histograms()[:3], stored.histograms()[:3]):
+                    assert np.array_equal(got, want), (C, path)
+                np.testing.assert_allclose(acc.histograms()[3], stored.histograms()[3], rtol=1e-9, atol=1e-30)
+                if ref is not None:
+                    assert np.array_equal(acc.histograms()[0], ref.histograms()[0])
+                ref = acc
+    finally:
+        _lib.set_option("k1_path", 0)

@@ -174,3 +174,26 @@ def test_oracle_vs_live_reference():
     risks, confids = rng.random(100), rng.random(100)
     assert ref.aurc(risks, confids) == oracle.aurc(risks, confids)
     assert ref.eaurc(risks, confids) == oracle.eaurc(risks, confids)
+
+
+def test_platt_fit_matches_golden():
+    """Oracle restatement of platt_scale_params (ace.py:14-285) against what the unmodified reference built and fitted."""
+    import os
+    from conftest import GOLDEN_DIR, case_names
+    from oracle import oracle
+    with np.load(os.path.join(GOLDEN_DIR, "platt_fit.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    for name in case_names(g):
+        ign = int(g[f"{name}/ignore"])
+        ign = None if ign == -999 else ign
+        for unc in ("TU", "AU", "EU"):
+            tot = np.zeros(256, np.int64); pos = tot.copy(); neg = tot.copy(); sums = np.zeros(256)
+            for i in range(int(g[f"{name}/n_img"])):
+                t, p, n, s = oracle.platt_fit_histogram(g[f"{name}/refs{i}"], g[f"{name}/pred{i}"], g[f"{name}/{unc}{i}"], ign)
+                tot += t; pos += p; neg += n; sums += s
+            assert np.array_equal(tot, pos + neg)
+            F, y, w = oracle.platt_fit_samples(tot, pos, neg, sums)
+            assert np.array_equal(y, g[f"{name}/{unc}_y"]) and np.array_equal(w, g[f"{name}/{unc}_w"])
+            np.testing.assert_allclose(F, g[f"{name}/{unc}_F"], rtol=1e-13)
+            a, b = oracle.platt_fit(tot, pos, neg, sums)
+            np.testing.assert_allclose([a, b], [g[f"{name}/{unc}_a"], g[f"{name}/{unc}_b"]], rtol=1e-9)
