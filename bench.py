@@ -134,6 +134,7 @@ def run_reference(args):
         return 0
     import torch
     from oracle import oracle
+    torch.set_num_threads(os.cpu_count() or 1)  # all host cores (torchrun exports OMP_NUM_THREADS=1)
     w = WORKLOAD
     V = w["spatial"][0] * w["spatial"][1]
     x, gt = make_cpu_image(0)
@@ -162,6 +163,7 @@ def run_reference(args):
 def cpu_baseline_leg(n_images: int):
     import torch
     from oracle import oracle
+    torch.set_num_threads(os.cpu_count() or 1)
     w = WORKLOAD
     V = w["spatial"][0] * w["spatial"][1]
     x, gt = make_cpu_image(0)

@@ -282,6 +282,83 @@ def platt_fit_cases(ref):
     return out
 
 
+def task_cases(ref):
+    """The reference's evaluation drivers (aggregate_uncertainties.py:133, prediction_shape_stats.py:70, ace.py:14/463,
+    ncc.py:46, aurc.py:130) run unmodified on an in-memory experiment; only their third-party hooks (medpy's load,
+    hydra's instantiate, jsbeautifier) are pointed at in-memory equivalents.  Records the JSON files they write."""
+    import pathlib
+    import types
+    import warnings
+    rng = np.random.default_rng(23)
+    H, W, R, n_img = 24, 40, 3, 4
+    ids = [f"img{i:02d}" for i in range(n_img)]
+    data = {}
+    for i in ids:
+        mean_pred = (rng.random((H, W)) < 0.35).astype(np.uint8)
+        mean_pred[8:16, 10:30] = 1
+        preds = [np.where(rng.random((H, W)) < 0.9, mean_pred, 1 - mean_pred).astype(np.uint8) for _ in range(3)]
+        maps = {u: (rng.random((H, W)) ** 3 * 0.69).astype(np.float32) for u in ("TU", "AU", "EU")}
+        refs = np.stack([np.where(rng.random((H, W)) < np.clip(maps["TU"] * 2, 0.03, 0.8), 1 - mean_pred, mean_pred) for _ in range(R)]).astype(np.uint8)
+        data[i] = dict(mean_pred=mean_pred, preds=preds, maps=maps, refs=refs)
+    agg_cfg = {
+        "patch_level": {"_target_": "evaluation.uncertainty_aggregation.aggregate_uncertainties.patch_level_aggregation", "patch_size": 10},
+        "image_level": {"_target_": "evaluation.uncertainty_aggregation.aggregate_uncertainties.image_level_aggregation"},
+        "threshold": {"_target_": "evaluation.uncertainty_aggregation.aggregate_uncertainties.threshold_aggregation"},
+        "area_normalized": {"_target_": "evaluation.uncertainty_aggregation.aggregate_uncertainties.area_normalized_aggregation", "stats_filename": "area.json"},
+        "border_normalized": {"_target_": "evaluation.uncertainty_aggregation.aggregate_uncertainties.border_normalized_aggregation", "stats_filename": "area.json"},
+    }
+    out = {"ids": np.array(ids), "agg_cfg": np.array(json.dumps(agg_cfg))}
+    for i in ids:
+        out[f"{i}/mean_pred"] = data[i]["mean_pred"]
+        out[f"{i}/preds"] = np.stack(data[i]["preds"])
+        out[f"{i}/refs"] = data[i]["refs"]
+        for u in ("TU", "AU", "EU"):
+            out[f"{i}/{u}"] = data[i]["maps"][u]
+    with tempfile.TemporaryDirectory() as td:
+        root = pathlib.Path(td)
+        ds = root / "test"
+        ds.mkdir()
+        version = types.SimpleNamespace(unc_types=["TU", "AU", "EU"], exp_path=root, pred_model="Softmax", unc_ending=".tif",
+                                        aggregations=["image_level", "threshold", "patch_level"], version_name="v0")
+        loader = types.SimpleNamespace(
+            exp_version=version, image_ids=ids, dataset_path=ds, unc_path_dict={u: ds / u for u in ("TU", "AU", "EU")},
+            get_reference_segs=lambda i: data[i]["refs"], get_mean_pred_seg=lambda i: data[i]["mean_pred"],
+            get_pred_segs=lambda i: data[i]["preds"], get_unc_map=lambda i, u: data[i]["maps"][u],
+            get_gt_unc_map=lambda i: np.var(data[i]["refs"], axis=0), dataloader=None)
+        thr = {"Softmax": {f"Mean {u} threshold": float(np.quantile(np.concatenate([data[i]["maps"][u].ravel() for i in ids]), 0.8)) for u in ("TU", "AU", "EU")}}
+        json.dump(thr, open(root / "threshold_analysis.json", "w"))
+        metrics = {i: {"metrics": {"dice": float(rng.random())}} for i in ids}
+        json.dump(metrics, open(ds / "metrics.json", "w"))
+        agg = ref.agg_module
+
+        def fake_load(path):
+            p = pathlib.Path(path)
+            return data[p.name[: -len(".tif")]]["maps"][p.parent.name], None
+
+        def fake_instantiate(cfg, **kw):
+            cfg = dict(cfg)
+            fn = getattr(agg, cfg.pop("_target_").rsplit(".", 1)[-1])
+            return fn(**cfg, **kw)
+
+        agg.load = fake_load
+        agg.hydra.utils.instantiate = fake_instantiate
+        agg.jsbeautifier.beautify = lambda s, opts: s
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref.shp_module.compute_prediction_shape_stats(loader)
+            agg.aggregate_uncertainties(loader, agg_cfg)
+            ref.ace_module.platt_scale_params(loader, ignore_value=None)
+            ref.ace_module.calibration_error(loader, ignore_value=None)
+            ref.ncc_module.main(loader)
+            ref.aurc_module.main(loader)
+        out["threshold_analysis.json"] = np.array(json.dumps(thr))
+        out["metrics.json"] = np.array(json.dumps(metrics))
+        for rel in ("test/area.json", "test/aggregated_TU.json", "test/aggregated_AU.json", "test/aggregated_EU.json",
+                    "platt_scale_params.json", "test/calibration.json", "test/ambiguity_modeling.json", "test/failure_detection.json"):
+            out[rel.split("/")[-1]] = np.array(open(root / rel).read())
+    return out
+
+
 def main():
     assert ref_shim.available(), "needs /root/reference"
     ref = ref_shim.load()
@@ -289,7 +366,7 @@ def main():
     torch.set_num_threads(1)  # thread-count independent reduction rows (see oracle.cascade_sum_f32)
     for fname, builder in (("uncertainty.npz", uncertainty_cases), ("aggregation.npz", aggregation_cases),
                            ("calibration.npz", calibration_cases), ("ncc_aurc.npz", ncc_aurc_cases),
-                           ("platt_fit.npz", platt_fit_cases)):
+                           ("platt_fit.npz", platt_fit_cases), ("tasks.npz", task_cases)):
         data = builder(ref)
         np.savez_compressed(os.path.join(GOLDEN, fname), **data)
         print(fname, len(data), "arrays", os.path.getsize(os.path.join(GOLDEN, fname)), "bytes")

@@ -75,6 +75,10 @@ def load() -> types.SimpleNamespace:
         compute_border=shp._compute_border,
         platt_scale_params=ace.platt_scale_params,
         ace_module=ace,
+        agg_module=agg,
+        shp_module=shp,
+        ncc_module=ncc,
+        aurc_module=aurc,
         platt_scale_confid=ace.platt_scale_confid,
         calib_stats=ace.calib_stats,
         calc_ace=ace.calc_ace,
