@@ -1,0 +1,64 @@
+"""CUDA-event timing of K2 (patch-level aggregation, border) and K3 (statistics on stored maps) on the BASELINE shapes
+(developer tool).   python bench/bench_k2k3.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import diffuncertainty_b200 as vu  # noqa: E402
+from diffuncertainty_b200 import _lib, aggregation, calibration, synth  # noqa: E402
+from sweep_k1 import time_call  # noqa: E402
+import ctypes as C  # noqa: E402
+
+SHAPES = {"cfg1 256x256": ((1, 256, 256), 256, 0), "cfg2 64^3": ((64, 64, 64), 128, 4), "cfg3 1024x2048": ((1, 1024, 2048), 8, 5),
+          "cfg4 128x128": ((1, 128, 128), 512, 4), "cfg5 512x1024": ((1, 512, 1024), 16, 1)}
+
+
+def main():
+    lib = _lib.load()
+    platt = [calibration.platt_edges(a, b).as_struct() for a, b in ((3.5, -1.25), (6.0, -2.0), (40.0, -0.5))]
+    for name, (dims, B, R) in SHAPES.items():
+        V = dims[0] * dims[1] * dims[2]
+        maps = [torch.rand((B, V), device="cuda") ** 3 * 0.69 for _ in range(3)]
+        labels = (torch.rand((B, V), device="cuda") < 0.3).to(torch.uint8)
+        gt = (torch.rand((B, max(R, 1), V), device="cuda") < 0.3).to(torch.uint8)
+        box = (10, 10, 10) if dims[0] > 1 else (1, 10, 10)
+        out_max = torch.empty(B, dtype=torch.float64, device="cuda")
+        out_first = torch.empty(B, dtype=torch.int64, device="cuda")
+        si = torch.zeros((B, 156), dtype=torch.int64, device="cuda")
+        sf = torch.zeros((B, 80), dtype=torch.float64, device="cuda")
+        st = _lib.current_stream_ptr()
+
+        def patch():
+            _lib.check(lib.vu_patch_max(maps[0].data_ptr(), B, dims[0], dims[1], dims[2], box[0], box[1], box[2], 0,
+                                        out_max.data_ptr(), out_first.data_ptr(), st), "patch")
+
+        def border():
+            _lib.check(lib.vu_border_count(labels.data_ptr(), B, dims[0], dims[1], dims[2], si.data_ptr(), st), "border")
+
+        a = _lib.MapStatsArgs()
+        a.struct_size = C.sizeof(_lib.MapStatsArgs)
+        a.stat_flags = 0x1f if R else 0x07
+        a.B, a.V = B, V
+        for k in range(3):
+            a.maps[k] = maps[k].data_ptr()
+            a.calib[k] = platt[k]
+            a.threshold[k] = 0.2
+        a.labels = labels.data_ptr()
+        if R:
+            a.gt.data, a.gt.dtype, a.gt.R = gt.data_ptr(), _lib.GT_U8, R
+            a.gt.stride_b, a.gt.stride_r, a.gt.stride_v = R * V, V, 1
+        a.stats_f64, a.stats_i64 = sf.data_ptr(), si.data_ptr()
+
+        def mapstats():
+            _lib.check(lib.vu_map_stats(C.byref(a), st), "map_stats")
+
+        for label, fn, nbytes in (("K2 patch_max (one map, 10^d box)", patch, 4 * V * B), ("K2 border", border, V * B),
+                                  (f"K3 map_stats flags={a.stat_flags:#x}", mapstats, (13 + R) * V * B)):
+            ms = time_call(fn, iters=10)
+            print(f"{name:16s} B={B:4d} {label:36s} {ms:8.3f} ms  {nbytes / ms / 1e6:8.1f} GB/s  {V * B / ms / 1e6:8.1f} Gvox/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,19 +15,19 @@ from conftest import GOLDEN_DIR
 pytestmark = pytest.mark.gpu
 
 
-def assert_json_close(got, want, path="", rtol=1e-5, skip=("eqace",)):
+def assert_json_close(got, want, path="", rtol=1e-5, skip=("eqace",), atol=1e-12):
     if isinstance(want, dict):
         assert isinstance(got, dict) and set(got) == set(want), (path, sorted(got), sorted(want))
         for k in want:
             if k in skip:
                 continue
-            assert_json_close(got[k], want[k], f"{path}/{k}", rtol, skip)
+            assert_json_close(got[k], want[k], f"{path}/{k}", rtol, skip, atol)
     elif isinstance(want, (list, tuple)):
         assert len(got) == len(want), path
         for i, (g, w) in enumerate(zip(got, want)):
-            assert_json_close(g, w, f"{path}[{i}]", rtol, skip)
+            assert_json_close(g, w, f"{path}[{i}]", rtol, skip, atol)
     elif isinstance(want, float):
-        np.testing.assert_allclose(got, want, rtol=rtol, atol=1e-12, err_msg=path)
+        np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, err_msg=path)
     else:
         assert got == want, (path, got, want)
 
@@ -77,7 +77,9 @@ def test_platt_and_calibration_tasks(experiment):
     assert_json_close(params, want, rtol=2e-4)
     (root / "platt_scale_params.json").write_text(str(g["platt_scale_params.json"]))  # evaluate with the reference's own fit
     tasks.calibration_error(loader, ignore_value=None)
-    assert_json_close(json.loads((ds / "calibration.json").read_text()), json.loads(str(g["calibration.json"])), rtol=1e-5)
+    # calibration errors are differences of two means in [0, 1]: compare them on that scale (the AU fit of this
+    # experiment saturates: every sample sits in the last bin and |acc - conf| is ~1e-8)
+    assert_json_close(json.loads((ds / "calibration.json").read_text()), json.loads(str(g["calibration.json"])), rtol=1e-5, atol=1e-6)
 
 
 def test_ncc_and_aurc_tasks(experiment):
