@@ -29,7 +29,8 @@ I64 = dict(THR_COUNT=0, AREA=3, BORDER=4, NVOX=5, BIN_TOTAL=6, BIN_TRUE=69, DICE
 
 class Slab(C.Structure):
     _fields_ = [("data", C.c_void_p), ("P", C.c_int64), ("B", C.c_int64), ("C", C.c_int64), ("V", C.c_int64),
-                ("stride_p", C.c_int64), ("stride_b", C.c_int64), ("stride_c", C.c_int64), ("stride_v", C.c_int64)]
+                ("stride_p", C.c_int64), ("stride_b", C.c_int64), ("stride_c", C.c_int64), ("stride_v", C.c_int64),
+                ("member_ptrs", C.c_void_p), ("member_ptrs_host", C.c_void_p)]
 
 
 class Gt(C.Structure):
@@ -51,7 +52,8 @@ class FusedArgs(C.Structure):
                 ("tu", C.c_void_p), ("au", C.c_void_p), ("eu", C.c_void_p), ("labels", C.c_void_p),
                 ("gt", Gt), ("threshold", C.c_float * N_UNC), ("calib", Calib * N_UNC),
                 ("calib_label_lut", C.c_void_p), ("stats_f64", C.c_void_p), ("stats_i64", C.c_void_p),
-                ("platt_fit", C.POINTER(PlattFit)), ("platt_i64", C.c_void_p), ("platt_f64", C.c_void_p)]
+                ("platt_fit", C.POINTER(PlattFit)), ("platt_i64", C.c_void_p), ("platt_f64", C.c_void_p),
+                ("member_labels", C.c_void_p)]
 
 
 class MapStatsArgs(C.Structure):

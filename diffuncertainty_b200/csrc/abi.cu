@@ -154,7 +154,14 @@ int vu_fused_pass(const vu_fused_args* a, void* stream) {
     if (s.P < 1 || s.B < 0 || s.C < 1 || s.V < 0) return set_error(VU_ERR_BAD_ARG, "slab sizes must be positive");
     if (s.C > 256) return set_error(VU_ERR_UNSUPPORTED, "C > 256 (labels are uint8)");
     if (s.B == 0 || s.V == 0) return VU_OK;  // empty batch: nothing to do (its data pointer may be NULL)
-    if (!s.data) return set_error(VU_ERR_BAD_ARG, "slab.data is NULL");
+    if (s.member_ptrs || s.member_ptrs_host) {
+        if (!s.member_ptrs || !s.member_ptrs_host)
+            return set_error(VU_ERR_BAD_ARG, "slab.member_ptrs needs both the device array and its host copy");
+        for (int64_t p = 0; p < s.P; ++p)
+            if (!s.member_ptrs_host[p]) return set_error(VU_ERR_BAD_ARG, "slab.member_ptrs_host holds a NULL member");
+    } else if (!s.data) {
+        return set_error(VU_ERR_BAD_ARG, "slab.data is NULL");
+    }
     StatParams st;
     const unsigned unc_mask = s.P > 1 ? 7u : 1u;
     int rc = fill_stat_params(st, a->stat_flags, unc_mask, s.V, a->gt, a->threshold, a->calib, a->calib_label_lut, nullptr,

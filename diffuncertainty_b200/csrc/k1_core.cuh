@@ -41,6 +41,8 @@ struct VoxelAcc {
     float m0s, m1s;         // scalar leftover class (ODD)
     f32x2 a0[NH], a1[NH];   // entropy sums (VEC >= 2: packed over voxels)
     float a0s, a1s;         // entropy sums (VEC == 1)
+    float bv[VEC];          // argmax of the member being added (per-member labels, test_2D.py:814-818)
+    int bi[VEC];
 
     __device__ __forceinline__ void init() {
 #pragma unroll
@@ -60,9 +62,35 @@ struct VoxelAcc {
 #pragma unroll
         for (int q = 0; q < NH; ++q) hm[q] = 0ull;
     }
+    // argmax over the classes [C0, C1) of one member, continuing from bv / bi when C0 > 0 (first max, NaN is max)
     template <int C0, int C1>
-    __device__ __forceinline__ void add_classes(const f32x2 (&xp)[(C1 - C0) * NH]) {
+    __device__ __forceinline__ void member_argmax(const f32x2* xp, float xs) {
+        if constexpr (VEC >= 2) {
+#pragma unroll
+            for (int c = C0; c < C1; ++c) {
+#pragma unroll
+                for (int q = 0; q < NH; ++q) {
+                    float x0, x1;
+                    upk2(xp[(c - C0) * NH + q], x0, x1);
+                    if (c == 0) { bv[2 * q] = x0; bi[2 * q] = 0; bv[2 * q + 1] = x1; bi[2 * q + 1] = 0; }
+                    else { argmax_step(x0, c, bv[2 * q], bi[2 * q]); argmax_step(x1, c, bv[2 * q + 1], bi[2 * q + 1]); }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                float x0, x1;
+                upk2(xp[j], x0, x1);
+                if (j == 0) { bv[0] = x0; bi[0] = 0; } else argmax_step(x0, 2 * j, bv[0], bi[0]);
+                argmax_step(x1, 2 * j + 1, bv[0], bi[0]);
+            }
+            if constexpr (ODD) argmax_step(xs, C - 1, bv[0], bi[0]);
+        }
+    }
+    template <int C0, int C1>
+    __device__ __forceinline__ void add_classes(const f32x2 (&xp)[(C1 - C0) * NH], bool want_member_label = false) {
         static_assert(VEC >= 2, "class chunks need VEC >= 2");
+        if (want_member_label) member_argmax<C0, C1>(xp, 0.f);
 #pragma unroll
         for (int c = C0; c < C1; ++c) {
 #pragma unroll
@@ -92,7 +120,8 @@ struct VoxelAcc {
     }
 
     // member number p (0-based); xp: its NP pairs, xs: the leftover value when ODD
-    __device__ __forceinline__ void add_member(const f32x2 (&xp)[NP], float xs, long long p) {
+    __device__ __forceinline__ void add_member(const f32x2 (&xp)[NP], float xs, long long p, bool want_member_label = false) {
+        if (want_member_label) member_argmax<0, C>(xp, xs);
         if constexpr (VEC >= 2) {
             f32x2 h[NH];
 #pragma unroll

@@ -18,12 +18,14 @@ extern __shared__ __align__(16) unsigned char vu_dyn_smem[];
 
 struct K1Params {
     const float* x;
+    const float* const* mptr;  // optional device array of P member base pointers (then x / sp are unused)
     long long P, B, C, V;
     long long sp, sb, sc, sv;
     float* tu;
     float* au;
     float* eu;
     uint8_t* lab;
+    uint8_t* mlab;  // per-member labels (P, B, V) or NULL
     long long tiles_per_img, total_tiles;
     StatParams st;
 };
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__
             if (do_stats) stats_prefetch_gt<VEC>(prm.st, b, v);
             Acc acc;
             acc.init();
-            const float* row0 = prm.x + (long long)b * prm.sb + v;
+            const long long off0 = (long long)b * prm.sb + v;  // offset of this thread's first voxel inside a member
 
             f32x2 xp[G][NP];
             float xs[G];
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__
                 for (int g = 0; g < G; ++g) {
                     xs[g] = 0.f;
                     if (G == 1 || p0 + g < P) {
-                        const float* r = row0 + (p0 + g) * prm.sp;
+                        const float* r = (prm.mptr ? ld_member_ptr(prm.mptr, p0 + g) : prm.x + (p0 + g) * prm.sp) + off0;
                         if constexpr (VEC >= 2) {
 #pragma unroll
                             for (int c = 0; c < C; ++c) PairLoad<VEC>::load(r + c * prm.sc, &xp[g][c * NH]);
@@ -115,7 +117,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__
                 }
 #pragma unroll
                 for (int g = 0; g < G; ++g)
-                    if (G == 1 || p0 + g < P) acc.add_member(xp[g], xs[g], p0 + g);
+                    if (G == 1 || p0 + g < P) {
+                        acc.add_member(xp[g], xs[g], p0 + g, prm.mlab != nullptr);
+                        if (prm.mlab) VecLoad<VEC>::store_u8(prm.mlab + ((p0 + g) * prm.B + b) * V + v, acc.bi);
+                    }
             }
 
             // Pull the first members of the CTA's next tile into L2 while this tile's epilogue and statistics
@@ -124,12 +129,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__
                 const bool wrap = (vt + 1 == tpi);
                 const long long nv = wrap ? (long long)threadIdx.x * VEC : v + kTileVox;
                 if (nv < V) {
-                    const float* nrow = prm.x + (long long)(wrap ? b + 1 : b) * prm.sb + nv;
+                    const long long noff = (long long)(wrap ? b + 1 : b) * prm.sb + nv;
 #pragma unroll
                     for (int g = 0; g < PF; ++g)
                         if (g < P) {
+                            const float* nrow = (prm.mptr ? ld_member_ptr(prm.mptr, g) : prm.x + g * prm.sp) + noff;
 #pragma unroll
-                            for (int c = 0; c < C; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + g * prm.sp + c * prm.sc));
+                            for (int c = 0; c < C; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + c * prm.sc));
                         }
                 }
             }
@@ -154,6 +160,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__
 // per-member entropies accumulate in shared memory (h[p][thread]).
 // Also serves P == 1 (calculate_one_minus_msr, test_utils.py:862-864).
 // ---------------------------------------------------------------------------
+// dynamic shared memory of the generic kernel before the statistics state: entropies [P][T] (P > 1) and, for member
+// labels, best value [P][T] + best index [P][T], rounded up to 16 bytes
+__host__ __device__ inline size_t generic_smem_bytes(long long P, int threads, bool member_labels) {
+    size_t n = (P > 1 ? (size_t)P * threads * sizeof(float) : 0);
+    if (member_labels) n += (size_t)P * threads * (sizeof(float) + 1);
+    return (n + 15) / 16 * 16;
+}
+
 struct Cascade {
     float a[4];
     __device__ __forceinline__ void reset() { a[0] = a[1] = a[2] = a[3] = 0.f; }
@@ -178,7 +192,11 @@ struct Cascade {
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1Params prm, int level_k) {
     float* h_smem = reinterpret_cast<float*>(vu_dyn_smem);  // [P][THREADS] (P > 1), then the statistics state
-    void* st_smem = vu_dyn_smem + (prm.P > 1 ? (size_t)prm.P * THREADS * sizeof(float) : 0);
+    // per-member argmax state when member labels are wanted: best value [P][THREADS], best index [P][THREADS]
+    const bool want_ml = prm.mlab != nullptr;
+    float* bv_smem = h_smem + (prm.P > 1 ? (size_t)prm.P * THREADS : 0);
+    uint8_t* bi_smem = reinterpret_cast<uint8_t*>(bv_smem + (want_ml ? (size_t)prm.P * THREADS : 0));
+    void* st_smem = vu_dyn_smem + generic_smem_bytes(prm.P, THREADS, want_ml);
     const bool do_stats = prm.st.flags != 0;
     StatsCursor<THREADS> cursor;
     if (do_stats) stats_init<THREADS>(prm.st, st_smem);
@@ -201,18 +219,29 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
         float u[VU_N_UNC] = {0.f, 0.f, 0.f};
         int label = 0;
         if (active) {
-            const float* base = prm.x + (long long)b * prm.sb + v * prm.sv;
+            const long long off0 = (long long)b * prm.sb + v * prm.sv;
             if (P > 1)
                 for (long long p = 0; p < P; ++p) h[p * THREADS] = 0.f;
             float best = 0.f, tu2 = 0.f;
             for (int c = 0; c < C; ++c) {
                 Cascade cas;
                 cas.reset();
-                const float* pc = base + (long long)c * prm.sc;
+                const long long offc = off0 + (long long)c * prm.sc;
                 for (long long p = 0; p < P; ++p) {
-                    const float x = ldg_stream(pc + p * prm.sp);
+                    const float x = ldg_stream((prm.mptr ? ld_member_ptr(prm.mptr, p) : prm.x + p * prm.sp) + offc);
                     cas.add(x, p, n_full, level_k);
                     if (P > 1) h[p * THREADS] = plog2p_acc(h[p * THREADS], x);
+                    if (want_ml) {
+                        float& bvp = bv_smem[p * THREADS + threadIdx.x];
+                        uint8_t& bip = bi_smem[p * THREADS + threadIdx.x];
+                        if (c == 0) { bvp = x; bip = 0; }
+                        else {
+                            float bb = bvp;
+                            int ii = bip;
+                            argmax_step(x, c, bb, ii);
+                            bvp = bb; bip = (uint8_t)ii;
+                        }
+                    }
                 }
                 const float mean = __fdiv_rn(cas.total(), Pf);
                 if (c == 0) { best = mean; label = 0; } else argmax_step(mean, c, best, label);
@@ -234,6 +263,8 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
                 if (prm.tu) __stcs(prm.tu + o, u[0]);
             }
             if (prm.lab) prm.lab[o] = (uint8_t)label;
+            if (want_ml)
+                for (long long p = 0; p < P; ++p) prm.mlab[(p * prm.B + b) * V + v] = bi_smem[p * THREADS + threadIdx.x];
         }
         if (do_stats) {
             const float u1[VU_N_UNC][1] = {{u[0]}, {u[1]}, {u[2]}};
@@ -298,8 +329,12 @@ static bool aligned_for(const vu_fused_args* a, int vec) {
     const uintptr_t bytes = (uintptr_t)vec * 4;
     auto ok = [&](const void* p) { return p == nullptr || ((uintptr_t)p % bytes) == 0; };
     if (!ok(s.data) || !ok(a->tu) || !ok(a->au) || !ok(a->eu)) return false;
+    if (s.member_ptrs_host)
+        for (int64_t p = 0; p < s.P; ++p)
+            if (!ok(s.member_ptrs_host[p])) return false;
     if (a->labels && ((uintptr_t)a->labels % vec) != 0) return false;
-    if (s.V % vec || s.stride_p % vec || s.stride_b % vec || s.stride_c % vec) return false;
+    if (a->member_labels && ((uintptr_t)a->member_labels % vec) != 0) return false;
+    if (s.V % vec || (!s.member_ptrs && s.stride_p % vec) || s.stride_b % vec || s.stride_c % vec) return false;
     return true;
 }
 
@@ -314,9 +349,11 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     const vu_slab& s = a->slab;
     K1Params prm;
     prm.x = s.data;
+    prm.mptr = s.member_ptrs;
     prm.P = s.P; prm.B = s.B; prm.C = s.C; prm.V = s.V;
     prm.sp = s.stride_p; prm.sb = s.stride_b; prm.sc = s.stride_c; prm.sv = s.stride_v;
     prm.tu = a->tu; prm.au = a->au; prm.eu = a->eu; prm.lab = a->labels;
+    prm.mlab = a->member_labels;
     prm.st = st;
 
     const int sms = device_sm_count();
@@ -367,8 +404,8 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     // generic path
     constexpr int T = 64;
     const size_t max_dyn = 160 * 1024;
-    size_t dyn = (size_t)(s.P > 1 ? s.P : 0) * T * sizeof(float) + stats_smem_bytes(st.flags, st.gt.R, T);
-    if (dyn > max_dyn) return set_error(VU_ERR_UNSUPPORTED, "P too large for the generic kernel (P*256 B of shared memory)");
+    size_t dyn = generic_smem_bytes(s.P, T, a->member_labels != nullptr) + stats_smem_bytes(st.flags, st.gt.R, T);
+    if (dyn > max_dyn) return set_error(VU_ERR_UNSUPPORTED, "P too large for the generic kernel (P*256 B of shared memory, P*576 B with member labels)");
     if (s.P > (1LL << 19)) return set_error(VU_ERR_UNSUPPORTED, "P > 2^19");
     static bool attr_set = false;
     if (!attr_set) {

@@ -27,12 +27,14 @@ extern __shared__ __align__(128) unsigned char vu_tma_smem[];
 
 struct K1TmaParams {
     const float* x;
+    const float* const* mptr;  // optional device array of P member base pointers (then x / sp are unused)
     long long P, B, C, V;
     long long sp, sb, sc;
     float* tu;
     float* au;
     float* eu;
     uint8_t* lab;
+    uint8_t* mlab;  // per-member labels (P, B, V) or NULL
     long long tiles_per_img, total_tiles;
     int nstages;
     unsigned bar_offset;    // byte offsets inside dynamic shared memory
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(CT + 32 + kStatThreads, 1) k1_tma(const __grid
             const long long v0 = (long long)vt * TV;
             const long long left = V - v0;
             const unsigned row_bytes = left >= TV ? kRowBytes : (unsigned)(left * sizeof(float));
-            const float* img = prm.x + (long long)b * prm.sb + v0;
+            const long long off0 = (long long)b * prm.sb + v0;  // offset of the tile inside a member
             for (int fi = 0; fi < fills; ++fi) {
                 int p0, c0, nrows;
                 if (NCH == 1) {
@@ -214,8 +216,8 @@ __global__ void __launch_bounds__(CT + 32 + kStatThreads, 1) k1_tma(const __grid
                 for (int r = lane; r < nrows; r += 32) {
                     const int g = (NCH == 1) ? r / C : 0;
                     const int c = (NCH == 1) ? r - g * C : c0 + r;
-                    bulk_g2s(dst0 + (unsigned)r * kRowBytes, img + (long long)(p0 + g) * prm.sp + (long long)c * prm.sc, row_bytes,
-                             full0 + 8 * stage, policy);
+                    const float* mem = prm.mptr ? ld_member_ptr(prm.mptr, p0 + g) : prm.x + (long long)(p0 + g) * prm.sp;
+                    bulk_g2s(dst0 + (unsigned)r * kRowBytes, mem + off0 + (long long)c * prm.sc, row_bytes, full0 + 8 * stage, policy);
                 }
                 if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
@@ -286,7 +288,8 @@ __global__ void __launch_bounds__(CT + 32 + kStatThreads, 1) k1_tma(const __grid
                             for (int j = 0; j < Acc::NP; ++j) xp[j] = pk2(srow[(2 * j) * TV], srow[(2 * j + 1) * TV]);
                             if constexpr (Acc::ODD) xs = srow[(C - 1) * TV];
                         }
-                        acc.add_member(xp, xs, p0 + g);
+                        acc.add_member(xp, xs, p0 + g, prm.mlab != nullptr);
+                        if (prm.mlab && active) VecLoad<VEC>::store_u8(prm.mlab + ((long long)(p0 + g) * prm.B + b) * V + v, acc.bi);
                     }
                 }
             } else {
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(CT + 32 + kStatThreads, 1) k1_tma(const __grid
                             xp[c] = pk2(w.x, w.y);
                         }
                     }
-                    acc.template add_classes<C0, C1>(xp);
+                    acc.template add_classes<C0, C1>(xp, prm.mlab != nullptr);
                 };
                 if ((fi & 1) == 0) {
                     acc.begin_member();
@@ -312,6 +315,7 @@ __global__ void __launch_bounds__(CT + 32 + kStatThreads, 1) k1_tma(const __grid
                 } else {
                     load_chunk(std::integral_constant<int, CH>(), std::integral_constant<int, C>());
                     acc.end_member(fi >> 1);
+                    if (prm.mlab && active) VecLoad<VEC>::store_u8(prm.mlab + ((long long)(fi >> 1) * prm.B + b) * V + v, acc.bi);
                 }
             }
             __syncwarp();
@@ -379,7 +383,10 @@ int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     if (get_option("k1_path", 0) == 1) return 1;  // 1 = register-streaming kernels only
     if (s.stride_v != 1 || s.P < 2 || s.P > 271) return 1;
     // bulk copies need 16-byte aligned rows and sizes
-    if ((uintptr_t)s.data % 16 || s.V % 4 || s.stride_p % 4 || s.stride_b % 4 || s.stride_c % 4) return 1;
+    if ((uintptr_t)s.data % 16 || s.V % 4 || (!s.member_ptrs && s.stride_p % 4) || s.stride_b % 4 || s.stride_c % 4) return 1;
+    if (s.member_ptrs_host)
+        for (int64_t p = 0; p < s.P; ++p)
+            if ((uintptr_t)s.member_ptrs_host[p] % 16) return 1;
     const int need_levels = s.P <= 17 ? 1 : 2;
     const TmaVariant* pick = nullptr;
     if (forced >= 0 && forced < kNumTma) {
@@ -399,13 +406,15 @@ int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     if (forced < 0 && get_option("k1_path", 0) != 2 && (st.flags & heavy) && s.C * s.P < 128) return 1;
     const int vec = pick->VEC;
     auto ok = [&](const void* p, uintptr_t al) { return p == nullptr || ((uintptr_t)p % al) == 0; };
-    if (!ok(a->tu, 4 * vec) || !ok(a->au, 4 * vec) || !ok(a->eu, 4 * vec) || !ok(a->labels, vec) || s.V % vec) return 1;
+    if (!ok(a->tu, 4 * vec) || !ok(a->au, 4 * vec) || !ok(a->eu, 4 * vec) || !ok(a->labels, vec) || !ok(a->member_labels, vec) || s.V % vec) return 1;
 
     K1TmaParams prm;
     prm.x = s.data;
+    prm.mptr = s.member_ptrs;
     prm.P = s.P; prm.B = s.B; prm.C = s.C; prm.V = s.V;
     prm.sp = s.stride_p; prm.sb = s.stride_b; prm.sc = s.stride_c;
     prm.tu = a->tu; prm.au = a->au; prm.eu = a->eu; prm.lab = a->labels;
+    prm.mlab = a->member_labels;
     prm.st = st;
     const long long tile_vox = (long long)pick->CT * vec;
     prm.tiles_per_img = (s.V + tile_vox - 1) / tile_vox;

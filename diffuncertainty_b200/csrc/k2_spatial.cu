@@ -117,6 +117,98 @@ __global__ void __launch_bounds__(kT1* kT2) patch_box(const float* __restrict__ 
     }
 }
 
+// ---- 2-D maps (d0 == 1): one thread per output column, marching down the rows ---------------------------------
+// A CTA owns kTX output columns and a chunk of output rows.  Per input row: the row segment goes to shared memory
+// (double-buffered, one barrier per row), each thread forms its K-tap x-sum in float64 and keeps the last K of
+// them in registers (the row loop is unrolled by K, so the ring is indexed statically); the box sum of an output
+// row is re-formed from the ring every time, so no add/subtract drift can build up.  MODE as in patch_box.
+constexpr int kTX = 256, kRowsPerCta = 128;
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(kTX) patch_box2d(const float* __restrict__ maps, long long H, long long W, unsigned long long* max_enc,
+                                                  long long* first, double scale) {
+    __shared__ float row[2][kTX + K - 1];
+    const long long b = blockIdx.z;
+    const long long o1 = H - K + 1, o2 = W - K + 1;
+    const long long x0 = (long long)blockIdx.x * kTX, oy0 = (long long)blockIdx.y * kRowsPerCta;
+    const long long oy1 = oy0 + kRowsPerCta < o1 ? oy0 + kRowsPerCta : o1;  // output rows [oy0, oy1)
+    const int tx = threadIdx.x;
+    const long long ox = x0 + tx;
+    const bool col_ok = ox < o2;
+    const float* img = maps + b * H * W;
+    double ring[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) ring[j] = 0.0;
+    double best = 0.0;
+    bool have = false;
+    long long best_idx = 0x7fffffffffffffffLL;
+    double peak = 0.0, tol = 0.0;
+    if (MODE == 1) {
+        peak = o2d(max_enc[b]);
+        tol = 1e-8 / scale + 1e-5 * fabs(peak);
+    }
+    auto load_row = [&](long long r, int buf) {
+        const float* src = img + r * W + x0;
+        row[buf][tx] = (x0 + tx < W) ? __ldg(src + tx) : 0.f;
+        if (tx < K - 1) row[buf][kTX + tx] = (x0 + kTX + tx < W) ? __ldg(src + kTX + tx) : 0.f;
+    };
+    const long long r_end = oy1 + K - 1;  // input rows [oy0, r_end)
+    load_row(oy0, 0);
+    __syncthreads();
+    for (long long base = oy0; base < r_end; base += K) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const long long r = base + j;
+            if (r < r_end) {  // uniform
+                const int buf = (int)((r - oy0) & 1);
+                if (r + 1 < r_end) load_row(r + 1, buf ^ 1);
+                double s = 0.0;
+#pragma unroll
+                for (int dx = 0; dx < K; ++dx) s += (double)row[buf][tx + dx];
+                ring[j] = s;
+                const long long oy = r - (K - 1);
+                if (oy >= oy0 && col_ok) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int i = 0; i < K; ++i) v += ring[i];
+                    if (MODE == 0) {
+                        if (!have || v > best) { best = v; have = true; }
+                    } else if (fabs(v - peak) <= tol) {
+                        const long long idx = oy * o2 + ox;
+                        if (idx < best_idx) best_idx = idx;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    if (MODE == 0) {
+        unsigned long long e = have ? d2o(best) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(kFull, e, o);
+            e = other > e ? other : e;
+        }
+        if ((tx & 31) == 0 && e) atomicMax(max_enc + b, e);
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            long long other = __shfl_xor_sync(kFull, best_idx, o);
+            best_idx = other < best_idx ? other : best_idx;
+        }
+        if ((tx & 31) == 0 && best_idx != 0x7fffffffffffffffLL) atomicMin(first + b, best_idx);
+    }
+}
+
+template <int K>
+static void launch_patch2d(const float* maps, long long B, long long H, long long W, unsigned long long* enc, long long* first,
+                           double scale, cudaStream_t stream) {
+    const long long o1 = H - K + 1, o2 = W - K + 1;
+    dim3 grid((unsigned)((o2 + kTX - 1) / kTX), (unsigned)((o1 + kRowsPerCta - 1) / kRowsPerCta), (unsigned)B);
+    patch_box2d<K, 0><<<grid, kTX, 0, stream>>>(maps, H, W, enc, first, scale);
+    patch_box2d<K, 1><<<grid, kTX, 0, stream>>>(maps, H, W, enc, first, scale);
+}
+
 int launch_patch_max(const float* maps, long long B, long long d0, long long d1, long long d2, int k0, int k1, int k2,
                      int mean, double* out_max, long long* out_first, cudaStream_t stream) {
     const double scale = mean ? 1.0 / ((double)k0 * k1 * k2) : 1.0;
@@ -136,6 +228,15 @@ int launch_patch_max(const float* maps, long long B, long long d0, long long d1,
     unsigned long long* enc = reinterpret_cast<unsigned long long*>(out_max);
     const unsigned ib = (unsigned)((B + 255) / 256);
     patch_init<<<ib, 256, 0, stream>>>(enc, out_first, B);
+    // 2-D maps with a square box of a specialised size: the column-marching kernel (4x faster than the tiled one)
+    if (d0 == 1 && k0 == 1 && k1 == k2 && (k1 == 10 || k1 == 4 || k1 == 16) && (d1 - k1 + 1 + kRowsPerCta - 1) / kRowsPerCta <= 65535) {
+        if (k1 == 10) launch_patch2d<10>(maps, B, d1, d2, enc, out_first, scale, stream);
+        else if (k1 == 4) launch_patch2d<4>(maps, B, d1, d2, enc, out_first, scale, stream);
+        else launch_patch2d<16>(maps, B, d1, d2, enc, out_first, scale, stream);
+        patch_finish<<<ib, 256, 0, stream>>>(enc, B, scale);
+        count_launch("patch_init"); count_launch("patch_box2d"); count_launch("patch_box2d"); count_launch("patch_finish");
+        return check_launch("patch_box2d");
+    }
     dim3 grid((unsigned)(tiles_y * tiles_x), (unsigned)B);
     patch_box<0><<<grid, kT1 * kT2, smem, stream>>>(maps, d0, d1, d2, k0, k1, k2, enc, out_first, scale, tiles_y, tiles_x);
     patch_box<1><<<grid, kT1 * kT2, smem, stream>>>(maps, d0, d1, d2, k0, k1, k2, enc, out_first, scale, tiles_y, tiles_x);

@@ -38,6 +38,11 @@ __device__ __forceinline__ float ldg_stream(const float* p) {
     return r;
 }
 
+// base pointer of member p from the device array of the "stack without copying" slab form (vu_slab.member_ptrs)
+__device__ __forceinline__ const float* ld_member_ptr(const float* const* a, long long p) {
+    return reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(a) + p));
+}
+
 template <int VEC>
 struct VecLoad;
 template <>

@@ -60,6 +60,7 @@ class FusedResult:
     n_voxels: int
     n_raters: int
     stat_flags: int
+    member_labels: Optional[torch.Tensor] = None   # (P, B, *S) uint8: argmax of every member (test_2D.py:810-818)
 
     # -- per-image scores, all computed on the host in float64 from the rows --
     def _rows(self):
@@ -139,12 +140,24 @@ def _fill_gt(gt_struct: _lib.Gt, gt: Optional[GroundTruth], B: int, spatial) -> 
     return seg  # keep alive
 
 
-def fused_pass(softmax_pred: torch.Tensor, gt: Optional[GroundTruth] = None, *, stats: int = 0,
+def _members_view(members):
+    """Sequence of P tensors (B, C, *S) with identical shape / strides / dtype / device -> (P, strides, host pointer list).
+    This is the "stack without copying" form: torch.stack(groups) of test_2D.py:1277 is never materialised."""
+    first = members[0]
+    for m in members:
+        _check_slab(m, "softmax_pred member")
+        if m.shape != first.shape or m.stride() != first.stride() or m.dtype != first.dtype or m.device != first.device:
+            raise ValueError("all members must share shape, strides, dtype and device")
+    return first
+
+
+def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0,
                thresholds: Optional[Sequence[float]] = None, calib=None, label_lut: Optional[torch.Tensor] = None,
                want_maps: bool = True, want_labels: bool = True,
                stats_out: Optional[tuple] = None, maps_out: Optional[Dict[str, torch.Tensor]] = None,
-               labels_out: Optional[torch.Tensor] = None, platt_fit=None) -> FusedResult:
-    """One launch over ``softmax_pred`` of shape (P, B, C, *S) (test_2D.py:1277).
+               labels_out: Optional[torch.Tensor] = None, platt_fit=None, want_member_labels: bool = False) -> FusedResult:
+    """One launch over ``softmax_pred`` of shape (P, B, C, *S) (test_2D.py:1277) -- or over a list of P member tensors
+    (B, C, *S), which are then read where they are (no torch.stack).
 
     stats      : OR of _lib.STAT_* flags
     thresholds : three floats (TU, AU, EU) for STAT_THRESHOLD
@@ -155,30 +168,55 @@ def fused_pass(softmax_pred: torch.Tensor, gt: Optional[GroundTruth] = None, *, 
     maps_out   : optional preallocated contiguous fp32 (B, *S) tensors keyed "TU","AU","EU"
                  (or "pred_entropy" when P == 1); labels_out: preallocated uint8 (B, *S)
     """
-    _check_slab(softmax_pred, "softmax_pred")
-    if softmax_pred.dim() < 4:
-        raise ValueError(f"softmax_pred must be (P, B, C, *spatial), got shape {tuple(softmax_pred.shape)}")
-    if softmax_pred.dtype != torch.float32:
-        # the reference computes fp32 maps whatever the input dtype (test_utils.py:836);
-        # the kernels read fp32 only, so other dtypes are upcast once here
-        softmax_pred = softmax_pred.float()
+    members = None
+    if isinstance(softmax_pred, (list, tuple)):
+        # P separate member tensors (B, C, *S): read where they are, no torch.stack
+        members = [m if m.dtype == torch.float32 else m.float() for m in softmax_pred]
+        if not members:
+            raise ValueError("softmax_pred: empty member list")
+        first = _members_view(members)
+        if first.dim() < 3:
+            raise ValueError(f"every member must be (B, C, *spatial), got shape {tuple(first.shape)}")
+        if _spatial_strides_flat(first, 2) is None:
+            members = [m.contiguous() for m in members]
+            first = members[0]
+        P, (B, Cn), spatial = len(members), first.shape[:2], tuple(first.shape[2:])
+        sv, dev = _spatial_strides_flat(first, 2), first.device
+        strides = (0, first.stride(0), first.stride(1))
+    else:
+        _check_slab(softmax_pred, "softmax_pred")
+        if softmax_pred.dim() < 4:
+            raise ValueError(f"softmax_pred must be (P, B, C, *spatial), got shape {tuple(softmax_pred.shape)}")
+        if softmax_pred.dtype != torch.float32:
+            # the reference computes fp32 maps whatever the input dtype (test_utils.py:836);
+            # the kernels read fp32 only, so other dtypes are upcast once here
+            softmax_pred = softmax_pred.float()
+        P, B, Cn = softmax_pred.shape[:3]
+        spatial = tuple(softmax_pred.shape[3:])
+        sv = _spatial_strides_flat(softmax_pred, 3)
+        if sv is None:
+            softmax_pred = softmax_pred.contiguous()
+            sv = 1
+        dev = softmax_pred.device
+        strides = (softmax_pred.stride(0), softmax_pred.stride(1), softmax_pred.stride(2))
     _lib.require_device()
     lib = _lib.load()
-    P, B, Cn = softmax_pred.shape[:3]
-    spatial = tuple(softmax_pred.shape[3:])
     V = int(np.prod(spatial)) if spatial else 1
-    sv = _spatial_strides_flat(softmax_pred, 3)
-    if sv is None:
-        softmax_pred = softmax_pred.contiguous()
-        sv = 1
-    dev = softmax_pred.device
     a = _lib.FusedArgs()
     a.struct_size = C.sizeof(_lib.FusedArgs)
     a.stat_flags = int(stats)
-    a.slab.data = softmax_pred.data_ptr()
     a.slab.P, a.slab.B, a.slab.C, a.slab.V = P, B, Cn, V
-    a.slab.stride_p, a.slab.stride_b, a.slab.stride_c = softmax_pred.stride(0), softmax_pred.stride(1), softmax_pred.stride(2)
+    a.slab.stride_p, a.slab.stride_b, a.slab.stride_c = strides
     a.slab.stride_v = sv
+    ptr_keep = None
+    if members is not None:
+        host_ptrs = (C.c_void_p * P)(*[m.data_ptr() for m in members])
+        dev_ptrs = torch.tensor([m.data_ptr() for m in members], dtype=torch.int64).to(dev, non_blocking=False)
+        a.slab.member_ptrs = dev_ptrs.data_ptr()
+        a.slab.member_ptrs_host = C.cast(host_ptrs, C.c_void_p)
+        ptr_keep = (host_ptrs, dev_ptrs, members)
+    else:
+        a.slab.data = softmax_pred.data_ptr()
 
     maps: Dict[str, torch.Tensor] = {}
     with torch.cuda.device(dev):
@@ -205,6 +243,10 @@ def fused_pass(softmax_pred: torch.Tensor, gt: Optional[GroundTruth] = None, *, 
             else:
                 labels = torch.empty((B,) + spatial, dtype=torch.uint8, device=dev)
         a.labels = labels.data_ptr() if labels is not None else None
+        member_labels = None
+        if want_member_labels:
+            member_labels = torch.empty((P, B) + spatial, dtype=torch.uint8, device=dev)
+            a.member_labels = member_labels.data_ptr()
         keep = _fill_gt(a.gt, gt, B, spatial)
         if thresholds is not None:
             for k in range(3):
@@ -238,9 +280,9 @@ def fused_pass(softmax_pred: torch.Tensor, gt: Optional[GroundTruth] = None, *, 
                 si = torch.zeros((B, I64["COLS"]), dtype=torch.int64, device=dev)
             a.stats_f64, a.stats_i64 = sf.data_ptr(), si.data_ptr()
         _lib.check(lib.vu_fused_pass(C.byref(a), _lib.current_stream_ptr()), "vu_fused_pass")
-    del keep
+    del keep, ptr_keep
     return FusedResult(maps=maps, labels=labels, stats_f64=sf, stats_i64=si, n_voxels=V,
-                       n_raters=int(a.gt.R) if gt is not None else 0, stat_flags=int(stats))
+                       n_raters=int(a.gt.R) if gt is not None else 0, stat_flags=int(stats), member_labels=member_labels)
 
 
 def calculate_uncertainty(softmax_preds: torch.Tensor) -> Dict[str, torch.Tensor]:

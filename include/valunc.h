@@ -96,6 +96,12 @@ typedef struct vu_slab {
     const float* data;
     int64_t P, B, C, V;
     int64_t stride_p, stride_b, stride_c, stride_v;
+    /* Optional "stack without copying" form (torch.stack(groups) of test_2D.py:1277 materialises the slab): the P
+     * members stay where the forward passes wrote them.  member_ptrs is a DEVICE array of P base pointers, each
+     * addressing a (B, C, V) tensor with the strides above (stride_p is ignored, data may be NULL);
+     * member_ptrs_host is the same array in HOST memory (used to validate alignment).  Both NULL = `data` form.   */
+    const float* const* member_ptrs;
+    const float* const* member_ptrs_host;
 } vu_slab;
 
 /* batch["seg"]: (B, R, V) reference segmentations (test_2D.py:1122-1124).    */
@@ -163,6 +169,11 @@ typedef struct vu_fused_args {
     const vu_platt_fit* platt_fit; /* HOST pointer; read during the call      */
     int64_t* platt_i64;
     double* platt_f64;
+    /* argmax of every member, (P, B, V) uint8 contiguous; NULL = do not store.
+     * save_prediction writes one label image per member next to the mean's
+     * (test_2D.py:810-818); they are also what prediction_shape_stats
+     * (mean_pred=False) and GED consume.                                      */
+    uint8_t* member_labels;
 } vu_fused_args;
 
 /* ABI / build info ---------------------------------------------------------- */

@@ -517,3 +517,64 @@ def test_platt_fit_fused_equals_stored_maps(vu):
                 ref = acc
     finally:
         _lib.set_option("k1_path", 0)
+
+
+def test_member_labels_match_torch_argmax(vu):
+    """Per-member labels (save_prediction writes one per member, test_2D.py:810-818): bit-exact with torch.argmax on every
+    kernel form, including ties (one-hot members, --discretize) and NaN (counts as the maximum)."""
+    from diffuncertainty_b200 import _lib
+    g = torch.Generator().manual_seed(77)
+    try:
+        for P, B, C, spatial in ((10, 2, 19, (40, 500)), (5, 3, 2, (16, 16, 64)), (20, 1, 19, (8, 512)), (7, 2, 5, (9, 7)), (1, 2, 3, (8, 16))):
+            x = torch.softmax(3 * torch.randn(P, B, C, *spatial, generator=g), dim=2)
+            x[0] = torch.nn.functional.one_hot(x[0].argmax(1), C).movedim(-1, 1).float()       # exact ties at 0 and a unique 1
+            x[-1, :, :, ..., :3] = 0.25                                                             # all classes tie
+            if C > 2:
+                x[P // 2, 0, 1, ..., 5] = float("nan")
+            want = x.argmax(dim=2).to(torch.uint8)
+            for path in (0, 1, 2):
+                _lib.set_option("k1_path", path)
+                try:
+                    r = vu.fused_pass(x.cuda(), want_member_labels=True)
+                except NotImplementedError:
+                    continue  # shape not eligible for the TMA form
+                assert r.member_labels.shape == want.shape
+                assert torch.equal(r.member_labels.cpu(), want), (P, C, path)
+            _lib.set_option("k1_path", 1)
+            _lib.set_option("k1_variant", -2)   # generic kernel
+            assert torch.equal(vu.fused_pass(x.cuda(), want_member_labels=True).member_labels.cpu(), want), (P, C, "generic")
+            _lib.set_option("k1_variant", -1)
+    finally:
+        _lib.set_option("k1_path", 0)
+        _lib.set_option("k1_variant", -1)
+
+
+def test_member_list_is_read_without_stacking(vu):
+    """A list of P member tensors (the groups of test_2D.py:1134-1136 before torch.stack, :1277) gives bit-identical
+    results to the stacked slab on every kernel form; members may live anywhere (different allocations, views)."""
+    from diffuncertainty_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    try:
+        for P, B, C, spatial in ((10, 2, 19, (40, 500)), (5, 2, 2, (16, 16, 64)), (6, 2, 5, (9, 7))):
+            members = []
+            for p in range(P):
+                pad = torch.empty(1024 * (p % 3 + 1), device="cuda")  # scatter the allocations
+                big = torch.softmax(3 * torch.randn(B + 1, C, *spatial, generator=g), dim=1).cuda()
+                members.append(big[1:] if p % 2 else big[:B])               # views into larger tensors
+                del pad
+            gt = torch.randint(0, C, (B, 2, *spatial), generator=g).to(torch.uint8).cuda()
+            stacked = torch.stack([m.contiguous() for m in members])
+            for path in (0, 1, 2):
+                _lib.set_option("k1_path", path)
+                try:
+                    want = vu.fused_pass(stacked, vu.GroundTruth(gt), stats=0x0f, thresholds=[0.3, 0.2, 0.02], want_member_labels=True)
+                    got = vu.fused_pass(members, vu.GroundTruth(gt), stats=0x0f, thresholds=[0.3, 0.2, 0.02], want_member_labels=True)
+                except NotImplementedError:
+                    continue
+                for k in ("TU", "AU", "EU"):
+                    assert torch.equal(got.maps[k], want.maps[k]), (P, C, path, k)
+                assert torch.equal(got.labels, want.labels) and torch.equal(got.member_labels, want.member_labels)
+                assert torch.equal(got.stats_i64, want.stats_i64)
+                torch.testing.assert_close(got.stats_f64, want.stats_f64, rtol=1e-9, atol=1e-12)
+    finally:
+        _lib.set_option("k1_path", 0)
