@@ -77,6 +77,9 @@ EXPORTS = {
     "vu_border_count": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "vu_platt_invert_edges_host": (C.c_int, [C.c_double, C.c_double, C.POINTER(Calib)]),
     "vu_platt_fit_edges_host": (C.c_int, [C.POINTER(PlattFit)]),
+    "vu_radix_hist": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Gt), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vu_binned_calib": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Gt), C.POINTER(Calib), C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "vu_synth_slab": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int64,
                                 C.c_float, C.c_void_p]),
     "vu_synth_gt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,

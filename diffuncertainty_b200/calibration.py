@@ -73,19 +73,20 @@ class PlattEdges:
         return np.where(np.isnan(u), N_BINS, b)
 
 
-def platt_edges(a: float, b: float) -> PlattEdges:
+def platt_edges(a: float, b: float, edges: Optional[np.ndarray] = None) -> PlattEdges:
     """Invert conf(u) = 1/(1+exp(-u*a+b)) (float32, NumPy's exp) on the 19
     interior bin edges by bisection over float32 bit patterns, vectorised over
     the edges.  increasing (a >= 0): smallest u with conf(u) >= edge;
-    decreasing: largest such u.  The result is made monotone in k."""
+    decreasing: largest such u.  The result is made monotone in k.
+    ``edges``: 19 non-decreasing float64 edges to use instead of the uniform ones (the quantile bins of calc_eqace)."""
     a32 = np.float32(a)
     increasing = bool(a32 >= 0)
-    edges = bin_edges()[1:N_BINS]
+    edges = bin_edges()[1:N_BINS] if edges is None else np.asarray(edges, np.float64)
     lo = np.full(19, _ord(np.array([-np.inf], np.float32))[0], np.uint64)
     hi = np.full(19, _ord(np.array([np.inf], np.float32))[0], np.uint64)
 
     def ok(keys):
-        conf = _platt_f32(_unord(keys), float(a), float(b)).astype(np.float64)
+        conf = np.clip(_platt_f32(_unord(keys), float(a), float(b)), 0, 1).astype(np.float64)  # ace.py:333 / :379 clip
         return conf >= edges
 
     if increasing:
@@ -113,10 +114,10 @@ def platt_edges(a: float, b: float) -> PlattEdges:
     return PlattEdges(a=float(a), b=float(b), edge_u=thr.astype(np.float32), mode=1 if increasing else 0)
 
 
-def identity_edges() -> PlattEdges:
+def identity_edges(edges: Optional[np.ndarray] = None) -> PlattEdges:
     """Edges for maps that already hold confidences: the smallest float32 that
     is >= each float64 edge, so ``conf >= edge`` has the same truth value."""
-    e64 = bin_edges()[1:N_BINS]
+    e64 = bin_edges()[1:N_BINS] if edges is None else np.asarray(edges, np.float64)
     e32 = e64.astype(np.float32)
     e32 = np.where(e32.astype(np.float64) < e64, np.nextafter(e32, np.float32(np.inf)), e32).astype(np.float32)
     return PlattEdges(a=0.0, b=0.0, edge_u=e32, mode=2)
@@ -375,3 +376,112 @@ def platt_scale_params(val_exp_dataloader, ignore_value=None, n_bins: int = 256,
     with open(val_exp_dataloader.exp_version.exp_path / "platt_scale_params.json", "w") as f:
         json.dump(params, f, indent=2)
     return params
+
+
+# ---------------------------------------------------------------------------
+# eqACE: adaptive calibration error on per-image quantile bins (ace.py:378-406)
+# ---------------------------------------------------------------------------
+def _needed_ranks(total: int, n_bins: int):
+    """The order statistics np.quantile(y_prob, np.linspace(0, 1, n_bins + 1)) touches (ace.py:387-388)."""
+    from .quantile import quantile_ranks
+    lo, hi, g = quantile_ranks(total, np.linspace(0.0, 1.0, n_bins + 1))
+    return np.unique(np.concatenate([lo, hi])), lo, hi, g
+
+
+def _quantile_edges(ranks, conf_at_ranks, lo, hi, g) -> np.ndarray:
+    """ace.py:388-391: the float64 lerp of np.quantile from the order statistics, first / last edge replaced by 0 and
+    1 + 1e-8, made non-decreasing."""
+    from .quantile import lerp
+    conf = np.asarray(conf_at_ranks, np.float64)
+    edges = lerp(conf[np.searchsorted(ranks, lo)], conf[np.searchsorted(ranks, hi)], g)
+    edges[0] = 0.0
+    edges[-1] = 1.0 + 1e-8
+    return np.maximum.accumulate(edges)
+
+
+def _eqace_from_histogram(counts: np.ndarray, sums: np.ndarray, n_bins: int) -> float:
+    """ace.py:392-406 from the bincounts (slot 20 = NaN confidences, which np.clip puts into the last bin)."""
+    tot = counts[0, :n_bins].astype(np.float64).copy()
+    tru = counts[1, :n_bins].astype(np.float64).copy()
+    s = sums[:n_bins].copy()
+    tot[n_bins - 1] += counts[0, n_bins:].sum(); tru[n_bins - 1] += counts[1, n_bins:].sum(); s[n_bins - 1] += sums[n_bins:].sum()
+    nz = tot > 0
+    if not nz.any():
+        return float("nan")
+    return float((1.0 / int(nz.sum())) * np.sum(np.abs(tru[nz] / tot[nz] - s[nz] / tot[nz])))
+
+
+def _binned(map_t, labels_t, gt_struct, calib_struct, lut=None):
+    lib = _lib.load()
+    dev = map_t.device
+    counts = torch.zeros((2, 21), dtype=torch.int64, device=dev)
+    sums = torch.zeros(21, dtype=torch.float64, device=dev)
+    _lib.check(lib.vu_binned_calib(map_t.data_ptr(), labels_t.data_ptr(), map_t.numel(), C.byref(gt_struct), C.byref(calib_struct),
+                                   None if lut is None else lut.data_ptr(), counts.data_ptr(), sums.data_ptr(),
+                                   _lib.current_stream_ptr()), "vu_binned_calib")
+    return counts.cpu().numpy(), sums.cpu().numpy()
+
+
+def calc_eqace(correct, calib_confids, n_bins: int = 20) -> float:
+    """Drop-in for ace.py:378-406 on per-sample arrays: quantile bin edges from an exact GPU rank selection, the three
+    bincounts from vu_binned_calib, float64 finalisation on the host."""
+    from . import quantile as _q
+    if n_bins != N_BINS:
+        raise NotImplementedError("the GPU path supports the reference's default of 20 bins")
+    _lib.require_device()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    conf = torch.as_tensor(np.ascontiguousarray(np.asarray(calib_confids, dtype=np.float32)).ravel()) \
+        if not isinstance(calib_confids, torch.Tensor) else calib_confids.reshape(-1).float()
+    corr = torch.as_tensor(np.ascontiguousarray(np.asarray(correct)).ravel()) if not isinstance(correct, torch.Tensor) else correct.reshape(-1)
+    if conf.numel() != corr.numel():
+        raise ValueError("correct and calib_confids must have the same number of elements")
+    n = conf.numel()
+    if n == 0:
+        return float("nan")
+    conf = conf.to(dev).clamp_(0.0, 1.0).contiguous()  # ace.py:379
+    corr = corr.to(dev).to(torch.uint8).contiguous()
+    ranks, lo, hi, g = _needed_ranks(n, n_bins)
+    edges = _quantile_edges(ranks, _q.RadixSelect([conf]).select(ranks), lo, hi, g)
+    ones = torch.ones(n, dtype=torch.uint8, device=dev)  # "label" 1: a sample is correct iff correct == 1
+    gs = _lib.Gt()
+    gs.data, gs.dtype, gs.R = corr.data_ptr(), _lib.GT_U8, 1
+    gs.stride_b, gs.stride_r, gs.stride_v = n, n, 1
+    counts, sums = _binned(conf, ones, gs, identity_edges(edges[1:n_bins]).as_struct())
+    return _eqace_from_histogram(counts, sums, n_bins)
+
+
+def eqace_from_maps(reference_segs, pred_seg, unc_map, a: float, b: float, ignore_value=None, n_bins: int = 20) -> float:
+    """calc_eqace for one image straight from the stored maps (the body of calibration_error, ace.py:484-515, without
+    materialising the per-(rater, pixel) arrays): ranks are selected on the uncertainty map with each voxel weighted by its
+    number of valid raters; the Platt map is monotone, so the quantiles of the confidences are the confidences of those
+    order statistics."""
+    from . import quantile as _q
+    _lib.require_device()
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def on_device(x, dtype=None):
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=dtype))
+        return t.to(dev)
+
+    refs = on_device(reference_segs)
+    refs = refs.to(torch.uint8 if refs.dtype in (torch.uint8, torch.bool) else torch.int64).contiguous().reshape(refs.shape[0], -1)
+    pred = on_device(pred_seg).to(torch.uint8).contiguous().reshape(-1)
+    unc = on_device(unc_map, np.float32).float().contiguous().reshape(-1)
+    V = unc.numel()
+    if V == 0:
+        return float("nan")
+    sel = _q.RadixSelect([unc], [refs], ignore_value)
+    total = sel.total
+    if total == 0:
+        return float("nan")
+    increasing = bool(np.float32(a) >= 0)
+    ranks, lo, hi, g = _needed_ranks(total, n_bins)
+    u_at = sel.select(ranks if increasing else (total - 1 - ranks))  # a >= 0: conf rises with u (x = -u, ace.py:329)
+    conf = np.clip(_platt_f32(u_at, float(a), float(b)), 0, 1)
+    edges = _quantile_edges(ranks, conf, lo, hi, g)
+    gs = _lib.Gt()
+    gs.data, gs.dtype, gs.R = refs.data_ptr(), (_lib.GT_U8 if refs.dtype == torch.uint8 else _lib.GT_I64), refs.shape[0]
+    gs.stride_b, gs.stride_r, gs.stride_v = refs.numel(), V, 1
+    gs.has_ignore, gs.ignore_index = (0, 0) if ignore_value is None else (1, int(ignore_value))
+    counts, sums = _binned(unc, pred, gs, platt_edges(a, b, edges[1:n_bins]).as_struct())
+    return _eqace_from_histogram(counts, sums, n_bins)

@@ -61,6 +61,18 @@ static int gt_alignment(const vu_gt& gt, long long V) {
     return 1;
 }
 
+static int make_gt_view(GtView& v, const vu_gt* gt, long long V) {
+    memset(&v, 0, sizeof(v));
+    if (!gt || !gt->data) return VU_OK;
+    if (gt->R < 1 || gt->R > VU_MAX_RATERS) return set_error(VU_ERR_UNSUPPORTED, "gt.R must be 1..8");
+    if (gt->dtype != VU_GT_U8 && gt->dtype != VU_GT_I64) return set_error(VU_ERR_BAD_ARG, "gt.dtype");
+    v.data = gt->data; v.dtype = gt->dtype; v.R = gt->R;
+    v.sb = gt->stride_b; v.sr = gt->stride_r; v.sv = gt->stride_v;
+    v.has_ignore = gt->has_ignore; v.ignore = gt->ignore_index;
+    v.align = gt_alignment(*gt, V);
+    return VU_OK;
+}
+
 static int fill_stat_params(StatParams& st, uint32_t flags, unsigned unc_mask, long long V, const vu_gt& gt,
                             const float* thr, const vu_calib* calib, const uint8_t* lut, const double* ncc_gt_map,
                             double* f64, int64_t* i64, const vu_platt_fit* platt_fit, int64_t* platt_i64, double* platt_f64) {
@@ -253,6 +265,36 @@ int vu_platt_invert_edges_host(double a, double b, vu_calib* calib) {
         }
     }
     return VU_OK;
+}
+
+int vu_radix_hist(const float* values, int64_t n, const vu_gt* weights_gt, int32_t level, const uint32_t* prefixes, int32_t n_prefix,
+                  uint64_t* hist, void* stream) {
+    if (n < 0 || level < 0 || level > 2) return set_error(VU_ERR_BAD_ARG, "bad size / level");
+    if (level > 0 && (!prefixes || n_prefix < 1 || n_prefix > 64)) return set_error(VU_ERR_BAD_ARG, "levels 1, 2 need 1..64 prefixes");
+    if (n == 0) return VU_OK;  // an empty map has no storage: its pointer may be NULL
+    if (!values || !hist) return set_error(VU_ERR_BAD_ARG, "NULL pointer");
+    GtView gv;
+    int rc = make_gt_view(gv, weights_gt, n);
+    if (rc != VU_OK) return rc;
+    return launch_radix_hist(values, n, gv, level, prefixes, n_prefix, reinterpret_cast<unsigned long long*>(hist), (cudaStream_t)stream);
+}
+
+int vu_binned_calib(const float* map, const uint8_t* labels, int64_t V, const vu_gt* gt, const vu_calib* calib, const uint8_t* label_lut,
+                    int64_t* out_counts, double* out_sums, void* stream) {
+    if (V < 0) return set_error(VU_ERR_BAD_ARG, "negative size");
+    if (V == 0) return VU_OK;
+    if (!map || !gt || !gt->data || !calib || !out_counts || !out_sums) return set_error(VU_ERR_BAD_ARG, "NULL pointer");
+    if (calib->mode < 0 || calib->mode > 2) return set_error(VU_ERR_BAD_ARG, "vu_calib.mode");
+    GtView gv;
+    int rc = make_gt_view(gv, gt, V);
+    if (rc != VU_OK) return rc;
+    CalibDev cd;
+    cd.a = calib->a; cd.b = calib->b;
+    cd.increasing = calib->mode != VU_CALIB_PLATT_DEC;
+    cd.identity = calib->mode == VU_CALIB_IDENTITY;
+    for (int e = 0; e < VU_N_EDGES; ++e) cd.edge[e] = cd.increasing ? calib->edge_u[e] : -calib->edge_u[e];
+    return launch_binned_calib(map, labels, V, gv, cd, label_lut, reinterpret_cast<unsigned long long*>(out_counts), out_sums,
+                               (cudaStream_t)stream);
 }
 
 int vu_platt_fit_edges_host(vu_platt_fit* out) {

@@ -1,0 +1,195 @@
+// K4: exact (weighted) order statistics by radix select, and calibration histograms on arbitrary bin edges.
+//
+//   vu_radix_hist     one histogram pass of a 3-level radix select (11 + 11 + 10 bits of the order-preserving
+//                     float key).  The host walks the cumulative counts between passes (quantile.py), so any
+//                     number of maps can be folded into one selection -- find_threshold.py:98-105 takes
+//                     np.quantile over the concatenation of all validation maps -- and samples can carry an
+//                     integer weight (the number of valid raters of a voxel: ace.py:378-406 ranks one confidence
+//                     per (rater, pixel) pair).
+//   vu_binned_calib   the three bincounts of calc_eqace (ace.py:392-396) on 19 caller-given thresholds (the
+//                     per-image quantile edges pulled back onto the uncertainty axis); float64 sums.
+#include "vu_common.cuh"
+#include "vu_host.h"
+
+namespace vu {
+
+// order-preserving key of a float's bit pattern: key(a) < key(b) <=> a < b; NaN (either sign) sorts last, like np.sort
+__device__ __forceinline__ unsigned bits2key(unsigned u) {
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0xffc00000u;  // the key of the canonical quiet NaN
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// number of raters whose reference is not the ignore value (weight of voxel i); 1 without references
+__device__ __forceinline__ int sample_weight(const GtView& gt, long long i) {
+    if (!gt.data) return 1;
+    int w = 0;
+    for (int r = 0; r < gt.R; ++r) {
+        const long long off = (long long)r * gt.sr + i * gt.sv;
+        const long long g = gt.dtype == VU_GT_U8 ? (long long)__ldg(reinterpret_cast<const uint8_t*>(gt.data) + off)
+                                                 : __ldg(reinterpret_cast<const long long*>(gt.data) + off);
+        w += !(gt.has_ignore && g == gt.ignore);
+    }
+    return w;
+}
+
+constexpr int kRadixThreads = 256;
+constexpr int kMaxPrefixes = 64;
+
+__global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const float* __restrict__ values, long long n, GtView gt, int level,
+                                                                  const unsigned* __restrict__ prefixes, int n_prefix,
+                                                                  unsigned long long* hist) {
+    __shared__ unsigned h0[2048];
+    __shared__ unsigned pre[kMaxPrefixes];
+    if (level == 0)
+        for (int t = threadIdx.x; t < 2048; t += kRadixThreads) h0[t] = 0u;
+    else
+        for (int t = threadIdx.x; t < n_prefix; t += kRadixThreads) pre[t] = prefixes[t];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    // every lane of a warp runs the same number of iterations (the aggregation below is warp-collective)
+    const long long stride = (long long)gridDim.x * kRadixThreads;
+    for (long long base = (long long)blockIdx.x * kRadixThreads; base < n; base += stride) {
+        const long long i = base + threadIdx.x;
+        unsigned target = 0xffffffffu;  // slot << 11 | digit, or "nothing to add"
+        int w = 0;
+        if (i < n) {
+            const unsigned key = bits2key(__ldg(reinterpret_cast<const unsigned*>(values) + i));  // never touched as a float
+            w = sample_weight(gt, i);
+            if (w > 0) {
+                if (level == 0) {
+                    target = key >> 21;
+                } else {
+                    const unsigned p = level == 1 ? key >> 21 : key >> 10;
+                    const unsigned digit = level == 1 ? (key >> 10) & 0x7ffu : key & 0x3ffu;
+                    for (int s = 0; s < n_prefix; ++s)
+                        if (pre[s] == p) { target = ((unsigned)s << 11) | digit; break; }
+                }
+            }
+        }
+        if (level == 0) {
+            if (target != 0xffffffffu) atomicAdd(&h0[target], (unsigned)w);
+        } else {
+            // warp-aggregated: equal values are common (background pixels with u == 0), one global atomic per group
+            const unsigned grp = __match_any_sync(kFull, target);
+            unsigned sum = 0;
+#pragma unroll
+            for (int bit = 0; bit < 4; ++bit) sum += (unsigned)__popc(grp & __ballot_sync(kFull, (w >> bit) & 1)) << bit;
+            if (target != 0xffffffffu && lane == __ffs(grp) - 1) atomicAdd(hist + target, (unsigned long long)sum);
+        }
+    }
+    if (level == 0) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < 2048; t += kRadixThreads)
+            if (h0[t]) atomicAdd(hist + t, (unsigned long long)h0[t]);
+    }
+}
+
+int launch_radix_hist(const float* values, long long n, const GtView& gt, int level, const unsigned* prefixes, int n_prefix,
+                      unsigned long long* hist, cudaStream_t stream) {
+    long long blocks = (n + kRadixThreads - 1) / kRadixThreads;
+    const long long cap = (long long)device_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    radix_hist_kernel<<<(unsigned)blocks, kRadixThreads, 0, stream>>>(values, n, gt, level, prefixes, n_prefix, hist);
+    count_launch("radix_hist");
+    return check_launch("radix_hist");
+}
+
+// ---- calibration histogram on caller-given thresholds -----------------------------------------------------------
+struct BinnedParams {
+    const float* map;
+    const uint8_t* labels;
+    long long V;
+    GtView gt;
+    CalibDev cal;  // edge[k]: thresholds on u (sign-adjusted), NaN = never reached
+    const uint8_t* lut;
+    unsigned long long* counts;  // [2][21]: samples, correct samples
+    double* sums;                // [21]
+};
+
+constexpr int kBinnedThreads = 256;
+
+__global__ void __launch_bounds__(kBinnedThreads) binned_calib_kernel(const __grid_constant__ BinnedParams prm) {
+    constexpr int WARPS = kBinnedThreads / 32;
+    __shared__ double s_sum[WARPS][VU_N_BINS];
+    __shared__ int s_tot[WARPS][VU_N_BINS], s_tru[WARPS][VU_N_BINS];
+    __shared__ float thr[VU_N_EDGES];
+    for (int t = threadIdx.x; t < WARPS * VU_N_BINS; t += kBinnedThreads) {
+        (&s_sum[0][0])[t] = 0.0; (&s_tot[0][0])[t] = 0; (&s_tru[0][0])[t] = 0;
+    }
+    if (threadIdx.x < VU_N_EDGES) thr[threadIdx.x] = prm.cal.edge[threadIdx.x];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * kBinnedThreads;
+    for (long long base = (long long)blockIdx.x * kBinnedThreads; base < prm.V; base += stride) {
+        const long long i = base + threadIdx.x;
+        int bin = -1, nv = 0, nc = 0;
+        double w = 0.0;
+        if (i < prm.V) {
+            const int label = prm.labels ? (int)__ldg(prm.labels + i) : 0;
+            const long long cmp = prm.lut ? (long long)__ldg(prm.lut + label) : (long long)label;
+            for (int r = 0; r < prm.gt.R; ++r) {
+                const long long off = (long long)r * prm.gt.sr + i * prm.gt.sv;
+                const long long g = prm.gt.dtype == VU_GT_U8 ? (long long)__ldg(reinterpret_cast<const uint8_t*>(prm.gt.data) + off)
+                                                             : __ldg(reinterpret_cast<const long long*>(prm.gt.data) + off);
+                const bool valid = !(prm.gt.has_ignore && g == prm.gt.ignore);
+                nv += valid;
+                nc += valid && g == cmp;
+            }
+            if (nv > 0) {
+                const float u = __ldg(prm.map + i);
+                if (u != u) {
+                    bin = VU_N_BINS - 1;  // NaN: past the last edge
+                    w = (double)u;
+                } else {
+                    const float uu = prm.cal.increasing ? u : -u;
+                    bin = 0;
+#pragma unroll
+                    for (int k = 0; k < VU_N_EDGES; ++k) bin += (uu >= thr[k]) ? 1 : 0;  // NaN thresholds compare false
+                    // ace.py:329 in float32 (the bins do not depend on it, only the float64 sums do)
+                    float conf;
+                    if (prm.cal.identity) conf = fminf(fmaxf(u, 0.0f), 1.0f);
+                    else conf = fminf(fmaxf(__fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fadd_rn(__fmul_rn(-u, prm.cal.a), prm.cal.b)))), 0.0f), 1.0f);
+                    w = (double)conf * (double)nv;
+                }
+            }
+        }
+        // one round per distinct bin present in the warp
+        unsigned todo = __ballot_sync(kFull, bin >= 0);
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const int bsel = __shfl_sync(kFull, bin, leader);
+            const bool mine = (bin == bsel);
+            const int tot = __reduce_add_sync(kFull, mine ? nv : 0);
+            const int tru = __reduce_add_sync(kFull, mine ? nc : 0);
+            const double sw = warp_sum(mine ? w : 0.0);
+            if (lane == 0) { s_tot[warp][bsel] += tot; s_tru[warp][bsel] += tru; s_sum[warp][bsel] += sw; }
+            todo &= ~__ballot_sync(kFull, mine);
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < VU_N_BINS; t += kBinnedThreads) {
+        long long tot = 0, tru = 0;
+        double s = 0.0;
+        for (int w = 0; w < WARPS; ++w) { tot += s_tot[w][t]; tru += s_tru[w][t]; s += s_sum[w][t]; }
+        if (tot) {
+            atomicAdd(prm.counts + t, (unsigned long long)tot);
+            if (tru) atomicAdd(prm.counts + VU_N_BINS + t, (unsigned long long)tru);
+            atomicAdd(prm.sums + t, s);
+        }
+    }
+}
+
+int launch_binned_calib(const float* map, const uint8_t* labels, long long V, const GtView& gt, const CalibDev& cal, const uint8_t* lut,
+                        unsigned long long* counts, double* sums, cudaStream_t stream) {
+    BinnedParams prm;
+    prm.map = map; prm.labels = labels; prm.V = V; prm.gt = gt; prm.cal = cal; prm.lut = lut; prm.counts = counts; prm.sums = sums;
+    long long blocks = (V + kBinnedThreads - 1) / kBinnedThreads;
+    const long long cap = (long long)device_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    binned_calib_kernel<<<(unsigned)blocks, kBinnedThreads, 0, stream>>>(prm);
+    count_launch("binned_calib");
+    return check_launch("binned_calib");
+}
+
+}  // namespace vu

@@ -10,6 +10,8 @@
 
 namespace vu {
 struct StatParams;
+struct GtView;
+struct CalibDev;
 
 int set_error(int code, const char* msg);        // records msg, returns code
 int set_cuda_error(const char* where);           // records cudaGetLastError text, returns VU_ERR_CUDA
@@ -28,6 +30,10 @@ int launch_patch_max(const float* maps, long long B, long long d0, long long d1,
                      int mean, double* out_max, long long* out_first, cudaStream_t stream);
 int launch_border(const uint8_t* labels, long long B, long long d0, long long d1, long long d2, long long* stats_i64,
                   cudaStream_t stream);
+int launch_radix_hist(const float* values, long long n, const GtView& gt, int level, const unsigned* prefixes, int n_prefix,
+                      unsigned long long* hist, cudaStream_t stream);
+int launch_binned_calib(const float* map, const uint8_t* labels, long long V, const GtView& gt, const CalibDev& cal, const uint8_t* lut,
+                        unsigned long long* counts, double* sums, cudaStream_t stream);
 int launch_synth_slab(float* out, long long P, long long B, long long C, long long V, uint64_t seed,
                       long long first_image, float scale, cudaStream_t stream);
 int launch_synth_gt(uint8_t* out, const float* slab, long long P, long long B, long long C, long long V, int R,

@@ -7,12 +7,14 @@
     aurc_main(exp_dataloader)                                aurc.py:130-153                    -> failure_detection.json
     calibration_error(exp_dataloader, ignore_value)          ace.py:463-534                     -> calibration.json
     calibration_main(exp_dataloader, ignore_value)           ace.py:537-545
+    get_foreground_quantile / save_foreground_quantiles /    find_threshold.py:15-66, 80-112 -> quantile_analysis.json,
+    threshold_images_paths / find_threshold                                                      threshold_analysis.json
 
 They take the reference's ``ExperimentDataloader`` (any object with the same attributes works), load each array once
 per image instead of once per aggregation, run the arithmetic on the GPU through libvalunc and write the same JSON
 files with the same keys.  Only file discovery, JSON and the image-count sized finalisation run on the host.
-``eqace`` (ace.py:378-406, per-image quantile bins) is not built yet: the key is written
-as ``null`` unless ``eqace_fn`` is given.
+``eqace`` (ace.py:378-406, per-image quantile bins) comes from an exact GPU rank selection
+(``calibration.eqace_from_maps``); pass ``eqace_fn=None`` to skip it.
 """
 from __future__ import annotations
 
@@ -25,7 +27,7 @@ from typing import Callable, Dict, Optional
 import numpy as np
 import torch
 
-from . import _lib, aggregation as _agg, aurc as _aurc, calibration as _cal, ncc as _ncc
+from . import _lib, aggregation as _agg, aurc as _aurc, calibration as _cal, ncc as _ncc, quantile as _qt
 
 _LOCAL_TARGETS = {
     "patch_level_aggregation": _agg.patch_level_aggregation,
@@ -169,7 +171,7 @@ def aurc_main(exp_dataloader):
     return results
 
 
-def calibration_error(exp_dataloader, ignore_value=None, eqace_fn: Optional[Callable] = None):
+def calibration_error(exp_dataloader, ignore_value=None, eqace_fn: Optional[Callable] = _cal.eqace_from_maps):
     """ace.py:463-534: per image and uncertainty type the 21-slot histogram comes from one vu_map_stats launch on
     (references, prediction, uncertainty map, Platt parameters); ACE / ECE and the dataset accumulator are finalised in
     float64 on the host."""
@@ -217,10 +219,7 @@ def calibration_error(exp_dataloader, ignore_value=None, eqace_fn: Optional[Call
             t = i[_lib.I64["BIN_TRUE"]:_lib.I64["BIN_TRUE"] + 21]
             n = i[_lib.I64["BIN_TOTAL"]:_lib.I64["BIN_TOTAL"] + 21]
             ace, ece = _cal.per_image_ace_ece(s, t, n)
-            eqace = None
-            if eqace_fn is not None:
-                valid = refs != ignore_value if ignore_value is not None else np.ones(refs.shape, bool)
-                eqace = eqace_fn(refs, pred, unc, a_p, b_p, valid)
+            eqace = eqace_fn(r, p, u, a_p, b_p, ignore_value) if eqace_fn is not None else None  # device tensors: no second upload
             acc.accumulate_histogram(s, t, n)
             calib_dict[image_id][unc_type] = {"metrics": {"ace": ace, "ece": ece, "eqace": eqace}}
             aces.append(ace); eces.append(ece)
@@ -244,3 +243,70 @@ def calibration_main(exp_dataloader, ignore_value=None, val_exp_dataloader=None)
             val_exp_dataloader = ExperimentDataloader(exp_dataloader.exp_version, "val")
         _cal.platt_scale_params(val_exp_dataloader, ignore_value=ignore_value)
     return calibration_error(exp_dataloader, ignore_value=ignore_value)
+
+
+# ---- threshold discovery on the validation split (find_threshold.py) ------------------------------------------------
+def get_foreground_quantile(exp_dataloader) -> dict:
+    """find_threshold.py:15-30: background share of every member prediction of every image (area counts on the GPU)."""
+    version = exp_dataloader.exp_version
+    all_quantiles = []
+    for image_id in exp_dataloader.image_ids:
+        for pred_seg in exp_dataloader.get_pred_segs(image_id):
+            all_quantiles.append(_qt.calculate_foreground_quantile_image(pred_seg))
+    return {version.pred_model: {version.version_name: {"quantiles": all_quantiles, "exp_path": Path(version.exp_path).as_posix()}}}
+
+
+def save_foreground_quantiles(results_dict, save_path=None) -> None:
+    """find_threshold.py:33-47."""
+    for method, versions in results_dict.items():
+        for _version_name, version_data in versions.items():
+            exp_path = Path(version_data["exp_path"])
+            exp_path.mkdir(parents=True, exist_ok=True)
+            quantiles = version_data["quantiles"]
+            if not quantiles:
+                continue
+            with open(exp_path / "quantile_analysis.json", "w") as f:
+                json.dump({method: float(np.mean(np.array(quantiles)))}, f, indent=2)
+
+
+def threshold_images_paths(exp_dataloader) -> dict:
+    """find_threshold.py:50-66.  The loader rides along under ``"exp_dataloader"`` so that find_threshold can ask it for
+    the maps (``load_unc_file``) instead of medpy."""
+    version = exp_dataloader.exp_version
+    version_dict = {"exp_path": Path(version.exp_path).as_posix(), "unc_paths": {}, "exp_dataloader": exp_dataloader}
+    for unc_type in version.unc_types:
+        unc_path = Path(exp_dataloader.unc_path_dict[unc_type])
+        version_dict["unc_paths"][unc_type] = [(unc_path / f"{image_id}{version.unc_ending}").as_posix()
+                                               for image_id in exp_dataloader.image_ids]
+    return {version.pred_model: {version.version_name: version_dict}}
+
+
+def find_threshold(results_dict, quantile_path=None, save_path=None) -> None:
+    """find_threshold.py:80-112: per uncertainty type the quantile of *all* validation maps together.  The maps are
+    uploaded one by one and folded into one radix selection; the concatenation is never built."""
+    for pred_model, versions in results_dict.items():
+        for version_name, version_data in versions.items():
+            exp_path = Path(version_data["exp_path"])
+            exp_path.mkdir(parents=True, exist_ok=True)
+            quantile_file = exp_path / "quantile_analysis.json"
+            if not quantile_file.is_file():
+                raise FileNotFoundError(f"Quantile file not found for {pred_model} {version_name}: {quantile_file}")
+            loader = version_data.get("exp_dataloader")
+            threshold_entries = {}
+            for unc, paths in version_data["unc_paths"].items():
+                if not paths:
+                    continue
+                maps = []
+                for path in paths:
+                    path = Path(path)
+                    if loader is not None and hasattr(loader, "load_unc_file"):
+                        image = np.asarray(loader.load_unc_file(unc, path.name[: len(path.name) - len(loader.exp_version.unc_ending)]))
+                    else:
+                        from medpy.io import load  # noqa: WPS433 (optional dependency of the reference)
+                        image = load(path)[0]
+                    maps.append(torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).cuda())
+                threshold_entries[f"Mean {unc.split('_')[0]} threshold"] = _qt.calculate_threshold_image(quantile_file, maps, method=pred_model)
+            if not threshold_entries:
+                continue
+            with open(exp_path / "threshold_analysis.json", "w") as f:
+                json.dump({pred_model: threshold_entries}, f, indent=2)

@@ -241,6 +241,24 @@ VU_API int vu_patch_max(const float* maps, int64_t B, int64_t d0, int64_t d1, in
 VU_API int vu_border_count(const uint8_t* labels, int64_t B, int64_t d0, int64_t d1, int64_t d2,
                     int64_t* stats_i64, void* stream);
 
+/* One histogram pass of an exact radix select over float32 values (order statistics for np.quantile:
+ * find_threshold.py:69-77, ace.py:387-388).  key = order-preserving 32-bit image of the float (NaN sorts last).
+ *   level 0: hist[key >> 21]                                   += w      (one slot of 2048 counters)
+ *   level 1: hist[s * 2048 + ((key >> 10) & 0x7ff)]            += w      for keys with  key >> 21 == prefixes[s]
+ *   level 2: hist[s * 2048 + (key & 0x3ff)]                    += w      for keys with  key >> 10 == prefixes[s]
+ * w = 1, or with `weights_gt` (R references over the same n voxels, batch stride unused) the number of references
+ * that are not the ignore value.  hist is uint64, accumulated: several maps can be folded into one selection.
+ * prefixes: DEVICE array of n_prefix <= 64 values (ignored at level 0).                                          */
+VU_API int vu_radix_hist(const float* values, int64_t n, const vu_gt* weights_gt, int32_t level, const uint32_t* prefixes,
+                         int32_t n_prefix, uint64_t* hist, void* stream);
+
+/* The three bincounts of calc_eqace (ace.py:392-396) for one map on 19 caller-given thresholds: sample u of voxel v
+ * (weight = valid references) falls into bin #{k : u' >= edge_u[k]}, u' = u (mode INC / IDENTITY) or -u with
+ * sign-flipped thresholds (mode DEC), NaN u into slot 20.  out_counts (2, 21): samples, correct samples;
+ * out_sums (21): float64 sum of the confidences (ace.py:329 in float32, clipped).  Accumulated.                  */
+VU_API int vu_binned_calib(const float* map, const uint8_t* labels, int64_t V, const vu_gt* gt, const vu_calib* calib,
+                           const uint8_t* label_lut, int64_t* out_counts, double* out_sums, void* stream);
+
 /* Host helper: pull the 19 interior edges of np.linspace(0, 1+1e-8, 21) back
  * through the reference's float32 Platt expression (ace.py:329) by bisection
  * over float32 bit patterns.  Fills calib->edge_u / increasing from a, b.    */

@@ -359,14 +359,129 @@ def task_cases(ref):
     return out
 
 
+def quantile_cases(ref):
+    """eqACE (ace.py:378-406) on the per-(rater, pixel) arrays the body of calibration_error builds, and threshold
+    discovery (find_threshold.py) through its own drivers on an in-memory experiment."""
+    import pathlib
+    import types
+    rng = np.random.default_rng(29)
+    out = {}
+    specs = {
+        "smooth": dict(H=24, W=32, R=4, n_cls=2, ignore=None, a=3.5, b=-1.25, kind="smooth"),
+        "background_zeros": dict(H=32, W=32, R=4, n_cls=2, ignore=None, a=3.5, b=-1.25, kind="zeros"),  # 70 % u == 0: edges collapse
+        "few_levels": dict(H=24, W=24, R=3, n_cls=2, ignore=None, a=5.0, b=-1.0, kind="levels"),     # 7 distinct values
+        "gta_like_ignore": dict(H=24, W=32, R=5, n_cls=19, ignore=255, a=6.0, b=-2.0, kind="smooth"),
+        "negative_a": dict(H=16, W=24, R=2, n_cls=2, ignore=None, a=-2.0, b=0.5, kind="smooth"),
+        "steep": dict(H=16, W=24, R=2, n_cls=2, ignore=None, a=900.0, b=-300.0, kind="smooth"),
+        "tiny": dict(H=1, W=3, R=1, n_cls=2, ignore=None, a=3.5, b=-1.25, kind="smooth"),               # fewer samples than bins
+        "single": dict(H=1, W=1, R=1, n_cls=2, ignore=None, a=3.5, b=-1.25, kind="smooth"),
+    }
+    names = []
+    for name, s in specs.items():
+        H, W, R = s["H"], s["W"], s["R"]
+        pred = rng.integers(0, s["n_cls"], (H, W)).astype(np.uint8)
+        refs = np.stack([np.where(rng.random((H, W)) < 0.8, pred, rng.integers(0, max(s["n_cls"], 2), (H, W)))
+                         for _ in range(R)]).astype(np.uint8)
+        if s["ignore"] is not None:
+            refs[rng.random(refs.shape) < 0.05] = s["ignore"]
+        unc = (rng.random((H, W)) ** 2 * 0.69).astype(np.float32)
+        if s["kind"] == "zeros":
+            unc[rng.random((H, W)) < 0.7] = 0.0
+        elif s["kind"] == "levels":
+            unc = (np.round(unc * 9) / 9).astype(np.float32)
+        with tempfile.TemporaryDirectory() as td:
+            pf = os.path.join(td, "platt_scale_params.json")
+            with open(pf, "w") as f:
+                json.dump({"TU": {"a": s["a"], "b": s["b"]}}, f)
+            pred_rep = np.repeat(pred[np.newaxis, :], R, 0)
+            unc_rep = np.repeat(unc[np.newaxis, :], R, 0)
+            correct = (refs == pred_rep).astype(int)
+            if s["ignore"] is not None:
+                keep = refs != s["ignore"]
+                conf = ref.platt_scale_confid(-unc_rep[keep], platt_scale_file=pf, uncertainty="TU")
+                cv = correct[keep]
+            else:
+                conf = ref.platt_scale_confid(-unc_rep.flatten(), platt_scale_file=pf, uncertainty="TU")
+                cv = correct.flatten()
+        names.append(name)
+        out[f"{name}/refs"] = refs
+        out[f"{name}/pred"] = pred
+        out[f"{name}/unc"] = unc
+        out[f"{name}/a"] = np.float64(s["a"])
+        out[f"{name}/b"] = np.float64(s["b"])
+        out[f"{name}/ignore"] = np.int64(-999 if s["ignore"] is None else s["ignore"])
+        out[f"{name}/conf"] = conf
+        out[f"{name}/correct"] = cv.astype(np.uint8)
+        out[f"{name}/eqace"] = np.float64(ref.calc_eqace(cv, conf))
+    out["eqace_cases"] = np.array(names)
+    out["empty/eqace"] = np.float64(ref.calc_eqace(np.zeros(0, int), np.zeros(0, np.float32)))
+
+    # np.quantile as find_threshold.py:76 calls it: float32 data, Python-float q
+    maps = [(rng.random(shape) ** 3 * 0.69).astype(np.float32) for shape in ((24, 40), (17, 23), (8, 8, 8), (1, 5))]
+    maps[1][rng.random(maps[1].shape) < 0.6] = 0.0
+    qs = np.array([0.0, 1.0, 0.5, 0.25, 0.8, 0.937, 0.999, 1.0 / 3.0, 0.9183673469387755])
+    for k, m in enumerate(maps):
+        out[f"thr/map{k}"] = m
+    out["thr/n_maps"] = np.int64(len(maps))
+    out["thr/qs"] = qs
+    with tempfile.TemporaryDirectory() as td:
+        qf = os.path.join(td, "quantile_analysis.json")
+        res_single, res_all = [], []
+        for q in qs:
+            with open(qf, "w") as f:
+                json.dump({"Softmax": float(q)}, f)
+            res_single.append([ref.calculate_threshold_image(qf, m, "Softmax") for m in maps])
+            res_all.append(ref.calculate_threshold_image(qf, np.concatenate([m.ravel() for m in maps]), "Softmax"))
+    out["thr/per_map"] = np.array(res_single, np.float64)
+    out["thr/all_maps"] = np.array(res_all, np.float64)
+
+    # the drivers: get_foreground_quantile -> save_foreground_quantiles -> threshold_images_paths -> find_threshold
+    H, W, n_img = 24, 40, 5
+    ids = [f"val{i:02d}" for i in range(n_img)]
+    data = {}
+    for i in ids:
+        base = (rng.random((H, W)) < 0.2).astype(np.uint8)
+        base[6:14, 8:24] = 1
+        preds = [np.where(rng.random((H, W)) < 0.93, base, 1 - base).astype(np.uint8) * 255 for _ in range(3)]
+        data[i] = dict(preds=preds, maps={u: (rng.random((H, W)) ** 3 * 0.69).astype(np.float32) for u in ("TU", "AU", "EU")})
+        out[f"drv/{i}/preds"] = np.stack(preds)
+        for u in ("TU", "AU", "EU"):
+            out[f"drv/{i}/{u}"] = data[i]["maps"][u]
+    out["drv/ids"] = np.array(ids)
+    thr = ref.thr_module
+    with tempfile.TemporaryDirectory() as td:
+        root = pathlib.Path(td)
+        ds = root / "val"
+        ds.mkdir()
+        version = types.SimpleNamespace(unc_types=["TU", "AU", "EU"], exp_path=root, pred_model="Softmax", unc_ending=".tif",
+                                        version_name="v0")
+        loader = types.SimpleNamespace(exp_version=version, image_ids=ids, dataset_path=ds,
+                                       unc_path_dict={u: ds / u for u in ("TU", "AU", "EU")},
+                                       get_pred_segs=lambda i: data[i]["preds"])
+
+        def fake_load(path):
+            p = pathlib.Path(path)
+            return data[p.name[: -len(".tif")]]["maps"][p.parent.name], None
+
+        thr.load = fake_load
+        thr.save_foreground_quantiles(thr.get_foreground_quantile(loader))
+        thr.find_threshold(thr.threshold_images_paths(loader))
+        out["drv/quantile_analysis.json"] = np.array(open(root / "quantile_analysis.json").read())
+        out["drv/threshold_analysis.json"] = np.array(open(root / "threshold_analysis.json").read())
+    return out
+
+
 def main():
     assert ref_shim.available(), "needs /root/reference"
     ref = ref_shim.load()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(1)  # thread-count independent reduction rows (see oracle.cascade_sum_f32)
+    only = set(sys.argv[1:])  # e.g. ``python -m oracle.make_golden quantile.npz``: regenerate one file
     for fname, builder in (("uncertainty.npz", uncertainty_cases), ("aggregation.npz", aggregation_cases),
                            ("calibration.npz", calibration_cases), ("ncc_aurc.npz", ncc_aurc_cases),
-                           ("platt_fit.npz", platt_fit_cases), ("tasks.npz", task_cases)):
+                           ("platt_fit.npz", platt_fit_cases), ("tasks.npz", task_cases), ("quantile.npz", quantile_cases)):
+        if only and fname not in only:
+            continue
         data = builder(ref)
         np.savez_compressed(os.path.join(GOLDEN, fname), **data)
         print(fname, len(data), "arrays", os.path.getsize(os.path.join(GOLDEN, fname)), "bytes")

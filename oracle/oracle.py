@@ -360,6 +360,79 @@ def calibration_inputs(refs: np.ndarray, pred: np.ndarray, unc: np.ndarray, a: f
 
 
 # --------------------------------------------------------------------------
+# quantiles: eqACE (evaluation/metrics/ace.py:378-406) and threshold discovery
+# (evaluation/uncertainty_aggregation/find_threshold.py:10-30, 69-112)
+# --------------------------------------------------------------------------
+def quantile_linear(x: np.ndarray, q) -> np.ndarray:
+    """``np.quantile(x, q)`` with the default method "linear" (NumPy is a third-party dependency of the reference; call
+    sites ace.py:388 and find_threshold.py:76), restated from its published algorithm as NumPy 2.3 (installed here, the
+    version the golden vectors were recorded with) runs it: a Python-scalar ``q`` is first cast to the data's float
+    dtype, an array ``q`` keeps its own; virtual index ``h = (n - 1) q`` in that dtype; neighbours ``floor(h)`` and
+    ``floor(h) + 1`` of the sorted data (NaN sorts last and poisons every quantile); weight ``g = h - floor(h)``; the
+    lerp ``a + (b - a) g`` is replaced by ``b - (b - a)(1 - g)`` where ``g >= 0.5``.
+    Version drift: numpy 1.24.3 (the reference's requirements.txt) keeps ``q`` and ``h`` in float64 for float32 data, so
+    its threshold differs from this one by about one float32 rounding."""
+    x = np.sort(np.ravel(np.asarray(x)))
+    scalar = np.ndim(q) == 0
+    if isinstance(q, (int, float)) and x.dtype.kind == "f":
+        qs = np.atleast_1d(np.asarray(q, dtype=x.dtype))
+    else:
+        qs = np.atleast_1d(np.asarray(q))
+    n = x.size
+    h = (n - 1) * qs
+    if n and np.isnan(x[-1]):
+        out = np.full(qs.shape, np.nan, np.result_type(x.dtype, h.dtype))
+        return out[0] if scalar else out
+    lo = np.minimum(np.floor(h).astype(np.intp), n - 1)  # _get_indexes: indexes above bounds take the last element
+    hi = np.minimum(lo + 1, n - 1)
+    g = np.asarray(h - lo, dtype=h.dtype)
+    a, b = x[lo], x[hi]
+    diff = b - a
+    out = np.where(g >= 0.5, b - diff * (1 - g), a + diff * g)
+    return out[0] if scalar else out
+
+
+def calc_eqace(correct, calib_confids, n_bins: int = N_CALIB_BINS) -> float:
+    """ace.py:378-406: adaptive calibration error on the image's own quantile
+    bins.  Confidences are clipped to [0, 1] and ranked in float64; the outer
+    edges are replaced by 0 and 1 + 1e-8 and the edges made non-decreasing."""
+    conf = np.clip(np.ravel(calib_confids), 0.0, 1.0).astype(np.float64)
+    y = np.ravel(correct).astype(np.float64)
+    if conf.size == 0:
+        return float("nan")
+    edges = quantile_linear(conf, np.linspace(0.0, 1.0, n_bins + 1))
+    edges[0] = 0.0
+    edges[-1] = 1.0 + 1e-8
+    edges = np.maximum.accumulate(edges)
+    ids = np.clip(np.digitize(conf, edges) - 1, 0, n_bins - 1)
+    bin_sums = np.bincount(ids, weights=conf, minlength=n_bins)
+    bin_true = np.bincount(ids, weights=y, minlength=n_bins)
+    bin_total = np.bincount(ids, minlength=n_bins)
+    filled = bin_total > 0
+    if not filled.any():
+        return float("nan")
+    gap = np.abs(bin_true[filled] / bin_total[filled] - bin_sums[filled] / bin_total[filled])
+    return float((1.0 / int(filled.sum())) * np.sum(gap))
+
+
+def foreground_quantile(image: np.ndarray) -> float:
+    """find_threshold.py:10-12: share of background pixels of one predicted segmentation."""
+    image = np.asarray(image)
+    return 1 - (np.count_nonzero(image) / image.size)
+
+
+def mean_foreground_quantile(pred_segs: Sequence[np.ndarray]) -> float:
+    """find_threshold.py:15-47: mean over every member prediction of every image."""
+    return float(np.mean(np.array([foreground_quantile(p) for p in pred_segs])))
+
+
+def uncertainty_threshold(unc_maps: Sequence[np.ndarray], method_quantile: float) -> float:
+    """find_threshold.py:69-77, 96-105: ``np.quantile`` of the concatenation of all
+    maps of one uncertainty type at the method's mean foreground quantile."""
+    return float(quantile_linear(np.concatenate([np.ravel(m) for m in unc_maps]), method_quantile))
+
+
+# --------------------------------------------------------------------------
 # Platt-scaling fit on the validation split (evaluation/metrics/ace.py:14-285)
 # --------------------------------------------------------------------------
 N_PLATT_BINS = 256  # ace.py:17

@@ -64,6 +64,7 @@ def load() -> types.SimpleNamespace:
     ace = importlib.import_module("evaluation.metrics.ace")
     ncc = importlib.import_module("evaluation.metrics.ncc")
     aurc = importlib.import_module("evaluation.metrics.aurc")
+    thr = importlib.import_module("evaluation.uncertainty_aggregation.find_threshold")
     return types.SimpleNamespace(
         calculate_uncertainty=tu.calculate_uncertainty,
         calculate_one_minus_msr=tu.calculate_one_minus_msr,
@@ -79,6 +80,9 @@ def load() -> types.SimpleNamespace:
         shp_module=shp,
         ncc_module=ncc,
         aurc_module=aurc,
+        thr_module=thr,
+        calculate_foreground_quantile_image=thr.calculate_foreground_quantile_image,
+        calculate_threshold_image=thr.calculate_threshold_image,
         platt_scale_confid=ace.platt_scale_confid,
         calib_stats=ace.calib_stats,
         calc_ace=ace.calc_ace,

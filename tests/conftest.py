@@ -42,3 +42,8 @@ def golden_ncc_aurc():
 
 def case_names(d):
     return sorted({k.split("/")[0] for k in d})
+
+
+@pytest.fixture(scope="session")
+def golden_quantile():
+    return _load("quantile.npz")

@@ -1,6 +1,8 @@
 """Pin oracle/oracle.py (the CPU restatement) against the golden vectors that
 were recorded from the unmodified reference, and -- when /root/reference is
 mounted -- against the reference functions themselves on fresh inputs."""
+import json
+
 import numpy as np
 import pytest
 import torch
@@ -197,3 +199,45 @@ def test_platt_fit_matches_golden():
             np.testing.assert_allclose(F, g[f"{name}/{unc}_F"], rtol=1e-13)
             a, b = oracle.platt_fit(tot, pos, neg, sums)
             np.testing.assert_allclose([a, b], [g[f"{name}/{unc}_a"], g[f"{name}/{unc}_b"]], rtol=1e-9)
+
+
+def test_quantile_restatement_matches_numpy():
+    """oracle.quantile_linear against np.quantile itself (the third-party routine behind ace.py:388 and
+    find_threshold.py:76), float32 and float64 data, ties, tiny inputs, NaN."""
+    from oracle import oracle
+    rng = np.random.default_rng(5)
+    qs = np.concatenate([np.linspace(0, 1, 21), rng.random(40)])
+    for dtype in (np.float32, np.float64):
+        for n in (1, 2, 3, 20, 21, 1000, 4097):
+            x = (rng.random(n) ** 3).astype(dtype)
+            x[rng.random(n) < 0.3] = 0
+            assert same_bits(oracle.quantile_linear(x, qs), np.quantile(x, qs))
+            assert same_bits(np.asarray(oracle.quantile_linear(x, 0.37)), np.asarray(np.quantile(x, 0.37)))
+    x = np.array([0.5, np.nan, 0.25], np.float32)
+    assert np.isnan(oracle.quantile_linear(x, [0.0, 0.5])).all() and np.isnan(np.quantile(x, [0.0, 0.5])).all()
+
+
+def test_eqace_and_thresholds_match_golden(golden_quantile):
+    from oracle import oracle
+    g = golden_quantile
+    for name in g["eqace_cases"]:
+        got = oracle.calc_eqace(g[f"{name}/correct"], g[f"{name}/conf"])
+        assert got == float(g[f"{name}/eqace"]), name
+        ign = int(g[f"{name}/ignore"])
+        correct, conf = oracle.calibration_inputs(g[f"{name}/refs"], g[f"{name}/pred"], g[f"{name}/unc"], float(g[f"{name}/a"]),
+                                                  float(g[f"{name}/b"]), None if ign == -999 else ign)
+        assert oracle.calc_eqace(correct, conf) == float(g[f"{name}/eqace"]), name
+    assert np.isnan(oracle.calc_eqace(np.zeros(0, int), np.zeros(0, np.float32))) and np.isnan(g["empty/eqace"])
+    maps = [g[f"thr/map{k}"] for k in range(int(g["thr/n_maps"]))]
+    for qi, q in enumerate(g["thr/qs"]):
+        for k, m in enumerate(maps):
+            assert oracle.uncertainty_threshold([m], float(q)) == g["thr/per_map"][qi, k]
+        assert oracle.uncertainty_threshold(maps, float(q)) == g["thr/all_maps"][qi]
+    # the drivers' JSON files (find_threshold.py:15-47, 80-112)
+    ids = list(g["drv/ids"])
+    want_q = json.loads(str(g["drv/quantile_analysis.json"]))["Softmax"]
+    got_q = oracle.mean_foreground_quantile([p for i in ids for p in g[f"drv/{i}/preds"]])
+    assert got_q == want_q
+    want_t = json.loads(str(g["drv/threshold_analysis.json"]))["Softmax"]
+    for u in ("TU", "AU", "EU"):
+        assert oracle.uncertainty_threshold([g[f"drv/{i}/{u}"] for i in ids], got_q) == want_t[f"Mean {u} threshold"]
