@@ -34,6 +34,13 @@ def main():
             _lib.check(lib.vu_patch_max(maps[0].data_ptr(), B, dims[0], dims[1], dims[2], box[0], box[1], box[2], 0,
                                         out_max.data_ptr(), out_first.data_ptr(), st), "patch")
 
+        ws_bytes = int(lib.vu_patch_workspace_bytes(B, dims[0], dims[1], dims[2], box[0], box[1], box[2]))
+        ws = torch.empty(max(ws_bytes // 8, 1), dtype=torch.int64, device="cuda")
+
+        def patch_ws():
+            _lib.check(lib.vu_patch_max_ws(maps[0].data_ptr(), B, dims[0], dims[1], dims[2], box[0], box[1], box[2], 0,
+                                           out_max.data_ptr(), out_first.data_ptr(), ws.data_ptr(), ws_bytes, st), "patch_ws")
+
         def border():
             _lib.check(lib.vu_border_count(labels.data_ptr(), B, dims[0], dims[1], dims[2], si.data_ptr(), st), "border")
 
@@ -54,7 +61,8 @@ def main():
         def mapstats():
             _lib.check(lib.vu_map_stats(C.byref(a), st), "map_stats")
 
-        for label, fn, nbytes in (("K2 patch_max (one map, 10^d box)", patch, 4 * V * B), ("K2 border", border, V * B),
+        for label, fn, nbytes in (("K2 patch_max (one map, 10^d box)", patch, 4 * V * B),
+                                  ("K2 patch_max_ws (with workspace)", patch_ws, 4 * V * B), ("K2 border", border, V * B),
                                   (f"K3 map_stats flags={a.stat_flags:#x}", mapstats, (13 + R) * V * B)):
             ms = time_call(fn, iters=10)
             print(f"{name:16s} B={B:4d} {label:36s} {ms:8.3f} ms  {nbytes / ms / 1e6:8.1f} GB/s  {V * B / ms / 1e6:8.1f} Gvox/s", flush=True)

@@ -72,6 +72,9 @@ EXPORTS = {
     "vu_struct_size": (C.c_int, [C.c_int]),
     "vu_fused_pass": (C.c_int, [C.POINTER(FusedArgs), C.c_void_p]),
     "vu_map_stats": (C.c_int, [C.POINTER(MapStatsArgs), C.c_void_p]),
+    "vu_patch_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
+    "vu_patch_max_ws": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "vu_patch_max": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vu_border_count": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),

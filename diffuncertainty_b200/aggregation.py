@@ -137,12 +137,15 @@ def patch_level_batched(maps: torch.Tensor, box: Sequence[int], mean: bool = Fal
     B, d0, d1, d2 = maps.shape
     out_max = torch.empty(B, dtype=torch.float64, device=maps.device)
     out_first = torch.empty(B, dtype=torch.int64, device=maps.device)
+    k = [int(box[0]), int(box[1]), int(box[2])]
     with torch.cuda.device(maps.device):
         for s in range(0, B, 65535):
             e = min(B, s + 65535)
-            _lib.check(lib.vu_patch_max(maps[s:e].data_ptr(), e - s, d0, d1, d2, int(box[0]), int(box[1]), int(box[2]),
-                                        1 if mean else 0, out_max[s:e].data_ptr(), out_first[s:e].data_ptr(),
-                                        _lib.current_stream_ptr()), "vu_patch_max")
+            ws_bytes = int(lib.vu_patch_workspace_bytes(e - s, d0, d1, d2, *k))  # per-CTA maxima: lets the index pass skip
+            ws = torch.empty(max(ws_bytes // 8, 1), dtype=torch.int64, device=maps.device)
+            _lib.check(lib.vu_patch_max_ws(maps[s:e].data_ptr(), e - s, d0, d1, d2, *k, 1 if mean else 0,
+                                           out_max[s:e].data_ptr(), out_first[s:e].data_ptr(),
+                                           ws.data_ptr() if ws_bytes else None, ws_bytes, _lib.current_stream_ptr()), "vu_patch_max_ws")
     return {"max_score": out_max.cpu().numpy(), "first_index": out_first.cpu().numpy()}
 
 

@@ -198,14 +198,27 @@ int vu_map_stats(const vu_map_stats_args* a, void* stream) {
     return launch_map_stats(a, st, (cudaStream_t)stream);
 }
 
-int vu_patch_max(const float* maps, int64_t B, int64_t d0, int64_t d1, int64_t d2, int32_t k0, int32_t k1, int32_t k2,
-                 int32_t mean, double* out_max, int64_t* out_first, void* stream) {
+int64_t vu_patch_workspace_bytes(int64_t B, int64_t d0, int64_t d1, int64_t d2, int32_t k0, int32_t k1, int32_t k2) {
+    if (B < 1 || d0 < 1 || d1 < 1 || d2 < 1 || k0 < 1 || k1 < 1 || k2 < 1 || k0 > d0 || k1 > d1 || k2 > d2) return 0;
+    return B * patch_ctas_per_image(d0, d1, d2, k0, k1, k2) * (int64_t)sizeof(unsigned long long);
+}
+
+int vu_patch_max_ws(const float* maps, int64_t B, int64_t d0, int64_t d1, int64_t d2, int32_t k0, int32_t k1, int32_t k2,
+                    int32_t mean, double* out_max, int64_t* out_first, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!maps || !out_max || !out_first) return set_error(VU_ERR_BAD_ARG, "NULL pointer");
     if (B < 0 || d0 < 1 || d1 < 1 || d2 < 1 || k0 < 1 || k1 < 1 || k2 < 1) return set_error(VU_ERR_BAD_ARG, "bad size");
     if (k0 > d0 || k1 > d1 || k2 > d2) return set_error(VU_ERR_BAD_ARG, "patch larger than the map (\"valid\" output is empty)");
     if (B == 0) return VU_OK;
+    if (workspace && workspace_bytes < vu_patch_workspace_bytes(B, d0, d1, d2, k0, k1, k2))
+        return set_error(VU_ERR_BAD_ARG, "workspace smaller than vu_patch_workspace_bytes");
+    if (workspace && (reinterpret_cast<uintptr_t>(workspace) & 7)) return set_error(VU_ERR_BAD_ARG, "workspace must be 8-byte aligned");
     return launch_patch_max(maps, B, d0, d1, d2, k0, k1, k2, mean, out_max, reinterpret_cast<long long*>(out_first),
-                            (cudaStream_t)stream);
+                            reinterpret_cast<unsigned long long*>(workspace), (cudaStream_t)stream);
+}
+
+int vu_patch_max(const float* maps, int64_t B, int64_t d0, int64_t d1, int64_t d2, int32_t k0, int32_t k1, int32_t k2,
+                 int32_t mean, double* out_max, int64_t* out_first, void* stream) {
+    return vu_patch_max_ws(maps, B, d0, d1, d2, k0, k1, k2, mean, out_max, out_first, nullptr, 0, stream);
 }
 
 int vu_border_count(const uint8_t* labels, int64_t B, int64_t d0, int64_t d1, int64_t d2, int64_t* stats_i64, void* stream) {

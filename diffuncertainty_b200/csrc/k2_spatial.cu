@@ -25,6 +25,7 @@ __global__ void patch_finish(unsigned long long* max_enc, long long B, double sc
     if (i < B) reinterpret_cast<double*>(max_enc)[i] = o2d(max_enc[i]) * scale;
 }
 
+// Fallback for boxes too large for patch_box3 (below).
 // "valid" box sum of a (d0, d1, d2) map with a (k0, k1, k2) box, exact in
 // float64.  A CTA owns a T1 x T2 window of output (y, x) positions and marches
 // along z: per input slice it forms the x-sums, then the y-sums, and keeps the
@@ -117,18 +118,220 @@ __global__ void __launch_bounds__(kT1* kT2) patch_box(const float* __restrict__ 
     }
 }
 
+
+// ---- general 3-D / 2-D kernel: sliding sums along all three axes --------------------------------------------------
+// A CTA owns a 32 x 32 window of output (y, x) positions and marches along z.
+//   step 1  every thread keeps float64 running sums over the last k0 slices for the input columns it owns (add the
+//           slice that enters the window, subtract the one that leaves; both were requested one iteration earlier, so
+//           their latency hides behind steps 2 and 3) and drops them into shared memory;
+//   step 2  x direction: a thread forms kP3Seg consecutive k2-wide sums of one row (first one directly, then slide);
+//   step 3  y direction: the same down a column, then max (MODE 0) or first-isclose index (MODE 1).
+// 2 barriers per slice.  Inputs are float32 and the accumulators float64, so the add / subtract steps are exact unless
+// a window spans more than ~2^29 in magnitude; otherwise the error per step is 2^-53 of the running value (score
+// tolerance: 1e-5).
+// tile_max (optional workspace, kP3ZChunks + 1 words per CTA): MODE 0 stores the CTA's own maximum and the maxima of
+// the chunks of kP3ZSlices output slices; MODE 1 returns at once when the CTA's maximum is not within the isclose
+// tolerance of the image's (normally all but one CTA per image), otherwise starts at the first chunk that holds a
+// candidate and stops after the first slice with a hit (later slices only have larger row-major indices).
+// KT: box edge as a compile-time constant for cubic / square boxes (0: read k0, k1, k2 at run time).
+constexpr int kP3T = 32, kP3Threads = 256, kP3Seg = 4;
+constexpr int kP3MaxCols = 16;   // input columns per thread: (32 + k - 1)^2 <= 16 * 256  <=>  k <= 33
+constexpr int kP3ZSlices = 8;    // output slices per chunk of the workspace
+__host__ __device__ inline int p3_zchunks(long long o0) { return (int)((o0 + kP3ZSlices - 1) / kP3ZSlices); }
+
+template <int MODE, int KT>
+__global__ void __launch_bounds__(kP3Threads, 2) patch_box3(const float* __restrict__ maps, long long d0, long long d1, long long d2,
+                                                           int rk0, int rk1, int rk2, unsigned long long* max_enc, long long* first,
+                                                           double scale, int tiles_x, unsigned long long* tile_max) {
+    extern __shared__ double smem_d[];
+    const int k0 = (KT > 0 && rk0 != 1) ? KT : rk0, k1 = KT > 0 ? KT : rk1, k2 = KT > 0 ? KT : rk2;  // KT with rk0 == 1: a 2-D box
+    constexpr int COLS = KT > 0 ? ((kP3T + KT - 1) * (kP3T + KT - 1) + kP3Threads - 1) / kP3Threads : kP3MaxCols;
+    const long long b = blockIdx.y;
+    const long long o0 = d0 - k0 + 1, o1 = d1 - k1 + 1, o2 = d2 - k2 + 1;
+    const int nchunk = p3_zchunks(o0);
+    unsigned long long* my_max = tile_max ? tile_max + (b * gridDim.x + blockIdx.x) * (nchunk + 1) : nullptr;
+    double peak = 0.0, tol = 0.0;
+    long long z_begin = 0;  // first input slice this CTA reads
+    if (MODE == 1) {
+        peak = o2d(max_enc[b]);
+        tol = 1e-8 / scale + 1e-5 * fabs(peak);  // np.isclose(v*scale, peak*scale): atol 1e-8, rtol 1e-5
+        if (my_max) {
+            const unsigned long long e = my_max[0];
+            if (e == 0ull || !(fabs(o2d(e) - peak) <= tol)) return;  // no candidate in this window (CTA-uniform)
+            int ch = 0;
+            while (ch < nchunk - 1 && !(my_max[1 + ch] != 0ull && fabs(o2d(my_max[1 + ch]) - peak) <= tol)) ++ch;
+            z_begin = (long long)ch * kP3ZSlices;  // output slice ch * 8 needs input slices from the same index on
+        }
+    }
+    const int in_h = kP3T + k1 - 1, in_w = kP3T + k2 - 1;
+    double* zs = smem_d;                        // [in_h][in_w]  z-window sums of the current slice
+    double* xs = zs + (size_t)in_h * in_w;      // [in_h][kP3T]  their x-sums
+    const int ty0 = (blockIdx.x / tiles_x) * kP3T, tx0 = (blockIdx.x % tiles_x) * kP3T;
+    const int tid = threadIdx.x;
+    const long long plane = d1 * d2;
+    const float* img = maps + b * d0 * plane;
+    const int n_in = in_h * in_w;
+
+    double run[COLS];
+    int off[COLS];            // input column tid + i * threads of the window: offset inside a slice (0 when outside the map)
+    float nv[COLS], ov[COLS];  // requested one iteration ahead: the column's element of the slice entering / leaving the window
+    unsigned inside = 0;      // bit i: column i lies inside the map
+#pragma unroll
+    for (int i = 0; i < COLS; ++i) {
+        const int c = tid + i * kP3Threads;
+        run[i] = 0.0;
+        off[i] = 0;
+        ov[i] = 0.f;
+        if (c < n_in) {
+            const int yy = c / in_w, xx = c % in_w;
+            const long long gy = ty0 + yy, gx = tx0 + xx;
+            if (gy < d1 && gx < d2) { off[i] = (int)(gy * d2 + gx); inside |= 1u << i; }
+        }
+        const float v = __ldg(img + z_begin * plane + off[i]);
+        nv[i] = ((inside >> i) & 1) ? v : 0.f;
+    }
+    double best = 0.0, chunk_best = 0.0;
+    bool have = false, chunk_have = false;
+    long long best_idx = 0x7fffffffffffffffLL;
+    constexpr int kSegs = kP3T / kP3Seg;
+    const int x3 = tid % kP3T, y3 = (tid / kP3T) * kP3Seg;  // step-3 item: column x3, outputs y3 .. y3+3 (32 x 8 items)
+    const long long ox3 = tx0 + x3;
+    __shared__ unsigned long long wmax[kP3Threads / 32];
+    __shared__ int s_hit;
+    if (MODE == 1 && tid == 0) s_hit = 0;
+
+    for (long long z = z_begin; z < d0; ++z) {
+#pragma unroll
+        for (int i = 0; i < COLS; ++i) {
+            const int c = tid + i * kP3Threads;
+            run[i] += (double)nv[i];
+            run[i] -= (double)ov[i];
+            if (KT > 0 ? (i < COLS - 1 || c < n_in) : (c < n_in)) zs[c] = run[i];
+        }
+        if (z + 1 < d0) {
+            const float* nxt = img + (z + 1) * plane;
+            const bool leaving = z + 1 - z_begin >= k0;
+            const float* old = leaving ? nxt - (long long)k0 * plane : nxt;
+#pragma unroll
+            for (int i = 0; i < COLS; ++i) {
+                const float a = __ldg(nxt + off[i]), o = __ldg(old + off[i]);
+                const bool in = (inside >> i) & 1;
+                nv[i] = in ? a : 0.f;
+                ov[i] = (in && leaving) ? o : 0.f;
+            }
+        }
+        if (z - z_begin < k0 - 1) continue;  // uniform: the window is not full yet (zs is rewritten next slice by the same threads)
+        __syncthreads();
+        for (int it = tid; it < in_h * kSegs; it += kP3Threads) {
+            const int r = it / kSegs, x0 = (it % kSegs) * kP3Seg;
+            const double* row = zs + r * in_w + x0;
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < (KT > 0 ? KT : 1); ++j) s += row[j];
+            if (KT == 0)
+                for (int j = 1; j < k2; ++j) s += row[j];
+            double* o = xs + r * kP3T + x0;
+            o[0] = s;
+#pragma unroll
+            for (int j = 1; j < kP3Seg; ++j) {
+                s += row[j + k2 - 1];
+                s -= row[j - 1];
+                o[j] = s;
+            }
+        }
+        __syncthreads();
+        const long long oz = z - (k0 - 1);
+        {
+            const double* col = xs + y3 * kP3T + x3;
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < (KT > 0 ? KT : 1); ++j) s += col[j * kP3T];
+            if (KT == 0)
+                for (int j = 1; j < k1; ++j) s += col[j * kP3T];
+#pragma unroll
+            for (int j = 0; j < kP3Seg; ++j) {
+                if (j > 0) {
+                    s += col[(j + k1 - 1) * kP3T];
+                    s -= col[(j - 1) * kP3T];
+                }
+                const long long oy = ty0 + y3 + j;
+                if (oy < o1 && ox3 < o2) {
+                    if (MODE == 0) {
+                        if (!chunk_have || s > chunk_best) { chunk_best = s; chunk_have = true; }
+                    } else if (fabs(s - peak) <= tol) {
+                        const long long idx = (oz * o1 + oy) * o2 + ox3;
+                        if (idx < best_idx) { best_idx = idx; s_hit = 1; }
+                    }
+                }
+            }
+        }
+        if (MODE == 0) {
+            // end of a chunk of output slices: fold the chunk's maximum into the CTA's and (with a workspace) store it
+            if ((oz + 1) % kP3ZSlices == 0 || oz + 1 == o0) {
+                if (chunk_have && (!have || chunk_best > best)) { best = chunk_best; have = true; }
+                if (my_max) {
+                    unsigned long long e = chunk_have ? d2o(chunk_best) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        unsigned long long other = __shfl_xor_sync(kFull, e, o);
+                        e = other > e ? other : e;
+                    }
+                    if ((tid & 31) == 0) wmax[tid >> 5] = e;
+                    __syncthreads();
+                    if (tid == 0) {
+                        for (int w = 1; w < kP3Threads / 32; ++w) e = wmax[w] > e ? wmax[w] : e;
+                        my_max[1 + oz / kP3ZSlices] = e;
+                    }
+                    // wmax is rewritten at the earliest after two more barriers (the next slice's steps 2 and 3)
+                }
+                chunk_have = false;
+            }
+        } else {
+            // a hit in this slice: every later slice only has larger indices (the barrier also orders s_hit)
+            __syncthreads();
+            if (s_hit) break;
+        }
+        // otherwise no barrier here: the next slice's step 1 only writes zs (last read before the second barrier above),
+        // and xs is rewritten only after the next slice's first barrier
+    }
+    if (MODE == 0) {
+        unsigned long long e = have ? d2o(best) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(kFull, e, o);
+            e = other > e ? other : e;
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) wmax[tid >> 5] = e;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kP3Threads / 32; ++w) e = wmax[w] > e ? wmax[w] : e;
+            if (my_max) my_max[0] = e;
+            if (e) atomicMax(max_enc + b, e);
+        }
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            long long other = __shfl_xor_sync(kFull, best_idx, o);
+            best_idx = other < best_idx ? other : best_idx;
+        }
+        if ((tid & 31) == 0 && best_idx != 0x7fffffffffffffffLL) atomicMin(first + b, best_idx);
+    }
+}
+
 // ---- 2-D maps (d0 == 1): one thread per output column, marching down the rows ---------------------------------
 // A CTA owns kTX output columns and a chunk of output rows.  Per input row: the row segment goes to shared memory
 // (double-buffered, one barrier per row), each thread forms its K-tap x-sum in float64 and keeps the last K of
 // them in registers (the row loop is unrolled by K, so the ring is indexed statically); the box sum of an output
 // row is re-formed from the ring every time, so no add/subtract drift can build up.  MODE as in patch_box.
-constexpr int kTX = 256, kRowsPerCta = 128;
+constexpr int kTX = 256, kRowsPerCta = 32;  // 32 output rows per CTA: enough CTAs to hide the row loads of one another
 
 template <int K, int MODE>
 __global__ void __launch_bounds__(kTX) patch_box2d(const float* __restrict__ maps, long long H, long long W, unsigned long long* max_enc,
-                                                  long long* first, double scale) {
+                                                  long long* first, double scale, unsigned long long* tile_max) {
     __shared__ float row[2][kTX + K - 1];
     const long long b = blockIdx.z;
+    const long long cta = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     const long long o1 = H - K + 1, o2 = W - K + 1;
     const long long x0 = (long long)blockIdx.x * kTX, oy0 = (long long)blockIdx.y * kRowsPerCta;
     const long long oy1 = oy0 + kRowsPerCta < o1 ? oy0 + kRowsPerCta : o1;  // output rows [oy0, oy1)
@@ -146,27 +349,42 @@ __global__ void __launch_bounds__(kTX) patch_box2d(const float* __restrict__ map
     if (MODE == 1) {
         peak = o2d(max_enc[b]);
         tol = 1e-8 / scale + 1e-5 * fabs(peak);
+        if (tile_max) {  // see patch_box3
+            const unsigned long long e = tile_max[cta];
+            if (e == 0ull || !(fabs(o2d(e) - peak) <= tol)) return;
+        }
     }
-    auto load_row = [&](long long r, int buf) {
+    // rows travel global -> registers (requested two rows ahead) -> shared (one row ahead) -> the K-tap x-sum
+    float pa = 0.f, pb = 0.f;
+    auto fetch_row = [&](long long r) {
         const float* src = img + r * W + x0;
-        row[buf][tx] = (x0 + tx < W) ? __ldg(src + tx) : 0.f;
-        if (tx < K - 1) row[buf][kTX + tx] = (x0 + kTX + tx < W) ? __ldg(src + kTX + tx) : 0.f;
+        pa = (x0 + tx < W) ? __ldg(src + tx) : 0.f;
+        if (tx < K - 1) pb = (x0 + kTX + tx < W) ? __ldg(src + kTX + tx) : 0.f;
+    };
+    auto stage_row = [&](int buf) {
+        row[buf][tx] = pa;
+        if (tx < K - 1) row[buf][kTX + tx] = pb;
     };
     const long long r_end = oy1 + K - 1;  // input rows [oy0, r_end)
-    load_row(oy0, 0);
+    fetch_row(oy0);
+    stage_row(0);
+    if (oy0 + 1 < r_end) fetch_row(oy0 + 1);
     __syncthreads();
-    for (long long base = oy0; base < r_end; base += K) {
+    bool done = false;
+    for (long long base = oy0; base < r_end && !done; base += K) {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const long long r = base + j;
-            if (r < r_end) {  // uniform
+            if (r < r_end && !done) {  // uniform
                 const int buf = (int)((r - oy0) & 1);
-                if (r + 1 < r_end) load_row(r + 1, buf ^ 1);
+                if (r + 1 < r_end) stage_row(buf ^ 1);
+                if (r + 2 < r_end) fetch_row(r + 2);
                 double s = 0.0;
 #pragma unroll
                 for (int dx = 0; dx < K; ++dx) s += (double)row[buf][tx + dx];
                 ring[j] = s;
                 const long long oy = r - (K - 1);
+                bool hit = false;
                 if (oy >= oy0 && col_ok) {
                     double v = 0.0;
 #pragma unroll
@@ -176,9 +394,12 @@ __global__ void __launch_bounds__(kTX) patch_box2d(const float* __restrict__ map
                     } else if (fabs(v - peak) <= tol) {
                         const long long idx = oy * o2 + ox;
                         if (idx < best_idx) best_idx = idx;
+                        hit = true;
                     }
                 }
-                __syncthreads();
+                // MODE 1: a hit in this row ends the search, every later row only has larger row-major indices
+                if (MODE == 1) done = __syncthreads_or(hit) != 0;
+                else __syncthreads();
             }
         }
     }
@@ -189,7 +410,14 @@ __global__ void __launch_bounds__(kTX) patch_box2d(const float* __restrict__ map
             unsigned long long other = __shfl_xor_sync(kFull, e, o);
             e = other > e ? other : e;
         }
-        if ((tx & 31) == 0 && e) atomicMax(max_enc + b, e);
+        __shared__ unsigned long long wmax[kTX / 32];
+        if ((tx & 31) == 0) wmax[tx >> 5] = e;
+        __syncthreads();
+        if (tx == 0) {
+            for (int w = 1; w < kTX / 32; ++w) e = wmax[w] > e ? wmax[w] : e;
+            if (tile_max) tile_max[cta] = e;
+            if (e) atomicMax(max_enc + b, e);
+        }
     } else {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -202,47 +430,79 @@ __global__ void __launch_bounds__(kTX) patch_box2d(const float* __restrict__ map
 
 template <int K>
 static void launch_patch2d(const float* maps, long long B, long long H, long long W, unsigned long long* enc, long long* first,
-                           double scale, cudaStream_t stream) {
+                           double scale, unsigned long long* tile_max, cudaStream_t stream) {
     const long long o1 = H - K + 1, o2 = W - K + 1;
     dim3 grid((unsigned)((o2 + kTX - 1) / kTX), (unsigned)((o1 + kRowsPerCta - 1) / kRowsPerCta), (unsigned)B);
-    patch_box2d<K, 0><<<grid, kTX, 0, stream>>>(maps, H, W, enc, first, scale);
-    patch_box2d<K, 1><<<grid, kTX, 0, stream>>>(maps, H, W, enc, first, scale);
+    patch_box2d<K, 0><<<grid, kTX, 0, stream>>>(maps, H, W, enc, first, scale, tile_max);
+    patch_box2d<K, 1><<<grid, kTX, 0, stream>>>(maps, H, W, enc, first, scale, tile_max);
+}
+
+static bool patch_uses_2d(long long d0, long long d1, int k0, int k1, int k2) {
+    return d0 == 1 && k0 == 1 && k1 == k2 && (k1 == 10 || k1 == 4 || k1 == 16) && (d1 - k1 + 1 + kRowsPerCta - 1) / kRowsPerCta <= 65535;
+}
+static bool patch_uses_box3(int k1, int k2) { return (kP3T + k1 - 1) * (kP3T + k2 - 1) <= kP3MaxCols * kP3Threads; }
+
+// CTAs per image of the kernel launch_patch_max picks (one workspace word each)
+long long patch_ctas_per_image(long long d0, long long d1, long long d2, int k0, int k1, int k2) {
+    const long long o1 = d1 - k1 + 1, o2 = d2 - k2 + 1;
+    if (patch_uses_2d(d0, d1, k0, k1, k2)) return ((o2 + kTX - 1) / kTX) * ((o1 + kRowsPerCta - 1) / kRowsPerCta);
+    if (patch_uses_box3(k1, k2)) return ((o1 + kP3T - 1) / kP3T) * ((o2 + kP3T - 1) / kP3T) * (p3_zchunks(d0 - k0 + 1) + 1);
+    return 0;  // the fallback kernel does not use the workspace
 }
 
 int launch_patch_max(const float* maps, long long B, long long d0, long long d1, long long d2, int k0, int k1, int k2,
-                     int mean, double* out_max, long long* out_first, cudaStream_t stream) {
+                     int mean, double* out_max, long long* out_first, unsigned long long* tile_max, cudaStream_t stream) {
     const double scale = mean ? 1.0 / ((double)k0 * k1 * k2) : 1.0;
     const long long o1 = d1 - k1 + 1, o2 = d2 - k2 + 1;
-    const int tiles_y = (int)((o1 + kT1 - 1) / kT1), tiles_x = (int)((o2 + kT2 - 1) / kT2);
-    const size_t smem = ((size_t)(kT1 + k1 - 1) * kT2 + (size_t)k0 * kT1 * kT2) * sizeof(double) +
-                        (size_t)(kT1 + k1 - 1) * (kT2 + k2 - 1) * sizeof(float);
-    if (smem > 200 * 1024) return set_error(VU_ERR_UNSUPPORTED, "patch too large for shared memory");
     if (B > 65535) return set_error(VU_ERR_UNSUPPORTED, "B > 65535 per vu_patch_max call");
-    static size_t attr = 0;
-    if (smem > attr) {
-        if (cudaFuncSetAttribute(patch_box<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-            cudaFuncSetAttribute(patch_box<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return set_cuda_error("cudaFuncSetAttribute(patch_box)");
-        attr = smem;
-    }
     unsigned long long* enc = reinterpret_cast<unsigned long long*>(out_max);
     const unsigned ib = (unsigned)((B + 255) / 256);
     patch_init<<<ib, 256, 0, stream>>>(enc, out_first, B);
-    // 2-D maps with a square box of a specialised size: the column-marching kernel (4x faster than the tiled one)
-    if (d0 == 1 && k0 == 1 && k1 == k2 && (k1 == 10 || k1 == 4 || k1 == 16) && (d1 - k1 + 1 + kRowsPerCta - 1) / kRowsPerCta <= 65535) {
-        if (k1 == 10) launch_patch2d<10>(maps, B, d1, d2, enc, out_first, scale, stream);
-        else if (k1 == 4) launch_patch2d<4>(maps, B, d1, d2, enc, out_first, scale, stream);
-        else launch_patch2d<16>(maps, B, d1, d2, enc, out_first, scale, stream);
-        patch_finish<<<ib, 256, 0, stream>>>(enc, B, scale);
-        count_launch("patch_init"); count_launch("patch_box2d"); count_launch("patch_box2d"); count_launch("patch_finish");
-        return check_launch("patch_box2d");
+    count_launch("patch_init");
+    // 2-D maps with a square box of a specialised size: the column-marching kernel
+    if (patch_uses_2d(d0, d1, k0, k1, k2)) {
+        if (k1 == 10) launch_patch2d<10>(maps, B, d1, d2, enc, out_first, scale, tile_max, stream);
+        else if (k1 == 4) launch_patch2d<4>(maps, B, d1, d2, enc, out_first, scale, tile_max, stream);
+        else launch_patch2d<16>(maps, B, d1, d2, enc, out_first, scale, tile_max, stream);
+        count_launch("patch_box2d"); count_launch("patch_box2d");
+    } else if (patch_uses_box3(k1, k2)) {
+        const int tiles_y = (int)((o1 + kP3T - 1) / kP3T), tiles_x = (int)((o2 + kP3T - 1) / kP3T);
+        const int in_h = kP3T + k1 - 1, in_w = kP3T + k2 - 1;
+        const size_t smem = ((size_t)in_h * in_w + (size_t)in_h * kP3T) * sizeof(double);
+        if (smem + 2048 > 200 * 1024) return set_error(VU_ERR_UNSUPPORTED, "patch too large for shared memory");
+        if (d1 * d2 > 0x7fffffffLL) return set_error(VU_ERR_UNSUPPORTED, "a slice of the map has more than 2^31 voxels");
+        dim3 grid((unsigned)(tiles_y * tiles_x), (unsigned)B);
+        const bool k10 = k1 == 10 && k2 == 10 && (k0 == 10 || k0 == 1);  // patch_size: 10 (aggregation_all.yaml:9), 3-D or 2-D
+        auto k_max = k10 ? patch_box3<0, 10> : patch_box3<0, 0>;
+        auto k_idx = k10 ? patch_box3<1, 10> : patch_box3<1, 0>;
+        if (smem + 2048 > 48 * 1024) {  // static shared memory comes on top
+            if (cudaFuncSetAttribute(k_max, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaFuncSetAttribute(k_idx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return set_cuda_error("cudaFuncSetAttribute(patch_box3)");
+        }
+        k_max<<<grid, kP3Threads, smem, stream>>>(maps, d0, d1, d2, k0, k1, k2, enc, out_first, scale, tiles_x, tile_max);
+        k_idx<<<grid, kP3Threads, smem, stream>>>(maps, d0, d1, d2, k0, k1, k2, enc, out_first, scale, tiles_x, tile_max);
+        count_launch("patch_box3"); count_launch("patch_box3");
+    } else {
+        const int tiles_y = (int)((o1 + kT1 - 1) / kT1), tiles_x = (int)((o2 + kT2 - 1) / kT2);
+        const size_t smem = ((size_t)(kT1 + k1 - 1) * kT2 + (size_t)k0 * kT1 * kT2) * sizeof(double) +
+                            (size_t)(kT1 + k1 - 1) * (kT2 + k2 - 1) * sizeof(float);
+        if (smem > 200 * 1024) return set_error(VU_ERR_UNSUPPORTED, "patch too large for shared memory");
+        static size_t attr = 0;
+        if (smem > attr) {
+            if (cudaFuncSetAttribute(patch_box<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaFuncSetAttribute(patch_box<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return set_cuda_error("cudaFuncSetAttribute(patch_box)");
+            attr = smem;
+        }
+        dim3 grid((unsigned)(tiles_y * tiles_x), (unsigned)B);
+        patch_box<0><<<grid, kT1 * kT2, smem, stream>>>(maps, d0, d1, d2, k0, k1, k2, enc, out_first, scale, tiles_y, tiles_x);
+        patch_box<1><<<grid, kT1 * kT2, smem, stream>>>(maps, d0, d1, d2, k0, k1, k2, enc, out_first, scale, tiles_y, tiles_x);
+        count_launch("patch_box"); count_launch("patch_box");
     }
-    dim3 grid((unsigned)(tiles_y * tiles_x), (unsigned)B);
-    patch_box<0><<<grid, kT1 * kT2, smem, stream>>>(maps, d0, d1, d2, k0, k1, k2, enc, out_first, scale, tiles_y, tiles_x);
-    patch_box<1><<<grid, kT1 * kT2, smem, stream>>>(maps, d0, d1, d2, k0, k1, k2, enc, out_first, scale, tiles_y, tiles_x);
     patch_finish<<<ib, 256, 0, stream>>>(enc, B, scale);
-    count_launch("patch_init"); count_launch("patch_box"); count_launch("patch_box"); count_launch("patch_finish");
-    return check_launch("patch_box");
+    count_launch("patch_finish");
+    return check_launch("patch_max");
 }
 
 // ---- border -----------------------------------------------------------------

@@ -27,7 +27,8 @@ int num_fast_variants();
 int describe_fast_variant(int i, int* out7);
 int launch_map_stats(const vu_map_stats_args* a, const StatParams& st, cudaStream_t stream);
 int launch_patch_max(const float* maps, long long B, long long d0, long long d1, long long d2, int k0, int k1, int k2,
-                     int mean, double* out_max, long long* out_first, cudaStream_t stream);
+                     int mean, double* out_max, long long* out_first, unsigned long long* tile_max, cudaStream_t stream);
+long long patch_ctas_per_image(long long d0, long long d1, long long d2, int k0, int k1, int k2);
 int launch_border(const uint8_t* labels, long long B, long long d0, long long d1, long long d2, long long* stats_i64,
                   cudaStream_t stream);
 int launch_radix_hist(const float* values, long long n, const GtView& gt, int level, const unsigned* prefixes, int n_prefix,

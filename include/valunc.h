@@ -235,6 +235,17 @@ VU_API int vu_map_stats(const vu_map_stats_args* args, void* stream);
 VU_API int vu_patch_max(const float* maps, int64_t B, int64_t d0, int64_t d1, int64_t d2,
                  int32_t k0, int32_t k1, int32_t k2, int32_t mean,
                  double* out_max, int64_t* out_first, void* stream);
+/* Same with an optional device workspace of vu_patch_workspace_bytes(...) bytes
+ * (8-byte aligned, contents irrelevant): the first pass leaves every CTA's own
+ * maximum there and the index pass skips the CTAs that cannot hold a box
+ * np.isclose to the image's maximum -- about half the time of vu_patch_max.
+ * workspace == NULL behaves like vu_patch_max.                                */
+VU_API int64_t vu_patch_workspace_bytes(int64_t B, int64_t d0, int64_t d1, int64_t d2,
+                 int32_t k0, int32_t k1, int32_t k2);
+VU_API int vu_patch_max_ws(const float* maps, int64_t B, int64_t d0, int64_t d1, int64_t d2,
+                 int32_t k0, int32_t k1, int32_t k2, int32_t mean,
+                 double* out_max, int64_t* out_first,
+                 void* workspace, int64_t workspace_bytes, void* stream);
 
 /* _compute_border (prediction_shape_stats.py:15-30) on (B, d0, d1, d2) uint8
  * label maps; adds into stats_i64[b][VU_I64_BORDER] (row stride VU_I64_COLS) */

@@ -272,6 +272,53 @@ def test_golden_aggregations(vu, golden_agg):
         agg.threshold_aggregation(golden_agg["img2d/image"])
 
 
+@pytest.mark.parametrize("shape,box", [
+    ((40, 70, 75), 10),           # 3-D, several 32 x 32 windows per image, ragged edges
+    ((64, 64, 64), 10),           # BASELINE configs[1]
+    ((12, 33, 97), (3, 5, 7)),    # anisotropic box
+    ((100, 130), 7),              # 2-D box without a specialised kernel
+    ((300, 520), 10),             # 2-D specialised kernel, several CTAs per image
+    ((9, 40, 40), (9, 33, 33)),   # the largest box of the sliding kernel, one output slice
+    ((6, 50, 50), (2, 34, 34)),   # larger still: the tiled fallback kernel
+])
+def test_patch_level_multi_window(vu, shape, box):
+    """patch_level_aggregation (aggregate_uncertainties.py:16-34) on maps that span several CTAs, with and without the
+    per-CTA-maximum workspace, against the oracle (scipy's convolve, as the reference calls it)."""
+    from diffuncertainty_b200 import _lib, aggregation as agg
+    from oracle import oracle
+    rng = np.random.default_rng(17)
+    ks = [box] * len(shape) if isinstance(box, int) else list(box)
+    imgs = []
+    a = (rng.random(shape) ** 4 * 0.69).astype(np.float32)                   # one dominant blob somewhere
+    imgs.append(a)
+    b = np.zeros(shape, np.float32)                                          # plateau: many boxes tie with the maximum,
+    b[tuple(slice(s // 3, s) for s in shape)] = 0.5                          # the first one in row-major order wins
+    imgs.append(b)
+    c = (rng.random(shape) * 1e-6).astype(np.float32)                        # two equal far-apart peaks in different windows
+    lo = tuple(slice(0, k) for k in ks)
+    hi = tuple(slice(s - k, s) for s, k in zip(shape, ks))
+    c[lo] += 1.0
+    c[hi] += 1.0
+    imgs.append(c)
+    for mean in (False, True):
+        for img in imgs:
+            want = oracle.patch_level_aggregation(img, ks, mean=mean)
+            got = agg.patch_level_aggregation(img, ks, mean=mean)
+            np.testing.assert_allclose(got["max_score"], want["max_score"], rtol=1e-7)  # scipy goes through an FFT
+            assert got["bounding_box"] == want["bounding_box"], (shape, box, mean)
+    # the plain entry point (no workspace) gives the same answer as the wrapper's vu_patch_max_ws
+    lib = _lib.load()
+    dims = [1] * (3 - len(shape)) + list(shape)
+    k3 = [1] * (3 - len(shape)) + ks
+    t = torch.from_numpy(np.stack(imgs)).cuda()
+    batched = agg.patch_level_batched(t.reshape(len(imgs), *dims), k3)
+    out_max = torch.empty(len(imgs), dtype=torch.float64, device="cuda")
+    out_first = torch.empty(len(imgs), dtype=torch.int64, device="cuda")
+    _lib.check(lib.vu_patch_max(t.data_ptr(), len(imgs), *dims, *k3, 0, out_max.data_ptr(), out_first.data_ptr(),
+                                _lib.current_stream_ptr()), "vu_patch_max")
+    assert np.array_equal(out_max.cpu().numpy(), batched["max_score"]) and np.array_equal(out_first.cpu().numpy(), batched["first_index"])
+
+
 def test_golden_calibration(vu, golden_calib):
     from diffuncertainty_b200 import _lib, calibration
     from diffuncertainty_b200.uncertainty import GroundTruth
