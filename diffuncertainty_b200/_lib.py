@@ -64,6 +64,14 @@ class MapStatsArgs(C.Structure):
                 ("platt_fit", C.POINTER(PlattFit)), ("platt_i64", C.c_void_p), ("platt_f64", C.c_void_p)]
 
 
+class MemberScoresArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("flags", C.c_uint32), ("slab", Slab), ("gt", Gt), ("labels", C.c_void_p),
+                ("eps", C.c_float), ("nll_sum", C.c_void_p), ("nll_count", C.c_void_p), ("nll_bad", C.c_void_p),
+                ("ged_counts", C.c_void_p)]
+
+
+MS_NLL, MS_GED = 1, 2
+
 EXPORTS = {
     "vu_abi_version": (C.c_int, []),
     "vu_build_info": (C.c_char_p, []),
@@ -80,6 +88,8 @@ EXPORTS = {
     "vu_border_count": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "vu_platt_invert_edges_host": (C.c_int, [C.c_double, C.c_double, C.POINTER(Calib)]),
     "vu_platt_fit_edges_host": (C.c_int, [C.POINTER(PlattFit)]),
+    "vu_ged_cols": (C.c_int64, [C.c_int32, C.c_int32]),
+    "vu_member_scores": (C.c_int, [C.POINTER(MemberScoresArgs), C.c_void_p]),
     "vu_radix_hist": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Gt), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "vu_binned_calib": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Gt), C.POINTER(Calib), C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),

@@ -155,6 +155,7 @@ int vu_struct_size(int which) {
         case 1: return (int)sizeof(vu_map_stats_args);
         case 2: return (int)sizeof(vu_calib);
         case 3: return (int)sizeof(vu_platt_fit);
+        case 4: return (int)sizeof(vu_member_scores_args);
         default: return -1;
     }
 }
@@ -308,6 +309,36 @@ int vu_binned_calib(const float* map, const uint8_t* labels, int64_t V, const vu
     for (int e = 0; e < VU_N_EDGES; ++e) cd.edge[e] = cd.increasing ? calib->edge_u[e] : -calib->edge_u[e];
     return launch_binned_calib(map, labels, V, gv, cd, label_lut, reinterpret_cast<unsigned long long*>(out_counts), out_sums,
                                (cudaStream_t)stream);
+}
+
+int64_t vu_ged_cols(int32_t P, int32_t R) {
+    if (P < 1 || R < 1) return 0;
+    return 2LL * P * R + R + (int64_t)P * P + P + 2LL * R * R + 3;
+}
+
+int vu_member_scores(const vu_member_scores_args* a, void* stream) {
+    if (!a) return set_error(VU_ERR_BAD_ARG, "args is NULL");
+    if (a->struct_size != sizeof(vu_member_scores_args)) return set_error(VU_ERR_BAD_ARG, "vu_member_scores_args.struct_size mismatch");
+    const vu_slab& s = a->slab;
+    if (s.P < 1 || s.B < 0 || s.C < 1 || s.V < 0) return set_error(VU_ERR_BAD_ARG, "slab sizes must be positive");
+    if (s.C > VU_MAX_CLASSES) return set_error(VU_ERR_UNSUPPORTED, "C > 255");
+    if (!(a->flags & (VU_MS_NLL | VU_MS_GED)) || (a->flags & ~(VU_MS_NLL | VU_MS_GED))) return set_error(VU_ERR_BAD_ARG, "flags");
+    if ((a->flags & VU_MS_GED) && s.C != 2) return set_error(VU_ERR_BAD_ARG, "GED counts need C == 2 (ged_fast.py:33)");
+    if ((a->flags & VU_MS_GED) && s.P > 32) return set_error(VU_ERR_UNSUPPORTED, "GED counts need P <= 32");
+    if (s.B == 0 || s.V == 0) return VU_OK;
+    if (s.member_ptrs || s.member_ptrs_host) {
+        if (!s.member_ptrs || !s.member_ptrs_host)
+            return set_error(VU_ERR_BAD_ARG, "slab.member_ptrs needs both the device array and its host copy");
+    } else if (!s.data) {
+        return set_error(VU_ERR_BAD_ARG, "slab.data is NULL");
+    }
+    if (!a->gt.data) return set_error(VU_ERR_BAD_ARG, "member scores need ground truth");
+    if ((a->flags & VU_MS_NLL) && (!a->nll_sum || !a->nll_count || !a->nll_bad)) return set_error(VU_ERR_BAD_ARG, "NLL outputs are NULL");
+    if ((a->flags & VU_MS_GED) && !a->ged_counts) return set_error(VU_ERR_BAD_ARG, "ged_counts is NULL");
+    GtView gv;
+    int rc = make_gt_view(gv, &a->gt, s.V);
+    if (rc != VU_OK) return rc;
+    return launch_member_scores(a, gv, (cudaStream_t)stream);
 }
 
 int vu_platt_fit_edges_host(vu_platt_fit* out) {

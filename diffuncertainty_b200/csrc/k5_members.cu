@@ -1,0 +1,316 @@
+// K5: member-level scores on the slab K1 reads:
+//   likelihood statistics   uncertainty_modeling/test_2D.py:1043-1120  (_compute_likelihood_stats, _compute_expected_nll)
+//   GED counts              evaluation/metrics/ged_fast.py:44-131      (ged_binary_fast)
+//
+// One pass over the (P, B, C, V) slab and the (B, R, V) references.  A warp owns "passes" of kGroups x 32 voxels of one
+// image (lane = voxel inside a group) and walks the members in order, kGroups x C loads in flight per lane:
+//   NLL   per member the lane picks log(max(p[gt_r], eps)) for each rater (C == 2: both logs, selected by the reference's
+//         bit; C > 2: a gather load per rater), sums its kGroups voxels in float32 and the warp folds the R sums of the
+//         member into the image's (R, P) float64 matrix with one atomic each;
+//   GED   (C == 2, P <= 32) the member's label bits of a group are one ballot word; lane p keeps member p's words.  After
+//         the last member every pair count is popc(word & word): lane p accumulates row p of the P x P intersection
+//         matrix (a shuffle per partner), of the P x R prediction / reference counts, lane i < R row i of the R x R
+//         reference matrix -- no cross-lane reduction until the CTA is done with the image.
+// All counts are integers (bit-exact); the float32 Dice / GED arithmetic of ged_fast.py:60-140 runs on the host on
+// P*R + P*P + R*R numbers.  Bound: HBM (the slab is read once more: 4 P C + R g bytes per voxel).
+#include "vu_common.cuh"
+#include "vu_host.h"
+
+namespace vu {
+
+struct MemberParams {
+    const float* data;
+    const float* const* member_ptrs;
+    long long P, B, C, V;
+    long long sp, sb, sc, sv;
+    GtView gt;
+    const uint8_t* labels;  // (B, V) label of the member mean, or NULL
+    unsigned flags;
+    float eps;
+    double* nll_sum;              // (B, R, P)
+    unsigned long long* nll_cnt;  // (B, R)
+    unsigned long long* nll_bad;  // (B)
+    unsigned long long* ged;      // (B, cols)
+    int ged_cols;
+    long long chunk;              // voxels per CTA (multiple of 32 * kGroups)
+};
+
+constexpr int kMsThreads = 256, kMsWarps = kMsThreads / 32, kGroups = 8;
+constexpr unsigned kInvalid = 0xffu;  // class byte of an ignored reference
+
+// ln(max(p, eps)) with torch.clamp's NaN rule (NaN stays NaN).  lg2.approx has an absolute error of ~2^-23.5 on
+// [0.5, 2], too much next to p = 1 where the term itself vanishes; there the K1 polynomial takes over (vu_common.cuh).
+__device__ __forceinline__ float log_clamped(float p, float eps) {
+    const float x = fmaxf(p, eps);
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(x));
+    const float f = __fadd_rn(x, -1.0f);
+    float t = __fmaf_rn(f, kQ3, kQ2);
+    t = __fmaf_rn(t, f, kQ1);
+    t = __fmaf_rn(t, f, kQ0);
+    const float l2 = (fabsf(f) < kNearOne) ? __fmul_rn(t, f) : lg;
+    return (p != p) ? p : l2 * kLn2;
+}
+
+__device__ __forceinline__ long long load_ref(const GtView& gt, long long off) {
+    return gt.dtype == VU_GT_U8 ? (long long)__ldg(reinterpret_cast<const uint8_t*>(gt.data) + off)
+                                : __ldg(reinterpret_cast<const long long*>(gt.data) + off);
+}
+
+template <bool C2>
+__global__ void __launch_bounds__(kMsThreads) member_scores_kernel(const __grid_constant__ MemberParams prm) {
+    extern __shared__ unsigned s_ged[];  // [ged_cols] CTA-wide GED counters (C2 && GED only)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long b = blockIdx.y;
+    const long long c0 = (long long)blockIdx.x * prm.chunk;
+    const long long c1 = c0 + prm.chunk < prm.V ? c0 + prm.chunk : prm.V;
+    const int P = (int)prm.P, R = prm.gt.R;
+    const bool want_nll = prm.flags & VU_MS_NLL, want_ged = C2 && (prm.flags & VU_MS_GED);
+    if (want_ged) {
+        for (int t = tid; t < prm.ged_cols; t += kMsThreads) s_ged[t] = 0u;
+        __syncthreads();
+    }
+    // per-lane GED accumulators: lane p holds row p of the P x P and P x R matrices, lane i < R row i of the R x R ones
+    unsigned pp[32], pg_tp[VU_MAX_RATERS], pg_pred[VU_MAX_RATERS], gg_tp[VU_MAX_RATERS], gg_sum[VU_MAX_RATERS], g_sum[VU_MAX_RATERS];
+    unsigned pos = 0, maj_tp = 0, maj_pred = 0, maj_gt = 0;
+    if (want_ged) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) pp[q] = 0u;
+#pragma unroll
+        for (int r = 0; r < VU_MAX_RATERS; ++r) { pg_tp[r] = 0u; pg_pred[r] = 0u; gg_tp[r] = 0u; gg_sum[r] = 0u; g_sum[r] = 0u; }
+    }
+    unsigned long long valid_cnt[VU_MAX_RATERS], bad_cnt = 0;
+#pragma unroll
+    for (int r = 0; r < VU_MAX_RATERS; ++r) valid_cnt[r] = 0ull;
+
+    const long long pass_vox = 32LL * kGroups;
+    for (long long v0 = c0 + (long long)warp * pass_vox; v0 < c1; v0 += (long long)kMsWarps * pass_vox) {
+        // ---- references of the pass: one class byte per (rater, group); kInvalid = ignored or out of range ----------
+        unsigned cls[VU_MAX_RATERS][kGroups / 4];  // 4 group bytes per word
+        unsigned long long is1 = 0, val = 0;       // bit (r * kGroups + j): reference == 1 (and valid) / valid
+        unsigned lab1 = 0;                         // bit j: label of the member mean == 1
+#pragma unroll
+        for (int r = 0; r < VU_MAX_RATERS; ++r) {
+#pragma unroll
+            for (int w = 0; w < kGroups / 4; ++w) cls[r][w] = 0u;
+            if (r < R) {
+#pragma unroll
+                for (int j = 0; j < kGroups; ++j) {
+                    const long long v = v0 + 32 * j + lane;
+                    unsigned c = kInvalid;
+                    if (v < c1) {
+                        const long long g = load_ref(prm.gt, b * prm.gt.sb + (long long)r * prm.gt.sr + v * prm.gt.sv);
+                        const bool valid = !(prm.gt.has_ignore && g == prm.gt.ignore);
+                        if (valid) {
+                            val |= 1ull << (r * kGroups + j);
+                            if (g == 1) is1 |= 1ull << (r * kGroups + j);
+                            valid_cnt[r] += 1;
+                            if (g >= 0 && g < prm.C) c = (unsigned)g;
+                            else if (want_nll) bad_cnt += 1;  // torch.gather would raise (test_2D.py:1067)
+                        }
+                    }
+                    cls[r][j >> 2] |= c << (8 * (j & 3));
+                }
+            }
+        }
+        if (want_ged && prm.labels) {
+#pragma unroll
+            for (int j = 0; j < kGroups; ++j) {
+                const long long v = v0 + 32 * j + lane;
+                if (v < c1 && __ldg(prm.labels + b * prm.V + v) == 1) lab1 |= 1u << j;
+            }
+        }
+        // ---- members ---------------------------------------------------------------------------------------------
+        unsigned myW[kGroups];  // lane p: label bits of member p, one word per group
+#pragma unroll
+        for (int j = 0; j < kGroups; ++j) myW[j] = 0u;
+        for (int p = 0; p < P; ++p) {
+            const float* base = (prm.member_ptrs ? ld_member_ptr(prm.member_ptrs, p) : prm.data + (long long)p * prm.sp) + b * prm.sb;
+            float acc[VU_MAX_RATERS];
+#pragma unroll
+            for (int r = 0; r < VU_MAX_RATERS; ++r) acc[r] = 0.f;
+            if (C2) {
+                float p0[kGroups], p1[kGroups];
+#pragma unroll
+                for (int j = 0; j < kGroups; ++j) {
+                    const long long v = v0 + 32 * j + lane;
+                    const bool in = v < c1;
+                    p0[j] = in ? ldg_stream(base + v * prm.sv) : 1.f;
+                    p1[j] = in ? ldg_stream(base + prm.sc + v * prm.sv) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < kGroups; ++j) {
+                    if (want_ged) {
+                        // torch.argmax over two classes: 1 iff p1 > p0, or p1 is NaN and p0 is not (ged_fast.py:44)
+                        const bool one = (p1[j] > p0[j]) || ((p1[j] != p1[j]) && (p0[j] == p0[j]));
+                        const unsigned w = __ballot_sync(kFull, one && (v0 + 32 * j + lane < c1));
+                        if (lane == p) myW[j] = w;
+                    }
+                    if (want_nll) {
+                        const float l0 = log_clamped(p0[j], prm.eps), l1 = log_clamped(p1[j], prm.eps);
+#pragma unroll
+                        for (int r = 0; r < VU_MAX_RATERS; ++r) {
+                            if (r >= R) break;
+                            const unsigned c = (cls[r][j >> 2] >> (8 * (j & 3))) & 0xffu;
+                            acc[r] += (c == 0u) ? l0 : ((c == 1u) ? l1 : 0.f);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < VU_MAX_RATERS; ++r) {
+                    if (r >= R) break;
+                    float x[kGroups];
+#pragma unroll
+                    for (int j = 0; j < kGroups; ++j) {
+                        const unsigned c = (cls[r][j >> 2] >> (8 * (j & 3))) & 0xffu;
+                        const long long v = v0 + 32 * j + lane;
+                        x[j] = (c != kInvalid) ? __ldg(base + (long long)c * prm.sc + v * prm.sv) : 1.f;  // ln 1 = 0
+                    }
+#pragma unroll
+                    for (int j = 0; j < kGroups; ++j) acc[r] += log_clamped(x[j], prm.eps);
+                }
+            }
+            if (want_nll) {
+#pragma unroll
+                for (int r = 0; r < VU_MAX_RATERS; ++r) {
+                    if (r >= R) break;
+                    const double s = warp_sum((double)acc[r]);
+                    if (lane == 0 && s != 0.0) atomicAdd(prm.nll_sum + (b * R + r) * P + p, s);
+                }
+            }
+        }
+        // ---- pair counts of the pass -------------------------------------------------------------------------------
+        if (want_ged) {
+#pragma unroll
+            for (int j = 0; j < kGroups; ++j) {
+                const unsigned w = myW[j];
+                pos += __popc(w);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    if (q >= P) break;
+                    pp[q] += __popc(w & __shfl_sync(kFull, w, q));
+                }
+                unsigned Gb[VU_MAX_RATERS], Gw[VU_MAX_RATERS], Vw[VU_MAX_RATERS];
+                unsigned myGb = 0u, n1 = 0u, all_valid = 1u;
+#pragma unroll
+                for (int r = 0; r < VU_MAX_RATERS; ++r) {
+                    if (r >= R) break;
+                    const unsigned one = (unsigned)(is1 >> (r * kGroups + j)) & 1u, ok = (unsigned)(val >> (r * kGroups + j)) & 1u;
+                    // is1 is only set on valid voxels; ged_fast.py:93 takes (gt == 1) before masking, which differs only
+                    // when the ignore value itself is 1
+                    const unsigned raw1 = (prm.gt.has_ignore && prm.gt.ignore == 1) ? (ok ^ 1u) & (unsigned)(v0 + 32 * j + lane < c1) : one;
+                    Gb[r] = __ballot_sync(kFull, raw1);
+                    Gw[r] = __ballot_sync(kFull, one);
+                    Vw[r] = __ballot_sync(kFull, ok);
+                    myGb = (lane == r) ? Gb[r] : myGb;
+                    n1 += raw1;
+                    all_valid &= ok;
+                }
+#pragma unroll
+                for (int r = 0; r < VU_MAX_RATERS; ++r) {
+                    if (r >= R) break;
+                    pg_tp[r] += __popc(w & Gw[r]);
+                    pg_pred[r] += __popc(w & Vw[r]);
+                    gg_tp[r] += __popc(myGb & Gw[r]);
+                    gg_sum[r] += __popc(myGb & Vw[r]);
+                    g_sum[r] += __popc(Gw[r]);
+                }
+                if (prm.labels) {
+                    // ged_fast.py:121-131: majority reference (share of raters with label 1 >= 0.5) on voxels no rater ignores
+                    const bool in = v0 + 32 * j + lane < c1;
+                    const unsigned Mg = __ballot_sync(kFull, in && 2u * n1 >= (unsigned)R);
+                    const unsigned Va = __ballot_sync(kFull, in && (prm.gt.has_ignore ? all_valid : 1u));
+                    const unsigned Lw = __ballot_sync(kFull, (lab1 >> j) & 1u);
+                    maj_tp += __popc(Lw & Mg & Va);
+                    maj_pred += __popc(Lw & Va);
+                    maj_gt += __popc(Mg & Va);
+                }
+            }
+        }
+    }
+    // ---- fold the CTA's partials into the image's rows ---------------------------------------------------------------
+    if (want_nll) {
+#pragma unroll
+        for (int r = 0; r < VU_MAX_RATERS; ++r) {
+            if (r >= R) break;
+            const unsigned long long n = (unsigned long long)warp_sum((double)valid_cnt[r]);  // exact: far below 2^53
+            if (lane == 0 && n) atomicAdd(prm.nll_cnt + b * R + r, n);
+        }
+        const unsigned long long nb = (unsigned long long)warp_sum((double)bad_cnt);
+        if (lane == 0 && nb) atomicAdd(prm.nll_bad + b, nb);
+    }
+    if (want_ged) {
+        const int G = R;
+        const int o_pg_tp = 0, o_pg_pred = P * G, o_gs = 2 * P * G, o_pp = o_gs + G, o_pos = o_pp + P * P, o_gg_tp = o_pos + P,
+                  o_gg_sum = o_gg_tp + G * G, o_maj = o_gg_sum + G * G;
+        if (lane < P) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+                if (q < P && pp[q]) atomicAdd(&s_ged[o_pp + lane * P + q], pp[q]);
+            if (pos) atomicAdd(&s_ged[o_pos + lane], pos);
+#pragma unroll
+            for (int r = 0; r < VU_MAX_RATERS; ++r)
+                if (r < G) {
+                    if (pg_tp[r]) atomicAdd(&s_ged[o_pg_tp + lane * G + r], pg_tp[r]);
+                    if (pg_pred[r]) atomicAdd(&s_ged[o_pg_pred + lane * G + r], pg_pred[r]);
+                }
+        }
+        if (lane < G) {
+#pragma unroll
+            for (int r = 0; r < VU_MAX_RATERS; ++r)
+                if (r < G) {
+                    if (gg_tp[r]) atomicAdd(&s_ged[o_gg_tp + lane * G + r], gg_tp[r]);
+                    if (gg_sum[r]) atomicAdd(&s_ged[o_gg_sum + lane * G + r], gg_sum[r]);
+                }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < VU_MAX_RATERS; ++r)
+                if (r < G && g_sum[r]) atomicAdd(&s_ged[o_gs + r], g_sum[r]);
+            if (maj_tp) atomicAdd(&s_ged[o_maj], maj_tp);
+            if (maj_pred) atomicAdd(&s_ged[o_maj + 1], maj_pred);
+            if (maj_gt) atomicAdd(&s_ged[o_maj + 2], maj_gt);
+        }
+        __syncthreads();
+        for (int t = tid; t < prm.ged_cols; t += kMsThreads)
+            if (s_ged[t]) atomicAdd(prm.ged + b * prm.ged_cols + t, (unsigned long long)s_ged[t]);
+    }
+}
+
+int launch_member_scores(const vu_member_scores_args* a, const GtView& gv, cudaStream_t stream) {
+    const vu_slab& s = a->slab;
+    MemberParams prm;
+    prm.data = s.data; prm.member_ptrs = s.member_ptrs;
+    prm.P = s.P; prm.B = s.B; prm.C = s.C; prm.V = s.V;
+    prm.sp = s.stride_p; prm.sb = s.stride_b; prm.sc = s.stride_c; prm.sv = s.stride_v;
+    prm.gt = gv;
+    prm.labels = a->labels;
+    prm.flags = a->flags;
+    prm.eps = a->eps;
+    prm.nll_sum = a->nll_sum;
+    prm.nll_cnt = reinterpret_cast<unsigned long long*>(a->nll_count);
+    prm.nll_bad = reinterpret_cast<unsigned long long*>(a->nll_bad);
+    prm.ged = reinterpret_cast<unsigned long long*>(a->ged_counts);
+    prm.ged_cols = (a->flags & VU_MS_GED) ? (int)vu_ged_cols((int)s.P, gv.R) : 0;
+    // CTAs per image: enough CTAs to fill the GPU, each with at least one pass per warp, counters below 2^32
+    const long long pass = 32LL * kGroups, cta_min = pass * kMsWarps;
+    long long per_image = (2LL * device_sm_count() * 4 + s.B - 1) / s.B;
+    const long long max_per_image = (s.V + cta_min - 1) / cta_min;
+    if (per_image > max_per_image) per_image = max_per_image;
+    if (per_image < 1) per_image = 1;
+    long long chunk = (s.V + per_image - 1) / per_image;
+    chunk = (chunk + pass - 1) / pass * pass;
+    if (chunk > (1LL << 30)) chunk = 1LL << 30;
+    per_image = (s.V + chunk - 1) / chunk;
+    prm.chunk = chunk;
+    if (s.B > 65535) return set_error(VU_ERR_UNSUPPORTED, "B > 65535 per vu_member_scores call");
+    dim3 grid((unsigned)per_image, (unsigned)s.B);
+    const size_t smem = (size_t)prm.ged_cols * sizeof(unsigned);
+    if (s.C == 2) member_scores_kernel<true><<<grid, kMsThreads, smem, stream>>>(prm);
+    else member_scores_kernel<false><<<grid, kMsThreads, 0, stream>>>(prm);
+    count_launch("member_scores");
+    return check_launch("member_scores");
+}
+
+}  // namespace vu

@@ -35,6 +35,7 @@ int launch_radix_hist(const float* values, long long n, const GtView& gt, int le
                       unsigned long long* hist, cudaStream_t stream);
 int launch_binned_calib(const float* map, const uint8_t* labels, long long V, const GtView& gt, const CalibDev& cal, const uint8_t* lut,
                         unsigned long long* counts, double* sums, cudaStream_t stream);
+int launch_member_scores(const vu_member_scores_args* a, const GtView& gt, cudaStream_t stream);
 int launch_synth_slab(float* out, long long P, long long B, long long C, long long V, uint64_t seed,
                       long long first_image, float scale, cudaStream_t stream);
 int launch_synth_gt(uint8_t* out, const float* slab, long long P, long long B, long long C, long long V, int R,

@@ -151,23 +151,10 @@ def _members_view(members):
     return first
 
 
-def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0,
-               thresholds: Optional[Sequence[float]] = None, calib=None, label_lut: Optional[torch.Tensor] = None,
-               want_maps: bool = True, want_labels: bool = True,
-               stats_out: Optional[tuple] = None, maps_out: Optional[Dict[str, torch.Tensor]] = None,
-               labels_out: Optional[torch.Tensor] = None, platt_fit=None, want_member_labels: bool = False) -> FusedResult:
-    """One launch over ``softmax_pred`` of shape (P, B, C, *S) (test_2D.py:1277) -- or over a list of P member tensors
-    (B, C, *S), which are then read where they are (no torch.stack).
-
-    stats      : OR of _lib.STAT_* flags
-    thresholds : three floats (TU, AU, EU) for STAT_THRESHOLD
-    calib      : three ``calibration.PlattEdges`` for STAT_CALIB
-    stats_out  : optional (stats_f64, stats_i64) device tensors to accumulate
-                 into (rows = images of this batch)
-    platt_fit  : a ``calibration.PlattFitAccumulator`` for STAT_PLATT_FIT (dataset-level buffers)
-    maps_out   : optional preallocated contiguous fp32 (B, *S) tensors keyed "TU","AU","EU"
-                 (or "pred_entropy" when P == 1); labels_out: preallocated uint8 (B, *S)
-    """
+def fill_slab(slab: _lib.Slab, softmax_pred):
+    """Describe ``softmax_pred`` -- a (P, B, C, *S) tensor with any strides, or a list of P member tensors (B, C, *S)
+    that are then read where they are (no torch.stack, test_2D.py:1277) -- in a vu_slab.  Returns
+    (P, B, C, spatial, device, keep-alive objects)."""
     members = None
     if isinstance(softmax_pred, (list, tuple)):
         # P separate member tensors (B, C, *S): read where they are, no torch.stack
@@ -199,24 +186,46 @@ def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0
             sv = 1
         dev = softmax_pred.device
         strides = (softmax_pred.stride(0), softmax_pred.stride(1), softmax_pred.stride(2))
-    _lib.require_device()
-    lib = _lib.load()
     V = int(np.prod(spatial)) if spatial else 1
-    a = _lib.FusedArgs()
-    a.struct_size = C.sizeof(_lib.FusedArgs)
-    a.stat_flags = int(stats)
-    a.slab.P, a.slab.B, a.slab.C, a.slab.V = P, B, Cn, V
-    a.slab.stride_p, a.slab.stride_b, a.slab.stride_c = strides
-    a.slab.stride_v = sv
-    ptr_keep = None
+    slab.P, slab.B, slab.C, slab.V = P, B, Cn, V
+    slab.stride_p, slab.stride_b, slab.stride_c = strides
+    slab.stride_v = sv
     if members is not None:
         host_ptrs = (C.c_void_p * P)(*[m.data_ptr() for m in members])
         dev_ptrs = torch.tensor([m.data_ptr() for m in members], dtype=torch.int64).to(dev, non_blocking=False)
-        a.slab.member_ptrs = dev_ptrs.data_ptr()
-        a.slab.member_ptrs_host = C.cast(host_ptrs, C.c_void_p)
-        ptr_keep = (host_ptrs, dev_ptrs, members)
+        slab.member_ptrs = dev_ptrs.data_ptr()
+        slab.member_ptrs_host = C.cast(host_ptrs, C.c_void_p)
+        keep = (host_ptrs, dev_ptrs, members)
     else:
-        a.slab.data = softmax_pred.data_ptr()
+        slab.data = softmax_pred.data_ptr()
+        keep = (softmax_pred,)
+    return P, B, Cn, spatial, dev, keep
+
+
+def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0,
+               thresholds: Optional[Sequence[float]] = None, calib=None, label_lut: Optional[torch.Tensor] = None,
+               want_maps: bool = True, want_labels: bool = True,
+               stats_out: Optional[tuple] = None, maps_out: Optional[Dict[str, torch.Tensor]] = None,
+               labels_out: Optional[torch.Tensor] = None, platt_fit=None, want_member_labels: bool = False) -> FusedResult:
+    """One launch over ``softmax_pred`` of shape (P, B, C, *S) (test_2D.py:1277) -- or over a list of P member tensors
+    (B, C, *S), which are then read where they are (no torch.stack).
+
+    stats      : OR of _lib.STAT_* flags
+    thresholds : three floats (TU, AU, EU) for STAT_THRESHOLD
+    calib      : three ``calibration.PlattEdges`` for STAT_CALIB
+    stats_out  : optional (stats_f64, stats_i64) device tensors to accumulate
+                 into (rows = images of this batch)
+    platt_fit  : a ``calibration.PlattFitAccumulator`` for STAT_PLATT_FIT (dataset-level buffers)
+    maps_out   : optional preallocated contiguous fp32 (B, *S) tensors keyed "TU","AU","EU"
+                 (or "pred_entropy" when P == 1); labels_out: preallocated uint8 (B, *S)
+    """
+    _lib.require_device()
+    lib = _lib.load()
+    a = _lib.FusedArgs()
+    a.struct_size = C.sizeof(_lib.FusedArgs)
+    a.stat_flags = int(stats)
+    P, B, Cn, spatial, dev, ptr_keep = fill_slab(a.slab, softmax_pred)
+    V = int(a.slab.V)
 
     maps: Dict[str, torch.Tensor] = {}
     with torch.cuda.device(dev):

@@ -252,6 +252,41 @@ VU_API int vu_patch_max_ws(const float* maps, int64_t B, int64_t d0, int64_t d1,
 VU_API int vu_border_count(const uint8_t* labels, int64_t B, int64_t d0, int64_t d1, int64_t d2,
                     int64_t* stats_i64, void* stream);
 
+/* Member-level scores on the slab vu_fused_pass reads (one more pass over it):
+ *   VU_MS_NLL  _compute_likelihood_stats / _compute_expected_nll (test_2D.py:1043-1120):
+ *              nll_sum[b][r][p] += sum over the valid voxels of reference r of ln(max(slab[p, b, gt, v], eps))
+ *              (float64), nll_count[b][r] += valid voxels (every voxel without gt.has_ignore, test_2D.py:1055-1060),
+ *              nll_bad[b] += valid voxels whose reference is not a class index (torch.gather raises there, :1067).
+ *   VU_MS_GED  every integer ged_binary_fast (ged_fast.py:44-131) is made of; needs C == 2 and P <= 32.
+ *              ged_counts[b][...], vu_ged_cols(P, R) int64 per image, G = R:
+ *                [0, PG)            pg_tp[p][g]    member p == 1 & reference g == 1 & g valid      (ged_fast.py:56-60)
+ *                [PG, 2PG)          pg_pred[p][g]  member p == 1 & g valid                         (:56,61)
+ *                + G                g_sum[g]       reference g == 1 & g valid                      (:57,62)
+ *                + P*P              pp_tp[p][q]    member p == 1 & member q == 1                   (:84-86)
+ *                + P                pos[p]         member p == 1                                   (:87)
+ *                + G*G              gg_tp[i][j]    reference i == 1 & reference j == 1 & j valid   (:98-101)
+ *                + G*G              gg_sum[i][j]   reference i == 1 & j valid                      (:100,102)
+ *                + 3                majority tp / pred / gt counts (:121-131); needs `labels`, the (B, V) label of the
+ *                                   member mean that vu_fused_pass wrote, else they stay untouched
+ *              member labels follow torch.argmax (first maximum, NaN is maximal).
+ * All outputs accumulate.  The float32 Dice / GED arithmetic on these P*G + P*P + G*G numbers is the caller's.       */
+#define VU_MS_NLL 0x1u
+#define VU_MS_GED 0x2u
+typedef struct vu_member_scores_args {
+    uint32_t struct_size;  /* sizeof(vu_member_scores_args) */
+    uint32_t flags;
+    vu_slab slab;
+    vu_gt gt;              /* required */
+    const uint8_t* labels; /* (B, V) or NULL */
+    float eps;             /* test_2D.py:1043: 1e-12 */
+    double* nll_sum;       /* (B, R, P) */
+    int64_t* nll_count;    /* (B, R) */
+    int64_t* nll_bad;      /* (B) */
+    int64_t* ged_counts;   /* (B, vu_ged_cols(P, R)) */
+} vu_member_scores_args;
+VU_API int64_t vu_ged_cols(int32_t P, int32_t R);
+VU_API int vu_member_scores(const vu_member_scores_args* args, void* stream);
+
 /* One histogram pass of an exact radix select over float32 values (order statistics for np.quantile:
  * find_threshold.py:69-77, ace.py:387-388).  key = order-preserving 32-bit image of the float (NaN sorts last).
  *   level 0: hist[key >> 21]                                   += w      (one slot of 2048 counters)

@@ -471,6 +471,70 @@ def quantile_cases(ref):
     return out
 
 
+def ged_nll_cases(ref):
+    """ged_binary_fast (ged_fast.py:5-142) and Tester._compute_likelihood_stats / _compute_expected_nll
+    (test_2D.py:1043-1120; unbound, with a stand-in ``self`` that only carries ignore_index)."""
+    import types
+    gen = torch.Generator().manual_seed(31)
+    rng = np.random.default_rng(31)
+    out = {}
+    names = []
+    am = ["dice", "max_dice_pred", "max_dice_gt", "major_dice"]
+    specs = {
+        "lidc_like": dict(P=8, C=2, G=4, S=(32, 32), ign=None, scale=2.0),
+        "diffusion32": dict(P=32, C=2, G=4, S=(24, 24), ign=None, scale=1.0),
+        "ignore255": dict(P=5, C=2, G=3, S=(16, 24), ign=255, scale=8.0),       # GED only: the reference's NLL cannot index 255
+        "peaked": dict(P=6, C=2, G=2, S=(16, 16), ign=None, scale=60.0),        # p below the 1e-12 clamp
+        "empty_pred": dict(P=4, C=2, G=3, S=(12, 12), ign=None, scale=2.0),     # both-empty / one-empty Dice rules
+        "multiclass": dict(P=4, C=5, G=2, S=(12, 20), ign=None, scale=3.0),     # NLL only
+        "single_rater_2d": dict(P=3, C=2, G=1, S=(9, 7), ign=None, scale=2.0),  # gt given as (H, W) to the likelihood functions
+    }
+    for name, sp in specs.items():
+        P, C, G, S = sp["P"], sp["C"], sp["G"], sp["S"]
+        logits = sp["scale"] * torch.randn(P, C, *S, generator=gen)
+        if name == "empty_pred":
+            logits[:, 1] -= 50.0  # every member predicts background everywhere
+        x = torch.softmax(logits, dim=1)
+        gt = torch.from_numpy(rng.integers(0, C, (G, *S))).long()
+        if name == "empty_pred":
+            gt[0] = 0  # one rater empty as well -> Dice 1 for that column, 0 for the others
+        if sp["ign"] is not None:
+            gt[torch.from_numpy(rng.random((G, *S)) < 0.1)] = sp["ign"]
+        names.append(name)
+        out[f"{name}/x"] = x.numpy()
+        out[f"{name}/gt"] = gt.numpy()
+        out[f"{name}/ignore"] = np.int64(-999 if sp["ign"] is None else sp["ign"])
+        if C == 2:
+            res = ref.ged_binary_fast(x, gt, ignore_index=sp["ign"], additional_metrics=am)
+            for k in ["ged"] + am:
+                out[f"{name}/{k}"] = np.float64(res[k])
+        if sp["ign"] is None:
+            stand_in = types.SimpleNamespace(ignore_index=-1)
+            gt_arg = gt[0] if name == "single_rater_2d" else gt
+            m, g, mean = ref.Tester._compute_likelihood_stats(stand_in, x, gt_arg)
+            out[f"{name}/gt_model_nll"] = np.array(m, np.float64)
+            out[f"{name}/gt_nll"] = np.array(g, np.float64)
+            out[f"{name}/mean_nll"] = np.float64(mean)
+            out[f"{name}/expected_nll"] = np.float64(ref.Tester._compute_expected_nll(stand_in, x, gt_arg))
+    # an ignore value that IS a valid class index (the only way the reference's NLL runs with ignore_index >= 0)
+    P, C, G, S = 4, 3, 2, (10, 14)
+    x = torch.softmax(2.0 * torch.randn(P, C, *S, generator=gen), dim=1)
+    gt = torch.from_numpy(rng.integers(0, C, (G, *S))).long()
+    gt[1][:] = 2  # rater 1 entirely ignored -> valid_count == 0 -> zeros (test_2D.py:1060-1061)
+    stand_in = types.SimpleNamespace(ignore_index=2)
+    m, g, mean = ref.Tester._compute_likelihood_stats(stand_in, x, gt)
+    names.append("ignore_is_class")
+    out["ignore_is_class/x"] = x.numpy()
+    out["ignore_is_class/gt"] = gt.numpy()
+    out["ignore_is_class/ignore"] = np.int64(2)
+    out["ignore_is_class/gt_model_nll"] = np.array(m, np.float64)
+    out["ignore_is_class/gt_nll"] = np.array(g, np.float64)
+    out["ignore_is_class/mean_nll"] = np.float64(mean)
+    out["ignore_is_class/expected_nll"] = np.float64(ref.Tester._compute_expected_nll(stand_in, x, gt))
+    out["cases"] = np.array(names)
+    return out
+
+
 def main():
     assert ref_shim.available(), "needs /root/reference"
     ref = ref_shim.load()
@@ -479,7 +543,7 @@ def main():
     only = set(sys.argv[1:])  # e.g. ``python -m oracle.make_golden quantile.npz``: regenerate one file
     for fname, builder in (("uncertainty.npz", uncertainty_cases), ("aggregation.npz", aggregation_cases),
                            ("calibration.npz", calibration_cases), ("ncc_aurc.npz", ncc_aurc_cases),
-                           ("platt_fit.npz", platt_fit_cases), ("tasks.npz", task_cases), ("quantile.npz", quantile_cases)):
+                           ("platt_fit.npz", platt_fit_cases), ("tasks.npz", task_cases), ("quantile.npz", quantile_cases), ("ged_nll.npz", ged_nll_cases)):
         if only and fname not in only:
             continue
         data = builder(ref)

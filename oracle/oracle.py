@@ -499,6 +499,140 @@ def platt_fit(total, pos, neg, sum_unc) -> Tuple[float, float]:
 
 
 # --------------------------------------------------------------------------
+# member-level scores on the same slab: GED (evaluation/metrics/ged_fast.py:5-142)
+# and the likelihood statistics (uncertainty_modeling/test_2D.py:1043-1120)
+# --------------------------------------------------------------------------
+def ged_counts(member_labels: np.ndarray, gt: np.ndarray, ignore_index=None, mean_label: np.ndarray | None = None) -> Dict[str, np.ndarray]:
+    """Every integer the GED of ged_fast.py is made of, from (P, V) member labels
+    (argmax of each member, ged_fast.py:44) and (G, V) references:
+    pg_tp / pg_pred (P, G) and g_sum (G) on each reference's valid voxels (:51-62), pp_tp (P, P) and pos (P) (:84-88),
+    gg_tp / gg_sum (G, G) with [i, j] masked by reference j's validity (:95-103), and the majority counts (:121-131)."""
+    lab = np.asarray(member_labels).reshape(member_labels.shape[0], -1)
+    g = np.asarray(gt).reshape(gt.shape[0], -1)
+    valid = np.ones(g.shape, bool) if ignore_index is None else (g != ignore_index)
+    pred1 = lab == 1
+    gt1 = g == 1
+    gpos = gt1 & valid
+    out = {
+        "pg_tp": np.einsum("pv,gv->pg", pred1.astype(np.int64), gpos.astype(np.int64)),
+        "pg_pred": np.einsum("pv,gv->pg", pred1.astype(np.int64), valid.astype(np.int64)),
+        "g_sum": gpos.sum(1).astype(np.int64),
+        "pp_tp": np.einsum("pv,qv->pq", pred1.astype(np.int64), pred1.astype(np.int64)),
+        "pos": pred1.sum(1).astype(np.int64),
+        "gg_tp": np.einsum("iv,jv->ij", gt1.astype(np.int64), gpos.astype(np.int64)),
+        "gg_sum": np.einsum("iv,jv->ij", gt1.astype(np.int64), valid.astype(np.int64)),
+    }
+    if mean_label is not None:
+        m1 = np.asarray(mean_label).reshape(-1) == 1
+        maj = gt1.astype(np.float32).mean(0) >= 0.5  # ged_fast.py:121-122
+        va = valid.all(0) if ignore_index is not None else np.ones(m1.shape, bool)
+        out["major"] = np.array([(m1 & maj & va).sum(), (m1 & va).sum(), (maj & va).sum()], np.int64)
+    return out
+
+
+def ged_from_counts(c: Dict[str, np.ndarray], additional_metrics=("dice",)) -> Dict[str, float]:
+    """ged_fast.py:60-140 from the counts, in the reference's float32 arithmetic."""
+    f = np.float32
+    tp, ps, gs = c["pg_tp"].astype(f), c["pg_pred"].astype(f), np.broadcast_to(c["g_sum"].astype(f), c["pg_tp"].shape)
+    denom = f(2) * tp + (ps - tp) + (gs - tp)
+    both_empty = (ps == 0) & (gs == 0)
+    one_empty = (ps == 0) ^ (gs == 0)
+    dice_pg = np.zeros(tp.shape, f)
+    dice_pg[both_empty] = 1.0
+    idx = ~(both_empty | one_empty) & (denom > 0)
+    dice_pg[idx] = (f(2) * tp[idx]) / denom[idx]
+    d_gp = float(np.mean(f(1) - dice_pg, dtype=f))
+    pos = c["pos"].astype(f)
+    den_pp = pos[:, None] + pos[None, :]
+    dice_pp = np.ones(den_pp.shape, f)
+    m = den_pp > 0
+    dice_pp[m] = (f(2) * c["pp_tp"].astype(f)[m]) / den_pp[m]
+    d_pp = float(np.mean(f(1) - dice_pp, dtype=f))
+    G = c["g_sum"].shape[0]
+    per_j = []
+    for j in range(G):
+        den = c["gg_sum"][:, j].astype(f) + f(c["g_sum"][j])
+        dice_g = np.ones(G, f)
+        mg = den > 0
+        dice_g[mg] = (f(2) * c["gg_tp"][:, j].astype(f)[mg]) / den[mg]
+        per_j.append(f(1) - np.mean(dice_g, dtype=f))
+    d_gg = float(np.mean(np.array(per_j, f), dtype=f)) if per_j else 0.0
+    res = {"ged": float(2 * d_gp - d_pp - d_gg)}
+    if "dice" in additional_metrics:
+        res["dice"] = float(np.mean(dice_pg, dtype=f))
+    if "max_dice_pred" in additional_metrics:
+        res["max_dice_pred"] = float(np.mean(dice_pg.max(1), dtype=f))
+    if "max_dice_gt" in additional_metrics:
+        res["max_dice_gt"] = float(np.mean(dice_pg.max(0), dtype=f))
+    if "major_dice" in additional_metrics:
+        tpm, psm, gsm = (f(x) for x in c["major"])
+        if psm == 0 and gsm == 0:
+            res["major_dice"] = 1.0
+        elif psm == 0 or gsm == 0:
+            res["major_dice"] = 0.0
+        else:
+            res["major_dice"] = float(f(2) * tpm / (psm + gsm))
+    return res
+
+
+def ged_binary_fast(output_softmax: torch.Tensor, ground_truth, ignore_index=None, additional_metrics=None) -> Dict[str, float]:
+    """ged_fast.py:5-142 for (P, 2, H, W) probabilities and (G, H, W) references."""
+    if additional_metrics is None:
+        additional_metrics = ["dice"]
+    if output_softmax.ndim != 4 or output_softmax.shape[1] != 2:
+        raise ValueError("ged_binary_fast expects (P, 2, H, W) softmax input for binary segmentation")
+    gt = np.asarray(ground_truth)
+    if gt.ndim != 3:
+        raise ValueError("ged_binary_fast expects ground_truth of shape (G, H, W)")
+    x = output_softmax.detach().cpu().numpy()
+    labels = np.stack([argmax_first_nan_max(m) for m in x])
+    mean_label = argmax_first_nan_max(mean_members_f32(x)) if "major_dice" in additional_metrics else None
+    return ged_from_counts(ged_counts(labels, gt, ignore_index, mean_label), additional_metrics)
+
+
+def likelihood_sums(image_preds: np.ndarray, gt: np.ndarray, ignore_index: int, eps: float = 1e-12):
+    """The reductions of test_2D.py:1043-1075: per reference g and member p the sum over valid voxels of
+    log(clamp(p[member, gt, voxel], eps)) (float64 here; the reference reduces in float32) and the valid count
+    (every voxel when ignore_index < 0, :1055-1060)."""
+    x = np.asarray(image_preds, np.float32)
+    P, C = x.shape[:2]
+    x = x.reshape(P, C, -1)
+    g = np.asarray(gt).reshape(gt.shape[0], -1).astype(np.int64)
+    logp = np.log(np.maximum(x, np.float32(eps)))  # torch.clamp(min=eps) then log, float32
+    logp = np.where(np.isnan(x), np.float32(np.nan), logp)
+    sums = np.zeros((g.shape[0], P), np.float64)
+    counts = np.zeros(g.shape[0], np.int64)
+    for r in range(g.shape[0]):
+        valid = g[r] != ignore_index if ignore_index >= 0 else np.ones(g.shape[1], bool)
+        counts[r] = int(valid.sum())
+        if counts[r] == 0:
+            continue
+        idx = np.where(valid, g[r], 0)
+        picked = np.take_along_axis(logp, np.broadcast_to(idx[None, None, :], (P, 1, idx.size)), axis=1)[:, 0]
+        sums[r] = (picked.astype(np.float64) * valid).sum(1)
+    return sums, counts
+
+
+def compute_likelihood_stats(image_preds: np.ndarray, gt: np.ndarray, ignore_index: int, eps: float = 1e-12):
+    """test_2D.py:1043-1083: (gt_model_nll [G][P], gt_nll [G], mean_nll)."""
+    sums, counts = likelihood_sums(image_preds, gt, ignore_index, eps)
+    nll = np.where(counts[:, None] > 0, -(sums / np.maximum(counts, 1)[:, None]), 0.0)
+    gt_model_nll = [[float(np.float32(v)) for v in row] for row in nll]
+    gt_nll = [float(np.mean(np.array(row, np.float32), dtype=np.float32)) for row in gt_model_nll]
+    flat = [v for row in gt_model_nll for v in row]
+    return gt_model_nll, gt_nll, (float(np.mean(np.array(flat))) if flat else 0.0)
+
+
+def compute_expected_nll(pred_samples: np.ndarray, gt: np.ndarray, ignore_index: int, eps: float = 1e-12) -> float:
+    """test_2D.py:1085-1120: mean over references and samples of the per-sample NLL."""
+    sums, counts = likelihood_sums(pred_samples, gt, ignore_index, eps)
+    if sums.size == 0:
+        return 0.0
+    nll = np.where(counts[:, None] > 0, -(sums / np.maximum(counts, 1)[:, None]), 0.0).astype(np.float32)
+    return float(np.mean(nll, dtype=np.float32))
+
+
+# --------------------------------------------------------------------------
 # ambiguity: NCC (evaluation/metrics/ncc.py:9-28, experiment_dataloader.py:283)
 # --------------------------------------------------------------------------
 def rater_variance_map(refs: np.ndarray) -> np.ndarray:

@@ -32,6 +32,9 @@ _STUBS = [
     "albumentations", "albumentations.pytorch", "albumentations.core",
     "albumentations.core.transforms_interface", "tifffile", "matplotlib", "matplotlib.pyplot",
     "skimage", "skimage.io", "seaborn", "wandb",
+    # uncertainty_modeling.test_2D (only for Tester._compute_likelihood_stats / _compute_expected_nll)
+    "pytorch_lightning.utilities", "pytorch_lightning.utilities.rank_zero", "pytorch_lightning.utilities.types",
+    "pytorch_lightning.strategies", "pytorch_lightning.callbacks.progress", "loss_modules",
 ]
 
 
@@ -65,6 +68,11 @@ def load() -> types.SimpleNamespace:
     ncc = importlib.import_module("evaluation.metrics.ncc")
     aurc = importlib.import_module("evaluation.metrics.aurc")
     thr = importlib.import_module("evaluation.uncertainty_aggregation.find_threshold")
+    ged = importlib.import_module("evaluation.metrics.ged_fast")
+    try:
+        tester = importlib.import_module("uncertainty_modeling.test_2D").Tester
+    except Exception:  # pragma: no cover - depends on which optional packages this container has
+        tester = None
     return types.SimpleNamespace(
         calculate_uncertainty=tu.calculate_uncertainty,
         calculate_one_minus_msr=tu.calculate_one_minus_msr,
@@ -81,6 +89,8 @@ def load() -> types.SimpleNamespace:
         ncc_module=ncc,
         aurc_module=aurc,
         thr_module=thr,
+        ged_binary_fast=ged.ged_binary_fast,
+        Tester=tester,
         calculate_foreground_quantile_image=thr.calculate_foreground_quantile_image,
         calculate_threshold_image=thr.calculate_threshold_image,
         platt_scale_confid=ace.platt_scale_confid,

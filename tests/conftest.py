@@ -47,3 +47,8 @@ def case_names(d):
 @pytest.fixture(scope="session")
 def golden_quantile():
     return _load("quantile.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_ged_nll():
+    return _load("ged_nll.npz")

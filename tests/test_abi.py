@@ -36,6 +36,8 @@ def test_header_constants_match_binding():
     assert lib.vu_struct_size(0) == C.sizeof(_lib.FusedArgs)
     assert lib.vu_struct_size(1) == C.sizeof(_lib.MapStatsArgs)
     assert lib.vu_struct_size(2) == C.sizeof(_lib.Calib)
+    assert lib.vu_struct_size(4) == C.sizeof(_lib.MemberScoresArgs)
+    assert lib.vu_ged_cols(32, 4) == 2 * 32 * 4 + 4 + 32 * 32 + 32 + 2 * 16 + 3
 
 
 def test_argument_errors_without_a_device():

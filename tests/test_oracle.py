@@ -241,3 +241,29 @@ def test_eqace_and_thresholds_match_golden(golden_quantile):
     want_t = json.loads(str(g["drv/threshold_analysis.json"]))["Softmax"]
     for u in ("TU", "AU", "EU"):
         assert oracle.uncertainty_threshold([g[f"drv/{i}/{u}"] for i in ids], got_q) == want_t[f"Mean {u} threshold"]
+
+
+def test_ged_and_likelihood_match_golden(golden_ged_nll):
+    """oracle.ged_binary_fast / compute_likelihood_stats / compute_expected_nll against what the unmodified
+    ged_fast.ged_binary_fast and Tester._compute_likelihood_stats / _compute_expected_nll returned (float32 reductions in
+    the reference: 2e-6 relative)."""
+    from oracle import oracle
+    g = golden_ged_nll
+    am = ["dice", "max_dice_pred", "max_dice_gt", "major_dice"]
+    for name in g["cases"]:
+        x, gt, ign = g[f"{name}/x"], g[f"{name}/gt"], int(g[f"{name}/ignore"])
+        if f"{name}/ged" in g:
+            got = oracle.ged_binary_fast(torch.from_numpy(x), gt, None if ign == -999 else ign, am)
+            for k in ["ged"] + am:
+                np.testing.assert_allclose(got[k], float(g[f"{name}/{k}"]), rtol=2e-6, atol=2e-7, err_msg=f"{name}/{k}")
+        if f"{name}/mean_nll" in g:
+            gt_arg = gt[0] if name == "single_rater_2d" else gt
+            gt_arg = gt_arg[None] if gt_arg.ndim == x.ndim - 2 else gt_arg
+            m, r, mean = oracle.compute_likelihood_stats(x, gt_arg, -1 if ign == -999 else ign)
+            np.testing.assert_allclose(np.array(m), g[f"{name}/gt_model_nll"], rtol=2e-6, atol=1e-7, err_msg=name)
+            np.testing.assert_allclose(np.array(r), g[f"{name}/gt_nll"], rtol=2e-6, atol=1e-7, err_msg=name)
+            np.testing.assert_allclose(mean, float(g[f"{name}/mean_nll"]), rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(oracle.compute_expected_nll(x, gt_arg, -1 if ign == -999 else ign),
+                                       float(g[f"{name}/expected_nll"]), rtol=2e-6, atol=1e-7)
+    with pytest.raises(ValueError):
+        oracle.ged_binary_fast(torch.zeros(3, 3, 4, 4), np.zeros((2, 4, 4), np.int64))
