@@ -201,12 +201,30 @@ __device__ __forceinline__ void load_gt(const GtView& gt, long long b, int r, lo
     }
 }
 
+// uint8 references of `VEC` consecutive voxels of rater r as they lie in memory: byte j = voxel v + j (upper bytes 0)
+template <int VEC>
+__device__ __forceinline__ unsigned load_gt_bytes(const GtView& gt, long long b, int r, long long v) {
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(gt.data) + b * gt.sb + (long long)r * gt.sr;
+    if (VEC == 4 && gt.align >= 4) return __ldg(reinterpret_cast<const unsigned*>(base + v));
+    if (VEC == 2 && gt.align >= 2) return (unsigned)__ldg(reinterpret_cast<const unsigned short*>(base + v));
+    unsigned w = 0;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) w |= (unsigned)__ldg(base + (v + k) * gt.sv) << (8 * k);
+    return w;
+}
+
+// ---- four voxels per word: byte-wise tests (results: 0x80 in the bytes where the test holds) --------------------------
+constexpr unsigned kB01 = 0x01010101u, kB80 = 0x80808080u, kB7f = 0x7f7f7f7fu;
+__device__ __forceinline__ unsigned bytes_nonzero(unsigned x) { return (((x & kB7f) + kB7f) | x) & kB80; }
+__device__ __forceinline__ unsigned bytes_equal(unsigned a, unsigned b) { return ~bytes_nonzero(a ^ b) & kB80; }
+
 struct CalibDev {
     float a, b;
     float edge[VU_N_EDGES];  // thresholds on u (sign-flipped when conf falls with u); NaN = never reached
     int increasing;
     int identity;  // the map already is the confidence
 };
+constexpr float kRoundMagic = 12582912.0f;  // 1.5 * 2^23: x + magic rounds x to an integer held in the low mantissa bits
 
 struct StatParams {
     unsigned flags;
@@ -257,7 +275,7 @@ constexpr int kHistBins = VU_N_BINS - 1;  // 20 real bins; slot 20 (NaN) is coun
 // histogram replicas per warp: 16 (two half-warp phases; the register-streaming kernels, 8 warps per CTA) or 32 (one
 // replica per lane, no phases; the three statistics warps of the TMA kernel)
 constexpr unsigned kRuntimeFlags = 0xffffffffu;  // template value: statistics mask read from StatParams at run time
-constexpr int kEdgePad = 24;  // E[0] = NaN, E[1..19] = edges, E[20..23] = NaN
+constexpr int kEdgePad = 24;  // per uncertainty type: float2 EP[k] = (lower, upper) edge of bin k on u; NaN = no such edge
 
 // Platt-fit data: one CTA-wide histogram [unc][bin][samples, correct, q_hi, q_lo] of int32 updated with native shared
 // atomics (768 bins are too many to replicate per lane), plus the edge table T[0..256] (padded) and 1 / edge
@@ -276,7 +294,7 @@ __host__ __device__ inline size_t stats_smem_bytes(unsigned flags, int R, int th
     if (!flags) return 0;
     size_t n = (size_t)(stats_num_fslots(flags) + stats_num_islots(flags, R)) * threads * 8;
     if (flags & VU_STAT_CALIB)
-        n += (size_t)(threads / 32) * (VU_N_UNC * kHistBins * rep) * sizeof(uint2) + (size_t)VU_N_UNC * kEdgePad * sizeof(float);
+        n += (size_t)(threads / 32) * (VU_N_UNC * kHistBins * rep) * sizeof(uint2) + (size_t)VU_N_UNC * kEdgePad * sizeof(float2);
     if (flags & VU_STAT_PLATT_FIT) n += (size_t)kPlattWords * sizeof(int) + (size_t)kPlattTab * 2 * sizeof(float);
     return n;
 }
@@ -287,7 +305,7 @@ struct StatsLayout {
     double* fs;
     unsigned long long* is;
     uint2* hist;  // [warp][unc][bin][replica]
-    float* E;
+    float2* E;    // [unc][kEdgePad]
     int* phist;   // Platt-fit data [unc][bin][4]
     float* pT;    // [kPlattTab] edges, then [kPlattTab] reciprocals
     int nF, nI;
@@ -297,7 +315,7 @@ struct StatsLayout {
         fs = reinterpret_cast<double*>(smem);
         is = reinterpret_cast<unsigned long long*>(fs + (size_t)nF * THREADS);
         hist = reinterpret_cast<uint2*>(is + (size_t)nI * THREADS);
-        E = reinterpret_cast<float*>(hist + ((sp.flags & VU_STAT_CALIB) ? (THREADS / 32) * kHistWordsPerWarp : 0));
+        E = reinterpret_cast<float2*>(hist + ((sp.flags & VU_STAT_CALIB) ? (THREADS / 32) * kHistWordsPerWarp : 0));
         phist = reinterpret_cast<int*>(E + ((sp.flags & VU_STAT_CALIB) ? VU_N_UNC * kEdgePad : 0));
         pT = reinterpret_cast<float*>(phist + kPlattWords);
     }
@@ -319,8 +337,10 @@ __device__ __noinline__ void stats_init(const StatParams& sp, void* smem) {
     if (sp.flags & VU_STAT_CALIB) {
         for (int t = ((int)threadIdx.x - TID0); t < (THREADS / 32) * kHistWordsPerWarp; t += THREADS) L.hist[t] = make_uint2(0u, 0u);
         for (int t = ((int)threadIdx.x - TID0); t < VU_N_UNC * kEdgePad; t += THREADS) {
-            const int k = t / kEdgePad, e = t % kEdgePad;
-            L.E[t] = (e >= 1 && e <= VU_N_EDGES) ? sp.calib[k].edge[e - 1] : __int_as_float(0x7fc00000);
+            const int k = t / kEdgePad, e = t % kEdgePad;  // bin e lies between interior edges e - 1 and e
+            const float nan = __int_as_float(0x7fc00000);
+            L.E[t] = make_float2((e >= 1 && e <= VU_N_EDGES) ? sp.calib[k].edge[e - 1] : nan,
+                                 (e >= 0 && e < VU_N_EDGES) ? sp.calib[k].edge[e] : nan);
         }
     }
     if (sp.flags & VU_STAT_PLATT_FIT) {
@@ -431,7 +451,7 @@ __device__ __noinline__ void stats_flush(const StatParams& sp, void* smem, long 
                 if (tru) atomicAdd(irow + VU_I64_BIN_TRUE + col, (unsigned long long)tru);
                 if (bin > 0)  // bin 0 is summed in floating point by the threads (slots FS_BIN0)
                     atomicAdd(frow + VU_F64_BIN_SUMS + col,
-                              (double)tot * (double)((float)bin * 0.05f) + (double)q * (1.0 / (double)(1 << kQBits)));
+                              (double)tot * ((double)bin * (double)0.05f) + (double)q * (1.0 / (double)(1 << kQBits)));  // q is relative to bin * 0.05f
             }
         }
     }
@@ -492,25 +512,15 @@ __device__ __forceinline__ void stats_prefetch_gt(const StatParams& sp, long lon
     for (int r = 0; r < sp.gt.R; ++r) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (long long)r * sp.gt.sr * esz));
 }
 
-// ace.py:329 in float32: 1 / (1 + exp((-u) * a + b)); ace.py:333 clips to [0, 1].  Bins are decided on u
-// itself (calib_bin), so this value only feeds the floating bin_sums: fast exp / reciprocal are enough.
-__device__ __forceinline__ float platt_conf(float u, float a, float b, int identity) {
+// ace.py:329 in float32: 1 / (1 + exp((-u) * a + b)); ace.py:333 clips to [0, 1].  Bins are decided on u itself (below), so
+// this value only feeds the floating bin_sums and the candidate bin: ex2.approx / rcp.approx are enough, and the result
+// lies in [0, 1] by construction (NaN for NaN u).  a2 = -a log2(e), b2 = b log2(e).
+__device__ __forceinline__ float platt_conf(float u, float a2, float b2, int identity) {
     if (identity) return fminf(fmaxf(u, 0.0f), 1.0f);
-    const float z = fmaf(-u, a, b);
-    const float c = __fdividef(1.0f, 1.0f + __expf(z));
-    return fminf(fmaxf(c, 0.0f), 1.0f);
-}
-
-// bin = number of interior edges e_k with conf(u) >= e_k, decided on u itself
-// (see vu_calib in valunc.h).  The device confidence is within a few ulp of the
-// reference's, so floor(conf * 20) is at most one bin off; the two neighbouring
-// thresholds on u settle it exactly.  E is padded with NaN (compares false).
-__device__ __forceinline__ int calib_bin(const float* E, int increasing, float u, float conf) {
-    const float uu = increasing ? u : -u;
-    int k0 = __float2int_rd(conf * 20.0f);
-    k0 = k0 > 19 ? 19 : (k0 < 0 ? 0 : k0);
-    const float e_lo = E[k0], e_hi = E[k0 + 1];  // E[j] = interior edge j-1, i.e. the lower edge of bin j
-    return k0 + (uu >= e_hi ? 1 : 0) - (uu < e_lo ? 1 : 0);
+    float e, c;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(u, a2, b2)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(1.0f + e));
+    return c;
 }
 
 template <int VEC> struct FVec;
@@ -591,41 +601,78 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
     }
     if (!(flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC | VU_STAT_PLATT_FIT))) return;
 
-    int n_valid[VEC], n_correct[VEC];
+    // ---- references: per voxel the number of valid / correct raters, as byte j of one word each (<= 8) -------------
+    constexpr unsigned kBytes = VEC == 4 ? 0xffffffffu : (VEC == 2 ? 0x0000ffffu : 0x000000ffu);
+    unsigned nv4 = 0, nc4 = 0;
     GAcc gsum[VEC], gsq[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) { n_valid[j] = 0; n_correct[j] = 0; gsum[j] = 0; gsq[j] = 0; }
+    for (int j = 0; j < VEC; ++j) { gsum[j] = 0; gsq[j] = 0; }
     const int R = sp.gt.data ? sp.gt.R : 0;
     if (active && R > 0) {
-        G cmp[VEC];
+        const unsigned lab4 = labels_packed & kBytes;
+        unsigned cmp4 = lab4;  // what a reference has to equal to count as correct (ace.py:488)
+        if (lut) {
+            cmp4 = 0u;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) cmp[j] = (G)(lut ? (int)__ldg(lut + label[j]) : label[j]);
+            for (int j = 0; j < VEC; ++j) cmp4 |= (unsigned)__ldg(lut + label[j]) << (8 * j);
+        }
+        const unsigned pp_hi = bytes_equal(lab4, kB01) & kBytes;  // predicted foreground (test_2D.py:878)
         const bool has_ign = sp.gt.has_ignore != 0;
-        const G ign = (G)sp.gt.ignore;
+        const bool ign_byte = has_ign && sp.gt.ignore >= 0 && sp.gt.ignore <= 255;  // else no uint8 reference can match it
+        const unsigned ign4 = ((unsigned)sp.gt.ignore & 0xffu) * kB01;
+        const long long ign = sp.gt.ignore;
 #pragma unroll 1
         for (int r0 = 0; r0 < R; r0 += RB) {
-            G g[RB][VEC];
+            unsigned w[RB];
+            long long g64[sizeof(GT) == 1 ? 1 : RB][VEC];
 #pragma unroll
-            for (int i = 0; i < RB; ++i)
-                if (r0 + i < R) load_gt<VEC>(sp.gt, b, r0 + i, v, g[i], GT());
+            for (int i = 0; i < RB; ++i) {
+                w[i] = 0u;
+                if (r0 + i < R) {
+                    if (sizeof(GT) == 1) w[i] = load_gt_bytes<VEC>(sp.gt, b, r0 + i, v);
+                    else load_gt<VEC>(sp.gt, b, r0 + i, v, g64[sizeof(GT) == 1 ? 0 : i], (long long)0);
+                }
+            }
 #pragma unroll
             for (int i = 0; i < RB; ++i) {
                 if (r0 + i >= R) break;
-                int tp = 0, ps = 0, gs = 0;
+                unsigned valid_hi, eq_hi, gp_hi;  // 0x80 in byte j: reference of voxel j is valid / equals the label / is 1
+                if (sizeof(GT) == 1) {
+                    valid_hi = (ign_byte ? bytes_nonzero(w[i] ^ ign4) : kB80) & kBytes;  // ace.py:492-499, test_2D.py:880
+                    eq_hi = bytes_equal(w[i], cmp4) & valid_hi;
+                    gp_hi = bytes_equal(w[i], kB01) & valid_hi;                          // test_2D.py:882
+                    if (flags & VU_STAT_NCC) {
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    const G gj = g[i][j];
-                    const bool valid = !(has_ign && gj == ign);                              // ace.py:492-499, test_2D.py:880
-                    const bool pp = (label[j] == 1) && valid, gp = (gj == (G)1) && valid;  // test_2D.py:878-886
-                    tp += (pp && gp); ps += pp; gs += gp;
-                    n_valid[j] += valid;
-                    n_correct[j] += (valid && gj == cmp[j]);                                 // ace.py:488
-                    gsum[j] += (GAcc)gj;
-                    gsq[j] += (GAcc)gj * (GAcc)gj;
+                        for (int j = 0; j < VEC; ++j) {
+                            const int gj = (int)((w[i] >> (8 * j)) & 0xffu);
+                            gsum[j] += (GAcc)gj;
+                            gsq[j] += (GAcc)(gj * gj);
+                        }
+                    }
+                } else {
+                    valid_hi = 0u; eq_hi = 0u; gp_hi = 0u;
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const long long gj = g64[sizeof(GT) == 1 ? 0 : i][j];
+                        const bool valid = !(has_ign && gj == ign);
+                        valid_hi |= valid ? (0x80u << (8 * j)) : 0u;
+                        eq_hi |= (valid && gj == (long long)((cmp4 >> (8 * j)) & 0xffu)) ? (0x80u << (8 * j)) : 0u;
+                        gp_hi |= (valid && gj == 1) ? (0x80u << (8 * j)) : 0u;
+                        if (flags & VU_STAT_NCC) {
+                            gsum[j] += (GAcc)gj;
+                            gsq[j] += (GAcc)gj * (GAcc)gj;
+                        }
+                    }
                 }
-                if ((flags & VU_STAT_DICE) && (tp | ps | gs))
-                    cs.is[(IS_DICE + r0 + i) * THREADS + tid] +=
-                        (unsigned long long)tp | ((unsigned long long)ps << kPackBits) | ((unsigned long long)gs << (2 * kPackBits));
+                nv4 += valid_hi >> 7;
+                nc4 += eq_hi >> 7;
+                if (flags & VU_STAT_DICE) {
+                    const unsigned ppv = pp_hi & valid_hi;
+                    const unsigned tp = __popc(ppv & gp_hi), ps = __popc(ppv), gs = __popc(gp_hi);
+                    if (tp | ps | gs)
+                        cs.is[(IS_DICE + r0 + i) * THREADS + tid] +=
+                            (unsigned long long)tp | ((unsigned long long)ps << kPackBits) | ((unsigned long long)gs << (2 * kPackBits));
+                }
             }
         }
     }
@@ -668,7 +715,7 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
             int* hk = cs.phist + k * (VU_N_PLATT_BINS * 4);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                const int nv = n_valid[j];
+                const int nv = (int)((nv4 >> (8 * j)) & 0xffu), nc = (int)((nc4 >> (8 * j)) & 0xffu);
                 if (active && nv > 0) {
                     const float x = u[k][j];
                     // candidate bin from log10(u), settled exactly by the two neighbouring edges (ace.py:117-126)
@@ -684,7 +731,7 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
                     const int q = __float2int_rn(rel * (float)(1 << kPlattQBits)) * nv;
                     int* h = hk + bin * 4;
                     atomicAdd(h, nv);
-                    if (n_correct[j]) atomicAdd(h + 1, n_correct[j]);
+                    if (nc) atomicAdd(h + 1, nc);
                     atomicAdd(h + 2, q >> kPlattQSplit);
                     atomicAdd(h + 3, q & ((1 << kPlattQSplit) - 1));
                 }
@@ -694,49 +741,74 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
     if (flags & VU_STAT_CALIB) {  // every lane of the warp walks through here (the half-warp phases are warp-synchronous)
         uint2* hw = cs.hist + (tid >> 5) * kHistWordsPerWarp + (lane & (kHistRep - 1));
         const bool upper = lane >= kHistRep;  // REP == 32: never
-        unsigned long long nan_tot = 0, nan_tru = 0;
+        // per voxel: samples | correct << 16 (what a hit adds to the count word) and the samples as a float; lanes past the
+        // end of the image and voxels without a valid rater carry zeros, so whatever bin they compute receives nothing
+        unsigned vc[VEC];
+        float nvf[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const unsigned nv = (nv4 >> (8 * j)) & 0xffu, nc = (nc4 >> (8 * j)) & 0xffu;
+            vc[j] = nv | (nc << 16);
+            nvf[j] = (float)nv;
+        }
+        unsigned nanbits = 0;  // bit (k * VEC + j): a sample with NaN uncertainty (rare: handled after the loops)
 #pragma unroll
         for (int k = 0; k < VU_N_UNC; ++k) {
             if (!((mask >> k) & 1)) continue;
             float bin0 = 0.f;
             const CalibDev& cal = sp.calib[k];
-            const float* E = cs.E + k * kEdgePad;
+            const float a2 = -cal.a * kLog2e, b2 = cal.b * kLog2e, sgn = cal.increasing ? 1.0f : -1.0f;
+            const float2* E = cs.E + k * kEdgePad;
             uint2* hk = hw + k * (kHistBins * kHistRep);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                const int nv = n_valid[j];
                 const float x = u[k][j];
                 const bool is_nan = x != x;
-                const bool sample = active && nv > 0;
-                const bool hit = sample && !is_nan;
-                // computed unconditionally (garbage for lanes that do not hit, which add nothing)
-                const float conf = platt_conf(x, cal.a, cal.b, cal.identity);
-                int bin = calib_bin(E, cal.increasing, x, conf);
-                bin = hit ? bin : 0;
-                const int q = __float2int_rn((conf - (float)bin * 0.05f) * (float)(1 << kQBits)) * nv;
-                bin0 += (hit && bin == 0) ? conf * (float)nv : 0.f;
-                if (sample && is_nan) {  // np.digitize puts NaN past the last edge: slot 20, counted in the integer slots
-                    nan_tot += (unsigned long long)nv << (k * kPackBits);
-                    nan_tru += (unsigned long long)n_correct[j] << (k * kPackBits);
-                }
-                const unsigned inc = hit ? ((unsigned)nv | ((unsigned)n_correct[j] << 16)) : 0u;
-                const unsigned qq = hit ? (unsigned)q : 0u;
-                uint2* h = hk + bin * kHistRep;
+                const float conf = platt_conf(x, a2, b2, cal.identity);
+                // candidate bin round(conf * 20), read off the mantissa (no conversion); the true bin is within one of it and
+                // the two neighbouring thresholds on u settle it exactly (see vu_calib in valunc.h; NaN edges compare false)
+                const float kf = fminf(fmaf(conf, 20.0f, kRoundMagic), kRoundMagic + 19.0f);
+                const int k0 = __float_as_int(kf) & 0xff;
+                const float2 e = E[k0];
+                const float uu = x * sgn;
+                const bool up = uu >= e.y, down = uu < e.x;
+                const int bin = k0 + (up ? 1 : 0) - (down ? 1 : 0);
+                const float binf = (kf - kRoundMagic) + (up ? 1.0f : 0.0f) - (down ? 1.0f : 0.0f);
+                // q = round((conf - bin / 20) * 2^21), again through the mantissa
+                const float qf = fmaf(binf, -0.05f * (float)(1 << kQBits), conf * (float)(1 << kQBits));
+                const int q = __float_as_int(qf + kRoundMagic) - __float_as_int(kRoundMagic);
+                const unsigned inc = is_nan ? 0u : vc[j];
+                const unsigned qq = (unsigned)(q * (int)(inc & 0xffffu));
+                bin0 += (bin == 0 && !is_nan) ? conf * nvf[j] : 0.f;
+                nanbits |= (is_nan && vc[j] != 0u) ? (1u << (k * VEC + j)) : 0u;
+                uint2* h = hk + (is_nan ? 0 : bin) * kHistRep;
                 if (kHistRep == 32) {
-                    // one replica per lane: plain read-modify-write, lanes that do not hit add zero to bin 0
-                    uint2 w = *h;
-                    w.x += inc; w.y += qq;
-                    *h = w;
+                    // one replica per lane: plain read-modify-write, lanes that do not hit add zero
+                    uint2 wd = *h;
+                    wd.x += inc; wd.y += qq;
+                    *h = wd;
                 } else {
-                    if (!upper) { uint2 w = *h; w.x += inc; w.y += qq; *h = w; }
+                    if (!upper) { uint2 wd = *h; wd.x += inc; wd.y += qq; *h = wd; }
                     __syncwarp();
-                    if (upper) { uint2 w = *h; w.x += inc; w.y += qq; *h = w; }
+                    if (upper) { uint2 wd = *h; wd.x += inc; wd.y += qq; *h = wd; }
                     __syncwarp();
                 }
             }
             if (bin0 != 0.f) cs.fs[(FS_BIN0 + k) * THREADS + tid] += (double)bin0;
         }
-        if (nan_tot) { cs.is[IS_NANTOT * THREADS + tid] += nan_tot; cs.is[IS_NANTRU * THREADS + tid] += nan_tru; }
+        if (nanbits) {  // np.digitize puts NaN past the last edge: slot 20, counted in the integer slots
+            unsigned long long nan_tot = 0, nan_tru = 0;
+#pragma unroll
+            for (int k = 0; k < VU_N_UNC; ++k)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                    if ((nanbits >> (k * VEC + j)) & 1u) {
+                        nan_tot += (unsigned long long)(vc[j] & 0xffffu) << (k * kPackBits);
+                        nan_tru += (unsigned long long)(vc[j] >> 16) << (k * kPackBits);
+                    }
+            cs.is[IS_NANTOT * THREADS + tid] += nan_tot;
+            cs.is[IS_NANTRU * THREADS + tid] += nan_tru;
+        }
     }
 }
 
