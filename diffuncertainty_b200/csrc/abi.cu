@@ -117,6 +117,9 @@ static int fill_stat_params(StatParams& st, uint32_t flags, unsigned unc_mask, l
         st.calib[k].increasing = mode != VU_CALIB_PLATT_DEC;
         st.calib[k].identity = mode == VU_CALIB_IDENTITY;
         for (int e = 0; e < VU_N_EDGES; ++e) st.calib[k].edge[e] = st.calib[k].increasing ? calib[k].edge_u[e] : -calib[k].edge_u[e];
+        st.calib[k].a2 = -calib[k].a * kLog2e;
+        st.calib[k].b2 = calib[k].b * kLog2e;
+        st.calib[k].sgn = st.calib[k].increasing ? 1.0f : -1.0f;
     }
     st.lut = lut;
     st.ncc_gt_map = ncc_gt_map;
@@ -307,6 +310,7 @@ int vu_binned_calib(const float* map, const uint8_t* labels, int64_t V, const vu
     cd.increasing = calib->mode != VU_CALIB_PLATT_DEC;
     cd.identity = calib->mode == VU_CALIB_IDENTITY;
     for (int e = 0; e < VU_N_EDGES; ++e) cd.edge[e] = cd.increasing ? calib->edge_u[e] : -calib->edge_u[e];
+    cd.a2 = -calib->a * kLog2e; cd.b2 = calib->b * kLog2e; cd.sgn = cd.increasing ? 1.0f : -1.0f;
     return launch_binned_calib(map, labels, V, gv, cd, label_lut, reinterpret_cast<unsigned long long*>(out_counts), out_sums,
                                (cudaStream_t)stream);
 }

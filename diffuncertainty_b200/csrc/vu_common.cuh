@@ -223,6 +223,8 @@ struct CalibDev {
     float edge[VU_N_EDGES];  // thresholds on u (sign-flipped when conf falls with u); NaN = never reached
     int increasing;
     int identity;  // the map already is the confidence
+    float a2, b2;  // -a log2(e), b log2(e): conf = 1 / (1 + 2^(u a2 + b2))
+    float sgn;     // +1 when conf rises with u, else -1 (the thresholds are sign-flipped to match)
 };
 constexpr float kRoundMagic = 12582912.0f;  // 1.5 * 2^23: x + magic rounds x to an integer held in the low mantissa bits
 
@@ -757,31 +759,30 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
             if (!((mask >> k) & 1)) continue;
             float bin0 = 0.f;
             const CalibDev& cal = sp.calib[k];
-            const float a2 = -cal.a * kLog2e, b2 = cal.b * kLog2e, sgn = cal.increasing ? 1.0f : -1.0f;
+            const float a2 = cal.a2, b2 = cal.b2, sgn = cal.sgn;
             const float2* E = cs.E + k * kEdgePad;
             uint2* hk = hw + k * (kHistBins * kHistRep);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 const float x = u[k][j];
                 const bool is_nan = x != x;
-                const float conf = platt_conf(x, a2, b2, cal.identity);
+                const float conf = is_nan ? 0.0f : platt_conf(x, a2, b2, cal.identity);  // finite from here on
                 // candidate bin round(conf * 20), read off the mantissa (no conversion); the true bin is within one of it and
-                // the two neighbouring thresholds on u settle it exactly (see vu_calib in valunc.h; NaN edges compare false)
+                // the two neighbouring thresholds on u settle it exactly (see vu_calib in valunc.h; NaN edges and NaN u
+                // compare false).  t = magic + bin stays in the mantissa domain: bin = low bits, float(bin) = t - magic.
                 const float kf = fminf(fmaf(conf, 20.0f, kRoundMagic), kRoundMagic + 19.0f);
-                const int k0 = __float_as_int(kf) & 0xff;
-                const float2 e = E[k0];
+                const float2 e = E[__float_as_int(kf) & 0xff];
                 const float uu = x * sgn;
-                const bool up = uu >= e.y, down = uu < e.x;
-                const int bin = k0 + (up ? 1 : 0) - (down ? 1 : 0);
-                const float binf = (kf - kRoundMagic) + (up ? 1.0f : 0.0f) - (down ? 1.0f : 0.0f);
+                const float t = (kf + ((uu >= e.y) ? 1.0f : 0.0f)) - ((uu < e.x) ? 1.0f : 0.0f);
+                const int bin = __float_as_int(t) & 0xff;
                 // q = round((conf - bin / 20) * 2^21), again through the mantissa
-                const float qf = fmaf(binf, -0.05f * (float)(1 << kQBits), conf * (float)(1 << kQBits));
+                const float qf = fmaf(t - kRoundMagic, -0.05f * (float)(1 << kQBits), conf * (float)(1 << kQBits));
                 const int q = __float_as_int(qf + kRoundMagic) - __float_as_int(kRoundMagic);
                 const unsigned inc = is_nan ? 0u : vc[j];
                 const unsigned qq = (unsigned)(q * (int)(inc & 0xffffu));
-                bin0 += (bin == 0 && !is_nan) ? conf * nvf[j] : 0.f;
-                nanbits |= (is_nan && vc[j] != 0u) ? (1u << (k * VEC + j)) : 0u;
-                uint2* h = hk + (is_nan ? 0 : bin) * kHistRep;
+                bin0 += (t == kRoundMagic) ? conf * nvf[j] : 0.f;  // a NaN sample has conf 0 here
+                nanbits |= is_nan ? (1u << (k * VEC + j)) : 0u;
+                uint2* h = hk + bin * kHistRep;
                 if (kHistRep == 32) {
                     // one replica per lane: plain read-modify-write, lanes that do not hit add zero
                     uint2 wd = *h;
@@ -802,7 +803,7 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
             for (int k = 0; k < VU_N_UNC; ++k)
 #pragma unroll
                 for (int j = 0; j < VEC; ++j)
-                    if ((nanbits >> (k * VEC + j)) & 1u) {
+                    if (((nanbits >> (k * VEC + j)) & 1u) && vc[j] != 0u) {
                         nan_tot += (unsigned long long)(vc[j] & 0xffffu) << (k * kPackBits);
                         nan_tru += (unsigned long long)(vc[j] >> 16) << (k * kPackBits);
                     }
