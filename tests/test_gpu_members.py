@@ -100,3 +100,27 @@ def test_member_scores_contract(members):
         members.member_scores(x.cpu(), gt)                             # no CPU fallback
     empty = members.member_scores(torch.rand(3, 0, 2, 4, 4).cuda(), vu.GroundTruth(torch.zeros(0, 1, 4, 4, dtype=torch.uint8).cuda()), ged=True)
     assert empty.nll_sum.shape == (0, 1, 3) and empty.ged_counts.shape[0] == 0
+
+
+def test_fast_and_generic_kernels_agree(members):
+    """The float4 kernel (4 consecutive voxels per lane) and the generic one (any strides) on the same slab: identical integer
+    counts, likelihood sums equal up to float32 summation order."""
+    from diffuncertainty_b200 import _lib, uncertainty as vu
+    gen = torch.Generator().manual_seed(77)
+    for P, B, spatial, R, ignore, dtype in ((32, 3, (64, 96), 4, None, torch.uint8), (6, 2, (12, 20, 8), 7, 255, torch.int64)):
+        x = torch.softmax(4.0 * torch.randn(P, B, 2, *spatial, generator=gen), dim=2).cuda()
+        gt = torch.randint(0, 2, (B, R, *spatial), generator=gen)
+        if ignore is not None:
+            gt[torch.rand(gt.shape, generator=gen) < 0.15] = ignore
+        gtd = vu.GroundTruth(gt.to(dtype).cuda(), ignore)
+        labels = vu.fused_pass(x, want_maps=False).labels
+        out = []
+        for path in (0, 1):
+            _lib.set_option("k5_path", path)
+            before = _lib.get_counter("launches.member_scores_c2v4")
+            out.append(members.member_scores(x, gtd, nll=True, ged=True, mean_labels=labels))
+            assert (_lib.get_counter("launches.member_scores_c2v4") > before) == (path == 0)
+        _lib.set_option("k5_path", 0)
+        assert np.array_equal(out[0].ged_counts, out[1].ged_counts)
+        assert np.array_equal(out[0].nll_count, out[1].nll_count)
+        np.testing.assert_allclose(out[0].nll_sum, out[1].nll_sum, rtol=2e-6)
