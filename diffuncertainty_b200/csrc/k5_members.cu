@@ -351,8 +351,10 @@ __global__ void __launch_bounds__(kMsThreads) member_scores_kernel(const __grid_
 // RMAX: raters the mask registers are sized for.
 constexpr int kAheadL2 = 6;
 
+constexpr int kAccLanes = 8;  // likelihood columns per (member, rater): the 32 lane sums are folded 4 to 1 before they are stored
+
 template <bool GED, int RMAX>
-__global__ void __launch_bounds__(kMsThreads) member_scores_c2v4(const __grid_constant__ MemberParams prm) {
+__global__ void __launch_bounds__(kMsThreads, 2) member_scores_c2v4(const __grid_constant__ MemberParams prm) {
     extern __shared__ __align__(16) unsigned char ms_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = blockDim.x >> 5;
     const long long b = blockIdx.y;
@@ -361,29 +363,27 @@ __global__ void __launch_bounds__(kMsThreads) member_scores_c2v4(const __grid_co
     const int P = (int)prm.P, R = prm.gt.R;
     const bool want_nll = prm.flags & VU_MS_NLL;
     const int n_acc = want_nll ? P * R : 0;
-    float* nll_acc = reinterpret_cast<float*>(ms_smem) + (size_t)warp * n_acc * 32;  // [member * R + r][lane]
-    unsigned* s_ged = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(ms_smem) + (size_t)warps * n_acc * 32);
-    for (int t = tid; t < warps * n_acc * 32; t += blockDim.x) reinterpret_cast<float*>(ms_smem)[t] = 0.f;
-    if (GED)
-        for (int t = tid; t < prm.ged_cols; t += blockDim.x) s_ged[t] = 0u;
+    // shared memory: [warps][n_acc][kAccLanes] float likelihood columns, [warps][P][P] pair counts (GED), [ged_cols] CTA counters
+    float* nll_all = reinterpret_cast<float*>(ms_smem);
+    float* nll_acc = nll_all + (size_t)warp * n_acc * kAccLanes;
+    unsigned* pp_all = reinterpret_cast<unsigned*>(nll_all + (size_t)warps * n_acc * kAccLanes);
+    unsigned* pp = pp_all + (size_t)warp * P * P;  // [partner q][member = lane]
+    unsigned* s_ged = pp_all + (GED ? (size_t)warps * P * P : 0);
+    const int n_words = warps * n_acc * kAccLanes + (GED ? warps * P * P + prm.ged_cols : 0);
+    for (int t = tid; t < n_words; t += blockDim.x) reinterpret_cast<unsigned*>(ms_smem)[t] = 0u;
     __syncthreads();
 
-    unsigned pp[32], pg_tp[VU_MAX_RATERS], pg_pred[VU_MAX_RATERS], gg_tp[VU_MAX_RATERS], gg_sum[VU_MAX_RATERS], g_sum[VU_MAX_RATERS];
+    unsigned pg_tp[RMAX], pg_pred[RMAX], gg_tp[RMAX], gg_sum[RMAX], g_sum[RMAX];
     unsigned pos = 0, maj_tp = 0, maj_pred = 0, maj_gt = 0;
-    if (GED) {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) pp[q] = 0u;
-#pragma unroll
-        for (int r = 0; r < VU_MAX_RATERS; ++r) { pg_tp[r] = 0u; pg_pred[r] = 0u; gg_tp[r] = 0u; gg_sum[r] = 0u; g_sum[r] = 0u; }
-    }
     unsigned valid_cnt[RMAX], bad_cnt = 0;
 #pragma unroll
-    for (int r = 0; r < RMAX; ++r) valid_cnt[r] = 0u;
+    for (int r = 0; r < RMAX; ++r) { pg_tp[r] = 0u; pg_pred[r] = 0u; gg_tp[r] = 0u; gg_sum[r] = 0u; g_sum[r] = 0u; valid_cnt[r] = 0u; }
     const bool ign_is_one = prm.gt.has_ignore && prm.gt.ignore == 1;
 
     for (long long v0 = c0 + 128LL * warp; v0 < c1; v0 += 128LL * warps) {
         const long long v = v0 + 4 * lane;
         const bool in = v < c1;  // V % 4 == 0 and the chunk is a multiple of 128: a lane's four voxels are all in or all out
+        const long long vs = in ? v : v0;  // lanes past the end read the warp's first voxels (valid memory) and are masked out
         // ---- references: bit (4 r + j) of okb / oneb / rawb = valid / valid & == 1 / == 1, and the likelihood masks --------
         unsigned okb = 0, oneb = 0, rawb = 0, lab1 = 0;
         float m01[RMAX][4], m1[RMAX][4];
@@ -420,41 +420,36 @@ __global__ void __launch_bounds__(kMsThreads) member_scores_c2v4(const __grid_co
 #pragma unroll
             for (int j = 0; j < 4; ++j) lab1 |= (__ldg(lp + j) == 1) ? (1u << j) : 0u;
         }
-        // ---- members: values requested two members ahead -------------------------------------------------------------------
-        auto member_base = [&](int p) {
-            return (prm.member_ptrs ? ld_member_ptr(prm.member_ptrs, p) : prm.data + (long long)p * prm.sp) + b * prm.sb + v;
+        // ---- members: values requested two members ahead; the row pointer just advances by the member stride ---------------
+        const long long row = b * prm.sb + vs;
+        auto member_row = [&](int p) {
+            return (prm.member_ptrs ? ld_member_ptr(prm.member_ptrs, p) : prm.data + (long long)p * prm.sp) + row;
         };
-        const float4 safe0 = make_float4(1.f, 1.f, 1.f, 1.f), safe1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 a0 = safe0, a1 = safe1, b0 = safe0, b1 = safe1;  // member p (a) and p + 1 (b)
-        if (in) {
-            const float* q0 = member_base(0);
-            a0 = __ldg(reinterpret_cast<const float4*>(q0));
-            a1 = __ldg(reinterpret_cast<const float4*>(q0 + prm.sc));
-            if (P > 1) {
-                const float* q1 = member_base(1);
-                b0 = __ldg(reinterpret_cast<const float4*>(q1));
-                b1 = __ldg(reinterpret_cast<const float4*>(q1 + prm.sc));
-            }
-            for (int q = 2; q < kAheadL2 && q < P; ++q) {
-                const float* f = member_base(q);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(f));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(f + prm.sc));
-            }
+        const float* q = member_row(0);
+        float4 a0 = __ldg(reinterpret_cast<const float4*>(q)), a1 = __ldg(reinterpret_cast<const float4*>(q + prm.sc));
+        float4 b0 = a0, b1 = a1;  // member p (a) and p + 1 (b)
+        if (P > 1) {
+            q = member_row(1);
+            b0 = __ldg(reinterpret_cast<const float4*>(q));
+            b1 = __ldg(reinterpret_cast<const float4*>(q + prm.sc));
+        }
+        for (int f = 2; f < kAheadL2 && f < P; ++f) {
+            const float* pf = member_row(f);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + prm.sc));
         }
         unsigned myW[4] = {0u, 0u, 0u, 0u};
         for (int p = 0; p < P; ++p) {
             const float x0[4] = {a0.x, a0.y, a0.z, a0.w}, x1[4] = {a1.x, a1.y, a1.z, a1.w};
             a0 = b0; a1 = b1;
-            if (in) {
-                if (p + 2 < P) {
-                    const float* q2 = member_base(p + 2);
-                    b0 = __ldg(reinterpret_cast<const float4*>(q2));
-                    b1 = __ldg(reinterpret_cast<const float4*>(q2 + prm.sc));
-                }
+            if (p + 2 < P) {
+                q = member_row(p + 2);
+                b0 = __ldg(reinterpret_cast<const float4*>(q));
+                b1 = __ldg(reinterpret_cast<const float4*>(q + prm.sc));
                 if (p + kAheadL2 < P) {
-                    const float* f = member_base(p + kAheadL2);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(f));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(f + prm.sc));
+                    const float* pf = member_row(p + kAheadL2);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + prm.sc));
                 }
             }
             if (GED) {
@@ -473,13 +468,16 @@ __global__ void __launch_bounds__(kMsThreads) member_scores_c2v4(const __grid_co
                     l0[j] = log_clamped(x0[j], prm.eps);
                     d[j] = log_clamped(x1[j], prm.eps) - l0[j];
                 }
+                float* col = nll_acc + p * R * kAccLanes + (lane >> 2);
 #pragma unroll
                 for (int r = 0; r < RMAX; ++r) {
                     if (r >= R) break;
                     float acc = 0.f;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc = fmaf(m1[r][j], d[j], fmaf(m01[r][j], l0[j], acc));
-                    nll_acc[(p * R + r) * 32 + lane] += acc;
+                    acc += __shfl_xor_sync(kFull, acc, 1);
+                    acc += __shfl_xor_sync(kFull, acc, 2);
+                    if ((lane & 3) == 0) col[r * kAccLanes] += acc;
                 }
             }
         }
@@ -489,10 +487,9 @@ __global__ void __launch_bounds__(kMsThreads) member_scores_c2v4(const __grid_co
             for (int j = 0; j < 4; ++j) {
                 const unsigned w = myW[j];
                 pos += __popc(w);
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    if (q >= P) break;
-                    pp[q] += __popc(w & __shfl_sync(kFull, w, q));
+                for (int qq = 0; qq < P; ++qq) {
+                    const unsigned c = __popc(w & __shfl_sync(kFull, w, qq));
+                    if (lane < P && c) pp[qq * P + lane] += c;  // the matrix is symmetric: [partner][member] is conflict-free
                 }
                 unsigned myGb = 0u, n1 = 0u, all_valid = 1u;
 #pragma unroll
@@ -533,9 +530,13 @@ __global__ void __launch_bounds__(kMsThreads) member_scores_c2v4(const __grid_co
     // ---- fold the CTA's partials into the image's rows ---------------------------------------------------------------------
     if (want_nll) {
         __syncwarp();
-        for (int i = 0; i < n_acc; ++i) {  // i = member * R + r
-            const double sum = warp_sum((double)nll_acc[i * 32 + lane]);
-            if (lane == 0 && sum != 0.0) atomicAdd(prm.nll_sum + (b * R + i % R) * P + i / R, sum);
+        for (int i0 = 0; i0 < n_acc; i0 += 4) {  // 4 (member, rater) pairs x 8 columns per round; i = member * R + r
+            const int i = i0 + (lane >> 3);
+            double sum = i < n_acc ? (double)nll_acc[i * kAccLanes + (lane & 7)] : 0.0;
+            sum += __shfl_xor_sync(kFull, sum, 1);
+            sum += __shfl_xor_sync(kFull, sum, 2);
+            sum += __shfl_xor_sync(kFull, sum, 4);
+            if ((lane & 7) == 0 && i < n_acc && sum != 0.0) atomicAdd(prm.nll_sum + (b * R + i % R) * P + i / R, sum);
         }
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) {
@@ -547,7 +548,38 @@ __global__ void __launch_bounds__(kMsThreads) member_scores_c2v4(const __grid_co
         if (lane == 0 && nb) atomicAdd(prm.nll_bad + b, nb);
     }
     if (GED) {
-        ged_fold_warp(s_ged, lane, P, R, pp, pos, pg_tp, pg_pred, gg_tp, gg_sum, g_sum, maj_tp, maj_pred, maj_gt);
+        // this warp's per-lane counters and pair matrix -> the CTA's counters (layout: valunc.h, vu_ged_cols) -> the image's row
+        const int G = R;
+        const int o_pg_pred = P * G, o_gs = 2 * P * G, o_pp = o_gs + G, o_pos = o_pp + P * P, o_gg_tp = o_pos + P,
+                  o_gg_sum = o_gg_tp + G * G, o_maj = o_gg_sum + G * G;
+        __syncwarp();
+        for (int t = lane; t < P * P; t += 32)
+            if (pp[t]) atomicAdd(&s_ged[o_pp + t], pp[t]);
+        if (lane < P) {
+            if (pos) atomicAdd(&s_ged[o_pos + lane], pos);
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r)
+                if (r < G) {
+                    if (pg_tp[r]) atomicAdd(&s_ged[lane * G + r], pg_tp[r]);
+                    if (pg_pred[r]) atomicAdd(&s_ged[o_pg_pred + lane * G + r], pg_pred[r]);
+                }
+        }
+        if (lane < G) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r)
+                if (r < G) {
+                    if (gg_tp[r]) atomicAdd(&s_ged[o_gg_tp + lane * G + r], gg_tp[r]);
+                    if (gg_sum[r]) atomicAdd(&s_ged[o_gg_sum + lane * G + r], gg_sum[r]);
+                }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r)
+                if (r < G && g_sum[r]) atomicAdd(&s_ged[o_gs + r], g_sum[r]);
+            if (maj_tp) atomicAdd(&s_ged[o_maj], maj_tp);
+            if (maj_pred) atomicAdd(&s_ged[o_maj + 1], maj_pred);
+            if (maj_gt) atomicAdd(&s_ged[o_maj + 2], maj_gt);
+        }
         __syncthreads();
         for (int t = tid; t < prm.ged_cols; t += blockDim.x)
             if (s_ged[t]) atomicAdd(prm.ged + b * prm.ged_cols + t, (unsigned long long)s_ged[t]);
@@ -591,10 +623,11 @@ int launch_member_scores(const vu_member_scores_args* a, const GtView& gv, cudaS
         }
     }
     int warps = kMsWarps;
-    const size_t acc_per_warp = (a->flags & VU_MS_NLL) ? (size_t)s.P * gv.R * 32 * sizeof(float) : 0;
+    const size_t acc_per_warp = ((a->flags & VU_MS_NLL) ? (size_t)s.P * gv.R * kAccLanes * sizeof(float) : 0) +
+                                ((a->flags & VU_MS_GED) ? (size_t)s.P * s.P * sizeof(unsigned) : 0);
     const size_t ged_bytes = (size_t)prm.ged_cols * sizeof(unsigned);
-    while (fast && warps > 1 && acc_per_warp * warps + ged_bytes > 160 * 1024) warps >>= 1;
-    if (fast && acc_per_warp * warps + ged_bytes > 160 * 1024) fast = false;
+    while (fast && warps > 1 && acc_per_warp * warps + ged_bytes > 100 * 1024) warps >>= 1;  // two CTAs per SM
+    if (fast && acc_per_warp * warps + ged_bytes > 200 * 1024) fast = false;
     if (fast) {
         // the pass is 128 voxels per warp here; re-derive the chunk for the CTA size chosen above
         const long long cta_vox = 128LL * warps;
