@@ -156,7 +156,7 @@ def run_reference(args):
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -344,11 +344,33 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_baseline_leg(args.cpu_images)
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when
+    NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the duration of the run and the line goes to the
+    original stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -365,6 +387,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    protect_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
