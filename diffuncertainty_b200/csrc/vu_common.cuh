@@ -550,7 +550,6 @@ template <int VEC, int THREADS, typename GT, int TID0 = 0, int REP = 16, unsigne
 __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, bool active, long long b, long long v,
                                           typename FVec<VEC>::type u0, typename FVec<VEC>::type u1,
                                           typename FVec<VEC>::type u2, unsigned labels_packed) {
-    using G = typename std::conditional<sizeof(GT) == 1, int, long long>::type;
     using GAcc = typename std::conditional<sizeof(GT) == 1, int, double>::type;
     constexpr int RB = sizeof(GT) == 1 ? 4 : (VEC == 4 ? 1 : 2);  // raters fetched together
     StatsLayout<THREADS, REP> cs(sp, smem);

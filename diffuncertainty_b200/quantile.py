@@ -59,8 +59,12 @@ class RadixSelect:
     like np.sort.  The level-0 histogram (and with it ``total``) is computed once; ``select`` runs two more passes per
     group of up to 64 ranks."""
 
-    def __init__(self, values: Sequence, refs: Optional[Sequence] = None, ignore_value=None):
+    def __init__(self, values: Sequence, refs: Optional[Sequence] = None, ignore_value=None, reduce=None):
+        """``reduce``: optional callable applied in place to every device histogram before it is read (``all_reduce_sum``
+        below when the maps are sharded over ranks: every rank then selects in the union of all shards -- the ranks it asks
+        for must be the same on all of them, which they are when they derive from ``total``)."""
         _lib.require_device()
+        self._reduce = reduce
         self._lib = _lib.load()
         self._dev = torch.device("cuda", torch.cuda.current_device())
         self._vals = [_as_device_f32(v) for v in values]
@@ -78,6 +82,8 @@ class RadixSelect:
             _lib.check(self._lib.vu_radix_hist(v.data_ptr(), v.numel(), C.byref(gs) if gs is not None else None, level,
                                                pre.data_ptr() if pre is not None else None, len(prefixes), hist.data_ptr(), stream),
                        "vu_radix_hist")
+        if self._reduce is not None:
+            self._reduce(hist)
         return hist.cpu().numpy()
 
     @staticmethod
@@ -110,9 +116,17 @@ class RadixSelect:
         return _key_to_float(out_keys)
 
 
-def order_statistics(values: Sequence, ranks: Sequence[int], refs: Optional[Sequence] = None, ignore_value=None):
+def all_reduce_sum(hist: torch.Tensor) -> None:
+    """``reduce`` hook for maps sharded over the ranks of the default process group (one int64 all-reduce per histogram
+    pass: 16 KB per prefix, latency-bound).  Counts are integers, so the selection is exact and identical on every rank."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+
+
+def order_statistics(values: Sequence, ranks: Sequence[int], refs: Optional[Sequence] = None, ignore_value=None, reduce=None):
     """(float32 array of the elements of rank ``ranks``, total number of samples); see RadixSelect."""
-    sel = RadixSelect(values, refs, ignore_value)
+    sel = RadixSelect(values, refs, ignore_value, reduce)
     return sel.select(ranks), sel.total
 
 
@@ -131,15 +145,17 @@ def lerp(a: np.ndarray, b: np.ndarray, t: np.ndarray) -> np.ndarray:
     return np.where(t >= 0.5, b - diff * (1 - t), a + diff * t)
 
 
-def quantile(values: Sequence, q, refs: Optional[Sequence] = None, ignore_value=None, dtype=np.float32):
+def quantile(values: Sequence, q, refs: Optional[Sequence] = None, ignore_value=None, dtype=np.float32, reduce=None):
     """np.quantile(np.concatenate(values), q) (method "linear") as NumPy 2.x evaluates it for data of ``dtype``: a Python
     scalar ``q`` is cast to ``dtype`` first (so the virtual index of a float32 map is a float32, find_threshold.py:76), an
-    array ``q`` keeps its own dtype (float64 for the ``np.linspace`` of ace.py:387).  NaN in the data gives NaN."""
+    array ``q`` keeps its own dtype (float64 for the ``np.linspace`` of ace.py:387).  NaN in the data gives NaN.
+    ``reduce=all_reduce_sum``: the maps of this rank are one shard of the data set (find_threshold.py:98-105 over a sharded
+    validation split); every rank gets the quantile of the union."""
     scalar = np.ndim(q) == 0
     qs = np.atleast_1d(np.asarray(q, dtype=dtype) if isinstance(q, (int, float)) else np.asarray(q))
     if qs.size and (np.nanmin(qs) < 0 or np.nanmax(qs) > 1 or np.isnan(qs).any()):
         raise ValueError("Quantiles must be in the range [0, 1]")
-    sel = RadixSelect(values, refs, ignore_value)
+    sel = RadixSelect(values, refs, ignore_value, reduce)
     total = sel.total
     if total == 0:
         res = np.full(qs.shape, np.nan)
@@ -163,10 +179,10 @@ def calculate_foreground_quantile_image(image) -> float:
     return 1 - (_compute_area(arr != 0) / size)
 
 
-def calculate_threshold_image(quantile_path, image, method: str) -> float:
+def calculate_threshold_image(quantile_path, image, method: str, reduce=None) -> float:
     """find_threshold.py:69-77: np.quantile of the (concatenated) uncertainty values at the method's mean foreground
     quantile.  ``image`` may be one array / tensor or a list of them (they are not concatenated)."""
     with open(Path(quantile_path)) as f:
         method_quantile = json.load(f)[method]
     maps = image if isinstance(image, (list, tuple)) else [image]
-    return float(quantile(maps, method_quantile))
+    return float(quantile(maps, method_quantile, reduce=reduce))

@@ -92,3 +92,17 @@ def test_c_platt_inversion_agrees_with_python(a, b):
     for thr in (ce[fin], py.edge_u[fin]):
         conf = calibration._platt_f32(thr.astype(np.float32), a, b).astype(np.float64)
         assert np.all(np.abs(conf - edges) <= 4e-7 * np.maximum(edges, 0.05) + (1e-5 if abs(a) > 100 else 0.0))
+
+
+def test_header_is_plain_c():
+    """include/valunc.h is the drop-in boundary: it must compile as C (no C++ / CUDA / torch types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = '#include "valunc.h"\nint main(void) { vu_fused_args a; vu_member_scores_args m; (void)a; (void)m; return vu_abi_version() == VU_ABI_VERSION ? 0 : 1; }\n'
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(root, "include"), "-x", "c", "-"],
+                       input=src, text=True, capture_output=True)
+    assert r.returncode == 0, r.stderr

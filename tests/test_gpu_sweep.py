@@ -79,6 +79,11 @@ def test_sharding_invariance_on_one_device(single, world):
     np.testing.assert_allclose(got.bin_sums, single.bin_sums, rtol=1e-12)
 
 
+def _quantile_maps():
+    rng = np.random.default_rng(41)
+    return [(rng.random(shape) ** 3 * 0.69).astype(np.float32) for shape in ((40, 64), (40, 64), (17, 23), (40, 64), (8, 8, 8))]
+
+
 def _nccl_worker(rank, world, port, outdir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
@@ -87,7 +92,12 @@ def _nccl_worker(rank, world, port, outdir):
     try:
         from diffuncertainty_b200 import sweep
         res = sweep.ShardedSweep(sweep.SweepConfig(**CFG), rank=rank, world=world).run()
-        np.savez(os.path.join(outdir, f"rank{rank}.npz"), bt=res.bin_total, bc=res.bin_true, bs=res.bin_sums, ri=res.rows_i64, rf=res.rows_f64)
+        # dataset-level quantile over maps sharded by rank (find_threshold.py:98-105): one int64 all-reduce per histogram pass
+        from diffuncertainty_b200 import quantile
+        maps = _quantile_maps()
+        mine = [torch.from_numpy(m).cuda() for i, m in enumerate(maps) if i % world == rank]
+        q = np.array([float(quantile.quantile(mine, qq, reduce=quantile.all_reduce_sum)) for qq in (0.0, 0.37, 0.9, 1.0)])
+        np.savez(os.path.join(outdir, f"rank{rank}.npz"), bt=res.bin_total, bc=res.bin_true, bs=res.bin_sums, ri=res.rows_i64, rf=res.rows_f64, q=q)
     finally:
         dist.destroy_process_group()
 
@@ -108,3 +118,5 @@ def test_nccl_exchange_on_all_visible_gpus(single):
             assert np.array_equal(z["ri"], single.rows_i64)
             np.testing.assert_allclose(z["rf"], single.rows_f64, rtol=1e-12, atol=1e-15)
             np.testing.assert_allclose(z["bs"], single.bin_sums, rtol=1e-12)
+            allv = np.concatenate([m.ravel() for m in _quantile_maps()])
+            assert np.array_equal(z["q"], np.array([float(np.quantile(allv, qq)) for qq in (0.0, 0.37, 0.9, 1.0)]))
