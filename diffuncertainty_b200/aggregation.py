@@ -12,7 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 from pathlib import Path
-from typing import Optional, Sequence
+from typing import Sequence
 
 import numpy as np
 import torch

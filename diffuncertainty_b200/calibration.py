@@ -12,7 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 from dataclasses import dataclass
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 import torch

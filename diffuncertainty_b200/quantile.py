@@ -14,7 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 from pathlib import Path
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch

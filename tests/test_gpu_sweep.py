@@ -27,7 +27,7 @@ def single():
 
 
 def test_sweep_matches_oracle(single):
-    from diffuncertainty_b200 import calibration, synth
+    from diffuncertainty_b200 import synth
     from oracle import oracle
     cfg = _cfg()
     x = synth.synth_slab(cfg.P, cfg.n_images, cfg.C, cfg.spatial, seed=cfg.seed, first_image=0, scale=cfg.scale)
