@@ -625,3 +625,49 @@ def test_member_list_is_read_without_stacking(vu):
                 torch.testing.assert_close(got.stats_f64, want.stats_f64, rtol=1e-9, atol=1e-12)
     finally:
         _lib.set_option("k1_path", 0)
+
+
+def test_entry_points_can_be_captured_in_a_cuda_graph(vu):
+    """The C ABI only enqueues work on the stream it is given (no hidden synchronisation, allocation or host read-back), so a
+    launch-bound inner loop -- many small batches through vu_fused_pass + vu_patch_max_ws -- can be captured once and replayed."""
+    from diffuncertainty_b200 import _lib, aggregation, calibration, synth
+    P, B, C, spatial, R = 10, 4, 2, (64, 64), 3
+    x = synth.synth_slab(P, B, C, spatial, seed=5, scale=3.0)
+    gt = vu.GroundTruth(synth.synth_gt(x, R, seed=5, flip=0.2), None)
+    flags = _lib.STAT_IMAGE_SUM | _lib.STAT_THRESHOLD | _lib.STAT_AREA | _lib.STAT_DICE | _lib.STAT_CALIB | _lib.STAT_NCC
+    calib = [calibration.platt_edges(a, b) for a, b in ((3.5, -1.25), (6.0, -2.0), (40.0, -0.5))]
+    maps = {k: torch.empty((B,) + spatial, dtype=torch.float32, device="cuda") for k in ("TU", "AU", "EU")}
+    labels = torch.empty((B,) + spatial, dtype=torch.uint8, device="cuda")
+    sf = torch.zeros((B, 80), dtype=torch.float64, device="cuda")
+    si = torch.zeros((B, 156), dtype=torch.int64, device="cuda")
+    lib = _lib.load()
+    out_max = torch.empty(B, dtype=torch.float64, device="cuda")
+    out_first = torch.empty(B, dtype=torch.int64, device="cuda")
+    ws_bytes = int(lib.vu_patch_workspace_bytes(B, 1, *spatial, 1, 10, 10))
+    ws = torch.empty(max(ws_bytes // 8, 1), dtype=torch.int64, device="cuda")
+
+    def work():
+        sf.zero_(); si.zero_()
+        vu.fused_pass(x, gt, stats=flags, thresholds=[0.3, 0.2, 0.02], calib=calib, stats_out=(sf, si), maps_out=maps, labels_out=labels)
+        _lib.check(lib.vu_patch_max_ws(maps["TU"].data_ptr(), B, 1, *spatial, 1, 10, 10, 0, out_max.data_ptr(), out_first.data_ptr(),
+                                       ws.data_ptr(), ws_bytes, _lib.current_stream_ptr()), "vu_patch_max_ws")
+
+    work()  # eager: also warms up the per-kernel attribute calls
+    torch.cuda.synchronize()
+    want = [t.clone() for t in (maps["TU"], maps["EU"], labels, sf, si, out_max, out_first)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            work()
+    for t in (maps["TU"], maps["EU"], labels, sf, si, out_max, out_first):
+        t.zero_()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    for got, ref in zip((maps["TU"], maps["EU"], labels, sf, si, out_max, out_first), want):
+        if got.dtype == torch.float64:  # sums folded with atomics: the order of the partials differs from run to run
+            torch.testing.assert_close(got, ref, rtol=1e-12, atol=1e-300)
+        else:
+            assert torch.equal(got, ref)
