@@ -193,6 +193,11 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback. Use --impl reference for the CPU arm.")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = None
+    if world > 1:
+        # every rank feeds its own GPU from host memory in the end-to-end leg: keep the pinned buffers on the GPU's NUMA node
+        from diffuncertainty_b200.host_pipeline import bind_host_thread_to_device_node
+        numa_node = bind_host_thread_to_device_node(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -304,7 +309,8 @@ def run_ours(args):
             dt = float(t[0])
         e2e = {"value": P * V * Be * world * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": r0.h2d_bytes,
                "d2h_bytes_per_step": r0.d2h_bytes, "images_per_step": Be, "steps": args.e2e_steps,
-               "api": "diffuncertainty_b200.host_pipeline.HostPipeline.run (pinned host slab -> host maps, labels, statistics rows)"}
+               "api": "diffuncertainty_b200.host_pipeline.HostPipeline.run (pinned host slab -> host maps, labels, statistics rows)",
+               "numa_node_of_rank0": numa_node}
         del pipe, xh, gh
 
     if rank != 0:

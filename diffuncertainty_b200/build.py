@@ -38,16 +38,39 @@ def _digest() -> str:
             h.update(n.encode())
             with open(p, "rb") as f:
                 h.update(f.read())
-    h.update(" ".join(FLAGS).encode())
+    # the flags without the checkout's absolute paths: the library built in one place (the build container) must be
+    # recognised as current where the tree is copied to (the GPU box) instead of being rebuilt by every process there
+    h.update(" ".join(f.replace(ROOT, "<root>") for f in FLAGS).encode())
     return h.hexdigest()
 
 
+def _current(stamp: str, digest: str) -> bool:
+    try:
+        return os.path.isfile(LIB) and open(stamp).read().strip() == digest
+    except OSError:
+        return False
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile and link libvalunc.so if it is missing or older than its sources.  Safe to call from many processes at once
+    (the ranks of a torchrun job): one of them builds under a file lock, into a temporary file that is renamed into place."""
+    import fcntl
     os.makedirs(OBJDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "build.stamp")
     digest = _digest()
-    if not force and os.path.isfile(LIB) and os.path.isfile(stamp) and open(stamp).read().strip() == digest:
+    if not force and _current(stamp, digest):
         return LIB
+    with open(os.path.join(LIBDIR, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _current(stamp, digest):  # another process built it while this one waited
+                return LIB
+            return _build_locked(stamp, digest, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(stamp: str, digest: str, verbose: bool) -> str:
     extra = ["-Xptxas", "-v"] if verbose else []
 
     def compile_one(src: str) -> str:
@@ -66,13 +89,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     # torch (one notion of the current device and of the streams torch hands over); a private static runtime
     # launches on device 0 whatever torch.cuda.current_device() is.  libcudart.so.12 is already in the process
     # when torch is imported; the rpath covers stand-alone C users.
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared",
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [NVCC, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared",
            "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr}")
-    with open(stamp, "w") as f:
+    os.replace(tmp, LIB)  # atomic: a process that loads the library concurrently sees the old or the new file, never half of one
+    with open(stamp + ".tmp", "w") as f:
         f.write(digest)
+    os.replace(stamp + ".tmp", stamp)
     return LIB
 
 

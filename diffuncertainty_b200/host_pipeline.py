@@ -22,6 +22,38 @@ from ._lib import F64, I64
 from .uncertainty import UNC_KEYS, GroundTruth, fused_pass
 
 
+def bind_host_thread_to_device_node(device) -> Optional[int]:
+    """Restrict the calling process to the CPU cores of the NUMA node the GPU hangs off, so that pinned buffers allocated
+    afterwards (first touch) lie in that node's memory and the host->device copies of the ranks of a multi-GPU box do not
+    cross the socket interconnect.  Returns the node, or None when the topology cannot be read (then nothing changes)."""
+    import os
+    try:
+        import ctypes
+        index = torch.device(device).index
+        index = torch.cuda.current_device() if index is None else index
+        buf = ctypes.create_string_buffer(32)
+        cudart = ctypes.CDLL("libcudart.so.12")  # already loaded by torch: resolves to the same library
+        if cudart.cudaDeviceGetPCIBusId(buf, 32, int(index)) != 0:
+            return None
+        bus = buf.value.decode().lower()  # "0000:1b:00.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 @dataclass
 class HostResult:
     maps: Dict[str, torch.Tensor]      # pinned host fp32 (B, *S)

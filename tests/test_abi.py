@@ -106,3 +106,22 @@ def test_header_is_plain_c():
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(root, "include"), "-x", "c", "-"],
                        input=src, text=True, capture_output=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_built_library_is_current_wherever_the_tree_is_copied():
+    """The library is built in one place and travels with the tree (gpurun snapshot, torchrun ranks): the staleness check must not
+    depend on the checkout's absolute path, or every process on the other side would rebuild -- and race -- on first use."""
+    import shutil
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    _lib.load()  # makes sure the in-tree library and its stamp exist
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copytree(os.path.join(root, "diffuncertainty_b200"), os.path.join(d, "diffuncertainty_b200"),
+                        ignore=shutil.ignore_patterns("__pycache__", "obj"))
+        shutil.copytree(os.path.join(root, "include"), os.path.join(d, "include"))
+        code = ("import sys; sys.path.insert(0, %r); from diffuncertainty_b200 import build as b; import os; "
+                "print(int(b._current(os.path.join(b.LIBDIR, 'build.stamp'), b._digest())))" % d)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and r.stdout.strip() == "1", r.stderr[-1000:]
