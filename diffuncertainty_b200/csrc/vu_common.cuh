@@ -265,7 +265,7 @@ struct StatParams {
 //   9      sum g        10  sum g*g     4+r    rater r: tp | pred << 21 | gt << 42
 //   11..13 sum u_k^2    14..16  sum g*u_k
 // histogram word (bins 0..19): x = samples | correct << 16,  y = sum of q * n_valid,
-//   q = round((conf - bin * 0.05) * 2^21)   (bin 0 is also summed in floating point, slots 6..8)
+//   q = round(conf * 2^21) - bin * kQBinStep   (bin 0 is also summed in floating point, slots 6..8)
 enum { FS_SUM = 0, FS_THR = 3, FS_BIN0 = 6, FS_G = 9, FS_GG = 10, FS_UU = 11, FS_GU = 14, FS_MAX = 17 };
 enum { IS_THRCNT = 0, IS_AREA = 1, IS_NANTOT = 2, IS_NANTRU = 3, IS_DICE = 4, IS_MAX = 4 + VU_MAX_RATERS };
 constexpr int kPackBits = 21;
@@ -273,6 +273,7 @@ constexpr unsigned long long kPackMask = (1ull << kPackBits) - 1;
 constexpr int kMaxVoxPerFlush = 1024;   // voxels per thread between flushes: x 2 lanes per replica x n_valid <= 8 keeps the
                                         // 16-bit counts (<= 16384) and the 32-bit q sums (< 2^31) from overflowing
 constexpr int kQBits = 21;
+constexpr int kQBinStep = 104858;        // round(0.05 * 2^21): what one bin is worth in q units (Sum conf = count * bin * step / 2^21 + Sum q / 2^21)
 constexpr int kHistBins = VU_N_BINS - 1;  // 20 real bins; slot 20 (NaN) is counted in the integer slots
 // histogram replicas per warp: 16 (two half-warp phases; the register-streaming kernels, 8 warps per CTA) or 32 (one
 // replica per lane, no phases; the three statistics warps of the TMA kernel)
@@ -453,7 +454,7 @@ __device__ __noinline__ void stats_flush(const StatParams& sp, void* smem, long 
                 if (tru) atomicAdd(irow + VU_I64_BIN_TRUE + col, (unsigned long long)tru);
                 if (bin > 0)  // bin 0 is summed in floating point by the threads (slots FS_BIN0)
                     atomicAdd(frow + VU_F64_BIN_SUMS + col,
-                              (double)tot * ((double)bin * (double)0.05f) + (double)q * (1.0 / (double)(1 << kQBits)));  // q is relative to bin * 0.05f
+                              ((double)tot * (double)(bin * kQBinStep) + (double)q) * (1.0 / (double)(1 << kQBits)));  // q is relative to bin * kQBinStep
             }
         }
     }
@@ -753,48 +754,88 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
             nvf[j] = (float)nv;
         }
         unsigned nanbits = 0;  // bit (k * VEC + j): a sample with NaN uncertainty (rare: handled after the loops)
+        const bool any_identity = sp.calib[0].identity | sp.calib[1].identity | sp.calib[2].identity;
+        if (kHistRep == 16 && mask == 7u && !any_identity) {
+            // Two half-warps share a histogram replica.  Instead of taking turns on every update, the lower half works on
+            // uncertainty type ks while the upper half works on (ks + 1) % 3: in the same step the halves never address the
+            // same histogram region, so ONE read-modify-write serves all 32 lanes and the warp only synchronises when the
+            // halves move on to the next pair of regions (3 times per tile instead of 24).
 #pragma unroll
-        for (int k = 0; k < VU_N_UNC; ++k) {
-            if (!((mask >> k) & 1)) continue;
-            float bin0 = 0.f;
-            const CalibDev& cal = sp.calib[k];
-            const float a2 = cal.a2, b2 = cal.b2, sgn = cal.sgn;
-            const float2* E = cs.E + k * kEdgePad;
-            uint2* hk = hw + k * (kHistBins * kHistRep);
+            for (int ks = 0; ks < VU_N_UNC; ++ks) {
+                const int ku = (ks + 1) % VU_N_UNC;
+                const int kk = upper ? ku : ks;
+                const float a2 = upper ? sp.calib[ku].a2 : sp.calib[ks].a2, b2 = upper ? sp.calib[ku].b2 : sp.calib[ks].b2;
+                const float sgn = upper ? sp.calib[ku].sgn : sp.calib[ks].sgn;
+                const float2* E = cs.E + kk * kEdgePad;
+                uint2* hk = hw + kk * (kHistBins * kHistRep);
+                float bin0 = 0.f;
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const float x = u[k][j];
-                const bool is_nan = x != x;
-                const float conf = is_nan ? 0.0f : platt_conf(x, a2, b2, cal.identity);  // finite from here on
-                // candidate bin round(conf * 20), read off the mantissa (no conversion); the true bin is within one of it and
-                // the two neighbouring thresholds on u settle it exactly (see vu_calib in valunc.h; NaN edges and NaN u
-                // compare false).  t = magic + bin stays in the mantissa domain: bin = low bits, float(bin) = t - magic.
-                const float kf = fminf(fmaf(conf, 20.0f, kRoundMagic), kRoundMagic + 19.0f);
-                const float2 e = E[__float_as_int(kf) & 0xff];
-                const float uu = x * sgn;
-                const float t = (kf + ((uu >= e.y) ? 1.0f : 0.0f)) - ((uu < e.x) ? 1.0f : 0.0f);
-                const int bin = __float_as_int(t) & 0xff;
-                // q = round((conf - bin / 20) * 2^21), again through the mantissa
-                const float qf = fmaf(t - kRoundMagic, -0.05f * (float)(1 << kQBits), conf * (float)(1 << kQBits));
-                const int q = __float_as_int(qf + kRoundMagic) - __float_as_int(kRoundMagic);
-                const unsigned inc = is_nan ? 0u : vc[j];
-                const unsigned qq = (unsigned)(q * (int)(inc & 0xffffu));
-                bin0 += (t == kRoundMagic) ? conf * nvf[j] : 0.f;  // a NaN sample has conf 0 here
-                nanbits |= is_nan ? (1u << (k * VEC + j)) : 0u;
-                uint2* h = hk + bin * kHistRep;
-                if (kHistRep == 32) {
-                    // one replica per lane: plain read-modify-write, lanes that do not hit add zero
+                for (int j = 0; j < VEC; ++j) {
+                    const float x = upper ? u[ku][j] : u[ks][j];
+                    const bool is_nan = x != x;
+                    const float conf = is_nan ? 0.0f : platt_conf(x, a2, b2, 0);
+                    const float kf = fminf(fmaf(conf, 20.0f, kRoundMagic), kRoundMagic + 19.0f);
+                    const float2 e = E[__float_as_int(kf) & 0xff];
+                    const float uu = x * sgn;
+                    const float t = (kf + ((uu >= e.y) ? 1.0f : 0.0f)) - ((uu < e.x) ? 1.0f : 0.0f);
+                    const int bin = __float_as_int(t) & 0xff;
+                    // q = round(conf * 2^21) - bin * kQBinStep: the rounding happens in the mantissa of conf * 2^21 + magic
+                    const int q = (__float_as_int(fmaf(conf, (float)(1 << kQBits), kRoundMagic)) - __float_as_int(kRoundMagic)) - bin * kQBinStep;
+                    const unsigned inc = is_nan ? 0u : vc[j];
+                    if (t == kRoundMagic) bin0 = fmaf(conf, nvf[j], bin0);
+                    nanbits |= is_nan ? (1u << (kk * VEC + j)) : 0u;
+                    uint2* h = hk + bin * kHistRep;
                     uint2 wd = *h;
-                    wd.x += inc; wd.y += qq;
+                    wd.x += inc;
+                    wd.y += (unsigned)(q * (int)(inc & 0xffffu));
                     *h = wd;
-                } else {
-                    if (!upper) { uint2 wd = *h; wd.x += inc; wd.y += qq; *h = wd; }
-                    __syncwarp();
-                    if (upper) { uint2 wd = *h; wd.x += inc; wd.y += qq; *h = wd; }
-                    __syncwarp();
                 }
+                if (bin0 != 0.f) cs.fs[(FS_BIN0 + kk) * THREADS + tid] += (double)bin0;
+                __syncwarp();
             }
-            if (bin0 != 0.f) cs.fs[(FS_BIN0 + k) * THREADS + tid] += (double)bin0;
+        } else {
+#pragma unroll
+            for (int k = 0; k < VU_N_UNC; ++k) {
+                if (!((mask >> k) & 1)) continue;
+                float bin0 = 0.f;
+                const CalibDev& cal = sp.calib[k];
+                const float a2 = cal.a2, b2 = cal.b2, sgn = cal.sgn;
+                const float2* E = cs.E + k * kEdgePad;
+                uint2* hk = hw + k * (kHistBins * kHistRep);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const float x = u[k][j];
+                    const bool is_nan = x != x;
+                    const float conf = is_nan ? 0.0f : platt_conf(x, a2, b2, cal.identity);  // finite from here on
+                    // candidate bin round(conf * 20), read off the mantissa (no conversion); the true bin is within one of it and
+                    // the two neighbouring thresholds on u settle it exactly (see vu_calib in valunc.h; NaN edges and NaN u
+                    // compare false).  t = magic + bin stays in the mantissa domain: bin = low bits, float(bin) = t - magic.
+                    const float kf = fminf(fmaf(conf, 20.0f, kRoundMagic), kRoundMagic + 19.0f);
+                    const float2 e = E[__float_as_int(kf) & 0xff];
+                    const float uu = x * sgn;
+                    const float t = (kf + ((uu >= e.y) ? 1.0f : 0.0f)) - ((uu < e.x) ? 1.0f : 0.0f);
+                    const int bin = __float_as_int(t) & 0xff;
+                    // q = round(conf * 2^21) - bin * kQBinStep: the rounding happens in the mantissa of conf * 2^21 + magic
+                    const int q = (__float_as_int(fmaf(conf, (float)(1 << kQBits), kRoundMagic)) - __float_as_int(kRoundMagic)) - bin * kQBinStep;
+                    const unsigned inc = is_nan ? 0u : vc[j];
+                    const unsigned qq = (unsigned)(q * (int)(inc & 0xffffu));
+                    if (t == kRoundMagic) bin0 = fmaf(conf, nvf[j], bin0);  // a NaN sample has conf 0 here
+                    nanbits |= is_nan ? (1u << (k * VEC + j)) : 0u;
+                    uint2* h = hk + bin * kHistRep;
+                    if (kHistRep == 32) {
+                        // one replica per lane: plain read-modify-write, lanes that do not hit add zero
+                        uint2 wd = *h;
+                        wd.x += inc; wd.y += qq;
+                        *h = wd;
+                    } else {
+                        if (!upper) { uint2 wd = *h; wd.x += inc; wd.y += qq; *h = wd; }
+                        __syncwarp();
+                        if (upper) { uint2 wd = *h; wd.x += inc; wd.y += qq; *h = wd; }
+                        __syncwarp();
+                    }
+                }
+                if (bin0 != 0.f) cs.fs[(FS_BIN0 + k) * THREADS + tid] += (double)bin0;
+            }
         }
         if (nanbits) {  // np.digitize puts NaN past the last edge: slot 20, counted in the integer slots
             unsigned long long nan_tot = 0, nan_tru = 0;
