@@ -70,6 +70,8 @@ static int make_gt_view(GtView& v, const vu_gt* gt, long long V) {
     v.sb = gt->stride_b; v.sr = gt->stride_r; v.sv = gt->stride_v;
     v.has_ignore = gt->has_ignore; v.ignore = gt->ignore_index;
     v.align = gt_alignment(*gt, V);
+    v.ign_byte = gt->has_ignore && gt->ignore_index >= 0 && gt->ignore_index <= 255;
+    v.ign4 = ((unsigned)gt->ignore_index & 0xffu) * 0x01010101u;
     return VU_OK;
 }
 
@@ -107,6 +109,8 @@ static int fill_stat_params(StatParams& st, uint32_t flags, unsigned unc_mask, l
         st.gt.sb = gt.stride_b; st.gt.sr = gt.stride_r; st.gt.sv = gt.stride_v;
         st.gt.has_ignore = gt.has_ignore; st.gt.ignore = gt.ignore_index;
         st.gt.align = gt_alignment(gt, V);
+        st.gt.ign_byte = gt.has_ignore && gt.ignore_index >= 0 && gt.ignore_index <= 255;
+        st.gt.ign4 = ((unsigned)gt.ignore_index & 0xffu) * 0x01010101u;
     }
     for (int k = 0; k < VU_N_UNC; ++k) {
         st.thr[k] = thr[k];

@@ -163,6 +163,8 @@ struct GtView {
     int has_ignore;
     long long ignore;
     int align;  // largest power of two <= 4 such that VEC = align voxels can be fetched with one vector load
+    int ign_byte;      // the ignore value can occur in a uint8 reference (has_ignore && 0 <= ignore <= 255)
+    unsigned ign4;     // ... and its byte replicated four times
 };
 
 template <typename T>
@@ -297,7 +299,8 @@ __host__ __device__ inline size_t stats_smem_bytes(unsigned flags, int R, int th
     if (!flags) return 0;
     size_t n = (size_t)(stats_num_fslots(flags) + stats_num_islots(flags, R)) * threads * 8;
     if (flags & VU_STAT_CALIB)
-        n += (size_t)(threads / 32) * (VU_N_UNC * kHistBins * rep) * sizeof(uint2) + (size_t)VU_N_UNC * kEdgePad * sizeof(float2);
+        n += (size_t)(threads / 32) * (VU_N_UNC * kHistBins * rep) * sizeof(uint2) + (size_t)VU_N_UNC * kEdgePad * sizeof(float2) +
+             (size_t)(VU_N_UNC + 1) * sizeof(float4);
     if (flags & VU_STAT_PLATT_FIT) n += (size_t)kPlattWords * sizeof(int) + (size_t)kPlattTab * 2 * sizeof(float);
     return n;
 }
@@ -309,6 +312,7 @@ struct StatsLayout {
     unsigned long long* is;
     uint2* hist;  // [warp][unc][bin][replica]
     float2* E;    // [unc][kEdgePad]
+    float4* CC;   // [unc]: (a2, b2, sgn, -) of the Platt expression, so that a lane can fetch its type's constants with one load
     int* phist;   // Platt-fit data [unc][bin][4]
     float* pT;    // [kPlattTab] edges, then [kPlattTab] reciprocals
     int nF, nI;
@@ -319,7 +323,8 @@ struct StatsLayout {
         is = reinterpret_cast<unsigned long long*>(fs + (size_t)nF * THREADS);
         hist = reinterpret_cast<uint2*>(is + (size_t)nI * THREADS);
         E = reinterpret_cast<float2*>(hist + ((sp.flags & VU_STAT_CALIB) ? (THREADS / 32) * kHistWordsPerWarp : 0));
-        phist = reinterpret_cast<int*>(E + ((sp.flags & VU_STAT_CALIB) ? VU_N_UNC * kEdgePad : 0));
+        CC = reinterpret_cast<float4*>(E + ((sp.flags & VU_STAT_CALIB) ? VU_N_UNC * kEdgePad : 0));
+        phist = reinterpret_cast<int*>(CC + ((sp.flags & VU_STAT_CALIB) ? VU_N_UNC + 1 : 0));
         pT = reinterpret_cast<float*>(phist + kPlattWords);
     }
 };
@@ -345,6 +350,8 @@ __device__ __noinline__ void stats_init(const StatParams& sp, void* smem) {
             L.E[t] = make_float2((e >= 1 && e <= VU_N_EDGES) ? sp.calib[k].edge[e - 1] : nan,
                                  (e >= 0 && e < VU_N_EDGES) ? sp.calib[k].edge[e] : nan);
         }
+        for (int t = ((int)threadIdx.x - TID0); t < VU_N_UNC; t += THREADS)
+            L.CC[t] = make_float4(sp.calib[t].a2, sp.calib[t].b2, sp.calib[t].sgn, 0.f);
     }
     if (sp.flags & VU_STAT_PLATT_FIT) {
         for (int t = ((int)threadIdx.x - TID0); t < kPlattWords; t += THREADS) L.phist[t] = 0;
@@ -511,6 +518,16 @@ template <int VEC>
 __device__ __forceinline__ void stats_prefetch_gt(const StatParams& sp, long long b, long long v) {
     if (!(sp.flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC | VU_STAT_PLATT_FIT)) || !sp.gt.data) return;
     const long long esz = sp.gt.dtype == VU_GT_U8 ? 1 : 8;
+    if (sp.gt.sv == 1) {
+        // the 32 x VEC voxels of a warp are one run of 128-byte lines per rater: the lanes share them out (one instruction for
+        // all raters instead of R per thread -- these launches are issue-bound)
+        const int lane = threadIdx.x & 31;
+        const int lpr = (int)((32 * VEC * esz + 127) / 128);  // lines per rater
+        const char* base = reinterpret_cast<const char*>(sp.gt.data) + (b * sp.gt.sb + (v - (long long)lane * VEC)) * esz;
+        for (int i = lane; i < sp.gt.R * lpr; i += 32)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (long long)(i / lpr) * sp.gt.sr * esz + (long long)(i % lpr) * 128));
+        return;
+    }
     const char* base = reinterpret_cast<const char*>(sp.gt.data) + (b * sp.gt.sb + v * sp.gt.sv) * esz;
     for (int r = 0; r < sp.gt.R; ++r) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (long long)r * sp.gt.sr * esz));
 }
@@ -620,8 +637,8 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
         }
         const unsigned pp_hi = bytes_equal(lab4, kB01) & kBytes;  // predicted foreground (test_2D.py:878)
         const bool has_ign = sp.gt.has_ignore != 0;
-        const bool ign_byte = has_ign && sp.gt.ignore >= 0 && sp.gt.ignore <= 255;  // else no uint8 reference can match it
-        const unsigned ign4 = ((unsigned)sp.gt.ignore & 0xffu) * kB01;
+        const bool ign_byte = sp.gt.ign_byte != 0;  // else no uint8 reference can match the ignore value
+        const unsigned ign4 = sp.gt.ign4;
         const long long ign = sp.gt.ignore;
 #pragma unroll 1
         for (int r0 = 0; r0 < R; r0 += RB) {
@@ -764,8 +781,8 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
             for (int ks = 0; ks < VU_N_UNC; ++ks) {
                 const int ku = (ks + 1) % VU_N_UNC;
                 const int kk = upper ? ku : ks;
-                const float a2 = upper ? sp.calib[ku].a2 : sp.calib[ks].a2, b2 = upper ? sp.calib[ku].b2 : sp.calib[ks].b2;
-                const float sgn = upper ? sp.calib[ku].sgn : sp.calib[ks].sgn;
+                const float4 cc = cs.CC[kk];
+                const float a2 = cc.x, b2 = cc.y, sgn = cc.z;
                 const float2* E = cs.E + kk * kEdgePad;
                 uint2* hk = hw + kk * (kHistBins * kHistRep);
                 float bin0 = 0.f;
