@@ -671,3 +671,26 @@ def test_entry_points_can_be_captured_in_a_cuda_graph(vu):
             torch.testing.assert_close(got, ref, rtol=1e-12, atol=1e-300)
         else:
             assert torch.equal(got, ref)
+
+
+def test_border_and_area_random_shapes(vu):
+    """_compute_area / _compute_border (prediction_shape_stats.py:10-30) on random label maps: the word-wise kernel (rows of a
+    multiple of 4 labels) and the scalar one, 1- to 3-D, several classes, batched through vu_border_count."""
+    from diffuncertainty_b200 import _lib, aggregation as agg
+    from oracle import oracle
+    rng = np.random.default_rng(9)
+    for shape in ((64, 64), (33, 40), (40, 33), (7, 9, 12), (5, 16, 20), (1, 8), (17,), (4, 4, 4), (3, 64, 128)):
+        for n_cls in (2, 5):
+            lab = rng.integers(0, n_cls, shape).astype(np.uint8)
+            blob = tuple(slice(s // 4, s // 4 + max(1, s // 2)) for s in shape)
+            lab[blob] = 1  # a compact region, so that not every neighbour pair differs
+            area, border = agg.prediction_shape_stats(lab)
+            assert area == oracle.compute_area(lab) and border == oracle.compute_border(lab), (shape, n_cls)
+    lib = _lib.load()
+    B, dims = 5, (6, 20, 24)
+    labs = rng.integers(0, 3, (B,) + dims).astype(np.uint8)
+    si = torch.zeros((B, _lib.I64["COLS"]), dtype=torch.int64, device="cuda")
+    t = torch.from_numpy(labs).cuda()
+    _lib.check(lib.vu_border_count(t.data_ptr(), B, *dims, si.data_ptr(), _lib.current_stream_ptr()), "vu_border_count")
+    got = si[:, _lib.I64["BORDER"]].cpu().numpy()
+    assert np.array_equal(got, [int(oracle.compute_border(l)) for l in labs])
