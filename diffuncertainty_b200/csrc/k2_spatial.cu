@@ -140,7 +140,7 @@ constexpr int kP3ZSlices = 8;    // output slices per chunk of the workspace
 __host__ __device__ inline int p3_zchunks(long long o0) { return (int)((o0 + kP3ZSlices - 1) / kP3ZSlices); }
 
 template <int MODE, int KT>
-__global__ void __launch_bounds__(kP3Threads, 2) patch_box3(const float* __restrict__ maps, long long d0, long long d1, long long d2,
+__global__ void __launch_bounds__(kP3Threads, KT > 0 ? 3 : 2) patch_box3(const float* __restrict__ maps, long long d0, long long d1, long long d2,
                                                            int rk0, int rk1, int rk2, unsigned long long* max_enc, long long* first,
                                                            double scale, int tiles_x, unsigned long long* tile_max) {
     extern __shared__ double smem_d[];
