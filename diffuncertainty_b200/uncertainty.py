@@ -151,6 +151,19 @@ def _members_view(members):
     return first
 
 
+def group_members(groups: Sequence[torch.Tensor]) -> list:
+    """test_2D.py:1277: ``torch.stack(groups).mean(dim=1)`` without the stack -- every group ``(n_g, B, C, *S)`` (one stochastic
+    sample per group unless several generative draws share one, test_2D.py:1134-1136, 1160) becomes one member ``(B, C, *S)``
+    that ``fused_pass`` / ``member_scores`` then read in place.  A single-sample group is a view, not a copy; the mean of a
+    larger group is torch's own reduction on the group's device, as in the reference."""
+    members = []
+    for g in groups:
+        if g.dim() < 4:
+            raise ValueError(f"every group must be (n_g, B, C, *spatial), got shape {tuple(g.shape)}")
+        members.append(g[0] if g.shape[0] == 1 else g.mean(dim=0))
+    return members
+
+
 def fill_slab(slab: _lib.Slab, softmax_pred):
     """Describe ``softmax_pred`` -- a (P, B, C, *S) tensor with any strides, or a list of P member tensors (B, C, *S)
     that are then read where they are (no torch.stack, test_2D.py:1277) -- in a vu_slab.  Returns

@@ -83,3 +83,25 @@ def test_dice_from_counts():
     got = vaurc.binary_dice_from_counts(tp, ps, gs)
     want = [oracle.binary_dice_from_counts(tp[i], ps[i], gs[i]) for i in range(2)]
     np.testing.assert_allclose(got, want, rtol=1e-7)
+
+
+def test_group_members_equals_stack_mean():
+    """test_2D.py:1277: torch.stack(groups).mean(dim=1) == one member per group; single-sample groups stay views."""
+    import torch
+    from diffuncertainty_b200 import group_members
+    gen = torch.Generator().manual_seed(3)
+    for n_g in (1, 3, 17):
+        groups = [torch.softmax(torch.randn(n_g, 2, 4, 5, 6, generator=gen), dim=2) for _ in range(4)]
+        want = torch.stack(groups).mean(dim=1)
+        got = group_members(groups)
+        assert len(got) == 4
+        for i, m in enumerate(got):
+            torch.testing.assert_close(m, want[i], rtol=1e-6, atol=1e-7)
+            if n_g == 1:
+                assert m.data_ptr() == groups[i].data_ptr() and torch.equal(m, want[i])
+    try:
+        group_members([torch.zeros(2, 3, 4)])
+    except ValueError:
+        pass
+    else:
+        raise AssertionError("a group without a spatial axis must be rejected")
