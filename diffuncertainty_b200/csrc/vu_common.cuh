@@ -530,9 +530,13 @@ __device__ __forceinline__ void stats_prefetch_gt(const StatParams& sp, long lon
         // all raters instead of R per thread -- these launches are issue-bound)
         const int lane = threadIdx.x & 31;
         const int lpr = (int)((32 * VEC * esz + 127) / 128);  // lines per rater
-        const char* base = reinterpret_cast<const char*>(sp.gt.data) + (b * sp.gt.sb + (v - (long long)lane * VEC)) * esz;
-        for (int i = lane; i < sp.gt.R * lpr; i += 32)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (long long)(i / lpr) * sp.gt.sr * esz + (long long)(i % lpr) * 128));
+        const long long vb = v - (long long)lane * VEC;  // first voxel of the warp
+        const char* base = reinterpret_cast<const char*>(sp.gt.data) + (b * sp.gt.sb + vb) * esz;
+        for (int i = lane; i < sp.gt.R * lpr; i += 32) {
+            const long long line = i % lpr;
+            if (vb + line * (128 / esz) < sp.V)  // never past the end of a rater's row (the last warp of an image is ragged)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (long long)(i / lpr) * sp.gt.sr * esz + line * 128));
+        }
         return;
     }
     const char* base = reinterpret_cast<const char*>(sp.gt.data) + (b * sp.gt.sb + v * sp.gt.sv) * esz;
