@@ -11,7 +11,6 @@ arithmetic on P*G + P*P + G*G numbers and the means over P*G numbers run here, i
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -21,14 +20,33 @@ from . import _lib
 from .uncertainty import GroundTruth, _fill_gt, fill_slab, fused_pass
 
 
-@dataclass
 class MemberScores:
-    P: int
-    R: int
-    nll_sum: Optional[np.ndarray] = None    # (B, R, P) float64: sum over valid voxels of ln(max(p[member, gt], eps))
-    nll_count: Optional[np.ndarray] = None  # (B, R) int64
-    ged_counts: Optional[np.ndarray] = None  # (B, vu_ged_cols(P, R)) int64
-    has_major: bool = False
+    """Result of one vu_member_scores launch.  The buffers stay on the device; ``nll_sum`` (B, R, P) float64 -- the sum over
+    valid voxels of ln(max(p[member, gt], eps)) --, ``nll_count`` (B, R) int64 and ``ged_counts`` (B, vu_ged_cols(P, R)) int64
+    are copied to the host on first use."""
+
+    def __init__(self, P: int, R: int, nll_sum=None, nll_count=None, ged_counts=None, has_major: bool = False):
+        self.P, self.R, self.has_major = P, R, has_major
+        self.device_buffers = {"nll_sum": nll_sum, "nll_count": nll_count, "ged_counts": ged_counts}
+        self._host = {}
+
+    def _get(self, name: str) -> Optional[np.ndarray]:
+        if name not in self._host:
+            t = self.device_buffers[name]
+            self._host[name] = None if t is None else t.cpu().numpy()
+        return self._host[name]
+
+    @property
+    def nll_sum(self) -> Optional[np.ndarray]:
+        return self._get("nll_sum")
+
+    @property
+    def nll_count(self) -> Optional[np.ndarray]:
+        return self._get("nll_count")
+
+    @property
+    def ged_counts(self) -> Optional[np.ndarray]:
+        return self._get("ged_counts")
 
     def ged_parts(self, b: int) -> Dict[str, np.ndarray]:
         """The count matrices of image b, by the names of valunc.h."""
@@ -152,9 +170,7 @@ def member_scores(softmax_pred, gt: GroundTruth, *, nll: bool = True, ged: bool 
             # torch.gather raises "index ... is out of bounds" in the reference (test_2D.py:1067)
             raise RuntimeError("ground truth holds values that are neither a class index nor the ignore value")
     del keep_slab, keep_gt
-    return MemberScores(P=P, R=R, nll_sum=None if nll_sum is None else nll_sum.cpu().numpy(),
-                        nll_count=None if nll_cnt is None else nll_cnt.cpu().numpy(),
-                        ged_counts=None if ged_counts is None else ged_counts.cpu().numpy(), has_major=mean_labels is not None and ged)
+    return MemberScores(P=P, R=R, nll_sum=nll_sum, nll_count=nll_cnt, ged_counts=ged_counts, has_major=mean_labels is not None and ged)
 
 
 def _as_gt(ground_truth, n_spatial: int, device, ignore_index) -> GroundTruth:
