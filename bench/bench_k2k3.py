@@ -61,11 +61,23 @@ def main():
         def mapstats():
             _lib.check(lib.vu_map_stats(C.byref(a), st), "map_stats")
 
+        def mapstats_general():
+            _lib.set_option("stats_path", 1)
+            mapstats()
+            _lib.set_option("stats_path", 0)
+
         for label, fn, nbytes in (("K2 patch_max (one map, 10^d box)", patch, 4 * V * B),
                                   ("K2 patch_max_ws (with workspace)", patch_ws, 4 * V * B), ("K2 border", border, V * B),
-                                  (f"K3 map_stats flags={a.stat_flags:#x}", mapstats, (13 + R) * V * B)):
+                                  (f"K3 map_stats flags={a.stat_flags:#x} (lean form)", mapstats, (13 + R) * V * B),
+                                  (f"K3 map_stats flags={a.stat_flags:#x} (general form)", mapstats_general, (13 + R) * V * B)):
             ms = time_call(fn, iters=10)
-            print(f"{name:16s} B={B:4d} {label:36s} {ms:8.3f} ms  {nbytes / ms / 1e6:8.1f} GB/s  {V * B / ms / 1e6:8.1f} Gvox/s", flush=True)
+            print(f"{name:16s} B={B:4d} {label:44s} {ms:8.3f} ms  {nbytes / ms / 1e6:8.1f} GB/s  {V * B / ms / 1e6:8.1f} Gvox/s", flush=True)
+        # the two forms must agree: integers exactly, float sums to rounding
+        sf.zero_(); si.zero_(); mapstats(); torch.cuda.synchronize()
+        f2, i2 = sf.clone(), si.clone()
+        sf.zero_(); si.zero_(); mapstats_general(); torch.cuda.synchronize()
+        rel = float(((f2 - sf).abs() / sf.abs().clamp_min(1e-300)).max())
+        print(f"{name:16s} lean vs general form: integers equal = {bool(torch.equal(i2, si))}, max rel diff of the float64 sums = {rel:.2e}", flush=True)
 
 
 if __name__ == "__main__":

@@ -8,6 +8,6 @@ Python call surface of JakobLC/DiffUncertainty's
 """
 from . import _lib  # noqa: F401
 from .uncertainty import (FusedResult, GroundTruth, calculate_one_minus_msr, calculate_uncertainty, fused_pass,  # noqa: F401
-                          group_members, mean_argmax_labels)
+                          group_members, map_stats, mean_argmax_labels)
 
 __version__ = "0.1.0"

@@ -81,6 +81,7 @@ static int fill_stat_params(StatParams& st, uint32_t flags, unsigned unc_mask, l
     memset(&st, 0, sizeof(st));
     st.flags = flags;
     st.unc_mask = unc_mask;
+    st.magic_bits = 0x4B400000u;
     st.V = V;
     if (flags == 0) return VU_OK;
     if (!f64 || !i64) return set_error(VU_ERR_BAD_ARG, "stat_flags set but stats_f64 / stats_i64 is NULL");

@@ -361,6 +361,9 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     // preferred path: the TMA-pipelined kernel (k1_tma.cu); "k1_path" = 1 keeps to the register-streaming
     // kernels, 2 insists on TMA
     if (forced == -1) {
+        // few-class slabs with reference-based statistics: the unified-warp TMA form (k1_uni.cu)
+        const int rcu = launch_k1_uni(a, st, stream);
+        if (rcu <= 0) return rcu;
         const int rc = launch_k1_tma(a, st, stream);
         if (rc <= 0) return rc;
         if (get_option("k1_path", 0) == 2) return set_error(VU_ERR_UNSUPPORTED, "slab not eligible for the TMA path");
@@ -407,12 +410,9 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     size_t dyn = generic_smem_bytes(s.P, T, a->member_labels != nullptr) + stats_smem_bytes(st.flags, st.gt.R, T);
     if (dyn > max_dyn) return set_error(VU_ERR_UNSUPPORTED, "P too large for the generic kernel (P*256 B of shared memory, P*576 B with member labels)");
     if (s.P > (1LL << 19)) return set_error(VU_ERR_UNSUPPORTED, "P > 2^19");
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k1_generic<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn) != cudaSuccess)
-            return set_cuda_error("cudaFuncSetAttribute(k1_generic)");
-        attr_set = true;
-    }
+    // the attribute is per device (and this may be the first launch on this one): set it whenever it is needed
+    if (dyn > 48 * 1024 && cudaFuncSetAttribute(k1_generic<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+        return set_cuda_error("cudaFuncSetAttribute(k1_generic)");
     prm.tiles_per_img = (s.V + T - 1) / T;
     prm.total_tiles = prm.tiles_per_img * s.B;
     if (prm.total_tiles >= (1LL << 31)) return set_error(VU_ERR_UNSUPPORTED, "more than 2^31 tiles in one launch; split the batch");

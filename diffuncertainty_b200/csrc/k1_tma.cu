@@ -19,6 +19,7 @@
 //
 // Reference semantics: see k1_fused.cu / k1_core.cuh.
 #include "k1_core.cuh"
+#include "tma_common.cuh"
 #include "vu_host.h"
 
 namespace vu {
@@ -43,64 +44,16 @@ struct K1TmaParams {
     StatParams st;
 };
 
-// ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-constexpr int kStatThreads = 96;   // 3 statistics warps: with the producer warp they fill one 128-thread group
 constexpr int kStatVec = 4;        // voxels per statistics thread and pass
-
-// same, for the statistics warps, which are ahead of the pipeline most of the time: sleep between probes instead
-// of burning issue slots the consumer warps need
-__device__ __forceinline__ void mbar_wait_relaxed(unsigned bar, unsigned parity) {
-    unsigned done = 0;
-    while (true) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        __nanosleep(100);
-    }
-}
-// global -> shared bulk copy, completion counted in bytes on an mbarrier; read-once data: evict-first in L2
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar, unsigned long long policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
-                 : "memory");
-}
-
 
 // The tile loop of the statistics warps: pick (TU, AU, EU, label) of each tile up from the hand-off buffer the consumers
 // filled and run the statistics phase on kStatVec voxels per thread and pass.
-template <int TV, int TID0, unsigned FL>
+// ST: statistics threads (a multiple of 32), REP: histogram replicas per warp (32: one per lane; 16: two half-warp phases).
+template <int TV, int TID0, unsigned FL, int ST, int REP>
 __device__ __forceinline__ void stat_warps_loop(const StatParams& st, void* st_smem, const unsigned char* hand, unsigned hand_bytes,
                                                 unsigned hfull0, unsigned hempty0, int t0, int t1, int tpi, long long V) {
-    constexpr int kRep = 32;
+    constexpr int kRep = REP;
+    constexpr int kStatThreads = ST;
     constexpr int kPasses = (TV + kStatThreads * kStatVec - 1) / (kStatThreads * kStatVec);
     const int s = (int)threadIdx.x - TID0;
     StatsCursor<kStatThreads> cursor;
@@ -145,8 +98,11 @@ __device__ __forceinline__ void stat_warps_loop(const StatParams& st, void* st_s
 // C classes, VEC voxels per consumer thread, CT consumer threads.
 // NCH == 1: a stage holds G whole members (G x C rows).  NCH == 2 (G == 1, VEC >= 2): a stage holds half a
 // member's classes ((C+1)/2 rows), for C = 19 where a whole member of a 1024-voxel tile would take 76 KB.
-template <int C, int VEC, int LEVELS, int CT, int G, int NCH, bool STATS>
-__global__ void __launch_bounds__(CT + 32 + kStatThreads, 1) k1_tma(const __grid_constant__ K1TmaParams prm) {
+// ST statistics threads (0: a launch without statistics), SREP histogram replicas per statistics warp.
+template <int C, int VEC, int LEVELS, int CT, int G, int NCH, int ST, int SREP>
+__global__ void __launch_bounds__(CT + 32 + ST, 1) k1_tma(const __grid_constant__ K1TmaParams prm) {
+    constexpr bool STATS = ST > 0;
+    constexpr int kStatThreads = ST;
     static_assert(NCH == 1 || (NCH == 2 && G == 1 && VEC >= 2), "class chunks: one member per stage, VEC >= 2");
     constexpr int TV = CT * VEC;  // voxels per tile
     constexpr int CH = (NCH == 1) ? C : (C + 1) / 2;
@@ -174,7 +130,7 @@ __global__ void __launch_bounds__(CT + 32 + kStatThreads, 1) k1_tma(const __grid
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(hfull0 + 8 * s, CT / 32);
-            mbar_init(hempty0 + 8 * s, kStatThreads / 32);
+            mbar_init(hempty0 + 8 * s, STATS ? kStatThreads / 32 : 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -233,10 +189,12 @@ __global__ void __launch_bounds__(CT + 32 + kStatThreads, 1) k1_tma(const __grid
         const bool plain = st.unc_mask == 7u && st.lut == nullptr && st.gt.dtype == VU_GT_U8;
         auto run = [&](auto fl_tag) {
             constexpr unsigned FL = decltype(fl_tag)::value;
-            stat_warps_loop<TV, kStat0, FL>(st, st_smem, hand, kHandBytes, hfull0, hempty0, t0, t1, tpi, V);
+            stat_warps_loop<TV, kStat0, FL, (ST > 0 ? ST : 32), SREP>(st, st_smem, hand, kHandBytes, hfull0, hempty0, t0, t1, tpi, V);
         };
         if (plain && st.flags == 0x1fu) run(std::integral_constant<unsigned, 0x1fu>());
         else if (plain && st.flags == 0x3fu) run(std::integral_constant<unsigned, 0x3fu>());
+        else if (plain && st.flags == 0x1du) run(std::integral_constant<unsigned, 0x1du>());
+        else if (plain && st.flags == 0x21u) run(std::integral_constant<unsigned, 0x21u>());
         else if (st.unc_mask == 7u && st.flags == 0x07u) run(std::integral_constant<unsigned, 0x07u>());
         else run(std::integral_constant<unsigned, kRuntimeFlags>());
         return;
@@ -359,12 +317,14 @@ __global__ void __launch_bounds__(CT + 32 + kStatThreads, 1) k1_tma(const __grid
 // ---------------------------------------------------------------------------
 typedef void (*K1TmaKernel)(const K1TmaParams);
 struct TmaVariant {
-    int C, VEC, LEVELS, CT, G, NCH;
+    int C, VEC, LEVELS, CT, G, NCH, ST, SREP;
+    int use;  // automatic selection: 0 = any launch, 1 = only launches with reference-based statistics on few-class slabs, -1 = never
     K1TmaKernel fn, fn_stats;
 };
-#define VU_TMA(C, VEC, LEVELS, CT, G, NCH)                                                  \
-    { C, VEC, LEVELS, CT, G, NCH, (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, NCH, false>,   \
-      (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, NCH, true> }
+#define VU_TMA_S(C, VEC, LEVELS, CT, G, NCH, ST, SREP, USE)                                              \
+    { C, VEC, LEVELS, CT, G, NCH, ST, SREP, USE, (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, NCH, 0, 32>, \
+      (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, NCH, ST, SREP> }
+#define VU_TMA(C, VEC, LEVELS, CT, G, NCH) VU_TMA_S(C, VEC, LEVELS, CT, G, NCH, 96, 32, 0)
 
 static const TmaVariant kTma[] = {
     VU_TMA(2, 4, 1, 512, 2, 1),  VU_TMA(2, 4, 2, 512, 2, 1),   // 0, 1
@@ -373,6 +333,9 @@ static const TmaVariant kTma[] = {
     VU_TMA(19, 2, 1, 256, 1, 1), VU_TMA(19, 2, 2, 256, 1, 1),  // 6, 7
     VU_TMA(3, 4, 1, 256, 2, 1),  VU_TMA(3, 4, 2, 256, 2, 1),   // 8, 9
     VU_TMA(4, 4, 1, 256, 2, 1),  VU_TMA(4, 4, 2, 256, 2, 1),   // 10, 11
+    // few classes with reference-based statistics: the statistics phase outweighs the streaming arithmetic, so the warp
+    // split follows the work (consumer warps : statistics warps)
+    VU_TMA_S(2, 4, 1, 256, 1, 1, 256, 16, -1), VU_TMA_S(2, 4, 2, 512, 2, 1, 192, 32, -1),  // 12, 13   8 : 8 (16 replicas), 16 : 6
 };
 static const int kNumTma = (int)(sizeof(kTma) / sizeof(kTma[0]));
 
@@ -396,7 +359,7 @@ int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t str
         pick = &f;
     } else {
         for (int i = 0; i < kNumTma && !pick; ++i)
-            if (kTma[i].C == s.C && kTma[i].LEVELS == need_levels) pick = &kTma[i];
+            if (kTma[i].C == s.C && kTma[i].LEVELS == need_levels && kTma[i].use == 0) pick = &kTma[i];
     }
     if (!pick) return 1;
     // With few classes the reference-based statistics outweigh the streaming arithmetic; three statistics warps
@@ -424,7 +387,7 @@ int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t str
 
     const int rows = pick->NCH == 1 ? pick->G * pick->C : (pick->C + 1) / 2;
     const size_t stage_bytes = (size_t)rows * tile_vox * sizeof(float);
-    const size_t stats_bytes = stats_smem_bytes(st.flags, st.gt.R, kStatThreads, 32);
+    const size_t stats_bytes = stats_smem_bytes(st.flags, st.gt.R, pick->ST, pick->SREP);
     const size_t hand_bytes = st.flags ? 2 * 13 * (size_t)tile_vox : 0;
     const size_t budget = 227 * 1024;
     const size_t fixed = 256 /* barriers */ + 256 /* alignment slack */ + stats_bytes + hand_bytes;
@@ -448,7 +411,7 @@ int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t str
         return set_cuda_error("cudaFuncSetAttribute(k1_tma)");
     long long grid = device_sm_count();
     if (grid > prm.total_tiles) grid = prm.total_tiles;
-    const int threads = pick->CT + 32 + (st.flags ? kStatThreads : 0);  // no statistics warps without statistics
+    const int threads = pick->CT + 32 + (st.flags ? pick->ST : 0);  // no statistics warps without statistics
     fn<<<(unsigned)grid, threads, dyn, stream>>>(prm);
     count_launch("k1_tma");
     return check_launch("k1_tma");

@@ -1,0 +1,284 @@
+// K1, unified-warp TMA form for binary slabs (C == 2): every consumer warp does the streaming arithmetic AND the statistics of
+// its own voxels.
+//
+// Why a third form: for few-class slabs with reference-based statistics (configs[1]: N = 5, C = 2, 4 raters, calibration
+// histograms; configs[3]: N = 32, NCC) the statistics outweigh the streaming arithmetic.  In the warp-specialised form
+// (k1_tma.cu) the split between consumer and statistics warps is fixed at compile time, so one of the two groups idles
+// (r02a, configs[1]: 16 + 3 warps 1.81 ms, 8 + 8 warps 0.71 ms, 8 + 12 warps 0.80 ms -- never balanced); in the
+// register-streaming form (k1_fused.cu) a warp has no loads in flight while it computes (0.81 ms).  Here one producer warp
+// keeps the shared-memory ring full with cp.async.bulk copies whatever the other warps do, and each of the CT / 32 consumer
+// warps alternates between consuming a tile and running the lean statistics phase (stats_v2.cuh) on the four voxels per
+// thread it has just finished, straight from registers: no hand-off buffer, no idle warps, any ratio of the two kinds of
+// work.  The ring (>= 96 KB) rides out the statistics phases of the warps.  Partial sums stay in registers, histograms are
+// private to a warp, and a warp flushes on its own when it moves to another image: no CTA-wide barrier after start-up.
+//
+// Reference semantics: see k1_fused.cu / k1_core.cuh (maps, labels) and stats_v2.cuh (statistics).
+#include "k1_core.cuh"
+#include "stats_v2.cuh"
+#include "tma_common.cuh"
+#include "vu_host.h"
+
+namespace vu {
+
+extern __shared__ __align__(128) unsigned char vu_uni_smem[];
+
+struct K1UniParams {
+    const float* x;
+    const float* const* mptr;  // optional device array of P member base pointers (then x / sp are unused)
+    long long P, B, V;
+    long long sp, sb, sc;
+    float* tu;
+    float* au;
+    float* eu;
+    uint8_t* lab;
+    uint8_t* mlab;  // per-member labels (P, B, V) or NULL
+    long long tiles_per_img, total_tiles;
+    int nstages;
+    unsigned bar_offset;    // byte offsets inside dynamic shared memory
+    unsigned stats_offset;
+    StatParams st;
+};
+
+constexpr int kUniRep = 16;  // histogram replicas per warp (two lanes share one; the half-warps walk the types in rotated order)
+
+// LEVELS: cascade levels of the member sum (1: P <= 17, 2: P <= 271); CT consumer threads; G members per ring stage;
+// FL: the statistics mask (compile time); RMAX: raters the reference registers are sized for.
+template <int LEVELS, int CT, int G, unsigned FL, int RMAX>
+__global__ void __launch_bounds__(CT + 32, 1) k1_uni(const __grid_constant__ K1UniParams prm) {
+    constexpr int C = 2, VEC = 4;
+    constexpr int TV = CT * VEC;  // voxels per tile
+    constexpr unsigned kRowBytes = TV * sizeof(float);
+    constexpr unsigned kStageBytes = G * C * kRowBytes;
+    constexpr int kStageFloats = kStageBytes / sizeof(float);
+    constexpr int kWarps = CT / 32;
+    using Acc = VoxelAcc<C, VEC, LEVELS>;
+
+    const int nstages = prm.nstages;
+    float* ring = reinterpret_cast<float*>(vu_uni_smem);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(vu_uni_smem + prm.bar_offset);
+    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + nstages);
+    void* st_smem = vu_uni_smem + prm.stats_offset;
+    const StatParams& sp = prm.st;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < nstages; ++s) {
+            mbar_init(full0 + 8 * s, 1);       // the producer's arrive.expect_tx
+            mbar_init(empty0 + 8 * s, kWarps);  // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    stats2_init<kUniRep>(sp, st_smem, tid, CT + 32, kWarps);
+    __syncthreads();
+
+    const long long P = prm.P, V = prm.V;
+    const int t0 = (int)(prm.total_tiles * (long long)blockIdx.x / gridDim.x);
+    const int t1 = (int)(prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x);
+    const int tpi = (int)prm.tiles_per_img;
+    const int fills = (int)((P + G - 1) / G);  // stage fills per tile
+
+    if (tid >= CT) {
+        // ------------------------------ producer warp ---------------------------------------------------
+        const int lane = tid - CT;
+        unsigned long long policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        int b = t0 / tpi, vt = t0 - b * tpi - 1;
+        int stage = 0;
+        unsigned phase = 0;
+        for (int tile = t0; tile < t1; ++tile) {
+            if (++vt == tpi) { vt = 0; ++b; }
+            const long long v0 = (long long)vt * TV;
+            const long long left = V - v0;
+            const unsigned row_bytes = left >= TV ? kRowBytes : (unsigned)(left * sizeof(float));
+            const long long off0 = (long long)b * prm.sb + v0;  // offset of the tile inside a member
+            for (int fi = 0; fi < fills; ++fi) {
+                const int p0 = fi * G;
+                const int nrows = ((P - p0) < G ? (int)(P - p0) : G) * C;
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);  // slot free (the first pass falls through)
+                if (lane == 0) mbar_arrive_expect_tx(full0 + 8 * stage, (unsigned)nrows * row_bytes);
+                __syncwarp();
+                const unsigned dst0 = smem_u32(ring) + (unsigned)stage * kStageBytes;
+                for (int r = lane; r < nrows; r += 32) {
+                    const int g = r / C, c = r - g * C;
+                    const float* mem = prm.mptr ? ld_member_ptr(prm.mptr, p0 + g) : prm.x + (long long)(p0 + g) * prm.sp;
+                    bulk_g2s(dst0 + (unsigned)r * kRowBytes, mem + off0 + (long long)c * prm.sc, row_bytes, full0 + 8 * stage, policy);
+                }
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------- consumer warps: streaming + statistics --------------------------------------------
+    const int warp = tid >> 5;
+    const float Pf = (float)P;
+    Stat2Ctx cx;
+    stats2_ctx<kUniRep>(cx, sp, st_smem, warp, kWarps);
+    const bool rot = stats2_rotated<kUniRep>();
+    StatAcc<FL, RMAX> A;
+    A.clear();
+    int cur_b = -1, vt_begin = 0;
+    auto flush = [&]() {
+        stats2_flush_regs<FL, RMAX, kUniRep>(A, sp, cur_b);
+        if (FL & VU_STAT_CALIB) stats2_flush_hist_warp<kUniRep>(sp, st_smem, cur_b, warp);
+    };
+
+    int b = t0 / tpi, vt = t0 - b * tpi - 1;
+    int stage = 0;
+    unsigned phase = 0;
+    for (int tile = t0; tile < t1; ++tile) {
+        if (++vt == tpi) { vt = 0; ++b; }
+        if (b != cur_b || (vt - vt_begin) * VEC >= kMaxVoxPerFlush) {  // warp-uniform
+            if (cur_b >= 0) flush();
+            cur_b = b;
+            vt_begin = vt;
+        }
+        const long long v = (long long)vt * TV + (long long)tid * VEC;
+        const bool active = v < V;
+        unsigned W[RMAX];
+        stats2_load_refs<FL, RMAX>(sp, active, b, v, W);  // in flight while the members stream
+
+        Acc acc;
+        acc.init();
+        for (int fi = 0; fi < fills; ++fi) {
+            mbar_wait(full0 + 8 * stage, phase);  // the bytes of this stage have landed
+            const float* sbase = ring + (size_t)stage * kStageFloats + tid * VEC;
+            // (a partial last tile leaves stale bytes behind the image's end: those threads are inactive and
+            //  their arithmetic is discarded)
+            const int p0 = fi * G;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (G == 1 || p0 + g < P) {
+                    f32x2 xp[Acc::NP];
+                    const float* srow = sbase + (size_t)g * C * TV;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float4 w = *reinterpret_cast<const float4*>(srow + c * TV);
+                        xp[c * 2] = pk2(w.x, w.y);
+                        xp[c * 2 + 1] = pk2(w.z, w.w);
+                    }
+                    acc.add_member(xp, 0.f, p0 + g, prm.mlab != nullptr);
+                    if (prm.mlab && active) VecLoad<VEC>::store_u8(prm.mlab + ((long long)(p0 + g) * prm.B + b) * V + v, acc.bi);
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(empty0 + 8 * stage);  // this warp is done reading the stage
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+
+        float u[VU_N_UNC][VEC];
+        int label[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { u[0][k] = u[1][k] = u[2][k] = 0.f; label[k] = 0; }
+        if (active) {
+            acc.finish(Pf, u, label);
+            const long long o = (long long)b * V + v;
+            if (prm.tu) VecLoad<VEC>::store(prm.tu + o, u[0]);
+            if (prm.au) VecLoad<VEC>::store(prm.au + o, u[1]);
+            if (prm.eu) VecLoad<VEC>::store(prm.eu + o, u[2]);
+            if (prm.lab) VecLoad<VEC>::store_u8(prm.lab + o, label);
+        }
+        // statistics of this thread's four voxels, in the lane's step order (stats_v2.cuh, "type rotation")
+        const unsigned lab4 = (unsigned)label[0] | ((unsigned)label[1] << 8) | ((unsigned)label[2] << 16) | ((unsigned)label[3] << 24);
+        float4 U[VU_N_UNC];
+#pragma unroll
+        for (int s = 0; s < VU_N_UNC; ++s) {
+            const int k1 = (s + 1) % VU_N_UNC;
+            U[s] = make_float4(rot ? u[k1][0] : u[s][0], rot ? u[k1][1] : u[s][1], rot ? u[k1][2] : u[s][2], rot ? u[k1][3] : u[s][3]);
+        }
+        stats2_tile<FL, RMAX, kUniRep>(A, sp, cx, active, b, U[0], U[1], U[2], lab4, W);
+    }
+    if (cur_b >= 0) flush();
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef void (*K1UniKernel)(const K1UniParams);
+struct UniVariant {
+    int LEVELS, CT, G;
+    unsigned FL;
+    int RMAX;
+    K1UniKernel fn;
+};
+#define VU_UNI(LEVELS, CT, G, FL, RMAX) { LEVELS, CT, G, FL, RMAX, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX> }
+// Registers are allocated per SM sub-partition: 16 consumer warps + the producer put 5 warps on one of them (96 registers per
+// thread), 15 + 1 leave 4 on each (128).  The masks with calibration histograms need the 128 (they spill 260-720 bytes at
+// 96); the others do not, and keep the power-of-two tile.
+#define VU_UNI_MASKS(LEVELS, G)                                                                                                      \
+    VU_UNI(LEVELS, 512, G, 0x0du, 4), VU_UNI(LEVELS, 512, G, 0x0fu, 4), VU_UNI(LEVELS, 480, G, 0x1du, 4), VU_UNI(LEVELS, 480, G, 0x1fu, 4), \
+    VU_UNI(LEVELS, 512, G, 0x21u, 4), VU_UNI(LEVELS, 480, G, 0x3fu, 4), VU_UNI(LEVELS, 480, G, 0x3fu, 8)
+
+static const UniVariant kUni[] = {
+    VU_UNI_MASKS(1, 1),
+    VU_UNI_MASKS(2, 2),
+};
+static const int kNumUni = (int)(sizeof(kUni) / sizeof(kUni[0]));
+
+bool stats2_eligible(const StatParams& st, long long V);  // k3_map_stats.cu
+
+// Returns VU_OK after launching, 1 if this launch is not one for the unified form (the caller goes on to the
+// warp-specialised / register-streaming kernels), or a negative vu_status.
+int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t stream) {
+    const vu_slab& s = a->slab;
+    const long long path = get_option("k1_path", 0);
+    if (path == 1 || path == 2) return 1;  // 1 = register-streaming kernels only, 2 = warp-specialised TMA kernels only
+    if (get_option("k1_tma_variant", -1) >= 0 || get_option("stats_path", 0) == 1) return 1;
+    if (s.C != 2 || s.stride_v != 1 || s.P < 2 || s.P > 271 || !st.flags) return 1;
+    const unsigned heavy = VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC;
+    if (!(st.flags & heavy) && path != 3) return 1;  // sums / thresholds / area only: the warp-specialised form is at the HBM roofline
+    if (!stats2_eligible(st, s.V)) return 1;
+    // bulk copies need 16-byte aligned rows and sizes
+    if ((uintptr_t)s.data % 16 || s.V % 4 || (!s.member_ptrs && s.stride_p % 4) || s.stride_b % 4 || s.stride_c % 4) return 1;
+    if (s.member_ptrs_host)
+        for (int64_t p = 0; p < s.P; ++p)
+            if ((uintptr_t)s.member_ptrs_host[p] % 16) return 1;
+    auto ok = [&](const void* p, uintptr_t al) { return p == nullptr || ((uintptr_t)p % al) == 0; };
+    if (!ok(a->tu, 16) || !ok(a->au, 16) || !ok(a->eu, 16) || !ok(a->labels, 4) || !ok(a->member_labels, 4)) return 1;
+    const int need_levels = s.P <= 17 ? 1 : 2;
+    const int rmax = (st.flags & heavy) && st.gt.R > 4 ? 8 : 4;
+    const UniVariant* pick = nullptr;
+    for (int i = 0; i < kNumUni && !pick; ++i)
+        if (kUni[i].LEVELS == need_levels && kUni[i].FL == st.flags && kUni[i].RMAX >= rmax) pick = &kUni[i];
+    if (!pick) return 1;
+
+    K1UniParams prm;
+    prm.x = s.data;
+    prm.mptr = s.member_ptrs;
+    prm.P = s.P; prm.B = s.B; prm.V = s.V;
+    prm.sp = s.stride_p; prm.sb = s.stride_b; prm.sc = s.stride_c;
+    prm.tu = a->tu; prm.au = a->au; prm.eu = a->eu; prm.lab = a->labels;
+    prm.mlab = a->member_labels;
+    prm.st = st;
+    const long long tile_vox = (long long)pick->CT * 4;
+    prm.tiles_per_img = (s.V + tile_vox - 1) / tile_vox;
+    prm.total_tiles = prm.tiles_per_img * s.B;
+    if (prm.total_tiles >= (1LL << 31)) return set_error(VU_ERR_UNSUPPORTED, "more than 2^31 tiles in one launch; split the batch");
+
+    const size_t stage_bytes = (size_t)pick->G * 2 * tile_vox * sizeof(float);
+    const size_t stats_bytes = stats2_smem_bytes(st.flags, pick->CT, kUniRep);
+    const size_t budget = 227 * 1024;
+    const size_t fixed = 256 /* barriers */ + 256 /* alignment slack */ + stats_bytes;
+    long long nstages = get_option("k1_tma_stages", 0);
+    const long long fit = fixed < budget ? (long long)((budget - fixed) / stage_bytes) : 0;
+    if (nstages <= 0) nstages = fit < 8 ? fit : 8;
+    if (nstages > fit) nstages = fit;
+    if (nstages > 8) nstages = 8;
+    if (nstages < 2) return 1;
+    prm.nstages = (int)nstages;
+    size_t off = (size_t)nstages * stage_bytes;
+    prm.bar_offset = (unsigned)off;
+    off = (off + 256 + 127) / 128 * 128;  // 2 x nstages mbarriers (<= 128 bytes)
+    prm.stats_offset = (unsigned)off;
+    const size_t dyn = off + stats_bytes;
+
+    if (cudaFuncSetAttribute(pick->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+        return set_cuda_error("cudaFuncSetAttribute(k1_uni)");
+    long long grid = device_sm_count();
+    if (grid > prm.total_tiles) grid = prm.total_tiles;
+    pick->fn<<<(unsigned)grid, pick->CT + 32, dyn, stream>>>(prm);
+    count_launch("k1_uni");
+    return check_launch("k1_uni");
+}
+
+}  // namespace vu

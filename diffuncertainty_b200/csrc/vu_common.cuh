@@ -240,6 +240,8 @@ constexpr float kRoundMagic = 12582912.0f;  // 1.5 * 2^23: x + magic rounds x to
 struct StatParams {
     unsigned flags;
     unsigned unc_mask;  // bit k set: uncertainty type k is present (TU/AU/EU; bit 0 only when P == 1)
+    unsigned magic_bits;  // bit pattern of kRoundMagic, handed over as a run-time value: table bases biased by it stay one
+                          // register (as a compile-time constant the compiler splits the bias off and re-adds it at every use)
     long long V;
     GtView gt;
     float thr[VU_N_UNC];

@@ -332,3 +332,62 @@ def mean_argmax_labels(softmax_pred: torch.Tensor) -> torch.Tensor:
     """argmax over classes of the member mean for a whole batch (test_2D.py:971, 871,
     815-818): (P, B, C, *S) -> (B, *S) uint8."""
     return fused_pass(softmax_pred, want_maps=False).labels
+
+
+def map_stats(maps: Dict[str, torch.Tensor], labels: Optional[torch.Tensor] = None, gt: Optional[GroundTruth] = None, *,
+              stats: int, thresholds: Optional[Sequence[float]] = None, calib=None, label_lut: Optional[torch.Tensor] = None,
+              ncc_gt_map: Optional[torch.Tensor] = None, stats_out: Optional[tuple] = None) -> FusedResult:
+    """The statistics of ``fused_pass`` on maps / labels that already exist in device memory -- what the reference's
+    file-based evaluation works on (evaluation/eval_experiments.py:348-355).  ``maps``: {"TU","AU","EU"} -> (B, *S) contiguous
+    fp32 CUDA tensors (a missing key skips that type); ``labels``: (B, *S) uint8; the other arguments as in ``fused_pass``."""
+    _lib.require_device()
+    lib = _lib.load()
+    present = [maps.get(k) for k in UNC_KEYS]
+    first = next((m for m in present if m is not None), None)
+    if first is None:
+        raise ValueError("map_stats needs at least one of the maps TU, AU, EU")
+    _check_slab(first, "maps")
+    B, spatial, dev = first.shape[0], tuple(first.shape[1:]), first.device
+    V = int(np.prod(spatial)) if spatial else 1
+    a = _lib.MapStatsArgs()
+    a.struct_size = C.sizeof(_lib.MapStatsArgs)
+    a.stat_flags = int(stats)
+    a.B, a.V = B, V
+    for k, m in enumerate(present):
+        if m is None:
+            continue
+        if m.shape != first.shape or m.dtype != torch.float32 or not m.is_contiguous() or m.device != dev:
+            raise ValueError("maps must be contiguous float32 CUDA tensors of one shape")
+        a.maps[k] = m.data_ptr()
+    if labels is not None:
+        if labels.shape != first.shape or labels.dtype != torch.uint8 or not labels.is_contiguous() or labels.device != dev:
+            raise ValueError("labels must be a contiguous uint8 tensor of the maps' shape")
+        a.labels = labels.data_ptr()
+    with torch.cuda.device(dev):
+        keep = _fill_gt(a.gt, gt, B, spatial)
+        if thresholds is not None:
+            for k in range(3):
+                a.threshold[k] = float(thresholds[k])
+        elif stats & _lib.STAT_THRESHOLD:
+            raise Exception("A threshold needs to be provided for threshold aggregation!")
+        if calib is not None:
+            for k in range(min(3, len(calib))):
+                a.calib[k] = calib[k].as_struct()
+        elif stats & _lib.STAT_CALIB:
+            raise ValueError("STAT_CALIB needs `calib` (three PlattEdges)")
+        if label_lut is not None:
+            a.calib_label_lut = label_lut.data_ptr()
+        if ncc_gt_map is not None:
+            if ncc_gt_map.shape != first.shape or ncc_gt_map.dtype != torch.float64 or not ncc_gt_map.is_contiguous():
+                raise ValueError("ncc_gt_map must be a contiguous float64 tensor of the maps' shape")
+            a.ncc_gt_map = ncc_gt_map.data_ptr()
+        if stats_out is not None:
+            sf, si = stats_out
+        else:
+            sf = torch.zeros((B, F64["COLS"]), dtype=torch.float64, device=dev)
+            si = torch.zeros((B, I64["COLS"]), dtype=torch.int64, device=dev)
+        a.stats_f64, a.stats_i64 = sf.data_ptr(), si.data_ptr()
+        _lib.check(lib.vu_map_stats(C.byref(a), _lib.current_stream_ptr()), "vu_map_stats")
+    del keep
+    return FusedResult(maps={k: m for k, m in zip(UNC_KEYS, present) if m is not None}, labels=labels, stats_f64=sf, stats_i64=si,
+                       n_voxels=V, n_raters=int(a.gt.R) if gt is not None else 0, stat_flags=int(stats))
