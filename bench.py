@@ -47,53 +47,91 @@ def algorithmic_bytes_per_voxel(P, C, R, gt_bytes=1):
 # clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU, sampled by a thread through NVML every ~2 ms (nvidia-smi's 100 ms loop
+    cannot see a 35 ms timed region); falls back to `nvidia-smi -lms 100` when NVML cannot be loaded.  `mark()` brackets
+    the timed region: the reported median is over the samples inside it (the run also keeps the load on for a moment
+    after the region, and says how many samples fell where)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []   # (t, sm_mhz, reasons bitmask)
+        self.marks = []
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
+        self.backend = None
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop_flag:
+            try:
+                reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _smi_loop(self):
+        fields = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={fields}", "--format=csv,noheader,nounits", "-lms", "100",
+                                      "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        bits = (0x8, 0x40, 0x20, 0x4)
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                mask = sum(bit for bit, val in zip(bits, parts[2:6]) if val.lower().startswith("active"))
+                self.samples.append((time.perf_counter(), float(parts[0]), mask))
+                self.max_mhz = float(parts[1])
+            except (ValueError, IndexError):
+                continue
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                                         text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
+            import pynvml as nv
+            nv.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            except Exception:
+                pass
+            h = None
+            if uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.backend = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
         except Exception:
-            self.proc = None
+            self.backend = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def mark(self):
+        self.marks.append(time.perf_counter())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.backend == "nvidia-smi" and getattr(self, "proc", None) is not None:
+            self.proc.terminate()
+        if self.thread is not None:
+            self.thread.join(timeout=5)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no clock samples"], "samples": 0}
+        lo, hi = (self.marks + [None, None])[:2]
+        inside = [s for s in self.samples if lo is not None and hi is not None and lo <= s[0] <= hi]
+        used = inside if len(inside) >= 3 else self.samples
+        sm = sorted(s[1] for s in used)
+        mask = 0
+        for s_ in used:
+            mask |= s_[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(n for b_, n in self.REASONS.items() if mask & b_),
+                "samples": len(used), "samples_inside_timed_region": len(inside), "source": self.backend}
 
 
 # ---------------------------------------------------------------------------
@@ -181,6 +219,17 @@ def cpu_baseline_leg(n_images: int):
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
+def k1_source_digest() -> str:
+    """Digest of the sources the dominant kernel is compiled from: `roofline.traffic` is an ncu measurement of one launch
+    (profiles/k1_traffic.json) and is only reported while the kernel it was taken from is the kernel that runs."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("k1_tma.cu", "k1_core.cuh", "vu_common.cuh", "stats_v2.cuh", "tma_common.cuh"):
+        with open(os.path.join(ROOT, "diffuncertainty_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -204,9 +253,8 @@ def run_ours(args):
 
     import diffuncertainty_b200 as vu
     from diffuncertainty_b200 import _lib, calibration, synth
-    from diffuncertainty_b200.host_pipeline import HostPipeline
-    from diffuncertainty_b200.sweep import exchange, pack_partials
-    from diffuncertainty_b200._lib import F64, I64
+    from diffuncertainty_b200.host_pipeline import HostPipeline, h2d_ceiling_gbs
+    from diffuncertainty_b200.sweep import Partials
 
     w = WORKLOAD
     P, C, S, R = w["P"], w["C"], w["spatial"], w["R"]
@@ -214,32 +262,44 @@ def run_ours(args):
     B = args.images_per_step
     flags = _lib.STAT_IMAGE_SUM | _lib.STAT_THRESHOLD | _lib.STAT_AREA | _lib.STAT_DICE | _lib.STAT_CALIB
     calib = [calibration.platt_edges(a, b) for a, b in w["platt"]]
+    lo, hi = rank * B, (rank + 1) * B
 
     # resident inputs: every rank owns its own block of images (weak scaling)
-    x = synth.synth_slab(P, B, C, S, seed=1234, first_image=rank * B, scale=w["scale"])
-    gt_t = synth.synth_gt(x, R, seed=1234, first_image=rank * B, flip=w["flip"], ignore_frac=w["ignore_frac"],
+    x = synth.synth_slab(P, B, C, S, seed=1234, first_image=lo, scale=w["scale"])
+    gt_t = synth.synth_gt(x, R, seed=1234, first_image=lo, flip=w["flip"], ignore_frac=w["ignore_frac"],
                           ignore_value=w["ignore_index"])
     gt = vu.GroundTruth(gt_t, w["ignore_index"])
     maps = {k: torch.empty((B,) + S, dtype=torch.float32, device=dev) for k in ("TU", "AU", "EU")}
     labels = torch.empty((B,) + S, dtype=torch.uint8, device=dev)
-    rows_f = torch.zeros((B, F64["COLS"]), dtype=torch.float64, device=dev)
-    rows_i = torch.zeros((B, I64["COLS"]), dtype=torch.int64, device=dev)
+    # The rows of ALL images of the job in one int64 buffer per step parity (sweep.Partials): the kernel accumulates straight
+    # into the rows this rank owns, and ONE int64 all-reduce gathers them (exactly: every element has one non-zero
+    # contributor).  Two buffers, so that the exchange of step i runs behind the kernel of step i + 1.
+    parts = [Partials(world * B, dev) for _ in range(2)]
+    works = [None, None]
     k1_events = []
 
-    def step(timed: bool, collective: bool = True):
-        rows_f.zero_()
-        rows_i.zero_()
+    def step(i: int, timed: bool, collective: bool = True):
+        part = parts[i % 2]
+        if works[i % 2] is not None:
+            works[i % 2].wait()  # the stream waits for the exchange that last used this buffer (no host block)
+            works[i % 2] = None
+        part.zero_()
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        vu.fused_pass(x, gt, stats=flags, thresholds=w["thresholds"], calib=calib, stats_out=(rows_f, rows_i),
+        vu.fused_pass(x, gt, stats=flags, thresholds=w["thresholds"], calib=calib, stats_out=part.local(lo, hi),
                       maps_out=maps, labels_out=labels)
         if timed:
             e1.record()
             k1_events.append((e0, e1))
         if world > 1 and collective:
-            ibuf, fbuf = pack_partials(rows_f, rows_i, rank * B, world * B)
-            exchange(ibuf, fbuf)
+            works[i % 2] = part.exchange(async_op=True)
+
+    def drain():
+        for j in range(2):
+            if works[j] is not None:
+                works[j].wait()
+                works[j] = None
 
     def fence():
         torch.cuda.synchronize()
@@ -247,33 +307,38 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step(False)
+    for i in range(args.warmup):
+        step(i, False)
+    drain()
     fence()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.05)
     launches0 = _lib.get_counter("launches")
     tma0 = _lib.get_counter("launches.k1_tma")
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
+    sampler.mark()
     start.record()
-    for _ in range(args.steps):
-        step(True)
+    for i in range(args.steps):
+        step(i, True)
+    drain()  # every exchange of the timed steps has completed before the end event
     end.record()
     fence()
+    sampler.mark()
     launches = _lib.get_counter("launches") - launches0
     kernel_name = ("k1_tma (vu_fused_pass, TMA-pipelined, producer / consumer / statistics warps)"
                    if _lib.get_counter("launches.k1_tma") - tma0 == launches else "k1_fast (vu_fused_pass, register-streaming)")
     ms_total = start.elapsed_time(end)
     k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / max(1, len(k1_events))
-    # keep the GPU busy a little longer so that the 100 ms clock sampler sees it under this load (rank 0 only, so
-    # without the collective: the other ranks are not taking part)
-    if rank == 0:
+    final = parts[(args.steps - 1) % 2]  # the gathered rows of the last timed step
+    # keep the GPU busy a little longer for the fallback sampler (nvidia-smi, 100 ms period); rank 0 only, so without the
+    # collective: the other ranks are not taking part.  Uses the buffer that does not hold the last step's rows.
+    if rank == 0 and sampler.backend != "nvml":
         t_end = time.time() + 1.0
         while time.time() < t_end:
-            step(False, collective=False)
+            step(args.steps, False, collective=False)
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -286,7 +351,7 @@ def run_ours(args):
     # ---- end to end: host buffers through the public host API, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        Be = args.e2e_images
+        Be = min(args.e2e_images, B)
         pipe = HostPipeline(P, C, S, Be, R=R, gt_dtype=torch.uint8, chunk_images=1, n_buffers=3, stats=flags,
                             thresholds=w["thresholds"], platt=w["platt"], ignore_index=w["ignore_index"], device=dev)
         xh = torch.empty((P, Be, C) + S, dtype=torch.float32).pin_memory()
@@ -303,15 +368,49 @@ def run_ours(args):
             r0 = pipe.run(xh, gh)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        fence()
+        ceiling = h2d_ceiling_gbs(xh, dev)  # all ranks at once: what the box's host memory / PCIe delivers to N GPUs
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            t = torch.tensor([dt, -ceiling], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t[0])
+            dt, ceiling = float(t[0]), -float(t[1])
         e2e = {"value": P * V * Be * world * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": r0.h2d_bytes,
-               "d2h_bytes_per_step": r0.d2h_bytes, "images_per_step": Be, "steps": args.e2e_steps,
-               "api": "diffuncertainty_b200.host_pipeline.HostPipeline.run (pinned host slab -> host maps, labels, statistics rows)",
+               "d2h_bytes_per_step": r0.d2h_bytes, "images_per_step": Be, "steps": args.e2e_steps, "seconds": dt,
+               "h2d_GBps_per_gpu": r0.h2d_bytes * args.e2e_steps / dt / 1e9,
+               "h2d_ceiling_GBps_per_gpu": ceiling,
+               "ceiling_note": "plain pinned host -> device copy of the same slab, all ranks at the same time (slowest rank)",
+               "api": "diffuncertainty_b200.host_pipeline.HostPipeline.run (pinned host slab -> host maps, labels, statistics rows; "
+                      "one strided copy per image chunk, 3 chunks in flight)",
                "numa_node_of_rank0": numa_node}
         del pipe, xh, gh
+
+    # ---- parity of the exchanged result with a single-GPU run of the whole job (outside every timed region): rank 0
+    # regenerates the images of EVERY rank (the synthetic source is keyed by the image index), runs them on its own GPU into
+    # a fresh buffer and compares with what the all-reduce of the last timed step delivered
+    parity = None
+    if world > 1:
+        fence()
+        if rank == 0:
+            ref = Partials(world * B, dev)
+            for r in range(world):
+                synth.synth_slab(P, B, C, S, seed=1234, first_image=r * B, scale=w["scale"], out=x)
+                g_r = synth.synth_gt(x, R, seed=1234, first_image=r * B, flip=w["flip"], ignore_frac=w["ignore_frac"],
+                                     ignore_value=w["ignore_index"])
+                vu.fused_pass(x, vu.GroundTruth(g_r, w["ignore_index"]), stats=flags, thresholds=w["thresholds"], calib=calib,
+                              stats_out=ref.local(r * B, (r + 1) * B), want_maps=False, want_labels=False)
+            torch.cuda.synchronize()
+            ints_equal = bool(torch.equal(ref.rows_i, final.rows_i))
+            fa, fb = ref.rows_f.cpu().numpy(), final.rows_f.cpu().numpy()
+            rel = float(np.max(np.abs(fa - fb) / np.maximum(np.abs(fa), 1e-300)))
+            res_a, res_b = ref.result(V, R), final.result(V, R)
+            hist_equal = bool(np.array_equal(res_a.bin_total, res_b.bin_total) and np.array_equal(res_a.bin_true, res_b.bin_true))
+            parity = {"verdict": "bit-exact" if ints_equal and hist_equal and rel <= 1e-12 else "MISMATCH",
+                      "int64_rows_equal": ints_equal, "dataset_histograms_equal": hist_equal, "float64_rows_max_rel_diff": rel,
+                      "images": world * B,
+                      "how": f"rank 0 re-ran the images of all {world} ranks on one GPU; integer rows and dataset-level bin counts "
+                             "compared bit for bit, float64 rows to 1e-12 (their atomics are unordered)"}
+            assert parity["verdict"] == "bit-exact", parity
+        fence()
 
     if rank != 0:
         if world > 1:
@@ -326,26 +425,50 @@ def run_ours(args):
         peak, peak_src = PEAKS_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
     bpv = algorithmic_bytes_per_voxel(P, C, R)
     achieved = bpv * V * B / (k1_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_source = None, None
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.isfile(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic = tj.get("dram_bytes_per_launch_at_images", {}).get(str(B))
-            if traffic is None and tj.get("dram_bytes_per_voxel") is not None:
-                traffic = tj["dram_bytes_per_voxel"] * V * B
+            if tj.get("k1_source_digest") != k1_source_digest():
+                traffic_source = (f"profiles/k1_traffic.json was measured on another version of the kernel (digest "
+                                  f"{tj.get('k1_source_digest')} != {k1_source_digest()}): not reported")
+            else:
+                traffic = tj.get("dram_bytes_per_launch_at_images", {}).get(str(B))
+                if traffic is None and tj.get("dram_bytes_per_voxel") is not None:
+                    traffic = tj["dram_bytes_per_voxel"] * V * B
+                traffic_source = f"profiles/k1_traffic.json ({tj.get('source')}), kernel source digest {tj.get('k1_source_digest')}"
         except Exception:
             traffic = None
+    del x, gt, gt_t, maps, labels
+    torch.cuda.empty_cache()
+
+    # ---- every BASELINE config, named pipeline, CUDA events, same process (bench/bench_configs.py)
+    configs = None
+    if world == 1 and not args.no_configs:
+        sys.path.insert(0, os.path.join(ROOT, "bench"))
+        from bench_configs import time_config
+        configs = []
+        for cid in (1, 2, 3, 4, 5):
+            c = time_config(cid, iters=10, peak=peak)
+            configs.append(c)
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(B), "parallelism": f"images sharded over {world} GPU(s), one int64 + one float64 all-reduce of packed partials per step" if world > 1 else "1 GPU",
+            "config": {"workload": workload_name(B), "parallelism": (f"images sharded over {world} GPU(s); one int64 all-reduce of the per-image rows per step "
+                                                                      "(exact gather), running behind the next step's kernel") if world > 1 else "1 GPU",
                        "l2": "inputs (10.2 GB per GPU at 16 images) are larger than L2; no flush between steps",
                        "bytes_per_voxel": bpv},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": kernel_name, "kernel_ms": k1_ms, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bpv * V * B},
+                         "traffic": traffic, "traffic_source": traffic_source, "kernel": kernel_name, "kernel_ms": k1_ms,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bpv * V * B},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e}
+    if parity is not None:
+        line["multi_gpu_parity"] = parity["verdict"]
+        line["multi_gpu_parity_detail"] = parity
+    if configs is not None:
+        line["configs"] = configs
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(args.cpu_images)
     else:
@@ -386,8 +509,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images-per-step", type=int, default=16)
-    ap.add_argument("--e2e-images", type=int, default=2)
+    ap.add_argument("--e2e-images", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config pipelines (configs[0..4]) in the JSON line")
     ap.add_argument("--cpu-images", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -20,6 +20,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import diffuncertainty_b200 as vu  # noqa: E402
 from diffuncertainty_b200 import _lib, aggregation, calibration, members, synth  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from sweep_k1 import time_call  # noqa: E402
 
 S = _lib
@@ -35,6 +36,73 @@ CONFIGS = {
 }
 
 
+NAMES = {1: "cfg1 toy 2-D TTA: N=10, C=2, 256x256, B=256; maps + labels + image-level mean",
+         2: "cfg2 LIDC 3-D ensemble: N=5, C=2, 64^3, R=4, B=128; maps + labels + image sums / area / Dice / ACE histograms, patch-level 10^3 box on TU, AU, EU",
+         3: "cfg3 GTA5 HRNet TTA: N=10, C=19, 1024x2048, R=5 with 2% ignore(255), B=4; maps + labels + image / threshold / area / Dice counts (AURC inputs)",
+         4: "cfg4 diffusion multi-rater: N=32, C=2, 128x128, R=4, B=1024; maps + labels + image sums + NCC sums; GED counts + likelihood sums",
+         5: "cfg5 sharded sweep: N=16, C=19, 512x1024, R=1 with 2% ignore(255), B=16; maps + labels + image / threshold / area / Dice / ECE-ACE histograms"}
+
+
+def time_config(cid: int, iters: int = 10, peak: float = 6532.2) -> dict:
+    """The named pipeline of BASELINE config `cid` on resident synthetic inputs, stage by stage with CUDA events."""
+    platt = [calibration.platt_edges(a, b) for a, b in ((3.5, -1.25), (6.0, -2.0), (40.0, -0.5))]
+    cfg = CONFIGS[cid]
+    P, C, B, R, spatial = cfg["P"], cfg["C"], cfg["B"], cfg["R"], cfg["spatial"]
+    x = synth.synth_slab(P, B, C, spatial, seed=cid, scale=3.0)
+    V = x[0, 0, 0].numel()
+    gt = None
+    if R:
+        gt = vu.GroundTruth(synth.synth_gt(x, R, seed=cid, flip=0.2, ignore_frac=0.02 if cfg["ignore"] is not None else 0.0,
+                                           ignore_value=cfg["ignore"] if cfg["ignore"] is not None else 255), cfg["ignore"])
+    sf = torch.zeros((B, 80), dtype=torch.float64, device="cuda")
+    si = torch.zeros((B, 156), dtype=torch.int64, device="cuda")
+    # the three maps are views of one buffer, so that patch-level aggregation takes all of them in one call (3 B "images")
+    maps3 = torch.empty((3, B) + tuple(spatial), dtype=torch.float32, device="cuda")
+    maps = {k: maps3[i] for i, k in enumerate(("TU", "AU", "EU"))}
+    labels = torch.empty((B,) + tuple(spatial), dtype=torch.uint8, device="cuda")
+    flags = cfg["flags"]
+    ms_out = members.MemberScoreBuffers(P, B, R, x.device) if cfg["members"] and hasattr(members, "MemberScoreBuffers") else None
+
+    def fused():
+        vu.fused_pass(x, gt, stats=flags, thresholds=[0.3, 0.2, 0.02], calib=platt if flags & S.STAT_CALIB else None,
+                      stats_out=(sf, si), maps_out=maps, labels_out=labels)
+
+    stages = {}
+    bytes_alg = (4 * P * C + 13 + R) * V * B
+    if cfg["members"] and hasattr(vu, "fused_pass_with_member_scores"):
+        def fused_ms():
+            vu.fused_pass_with_member_scores(x, gt, stats=flags, stats_out=(sf, si), maps_out=maps, labels_out=labels, out=ms_out)
+
+        stages["vu_fused_pass + member scores (one slab read)"] = time_call(fused_ms, iters=iters)
+        stages["(vu_fused_pass alone)"] = time_call(fused, iters=iters)
+    else:
+        stages["vu_fused_pass"] = time_call(fused, iters=iters)
+        if cfg["members"]:
+            def member_scores():
+                members.member_scores(x, gt, nll=True, ged=True, mean_labels=labels)
+
+            stages["vu_member_scores"] = time_call(member_scores, iters=iters)
+    if cfg["patch"]:
+        dims = [1] * (3 - len(spatial)) + list(spatial)
+
+        def patch():
+            aggregation.patch_level_batched(maps3.reshape(3 * B, *dims), cfg["patch"])
+
+        stages["vu_patch_max_ws (TU, AU, EU in one call)"] = time_call(patch, iters=iters)
+    total = sum(v for k, v in stages.items() if not k.startswith("("))
+    first = next(iter(stages.values()))
+    fused_ms_only = stages.get("(vu_fused_pass alone)", stages.get("vu_fused_pass", first))
+    line = {"workload": NAMES[cid], "config": f"cfg{cid}", "stat_flags": hex(flags),
+            "stages_ms": {k: round(v, 4) for k, v in stages.items()}, "ms": round(total, 4),
+            "algorithmic_bytes": bytes_alg, "GBps": round(bytes_alg / total / 1e6, 1), "frac": round(bytes_alg / total / 1e6 / peak, 3),
+            "fused_pass_ms": round(fused_ms_only, 4), "fused_pass_GBps": round(bytes_alg / fused_ms_only / 1e6, 1),
+            "fused_pass_frac": round(bytes_alg / fused_ms_only / 1e6 / peak, 3),
+            "sample_voxels_per_s": round(P * V * B / total * 1e3, 1), "peak_GBps": peak}
+    del x, gt, maps, maps3, labels
+    torch.cuda.empty_cache()
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,2,3,4,5")
@@ -44,51 +112,8 @@ def main():
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.isfile(pk):
         peak = float(json.load(open(pk))["hbm_gbs"])
-    platt = [calibration.platt_edges(a, b) for a, b in ((3.5, -1.25), (6.0, -2.0), (40.0, -0.5))]
     for cid in [int(c) for c in args.configs.split(",")]:
-        cfg = CONFIGS[cid]
-        P, C, B, R, spatial = cfg["P"], cfg["C"], cfg["B"], cfg["R"], cfg["spatial"]
-        x = synth.synth_slab(P, B, C, spatial, seed=cid, scale=3.0)
-        V = x[0, 0, 0].numel()
-        gt = None
-        if R:
-            gt = vu.GroundTruth(synth.synth_gt(x, R, seed=cid, flip=0.2, ignore_frac=0.02 if cfg["ignore"] is not None else 0.0,
-                                               ignore_value=cfg["ignore"] if cfg["ignore"] is not None else 255), cfg["ignore"])
-        sf = torch.zeros((B, 80), dtype=torch.float64, device="cuda")
-        si = torch.zeros((B, 156), dtype=torch.int64, device="cuda")
-        # the three maps are views of one buffer, so that patch-level aggregation takes all of them in one call (3 B "images")
-        maps3 = torch.empty((3, B) + tuple(spatial), dtype=torch.float32, device="cuda")
-        maps = {k: maps3[i] for i, k in enumerate(("TU", "AU", "EU"))}
-        labels = torch.empty((B,) + tuple(spatial), dtype=torch.uint8, device="cuda")
-        flags = cfg["flags"]
-
-        def fused():
-            vu.fused_pass(x, gt, stats=flags, thresholds=[0.3, 0.2, 0.02], calib=platt if flags & S.STAT_CALIB else None,
-                          stats_out=(sf, si), maps_out=maps, labels_out=labels)
-
-        stages = {"vu_fused_pass": time_call(fused, iters=args.iters)}
-        bytes_alg = (4 * P * C + 13 + R) * V * B
-        if cfg["patch"]:
-            dims = [1] * (3 - len(spatial)) + list(spatial)
-
-            def patch():
-                aggregation.patch_level_batched(maps3.reshape(3 * B, *dims), cfg["patch"])
-
-            stages["vu_patch_max_ws (TU, AU, EU in one call)"] = time_call(patch, iters=args.iters)
-        if cfg["members"]:
-            def member_scores():
-                members.member_scores(x, gt, nll=True, ged=True, mean_labels=labels)
-
-            stages["vu_member_scores"] = time_call(member_scores, iters=args.iters)
-        total = sum(stages.values())
-        line = {"config": f"cfg{cid}", "P": P, "C": C, "spatial": list(spatial), "B": B, "R": R, "stat_flags": hex(flags),
-                "stages_ms": {k: round(v, 4) for k, v in stages.items()}, "total_ms": round(total, 4),
-                "algorithmic_bytes": bytes_alg, "fused_pass_GBps": round(bytes_alg / stages["vu_fused_pass"] / 1e6, 1),
-                "fused_pass_frac_of_peak": round(bytes_alg / stages["vu_fused_pass"] / 1e6 / peak, 3),
-                "pipeline_GBps": round(bytes_alg / total / 1e6, 1), "pipeline_frac_of_peak": round(bytes_alg / total / 1e6 / peak, 3),
-                "sample_voxels_per_s": round(P * V * B / total * 1e3, 1), "peak_GBps": peak}
-        print(json.dumps(line), flush=True)
-        del x, gt, maps, maps3, labels
+        print(json.dumps(time_config(cid, args.iters, peak)), flush=True)
 
 
 if __name__ == "__main__":

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--configs", default="2,4")
     ap.add_argument("--variants", default="-1")
     ap.add_argument("--stages", default="0")
+    ap.add_argument("--shapes", default="0", help="k1_uni_shape values (CT * 100 + G * 10 + MINB), 0 = automatic")
     ap.add_argument("--flags", default=None)
     ap.add_argument("--iters", type=int, default=10)
     args = ap.parse_args()
@@ -39,7 +40,8 @@ def main():
         for flags in ([cfg["flags"]] if args.flags is None else [int(f, 0) for f in args.flags.split(",")]):
             ref = None
             for var in [int(v) for v in args.variants.split(",")]:
-                for stages in [int(s) for s in args.stages.split(",")]:
+                for stages, shape in [(int(s), int(h)) for s in args.stages.split(",") for h in (args.shapes.split(",") if var == -3 else ["0"])]:
+                    _lib.set_option("k1_uni_shape", shape)
                     _lib.set_option("k1_path", 1 if var == -1 else (0 if var == -3 else 2))  # -1 registers, -3 automatic, >= 0 that TMA variant
                     _lib.set_option("k1_tma_variant", var if var >= 0 else -1)
                     _lib.set_option("k1_tma_stages", stages)
@@ -55,7 +57,7 @@ def main():
                         cur = (si.clone(), sf.clone())
                         ms = time_call(run, iters=args.iters)
                     except Exception as exc:
-                        print(f"cfg{cid} flags={flags:#04x} var={var} stages={stages}: {str(exc)[:150]}", flush=True)
+                        print(f"cfg{cid} flags={flags:#04x} var={var} stages={stages} shape={shape}: {str(exc)[:150]}", flush=True)
                         continue
                     same = ""
                     if ref is None:
@@ -64,11 +66,12 @@ def main():
                         same = " ints==" + str(bool(torch.equal(ref[0], cur[0]))) + \
                                f" fmaxrel={float(((ref[1] - cur[1]).abs() / ref[1].abs().clamp_min(1e-30)).max()):.1e}"
                     bpv = 4 * P * C + 13 + (R if flags & 0x78 else 0)
-                    print(f"cfg{cid} flags={flags:#04x} var={var:3d} stages={stages}: {ms:8.4f} ms  {bpv * V * B / ms / 1e6:7.1f} GB/s "
+                    print(f"cfg{cid} flags={flags:#04x} var={var:3d} stages={stages} shape={shape:5d}: {ms:8.4f} ms  {bpv * V * B / ms / 1e6:7.1f} GB/s "
                           f"({bpv * V * B / ms / 1e6 / 6532.2:.3f}){same}", flush=True)
         _lib.set_option("k1_path", 0)
         _lib.set_option("k1_tma_variant", -1)
         _lib.set_option("k1_tma_stages", 0)
+        _lib.set_option("k1_uni_shape", 0)
         del x, gt
         torch.cuda.empty_cache()
 

@@ -97,6 +97,7 @@ EXPORTS = {
                                 C.c_float, C.c_void_p]),
     "vu_synth_gt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                               C.c_uint64, C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
+    "vu_copy_2d_async": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
     "vu_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
     "vu_get_counter": (C.c_int64, [C.c_char_p]),
 }

@@ -377,6 +377,18 @@ int vu_synth_gt(uint8_t* out, const float* slab, int64_t P, int64_t B, int64_t C
     return launch_synth_gt(out, slab, P, B, C, V, R, seed, first_image, flip, ignore_frac, ignore_value, (cudaStream_t)stream);
 }
 
+int vu_copy_2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width, int64_t height, int32_t kind,
+                     void* stream) {
+    if (!dst || !src) return set_error(VU_ERR_BAD_ARG, "NULL pointer");
+    if (width < 0 || height < 0 || dst_pitch < width || src_pitch < width) return set_error(VU_ERR_BAD_ARG, "bad width / height / pitch");
+    if (kind != 1 && kind != 2) return set_error(VU_ERR_BAD_ARG, "kind must be 1 (host -> device) or 2 (device -> host)");
+    if (width == 0 || height == 0) return VU_OK;
+    if (cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width, (size_t)height,
+                          kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess)
+        return set_cuda_error("cudaMemcpy2DAsync");
+    return VU_OK;
+}
+
 int vu_set_option(const char* key, int64_t value) {
     if (!key) return set_error(VU_ERR_BAD_ARG, "key is NULL");
     std::lock_guard<std::mutex> lk(g_mu);

@@ -163,18 +163,64 @@ struct VoxelAcc {
     __device__ __forceinline__ void finish(float Pf, float (&u)[VU_N_UNC][VEC], int (&label)[VEC]) const {
         const bool fast_div = Pf <= 271.0f;
         const float rP = __frcp_rn(Pf);
-        auto mean_of = [&](float s) { return fast_div ? div_by_count(s, Pf, rP) : __fdiv_rn(s, Pf); };
-        float mean[C][VEC], asum[VEC], tu2[VEC];
+        // The sums of all classes first, then ONE test whether every one of them is in the range where the two-FMA division
+        // is exact (zero is: it stays zero); the IEEE division is the rare, warp-divergent fallback for the whole thread.
+        // (A range test with a branch per value cost more than the division itself: 8 branchy values per thread for C = 2.)
+        float sums[C * VEC], asum[VEC];
+#pragma unroll
+        for (int e = 0; e < NP; ++e) {
+            const f32x2 S = (LEVELS > 1) ? add2(m0[e], m1[e < NP1 ? e : 0]) : m0[e];
+            upk2(S, sums[2 * e], sums[2 * e + 1]);
+        }
+        if constexpr (ODD) sums[E - 1] = (LEVELS > 1) ? __fadd_rn(m0s, m1s) : m0s;
+        if constexpr (VEC >= 2) {
+#pragma unroll
+            for (int q = 0; q < NH; ++q) {
+                const f32x2 A = (LEVELS > 1) ? add2(a0[q], a1[q]) : a0[q];
+                upk2(A, asum[2 * q], asum[2 * q + 1]);
+            }
+        } else {
+            asum[0] = (LEVELS > 1) ? __fadd_rn(a0s, a1s) : a0s;
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) asum[k] = -(asum[k] * kLn2);
+        bool exact = fast_div;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const float a = fabsf(sums[e]);
+            exact = exact && ((a > 1e-30f && a < 1e30f) || sums[e] == 0.0f);
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float a = fabsf(asum[k]);
+            exact = exact && ((a > 1e-30f && a < 1e30f) || asum[k] == 0.0f);
+        }
+        float qs[C * VEC], au[VEC];
+        if (exact) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const float q = __fmul_rn(sums[e], rP);
+                qs[e] = __fmaf_rn(__fmaf_rn(-q, Pf, sums[e]), rP, q);
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const float q = __fmul_rn(asum[k], rP);
+                au[k] = __fmaf_rn(__fmaf_rn(-q, Pf, asum[k]), rP, q);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) qs[e] = __fdiv_rn(sums[e], Pf);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) au[k] = __fdiv_rn(asum[k], Pf);
+        }
+        float mean[C][VEC], tu2[VEC];
         f32x2 T[NH];  // TU sums (VEC >= 2: packed over voxels, like the member entropies)
 #pragma unroll
         for (int q = 0; q < NH; ++q) T[q] = 0ull;
         float ts = 0.f;
 #pragma unroll
         for (int e = 0; e < NP; ++e) {
-            const f32x2 S = (LEVELS > 1) ? add2(m0[e], m1[e < NP1 ? e : 0]) : m0[e];
-            float s0, s1;
-            upk2(S, s0, s1);
-            const float q0 = mean_of(s0), q1 = mean_of(s1);
+            const float q0 = qs[2 * e], q1 = qs[2 * e + 1];
             mean[(2 * e) / VEC][(2 * e) % VEC] = q0;
             mean[(2 * e + 1) / VEC][(2 * e + 1) % VEC] = q1;
             f32x2 PC, L;
@@ -190,18 +236,13 @@ struct VoxelAcc {
             }
         }
         if constexpr (ODD) {
-            mean[C - 1][0] = mean_of((LEVELS > 1) ? __fadd_rn(m0s, m1s) : m0s);
+            mean[C - 1][0] = qs[E - 1];
             ts = plog2p_acc(ts, mean[C - 1][0]);
         }
         if constexpr (VEC >= 2) {
 #pragma unroll
-            for (int q = 0; q < NH; ++q) {
-                const f32x2 A = (LEVELS > 1) ? add2(a0[q], a1[q]) : a0[q];
-                upk2(A, asum[2 * q], asum[2 * q + 1]);
-                upk2(T[q], tu2[2 * q], tu2[2 * q + 1]);
-            }
+            for (int q = 0; q < NH; ++q) upk2(T[q], tu2[2 * q], tu2[2 * q + 1]);
         } else {
-            asum[0] = (LEVELS > 1) ? __fadd_rn(a0s, a1s) : a0s;
             tu2[0] = ts;
         }
 #pragma unroll
@@ -211,8 +252,7 @@ struct VoxelAcc {
 #pragma unroll
             for (int c = 1; c < C; ++c) argmax_step(mean[c][k], c, best, idx);
             const float tu = -(tu2[k] * kLn2);
-            const float au = (-(asum[k] * kLn2)) / Pf;
-            u[0][k] = tu; u[1][k] = au; u[2][k] = tu - au;
+            u[0][k] = tu; u[1][k] = au[k]; u[2][k] = tu - au[k];
             label[k] = idx;
         }
     }

@@ -43,8 +43,9 @@ constexpr int kUniRep = 16;  // histogram replicas per warp (two lanes share one
 
 // LEVELS: cascade levels of the member sum (1: P <= 17, 2: P <= 271); CT consumer threads; G members per ring stage;
 // FL: the statistics mask (compile time); RMAX: raters the reference registers are sized for.
-template <int LEVELS, int CT, int G, unsigned FL, int RMAX>
-__global__ void __launch_bounds__(CT + 32, 1) k1_uni(const __grid_constant__ K1UniParams prm) {
+// MINB: CTAs per SM (each with its own producer warp, ring and histograms: independent pipelines that fill each other's gaps).
+template <int LEVELS, int CT, int G, unsigned FL, int RMAX, int MINB>
+__global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ K1UniParams prm) {
     constexpr int C = 2, VEC = 4;
     constexpr int TV = CT * VEC;  // voxels per tile
     constexpr unsigned kRowBytes = TV * sizeof(float);
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(CT + 32, 1) k1_uni(const __grid_constant__ K1U
             for (int fi = 0; fi < fills; ++fi) {
                 const int p0 = fi * G;
                 const int nrows = ((P - p0) < G ? (int)(P - p0) : G) * C;
-                mbar_wait(empty0 + 8 * stage, phase ^ 1);  // slot free (the first pass falls through)
+                mbar_wait_hint(empty0 + 8 * stage, phase ^ 1, 4000u);  // slot free (the first pass falls through)
                 if (lane == 0) mbar_arrive_expect_tx(full0 + 8 * stage, (unsigned)nrows * row_bytes);
                 __syncwarp();
                 const unsigned dst0 = smem_u32(ring) + (unsigned)stage * kStageBytes;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(CT + 32, 1) k1_uni(const __grid_constant__ K1U
     const int warp = tid >> 5;
     const float Pf = (float)P;
     Stat2Ctx cx;
-    stats2_ctx<kUniRep>(cx, sp, st_smem, warp, kWarps);
+    stats2_ctx<kUniRep, (CT + 32 <= 512)>(cx, sp, st_smem, warp, kWarps);  // more than 16 warps: 96 registers per thread
     const bool rot = stats2_rotated<kUniRep>();
     StatAcc<FL, RMAX> A;
     A.clear();
@@ -124,25 +125,33 @@ __global__ void __launch_bounds__(CT + 32, 1) k1_uni(const __grid_constant__ K1U
     };
 
     int b = t0 / tpi, vt = t0 - b * tpi - 1;
-    int stage = 0;
+    unsigned stage_off = 0u;  // byte offset of the current stage inside the ring
+    unsigned full_bar = full0, empty_bar = empty0;
     unsigned phase = 0;
+    const unsigned ring_end = (unsigned)nstages * kStageBytes;
+    const unsigned my_ring = smem_u32(ring) + (unsigned)tid * (VEC * (unsigned)sizeof(float));
+    const bool want_ml = prm.mlab != nullptr;
+    long long img_out = 0;       // b * V: offset of the image in the (B, V) outputs
+    const uint8_t* gt_img = nullptr;  // references of the image
     for (int tile = t0; tile < t1; ++tile) {
         if (++vt == tpi) { vt = 0; ++b; }
-        if (b != cur_b || (vt - vt_begin) * VEC >= kMaxVoxPerFlush) {  // warp-uniform
+        if (b != cur_b || vt - vt_begin >= kMaxTilesPerFlush2) {  // warp-uniform
             if (cur_b >= 0) flush();
             cur_b = b;
             vt_begin = vt;
+            img_out = (long long)b * V;
+            gt_img = reinterpret_cast<const uint8_t*>(sp.gt.data) + (long long)b * sp.gt.sb;
         }
         const long long v = (long long)vt * TV + (long long)tid * VEC;
         const bool active = v < V;
         unsigned W[RMAX];
-        stats2_load_refs<FL, RMAX>(sp, active, b, v, W);  // in flight while the members stream
+        stats2_load_refs<FL, RMAX>(sp, active, gt_img, v, W);  // in flight while the members stream
 
         Acc acc;
         acc.init();
         for (int fi = 0; fi < fills; ++fi) {
-            mbar_wait(full0 + 8 * stage, phase);  // the bytes of this stage have landed
-            const float* sbase = ring + (size_t)stage * kStageFloats + tid * VEC;
+            mbar_wait(full_bar, phase);  // the bytes of this stage have landed
+            const unsigned sbase = my_ring + stage_off;
             // (a partial last tile leaves stale bytes behind the image's end: those threads are inactive and
             //  their arithmetic is discarded)
             const int p0 = fi * G;
@@ -150,20 +159,17 @@ __global__ void __launch_bounds__(CT + 32, 1) k1_uni(const __grid_constant__ K1U
             for (int g = 0; g < G; ++g) {
                 if (G == 1 || p0 + g < P) {
                     f32x2 xp[Acc::NP];
-                    const float* srow = sbase + (size_t)g * C * TV;
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const float4 w = *reinterpret_cast<const float4*>(srow + c * TV);
-                        xp[c * 2] = pk2(w.x, w.y);
-                        xp[c * 2 + 1] = pk2(w.z, w.w);
-                    }
-                    acc.add_member(xp, 0.f, p0 + g, prm.mlab != nullptr);
-                    if (prm.mlab && active) VecLoad<VEC>::store_u8(prm.mlab + ((long long)(p0 + g) * prm.B + b) * V + v, acc.bi);
+                    for (int c = 0; c < C; ++c)
+                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xp[c * 2]), "=l"(xp[c * 2 + 1]) : "r"(sbase + (unsigned)((g * C + c) * kRowBytes)));
+                    acc.add_member(xp, 0.f, p0 + g, want_ml);
+                    if (want_ml && active) VecLoad<VEC>::store_u8(prm.mlab + ((long long)(p0 + g) * prm.B + b) * V + v, acc.bi);
                 }
             }
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(empty0 + 8 * stage);  // this warp is done reading the stage
-            if (++stage == nstages) { stage = 0; phase ^= 1; }
+            if ((tid & 31) == 0) mbar_arrive(empty_bar);  // this warp is done reading the stage
+            stage_off += kStageBytes; full_bar += 8; empty_bar += 8;
+            if (stage_off == ring_end) { stage_off = 0u; full_bar = full0; empty_bar = empty0; phase ^= 1; }
         }
 
         float u[VU_N_UNC][VEC];
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(CT + 32, 1) k1_uni(const __grid_constant__ K1U
         for (int k = 0; k < VEC; ++k) { u[0][k] = u[1][k] = u[2][k] = 0.f; label[k] = 0; }
         if (active) {
             acc.finish(Pf, u, label);
-            const long long o = (long long)b * V + v;
+            const long long o = img_out + v;
             if (prm.tu) VecLoad<VEC>::store(prm.tu + o, u[0]);
             if (prm.au) VecLoad<VEC>::store(prm.au + o, u[1]);
             if (prm.eu) VecLoad<VEC>::store(prm.eu + o, u[2]);
@@ -198,20 +204,27 @@ typedef void (*K1UniKernel)(const K1UniParams);
 struct UniVariant {
     int LEVELS, CT, G;
     unsigned FL;
-    int RMAX;
+    int RMAX, MINB;
+    int use;  // 1: automatic selection, 0: only through the "k1_uni_shape" option (tuning sweep)
     K1UniKernel fn;
 };
-#define VU_UNI(LEVELS, CT, G, FL, RMAX) { LEVELS, CT, G, FL, RMAX, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX> }
+#define VU_UNI(LEVELS, CT, G, FL, RMAX, MINB, USE) { LEVELS, CT, G, FL, RMAX, MINB, USE, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX, MINB> }
 // Registers are allocated per SM sub-partition: 16 consumer warps + the producer put 5 warps on one of them (96 registers per
 // thread), 15 + 1 leave 4 on each (128).  The masks with calibration histograms need the 128 (they spill 260-720 bytes at
 // 96); the others do not, and keep the power-of-two tile.
-#define VU_UNI_MASKS(LEVELS, G)                                                                                                      \
-    VU_UNI(LEVELS, 512, G, 0x0du, 4), VU_UNI(LEVELS, 512, G, 0x0fu, 4), VU_UNI(LEVELS, 480, G, 0x1du, 4), VU_UNI(LEVELS, 480, G, 0x1fu, 4), \
-    VU_UNI(LEVELS, 512, G, 0x21u, 4), VU_UNI(LEVELS, 480, G, 0x3fu, 4), VU_UNI(LEVELS, 480, G, 0x3fu, 8)
+#define VU_UNI_MASKS(LEVELS, G)                                                                                                              \
+    VU_UNI(LEVELS, 512, G, 0x0du, 4, 1, 1), VU_UNI(LEVELS, 512, G, 0x0fu, 4, 1, 1), VU_UNI(LEVELS, 480, G, 0x1du, 4, 1, 1),                   \
+    VU_UNI(LEVELS, 480, G, 0x1fu, 4, 1, 1), VU_UNI(LEVELS, 512, G, 0x21u, 4, 1, 1), VU_UNI(LEVELS, 480, G, 0x3fu, 4, 1, 1),                   \
+    VU_UNI(LEVELS, 480, G, 0x3fu, 8, 1, 1)
 
+// Two members per ring stage: a stage costs ~20 instructions of waiting, releasing and bookkeeping per warp whatever it
+// holds (r02e, configs[1]: one member per stage 0.465 ms, two 0.450 ms; two CTAs of 7 + 1 warps per SM 0.53 ms, 11 + 1 warps
+// 0.57 ms, 16 + 1 or 19 + 1 warps at 96 registers 0.61-0.64 ms -- they spill).
 static const UniVariant kUni[] = {
-    VU_UNI_MASKS(1, 1),
+    VU_UNI_MASKS(1, 2),
     VU_UNI_MASKS(2, 2),
+    // tuning candidates ("k1_uni_shape" = CT * 100 + G * 10 + MINB)
+    VU_UNI(1, 480, 1, 0x1du, 4, 1, 0), VU_UNI(1, 480, 3, 0x1du, 4, 1, 0),
 };
 static const int kNumUni = (int)(sizeof(kUni) / sizeof(kUni[0]));
 
@@ -238,9 +251,13 @@ int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     const int need_levels = s.P <= 17 ? 1 : 2;
     const int rmax = (st.flags & heavy) && st.gt.R > 4 ? 8 : 4;
     const UniVariant* pick = nullptr;
-    for (int i = 0; i < kNumUni && !pick; ++i)
-        if (kUni[i].LEVELS == need_levels && kUni[i].FL == st.flags && kUni[i].RMAX >= rmax) pick = &kUni[i];
-    if (!pick) return 1;
+    const long long shape = get_option("k1_uni_shape", 0);
+    for (int i = 0; i < kNumUni && !pick; ++i) {
+        const UniVariant& u = kUni[i];
+        if (u.LEVELS != need_levels || u.FL != st.flags || u.RMAX < rmax) continue;
+        if (shape ? (u.CT * 100 + u.G * 10 + u.MINB == shape) : u.use == 1) pick = &u;
+    }
+    if (!pick) return shape ? set_error(VU_ERR_UNSUPPORTED, "k1_uni_shape: no such kernel for this launch") : 1;
 
     K1UniParams prm;
     prm.x = s.data;
@@ -257,7 +274,7 @@ int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t str
 
     const size_t stage_bytes = (size_t)pick->G * 2 * tile_vox * sizeof(float);
     const size_t stats_bytes = stats2_smem_bytes(st.flags, pick->CT, kUniRep);
-    const size_t budget = 227 * 1024;
+    const size_t budget = (pick->MINB == 1 ? 227 : (pick->MINB == 2 ? 113 : 75)) * 1024 - (pick->MINB > 1 ? 1024 : 0);  // per CTA (1 KB reserved per CTA)
     const size_t fixed = 256 /* barriers */ + 256 /* alignment slack */ + stats_bytes;
     long long nstages = get_option("k1_tma_stages", 0);
     const long long fit = fixed < budget ? (long long)((budget - fixed) / stage_bytes) : 0;
@@ -274,7 +291,7 @@ int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t str
 
     if (cudaFuncSetAttribute(pick->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
         return set_cuda_error("cudaFuncSetAttribute(k1_uni)");
-    long long grid = device_sm_count();
+    long long grid = (long long)device_sm_count() * pick->MINB;
     if (grid > prm.total_tiles) grid = prm.total_tiles;
     pick->fn<<<(unsigned)grid, pick->CT + 32, dyn, stream>>>(prm);
     count_launch("k1_uni");

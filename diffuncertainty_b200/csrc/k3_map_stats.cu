@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kK3v2Threads) k3_map_stats_v2(const __grid_con
     };
     for (int tile = t0; tile < t1; ++tile) {
         if (++vt == tpi) { vt = 0; ++b; }
-        if (b != cur_b || (vt - vt_begin) * 4 >= kMaxVoxPerFlush) {
+        if (b != cur_b || vt - vt_begin >= kMaxTilesPerFlush2) {
             if (cur_b >= 0) flush();
             cur_b = b;
             vt_begin = vt;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kK3v2Threads) k3_map_stats_v2(const __grid_con
             lab4 = __ldg(reinterpret_cast<const unsigned*>(prm.labels + o));
         }
         unsigned W[RMAX];
-        stats2_load_refs<FL, RMAX>(sp, active, b, v, W);
+        stats2_load_refs<FL, RMAX>(sp, active, reinterpret_cast<const uint8_t*>(sp.gt.data) + (long long)b * sp.gt.sb, v, W);
         stats2_tile<FL, RMAX, kK3v2Rep>(A, sp, cx, active, b, U[0], U[1], U[2], lab4, W);
     }
     if (cur_b >= 0) flush();

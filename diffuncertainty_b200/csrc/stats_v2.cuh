@@ -27,6 +27,9 @@ constexpr unsigned kMagicBits = 0x4B400000u;  // bit pattern of kRoundMagic (1.5
 // that is q + kYBias (mod 2^32); the flush subtracts samples * kYBias again
 constexpr unsigned kYBias = kMagicBits - kMagicBits * (unsigned)kQBinStep;
 constexpr int kBins2 = kHistBins;  // 20 bins per type and replica (NaN / inf samples never reach the histogram)
+// tiles (of four voxels per thread) a thread may go through between two flushes: the Dice counters are byte-sliced (one
+// count per voxel position and byte, no popc while streaming), the histogram words hold 16-bit counts of two lanes x 8 raters
+constexpr int kMaxTilesPerFlush2 = 255;
 
 template <unsigned FL>
 struct StatFlags {
@@ -53,7 +56,7 @@ struct StatAcc {
     double thr[F::thr ? 3 : 1];
     unsigned thrn[F::thr ? 3 : 1];
     unsigned area, nvox;
-    unsigned tp[F::dice ? RMAX : 1], ps[F::dice ? RMAX : 1], gs[F::dice ? RMAX : 1];
+    unsigned tp[F::dice ? RMAX : 1], ps[F::dice ? RMAX : 1], gs[F::dice ? RMAX : 1];  // byte j: count of voxel position j
     double bin0[F::calib ? 3 : 1];
     double n1, n2, uu[F::ncc ? 3 : 1], nu[F::ncc ? 3 : 1];  // NCC with n = R sum g^2 - (sum g)^2 = R^2 var(g)
     __device__ __forceinline__ void clear() {
@@ -143,7 +146,9 @@ __device__ __forceinline__ void stats2_init(const StatParams& sp, void* smem, in
 }
 
 // warp = index of the caller's warp among the `warps` statistics warps
-template <int REP>
+// PIN_ALL = false leaves the Platt constants and thresholds to the compiler (it re-reads them from the constant bank with a
+// computed index): 12 registers less for kernels that are short of them.
+template <int REP, bool PIN_ALL = true>
 __device__ __forceinline__ void stats2_ctx(Stat2Ctx& cx, const StatParams& sp, void* smem, int warp, int warps) {
     uint2* hist = reinterpret_cast<uint2*>(smem);
     const int nh = warps * (VU_N_UNC * kBins2 * REP);
@@ -162,7 +167,8 @@ __device__ __forceinline__ void stats2_ctx(Stat2Ctx& cx, const StatParams& sp, v
         cx.hbase[s] = (unsigned)__cvta_generic_to_shared(hist + (warp * VU_N_UNC + k) * (kBins2 * REP) + (lane & (REP - 1))) -
                       sp.magic_bits * (unsigned)(REP * 8);
         // pin the values: without this the compiler re-derives them from the kernel parameters inside the tile loop
-        asm volatile("" : "+f"(cx.sgn[s]), "+f"(cx.a2s[s]), "+f"(cx.b2[s]), "+f"(cx.thr[s]), "+r"(cx.ebase[s]), "+r"(cx.hbase[s]));
+        if (PIN_ALL) asm volatile("" : "+f"(cx.sgn[s]), "+f"(cx.a2s[s]), "+f"(cx.b2[s]), "+f"(cx.thr[s]));
+        asm volatile("" : "+r"(cx.ebase[s]), "+r"(cx.hbase[s]));
     }
 }
 
@@ -233,18 +239,22 @@ __device__ __noinline__ double calib2_slow(const StatParams& sp, int k, float x,
     return bb == kMagicBits ? (double)conf * (double)nv : 0.0;
 }
 
-// The reference words of the four voxels v .. v + 3 of image b, one per rater (zero past the last rater).  Issued early by
+// The reference words of the four voxels v .. v + 3 of an image, one per rater (zero past the last rater).  Issued early by
 // the kernels that can (the latency of the load then hides behind their streaming phase).
 template <unsigned FL, int RMAX>
-__device__ __forceinline__ void stats2_load_refs(const StatParams& sp, bool active, long long b, long long v, unsigned (&W)[RMAX]) {
+__device__ __forceinline__ void stats2_load_refs(const StatParams& sp, bool active, const uint8_t* gt_img, long long v, unsigned (&W)[RMAX]) {
+    // gt_img: references of the image (gt.data + b * gt.stride_b; the kernels keep it per image instead of forming the
+    // 64-bit product for every tile)
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) W[r] = 0u;
     if (StatFlags<FL>::refs && active) {
         const int R = sp.gt.R;
-        const uint8_t* gp = reinterpret_cast<const uint8_t*>(sp.gt.data) + b * sp.gt.sb + v;
+        const uint8_t* gp = gt_img + v;
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-            if (r < R) W[r] = __ldg(reinterpret_cast<const unsigned*>(gp + (long long)r * sp.gt.sr));
+        for (int r = 0; r < RMAX; ++r) {
+            if (r < R) W[r] = __ldg(reinterpret_cast<const unsigned*>(gp));
+            gp += sp.gt.sr;
+        }
     }
 }
 
@@ -302,24 +312,24 @@ __device__ __forceinline__ void stats2_tile(StatAcc<FL, RMAX>& A, const StatPara
                         if (F::dice) {
                             const unsigned gp_hi = ~bytes_nonzero(W[r] ^ kB01) & valid_hi;  // test_2D.py:882
                             const unsigned ppv = pp_hi & valid_hi;
-                            A.tp[r] += __popc(ppv & gp_hi);
-                            A.ps[r] += __popc(ppv);
-                            A.gs[r] += __popc(gp_hi);
+                            A.tp[r] += (ppv & gp_hi) >> 7;
+                            A.ps[r] += ppv >> 7;
+                            A.gs[r] += gp_hi >> 7;
                         }
                     }
                 }
             } else {  // no reference can be the ignore value: every rater is valid everywhere
                 nv4 = (unsigned)R * kB01;
-                const unsigned ps = __popc(pp_hi);
+                const unsigned ps = pp_hi >> 7;
 #pragma unroll
                 for (int r = 0; r < RMAX; ++r) {
                     if (r < R) {
                         nc4 += (~bytes_nonzero(W[r] ^ lab4) & kB80) >> 7;
                         if (F::dice) {
                             const unsigned gp_hi = ~bytes_nonzero(W[r] ^ kB01) & kB80;
-                            A.tp[r] += __popc(pp_hi & gp_hi);
+                            A.tp[r] += (pp_hi & gp_hi) >> 7;
                             A.ps[r] += ps;
-                            A.gs[r] += __popc(gp_hi);
+                            A.gs[r] += gp_hi >> 7;
                         }
                     }
                 }
@@ -482,7 +492,11 @@ __device__ __forceinline__ void stats2_flush_regs(StatAcc<FL, RMAX>& A, const St
     if (F::dice) {
 #pragma unroll
         for (int r = 0; r < RMAX; ++r)
-            if (r < sp.gt.R) { iadd(VU_I64_DICE_TP + r, A.tp[r]); iadd(VU_I64_DICE_PRED + r, A.ps[r]); iadd(VU_I64_DICE_GT + r, A.gs[r]); }
+            if (r < sp.gt.R) {
+                iadd(VU_I64_DICE_TP + r, dp4a_u(A.tp[r], kB01, 0u));  // the four byte counters of the thread
+                iadd(VU_I64_DICE_PRED + r, dp4a_u(A.ps[r], kB01, 0u));
+                iadd(VU_I64_DICE_GT + r, dp4a_u(A.gs[r], kB01, 0u));
+            }
     }
     if (F::calib) {
 #pragma unroll

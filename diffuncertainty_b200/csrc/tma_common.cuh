@@ -27,6 +27,20 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
 }
+// same with a suspend-time hint: the hardware parks the thread for up to `ns` nanoseconds (or until the phase completes)
+// before the probe returns, so a warp that waits long -- the producer on a full ring -- spins with far fewer instructions
+__device__ __forceinline__ void mbar_wait_hint(unsigned bar, unsigned parity, unsigned ns) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITH_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONEH_%=;\n"
+        "bra WAITH_%=;\n"
+        "DONEH_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity), "r"(ns)
+        : "memory");
+}
 // same, for the statistics warps, which are ahead of the pipeline most of the time: sleep between probes instead
 // of burning issue slots the consumer warps need
 __device__ __forceinline__ void mbar_wait_relaxed(unsigned bar, unsigned parity) {

@@ -22,6 +22,20 @@ from ._lib import F64, I64
 from .uncertainty import UNC_KEYS, GroundTruth, fused_pass
 
 
+def h2d_ceiling_gbs(host: torch.Tensor, device, reps: int = 2) -> float:
+    """What the box delivers for a plain pinned host -> device copy of ``host`` (one contiguous transfer, GB/s): the ceiling
+    of any end-to-end number that feeds the GPU from host memory."""
+    import time
+    dst = torch.empty(host.shape, dtype=host.dtype, device=device)
+    dst.copy_(host, non_blocking=True)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(host, non_blocking=True)
+    torch.cuda.synchronize(device)
+    return host.numel() * host.element_size() * reps / (time.perf_counter() - t0) / 1e9
+
+
 def bind_host_thread_to_device_node(device) -> Optional[int]:
     """Restrict the calling process to the CPU cores of the NUMA node the GPU hangs off, so that pinned buffers allocated
     afterwards (first touch) lie in that node's memory and the host->device copies of the ranks of a multi-GPU box do not
@@ -76,16 +90,19 @@ class HostPipeline:
         self.stats, self.thresholds, self.ignore_index = stats, thresholds, ignore_index
         self.calib = [calibration.platt_edges(a, b) for a, b in platt] if (platt is not None and stats & _lib.STAT_CALIB) else None
         S = self.spatial
+        # P == 1 is the single-prediction path (calculate_one_minus_msr, test_2D.py:1006-1007): one map, key "pred_entropy"
+        self.map_keys = UNC_KEYS if P > 1 else ("pred_entropy",)
+        self._lib = _lib.load()
         with torch.cuda.device(self.dev):
             self.d_slab = [torch.empty((P, self.chunk, C) + S, dtype=torch.float32, device=self.dev) for _ in range(n_buffers)]
             self.d_gt = [torch.empty((self.chunk, R) + S, dtype=gt_dtype, device=self.dev) for _ in range(n_buffers)] if R else None
-            self.d_maps = [{k: torch.empty((self.chunk,) + S, dtype=torch.float32, device=self.dev) for k in UNC_KEYS}
+            self.d_maps = [{k: torch.empty((self.chunk,) + S, dtype=torch.float32, device=self.dev) for k in self.map_keys}
                            for _ in range(n_buffers)]
             self.d_labels = [torch.empty((self.chunk,) + S, dtype=torch.uint8, device=self.dev) for _ in range(n_buffers)]
             self.rows_f = torch.zeros((batch, F64["COLS"]), dtype=torch.float64, device=self.dev)
             self.rows_i = torch.zeros((batch, I64["COLS"]), dtype=torch.int64, device=self.dev)
             self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
-        self.h_maps = {k: torch.empty((batch,) + S, dtype=torch.float32).pin_memory() for k in UNC_KEYS}
+        self.h_maps = {k: torch.empty((batch,) + S, dtype=torch.float32).pin_memory() for k in self.map_keys}
         self.h_labels = torch.empty((batch,) + S, dtype=torch.uint8).pin_memory()
         self.h_rows_f = torch.empty((batch, F64["COLS"]), dtype=torch.float64).pin_memory()
         self.h_rows_i = torch.empty((batch, I64["COLS"]), dtype=torch.int64).pin_memory()
@@ -98,6 +115,7 @@ class HostPipeline:
         if self.R and (gt_host is None or tuple(gt_host.shape) != (B, self.R) + self.spatial):
             raise ValueError("gt_host must have shape (B, R, *spatial)")
         h2d = d2h = 0
+        img_bytes = self.C * int(np.prod(self.spatial)) * 4
         ev_in = [torch.cuda.Event() for _ in range(nb)]
         ev_run = [torch.cuda.Event() for _ in range(nb)]
         ev_out = [None] * nb
@@ -112,9 +130,17 @@ class HostPipeline:
                 n, j = e - s, i % nb
                 with torch.cuda.stream(self.s_in):
                     self.s_in.wait_event(ev_run[j]) if i >= nb else None   # buffer j is free once its kernel ran
-                    for p in range(P):                                      # each source run is contiguous
-                        self.d_slab[j][p, :n].copy_(x_host[p, s:e], non_blocking=True)
-                    h2d += x_host[:, s:e].numel() * 4
+                    # the chunk is P runs of n images, one per member, B images apart in the host slab: ONE strided copy
+                    # (P separate copies before: at 1 image per chunk the copy engine saw 16 small transfers per chunk)
+                    run = n * img_bytes
+                    src_pitch, dst_pitch = B * img_bytes, self.chunk * img_bytes
+                    if x_host.is_contiguous() and src_pitch < 2 ** 31:
+                        _lib.check(self._lib.vu_copy_2d_async(self.d_slab[j].data_ptr(), dst_pitch, x_host.data_ptr() + s * img_bytes,
+                                                              src_pitch, run, P, 1, self.s_in.cuda_stream), "vu_copy_2d_async")
+                    else:
+                        for p in range(P):                                  # each source run is contiguous
+                            self.d_slab[j][p, :n].copy_(x_host[p, s:e], non_blocking=True)
+                    h2d += P * run
                     if self.R:
                         self.d_gt[j][:n].copy_(gt_host[s:e], non_blocking=True)
                         h2d += gt_host[s:e].numel() * gt_host.element_size()
@@ -131,10 +157,10 @@ class HostPipeline:
                     ev_run[j].record(self.s_run)
                 with torch.cuda.stream(self.s_out):
                     self.s_out.wait_event(ev_run[j])
-                    for k in UNC_KEYS:
+                    for k in self.map_keys:
                         self.h_maps[k][s:e].copy_(self.d_maps[j][k][:n], non_blocking=True)
                     self.h_labels[s:e].copy_(self.d_labels[j][:n], non_blocking=True)
-                    d2h += n * int(np.prod(self.spatial)) * 13
+                    d2h += n * int(np.prod(self.spatial)) * (4 * len(self.map_keys) + 1)
                     ev_out[j] = torch.cuda.Event()
                     ev_out[j].record(self.s_out)
             with torch.cuda.stream(self.s_out):

@@ -8,11 +8,11 @@ the per-uncertainty / per-image loops of the evaluation tasks
 evaluation/metrics/ace.py:463-534, evaluation/metrics/aurc.py:130-153) -- by one
 fused launch per batch that accumulates per-image rows on the device.  Images are
 independent, so ranks own contiguous blocks of image indices and no data-path
-collective is needed; only the dataset-level histogram partials (int64 counts,
-float64 sums) and the per-image rows (scores, Dice counts: the AURC inputs) are
-combined with all-reduces (NCCL on GPUs; the same code runs over gloo on CPU
-tensors in the tests).  Integer partials are summed as int64, so the combined
-histograms are bit-identical at any GPU count.
+collective is needed; only the per-image rows (histogram partials, scores, Dice
+counts: the ECE / ACE and AURC inputs) are combined, with ONE int64 all-reduce
+(NCCL on GPUs; the same code runs over gloo on CPU tensors in the tests) that
+acts as an exact all-gather (``Partials``), so the combined rows and the
+dataset-level histograms are bit-identical at any GPU count.
 
 The finalisation (ACE / ECE, AURC / E-AURC) is image-count sized and stays on
 the host in float64, mirroring ace.py:357-375,439-460 and aurc.py:14-67.
@@ -65,31 +65,59 @@ def shard_bounds(n_images: int, rank: int, world: int) -> Tuple[int, int]:
 # ---------------------------------------------------------------------------
 # exchange step
 # ---------------------------------------------------------------------------
-def pack_partials(rows_f64: torch.Tensor, rows_i64: torch.Tensor, lo: int, n_images: int):
-    """Build the two buffers that cross GPUs:
-    int64  [ dataset bin_total 3x21 | dataset bin_true 3x21 | per-image int rows ]
-    float64[ dataset bin_sums 3x21 | per-image float rows ]
-    `rows_*` are this rank's rows (local image order); they land at their global
-    positions, zeros elsewhere, so a sum all-reduce is an exact all-gather."""
-    dev = rows_f64.device
+class Partials:
+    """Everything that crosses GPUs, in ONE int64 buffer:
+
+        [ n_images x 156 int64 rows | n_images x 80 float64 rows, viewed as int64 ]
+
+    ``vu_fused_pass`` accumulates straight into the rows of the images a rank owns (``local``); every other row stays zero,
+    so a SUM all-reduce over the int64 view is an exact all-gather -- each element has one non-zero contributor, and adding
+    zeros to the bit pattern of a float64 leaves it untouched.  One latency-bound ``ncclInt64`` all-reduce per exchange, no
+    packing kernels, and the combined rows are bit-identical at any GPU count.  The dataset-level histograms are the column
+    sums of the gathered rows and are formed on the host (``result``)."""
+
+    def __init__(self, n_images: int, device):
+        self.n_images = n_images
+        self.buf = torch.zeros(n_images * (I64["COLS"] + F64["COLS"]), dtype=torch.int64, device=device)
+        self.rows_i = self.buf[:n_images * I64["COLS"]].view(n_images, I64["COLS"])
+        self.rows_f = self.buf[n_images * I64["COLS"]:].view(torch.float64).view(n_images, F64["COLS"])
+
+    def local(self, lo: int, hi: int):
+        """(stats_f64, stats_i64) of the images lo .. hi - 1: the ``stats_out`` argument of ``fused_pass``."""
+        return self.rows_f[lo:hi], self.rows_i[lo:hi]
+
+    def zero_(self) -> None:
+        self.buf.zero_()
+
+    def exchange(self, async_op: bool = False):
+        """The only collective of the sweep.  Returns the work handle when ``async_op`` (else None)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, async_op=async_op)
+        return None
+
+    def result(self, n_voxels: int, n_raters: int) -> "SweepResult":
+        i = self.rows_i.cpu().numpy().copy()
+        f = self.rows_f.cpu().numpy().copy()
+        return SweepResult(n_images=self.n_images, n_voxels=n_voxels, n_raters=n_raters,
+                           bin_total=i[:, I64["BIN_TOTAL"]:I64["BIN_TOTAL"] + 63].sum(0).reshape(3, 21),
+                           bin_true=i[:, I64["BIN_TRUE"]:I64["BIN_TRUE"] + 63].sum(0).reshape(3, 21),
+                           bin_sums=f[:, F64["BIN_SUMS"]:F64["BIN_SUMS"] + 63].sum(0).reshape(3, 21), rows_f64=f, rows_i64=i)
+
+
+def pack_partials(rows_f64: torch.Tensor, rows_i64: torch.Tensor, lo: int, n_images: int) -> Partials:
+    """A ``Partials`` buffer holding this rank's rows (local image order) at their global positions, zeros elsewhere.
+    (The sweep itself lets the kernel write into ``Partials.local``; this is for rows that already exist.)"""
+    p = Partials(n_images, rows_f64.device)
     n_local = rows_f64.shape[0]
-    ibuf = torch.zeros(126 + n_images * I64["COLS"], dtype=torch.int64, device=dev)
-    fbuf = torch.zeros(63 + n_images * F64["COLS"], dtype=torch.float64, device=dev)
     if n_local:
-        ibuf[0:63] = rows_i64[:, I64["BIN_TOTAL"]:I64["BIN_TOTAL"] + 63].sum(0)
-        ibuf[63:126] = rows_i64[:, I64["BIN_TRUE"]:I64["BIN_TRUE"] + 63].sum(0)
-        fbuf[0:63] = rows_f64[:, F64["BIN_SUMS"]:F64["BIN_SUMS"] + 63].sum(0)
-        ibuf[126:].view(n_images, I64["COLS"])[lo:lo + n_local] = rows_i64
-        fbuf[63:].view(n_images, F64["COLS"])[lo:lo + n_local] = rows_f64
-    return ibuf, fbuf
+        p.rows_i[lo:lo + n_local] = rows_i64
+        p.rows_f[lo:lo + n_local] = rows_f64
+    return p
 
 
-def exchange(ibuf: torch.Tensor, fbuf: torch.Tensor) -> None:
-    """The only collectives of the sweep: one int64 and one float64 sum all-reduce."""
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(ibuf, op=dist.ReduceOp.SUM)
-        dist.all_reduce(fbuf, op=dist.ReduceOp.SUM)
+def exchange(partials: Partials) -> None:
+    partials.exchange()
 
 
 # ---------------------------------------------------------------------------
@@ -148,14 +176,8 @@ class SweepResult:
         return out
 
 
-def unpack_result(ibuf: torch.Tensor, fbuf: torch.Tensor, cfg_or_shape, n_images: int, n_voxels: int, n_raters: int) -> SweepResult:
-    i = ibuf.cpu().numpy()
-    f = fbuf.cpu().numpy()
-    return SweepResult(n_images=n_images, n_voxels=n_voxels, n_raters=n_raters,
-                       bin_total=i[0:63].reshape(3, 21).copy(), bin_true=i[63:126].reshape(3, 21).copy(),
-                       bin_sums=f[0:63].reshape(3, 21).copy(),
-                       rows_f64=f[63:].reshape(n_images, F64["COLS"]).copy(),
-                       rows_i64=i[126:].reshape(n_images, I64["COLS"]).copy())
+def unpack_result(partials: Partials, n_voxels: int, n_raters: int) -> SweepResult:
+    return partials.result(n_voxels, n_raters)
 
 
 # ---------------------------------------------------------------------------
@@ -195,8 +217,8 @@ class ShardedSweep:
         from .uncertainty import GroundTruth, fused_pass
         cfg = self.cfg
         n_local = self.hi - self.lo
-        rows_f = torch.zeros((n_local, F64["COLS"]), dtype=torch.float64, device=self.device)
-        rows_i = torch.zeros((n_local, I64["COLS"]), dtype=torch.int64, device=self.device)
+        partials = Partials(cfg.n_images, self.device)
+        rows_f, rows_i = partials.local(self.lo, self.hi)  # the kernel accumulates straight into the exchange buffer
         kept = {k: [] for k in UNC}
         kept_labels = []
         for s in range(0, n_local, cfg.batch):
@@ -209,9 +231,8 @@ class ShardedSweep:
                 for k in UNC:
                     kept[k].append(res.maps[k])
                 kept_labels.append(res.labels)
-        ibuf, fbuf = pack_partials(rows_f, rows_i, self.lo, cfg.n_images)
-        exchange(ibuf, fbuf)
-        out = unpack_result(ibuf, fbuf, cfg, cfg.n_images, cfg.V, cfg.R)
+        partials.exchange()  # once, at the end of the sweep
+        out = partials.result(cfg.V, cfg.R)
         if cfg.keep_maps and kept_labels:
             out.maps = {k: torch.cat(v) for k, v in kept.items()}
             out.labels = torch.cat(kept_labels)

@@ -324,6 +324,14 @@ VU_API int vu_synth_gt(uint8_t* out, const float* slab, int64_t P, int64_t B, in
                 int32_t R, uint64_t seed, int64_t first_image, float flip, float ignore_frac,
                 int32_t ignore_value, void* stream);
 
+/* Host <-> device staging helper of the end-to-end path (host_pipeline.py): `height` rows of `width` bytes between pitched
+ * buffers in ONE asynchronous copy on `stream` -- the (P, n, C, V) block of n images out of a (P, B, C, V) slab in pinned host
+ * memory is P runs of n*C*V floats, `B*C*V*4` bytes apart.  kind: 1 host -> device, 2 device -> host.  The stacked
+ * predictions of test_2D.py:1277 live in host memory whenever the forward passes ran on another device or were read back from
+ * the files of test_2D.py:857.                                                                                            */
+VU_API int vu_copy_2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width, int64_t height,
+                            int32_t kind, void* stream);
+
 /* tuning / introspection used by bench.py and the variant sweep */
 VU_API int vu_set_option(const char* key, int64_t value); /* e.g. "k1_variant"       */
 VU_API int64_t vu_get_counter(const char* key);           /* e.g. "launches"         */

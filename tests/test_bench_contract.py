@@ -41,7 +41,7 @@ def test_gpu_arm_prints_one_json_line():
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    line = run_bench("--steps", "3", "--warmup", "3", "--images-per-step", "2", "--e2e-images", "1", "--e2e-steps", "1", "--cpu-images", "1")
+    line = run_bench("--steps", "3", "--warmup", "3", "--images-per-step", "2", "--e2e-images", "1", "--e2e-steps", "1", "--cpu-images", "1", "--no-configs")
     assert BASE_KEYS | {"roofline", "clocks"} <= set(line)
     rf = line["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and 0 < rf["frac"] < 1.2 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9

@@ -57,22 +57,23 @@ def test_sharding_invariance_on_one_device(single, world):
     """Ranks run one after the other on one GPU; their packed buffers are summed like the all-reduce would."""
     from diffuncertainty_b200 import sweep
     cfg = _cfg()
-    isum = fsum = None
+    total = None
     for rank in range(world):
         sh = sweep.ShardedSweep(cfg, rank=rank, world=world)
         n_local = sh.hi - sh.lo
-        rows_f = torch.zeros((n_local, 80), dtype=torch.float64, device="cuda")
-        rows_i = torch.zeros((n_local, 156), dtype=torch.int64, device="cuda")
+        part = sweep.Partials(cfg.n_images, "cuda")
+        rows_f, rows_i = part.local(sh.lo, sh.hi)
         from diffuncertainty_b200.uncertainty import GroundTruth, fused_pass
         for s in range(0, n_local, cfg.batch):
             n = min(cfg.batch, n_local - s)
             x, gt = sh.source(sh.lo + s, n)
             fused_pass(x, GroundTruth(gt, cfg.ignore_index), stats=cfg.stats, thresholds=cfg.thresholds, calib=sh._calib,
                        want_maps=False, want_labels=False, stats_out=(rows_f[s:s + n], rows_i[s:s + n]))
-        ibuf, fbuf = sweep.pack_partials(rows_f, rows_i, sh.lo, cfg.n_images)
-        isum = ibuf if isum is None else isum + ibuf
-        fsum = fbuf if fsum is None else fsum + fbuf
-    got = sweep.unpack_result(isum, fsum, cfg, cfg.n_images, cfg.V, cfg.R)
+        if total is None:
+            total = part
+        else:
+            total.buf += part.buf  # what the int64 all-reduce does
+    got = total.result(cfg.V, cfg.R)
     assert np.array_equal(got.bin_total, single.bin_total) and np.array_equal(got.bin_true, single.bin_true)
     assert np.array_equal(got.rows_i64, single.rows_i64)
     np.testing.assert_allclose(got.rows_f64, single.rows_f64, rtol=1e-12, atol=1e-15)

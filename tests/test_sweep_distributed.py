@@ -1,6 +1,6 @@
 """Host side of the sharded sweep on CPU: image sharding, the
-packed int64 / float64 partial buffers and their all-reduce over gloo with two
-processes, and the float64 finalisation.  The rows that the CUDA kernels would
+single int64 exchange buffer (float64 rows travel as bit patterns) and its all-reduce over gloo with two
+and three processes, and the float64 finalisation.  The rows that the CUDA kernels would
 produce are replaced by seeded fake rows -- no compute kernel is called here."""
 import os
 import socket
@@ -40,8 +40,7 @@ def fake_rows(n_images, seed=0):
 
 def single_process_result(n_images):
     f, i = fake_rows(n_images)
-    ibuf, fbuf = sweep.pack_partials(torch.from_numpy(f), torch.from_numpy(i), 0, n_images)
-    return sweep.unpack_result(ibuf, fbuf, None, n_images, 4096, 2)
+    return sweep.pack_partials(torch.from_numpy(f), torch.from_numpy(i), 0, n_images).result(4096, 2)
 
 
 def test_shard_bounds_cover_every_image_once():
@@ -78,9 +77,9 @@ def _worker(rank, world, port, n_images, outdir):
     try:
         f, i = fake_rows(n_images)
         lo, hi = sweep.shard_bounds(n_images, rank, world)
-        ibuf, fbuf = sweep.pack_partials(torch.from_numpy(f[lo:hi].copy()), torch.from_numpy(i[lo:hi].copy()), lo, n_images)
-        sweep.exchange(ibuf, fbuf)
-        np.savez(os.path.join(outdir, f"rank{rank}.npz"), i=ibuf.numpy(), f=fbuf.numpy())
+        part = sweep.pack_partials(torch.from_numpy(f[lo:hi].copy()), torch.from_numpy(i[lo:hi].copy()), lo, n_images)
+        sweep.exchange(part)  # ONE int64 all-reduce
+        np.savez(os.path.join(outdir, f"rank{rank}.npz"), buf=part.buf.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -96,9 +95,12 @@ def test_exchange_over_gloo_matches_single_process(world):
         want = single_process_result(n_images)
         for r in range(world):
             z = np.load(os.path.join(d, f"rank{r}.npz"))
-            got = sweep.unpack_result(torch.from_numpy(z["i"]), torch.from_numpy(z["f"]), None, n_images, 4096, 2)
-            # integer partials: bit-identical at any world size; rows: exact (sum with zeros)
+            part = sweep.Partials(n_images, "cpu")
+            part.buf.copy_(torch.from_numpy(z["buf"]))
+            got = part.result(4096, 2)
+            # everything is bit-identical at any world size: the all-reduce adds zeros to every element (float64 rows travel
+            # as their bit patterns), and the dataset-level histograms are column sums of identical rows
             assert np.array_equal(got.bin_total, want.bin_total) and np.array_equal(got.bin_true, want.bin_true)
             assert np.array_equal(got.rows_i64, want.rows_i64) and np.array_equal(got.rows_f64, want.rows_f64)
-            np.testing.assert_allclose(got.bin_sums, want.bin_sums, rtol=1e-12)
+            assert np.array_equal(got.bin_sums, want.bin_sums)
             assert got.calibration()["TU"]["ace"] == pytest.approx(want.calibration()["TU"]["ace"], rel=1e-12)
