@@ -159,6 +159,31 @@ struct VoxelAcc {
         cascade_step(p);
     }
 
+    // add_member for VEC >= 2 that also hands out L(p) = log2(max(p, FLT_MIN)) (near-one polynomial) of every element, for the
+    // member-level likelihood sums folded into the pass (members_fold.cuh).  Same operations, same order.
+    __device__ __forceinline__ void add_member_L(const f32x2 (&xp)[NP], long long p, bool want_member_label, f32x2 (&Lout)[NP]) {
+        static_assert(VEC >= 2, "add_member_L needs VEC >= 2");
+        if (want_member_label) member_argmax<0, C>(xp, 0.f);
+        f32x2 h[NH];
+#pragma unroll
+        for (int q = 0; q < NH; ++q) h[q] = 0ull;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+#pragma unroll
+            for (int q = 0; q < NH; ++q) {
+                const f32x2 X = xp[c * NH + q];
+                m0[c * NH + q] = add2(m0[c * NH + q], X);
+                f32x2 PC, L;
+                plog2p_parts2(X, PC, L);
+                Lout[c * NH + q] = L;
+                h[q] = fma2(PC, L, h[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NH; ++q) a0[q] = add2(a0[q], h[q]);
+        cascade_step(p);
+    }
+
     // mean (true division, test_2D.py:971), label, TU, AU, EU of the VEC voxels
     __device__ __forceinline__ void finish(float Pf, float (&u)[VU_N_UNC][VEC], int (&label)[VEC]) const {
         const bool fast_div = Pf <= 271.0f;
