@@ -10,4 +10,6 @@ from . import _lib  # noqa: F401
 from .uncertainty import (FusedResult, GroundTruth, calculate_one_minus_msr, calculate_uncertainty, fused_pass,  # noqa: F401
                           group_members, map_stats, mean_argmax_labels)
 
-__version__ = "0.1.0"
+from .members import MemberScoreBuffers, fused_pass_with_member_scores  # noqa: F401,E402
+
+__version__ = "0.2.0"

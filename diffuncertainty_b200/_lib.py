@@ -14,10 +14,11 @@ LIB_PATH = os.path.join(PKG, "lib", "libvalunc.so")
 
 VU_OK = 0
 VU_ERR_BAD_ARG, VU_ERR_UNSUPPORTED, VU_ERR_CUDA, VU_ERR_NO_DEVICE = -1, -2, -3, -4
-VU_ABI_VERSION = 2
+VU_ABI_VERSION = 3
 N_UNC, N_BINS, N_EDGES, MAX_RATERS = 3, 21, 19, 8
 GT_U8, GT_I64 = 0, 1
 STAT_IMAGE_SUM, STAT_THRESHOLD, STAT_AREA, STAT_DICE, STAT_CALIB, STAT_NCC, STAT_PLATT_FIT = 1, 2, 4, 8, 16, 32, 64
+STAT_CLASS_COUNTS = 128
 N_PLATT_BINS = 256
 STAT_ALL_NO_GT = STAT_IMAGE_SUM | STAT_THRESHOLD | STAT_AREA
 
@@ -47,13 +48,18 @@ class PlattFit(C.Structure):
     _fields_ = [("edge_u", C.c_float * (N_PLATT_BINS + 1))]
 
 
+class MemberOut(C.Structure):
+    _fields_ = [("flags", C.c_uint32), ("eps", C.c_float), ("nll_sum", C.c_void_p), ("nll_count", C.c_void_p),
+                ("nll_bad", C.c_void_p), ("ged_counts", C.c_void_p)]
+
+
 class FusedArgs(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("stat_flags", C.c_uint32), ("slab", Slab),
                 ("tu", C.c_void_p), ("au", C.c_void_p), ("eu", C.c_void_p), ("labels", C.c_void_p),
                 ("gt", Gt), ("threshold", C.c_float * N_UNC), ("calib", Calib * N_UNC),
                 ("calib_label_lut", C.c_void_p), ("stats_f64", C.c_void_p), ("stats_i64", C.c_void_p),
                 ("platt_fit", C.POINTER(PlattFit)), ("platt_i64", C.c_void_p), ("platt_f64", C.c_void_p),
-                ("member_labels", C.c_void_p)]
+                ("member_labels", C.c_void_p), ("members", MemberOut), ("class_counts", C.c_void_p)]
 
 
 class MapStatsArgs(C.Structure):
@@ -61,7 +67,8 @@ class MapStatsArgs(C.Structure):
                 ("maps", C.c_void_p * N_UNC), ("labels", C.c_void_p), ("gt", Gt),
                 ("threshold", C.c_float * N_UNC), ("calib", Calib * N_UNC), ("calib_label_lut", C.c_void_p),
                 ("ncc_gt_map", C.c_void_p), ("stats_f64", C.c_void_p), ("stats_i64", C.c_void_p),
-                ("platt_fit", C.POINTER(PlattFit)), ("platt_i64", C.c_void_p), ("platt_f64", C.c_void_p)]
+                ("platt_fit", C.POINTER(PlattFit)), ("platt_i64", C.c_void_p), ("platt_f64", C.c_void_p),
+                ("class_counts", C.c_void_p), ("n_classes", C.c_int32)]
 
 
 class MemberScoresArgs(C.Structure):
@@ -79,6 +86,7 @@ EXPORTS = {
     "vu_device_check": (C.c_int, []),
     "vu_struct_size": (C.c_int, [C.c_int]),
     "vu_fused_pass": (C.c_int, [C.POINTER(FusedArgs), C.c_void_p]),
+    "vu_fused_members_supported": (C.c_int, [C.POINTER(FusedArgs)]),
     "vu_map_stats": (C.c_int, [C.POINTER(MapStatsArgs), C.c_void_p]),
     "vu_patch_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "vu_patch_max_ws": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

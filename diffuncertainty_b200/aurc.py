@@ -23,6 +23,36 @@ def binary_dice_from_counts(tp, pred_sum, gt_sum) -> np.ndarray:
     return dice.mean(axis=-1)
 
 
+def multiclass_dice_from_counts(tp, pred_sum, gt_sum, include_background: bool = False) -> np.ndarray:
+    """The general path of ``Tester.calculate_test_metrics`` (test_2D.py:901-918) on the integer counts of
+    ``STAT_CLASS_COUNTS``: for every rater ``dice(pred, rater, ignore_index, include_background=False, average="macro")``
+    (evaluation/metrics/dice_wrapped.py:17-104), then the mean over raters.  (..., R, C) count arrays -> (...,) float64.
+
+    dice_wrapped moves the ignored pixels into channel 0 of prediction AND target and drops that channel (together with
+    class 0 when ``include_background`` is False): what is left per class c is tp = #(pred == c & gt == c), #(pred == c) and
+    #(gt == c) over the pixels the rater does not ignore -- the counts the kernel emits.  The macro reduction is
+    torchmetrics' ``DiceScore(average="macro", aggregation_level="global", include_background=False)``: 2 tp / (pred + gt) per
+    class, classes that occur in neither prediction nor target (0 / 0) skipped by a nan-mean.  torchmetrics is absent from
+    the reference tree and from this image, so THIS reduction is restated from the published algorithm (torchmetrics >= 1.6,
+    ``segmentation/dice.py::_dice_score_compute``) and not pinned against it; the counts it consumes are pinned bit-exactly.
+    dice_wrapped's early returns: every pixel ignored -> 1; prediction and target all background -> 1."""
+    tp = np.asarray(tp, np.float64)
+    ps = np.asarray(pred_sum, np.float64)
+    gs = np.asarray(gt_sum, np.float64)
+    first = 0 if include_background else 1
+    valid_pixels = ps.sum(axis=-1)                       # pixels the rater does not ignore (every pixel has one label)
+    num, den = 2.0 * tp[..., first:], ps[..., first:] + gs[..., first:]
+    present = den > 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        per_class = np.where(present, num / np.where(present, den, 1.0), np.nan)
+        n_present = present.sum(axis=-1)
+        macro = np.where(n_present > 0, np.nansum(per_class, axis=-1) / np.maximum(n_present, 1), np.nan)
+    macro = np.where(valid_pixels == 0, 1.0, macro)     # dice_wrapped.py:93-94
+    if not include_background:
+        macro = np.where((valid_pixels > 0) & (n_present == 0), 1.0, macro)  # :95-99: only background on both sides
+    return macro.mean(axis=-1)
+
+
 def rc_curve_stats(risks, confids):
     """aurc.py:14-51 vectorised: images sorted by confidence; a curve point is
     emitted after dropping image i only if i == 0 or its confidence differs from

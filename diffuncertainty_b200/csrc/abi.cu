@@ -77,7 +77,8 @@ static int make_gt_view(GtView& v, const vu_gt* gt, long long V) {
 
 static int fill_stat_params(StatParams& st, uint32_t flags, unsigned unc_mask, long long V, const vu_gt& gt,
                             const float* thr, const vu_calib* calib, const uint8_t* lut, const double* ncc_gt_map,
-                            double* f64, int64_t* i64, const vu_platt_fit* platt_fit, int64_t* platt_i64, double* platt_f64) {
+                            double* f64, int64_t* i64, const vu_platt_fit* platt_fit, int64_t* platt_i64, double* platt_f64,
+                            int64_t* class_counts = nullptr, int n_classes = 0) {
     memset(&st, 0, sizeof(st));
     st.flags = flags;
     st.unc_mask = unc_mask;
@@ -86,9 +87,15 @@ static int fill_stat_params(StatParams& st, uint32_t flags, unsigned unc_mask, l
     if (flags == 0) return VU_OK;
     if (!f64 || !i64) return set_error(VU_ERR_BAD_ARG, "stat_flags set but stats_f64 / stats_i64 is NULL");
     const uint32_t known = VU_STAT_IMAGE_SUM | VU_STAT_THRESHOLD | VU_STAT_AREA | VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC |
-                           VU_STAT_PLATT_FIT;
+                           VU_STAT_PLATT_FIT | VU_STAT_CLASS_COUNTS;
     if (flags & ~known) return set_error(VU_ERR_BAD_ARG, "unknown stat flag");
-    const bool needs_gt = (flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_PLATT_FIT)) || ((flags & VU_STAT_NCC) && !ncc_gt_map);
+    const bool needs_gt = (flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_PLATT_FIT | VU_STAT_CLASS_COUNTS)) || ((flags & VU_STAT_NCC) && !ncc_gt_map);
+    if (flags & VU_STAT_CLASS_COUNTS) {
+        if (!class_counts) return set_error(VU_ERR_BAD_ARG, "VU_STAT_CLASS_COUNTS needs class_counts");
+        if (n_classes < 1 || n_classes > 256) return set_error(VU_ERR_BAD_ARG, "VU_STAT_CLASS_COUNTS needs 1..256 classes");
+        st.cls = reinterpret_cast<long long*>(class_counts);
+        st.ncls = n_classes;
+    }
     if (flags & VU_STAT_PLATT_FIT) {
         if (!platt_fit || !platt_i64 || !platt_f64)
             return set_error(VU_ERR_BAD_ARG, "VU_STAT_PLATT_FIT needs platt_fit, platt_i64 and platt_f64");
@@ -164,6 +171,7 @@ int vu_struct_size(int which) {
         case 2: return (int)sizeof(vu_calib);
         case 3: return (int)sizeof(vu_platt_fit);
         case 4: return (int)sizeof(vu_member_scores_args);
+        case 5: return (int)sizeof(vu_member_out);
         default: return -1;
     }
 }
@@ -186,9 +194,26 @@ int vu_fused_pass(const vu_fused_args* a, void* stream) {
     StatParams st;
     const unsigned unc_mask = s.P > 1 ? 7u : 1u;
     int rc = fill_stat_params(st, a->stat_flags, unc_mask, s.V, a->gt, a->threshold, a->calib, a->calib_label_lut, nullptr,
-                              a->stats_f64, a->stats_i64, a->platt_fit, a->platt_i64, a->platt_f64);
+                              a->stats_f64, a->stats_i64, a->platt_fit, a->platt_i64, a->platt_f64, a->class_counts, (int)s.C);
     if (rc != VU_OK) return rc;
+    if (a->members.flags) {
+        // member-level scores in the same pass: only the unified-warp kernel computes them
+        if (a->stat_flags == 0) return set_error(VU_ERR_UNSUPPORTED, "member scores in the fused pass need a statistics mask (e.g. VU_STAT_IMAGE_SUM)");
+        rc = launch_k1_uni(a, st, (cudaStream_t)stream);
+        return rc == 1 ? set_error(VU_ERR_UNSUPPORTED, "member scores in the fused pass: launch not eligible") : rc;
+    }
     return launch_k1(a, st, (cudaStream_t)stream);
+}
+
+int vu_fused_members_supported(const vu_fused_args* a) {
+    if (!a || a->struct_size != sizeof(vu_fused_args) || !a->members.flags || a->stat_flags == 0) return 0;
+    const vu_slab& s = a->slab;
+    if (s.P < 1 || s.B < 1 || s.C < 1 || s.V < 1) return 0;
+    StatParams st;
+    if (fill_stat_params(st, a->stat_flags, s.P > 1 ? 7u : 1u, s.V, a->gt, a->threshold, a->calib, a->calib_label_lut, nullptr,
+                         a->stats_f64, a->stats_i64, a->platt_fit, a->platt_i64, a->platt_f64) != VU_OK)
+        return 0;
+    return launch_k1_uni(a, st, nullptr, true) == VU_OK ? 1 : 0;
 }
 
 int vu_map_stats(const vu_map_stats_args* a, void* stream) {
@@ -196,13 +221,14 @@ int vu_map_stats(const vu_map_stats_args* a, void* stream) {
     if (a->struct_size != sizeof(vu_map_stats_args)) return set_error(VU_ERR_BAD_ARG, "vu_map_stats_args.struct_size mismatch");
     if (a->B < 0 || a->V < 0) return set_error(VU_ERR_BAD_ARG, "negative size");
     if (a->B == 0 || a->V == 0 || a->stat_flags == 0) return VU_OK;
-    if ((a->stat_flags & (VU_STAT_AREA | VU_STAT_DICE | VU_STAT_CALIB)) && !a->labels)
-        return set_error(VU_ERR_BAD_ARG, "AREA / DICE / CALIB need labels");
+    if ((a->stat_flags & (VU_STAT_AREA | VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_CLASS_COUNTS)) && !a->labels)
+        return set_error(VU_ERR_BAD_ARG, "AREA / DICE / CALIB / CLASS_COUNTS need labels");
     StatParams st;
     unsigned unc_mask = 0;
     for (int k = 0; k < VU_N_UNC; ++k) unc_mask |= a->maps[k] ? (1u << k) : 0u;
     int rc = fill_stat_params(st, a->stat_flags, unc_mask, a->V, a->gt, a->threshold, a->calib, a->calib_label_lut,
-                              a->ncc_gt_map, a->stats_f64, a->stats_i64, a->platt_fit, a->platt_i64, a->platt_f64);
+                              a->ncc_gt_map, a->stats_f64, a->stats_i64, a->platt_fit, a->platt_i64, a->platt_f64, a->class_counts,
+                              a->n_classes);
     if (rc != VU_OK) return rc;
     return launch_map_stats(a, st, (cudaStream_t)stream);
 }

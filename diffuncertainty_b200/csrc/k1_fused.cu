@@ -391,7 +391,7 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
         prm.total_tiles = prm.tiles_per_img * s.B;
         if (prm.total_tiles >= (1LL << 31)) return set_error(VU_ERR_UNSUPPORTED, "more than 2^31 tiles in one launch; split the batch");
         K1Kernel fn = st.flags ? pick->fn_stats : pick->fn;
-        const size_t dyn = stats_smem_bytes(st.flags, st.gt.R, pick->THREADS);
+        const size_t dyn = stats_smem_bytes(st.flags, st.gt.R, pick->THREADS) + stats_class_bytes(st.flags, st.gt.R, st.ncls);
         if (dyn > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
             return set_cuda_error("cudaFuncSetAttribute(k1_fast)");
         int occ = 0;
@@ -407,7 +407,8 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     // generic path
     constexpr int T = 64;
     const size_t max_dyn = 160 * 1024;
-    size_t dyn = generic_smem_bytes(s.P, T, a->member_labels != nullptr) + stats_smem_bytes(st.flags, st.gt.R, T);
+    size_t dyn = generic_smem_bytes(s.P, T, a->member_labels != nullptr) + stats_smem_bytes(st.flags, st.gt.R, T) +
+                 stats_class_bytes(st.flags, st.gt.R, st.ncls);
     if (dyn > max_dyn) return set_error(VU_ERR_UNSUPPORTED, "P too large for the generic kernel (P*256 B of shared memory, P*576 B with member labels)");
     if (s.P > (1LL << 19)) return set_error(VU_ERR_UNSUPPORTED, "P > 2^19");
     // the attribute is per device (and this may be the first launch on this one): set it whenever it is needed

@@ -366,7 +366,7 @@ int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     // cannot keep up with sixteen consumer warps there, so those launches stay on the register-streaming kernel,
     // where every warp does both (measured r01: cfg2 / cfg4 with Dice + calibration statistics 1.3-2.2x faster
     // that way; without reference-based statistics the TMA form wins everywhere).
-    const unsigned heavy = VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC | VU_STAT_PLATT_FIT;
+    const unsigned heavy = VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC | VU_STAT_PLATT_FIT | VU_STAT_CLASS_COUNTS;
     if (forced < 0 && get_option("k1_path", 0) != 2 && (st.flags & heavy) && s.C * s.P < 128) return 1;
     const int vec = pick->VEC;
     auto ok = [&](const void* p, uintptr_t al) { return p == nullptr || ((uintptr_t)p % al) == 0; };
@@ -387,7 +387,7 @@ int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t str
 
     const int rows = pick->NCH == 1 ? pick->G * pick->C : (pick->C + 1) / 2;
     const size_t stage_bytes = (size_t)rows * tile_vox * sizeof(float);
-    const size_t stats_bytes = stats_smem_bytes(st.flags, st.gt.R, pick->ST, pick->SREP);
+    const size_t stats_bytes = stats_smem_bytes(st.flags, st.gt.R, pick->ST, pick->SREP) + stats_class_bytes(st.flags, st.gt.R, st.ncls);
     const size_t hand_bytes = st.flags ? 2 * 13 * (size_t)tile_vox : 0;
     const size_t budget = 227 * 1024;
     const size_t fixed = 256 /* barriers */ + 256 /* alignment slack */ + stats_bytes + hand_bytes;

@@ -14,8 +14,12 @@
 //
 // Reference semantics: see k1_fused.cu / k1_core.cuh (maps, labels) and stats_v2.cuh (statistics).
 #include "k1_core.cuh"
+#include "members_fold.cuh"
 #include "stats_v2.cuh"
 #include "tma_common.cuh"
+#include <math.h>
+#include <string.h>
+
 #include "vu_host.h"
 
 namespace vu {
@@ -36,7 +40,9 @@ struct K1UniParams {
     int nstages;
     unsigned bar_offset;    // byte offsets inside dynamic shared memory
     unsigned stats_offset;
+    unsigned ms_offset;     // per-warp state of the member-level scores (MS kernels)
     StatParams st;
+    MsParams ms;
 };
 
 constexpr int kUniRep = 16;  // histogram replicas per warp (two lanes share one; the half-warps walk the types in rotated order)
@@ -44,8 +50,10 @@ constexpr int kUniRep = 16;  // histogram replicas per warp (two lanes share one
 // LEVELS: cascade levels of the member sum (1: P <= 17, 2: P <= 271); CT consumer threads; G members per ring stage;
 // FL: the statistics mask (compile time); RMAX: raters the reference registers are sized for.
 // MINB: CTAs per SM (each with its own producer warp, ring and histograms: independent pipelines that fill each other's gaps).
-template <int LEVELS, int CT, int G, unsigned FL, int RMAX, int MINB>
+// MS: the member-level scores (GED counts, likelihood sums; members_fold.cuh) are computed in the same pass.
+template <int LEVELS, int CT, int G, unsigned FL, int RMAX, int MINB, bool MS>
 __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ K1UniParams prm) {
+    static_assert(!MS || RMAX == kMsR, "the member-score fold is built for up to four raters");
     constexpr int C = 2, VEC = 4;
     constexpr int TV = CT * VEC;  // voxels per tile
     constexpr unsigned kRowBytes = TV * sizeof(float);
@@ -119,9 +127,14 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
     StatAcc<FL, RMAX> A;
     A.clear();
     int cur_b = -1, vt_begin = 0;
+    MsWarp mw;
+    const bool ms_nll = MS && (prm.ms.flags & VU_MS_NLL), ms_ged = MS && (prm.ms.flags & VU_MS_GED);
+    const bool ign_is_one = sp.gt.has_ignore && sp.gt.ignore == 1;
+    if constexpr (MS) mw.init(vu_uni_smem + prm.ms_offset + (unsigned)warp * kMsWarpBytes);
     auto flush = [&]() {
         stats2_flush_regs<FL, RMAX, kUniRep>(A, sp, cur_b);
         if (FL & VU_STAT_CALIB) stats2_flush_hist_warp<kUniRep>(sp, st_smem, cur_b, warp);
+        if constexpr (MS) mw.flush(prm.ms, cur_b, (int)P, sp.gt.R, true);
     };
 
     int b = t0 / tpi, vt = t0 - b * tpi - 1;
@@ -133,6 +146,12 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
     const bool want_ml = prm.mlab != nullptr;
     long long img_out = 0;       // b * V: offset of the image in the (B, V) outputs
     const uint8_t* gt_img = nullptr;  // references of the image
+    unsigned Wn[RMAX];           // MS: the reference words of the next tile
+    if constexpr (MS) if (t0 < t1) {
+        const int b0 = t0 / tpi, vt0 = t0 - b0 * tpi;
+        const long long v0 = (long long)vt0 * TV + (long long)tid * VEC;
+        stats2_load_refs<FL | VU_STAT_DICE, RMAX>(sp, v0 < V, reinterpret_cast<const uint8_t*>(sp.gt.data) + (long long)b0 * sp.gt.sb, v0, Wn);
+    }
     for (int tile = t0; tile < t1; ++tile) {
         if (++vt == tpi) { vt = 0; ++b; }
         if (b != cur_b || vt - vt_begin >= kMaxTilesPerFlush2) {  // warp-uniform
@@ -145,7 +164,21 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
         const long long v = (long long)vt * TV + (long long)tid * VEC;
         const bool active = v < V;
         unsigned W[RMAX];
-        stats2_load_refs<FL, RMAX>(sp, active, gt_img, v, W);  // in flight while the members stream
+        if constexpr (MS) {
+            // the reference words are needed before the first member (likelihood masks): they were requested during the
+            // previous tile; request the next tile's now
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) W[r] = Wn[r];
+            if (tile + 1 < t1) {
+                const bool wrap = vt + 1 == tpi;
+                const long long nv = (long long)(wrap ? 0 : vt + 1) * TV + (long long)tid * VEC;
+                const uint8_t* ngt = wrap ? gt_img + sp.gt.sb : gt_img;
+                stats2_load_refs<FL | VU_STAT_DICE, RMAX>(sp, nv < V, ngt, nv, Wn);
+            }
+            mw.tile_begin(W, active, sp.gt, ms_nll);
+        } else {
+            stats2_load_refs<FL, RMAX>(sp, active, gt_img, v, W);  // in flight while the members stream
+        }
 
         Acc acc;
         acc.init();
@@ -155,15 +188,46 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
             // (a partial last tile leaves stale bytes behind the image's end: those threads are inactive and
             //  their arithmetic is discarded)
             const int p0 = fi * G;
+            if constexpr (MS) {
+                // two members per stage: their likelihood values are folded over the lanes together
+                static_assert(!MS || G == 2, "the member-score fold takes the members in pairs");
+                const bool has_b = p0 + 1 < P;
+                f32x2 xa[Acc::NP], xb[Acc::NP], La[Acc::NP], Lb[Acc::NP];
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                if (G == 1 || p0 + g < P) {
-                    f32x2 xp[Acc::NP];
+                for (int c = 0; c < C; ++c) {
+                    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xa[c * 2]), "=l"(xa[c * 2 + 1]) : "r"(sbase + (unsigned)(c * kRowBytes)));
+                    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xb[c * 2]), "=l"(xb[c * 2 + 1]) : "r"(sbase + (unsigned)((C + c) * kRowBytes)));
+                }
+                if (!has_b) {  // odd member count: the second half of the stage holds no member
 #pragma unroll
-                    for (int c = 0; c < C; ++c)
-                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xp[c * 2]), "=l"(xp[c * 2 + 1]) : "r"(sbase + (unsigned)((g * C + c) * kRowBytes)));
-                    acc.add_member(xp, 0.f, p0 + g, want_ml);
-                    if (want_ml && active) VecLoad<VEC>::store_u8(prm.mlab + ((long long)(p0 + g) * prm.B + b) * V + v, acc.bi);
+                    for (int i = 0; i < Acc::NP; ++i) xb[i] = 0ull;
+                }
+                // one member after the other (the registers do not hold both members' logarithms); only the fold over the lanes
+                // is shared
+                const bool slow = ms_nll && (!mw.fast || __any_sync(kFull, (MsWarp::nan_probe(xa) + MsWarp::nan_probe(xb)) != 0.0f));
+                float va[kMsVals], vb[kMsVals];
+#pragma unroll
+                for (int i = 0; i < kMsVals; ++i) { va[i] = 0.f; vb[i] = 0.f; }
+                acc.add_member_L(xa, p0, false, La);
+                if (ms_ged) mw.member_labels(p0, xa);
+                if (ms_nll) mw.member_values(xa, La, sp.gt.R, prm.ms.log2eps, slow, va);
+                if (has_b) {
+                    acc.add_member_L(xb, p0 + 1, false, Lb);
+                    if (ms_ged) mw.member_labels(p0 + 1, xb);
+                    if (ms_nll) mw.member_values(xb, Lb, sp.gt.R, prm.ms.log2eps, slow, vb);
+                }
+                if (ms_nll) mw.fold_pair(p0, va, vb, has_b);
+            } else {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    if (G == 1 || p0 + g < P) {
+                        f32x2 xp[Acc::NP];
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+                            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xp[c * 2]), "=l"(xp[c * 2 + 1]) : "r"(sbase + (unsigned)((g * C + c) * kRowBytes)));
+                        acc.add_member(xp, 0.f, p0 + g, want_ml);
+                        if (want_ml && active) VecLoad<VEC>::store_u8(prm.mlab + ((long long)(p0 + g) * prm.B + b) * V + v, acc.bi);
+                    }
                 }
             }
             __syncwarp();
@@ -193,6 +257,10 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
             U[s] = make_float4(rot ? u[k1][0] : u[s][0], rot ? u[k1][1] : u[s][1], rot ? u[k1][2] : u[s][2], rot ? u[k1][3] : u[s][3]);
         }
         stats2_tile<FL, RMAX, kUniRep>(A, sp, cx, active, b, U[0], U[1], U[2], lab4, W);
+        if constexpr (MS) if (ms_ged) {
+            const unsigned lab1 = (label[0] == 1 ? 1u : 0u) | (label[1] == 1 ? 2u : 0u) | (label[2] == 1 ? 4u : 0u) | (label[3] == 1 ? 8u : 0u);
+            mw.tile_end((int)P, sp.gt.R, lab1, sp.gt.has_ignore != 0, ign_is_one, true);
+        }
     }
     if (cur_b >= 0) flush();
 }
@@ -206,14 +274,18 @@ struct UniVariant {
     unsigned FL;
     int RMAX, MINB;
     int use;  // 1: automatic selection, 0: only through the "k1_uni_shape" option (tuning sweep)
+    int ms;   // 1: computes the member-level scores as well
     K1UniKernel fn;
 };
-#define VU_UNI(LEVELS, CT, G, FL, RMAX, MINB, USE) { LEVELS, CT, G, FL, RMAX, MINB, USE, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX, MINB> }
+#define VU_UNI(LEVELS, CT, G, FL, RMAX, MINB, USE) \
+    { LEVELS, CT, G, FL, RMAX, MINB, USE, 0, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX, MINB, false> }
+#define VU_UNI_MS(LEVELS, CT, G, FL) { LEVELS, CT, G, FL, 4, 1, 1, 1, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, 4, 1, true> }
 // Registers are allocated per SM sub-partition: 16 consumer warps + the producer put 5 warps on one of them (96 registers per
 // thread), 15 + 1 leave 4 on each (128).  The masks with calibration histograms need the 128 (they spill 260-720 bytes at
 // 96); the others do not, and keep the power-of-two tile.
 #define VU_UNI_MASKS(LEVELS, G)                                                                                                              \
     VU_UNI(LEVELS, 512, G, 0x0du, 4, 1, 1), VU_UNI(LEVELS, 512, G, 0x0fu, 4, 1, 1), VU_UNI(LEVELS, 480, G, 0x1du, 4, 1, 1),                   \
+    VU_UNI(LEVELS, 512, G, 0x2du, 4, 1, 1),                                                                                                  \
     VU_UNI(LEVELS, 480, G, 0x1fu, 4, 1, 1), VU_UNI(LEVELS, 512, G, 0x21u, 4, 1, 1), VU_UNI(LEVELS, 480, G, 0x3fu, 4, 1, 1),                   \
     VU_UNI(LEVELS, 480, G, 0x3fu, 8, 1, 1)
 
@@ -225,6 +297,9 @@ static const UniVariant kUni[] = {
     VU_UNI_MASKS(2, 2),
     // tuning candidates ("k1_uni_shape" = CT * 100 + G * 10 + MINB)
     VU_UNI(1, 480, 1, 0x1du, 4, 1, 0), VU_UNI(1, 480, 3, 0x1du, 4, 1, 0),
+    // with the member-level scores (GED counts + likelihood sums) in the same pass: 15 + 1 warps (128 registers)
+    VU_UNI_MS(1, 480, 2, 0x21u), VU_UNI_MS(2, 480, 2, 0x21u), VU_UNI_MS(1, 480, 2, 0x2du), VU_UNI_MS(2, 480, 2, 0x2du),
+    VU_UNI_MS(1, 480, 2, 0x01u), VU_UNI_MS(2, 480, 2, 0x01u),
 };
 static const int kNumUni = (int)(sizeof(kUni) / sizeof(kUni[0]));
 
@@ -232,32 +307,46 @@ bool stats2_eligible(const StatParams& st, long long V);  // k3_map_stats.cu
 
 // Returns VU_OK after launching, 1 if this launch is not one for the unified form (the caller goes on to the
 // warp-specialised / register-streaming kernels), or a negative vu_status.
-int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t stream) {
+int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t stream, bool dry_run) {
     const vu_slab& s = a->slab;
+    const bool want_ms = a->members.flags != 0;
+    auto no = [&](const char* why) { return want_ms ? set_error(VU_ERR_UNSUPPORTED, why) : 1; };
     const long long path = get_option("k1_path", 0);
-    if (path == 1 || path == 2) return 1;  // 1 = register-streaming kernels only, 2 = warp-specialised TMA kernels only
-    if (get_option("k1_tma_variant", -1) >= 0 || get_option("stats_path", 0) == 1) return 1;
-    if (s.C != 2 || s.stride_v != 1 || s.P < 2 || s.P > 271 || !st.flags) return 1;
+    if (path == 1 || path == 2) return no("k1_path option excludes the unified kernel");  // 1 = register-streaming kernels only, 2 = warp-specialised TMA kernels only
+    if (get_option("k1_tma_variant", -1) >= 0 || get_option("stats_path", 0) == 1) return no("tuning options exclude the unified kernel");
+    if (s.C != 2 || s.stride_v != 1 || s.P < 2 || s.P > 271 || !st.flags) return no("member scores in the fused pass need C == 2, unit voxel stride, a statistics mask");
     const unsigned heavy = VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC;
-    if (!(st.flags & heavy) && path != 3) return 1;  // sums / thresholds / area only: the warp-specialised form is at the HBM roofline
-    if (!stats2_eligible(st, s.V)) return 1;
+    if (!want_ms && !(st.flags & heavy) && path != 3) return 1;  // sums / thresholds / area only: the warp-specialised form is at the HBM roofline
+    if (!stats2_eligible(st, s.V)) return no("statistics not eligible for the lean form (uint8 word-aligned references, V % 4 == 0, no LUT)");
+    if (want_ms) {
+        if (s.P > kMsP) return no("member scores in the fused pass need P <= 32");
+        if (!st.gt.data || st.gt.dtype != VU_GT_U8 || st.gt.align < 4 || st.gt.R > kMsR)
+            return no("member scores in the fused pass need at most 4 uint8 references with word-aligned rows");
+        if ((a->members.flags & ~(VU_MS_NLL | VU_MS_GED))) return set_error(VU_ERR_BAD_ARG, "members.flags");
+        if ((a->members.flags & VU_MS_NLL) && (!a->members.nll_sum || !a->members.nll_count || !a->members.nll_bad))
+            return set_error(VU_ERR_BAD_ARG, "members: NLL outputs are NULL");
+        if ((a->members.flags & VU_MS_GED) && !a->members.ged_counts) return set_error(VU_ERR_BAD_ARG, "members.ged_counts is NULL");
+        if (a->member_labels) return no("member scores in the fused pass and member_labels are not computed by the same kernel");
+    }
     // bulk copies need 16-byte aligned rows and sizes
-    if ((uintptr_t)s.data % 16 || s.V % 4 || (!s.member_ptrs && s.stride_p % 4) || s.stride_b % 4 || s.stride_c % 4) return 1;
+    if ((uintptr_t)s.data % 16 || s.V % 4 || (!s.member_ptrs && s.stride_p % 4) || s.stride_b % 4 || s.stride_c % 4) return no("rows are not 16-byte aligned");
     if (s.member_ptrs_host)
         for (int64_t p = 0; p < s.P; ++p)
-            if ((uintptr_t)s.member_ptrs_host[p] % 16) return 1;
+            if ((uintptr_t)s.member_ptrs_host[p] % 16) return no("rows are not 16-byte aligned");
     auto ok = [&](const void* p, uintptr_t al) { return p == nullptr || ((uintptr_t)p % al) == 0; };
-    if (!ok(a->tu, 16) || !ok(a->au, 16) || !ok(a->eu, 16) || !ok(a->labels, 4) || !ok(a->member_labels, 4)) return 1;
+    if (!ok(a->tu, 16) || !ok(a->au, 16) || !ok(a->eu, 16) || !ok(a->labels, 4) || !ok(a->member_labels, 4)) return no("outputs are not 16-byte aligned");
     const int need_levels = s.P <= 17 ? 1 : 2;
     const int rmax = (st.flags & heavy) && st.gt.R > 4 ? 8 : 4;
     const UniVariant* pick = nullptr;
     const long long shape = get_option("k1_uni_shape", 0);
     for (int i = 0; i < kNumUni && !pick; ++i) {
         const UniVariant& u = kUni[i];
-        if (u.LEVELS != need_levels || u.FL != st.flags || u.RMAX < rmax) continue;
-        if (shape ? (u.CT * 100 + u.G * 10 + u.MINB == shape) : u.use == 1) pick = &u;
+        if (u.LEVELS != need_levels || u.FL != st.flags || u.RMAX < rmax || (u.ms != 0) != want_ms) continue;
+        if (shape && !want_ms ? (u.CT * 100 + u.G * 10 + u.MINB == shape) : u.use == 1) pick = &u;
     }
-    if (!pick) return shape ? set_error(VU_ERR_UNSUPPORTED, "k1_uni_shape: no such kernel for this launch") : 1;
+    if (!pick) return shape && !want_ms ? set_error(VU_ERR_UNSUPPORTED, "k1_uni_shape: no such kernel for this launch")
+                                        : no("no unified kernel is built for this statistics mask");
+    if (dry_run) return VU_OK;
 
     K1UniParams prm;
     prm.x = s.data;
@@ -267,13 +356,23 @@ int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     prm.tu = a->tu; prm.au = a->au; prm.eu = a->eu; prm.lab = a->labels;
     prm.mlab = a->member_labels;
     prm.st = st;
+    memset(&prm.ms, 0, sizeof(prm.ms));
+    if (want_ms) {
+        prm.ms.flags = a->members.flags;
+        prm.ms.log2eps = (float)log2((double)a->members.eps > 0.0 ? (double)a->members.eps : 1e-45);
+        prm.ms.nll_sum = a->members.nll_sum;
+        prm.ms.nll_cnt = reinterpret_cast<unsigned long long*>(a->members.nll_count);
+        prm.ms.nll_bad = reinterpret_cast<unsigned long long*>(a->members.nll_bad);
+        prm.ms.ged = reinterpret_cast<unsigned long long*>(a->members.ged_counts);
+        prm.ms.ged_cols = (int)vu_ged_cols((int)s.P, st.gt.R);
+    }
     const long long tile_vox = (long long)pick->CT * 4;
     prm.tiles_per_img = (s.V + tile_vox - 1) / tile_vox;
     prm.total_tiles = prm.tiles_per_img * s.B;
     if (prm.total_tiles >= (1LL << 31)) return set_error(VU_ERR_UNSUPPORTED, "more than 2^31 tiles in one launch; split the batch");
 
     const size_t stage_bytes = (size_t)pick->G * 2 * tile_vox * sizeof(float);
-    const size_t stats_bytes = stats2_smem_bytes(st.flags, pick->CT, kUniRep);
+    const size_t stats_bytes = (stats2_smem_bytes(st.flags, pick->CT, kUniRep) + 15) / 16 * 16 + (want_ms ? (size_t)(pick->CT / 32) * kMsWarpBytes : 0);
     const size_t budget = (pick->MINB == 1 ? 227 : (pick->MINB == 2 ? 113 : 75)) * 1024 - (pick->MINB > 1 ? 1024 : 0);  // per CTA (1 KB reserved per CTA)
     const size_t fixed = 256 /* barriers */ + 256 /* alignment slack */ + stats_bytes;
     long long nstages = get_option("k1_tma_stages", 0);
@@ -287,6 +386,7 @@ int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     prm.bar_offset = (unsigned)off;
     off = (off + 256 + 127) / 128 * 128;  // 2 x nstages mbarriers (<= 128 bytes)
     prm.stats_offset = (unsigned)off;
+    prm.ms_offset = (unsigned)(off + (stats2_smem_bytes(st.flags, pick->CT, kUniRep) + 15) / 16 * 16);
     const size_t dyn = off + stats_bytes;
 
     if (cudaFuncSetAttribute(pick->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(kK3Threads) k3_map_stats(const __grid_constant
     const int t0 = (int)(prm.total_tiles * (long long)blockIdx.x / gridDim.x);
     const int t1 = (int)(prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x);
     const int tpi = (int)prm.tiles_per_img;
-    const bool light = !(prm.st.flags & (VU_STAT_CALIB | VU_STAT_PLATT_FIT | VU_STAT_NCC));
+    const bool light = !(prm.st.flags & (VU_STAT_CALIB | VU_STAT_PLATT_FIT | VU_STAT_NCC | VU_STAT_CLASS_COUNTS));
     int b = t0 / tpi, vt = t0 - b * tpi - 1;
     for (int tile = t0; tile < t1; ++tile) {
         if (++vt == tpi) { vt = 0; ++b; }
@@ -183,7 +183,7 @@ int launch_map_stats(const vu_map_stats_args* a, const StatParams& st, cudaStrea
         }
     }
     void (*fn)(const K3Params) = vec4 ? k3_map_stats<4> : k3_map_stats<1>;
-    const size_t dyn = stats_smem_bytes(st.flags, st.gt.R, kK3Threads);
+    const size_t dyn = stats_smem_bytes(st.flags, st.gt.R, kK3Threads) + stats_class_bytes(st.flags, st.gt.R, st.ncls);
     if (dyn > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
         return set_cuda_error("cudaFuncSetAttribute(k3_map_stats)");
     int occ = 0;

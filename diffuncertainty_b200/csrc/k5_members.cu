@@ -468,13 +468,23 @@ __global__ void __launch_bounds__(kMsThreads, 2) member_scores_c2v4(const __grid
                     l0[j] = log_clamped(x0[j], prm.eps);
                     d[j] = log_clamped(x1[j], prm.eps) - l0[j];
                 }
+                // A NaN probability must only reach the sums of the raters whose reference selects it (torch.gather picks
+                // before the sum, test_2D.py:1064-1068); through the 0 / 1 masks it would reach all of them (0 * NaN = NaN).
+                const float chk = (((x0[0] + x0[1]) + (x0[2] + x0[3])) + ((x1[0] + x1[1]) + (x1[2] + x1[3]))) * 0.0f;
+                const bool has_nan = __any_sync(kFull, chk != 0.0f);
                 float* col = nll_acc + p * R * kAccLanes + (lane >> 2);
 #pragma unroll
                 for (int r = 0; r < RMAX; ++r) {
                     if (r >= R) break;
                     float acc = 0.f;
+                    if (has_nan) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc = fmaf(m1[r][j], d[j], fmaf(m01[r][j], l0[j], acc));
+                        for (int j = 0; j < 4; ++j)
+                            if (m01[r][j] != 0.f) acc += (m1[r][j] != 0.f) ? l0[j] + d[j] : l0[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc = fmaf(m1[r][j], d[j], fmaf(m01[r][j], l0[j], acc));
+                    }
                     acc += __shfl_xor_sync(kFull, acc, 1);
                     acc += __shfl_xor_sync(kFull, acc, 2);
                     if ((lane & 3) == 0) col[r * kAccLanes] += acc;

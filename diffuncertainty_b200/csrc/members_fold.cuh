@@ -33,48 +33,56 @@ struct MsParams {
 
 constexpr int kMsP = 32, kMsR = 4;
 constexpr int kMsVals = 1 + kMsR;  // per member: sum of l0 over the voxels, then one value per rater
-constexpr int kMsCols = 4;         // columns per value (the 32 lane sums are folded 8 to 1 before they are stored)
+constexpr int kMsCols = 4;         // columns per member (the 32 lane sums are folded 8 to 1 before they are stored)
+constexpr int kMsValPad = 8;       // floats per (member, column): the five values, padded to 32 bytes (vector load / store)
 // counter words per lane (two 16-bit counters each; a warp flushes at least every 255 tiles of 128 voxels)
 enum { MC_PG = 0 /* [r]: pg_tp | pg_pred << 16 */, MC_GG = 4 /* [r]: gg_tp | gg_sum << 16 */, MC_GS = 8 /* [r]: g_sum | valid << 16 */,
        MC_POS = 12 /* pos | bad << 16 */, MC_MAJ = 13 /* tp | pred << 16 */, MC_MAJG = 14, MC_N = 15 };
-constexpr int kMsNllBytes = kMsP * kMsVals * kMsCols * 4, kMsPpBytes = kMsP * 32 * 2, kMsCntBytes = MC_N * 32 * 4;
-constexpr int kMsWarpBytes = kMsNllBytes + kMsPpBytes + kMsCntBytes;  // 2560 + 2048 + 1920
+constexpr int kMsNllBytes = kMsP * kMsCols * kMsValPad * 4, kMsPpBytes = kMsP * 32 * 2, kMsCntBytes = MC_N * 32 * 4;
+constexpr int kMsWarpBytes = kMsNllBytes + kMsPpBytes + kMsCntBytes;  // 4096 + 2048 + 1920
+
+__device__ __forceinline__ unsigned lds_u32(unsigned a) { unsigned r; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
+__device__ __forceinline__ void sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned lds_u16(unsigned a) { unsigned short r; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a)); return r; }
+__device__ __forceinline__ void sts_u16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void smem_add_u32(unsigned a, unsigned v) { sts_u32(a, lds_u32(a) + v); }
 
 struct MsWarp {
-    float* nll;           // [member][value][column]
-    unsigned short* pp;   // [partner q][member = lane]
-    unsigned* cnt;        // [counter][lane]
+    unsigned nll_a, pp_a, cnt_a;  // shared-memory addresses: nll [member][column][8 floats], pp u16 [partner q][member = lane],
+                                  // cnt u32 [counter][lane]
+    float* nll;                   // the same as a pointer (hot loop: the compiler may then overlap the columns of two members)
     // per tile
     f32x2 m1[2][4];       // (rater pair, voxel): 1.0 where the reference is class 1 and valid
     float mv;             // 1.0 for a lane inside the image
-    unsigned okb, oneb, rawb;  // bit (4 r + j): reference valid / valid and 1 / 1
+    unsigned actw;        // ballot of the lanes inside the image
+    unsigned okb, oneb, rawb, clsb;  // bit (4 r + j): reference valid / valid and 1 / 1 / valid and a class index (0 or 1)
     unsigned myW[4];      // lane p: label bits of member p, one word per voxel slot j
     bool fast;            // warp-uniform: every reference of the tile is a class index (no ignore value, nothing out of range)
 
     __device__ __forceinline__ void init(unsigned char* smem_warp) {
         nll = reinterpret_cast<float*>(smem_warp);
-        pp = reinterpret_cast<unsigned short*>(smem_warp + kMsNllBytes);
-        cnt = reinterpret_cast<unsigned*>(smem_warp + kMsNllBytes + kMsPpBytes);
+        nll_a = (unsigned)__cvta_generic_to_shared(smem_warp);
+        pp_a = nll_a + kMsNllBytes;
+        cnt_a = pp_a + kMsPpBytes;
         const int lane = threadIdx.x & 31;
-        for (int i = lane; i < kMsWarpBytes / 4; i += 32) reinterpret_cast<unsigned*>(smem_warp)[i] = 0u;
+        for (int i = lane; i < kMsWarpBytes / 4; i += 32) sts_u32(nll_a + 4u * i, 0u);
         __syncwarp();
     }
 
     // W[r]: the reference bytes of the lane's four voxels (stats2_load_refs); active: the lane is inside the image
     __device__ __forceinline__ void tile_begin(const unsigned (&W)[kMsR], bool active, const GtView& gt, bool want_nll) {
-        const int lane = threadIdx.x & 31;
-        okb = oneb = rawb = 0u;
+        const unsigned lane = threadIdx.x & 31;
+        okb = oneb = rawb = clsb = 0u;
         unsigned bad = 0u, nvalid[kMsR];
         bool all01 = true;
 #pragma unroll
         for (int r = 0; r < kMsR; ++r) {
             nvalid[r] = 0u;
-            unsigned one_hi = 0u;
             if (r < gt.R && active) {
                 const unsigned valid_hi = gt.ign_byte ? bytes_nonzero(W[r] ^ gt.ign4) : kB80;
                 const unsigned raw_hi = ~bytes_nonzero(W[r] ^ kB01) & kB80;
                 const unsigned zero_hi = ~bytes_nonzero(W[r]) & kB80;
-                one_hi = raw_hi & valid_hi;
+                const unsigned one_hi = raw_hi & valid_hi;
                 const unsigned cls_hi = (raw_hi | zero_hi) & valid_hi;  // a class index of a binary slab
                 all01 = all01 && cls_hi == kB80;
 #pragma unroll
@@ -82,12 +90,14 @@ struct MsWarp {
                     okb |= ((valid_hi >> (8 * j + 7)) & 1u) << (4 * r + j);
                     oneb |= ((one_hi >> (8 * j + 7)) & 1u) << (4 * r + j);
                     rawb |= ((raw_hi >> (8 * j + 7)) & 1u) << (4 * r + j);
+                    clsb |= ((cls_hi >> (8 * j + 7)) & 1u) << (4 * r + j);
                 }
                 nvalid[r] = __popc(valid_hi);
                 bad += __popc(valid_hi & ~cls_hi);  // torch.gather would raise (test_2D.py:1067)
             }
         }
         mv = active ? 1.0f : 0.0f;
+        actw = __ballot_sync(kFull, active);
 #pragma unroll
         for (int rp = 0; rp < 2; ++rp)
 #pragma unroll
@@ -99,42 +109,66 @@ struct MsWarp {
         if (want_nll) {
 #pragma unroll
             for (int r = 0; r < kMsR; ++r)
-                if (nvalid[r]) cnt[(MC_GS + r) * 32 + lane] += nvalid[r] << 16;
-            if (bad) cnt[MC_POS * 32 + lane] += bad << 16;
+                if (nvalid[r]) smem_add_u32(cnt_a + ((MC_GS + r) * 32 + lane) * 4u, nvalid[r] << 16);
+            if (bad) smem_add_u32(cnt_a + (MC_POS * 32 + lane) * 4u, bad << 16);
         }
     }
 
-    // member p: x = its values (pairs: class 0 voxels 01, 23, class 1 voxels 01, 23), L = log2(max(x, FLT_MIN)) of the same
-    __device__ __forceinline__ void member(int p, const f32x2 (&x)[4], const f32x2 (&L)[4], bool active, int R, float log2eps, bool want_nll,
-                                           bool want_ged) {
-        const int lane = threadIdx.x & 31;
+    // the general form of a member's likelihood terms: every term on its own, with torch's NaN rule (torch.clamp keeps NaN)
+    // and only where the reference is a class index.  Rare (tiles with ignored voxels, members with NaN values): out of line.
+    // (Inlined although it is cold: out of line its array arguments -- and with them the hot path's values -- live in local memory.)
+    __device__ __forceinline__ static void member_general(float (&v)[kMsVals], const float (&x0)[4], const float (&x1)[4], const float (&l0)[4],
+                                                       const float (&l1)[4], unsigned clsb, unsigned oneb, int R, float log2eps) {
+        v[0] = 0.f;
+#pragma unroll
+        for (int r = 0; r < kMsR; ++r) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // (a valid reference that is neither 0 nor 1 is counted in `bad` and contributes nothing)
+                const bool cls = (clsb >> (4 * r + j)) & 1u, one = (oneb >> (4 * r + j)) & 1u;
+                const float xs = one ? x1[j] : x0[j];
+                const float ls = fmaxf(one ? l1[j] : l0[j], log2eps);
+                if (r < R && cls) a += (xs != xs) ? xs : ls;
+            }
+            v[1 + r] = a;
+        }
+    }
+
+    // label bits of member p (GED): x = its values (pairs: class 0 voxels 01, 23, class 1 voxels 01, 23)
+    __device__ __forceinline__ void member_labels(int p, const f32x2 (&x)[4]) {
+        const bool mine = (threadIdx.x & 31) == (unsigned)p;
         float x0[4], x1[4];
         upk2(x[0], x0[0], x0[1]); upk2(x[1], x0[2], x0[3]);
         upk2(x[2], x1[0], x1[1]); upk2(x[3], x1[2], x1[3]);
-        if (want_ged) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                // torch.argmax over two classes: 1 iff p1 > p0, or p1 is NaN and p0 is not (ged_fast.py:44)
-                const bool one = !(x1[j] <= x0[j]) && (x0[j] == x0[j]);
-                const unsigned w = __ballot_sync(kFull, one && active);
-                if (lane == p) myW[j] = w;
-            }
+        for (int j = 0; j < 4; ++j) {
+            // torch.argmax over two classes: 1 iff p1 > p0, or p1 is NaN and p0 is not (ged_fast.py:44)
+            // (lanes outside the image vote on stale bytes: their bits are masked out once per tile, in tile_end)
+            const unsigned w = __ballot_sync(kFull, !(x1[j] <= x0[j]) && (x0[j] == x0[j]));
+            myW[j] = mine ? w : myW[j];
         }
-        if (!want_nll) return;
-        float l0[4], l1[4], v[kMsVals];
-        upk2(L[0], l0[0], l0[1]); upk2(L[1], l0[2], l0[3]);
-        upk2(L[2], l1[0], l1[1]); upk2(L[3], l1[2], l1[3]);
-        // a NaN probability makes the member's sums NaN (torch.clamp keeps NaN); the pass's L does not (it clamps first)
+    }
+
+    // the five per-lane likelihood values of one member (sum of l0 over the lane's voxels, then one value per rater);
+    // x as above, L = log2(max(x, FLT_MIN)) of the same elements
+    // 0 unless one of the member's values is NaN (or +inf and -inf meet): such a member takes the general form, because a NaN
+    // probability makes its sums NaN (torch.clamp keeps NaN) while the pass's L does not (it clamps first)
+    __device__ __forceinline__ static float nan_probe(const f32x2 (&x)[4]) {
         float lo, hi;
         upk2(add2(add2(x[0], x[1]), add2(x[2], x[3])), lo, hi);
-        const float chk = (lo + hi) * 0.0f;
-        const bool slow = !fast || __any_sync(kFull, chk != 0.0f);
+        return (lo + hi) * 0.0f;
+    }
+
+    // slow: warp-uniform, the tile or the member needs the general form
+    __device__ __forceinline__ void member_values(const f32x2 (&x)[4], const f32x2 (&L)[4], int R, float log2eps, bool slow, float (&v)[kMsVals]) {
+        float l0[4], l1[4], lo, hi;
+        upk2(L[0], l0[0], l0[1]); upk2(L[1], l0[2], l0[3]);
+        upk2(L[2], l1[0], l1[1]); upk2(L[3], l1[2], l1[3]);
         if (!slow) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) { l0[j] = fmaxf(l0[j], log2eps); l1[j] = fmaxf(l1[j], log2eps); }
-            const f32x2 D01 = add2(pk2(l1[0], l1[1]), pk2(-l0[0], -l0[1])), D23 = add2(pk2(l1[2], l1[3]), pk2(-l0[2], -l0[3]));
-            float d[4];
-            upk2(D01, d[0], d[1]); upk2(D23, d[2], d[3]);
+            const float d[4] = {l1[0] - l0[0], l1[1] - l0[1], l1[2] - l0[2], l1[3] - l0[3]};
             v[0] = ((l0[0] + l0[1]) + (l0[2] + l0[3])) * mv;
             f32x2 A0 = 0ull, A1 = 0ull;
 #pragma unroll
@@ -146,49 +180,64 @@ struct MsWarp {
             upk2(A0, v[1], v[2]);
             upk2(A1, v[3], v[4]);
         } else {
-            // the general form: every term on its own, with torch's NaN rule and only where the reference is a class index
-            v[0] = 0.f;
+            float x0[4], x1[4];
+            upk2(x[0], x0[0], x0[1]); upk2(x[1], x0[2], x0[3]);
+            upk2(x[2], x1[0], x1[1]); upk2(x[3], x1[2], x1[3]);
+            member_general(v, x0, x1, l0, l1, clsb, oneb, R, log2eps);
+        }
+    }
+
+    // Fold the values of the two members p and p + 1 over the lanes and add them to the warp's columns.  The two members
+    // travel as packed pairs (one add serves both); 8 lanes are folded to 1 by three shuffles and the lanes 0, 8, 16, 24 add
+    // the sums to their column of each member.  has_b = false: only member p (odd member count).
+    __device__ __forceinline__ void fold_pair(int p, const float (&va)[kMsVals], const float (&vb)[kMsVals], bool has_b) {
+        const unsigned lane = threadIdx.x & 31;
+        f32x2 V[kMsVals];
 #pragma unroll
-            for (int r = 0; r < kMsR; ++r) {
-                float a = 0.f;
+        for (int i = 0; i < kMsVals; ++i) V[i] = pk2(va[i], vb[i]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool ok = (okb >> (4 * r + j)) & 1u, one = (oneb >> (4 * r + j)) & 1u, raw1 = (rawb >> (4 * r + j)) & 1u;
-                    const float xs = one ? x1[j] : x0[j];
-                    const float ls = fmaxf(one ? l1[j] : l0[j], log2eps);
-                    const bool cls = ok && (one || !raw1) && (one || x0[j] == x0[j] || true);
-                    // (a valid reference that is neither 0 nor 1 is counted in `bad` and contributes nothing)
-                    const bool is0 = ok && !raw1;
-                    if (r < R && cls && (one || is0)) a += (xs != xs) ? xs : ls;
-                }
-                v[1 + r] = a;
+        for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+            for (int i = 0; i < kMsVals; ++i) {
+                float a, b;
+                upk2(V[i], a, b);
+                V[i] = add2(V[i], pk2(__shfl_xor_sync(kFull, a, o), __shfl_xor_sync(kFull, b, o)));
             }
         }
-        float* col = nll + (p * kMsVals) * kMsCols + (lane >> 3);
+        if ((lane & 7u) == 0u) {
+            float sa[kMsVals], sb[kMsVals];
 #pragma unroll
-        for (int i = 0; i < kMsVals; ++i) {
-            float s = v[i];
-            s += __shfl_xor_sync(kFull, s, 1);
-            s += __shfl_xor_sync(kFull, s, 2);
-            s += __shfl_xor_sync(kFull, s, 4);
-            if ((lane & 7) == 0) col[i * kMsCols] += s;
+            for (int i = 0; i < kMsVals; ++i) upk2(V[i], sa[i], sb[i]);
+            float* ca = nll + ((unsigned)p * kMsCols + (lane >> 3)) * kMsValPad;
+            float4 q = *reinterpret_cast<float4*>(ca);
+            q.x += sa[0]; q.y += sa[1]; q.z += sa[2]; q.w += sa[3];
+            *reinterpret_cast<float4*>(ca) = q;
+            ca[4] += sa[4];
+            if (has_b) {
+                float* cb = ca + kMsCols * kMsValPad;
+                float4 t = *reinterpret_cast<float4*>(cb);
+                t.x += sb[0]; t.y += sb[1]; t.z += sb[2]; t.w += sb[3];
+                *reinterpret_cast<float4*>(cb) = t;
+                cb[4] += sb[4];
+            }
         }
     }
 
     // after the last member of the tile: lab1 = bit j set where the label of the member mean of voxel j is 1 (majority Dice)
-    __device__ __forceinline__ void tile_end(int P, int R, bool active, unsigned lab1, bool has_ignore, bool ign_is_one, bool want_major) {
-        const int lane = threadIdx.x & 31;
+    __device__ __forceinline__ void tile_end(int P, int R, unsigned lab1, bool has_ignore, bool ign_is_one, bool want_major) {
+        const unsigned lane = threadIdx.x & 31;
         unsigned pos = 0u, pg_tp[kMsR], pg_pred[kMsR], gg_tp[kMsR], gg_sum[kMsR], g_sum[kMsR], maj_tp = 0u, maj_pred = 0u, maj_gt = 0u;
 #pragma unroll
         for (int r = 0; r < kMsR; ++r) { pg_tp[r] = 0u; pg_pred[r] = 0u; gg_tp[r] = 0u; gg_sum[r] = 0u; g_sum[r] = 0u; }
         // pair counts member x member: lane p against every partner q
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pos += __popc(myW[j]);
+        for (int j = 0; j < 4; ++j) { myW[j] &= actw; pos += __popc(myW[j]); }
         for (int q = 0; q < P; ++q) {
             unsigned c = 0u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) c += __popc(myW[j] & __shfl_sync(kFull, myW[j], q));
-            if (c) pp[q * 32 + lane] += (unsigned short)c;  // lanes >= P hold zero words
+            const unsigned a = pp_a + ((unsigned)q * 32u + lane) * 2u;
+            if (c) sts_u16(a, lds_u16(a) + c);  // lanes >= P hold zero words
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -204,8 +253,8 @@ struct MsWarp {
                     const unsigned raw1 = ign_is_one ? (rawb >> (4 * r + j)) & 1u : one;
                     const unsigned Gb = ign_is_one ? __ballot_sync(kFull, raw1) : 0u;
                     Gw[r] = __ballot_sync(kFull, one);
-                    Vw[r] = __ballot_sync(kFull, ok);
-                    myGb = (lane == r) ? (ign_is_one ? Gb : Gw[r]) : myGb;
+                    Vw[r] = has_ignore ? __ballot_sync(kFull, ok) : actw;
+                    myGb = (lane == (unsigned)r) ? (ign_is_one ? Gb : Gw[r]) : myGb;
                     n1 += raw1;
                     all_valid &= ok;
                     pg_tp[r] += __popc(w & Gw[r]);
@@ -222,8 +271,9 @@ struct MsWarp {
             }
             if (want_major) {
                 // ged_fast.py:121-131: majority reference (share of raters with label 1 >= 0.5) on voxels no rater ignores
+                const bool active = (actw >> lane) & 1u;
                 const unsigned Mg = __ballot_sync(kFull, active && 2u * n1 >= (unsigned)R);
-                const unsigned Va = __ballot_sync(kFull, active && (has_ignore ? all_valid : 1u));
+                const unsigned Va = has_ignore ? __ballot_sync(kFull, active && all_valid) : actw;
                 const unsigned Lw = __ballot_sync(kFull, (lab1 >> j) & 1u);
                 maj_tp += __popc(Lw & Mg & Va);
                 maj_pred += __popc(Lw & Va);
@@ -234,87 +284,99 @@ struct MsWarp {
 #pragma unroll
         for (int r = 0; r < kMsR; ++r) {
             if (r < R) {
-                const unsigned a = pg_tp[r] | (pg_pred[r] << 16), g = (lane < R) ? (gg_tp[r] | (gg_sum[r] << 16)) : 0u;
-                if (a) cnt[(MC_PG + r) * 32 + lane] += a;
-                if (g) cnt[(MC_GG + r) * 32 + lane] += g;
-                if (lane == 0 && g_sum[r]) cnt[(MC_GS + r) * 32] += g_sum[r];
+                const unsigned a = pg_tp[r] | (pg_pred[r] << 16), g = (lane < (unsigned)R) ? (gg_tp[r] | (gg_sum[r] << 16)) : 0u;
+                if (a) smem_add_u32(cnt_a + ((MC_PG + r) * 32 + lane) * 4u, a);
+                if (g) smem_add_u32(cnt_a + ((MC_GG + r) * 32 + lane) * 4u, g);
+                if (lane == 0 && g_sum[r]) smem_add_u32(cnt_a + ((MC_GS + r) * 32) * 4u, g_sum[r]);
             }
         }
-        if (pos) cnt[MC_POS * 32 + lane] += pos;
+        if (pos) smem_add_u32(cnt_a + (MC_POS * 32 + lane) * 4u, pos);
         if (lane == 0 && want_major) {
-            cnt[MC_MAJ * 32] += maj_tp | (maj_pred << 16);
-            cnt[MC_MAJG * 32] += maj_gt;
+            smem_add_u32(cnt_a + (MC_MAJ * 32) * 4u, maj_tp | (maj_pred << 16));
+            smem_add_u32(cnt_a + (MC_MAJG * 32) * 4u, maj_gt);
         }
     }
 
-    // add the warp's partials into the rows of image b (layout: valunc.h, vu_member_scores) and clear them
-    __device__ __noinline__ void flush(const MsParams& ms, long long b, int P, int R, bool want_major) {
-        const int lane = threadIdx.x & 31;
-        __syncwarp();
-        if (ms.flags & VU_MS_NLL) {
-            if (lane < P) {
-                float* row = nll + lane * kMsVals * kMsCols;
-                double s[kMsVals];
+    __device__ __forceinline__ void flush(const MsParams& ms, long long b, int P, int R, bool want_major);
+};
+
+// add a warp's partials into the rows of image b (layout: valunc.h, vu_member_scores) and clear them.  Out of line and on
+// plain addresses, so that the per-tile state of MsWarp stays in registers.
+__device__ __noinline__ void ms_flush_warp(unsigned nll_a, unsigned pp_a, unsigned cnt_a, const MsParams& ms, long long b, int P, int R,
+                                           bool want_major) {
+    const unsigned lane = threadIdx.x & 31;
+    auto cnt = [&](int c, unsigned l) { return lds_u32(cnt_a + ((unsigned)c * 32u + l) * 4u); };
+    __syncwarp();
+    if (ms.flags & VU_MS_NLL) {
+        if (lane < (unsigned)P) {
+            double s[kMsVals];
 #pragma unroll
-                for (int i = 0; i < kMsVals; ++i) {
-                    s[i] = 0.0;
+            for (int i = 0; i < kMsVals; ++i) {
+                s[i] = 0.0;
 #pragma unroll
-                    for (int c = 0; c < kMsCols; ++c) { s[i] += (double)row[i * kMsCols + c]; row[i * kMsCols + c] = 0.f; }
-                }
-                for (int r = 0; r < R; ++r) {
-                    const double t = (s[0] + s[1 + r]) * 0.6931471805599453;  // log2 -> ln
-                    if (t != 0.0) atomicAdd(ms.nll_sum + (b * R + r) * P + lane, t);
+                for (int c = 0; c < kMsCols; ++c) {
+                    const unsigned a = nll_a + ((lane * kMsCols + c) * kMsValPad + i) * 4u;
+                    s[i] += (double)__uint_as_float(lds_u32(a));
+                    sts_u32(a, 0u);
                 }
             }
             for (int r = 0; r < R; ++r) {
-                const unsigned n = __reduce_add_sync(kFull, cnt[(MC_GS + r) * 32 + lane] >> 16);
-                if (lane == 0 && n) atomicAdd(ms.nll_cnt + b * R + r, (unsigned long long)n);
-            }
-            const unsigned nb = __reduce_add_sync(kFull, cnt[MC_POS * 32 + lane] >> 16);
-            if (lane == 0 && nb) atomicAdd(ms.nll_bad + b, (unsigned long long)nb);
-        }
-        if (ms.flags & VU_MS_GED) {
-            const int G = R;
-            const int o_pg_pred = P * G, o_gs = 2 * P * G, o_pp = o_gs + G, o_pos = o_pp + P * P, o_gg_tp = o_pos + P, o_gg_sum = o_gg_tp + G * G,
-                      o_maj = o_gg_sum + G * G;
-            unsigned long long* row = ms.ged + b * ms.ged_cols;
-            if (lane < P) {
-                for (int q = 0; q < P; ++q) {
-                    const unsigned c = pp[q * 32 + lane];
-                    if (c) atomicAdd(row + o_pp + lane * P + q, (unsigned long long)c);
-                }
-                const unsigned ps = cnt[MC_POS * 32 + lane] & 0xffffu;
-                if (ps) atomicAdd(row + o_pos + lane, (unsigned long long)ps);
-                for (int r = 0; r < G; ++r) {
-                    const unsigned a = cnt[(MC_PG + r) * 32 + lane];
-                    if (a & 0xffffu) atomicAdd(row + lane * G + r, (unsigned long long)(a & 0xffffu));
-                    if (a >> 16) atomicAdd(row + o_pg_pred + lane * G + r, (unsigned long long)(a >> 16));
-                }
-            }
-            if (lane < G) {
-                for (int r = 0; r < G; ++r) {
-                    const unsigned g = cnt[(MC_GG + r) * 32 + lane];
-                    if (g & 0xffffu) atomicAdd(row + o_gg_tp + lane * G + r, (unsigned long long)(g & 0xffffu));
-                    if (g >> 16) atomicAdd(row + o_gg_sum + lane * G + r, (unsigned long long)(g >> 16));
-                }
-            }
-            if (lane == 0) {
-                for (int r = 0; r < G; ++r) {
-                    const unsigned g = cnt[(MC_GS + r) * 32] & 0xffffu;
-                    if (g) atomicAdd(row + o_gs + r, (unsigned long long)g);
-                }
-                if (want_major) {
-                    const unsigned m = cnt[MC_MAJ * 32], mg = cnt[MC_MAJG * 32];
-                    if (m & 0xffffu) atomicAdd(row + o_maj, (unsigned long long)(m & 0xffffu));
-                    if (m >> 16) atomicAdd(row + o_maj + 1, (unsigned long long)(m >> 16));
-                    if (mg) atomicAdd(row + o_maj + 2, (unsigned long long)mg);
-                }
+                const double t = (s[0] + s[1 + r]) * 0.6931471805599453;  // log2 -> ln
+                if (t != 0.0) atomicAdd(ms.nll_sum + (b * R + r) * P + lane, t);
             }
         }
-        __syncwarp();
-        for (int i = lane; i < (kMsPpBytes + kMsCntBytes) / 4; i += 32) reinterpret_cast<unsigned*>(pp)[i] = 0u;
-        __syncwarp();
+        for (int r = 0; r < R; ++r) {
+            const unsigned n = __reduce_add_sync(kFull, cnt(MC_GS + r, lane) >> 16);
+            if (lane == 0 && n) atomicAdd(ms.nll_cnt + b * R + r, (unsigned long long)n);
+        }
+        const unsigned nb = __reduce_add_sync(kFull, cnt(MC_POS, lane) >> 16);
+        if (lane == 0 && nb) atomicAdd(ms.nll_bad + b, (unsigned long long)nb);
     }
-};
+    if (ms.flags & VU_MS_GED) {
+        const int G = R;
+        const int o_pg_pred = P * G, o_gs = 2 * P * G, o_pp = o_gs + G, o_pos = o_pp + P * P, o_gg_tp = o_pos + P, o_gg_sum = o_gg_tp + G * G,
+                  o_maj = o_gg_sum + G * G;
+        unsigned long long* row = ms.ged + b * ms.ged_cols;
+        if (lane < (unsigned)P) {
+            for (int q = 0; q < P; ++q) {
+                const unsigned c = lds_u16(pp_a + ((unsigned)q * 32u + lane) * 2u);
+                if (c) atomicAdd(row + o_pp + lane * P + q, (unsigned long long)c);
+            }
+            const unsigned ps = cnt(MC_POS, lane) & 0xffffu;
+            if (ps) atomicAdd(row + o_pos + lane, (unsigned long long)ps);
+            for (int r = 0; r < G; ++r) {
+                const unsigned a = cnt(MC_PG + r, lane);
+                if (a & 0xffffu) atomicAdd(row + lane * G + r, (unsigned long long)(a & 0xffffu));
+                if (a >> 16) atomicAdd(row + o_pg_pred + lane * G + r, (unsigned long long)(a >> 16));
+            }
+        }
+        if (lane < (unsigned)G) {
+            for (int r = 0; r < G; ++r) {
+                const unsigned g = cnt(MC_GG + r, lane);
+                if (g & 0xffffu) atomicAdd(row + o_gg_tp + lane * G + r, (unsigned long long)(g & 0xffffu));
+                if (g >> 16) atomicAdd(row + o_gg_sum + lane * G + r, (unsigned long long)(g >> 16));
+            }
+        }
+        if (lane == 0) {
+            for (int r = 0; r < G; ++r) {
+                const unsigned g = cnt(MC_GS + r, 0) & 0xffffu;
+                if (g) atomicAdd(row + o_gs + r, (unsigned long long)g);
+            }
+            if (want_major) {
+                const unsigned m = cnt(MC_MAJ, 0), mg = cnt(MC_MAJG, 0);
+                if (m & 0xffffu) atomicAdd(row + o_maj, (unsigned long long)(m & 0xffffu));
+                if (m >> 16) atomicAdd(row + o_maj + 1, (unsigned long long)(m >> 16));
+                if (mg) atomicAdd(row + o_maj + 2, (unsigned long long)mg);
+            }
+        }
+    }
+    __syncwarp();
+    for (unsigned i = lane; i < (kMsPpBytes + kMsCntBytes) / 4; i += 32) sts_u32(pp_a + 4u * i, 0u);
+    __syncwarp();
+}
+
+__device__ __forceinline__ void MsWarp::flush(const MsParams& ms, long long b, int P, int R, bool want_major) {
+    ms_flush_warp(nll_a, pp_a, cnt_a, ms, b, P, R, want_major);
+}
 
 }  // namespace vu

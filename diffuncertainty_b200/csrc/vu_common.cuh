@@ -250,6 +250,9 @@ struct StatParams {
     const double* ncc_gt_map;
     double* f64;
     long long* i64;
+    // VU_STAT_CLASS_COUNTS: (B, R, ncls, 3) tp / pred / gt per rater and class
+    long long* cls;
+    int ncls;
     // VU_STAT_PLATT_FIT (dataset-level outputs)
     long long* platt_i64;
     double* platt_f64;
@@ -313,6 +316,10 @@ __host__ __device__ inline size_t stats_smem_bytes(unsigned flags, int R, int th
     if (flags & VU_STAT_PLATT_FIT) n += (size_t)kPlattWords * sizeof(int) + (size_t)kPlattTab * 2 * sizeof(float);
     return n;
 }
+// the per-class counters of VU_STAT_CLASS_COUNTS ([rater][class][tp, pred, gt] of uint32, one set per CTA) follow the state above
+__host__ __device__ inline size_t stats_class_bytes(unsigned flags, int R, int ncls) {
+    return (flags & VU_STAT_CLASS_COUNTS) ? (size_t)R * ncls * 3 * sizeof(unsigned) : 0;
+}
 
 template <int THREADS, int REP = 16>
 struct StatsLayout {
@@ -324,6 +331,7 @@ struct StatsLayout {
     float4* CC;   // [unc]: (a2, b2, sgn, -) of the Platt expression, so that a lane can fetch its type's constants with one load
     int* phist;   // Platt-fit data [unc][bin][4]
     float* pT;    // [kPlattTab] edges, then [kPlattTab] reciprocals
+    unsigned* cc; // class counters [rater][class][3]
     int nF, nI;
     __device__ __forceinline__ StatsLayout(const StatParams& sp, void* smem) {
         nF = stats_num_fslots(sp.flags);
@@ -335,6 +343,7 @@ struct StatsLayout {
         CC = reinterpret_cast<float4*>(E + ((sp.flags & VU_STAT_CALIB) ? VU_N_UNC * kEdgePad : 0));
         phist = reinterpret_cast<int*>(CC + ((sp.flags & VU_STAT_CALIB) ? VU_N_UNC + 1 : 0));
         pT = reinterpret_cast<float*>(phist + kPlattWords);
+        cc = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(smem) + stats_smem_bytes(sp.flags, sp.gt.R, THREADS, REP));
     }
 };
 
@@ -362,6 +371,8 @@ __device__ __noinline__ void stats_init(const StatParams& sp, void* smem) {
         for (int t = ((int)threadIdx.x - TID0); t < VU_N_UNC; t += THREADS)
             L.CC[t] = make_float4(sp.calib[t].a2, sp.calib[t].b2, sp.calib[t].sgn, 0.f);
     }
+    if (sp.flags & VU_STAT_CLASS_COUNTS)
+        for (int t = ((int)threadIdx.x - TID0); t < sp.gt.R * sp.ncls * 3; t += THREADS) L.cc[t] = 0u;
     if (sp.flags & VU_STAT_PLATT_FIT) {
         for (int t = ((int)threadIdx.x - TID0); t < kPlattWords; t += THREADS) L.phist[t] = 0;
         for (int t = ((int)threadIdx.x - TID0); t < kPlattTab; t += THREADS) {
@@ -474,6 +485,13 @@ __device__ __noinline__ void stats_flush(const StatParams& sp, void* smem, long 
             }
         }
     }
+    if (flags & VU_STAT_CLASS_COUNTS) {
+        unsigned long long* crow = reinterpret_cast<unsigned long long*>(sp.cls) + b * ((long long)sp.gt.R * sp.ncls * 3);
+        for (int t = ((int)threadIdx.x - TID0); t < sp.gt.R * sp.ncls * 3; t += THREADS) {
+            const unsigned c = L.cc[t];
+            if (c) { atomicAdd(crow + t, (unsigned long long)c); L.cc[t] = 0u; }
+        }
+    }
     if (flags & VU_STAT_PLATT_FIT) {  // dataset-level: not tied to the image row
         for (int t = ((int)threadIdx.x - TID0); t < VU_N_UNC * VU_N_PLATT_BINS; t += THREADS) {
             int* h = L.phist + t * 4;
@@ -525,7 +543,7 @@ struct StatsCursor {
 // the slab is read with no-allocate loads), so that the statistics phase does not wait on HBM.
 template <int VEC>
 __device__ __forceinline__ void stats_prefetch_gt(const StatParams& sp, long long b, long long v) {
-    if (!(sp.flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC | VU_STAT_PLATT_FIT)) || !sp.gt.data) return;
+    if (!(sp.flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC | VU_STAT_PLATT_FIT | VU_STAT_CLASS_COUNTS)) || !sp.gt.data) return;
     const long long esz = sp.gt.dtype == VU_GT_U8 ? 1 : 8;
     if (sp.gt.sv == 1) {
         // the 32 x VEC voxels of a warp are one run of 128-byte lines per rater: the lanes share them out (one instruction for
@@ -631,7 +649,7 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
         for (int j = 0; j < VEC; ++j) n += (label[j] > 0);
         if (n) cs.is[IS_AREA * THREADS + tid] += (unsigned long long)n;
     }
-    if (!(flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC | VU_STAT_PLATT_FIT))) return;
+    if (!(flags & (VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC | VU_STAT_PLATT_FIT | VU_STAT_CLASS_COUNTS))) return;
 
     // ---- references: per voxel the number of valid / correct raters, as byte j of one word each (<= 8) -------------
     constexpr unsigned kBytes = VEC == 4 ? 0xffffffffu : (VEC == 2 ? 0x0000ffffu : 0x000000ffu);
@@ -704,6 +722,39 @@ __device__ VU_STATS_INLINE void stats_tile_t(const StatParams& sp, void* smem, b
                     if (tp | ps | gs)
                         cs.is[(IS_DICE + r0 + i) * THREADS + tid] +=
                             (unsigned long long)tp | ((unsigned long long)ps << kPackBits) | ((unsigned long long)gs << (2 * kPackBits));
+                }
+            }
+        }
+    }
+    if (flags & VU_STAT_CLASS_COUNTS) {
+        // Per rater one counter update per (label, reference) pair present in the warp: neighbouring voxels mostly carry the
+        // same pair, so the lanes are grouped by it (match.any) and the first lane of a group adds the group's size.  Every
+        // lane of the warp walks through here; the references come from L1 (the loop above has just read them).
+        const int Rr = sp.gt.data ? sp.gt.R : 0, ncls = sp.ncls;
+        for (int r = 0; r < Rr; ++r) {
+            long long g[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) g[j] = -1;
+            if (active) {
+                if (sizeof(GT) == 1) {
+                    const unsigned w = load_gt_bytes<VEC>(sp.gt, b, r, v);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) g[j] = (long long)((w >> (8 * j)) & 0xffu);
+                } else {
+                    load_gt<VEC>(sp.gt, b, r, v, g, (long long)0);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const bool ok = active && !(sp.gt.has_ignore && g[j] == sp.gt.ignore) && g[j] >= 0 && g[j] < ncls && label[j] < ncls;
+                const unsigned key = ok ? ((unsigned)label[j] << 8) | (unsigned)g[j] : 0xffffffffu;
+                const unsigned grp = __match_any_sync(kFull, key);
+                if (ok && lane == __ffs(grp) - 1) {
+                    const unsigned n = __popc(grp);
+                    unsigned* c = cs.cc + (r * ncls) * 3;
+                    atomicAdd(c + label[j] * 3 + 1, n);
+                    atomicAdd(c + (int)g[j] * 3 + 2, n);
+                    if ((long long)label[j] == g[j]) atomicAdd(c + label[j] * 3, n);
                 }
             }
         }

@@ -81,6 +81,69 @@ class MemberScores:
         return float(np.mean(nll, dtype=np.float32)) if nll.size else 0.0
 
 
+class MemberScoreBuffers:
+    """Device outputs of the member-level scores for a batch of B images: ``nll_sum`` (B, R, P) float64, ``nll_count`` (B, R),
+    ``nll_bad`` (B), ``ged_counts`` (B, vu_ged_cols(P, R)) int64.  They ACCUMULATE like the statistics rows (zero them with
+    ``zero_()`` to start over); ``scores()`` wraps them in a ``MemberScores``."""
+
+    def __init__(self, P: int, B: int, R: int, device, nll: bool = True, ged: bool = True, eps: float = 1e-12):
+        lib = _lib.load()
+        self.P, self.B, self.R, self.eps = P, B, R, float(eps)
+        self.flags = (_lib.MS_NLL if nll else 0) | (_lib.MS_GED if ged else 0)
+        self.nll_sum = torch.zeros((B, R, P), dtype=torch.float64, device=device) if nll else None
+        self.nll_count = torch.zeros((B, R), dtype=torch.int64, device=device) if nll else None
+        self.nll_bad = torch.zeros((B,), dtype=torch.int64, device=device) if nll else None
+        self.ged_counts = torch.zeros((B, int(lib.vu_ged_cols(P, R))), dtype=torch.int64, device=device) if ged else None
+
+    def zero_(self) -> None:
+        for t in (self.nll_sum, self.nll_count, self.nll_bad, self.ged_counts):
+            if t is not None:
+                t.zero_()
+
+    def fill(self, m: "_lib.MemberOut", P: int, B: int, R: int, device) -> None:
+        if (P, B, R) != (self.P, self.B, self.R) or (self.nll_sum if self.nll_sum is not None else self.ged_counts).device != device:
+            raise ValueError(f"MemberScoreBuffers were made for P, B, R = {(self.P, self.B, self.R)}, this launch has {(P, B, R)}")
+        m.flags, m.eps = self.flags, self.eps
+        if self.nll_sum is not None:
+            m.nll_sum, m.nll_count, m.nll_bad = self.nll_sum.data_ptr(), self.nll_count.data_ptr(), self.nll_bad.data_ptr()
+        if self.ged_counts is not None:
+            m.ged_counts = self.ged_counts.data_ptr()
+
+    def scores(self, check: bool = True) -> MemberScores:
+        if check and self.nll_bad is not None and int(self.nll_bad.sum()) != 0:
+            # torch.gather raises "index ... is out of bounds" in the reference (test_2D.py:1067)
+            raise RuntimeError("ground truth holds values that are neither a class index nor the ignore value")
+        return MemberScores(P=self.P, R=self.R, nll_sum=self.nll_sum, nll_count=self.nll_count, ged_counts=self.ged_counts,
+                            has_major=self.ged_counts is not None)
+
+
+def fused_pass_with_member_scores(softmax_pred, gt: GroundTruth, *, nll: bool = True, ged: bool = True, eps: float = 1e-12,
+                                  out: Optional[MemberScoreBuffers] = None, **fused_kwargs):
+    """``fused_pass`` (maps, labels, statistics) AND the member-level scores of ``member_scores`` for the same batch: what
+    ``Tester.process_output`` computes per image (test_2D.py:968-1120) in one read of the slab where the kernel supports it
+    (binary slabs, at most 32 members and 4 uint8 references; see ``vu_member_out`` in valunc.h), in two passes otherwise.
+    Returns (FusedResult, MemberScores); ``fused_kwargs`` are those of ``fused_pass`` (``stats`` must not be 0 for the
+    single-pass form)."""
+    if gt is None:
+        raise ValueError("member scores need ground truth")
+    probe = _lib.Slab()
+    P, B, Cn, spatial, dev, _keep = fill_slab(probe, softmax_pred)
+    seg = gt.seg if gt.seg.dim() > 1 + len(spatial) else gt.seg.unsqueeze(1)
+    R = int(seg.shape[1])
+    can_ged = ged and Cn == 2
+    if ged and not can_ged:
+        raise ValueError("ged_binary_fast expects (P, 2, H, W) softmax input for binary segmentation")  # ged_fast.py:33-34
+    bufs = out if out is not None else MemberScoreBuffers(P, B, R, dev, nll=nll, ged=ged, eps=eps)
+    try:
+        res = fused_pass(softmax_pred, gt, members_out=bufs, **fused_kwargs)
+        return res, bufs.scores()
+    except NotImplementedError:
+        pass
+    res = fused_pass(softmax_pred, gt, **fused_kwargs)
+    ms = member_scores(softmax_pred, gt, nll=nll, ged=ged, mean_labels=res.labels if ged else None, eps=eps)
+    return res, ms
+
+
 def ged_from_counts(c: Dict[str, np.ndarray], additional_metrics=("dice",)) -> Dict[str, float]:
     """ged_fast.py:60-140 on the integer counts, in float32 like the reference (counts above 2^24 round the same way)."""
     f = np.float32

@@ -76,11 +76,16 @@ class Partials:
     packing kernels, and the combined rows are bit-identical at any GPU count.  The dataset-level histograms are the column
     sums of the gathered rows and are formed on the host (``result``)."""
 
-    def __init__(self, n_images: int, device):
+    def __init__(self, n_images: int, device, class_shape: Optional[Tuple[int, int]] = None):
+        """``class_shape`` = (R, C): the buffer also carries the per-rater, per-class tp / pred / gt counts of
+        ``STAT_CLASS_COUNTS`` (n_images x R x C x 3 int64) behind the rows."""
         self.n_images = n_images
-        self.buf = torch.zeros(n_images * (I64["COLS"] + F64["COLS"]), dtype=torch.int64, device=device)
-        self.rows_i = self.buf[:n_images * I64["COLS"]].view(n_images, I64["COLS"])
-        self.rows_f = self.buf[n_images * I64["COLS"]:].view(torch.float64).view(n_images, F64["COLS"])
+        n_i, n_f = n_images * I64["COLS"], n_images * F64["COLS"]
+        n_c = n_images * class_shape[0] * class_shape[1] * 3 if class_shape else 0
+        self.buf = torch.zeros(n_i + n_f + n_c, dtype=torch.int64, device=device)
+        self.rows_i = self.buf[:n_i].view(n_images, I64["COLS"])
+        self.rows_f = self.buf[n_i:n_i + n_f].view(torch.float64).view(n_images, F64["COLS"])
+        self.rows_c = self.buf[n_i + n_f:].view(n_images, class_shape[0], class_shape[1], 3) if class_shape else None
 
     def local(self, lo: int, hi: int):
         """(stats_f64, stats_i64) of the images lo .. hi - 1: the ``stats_out`` argument of ``fused_pass``."""
@@ -102,7 +107,8 @@ class Partials:
         return SweepResult(n_images=self.n_images, n_voxels=n_voxels, n_raters=n_raters,
                            bin_total=i[:, I64["BIN_TOTAL"]:I64["BIN_TOTAL"] + 63].sum(0).reshape(3, 21),
                            bin_true=i[:, I64["BIN_TRUE"]:I64["BIN_TRUE"] + 63].sum(0).reshape(3, 21),
-                           bin_sums=f[:, F64["BIN_SUMS"]:F64["BIN_SUMS"] + 63].sum(0).reshape(3, 21), rows_f64=f, rows_i64=i)
+                           bin_sums=f[:, F64["BIN_SUMS"]:F64["BIN_SUMS"] + 63].sum(0).reshape(3, 21), rows_f64=f, rows_i64=i,
+                           class_counts=None if self.rows_c is None else self.rows_c.cpu().numpy().copy())
 
 
 def pack_partials(rows_f64: torch.Tensor, rows_i64: torch.Tensor, lo: int, n_images: int) -> Partials:
@@ -135,6 +141,7 @@ class SweepResult:
     rows_i64: np.ndarray             # (n_images, 156)
     maps: Dict[str, torch.Tensor] = field(default_factory=dict)   # local images only (keep_maps)
     labels: Optional[torch.Tensor] = None
+    class_counts: Optional[np.ndarray] = None   # (n_images, R, C, 3) int64 tp / pred / gt (STAT_CLASS_COUNTS)
 
     def image_level(self, mean: bool = True) -> np.ndarray:
         s = self.rows_f64[:, F64["SUM"]:F64["SUM"] + 3]
@@ -146,6 +153,11 @@ class SweepResult:
         return np.where(n > 0, s / np.maximum(n, 1), s) if mean else s
 
     def dice(self) -> np.ndarray:
+        """Per-image Dice, mean over raters: the multi-class macro Dice of test_2D.py:901-918 when the sweep carried the class
+        counts of a slab with more than two classes, else the binary Dice of test_2D.py:873-899."""
+        if self.class_counts is not None and self.class_counts.shape[2] > 2:
+            c = self.class_counts
+            return _aurc.multiclass_dice_from_counts(c[..., 0], c[..., 1], c[..., 2])
         R = self.n_raters
         i = self.rows_i64
         return _aurc.binary_dice_from_counts(i[:, I64["DICE_TP"]:I64["DICE_TP"] + R], i[:, I64["DICE_PRED"]:I64["DICE_PRED"] + R],
@@ -208,7 +220,7 @@ class ShardedSweep:
             self._slab = torch.empty((cfg.P, n, cfg.C) + tuple(cfg.spatial), dtype=torch.float32, device=self.device)
         x = synth.synth_slab(cfg.P, n, cfg.C, cfg.spatial, seed=cfg.seed, first_image=first, scale=cfg.scale, out=self._slab)
         gt = None
-        if cfg.stats & (_lib.STAT_DICE | _lib.STAT_CALIB | _lib.STAT_NCC):
+        if cfg.stats & (_lib.STAT_DICE | _lib.STAT_CALIB | _lib.STAT_NCC | _lib.STAT_CLASS_COUNTS):
             gt = synth.synth_gt(x, cfg.R, seed=cfg.seed, first_image=first, flip=cfg.flip, ignore_frac=cfg.ignore_frac,
                                 ignore_value=255 if cfg.ignore_index is None else cfg.ignore_index)
         return x, gt
@@ -217,7 +229,8 @@ class ShardedSweep:
         from .uncertainty import GroundTruth, fused_pass
         cfg = self.cfg
         n_local = self.hi - self.lo
-        partials = Partials(cfg.n_images, self.device)
+        want_cls = bool(cfg.stats & _lib.STAT_CLASS_COUNTS)
+        partials = Partials(cfg.n_images, self.device, (cfg.R, cfg.C) if want_cls else None)
         rows_f, rows_i = partials.local(self.lo, self.hi)  # the kernel accumulates straight into the exchange buffer
         kept = {k: [] for k in UNC}
         kept_labels = []
@@ -226,7 +239,8 @@ class ShardedSweep:
             x, gt = self.source(self.lo + s, n)
             res = fused_pass(x, None if gt is None else GroundTruth(gt, cfg.ignore_index), stats=cfg.stats,
                              thresholds=cfg.thresholds, calib=self._calib, want_maps=cfg.keep_maps, want_labels=cfg.keep_maps,
-                             stats_out=(rows_f[s:s + n], rows_i[s:s + n]))
+                             stats_out=(rows_f[s:s + n], rows_i[s:s + n]),
+                             class_counts_out=partials.rows_c[self.lo + s:self.lo + s + n] if want_cls else None)
             if cfg.keep_maps:
                 for k in UNC:
                     kept[k].append(res.maps[k])

@@ -61,6 +61,7 @@ class FusedResult:
     n_raters: int
     stat_flags: int
     member_labels: Optional[torch.Tensor] = None   # (P, B, *S) uint8: argmax of every member (test_2D.py:810-818)
+    class_counts: Optional[torch.Tensor] = None    # (B, R, C, 3) int64: tp / pred / gt per rater and class (STAT_CLASS_COUNTS)
 
     # -- per-image scores, all computed on the host in float64 from the rows --
     def _rows(self):
@@ -104,6 +105,13 @@ class FusedResult:
         return (f[:, F64["BIN_SUMS"]:F64["BIN_SUMS"] + 63].reshape(B, 3, 21),
                 i[:, I64["BIN_TRUE"]:I64["BIN_TRUE"] + 63].reshape(B, 3, 21),
                 i[:, I64["BIN_TOTAL"]:I64["BIN_TOTAL"] + 63].reshape(B, 3, 21))
+
+    def class_count_arrays(self):
+        """(tp, pred, gt), each (B, R, C) int64: the integers of the multi-class Dice of test_2D.py:901-918."""
+        if self.class_counts is None:
+            raise ValueError("this pass was run without STAT_CLASS_COUNTS")
+        c = self.class_counts.cpu().numpy()
+        return c[..., 0], c[..., 1], c[..., 2]
 
     def ncc_sums(self):
         f, _ = self._rows()
@@ -219,7 +227,8 @@ def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0
                thresholds: Optional[Sequence[float]] = None, calib=None, label_lut: Optional[torch.Tensor] = None,
                want_maps: bool = True, want_labels: bool = True,
                stats_out: Optional[tuple] = None, maps_out: Optional[Dict[str, torch.Tensor]] = None,
-               labels_out: Optional[torch.Tensor] = None, platt_fit=None, want_member_labels: bool = False) -> FusedResult:
+               labels_out: Optional[torch.Tensor] = None, platt_fit=None, want_member_labels: bool = False,
+               members_out=None, class_counts_out: Optional[torch.Tensor] = None) -> FusedResult:
     """One launch over ``softmax_pred`` of shape (P, B, C, *S) (test_2D.py:1277) -- or over a list of P member tensors
     (B, C, *S), which are then read where they are (no torch.stack).
 
@@ -231,6 +240,9 @@ def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0
     platt_fit  : a ``calibration.PlattFitAccumulator`` for STAT_PLATT_FIT (dataset-level buffers)
     maps_out   : optional preallocated contiguous fp32 (B, *S) tensors keyed "TU","AU","EU"
                  (or "pred_entropy" when P == 1); labels_out: preallocated uint8 (B, *S)
+    members_out: a ``members.MemberScoreBuffers``: the member-level scores (GED counts, likelihood sums) are computed in the
+                 same pass -- one read of the slab.  Raises NotImplementedError when this launch cannot do that (see
+                 ``vu_member_out`` in valunc.h); ``members.fused_pass_with_member_scores`` falls back to a second pass then.
     """
     _lib.require_device()
     lib = _lib.load()
@@ -301,10 +313,25 @@ def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0
                 sf = torch.zeros((B, F64["COLS"]), dtype=torch.float64, device=dev)
                 si = torch.zeros((B, I64["COLS"]), dtype=torch.int64, device=dev)
             a.stats_f64, a.stats_i64 = sf.data_ptr(), si.data_ptr()
+        cls = None
+        if stats & _lib.STAT_CLASS_COUNTS:
+            if gt is None:
+                raise ValueError("STAT_CLASS_COUNTS needs ground truth")
+            shape = (B, int(a.gt.R), Cn, 3)
+            cls = class_counts_out if class_counts_out is not None else torch.zeros(shape, dtype=torch.int64, device=dev)
+            if tuple(cls.shape) != shape or cls.dtype != torch.int64 or not cls.is_contiguous() or cls.device != dev:
+                raise ValueError(f"class_counts_out must be a contiguous int64 {shape} tensor on {dev}")
+            a.class_counts = cls.data_ptr()
+        if members_out is not None:
+            members_out.fill(a.members, P, B, int(a.gt.R) if gt is not None else 0, dev)
+            if not lib.vu_fused_members_supported(C.byref(a)):
+                raise NotImplementedError("vu_fused_pass cannot compute the member-level scores in this launch: "
+                                          + lib.vu_last_error().decode(errors="replace"))
         _lib.check(lib.vu_fused_pass(C.byref(a), _lib.current_stream_ptr()), "vu_fused_pass")
     del keep, ptr_keep
     return FusedResult(maps=maps, labels=labels, stats_f64=sf, stats_i64=si, n_voxels=V,
-                       n_raters=int(a.gt.R) if gt is not None else 0, stat_flags=int(stats), member_labels=member_labels)
+                       n_raters=int(a.gt.R) if gt is not None else 0, stat_flags=int(stats), member_labels=member_labels,
+                       class_counts=cls)
 
 
 def calculate_uncertainty(softmax_preds: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -336,7 +363,8 @@ def mean_argmax_labels(softmax_pred: torch.Tensor) -> torch.Tensor:
 
 def map_stats(maps: Dict[str, torch.Tensor], labels: Optional[torch.Tensor] = None, gt: Optional[GroundTruth] = None, *,
               stats: int, thresholds: Optional[Sequence[float]] = None, calib=None, label_lut: Optional[torch.Tensor] = None,
-              ncc_gt_map: Optional[torch.Tensor] = None, stats_out: Optional[tuple] = None) -> FusedResult:
+              ncc_gt_map: Optional[torch.Tensor] = None, stats_out: Optional[tuple] = None, n_classes: Optional[int] = None,
+              class_counts_out: Optional[torch.Tensor] = None) -> FusedResult:
     """The statistics of ``fused_pass`` on maps / labels that already exist in device memory -- what the reference's
     file-based evaluation works on (evaluation/eval_experiments.py:348-355).  ``maps``: {"TU","AU","EU"} -> (B, *S) contiguous
     fp32 CUDA tensors (a missing key skips that type); ``labels``: (B, *S) uint8; the other arguments as in ``fused_pass``."""
@@ -387,7 +415,16 @@ def map_stats(maps: Dict[str, torch.Tensor], labels: Optional[torch.Tensor] = No
             sf = torch.zeros((B, F64["COLS"]), dtype=torch.float64, device=dev)
             si = torch.zeros((B, I64["COLS"]), dtype=torch.int64, device=dev)
         a.stats_f64, a.stats_i64 = sf.data_ptr(), si.data_ptr()
+        cls = None
+        if stats & _lib.STAT_CLASS_COUNTS:
+            if gt is None or n_classes is None:
+                raise ValueError("STAT_CLASS_COUNTS needs ground truth and n_classes")
+            shape = (B, int(a.gt.R), int(n_classes), 3)
+            cls = class_counts_out if class_counts_out is not None else torch.zeros(shape, dtype=torch.int64, device=dev)
+            if tuple(cls.shape) != shape or cls.dtype != torch.int64 or not cls.is_contiguous():
+                raise ValueError(f"class_counts_out must be a contiguous int64 {shape} tensor")
+            a.class_counts, a.n_classes = cls.data_ptr(), int(n_classes)
         _lib.check(lib.vu_map_stats(C.byref(a), _lib.current_stream_ptr()), "vu_map_stats")
     del keep
     return FusedResult(maps={k: m for k, m in zip(UNC_KEYS, present) if m is not None}, labels=labels, stats_f64=sf, stats_i64=si,
-                       n_voxels=V, n_raters=int(a.gt.R) if gt is not None else 0, stat_flags=int(stats))
+                       n_voxels=V, n_raters=int(a.gt.R) if gt is not None else 0, stat_flags=int(stats), class_counts=cls)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VU_ABI_VERSION 2
+#define VU_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define VU_API __attribute__((visibility("default")))
@@ -66,6 +66,10 @@ typedef enum vu_status {
                                    level: accumulates into platt_i64 / platt_f64,
                                    not into the per-image rows                   */
 #define VU_N_PLATT_BINS 256     /* ace.py:17,31: np.logspace(-12, 2, 257) edges  */
+#define VU_STAT_CLASS_COUNTS 0x80u /* test_2D.py:901-918 (multi-class Dice, the risk of the AURC of GTA-like sets): per rater and
+                                   class the integers its macro Dice is made of -- tp = #(label == c & gt == c), pred =
+                                   #(label == c), gt = #(gt == c) over the voxels the rater does not ignore (needs gt);
+                                   accumulates into class_counts, not into the per-image rows                      */
 
 /* ---- layout of one row of the per-image statistics buffers --------------- */
 /* double row (VU_F64_COLS doubles per image)                                 */
@@ -141,6 +145,22 @@ typedef struct vu_platt_fit {
     float edge_u[VU_N_PLATT_BINS + 1];
 } vu_platt_fit;
 
+/* Member-level scores computed by vu_fused_pass itself, while it streams the slab for the maps (one read of the slab instead
+ * of the two of vu_fused_pass + vu_member_scores): the outputs, their layout and their meaning are those of
+ * vu_member_scores_args below (GED: ged_fast.py:44-131 with the majority counts taken from the labels the pass computes;
+ * NLL: test_2D.py:1043-1120).  flags == 0: not requested.  Available for binary slabs (C == 2) of at most 32 members with
+ * unit voxel stride and 16-byte aligned rows, at most 4 uint8 references with word-aligned rows, and a statistics mask the
+ * unified kernel is built for (vu_fused_members_supported); otherwise vu_fused_pass returns VU_ERR_UNSUPPORTED and the caller
+ * runs vu_member_scores as a second pass.                                                                                */
+typedef struct vu_member_out {
+    uint32_t flags;      /* VU_MS_NLL | VU_MS_GED                              */
+    float eps;           /* test_2D.py:1043: 1e-12                             */
+    double* nll_sum;     /* (B, R, P), accumulated                             */
+    int64_t* nll_count;  /* (B, R)                                             */
+    int64_t* nll_bad;    /* (B)                                                */
+    int64_t* ged_counts; /* (B, vu_ged_cols(P, R))                             */
+} vu_member_out;
+
 typedef struct vu_fused_args {
     uint32_t struct_size; /* sizeof(vu_fused_args), ABI check                 */
     uint32_t stat_flags;  /* VU_STAT_* or 0                                   */
@@ -174,6 +194,10 @@ typedef struct vu_fused_args {
      * (test_2D.py:810-818); they are also what prediction_shape_stats
      * (mean_pred=False) and GED consume.                                      */
     uint8_t* member_labels;
+    vu_member_out members; /* member-level scores in the same pass (see vu_member_out) */
+    /* VU_STAT_CLASS_COUNTS: (B, R, C, 3) int64, [.., c, 0] tp, [.., c, 1] pred, [.., c, 2] gt; accumulated.  References that
+     * are not a class index (and not the ignore value) are skipped here; dice() raises on them (dice_wrapped.py:57-58).   */
+    int64_t* class_counts;
 } vu_fused_args;
 
 /* ABI / build info ---------------------------------------------------------- */
@@ -198,6 +222,9 @@ VU_API int vu_struct_size(int which);   /* 0 vu_fused_args, 1 vu_map_stats_args,
  *   NCC sums                 ncc.py:17-27
  * reading the slab exactly once.                                             */
 VU_API int vu_fused_pass(const vu_fused_args* args, void* stream);
+/* 1 if vu_fused_pass can compute args->members in the same pass (see vu_member_out), 0 if not (the reason is left in
+ * vu_last_error).  Nothing is launched.                                                                                  */
+VU_API int vu_fused_members_supported(const vu_fused_args* args);
 
 /* Same reductions on maps / labels that already exist in device memory (the
  * reference's file-based evaluation, evaluation/eval_experiments.py:348-355,
@@ -221,6 +248,8 @@ typedef struct vu_map_stats_args {
     const vu_platt_fit* platt_fit; /* HOST pointer (VU_STAT_PLATT_FIT)        */
     int64_t* platt_i64;            /* (3, 256, 2), accumulated                */
     double* platt_f64;             /* (3, 256), accumulated                   */
+    int64_t* class_counts;         /* VU_STAT_CLASS_COUNTS: (B, R, n_classes, 3), accumulated */
+    int32_t n_classes;             /* classes of `labels` (1..256), VU_STAT_CLASS_COUNTS only */
 } vu_map_stats_args;
 VU_API int vu_map_stats(const vu_map_stats_args* args, void* stream);
 

@@ -755,3 +755,50 @@ def reference_pipeline_image(image_preds: torch.Tensor, gt: np.ndarray | None = 
     res["area"] = compute_area(label)
     res["border"] = compute_border(label)
     return res
+
+
+# ---------------------------------------------------------------------------
+# multi-class Dice inputs (uncertainty_modeling/test_2D.py:901-918 -> evaluation/metrics/dice_wrapped.py:17-104)
+# ---------------------------------------------------------------------------
+def class_counts(label, gt, n_classes, ignore_value=None):
+    """Per rater and class the integers dice_wrapped's macro Dice is made of: tp = #(label == c & gt == c), pred =
+    #(label == c), gt = #(gt == c), over the pixels the rater does not ignore (dice_wrapped.py:47,74-75 move the ignored
+    pixels into a channel that DiceScore(include_background=False) drops).  label: (*S) ints, gt: (R, *S) ints.
+    Returns three (R, n_classes) int64 arrays."""
+    label = np.asarray(label).astype(np.int64).ravel()
+    gt = np.asarray(gt).astype(np.int64).reshape(np.asarray(gt).shape[0], -1)
+    R = gt.shape[0]
+    tp = np.zeros((R, n_classes), np.int64)
+    ps = np.zeros((R, n_classes), np.int64)
+    gs = np.zeros((R, n_classes), np.int64)
+    for r in range(R):
+        valid = np.ones(label.shape, bool) if ignore_value is None else gt[r] != ignore_value
+        valid = valid & (gt[r] >= 0) & (gt[r] < n_classes)  # (dice() raises on other values; the kernel skips them)
+        lv, gv = label[valid], gt[r][valid]
+        ps[r] = np.bincount(lv, minlength=n_classes)[:n_classes]
+        gs[r] = np.bincount(gv, minlength=n_classes)[:n_classes]
+        tp[r] = np.bincount(lv[lv == gv], minlength=n_classes)[:n_classes]
+    return tp, ps, gs
+
+
+def macro_dice_reference_semantics(label, gt_rater, n_classes, ignore_value=None):
+    """ONE rater through dice_wrapped.dice(..., include_background=False, average="macro") with torchmetrics' DiceScore
+    restated on one-hot arrays (torchmetrics >= 1.6 _dice_score_update / _dice_score_compute: per class 2 * intersection /
+    (pred + target) over the channels 1..C-1, nan-mean over the classes with a non-zero denominator).  torchmetrics is not
+    installed here: parity of this reduction is unpinned; it cross-checks the count-based form."""
+    pred = np.asarray(label).astype(np.int64).ravel().copy()
+    tgt = np.asarray(gt_rater).astype(np.int64).ravel().copy()
+    ign = np.zeros(tgt.shape, bool) if ignore_value is None else tgt == ignore_value
+    if ign.all():
+        return 1.0
+    pred[ign] = 0
+    tgt[ign] = 0
+    if (pred[~ign] == 0).all() and (tgt[~ign] == 0).all():
+        return 1.0
+    vals = []
+    for c in range(1, n_classes):
+        p, t = pred == c, tgt == c
+        den = p.sum() + t.sum()
+        if den > 0:
+            vals.append(2.0 * (p & t).sum() / den)
+    return float(np.mean(vals)) if vals else float("nan")
