@@ -50,9 +50,12 @@ constexpr int kUniRep = 16;  // histogram replicas per warp (two lanes share one
 // LEVELS: cascade levels of the member sum (1: P <= 17, 2: P <= 271); CT consumer threads; G members per ring stage;
 // FL: the statistics mask (compile time); RMAX: raters the reference registers are sized for.
 // MINB: CTAs per SM (each with its own producer warp, ring and histograms: independent pipelines that fill each other's gaps).
-// MS: the member-level scores (GED counts, likelihood sums; members_fold.cuh) are computed in the same pass.
-template <int LEVELS, int CT, int G, unsigned FL, int RMAX, int MINB, bool MS>
+// MSS >= 0: the member-level scores (GED counts, likelihood sums; members_fold.cuh) are computed in the same pass, with MSS
+// shuffle steps per member pair before the partial sums go to shared memory (MsGeom); MSS < 0: no member scores.
+template <int LEVELS, int CT, int G, unsigned FL, int RMAX, int MINB, int MSS>
 __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ K1UniParams prm) {
+    constexpr bool MS = MSS >= 0;
+    constexpr int kMsS = MS ? MSS : 3;
     static_assert(!MS || RMAX == kMsR, "the member-score fold is built for up to four raters");
     constexpr int C = 2, VEC = 4;
     constexpr int TV = CT * VEC;  // voxels per tile
@@ -127,10 +130,10 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
     StatAcc<FL, RMAX> A;
     A.clear();
     int cur_b = -1, vt_begin = 0;
-    MsWarp mw;
+    MsWarp<kMsS> mw;
     const bool ms_nll = MS && (prm.ms.flags & VU_MS_NLL), ms_ged = MS && (prm.ms.flags & VU_MS_GED);
     const bool ign_is_one = sp.gt.has_ignore && sp.gt.ignore == 1;
-    if constexpr (MS) mw.init(vu_uni_smem + prm.ms_offset + (unsigned)warp * kMsWarpBytes);
+    if constexpr (MS) mw.init(vu_uni_smem + prm.ms_offset + (unsigned)warp * MsWarp<kMsS>::kWarpBytes);
     auto flush = [&]() {
         stats2_flush_regs<FL, RMAX, kUniRep>(A, sp, cur_b);
         if (FL & VU_STAT_CALIB) stats2_flush_hist_warp<kUniRep>(sp, st_smem, cur_b, warp);
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
                 }
                 // one member after the other (the registers do not hold both members' logarithms); only the fold over the lanes
                 // is shared
-                const bool slow = ms_nll && (!mw.fast || __any_sync(kFull, (MsWarp::nan_probe(xa) + MsWarp::nan_probe(xb)) != 0.0f));
+                const bool slow = ms_nll && (!mw.fast || __any_sync(kFull, (MsWarp<kMsS>::nan_probe(xa) + MsWarp<kMsS>::nan_probe(xb)) != 0.0f));
                 float va[kMsVals], vb[kMsVals];
 #pragma unroll
                 for (int i = 0; i < kMsVals; ++i) { va[i] = 0.f; vb[i] = 0.f; }
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
                     if (ms_ged) mw.member_labels(p0 + 1, xb);
                     if (ms_nll) mw.member_values(xb, Lb, sp.gt.R, prm.ms.log2eps, slow, vb);
                 }
-                if (ms_nll) mw.fold_pair(p0, va, vb, has_b);
+                if (ms_nll) mw.fold_pair(p0, va, vb);
             } else {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
@@ -275,11 +278,12 @@ struct UniVariant {
     int RMAX, MINB;
     int use;  // 1: automatic selection, 0: only through the "k1_uni_shape" option (tuning sweep)
     int ms;   // 1: computes the member-level scores as well
+    int mss;  // ... with this many shuffle steps per member pair (MsGeom)
     K1UniKernel fn;
 };
 #define VU_UNI(LEVELS, CT, G, FL, RMAX, MINB, USE) \
-    { LEVELS, CT, G, FL, RMAX, MINB, USE, 0, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX, MINB, false> }
-#define VU_UNI_MS(LEVELS, CT, G, FL) { LEVELS, CT, G, FL, 4, 1, 1, 1, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, 4, 1, true> }
+    { LEVELS, CT, G, FL, RMAX, MINB, USE, 0, -1, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX, MINB, -1> }
+#define VU_UNI_MS(LEVELS, CT, FL, MSS, USE) { LEVELS, CT, 2, FL, 4, 1, USE, 1, MSS, (K1UniKernel)k1_uni<LEVELS, CT, 2, FL, 4, 1, MSS> }
 // Registers are allocated per SM sub-partition: 16 consumer warps + the producer put 5 warps on one of them (96 registers per
 // thread), 15 + 1 leave 4 on each (128).  The masks with calibration histograms need the 128 (they spill 260-720 bytes at
 // 96); the others do not, and keep the power-of-two tile.
@@ -298,8 +302,10 @@ static const UniVariant kUni[] = {
     // tuning candidates ("k1_uni_shape" = CT * 100 + G * 10 + MINB)
     VU_UNI(1, 480, 1, 0x1du, 4, 1, 0), VU_UNI(1, 480, 3, 0x1du, 4, 1, 0),
     // with the member-level scores (GED counts + likelihood sums) in the same pass: 15 + 1 warps (128 registers)
-    VU_UNI_MS(1, 480, 2, 0x21u), VU_UNI_MS(2, 480, 2, 0x21u), VU_UNI_MS(1, 480, 2, 0x2du), VU_UNI_MS(2, 480, 2, 0x2du),
-    VU_UNI_MS(1, 480, 2, 0x01u), VU_UNI_MS(2, 480, 2, 0x01u),
+    VU_UNI_MS(1, 480, 0x21u, 3, 1), VU_UNI_MS(2, 480, 0x21u, 3, 1), VU_UNI_MS(1, 480, 0x2du, 3, 1), VU_UNI_MS(2, 480, 0x2du, 3, 1),
+    VU_UNI_MS(1, 480, 0x01u, 3, 1), VU_UNI_MS(2, 480, 0x01u, 3, 1),
+    // (r02k, configs[3] pipeline: 15 warps with three shuffle steps 2.08 ms; 8 warps without shuffles (166 registers) 2.32 ms,
+    //  12 warps with one or two steps 2.28 ms, 10 warps with one step 2.25 ms -- the warp count matters more than the shuffles)
 };
 static const int kNumUni = (int)(sizeof(kUni) / sizeof(kUni[0]));
 
@@ -342,10 +348,11 @@ int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     for (int i = 0; i < kNumUni && !pick; ++i) {
         const UniVariant& u = kUni[i];
         if (u.LEVELS != need_levels || u.FL != st.flags || u.RMAX < rmax || (u.ms != 0) != want_ms) continue;
-        if (shape && !want_ms ? (u.CT * 100 + u.G * 10 + u.MINB == shape) : u.use == 1) pick = &u;
+        const long long ushape = u.ms ? u.CT * 100 + u.G * 10 + u.mss : u.CT * 100 + u.G * 10 + u.MINB;
+        if (shape ? ushape == shape : u.use == 1) pick = &u;
     }
-    if (!pick) return shape && !want_ms ? set_error(VU_ERR_UNSUPPORTED, "k1_uni_shape: no such kernel for this launch")
-                                        : no("no unified kernel is built for this statistics mask");
+    if (!pick) return shape ? set_error(VU_ERR_UNSUPPORTED, "k1_uni_shape: no such kernel for this launch")
+                            : no("no unified kernel is built for this statistics mask");
     if (dry_run) return VU_OK;
 
     K1UniParams prm;
@@ -372,7 +379,8 @@ int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     if (prm.total_tiles >= (1LL << 31)) return set_error(VU_ERR_UNSUPPORTED, "more than 2^31 tiles in one launch; split the batch");
 
     const size_t stage_bytes = (size_t)pick->G * 2 * tile_vox * sizeof(float);
-    const size_t stats_bytes = (stats2_smem_bytes(st.flags, pick->CT, kUniRep) + 15) / 16 * 16 + (want_ms ? (size_t)(pick->CT / 32) * kMsWarpBytes : 0);
+    const size_t ms_warp = !want_ms ? 0 : (pick->mss == 0 ? ms_warp_bytes<0>() : pick->mss == 1 ? ms_warp_bytes<1>() : pick->mss == 2 ? ms_warp_bytes<2>() : ms_warp_bytes<3>());
+    const size_t stats_bytes = (stats2_smem_bytes(st.flags, pick->CT, kUniRep) + 15) / 16 * 16 + (size_t)(pick->CT / 32) * ms_warp;
     const size_t budget = (pick->MINB == 1 ? 227 : (pick->MINB == 2 ? 113 : 75)) * 1024 - (pick->MINB > 1 ? 1024 : 0);  // per CTA (1 KB reserved per CTA)
     const size_t fixed = 256 /* barriers */ + 256 /* alignment slack */ + stats_bytes;
     long long nstages = get_option("k1_tma_stages", 0);

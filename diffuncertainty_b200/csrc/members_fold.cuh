@@ -14,7 +14,7 @@
 //         not depend on the rater: per member one sum of l0 and one FMA per rater and voxel on 0 / 1 float masks.  The five
 //         per-lane values (sum l0, four raters) are folded 8 lanes to 1 by three shuffles and added to lane-private float32
 //         columns in shared memory; ln 2 is applied once, in float64, when the warp leaves the image.
-// All per-warp state lives in kMsWarpBytes of shared memory; a warp flushes on its own (global atomics) when it moves to
+// All per-warp state lives in ms_warp_bytes<S>() of shared memory; a warp flushes on its own (global atomics) when it moves to
 // another image.
 #pragma once
 #include "vu_common.cuh"
@@ -33,13 +33,19 @@ struct MsParams {
 
 constexpr int kMsP = 32, kMsR = 4;
 constexpr int kMsVals = 1 + kMsR;  // per member: sum of l0 over the voxels, then one value per rater
-constexpr int kMsCols = 4;         // columns per member (the 32 lane sums are folded 8 to 1 before they are stored)
-constexpr int kMsValPad = 8;       // floats per (member, column): the five values, padded to 32 bytes (vector load / store)
+// The five per-lane values of a member have to be summed over the lanes of the warp.  S = shuffle steps taken per member
+// before the partial sums go to lane-private columns in shared memory: 32 >> S columns per (member pair, value), the lanes
+// whose low S bits are zero own one each.  S = 0: no shuffles at all, 20 KB per warp; S = 3: three steps, 2.5 KB per warp.
+// The columns hold the values of two members side by side (f32x2): one packed add serves both.
+template <int S> struct MsGeom {
+    static constexpr int kCols = 32 >> S;
+    static constexpr int kNllBytes = (kMsP / 2) * kMsVals * kCols * 8;
+};
 // counter words per lane (two 16-bit counters each; a warp flushes at least every 255 tiles of 128 voxels)
 enum { MC_PG = 0 /* [r]: pg_tp | pg_pred << 16 */, MC_GG = 4 /* [r]: gg_tp | gg_sum << 16 */, MC_GS = 8 /* [r]: g_sum | valid << 16 */,
        MC_POS = 12 /* pos | bad << 16 */, MC_MAJ = 13 /* tp | pred << 16 */, MC_MAJG = 14, MC_N = 15 };
-constexpr int kMsNllBytes = kMsP * kMsCols * kMsValPad * 4, kMsPpBytes = kMsP * 32 * 2, kMsCntBytes = MC_N * 32 * 4;
-constexpr int kMsWarpBytes = kMsNllBytes + kMsPpBytes + kMsCntBytes;  // 4096 + 2048 + 1920
+constexpr int kMsPpBytes = kMsP * 32 * 2, kMsCntBytes = MC_N * 32 * 4;
+template <int S> constexpr int ms_warp_bytes() { return MsGeom<S>::kNllBytes + kMsPpBytes + kMsCntBytes; }
 
 __device__ __forceinline__ unsigned lds_u32(unsigned a) { unsigned r; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
 __device__ __forceinline__ void sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
@@ -47,10 +53,89 @@ __device__ __forceinline__ unsigned lds_u16(unsigned a) { unsigned short r; asm 
 __device__ __forceinline__ void sts_u16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ void smem_add_u32(unsigned a, unsigned v) { sts_u32(a, lds_u32(a) + v); }
 
+// add a warp's partials into the rows of image b (layout: valunc.h, vu_member_scores) and clear them.  Out of line and on
+// plain addresses, so that the per-tile state of MsWarp stays in registers.
+__device__ __noinline__ void ms_flush_warp(unsigned nll_a, int cols, unsigned pp_a, unsigned cnt_a, const MsParams& ms, long long b, int P,
+                                           int R, bool want_major) {
+    const unsigned lane = threadIdx.x & 31;
+    auto cnt = [&](int c, unsigned l) { return lds_u32(cnt_a + ((unsigned)c * 32u + l) * 4u); };
+    __syncwarp();
+    if (ms.flags & VU_MS_NLL) {
+        if (lane < (unsigned)P) {
+            // lane p: member p is half (p & 1) of the packed columns of pair p >> 1; the lanes start at different columns so
+            // that they do not all hit one bank
+            double s[kMsVals];
+#pragma unroll
+            for (int i = 0; i < kMsVals; ++i) {
+                s[i] = 0.0;
+                for (int c0 = 0; c0 < cols; ++c0) {
+                    const unsigned c = (c0 + lane) & (unsigned)(cols - 1);
+                    const unsigned a = nll_a + ((((lane >> 1) * kMsVals + i) * cols + c) * 2u + (lane & 1u)) * 4u;
+                    s[i] += (double)__uint_as_float(lds_u32(a));
+                    sts_u32(a, 0u);
+                }
+            }
+            for (int r = 0; r < R; ++r) {
+                const double t = (s[0] + s[1 + r]) * 0.6931471805599453;  // log2 -> ln
+                if (t != 0.0) atomicAdd(ms.nll_sum + (b * R + r) * P + lane, t);
+            }
+        }
+        for (int r = 0; r < R; ++r) {
+            const unsigned n = __reduce_add_sync(kFull, cnt(MC_GS + r, lane) >> 16);
+            if (lane == 0 && n) atomicAdd(ms.nll_cnt + b * R + r, (unsigned long long)n);
+        }
+        const unsigned nb = __reduce_add_sync(kFull, cnt(MC_POS, lane) >> 16);
+        if (lane == 0 && nb) atomicAdd(ms.nll_bad + b, (unsigned long long)nb);
+    }
+    if (ms.flags & VU_MS_GED) {
+        const int G = R;
+        const int o_pg_pred = P * G, o_gs = 2 * P * G, o_pp = o_gs + G, o_pos = o_pp + P * P, o_gg_tp = o_pos + P, o_gg_sum = o_gg_tp + G * G,
+                  o_maj = o_gg_sum + G * G;
+        unsigned long long* row = ms.ged + b * ms.ged_cols;
+        if (lane < (unsigned)P) {
+            for (int q = 0; q < P; ++q) {
+                const unsigned c = lds_u16(pp_a + ((unsigned)q * 32u + lane) * 2u);
+                if (c) atomicAdd(row + o_pp + lane * P + q, (unsigned long long)c);
+            }
+            const unsigned ps = cnt(MC_POS, lane) & 0xffffu;
+            if (ps) atomicAdd(row + o_pos + lane, (unsigned long long)ps);
+            for (int r = 0; r < G; ++r) {
+                const unsigned a = cnt(MC_PG + r, lane);
+                if (a & 0xffffu) atomicAdd(row + lane * G + r, (unsigned long long)(a & 0xffffu));
+                if (a >> 16) atomicAdd(row + o_pg_pred + lane * G + r, (unsigned long long)(a >> 16));
+            }
+        }
+        if (lane < (unsigned)G) {
+            for (int r = 0; r < G; ++r) {
+                const unsigned g = cnt(MC_GG + r, lane);
+                if (g & 0xffffu) atomicAdd(row + o_gg_tp + lane * G + r, (unsigned long long)(g & 0xffffu));
+                if (g >> 16) atomicAdd(row + o_gg_sum + lane * G + r, (unsigned long long)(g >> 16));
+            }
+        }
+        if (lane == 0) {
+            for (int r = 0; r < G; ++r) {
+                const unsigned g = cnt(MC_GS + r, 0) & 0xffffu;
+                if (g) atomicAdd(row + o_gs + r, (unsigned long long)g);
+            }
+            if (want_major) {
+                const unsigned m = cnt(MC_MAJ, 0), mg = cnt(MC_MAJG, 0);
+                if (m & 0xffffu) atomicAdd(row + o_maj, (unsigned long long)(m & 0xffffu));
+                if (m >> 16) atomicAdd(row + o_maj + 1, (unsigned long long)(m >> 16));
+                if (mg) atomicAdd(row + o_maj + 2, (unsigned long long)mg);
+            }
+        }
+    }
+    __syncwarp();
+    for (unsigned i = lane; i < (kMsPpBytes + kMsCntBytes) / 4; i += 32) sts_u32(pp_a + 4u * i, 0u);
+    __syncwarp();
+}
+
+template <int S>
 struct MsWarp {
-    unsigned nll_a, pp_a, cnt_a;  // shared-memory addresses: nll [member][column][8 floats], pp u16 [partner q][member = lane],
-                                  // cnt u32 [counter][lane]
-    float* nll;                   // the same as a pointer (hot loop: the compiler may then overlap the columns of two members)
+    static constexpr int kCols = MsGeom<S>::kCols, kNllBytes = MsGeom<S>::kNllBytes, kWarpBytes = ms_warp_bytes<S>();
+    unsigned nll_a, pp_a, cnt_a;  // shared-memory addresses: nll f32x2 [member pair][value][column], pp u16 [partner q][member =
+                                  // lane], cnt u32 [counter][lane]
+    f32x2* nll;                   // the same as a pointer (hot loop)
     // per tile
     f32x2 m1[2][4];       // (rater pair, voxel): 1.0 where the reference is class 1 and valid
     float mv;             // 1.0 for a lane inside the image
@@ -60,12 +145,12 @@ struct MsWarp {
     bool fast;            // warp-uniform: every reference of the tile is a class index (no ignore value, nothing out of range)
 
     __device__ __forceinline__ void init(unsigned char* smem_warp) {
-        nll = reinterpret_cast<float*>(smem_warp);
+        nll = reinterpret_cast<f32x2*>(smem_warp);
         nll_a = (unsigned)__cvta_generic_to_shared(smem_warp);
-        pp_a = nll_a + kMsNllBytes;
+        pp_a = nll_a + kNllBytes;
         cnt_a = pp_a + kMsPpBytes;
         const int lane = threadIdx.x & 31;
-        for (int i = lane; i < kMsWarpBytes / 4; i += 32) sts_u32(nll_a + 4u * i, 0u);
+        for (int i = lane; i < kWarpBytes / 4; i += 32) sts_u32(nll_a + 4u * i, 0u);
         __syncwarp();
     }
 
@@ -187,39 +272,27 @@ struct MsWarp {
         }
     }
 
-    // Fold the values of the two members p and p + 1 over the lanes and add them to the warp's columns.  The two members
-    // travel as packed pairs (one add serves both); 8 lanes are folded to 1 by three shuffles and the lanes 0, 8, 16, 24 add
-    // the sums to their column of each member.  has_b = false: only member p (odd member count).
-    __device__ __forceinline__ void fold_pair(int p, const float (&va)[kMsVals], const float (&vb)[kMsVals], bool has_b) {
+    // Add the values of the two members p (even) and p + 1 to the warp's columns: S shuffle steps over the lanes (the two
+    // members travel as packed pairs), then the lanes whose low S bits are zero add the partial sums to their column.
+    // Without a member p + 1 (odd member count) vb is zero.
+    __device__ __forceinline__ void fold_pair(int p, const float (&va)[kMsVals], const float (&vb)[kMsVals]) {
         const unsigned lane = threadIdx.x & 31;
         f32x2 V[kMsVals];
 #pragma unroll
         for (int i = 0; i < kMsVals; ++i) V[i] = pk2(va[i], vb[i]);
 #pragma unroll
-        for (int o = 1; o <= 4; o <<= 1) {
+        for (int st = 0; st < S; ++st) {
 #pragma unroll
             for (int i = 0; i < kMsVals; ++i) {
                 float a, b;
                 upk2(V[i], a, b);
-                V[i] = add2(V[i], pk2(__shfl_xor_sync(kFull, a, o), __shfl_xor_sync(kFull, b, o)));
+                V[i] = add2(V[i], pk2(__shfl_xor_sync(kFull, a, 1 << st), __shfl_xor_sync(kFull, b, 1 << st)));
             }
         }
-        if ((lane & 7u) == 0u) {
-            float sa[kMsVals], sb[kMsVals];
+        if (S == 0 || (lane & ((1u << S) - 1u)) == 0u) {
+            f32x2* c = nll + ((unsigned)(p >> 1) * kMsVals) * kCols + (lane >> S);
 #pragma unroll
-            for (int i = 0; i < kMsVals; ++i) upk2(V[i], sa[i], sb[i]);
-            float* ca = nll + ((unsigned)p * kMsCols + (lane >> 3)) * kMsValPad;
-            float4 q = *reinterpret_cast<float4*>(ca);
-            q.x += sa[0]; q.y += sa[1]; q.z += sa[2]; q.w += sa[3];
-            *reinterpret_cast<float4*>(ca) = q;
-            ca[4] += sa[4];
-            if (has_b) {
-                float* cb = ca + kMsCols * kMsValPad;
-                float4 t = *reinterpret_cast<float4*>(cb);
-                t.x += sb[0]; t.y += sb[1]; t.z += sb[2]; t.w += sb[3];
-                *reinterpret_cast<float4*>(cb) = t;
-                cb[4] += sb[4];
-            }
+            for (int i = 0; i < kMsVals; ++i) c[i * kCols] = add2(c[i * kCols], V[i]);
         }
     }
 
@@ -297,86 +370,9 @@ struct MsWarp {
         }
     }
 
-    __device__ __forceinline__ void flush(const MsParams& ms, long long b, int P, int R, bool want_major);
+    __device__ __forceinline__ void flush(const MsParams& ms, long long b, int P, int R, bool want_major) {
+        ms_flush_warp(nll_a, kCols, pp_a, cnt_a, ms, b, P, R, want_major);
+    }
 };
-
-// add a warp's partials into the rows of image b (layout: valunc.h, vu_member_scores) and clear them.  Out of line and on
-// plain addresses, so that the per-tile state of MsWarp stays in registers.
-__device__ __noinline__ void ms_flush_warp(unsigned nll_a, unsigned pp_a, unsigned cnt_a, const MsParams& ms, long long b, int P, int R,
-                                           bool want_major) {
-    const unsigned lane = threadIdx.x & 31;
-    auto cnt = [&](int c, unsigned l) { return lds_u32(cnt_a + ((unsigned)c * 32u + l) * 4u); };
-    __syncwarp();
-    if (ms.flags & VU_MS_NLL) {
-        if (lane < (unsigned)P) {
-            double s[kMsVals];
-#pragma unroll
-            for (int i = 0; i < kMsVals; ++i) {
-                s[i] = 0.0;
-#pragma unroll
-                for (int c = 0; c < kMsCols; ++c) {
-                    const unsigned a = nll_a + ((lane * kMsCols + c) * kMsValPad + i) * 4u;
-                    s[i] += (double)__uint_as_float(lds_u32(a));
-                    sts_u32(a, 0u);
-                }
-            }
-            for (int r = 0; r < R; ++r) {
-                const double t = (s[0] + s[1 + r]) * 0.6931471805599453;  // log2 -> ln
-                if (t != 0.0) atomicAdd(ms.nll_sum + (b * R + r) * P + lane, t);
-            }
-        }
-        for (int r = 0; r < R; ++r) {
-            const unsigned n = __reduce_add_sync(kFull, cnt(MC_GS + r, lane) >> 16);
-            if (lane == 0 && n) atomicAdd(ms.nll_cnt + b * R + r, (unsigned long long)n);
-        }
-        const unsigned nb = __reduce_add_sync(kFull, cnt(MC_POS, lane) >> 16);
-        if (lane == 0 && nb) atomicAdd(ms.nll_bad + b, (unsigned long long)nb);
-    }
-    if (ms.flags & VU_MS_GED) {
-        const int G = R;
-        const int o_pg_pred = P * G, o_gs = 2 * P * G, o_pp = o_gs + G, o_pos = o_pp + P * P, o_gg_tp = o_pos + P, o_gg_sum = o_gg_tp + G * G,
-                  o_maj = o_gg_sum + G * G;
-        unsigned long long* row = ms.ged + b * ms.ged_cols;
-        if (lane < (unsigned)P) {
-            for (int q = 0; q < P; ++q) {
-                const unsigned c = lds_u16(pp_a + ((unsigned)q * 32u + lane) * 2u);
-                if (c) atomicAdd(row + o_pp + lane * P + q, (unsigned long long)c);
-            }
-            const unsigned ps = cnt(MC_POS, lane) & 0xffffu;
-            if (ps) atomicAdd(row + o_pos + lane, (unsigned long long)ps);
-            for (int r = 0; r < G; ++r) {
-                const unsigned a = cnt(MC_PG + r, lane);
-                if (a & 0xffffu) atomicAdd(row + lane * G + r, (unsigned long long)(a & 0xffffu));
-                if (a >> 16) atomicAdd(row + o_pg_pred + lane * G + r, (unsigned long long)(a >> 16));
-            }
-        }
-        if (lane < (unsigned)G) {
-            for (int r = 0; r < G; ++r) {
-                const unsigned g = cnt(MC_GG + r, lane);
-                if (g & 0xffffu) atomicAdd(row + o_gg_tp + lane * G + r, (unsigned long long)(g & 0xffffu));
-                if (g >> 16) atomicAdd(row + o_gg_sum + lane * G + r, (unsigned long long)(g >> 16));
-            }
-        }
-        if (lane == 0) {
-            for (int r = 0; r < G; ++r) {
-                const unsigned g = cnt(MC_GS + r, 0) & 0xffffu;
-                if (g) atomicAdd(row + o_gs + r, (unsigned long long)g);
-            }
-            if (want_major) {
-                const unsigned m = cnt(MC_MAJ, 0), mg = cnt(MC_MAJG, 0);
-                if (m & 0xffffu) atomicAdd(row + o_maj, (unsigned long long)(m & 0xffffu));
-                if (m >> 16) atomicAdd(row + o_maj + 1, (unsigned long long)(m >> 16));
-                if (mg) atomicAdd(row + o_maj + 2, (unsigned long long)mg);
-            }
-        }
-    }
-    __syncwarp();
-    for (unsigned i = lane; i < (kMsPpBytes + kMsCntBytes) / 4; i += 32) sts_u32(pp_a + 4u * i, 0u);
-    __syncwarp();
-}
-
-__device__ __forceinline__ void MsWarp::flush(const MsParams& ms, long long b, int P, int R, bool want_major) {
-    ms_flush_warp(nll_a, pp_a, cnt_a, ms, b, P, R, want_major);
-}
 
 }  // namespace vu
