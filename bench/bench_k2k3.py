@@ -80,5 +80,50 @@ def main():
         print(f"{name:16s} lean vs general form: integers equal = {bool(torch.equal(i2, si))}, max rel diff of the float64 sums = {rel:.2e}", flush=True)
 
 
+def bench_k4():
+    """K4: exact order statistics (radix select with the descent on the device) and what sits on them -- wall-clock per call
+    (host work and the read-back included: these entry points return Python floats)."""
+    import time
+    import numpy as np
+    from diffuncertainty_b200 import quantile
+    torch.manual_seed(0)
+    for name, shape, R in (("cfg5 512x1024", (512, 1024), 1), ("cfg2 64^3", (64, 64, 64), 4), ("cfg3 1024x2048", (1024, 2048), 5)):
+        V = int(np.prod(shape))
+        u = (torch.rand(shape, device="cuda") ** 3 * 0.69).contiguous()
+        pred = (torch.rand(shape, device="cuda") < 0.3).to(torch.uint8)
+        refs = (torch.rand((R,) + shape, device="cuda") < 0.3).to(torch.uint8)
+
+        def wall(fn, iters=10):
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / iters * 1e3
+
+        sel = quantile.RadixSelect([u])
+        qs = np.linspace(0.0, 1.0, 21)
+        t_sel = wall(lambda: sel.select_quantile_stats(qs))
+        t_old = wall(lambda: quantile.RadixSelect([u]).select(np.arange(0, V, V // 40)))
+        t_q = wall(lambda: quantile.quantile([u], 0.9))
+        t_eq = wall(lambda: calibration.eqace_from_maps(refs, pred, u, 3.5, -1.25))
+        # device time of the three histogram passes alone
+        lib = _lib.load()
+        hist = torch.zeros((64, 2048), dtype=torch.int64, device="cuda")
+        st = _lib.current_stream_ptr()
+
+        def level0():
+            _lib.check(lib.vu_radix_hist_state(u.data_ptr(), V, None, 0, None, hist.data_ptr(), st), "hist0")
+
+        ms0 = time_call(level0, iters=10)
+        print(f"{name:16s} K4 vu_radix_hist level 0 (device)              {ms0:8.3f} ms  {4 * V / ms0 / 1e6:8.1f} GB/s", flush=True)
+        print(f"{name:16s} K4 21-quantile selection, descent on device  {t_sel:8.3f} ms wall (3 passes + 3 walks + 1 read-back)", flush=True)
+        print(f"{name:16s} K4 same ranks, descent on the host (r01)      {t_old:8.3f} ms wall (3 read-backs)", flush=True)
+        print(f"{name:16s} K4 quantile(map, 0.9)                          {t_q:8.3f} ms wall", flush=True)
+        print(f"{name:16s} K4 eqace_from_maps (R={R}), one image            {t_eq:8.3f} ms wall", flush=True)
+
+
 if __name__ == "__main__":
     main()
+    bench_k4()

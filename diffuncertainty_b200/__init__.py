@@ -7,7 +7,7 @@ Python call surface of JakobLC/DiffUncertainty's
 ``evaluation/metrics`` (ECE/ACE, NCC, AURC inputs).  There is no CPU fallback.
 """
 from . import _lib  # noqa: F401
-from .uncertainty import (FusedResult, GroundTruth, calculate_one_minus_msr, calculate_uncertainty, fused_pass,  # noqa: F401
+from .uncertainty import (FusedResult, GroundTruth, Groups, calculate_one_minus_msr, calculate_uncertainty, fused_pass,  # noqa: F401
                           group_members, map_stats, mean_argmax_labels)
 
 from .members import MemberScoreBuffers, fused_pass_with_member_scores  # noqa: F401,E402

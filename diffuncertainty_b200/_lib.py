@@ -20,6 +20,7 @@ GT_U8, GT_I64 = 0, 1
 STAT_IMAGE_SUM, STAT_THRESHOLD, STAT_AREA, STAT_DICE, STAT_CALIB, STAT_NCC, STAT_PLATT_FIT = 1, 2, 4, 8, 16, 32, 64
 STAT_CLASS_COUNTS = 128
 N_PLATT_BINS = 256
+SLAB_RENORMALIZE, SLAB_DISCRETIZE = 1, 2
 STAT_ALL_NO_GT = STAT_IMAGE_SUM | STAT_THRESHOLD | STAT_AREA
 
 # column layout of the per-image rows (keep in sync with valunc.h; checked in tests/test_abi.py)
@@ -31,7 +32,8 @@ I64 = dict(THR_COUNT=0, AREA=3, BORDER=4, NVOX=5, BIN_TOTAL=6, BIN_TRUE=69, DICE
 class Slab(C.Structure):
     _fields_ = [("data", C.c_void_p), ("P", C.c_int64), ("B", C.c_int64), ("C", C.c_int64), ("V", C.c_int64),
                 ("stride_p", C.c_int64), ("stride_b", C.c_int64), ("stride_c", C.c_int64), ("stride_v", C.c_int64),
-                ("member_ptrs", C.c_void_p), ("member_ptrs_host", C.c_void_p)]
+                ("member_ptrs", C.c_void_p), ("member_ptrs_host", C.c_void_p),
+                ("stride_d", C.c_int64), ("draws", C.c_int32), ("flags", C.c_uint32), ("renorm_eps", C.c_float)]
 
 
 class Gt(C.Structure):
@@ -77,6 +79,12 @@ class MemberScoresArgs(C.Structure):
                 ("ged_counts", C.c_void_p)]
 
 
+class RadixState(C.Structure):
+    _fields_ = [("total", C.c_int64), ("n_rank", C.c_int32), ("n_slot", C.c_int32), ("rank", C.c_int64 * 64),
+                ("residual", C.c_int64 * 64), ("prefix", C.c_uint32 * 64), ("slot", C.c_int32 * 64),
+                ("slot_prefix", C.c_uint32 * 64), ("key", C.c_uint32 * 64)]
+
+
 MS_NLL, MS_GED = 1, 2
 
 EXPORTS = {
@@ -99,6 +107,10 @@ EXPORTS = {
     "vu_ged_cols": (C.c_int64, [C.c_int32, C.c_int32]),
     "vu_member_scores": (C.c_int, [C.POINTER(MemberScoresArgs), C.c_void_p]),
     "vu_radix_hist": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Gt), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vu_radix_walk": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vu_radix_hist_state": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Gt), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vu_quantile_select": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Gt), C.POINTER(C.c_double), C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "vu_binned_calib": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Gt), C.POINTER(Calib), C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "vu_synth_slab": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int64,

@@ -73,25 +73,49 @@ class PlattEdges:
         return np.where(np.isnan(u), N_BINS, b)
 
 
-def platt_edges(a: float, b: float, edges: Optional[np.ndarray] = None) -> PlattEdges:
-    """Invert conf(u) = 1/(1+exp(-u*a+b)) (float32, NumPy's exp) on the 19
-    interior bin edges by bisection over float32 bit patterns, vectorised over
-    the edges.  increasing (a >= 0): smallest u with conf(u) >= edge;
-    decreasing: largest such u.  The result is made monotone in k.
-    ``edges``: 19 non-decreasing float64 edges to use instead of the uniform ones (the quantile bins of calc_eqace)."""
+def platt_edges(a: float, b: float, edges: Optional[np.ndarray] = None, hints: Optional[np.ndarray] = None) -> PlattEdges:
+    """Invert conf(u) = 1/(1+exp(-u*a+b)) (float32, NumPy's exp) on the 19 interior bin edges by bisection over float32 bit
+    patterns, vectorised over the edges.  increasing (a >= 0): smallest u with conf(u) >= edge; decreasing: largest such u.
+    The result is made monotone in k.
+    ``edges``: 19 non-decreasing float64 edges to use instead of the uniform ones (the quantile bins of calc_eqace).
+    ``hints``: (n, 19) uncertainty values near the thresholds (for quantile edges: the two order statistics every edge was
+    interpolated from); they only narrow the bisection brackets -- the result does not depend on them."""
     a32 = np.float32(a)
     increasing = bool(a32 >= 0)
     edges = bin_edges()[1:N_BINS] if edges is None else np.asarray(edges, np.float64)
-    lo = np.full(19, _ord(np.array([-np.inf], np.float32))[0], np.uint64)
-    hi = np.full(19, _ord(np.array([np.inf], np.float32))[0], np.uint64)
+    if a32 == 0:
+        # the reference's own fallback (ace.py: a, b = 0.0, 0.0 when the fit fails): conf is the constant 1 / (1 + exp(b)),
+        # every sample lies in one bin.  (-inf) * 0 is NaN, so the bisection below cannot be used: edges at or below the constant
+        # are passed by every u (threshold -inf), the others by none (+inf, not NaN: the kernels look at ONE edge of the
+        # candidate bin round(conf * 20) and step down when u lies below it -- a NaN there would leave the candidate standing).
+        conf0 = np.clip(_platt_f32(np.zeros(1, np.float32), float(a), float(b)), 0, 1).astype(np.float64)[0]
+        thr = np.where(edges <= conf0, -np.inf, np.inf).astype(np.float32)
+        return PlattEdges(a=float(a), b=float(b), edge_u=thr, mode=1)
+    key_min, key_max = _ord(np.array([-np.inf], np.float32))[0], _ord(np.array([np.inf], np.float32))[0]
+    lo = np.full(19, key_min, np.uint64)
+    hi = np.full(19, key_max, np.uint64)
 
     def ok(keys):
         conf = np.clip(_platt_f32(_unord(keys), float(a), float(b)), 0, 1).astype(np.float64)  # ace.py:333 / :379 clip
         return conf >= edges
 
+    reach = ok(hi) if increasing else ok(lo)
+    if hints is not None:
+        for h in np.asarray(hints, np.float32).reshape(-1, 19):
+            fin = ~np.isnan(h)
+            k = np.where(fin, _ord(np.where(fin, h, np.float32(0))), key_min).astype(np.uint64)
+            good = ok(k) & fin
+            bad = ~good & fin
+            if increasing:   # smallest ok key: every ok hint bounds it from above, every failing hint from below
+                hi = np.where(good, np.minimum(hi, k), hi)
+                lo = np.where(bad, np.maximum(lo, np.minimum(k + 1, hi)), lo)
+            else:            # largest ok key
+                lo = np.where(good, np.maximum(lo, k), lo)
+                hi = np.where(bad, np.minimum(hi, np.maximum(k - 1, lo)), hi)
     if increasing:
-        reach = ok(hi)
         for _ in range(34):
+            if np.all(lo >= hi):
+                break
             mid = lo + (hi - lo) // 2
             good = ok(mid)
             hi = np.where(good, mid, hi)
@@ -101,8 +125,9 @@ def platt_edges(a: float, b: float, edges: Optional[np.ndarray] = None) -> Platt
         fin = ~np.isnan(thr)
         thr[fin] = np.maximum.accumulate(thr[fin])
     else:
-        reach = ok(lo)
         for _ in range(34):
+            if np.all(lo >= hi):
+                break
             mid = lo + (hi - lo + 1) // 2
             good = ok(mid)
             lo = np.where(good, mid, lo)
@@ -156,8 +181,19 @@ def per_image_ace_ece(bin_sums, bin_true, bin_total) -> Tuple[float, float]:
     return ace_ece_from_histogram(bin_sums, bin_true, bin_total)
 
 
+def _warn_float64(calib_confids) -> None:
+    dt = getattr(calib_confids, "dtype", None)
+    if dt is not None and str(dt).endswith("float64"):
+        import warnings
+        warnings.warn("float64 confidences are binned after rounding to float32 (the reference's own pipeline produces float32 "
+                      "confidences, ace.py:325-329, and only those are bit-compatible): a float64 value within one float32 ulp of a "
+                      "bin edge can land in the neighbouring bin", stacklevel=3)
+
+
 def _device_histogram(correct, calib_confids):
-    """(correct, conf) arrays -> 21-slot histogram on the GPU (ace.py:352-356)."""
+    """(correct, conf) arrays -> 21-slot histogram on the GPU (ace.py:352-356).  Confidences are binned as float32 -- what
+    platt_scale_confid returns for the float32 maps the pipeline stores; float64 input is rounded first (and warned about)."""
+    _warn_float64(calib_confids)
     _lib.require_device()
     lib = _lib.load()
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -399,6 +435,16 @@ def _quantile_edges(ranks, conf_at_ranks, lo, hi, g) -> np.ndarray:
     return np.maximum.accumulate(edges)
 
 
+def _edges_from_stats(conf_lo, conf_hi, total: int, n_bins: int) -> np.ndarray:
+    """ace.py:387-391 from the two order statistics of every quantile (RadixSelect.select_quantile_stats)."""
+    from .quantile import lerp, quantile_ranks
+    _, _, g = quantile_ranks(total, np.linspace(0.0, 1.0, n_bins + 1))
+    edges = lerp(np.asarray(conf_lo, np.float64), np.asarray(conf_hi, np.float64), g)
+    edges[0] = 0.0
+    edges[-1] = 1.0 + 1e-8
+    return np.maximum.accumulate(edges)
+
+
 def _eqace_from_histogram(counts: np.ndarray, sums: np.ndarray, n_bins: int) -> float:
     """ace.py:392-406 from the bincounts (slot 20 = NaN confidences, which np.clip puts into the last bin)."""
     tot = counts[0, :n_bins].astype(np.float64).copy()
@@ -440,8 +486,8 @@ def calc_eqace(correct, calib_confids, n_bins: int = 20) -> float:
         return float("nan")
     conf = conf.to(dev).clamp_(0.0, 1.0).contiguous()  # ace.py:379
     corr = corr.to(dev).to(torch.uint8).contiguous()
-    ranks, lo, hi, g = _needed_ranks(n, n_bins)
-    edges = _quantile_edges(ranks, _q.RadixSelect([conf]).select(ranks), lo, hi, g)
+    total, s_lo, s_hi, _ = _q.RadixSelect([conf]).select_quantile_stats(np.linspace(0.0, 1.0, n_bins + 1))
+    edges = _edges_from_stats(s_lo, s_hi, total, n_bins)
     ones = torch.ones(n, dtype=torch.uint8, device=dev)  # "label" 1: a sample is correct iff correct == 1
     gs = _lib.Gt()
     gs.data, gs.dtype, gs.R = corr.data_ptr(), _lib.GT_U8, 1
@@ -471,17 +517,15 @@ def eqace_from_maps(reference_segs, pred_seg, unc_map, a: float, b: float, ignor
     if V == 0:
         return float("nan")
     sel = _q.RadixSelect([unc], [refs], ignore_value)
-    total = sel.total
+    increasing = bool(np.float32(a) >= 0)  # a >= 0: conf rises with u (x = -u, ace.py:329); else the ranks are mirrored
+    total, u_lo, u_hi, _ = sel.select_quantile_stats(np.linspace(0.0, 1.0, n_bins + 1), reverse=not increasing)
     if total == 0:
         return float("nan")
-    increasing = bool(np.float32(a) >= 0)
-    ranks, lo, hi, g = _needed_ranks(total, n_bins)
-    u_at = sel.select(ranks if increasing else (total - 1 - ranks))  # a >= 0: conf rises with u (x = -u, ace.py:329)
-    conf = np.clip(_platt_f32(u_at, float(a), float(b)), 0, 1)
-    edges = _quantile_edges(ranks, conf, lo, hi, g)
+    edges = _edges_from_stats(np.clip(_platt_f32(u_lo, float(a), float(b)), 0, 1), np.clip(_platt_f32(u_hi, float(a), float(b)), 0, 1),
+                              total, n_bins)
     gs = _lib.Gt()
     gs.data, gs.dtype, gs.R = refs.data_ptr(), (_lib.GT_U8 if refs.dtype == torch.uint8 else _lib.GT_I64), refs.shape[0]
     gs.stride_b, gs.stride_r, gs.stride_v = refs.numel(), V, 1
     gs.has_ignore, gs.ignore_index = (0, 0) if ignore_value is None else (1, int(ignore_value))
-    counts, sums = _binned(unc, pred, gs, platt_edges(a, b, edges[1:n_bins]).as_struct())
+    counts, sums = _binned(unc, pred, gs, platt_edges(a, b, edges[1:n_bins], hints=np.stack([u_lo[1:n_bins], u_hi[1:n_bins]])).as_struct())
     return _eqace_from_histogram(counts, sums, n_bins)

@@ -172,6 +172,7 @@ int vu_struct_size(int which) {
         case 3: return (int)sizeof(vu_platt_fit);
         case 4: return (int)sizeof(vu_member_scores_args);
         case 5: return (int)sizeof(vu_member_out);
+        case 6: return (int)sizeof(vu_radix_state);
         default: return -1;
     }
 }
@@ -183,10 +184,15 @@ int vu_fused_pass(const vu_fused_args* a, void* stream) {
     if (s.P < 1 || s.B < 0 || s.C < 1 || s.V < 0) return set_error(VU_ERR_BAD_ARG, "slab sizes must be positive");
     if (s.C > 256) return set_error(VU_ERR_UNSUPPORTED, "C > 256 (labels are uint8)");
     if (s.B == 0 || s.V == 0) return VU_OK;  // empty batch: nothing to do (its data pointer may be NULL)
+    if (s.draws < 0 || s.draws > 4096 || (s.flags & ~(VU_SLAB_RENORMALIZE | VU_SLAB_DISCRETIZE)))
+        return set_error(VU_ERR_BAD_ARG, "slab.draws / slab.flags");
+    if ((s.draws > 1 || s.flags) && a->members.flags)
+        return set_error(VU_ERR_UNSUPPORTED, "member scores in the fused pass are not available for grouped / renormalised / discretised slabs");
+    const int64_t n_ptrs = s.P * (s.draws > 1 ? s.draws : 1);
     if (s.member_ptrs || s.member_ptrs_host) {
         if (!s.member_ptrs || !s.member_ptrs_host)
             return set_error(VU_ERR_BAD_ARG, "slab.member_ptrs needs both the device array and its host copy");
-        for (int64_t p = 0; p < s.P; ++p)
+        for (int64_t p = 0; p < n_ptrs; ++p)
             if (!s.member_ptrs_host[p]) return set_error(VU_ERR_BAD_ARG, "slab.member_ptrs_host holds a NULL member");
     } else if (!s.data) {
         return set_error(VU_ERR_BAD_ARG, "slab.data is NULL");
@@ -296,6 +302,14 @@ int vu_platt_invert_edges_host(double a, double b, vu_calib* calib) {
     calib->b = bf;
     calib->mode = af >= 0.0f ? VU_CALIB_PLATT_INC : VU_CALIB_PLATT_DEC;
     const bool increasing = calib->mode == VU_CALIB_PLATT_INC;
+    if (af == 0.0f) {
+        // conf is the constant 1 / (1 + exp(b)) (the reference's fallback a = b = 0 when the fit fails): every u passes the edges at
+        // or below it, none passes the others
+        const float c0 = platt_host(0.0f, af, bf);
+        for (int k = 0; k < VU_N_EDGES; ++k)
+            calib->edge_u[k] = (double)c0 >= (1.0 + 1e-8) * (double)(k + 1) / 20.0 ? -INFINITY : INFINITY;
+        return VU_OK;
+    }
     const uint32_t lo_all = f2o(-INFINITY), hi_all = f2o(INFINITY);
     for (int k = 0; k < VU_N_EDGES; ++k) {
         const double edge = (1.0 + 1e-8) * (double)(k + 1) / 20.0;
@@ -325,6 +339,42 @@ int vu_radix_hist(const float* values, int64_t n, const vu_gt* weights_gt, int32
     int rc = make_gt_view(gv, weights_gt, n);
     if (rc != VU_OK) return rc;
     return launch_radix_hist(values, n, gv, level, prefixes, n_prefix, reinterpret_cast<unsigned long long*>(hist), (cudaStream_t)stream);
+}
+
+int vu_radix_walk(const uint64_t* hist, int32_t level, const double* q_host, int32_t n_q, int32_t q_is_f32, int32_t reverse,
+                  vu_radix_state* state, void* stream) {
+    if (!hist || !state || level < 0 || level > 2) return set_error(VU_ERR_BAD_ARG, "NULL pointer / bad level");
+    if (level == 0 && (n_q < 0 || n_q > 31 || (n_q > 0 && !q_host))) return set_error(VU_ERR_BAD_ARG, "level 0 needs 0..31 quantile fractions");
+    if (level == 0)
+        for (int i = 0; i < n_q; ++i)
+            if (!(q_host[i] >= 0.0 && q_host[i] <= 1.0)) return set_error(VU_ERR_BAD_ARG, "Quantiles must be in the range [0, 1]");
+    return launch_radix_walk(reinterpret_cast<const unsigned long long*>(hist), level, q_host, n_q, q_is_f32, reverse, state, (cudaStream_t)stream);
+}
+
+int vu_radix_hist_state(const float* values, int64_t n, const vu_gt* weights_gt, int32_t level, const vu_radix_state* state, uint64_t* hist,
+                        void* stream) {
+    if (n < 0 || level < 0 || level > 2) return set_error(VU_ERR_BAD_ARG, "bad size / level");
+    if (level > 0 && !state) return set_error(VU_ERR_BAD_ARG, "levels 1, 2 need the state");
+    if (n == 0) return VU_OK;
+    if (!values || !hist) return set_error(VU_ERR_BAD_ARG, "NULL pointer");
+    GtView gv;
+    int rc = make_gt_view(gv, weights_gt, n);
+    if (rc != VU_OK) return rc;
+    return launch_radix_hist(values, n, gv, level, nullptr, 0, reinterpret_cast<unsigned long long*>(hist), (cudaStream_t)stream, state);
+}
+
+int vu_quantile_select(const float* values, int64_t n, const vu_gt* weights_gt, const double* q_host, int32_t n_q, int32_t q_is_f32,
+                       int32_t reverse, uint64_t* hist, vu_radix_state* state, void* stream) {
+    if (!hist || !state || n < 0 || (n > 0 && !values)) return set_error(VU_ERR_BAD_ARG, "NULL pointer / negative size");
+    for (int level = 0; level < 3; ++level) {
+        if (cudaMemsetAsync(hist, 0, (size_t)VU_RADIX_MAX_RANKS * 2048 * sizeof(uint64_t), (cudaStream_t)stream) != cudaSuccess)
+            return set_cuda_error("cudaMemsetAsync(hist)");
+        int rc = vu_radix_hist_state(values, n, weights_gt, level, state, hist, stream);
+        if (rc != VU_OK) return rc;
+        rc = vu_radix_walk(hist, level, q_host, n_q, q_is_f32, reverse, state, stream);
+        if (rc != VU_OK) return rc;
+    }
+    return VU_OK;
 }
 
 int vu_binned_calib(const float* map, const uint8_t* labels, int64_t V, const vu_gt* gt, const vu_calib* calib, const uint8_t* label_lut,
@@ -360,6 +410,7 @@ int vu_member_scores(const vu_member_scores_args* a, void* stream) {
     if (!(a->flags & (VU_MS_NLL | VU_MS_GED)) || (a->flags & ~(VU_MS_NLL | VU_MS_GED))) return set_error(VU_ERR_BAD_ARG, "flags");
     if ((a->flags & VU_MS_GED) && s.C != 2) return set_error(VU_ERR_BAD_ARG, "GED counts need C == 2 (ged_fast.py:33)");
     if ((a->flags & VU_MS_GED) && s.P > 32) return set_error(VU_ERR_UNSUPPORTED, "GED counts need P <= 32");
+    if (s.draws > 1 || s.flags) return set_error(VU_ERR_UNSUPPORTED, "member scores take the members as they are (no draws / producer flags)");
     if (s.B == 0 || s.V == 0) return VU_OK;
     if (s.member_ptrs || s.member_ptrs_host) {
         if (!s.member_ptrs || !s.member_ptrs_host)

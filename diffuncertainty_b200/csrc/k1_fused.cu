@@ -21,6 +21,10 @@ struct K1Params {
     const float* const* mptr;  // optional device array of P member base pointers (then x / sp are unused)
     long long P, B, C, V;
     long long sp, sb, sc, sv;
+    long long sd;        // stride between the draws of a member (data form)
+    int draws;           // draws per member (>= 1)
+    unsigned sflags;     // VU_SLAB_RENORMALIZE | VU_SLAB_DISCRETIZE
+    float renorm_eps;
     float* tu;
     float* au;
     float* eu;
@@ -162,9 +166,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_fast(const __grid_constant__
 // ---------------------------------------------------------------------------
 // dynamic shared memory of the generic kernel before the statistics state: entropies [P][T] (P > 1) and, for member
 // labels, best value [P][T] + best index [P][T], rounded up to 16 bytes
-__host__ __device__ inline size_t generic_smem_bytes(long long P, int threads, bool member_labels) {
+// (+ with renormalised / discretised draws: the class sum [P * draws][T] and the argmax [P * draws][T] of every draw)
+__host__ __device__ inline size_t generic_smem_bytes(long long P, int threads, bool member_labels, long long draws = 1, unsigned sflags = 0) {
     size_t n = (P > 1 ? (size_t)P * threads * sizeof(float) : 0);
     if (member_labels) n += (size_t)P * threads * (sizeof(float) + 1);
+    n = (n + 3) / 4 * 4;
+    if (sflags & VU_SLAB_RENORMALIZE) n += (size_t)P * draws * threads * sizeof(float);
+    if (sflags & VU_SLAB_DISCRETIZE) n += (size_t)P * draws * threads;
     return (n + 15) / 16 * 16;
 }
 
@@ -196,7 +204,12 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
     const bool want_ml = prm.mlab != nullptr;
     float* bv_smem = h_smem + (prm.P > 1 ? (size_t)prm.P * THREADS : 0);
     uint8_t* bi_smem = reinterpret_cast<uint8_t*>(bv_smem + (want_ml ? (size_t)prm.P * THREADS : 0));
-    void* st_smem = vu_dyn_smem + generic_smem_bytes(prm.P, THREADS, want_ml);
+    const int D = prm.draws;
+    const bool renorm = prm.sflags & VU_SLAB_RENORMALIZE, onehot = prm.sflags & VU_SLAB_DISCRETIZE;
+    const size_t pre_bytes = ((prm.P > 1 ? (size_t)prm.P * THREADS * 4 : 0) + (want_ml ? (size_t)prm.P * THREADS * 5 : 0) + 3) / 4 * 4;
+    float* norm_smem = reinterpret_cast<float*>(vu_dyn_smem + pre_bytes);  // class sum of every draw (renormalisation)
+    uint8_t* amax_smem = reinterpret_cast<uint8_t*>(norm_smem + (renorm ? (size_t)prm.P * D * THREADS : 0));  // argmax of every draw
+    void* st_smem = vu_dyn_smem + generic_smem_bytes(prm.P, THREADS, want_ml, D, prm.sflags);
     const bool do_stats = prm.st.flags != 0;
     StatsCursor<THREADS> cursor;
     if (do_stats) stats_init<THREADS>(prm.st, st_smem);
@@ -205,6 +218,24 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
     const int C = (int)prm.C;
     const float Pf = (float)P;
     const long long n_full = (P >> level_k) << level_k;
+    // the cascade of a sum over the classes of a draw (torch.sum(dim=1)) and over the draws of a member (mean(dim=1))
+    auto level_of = [](long long n) { int lg = 0; while ((1LL << lg) < n) ++lg; return lg / 4 > 4 ? lg / 4 : 4; };
+    const int kC = level_of(C), kD = level_of(D);
+    const long long nfC = ((long long)C >> kC) << kC, nfD = ((long long)D >> kD) << kD;
+    const float Df = (float)D;
+    // draw d of member p
+    auto draw_base = [&](long long p, int d) {
+        return prm.mptr ? ld_member_ptr(prm.mptr, p * D + d) : prm.x + p * prm.sp + (long long)d * prm.sd;
+    };
+    // what the reference's producers make of the raw value x of class c of draw pd at this thread's voxel
+    auto produced = [&](float x, long long pd, int c) {
+        if (renorm) {
+            const float nrm = norm_smem[pd * THREADS + threadIdx.x];
+            x = (nrm > prm.renorm_eps) ? __fdiv_rn(x, fmaxf(nrm, prm.renorm_eps)) : x;  // test_2D.py:190-194
+        }
+        if (onehot) x = (amax_smem[pd * THREADS + threadIdx.x] == (uint8_t)c) ? 1.0f : 0.0f;  // test_2D.py:1274
+        return x;
+    };
     const int t0 = (int)(prm.total_tiles * (long long)blockIdx.x / gridDim.x);
     const int t1 = (int)(prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x);
     const int tpi = (int)prm.tiles_per_img;
@@ -222,13 +253,49 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
             const long long off0 = (long long)b * prm.sb + v * prm.sv;
             if (P > 1)
                 for (long long p = 0; p < P; ++p) h[p * THREADS] = 0.f;
+            if (renorm | onehot) {
+                // first pass over the draws: the class sum (torch.sum(dim=1): cascade order) and the argmax of the
+                // (renormalised) draw
+                for (long long pd = 0; pd < P * D; ++pd) {
+                    const float* base = draw_base(pd / D, (int)(pd % D)) + off0;
+                    if (renorm) {
+                        Cascade cs;
+                        cs.reset();
+                        for (int c = 0; c < C; ++c) cs.add(ldg_stream(base + (long long)c * prm.sc), c, nfC, kC);
+                        norm_smem[pd * THREADS + threadIdx.x] = cs.total();
+                    }
+                    if (onehot) {
+                        const float nrm = renorm ? norm_smem[pd * THREADS + threadIdx.x] : 0.f;
+                        float bv = 0.f;
+                        int bi = 0;
+                        for (int c = 0; c < C; ++c) {
+                            float x = ldg_stream(base + (long long)c * prm.sc);
+                            if (renorm) x = (nrm > prm.renorm_eps) ? __fdiv_rn(x, fmaxf(nrm, prm.renorm_eps)) : x;
+                            if (c == 0) { bv = x; bi = 0; } else argmax_step(x, c, bv, bi);
+                        }
+                        amax_smem[pd * THREADS + threadIdx.x] = (uint8_t)bi;
+                    }
+                }
+            }
             float best = 0.f, tu2 = 0.f;
             for (int c = 0; c < C; ++c) {
                 Cascade cas;
                 cas.reset();
                 const long long offc = off0 + (long long)c * prm.sc;
                 for (long long p = 0; p < P; ++p) {
-                    const float x = ldg_stream((prm.mptr ? ld_member_ptr(prm.mptr, p) : prm.x + p * prm.sp) + offc);
+                    float x;
+                    if (D == 1 && !(renorm | onehot)) {
+                        x = ldg_stream((prm.mptr ? ld_member_ptr(prm.mptr, p) : prm.x + p * prm.sp) + offc);
+                    } else {
+                        // the member is the mean of its draws (test_2D.py:1277): cascade sum, true division
+                        Cascade cd;
+                        cd.reset();
+                        for (int d = 0; d < D; ++d) {
+                            const float raw = onehot ? 0.f : ldg_stream(draw_base(p, d) + offc);
+                            cd.add(produced(raw, p * D + d, c), d, nfD, kD);
+                        }
+                        x = D > 1 ? __fdiv_rn(cd.total(), Df) : cd.total();
+                    }
                     cas.add(x, p, n_full, level_k);
                     if (P > 1) h[p * THREADS] = plog2p_acc(h[p * THREADS], x);
                     if (want_ml) {
@@ -352,6 +419,8 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     prm.mptr = s.member_ptrs;
     prm.P = s.P; prm.B = s.B; prm.C = s.C; prm.V = s.V;
     prm.sp = s.stride_p; prm.sb = s.stride_b; prm.sc = s.stride_c; prm.sv = s.stride_v;
+    prm.sd = s.stride_d; prm.draws = s.draws > 1 ? s.draws : 1; prm.sflags = s.flags; prm.renorm_eps = s.renorm_eps;
+    const bool produced = prm.draws > 1 || s.flags != 0;  // upstream producers folded into the read: generic kernel
     prm.tu = a->tu; prm.au = a->au; prm.eu = a->eu; prm.lab = a->labels;
     prm.mlab = a->member_labels;
     prm.st = st;
@@ -360,7 +429,7 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     const long long forced = get_option("k1_variant", -1);
     // preferred path: the TMA-pipelined kernel (k1_tma.cu); "k1_path" = 1 keeps to the register-streaming
     // kernels, 2 insists on TMA
-    if (forced == -1) {
+    if (forced == -1 && !produced) {
         // few-class slabs with reference-based statistics: the unified-warp TMA form (k1_uni.cu)
         const int rcu = launch_k1_uni(a, st, stream);
         if (rcu <= 0) return rcu;
@@ -371,7 +440,7 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     const int need_levels = s.P <= 17 ? 1 : (s.P <= 271 ? 2 : 3);
 
     const FastVariant* pick = nullptr;
-    if (s.stride_v == 1 && s.P >= 2 && need_levels <= 2 && forced != -2) {
+    if (s.stride_v == 1 && s.P >= 2 && need_levels <= 2 && forced != -2 && !produced) {
         if (forced >= 0 && forced < kNumFast) {
             const FastVariant& f = kFast[forced];
             if (f.C == s.C && f.LEVELS >= need_levels && aligned_for(a, f.VEC)) pick = &f;
@@ -407,9 +476,9 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     // generic path
     constexpr int T = 64;
     const size_t max_dyn = 160 * 1024;
-    size_t dyn = generic_smem_bytes(s.P, T, a->member_labels != nullptr) + stats_smem_bytes(st.flags, st.gt.R, T) +
+    size_t dyn = generic_smem_bytes(s.P, T, a->member_labels != nullptr, prm.draws, s.flags) + stats_smem_bytes(st.flags, st.gt.R, T) +
                  stats_class_bytes(st.flags, st.gt.R, st.ncls);
-    if (dyn > max_dyn) return set_error(VU_ERR_UNSUPPORTED, "P too large for the generic kernel (P*256 B of shared memory, P*576 B with member labels)");
+    if (dyn > max_dyn) return set_error(VU_ERR_UNSUPPORTED, "P (x draws) too large for the generic kernel (P*256 B of shared memory, P*576 B with member labels, + P*draws*320 B for renormalised / discretised draws)");
     if (s.P > (1LL << 19)) return set_error(VU_ERR_UNSUPPORTED, "P > 2^19");
     // the attribute is per device (and this may be the first launch on this one): set it whenever it is needed
     if (dyn > 48 * 1024 && cudaFuncSetAttribute(k1_generic<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)

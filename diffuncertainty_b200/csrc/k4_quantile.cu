@@ -37,14 +37,19 @@ constexpr int kMaxPrefixes = 64;
 
 __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const float* __restrict__ values, long long n, GtView gt, int level,
                                                                   const unsigned* __restrict__ prefixes, int n_prefix,
-                                                                  unsigned long long* hist) {
+                                                                  unsigned long long* hist, const vu_radix_state* state) {
     __shared__ unsigned h0[2048];
     __shared__ unsigned pre[kMaxPrefixes];
+    if (state && level > 0) {  // prefixes left on the device by vu_radix_walk
+        n_prefix = state->n_slot;
+        prefixes = state->slot_prefix;
+    }
     if (level == 0)
         for (int t = threadIdx.x; t < 2048; t += kRadixThreads) h0[t] = 0u;
     else
         for (int t = threadIdx.x; t < n_prefix; t += kRadixThreads) pre[t] = prefixes[t];
     __syncthreads();
+    if (level > 0 && n_prefix == 0) return;
     const int lane = threadIdx.x & 31;
     // every lane of a warp runs the same number of iterations (the aggregation below is warp-collective)
     const long long stride = (long long)gridDim.x * kRadixThreads;
@@ -84,13 +89,143 @@ __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const float* 
     }
 }
 
+// The descent of every rank by one level (see vu_radix_walk in valunc.h).  One CTA of 32 warps; a warp takes a rank at a time:
+// every lane sums 64 consecutive counters of the rank's slot (independent loads), a warp scan finds the lane in whose run the
+// residual rank falls, and that lane walks its 64 counters.  (A single thread walking 2048 counters is a chain of dependent
+// global loads: ~0.2 ms per level.)
+struct WalkQ { double q[32]; };
+constexpr int kWalkThreads = 1024;
+__global__ void __launch_bounds__(kWalkThreads) radix_walk_kernel(const unsigned long long* __restrict__ hist, int level, WalkQ wq, int n_q,
+                                                                   int q_is_f32, int reverse, vu_radix_state* st) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ long long s_part[32];
+    __shared__ long long s_total;
+    __shared__ unsigned s_prefix[VU_RADIX_MAX_RANKS];
+    __shared__ int s_n_rank;
+    if (level == 0) {
+        long long part = 0;
+        for (int i = tid; i < 2048; i += kWalkThreads) part += (long long)hist[i];
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+        if (lane == 0) s_part[warp] = part;
+        __syncthreads();
+        if (tid == 0) {
+            long long t = 0;
+            for (int w = 0; w < 32; ++w) t += s_part[w];
+            s_total = t;
+            st->total = t;
+            st->n_rank = t > 0 ? 2 * n_q + 1 : 0;
+            if (t <= 0) st->n_slot = 0;
+        }
+        __syncthreads();
+        const long long total = s_total;
+        if (total <= 0) return;
+        if (tid < 2 * n_q + 1) {
+            long long rank = total - 1;
+            if (tid < 2 * n_q) {
+                const double q = wq.q[tid >> 1];
+                // NumPy's virtual index (n - 1) q in the dtype it uses for q (float64, or float32 for float32 data and a Python
+                // scalar q under NumPy 2); a float32 h can round above n - 1: NumPy takes the last element
+                const double h = q_is_f32 ? (double)__fmul_rn((float)(total - 1), (float)q) : __dmul_rn((double)(total - 1), q);
+                long long lo = (long long)floor(h);
+                lo = lo > total - 1 ? total - 1 : (lo < 0 ? 0 : lo);
+                const long long hi = lo + 1 > total - 1 ? total - 1 : lo + 1;
+                rank = (tid & 1) ? hi : lo;
+            }
+            if (reverse) rank = total - 1 - rank;
+            st->rank[tid] = rank;
+            st->residual[tid] = rank;
+            st->prefix[tid] = 0u;
+            st->slot[tid] = 0;
+        }
+        if (tid == 0) s_n_rank = 2 * n_q + 1;
+    } else if (tid == 0) {
+        s_n_rank = st->n_rank;
+    }
+    __syncthreads();
+    const int n_rank = s_n_rank;
+    const int bins = level == 2 ? 1024 : 2048, per = bins / 32;
+    for (int r = warp; r < n_rank; r += kWalkThreads / 32) {
+        const unsigned long long* h = hist + (size_t)st->slot[r] * 2048 + lane * per;
+        const long long res = st->residual[r];
+        unsigned long long c[64];
+        long long mine = 0;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            c[i] = i < per ? h[i] : 0ull;
+            mine += (long long)c[i];
+        }
+        long long incl = mine;  // inclusive scan over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long up = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const long long before = incl - mine;
+        // the first lane whose inclusive count exceeds the residual owns the digit (the last lane if none does: the residual
+        // is below the slot's total by construction)
+        const unsigned hit = __ballot_sync(kFull, incl > res);
+        const int owner = hit ? __ffs(hit) - 1 : 31;
+        if (lane == owner) {
+            long long cum = before;
+            int d = 0;
+            for (; d < per - 1; ++d) {
+                if (cum + (long long)c[d] > res) break;
+                cum += (long long)c[d];
+            }
+            const unsigned digit = (unsigned)(lane * per + d);
+            const unsigned prefix = level == 0 ? digit : (st->prefix[r] << (level == 1 ? 11 : 10)) | digit;
+            st->residual[r] = res - cum;
+            st->prefix[r] = prefix;
+            s_prefix[r] = prefix;
+            if (level == 2) st->key[r] = prefix;
+        }
+    }
+    __syncthreads();
+    if (level < 2 && tid < n_rank) {
+        // ranks with one prefix share a histogram slot: the slot of a rank is the number of distinct prefixes among the ranks
+        // before its first occurrence
+        const int r = tid;
+        int first = r;
+        for (int j = 0; j < r; ++j)
+            if (s_prefix[j] == s_prefix[r]) { first = j; break; }
+        int slot = 0;
+        for (int j = 0; j < first; ++j) {
+            bool fresh = true;
+            for (int k = 0; k < j; ++k)
+                if (s_prefix[k] == s_prefix[j]) { fresh = false; break; }
+            slot += fresh;
+        }
+        st->slot[r] = slot;
+        if (first == r) st->slot_prefix[slot] = s_prefix[r];
+    }
+    if (level < 2 && tid == 0) {
+        int n_slot = 0;
+        for (int j = 0; j < n_rank; ++j) {
+            bool fresh = true;
+            for (int k = 0; k < j; ++k)
+                if (s_prefix[k] == s_prefix[j]) { fresh = false; break; }
+            n_slot += fresh;
+        }
+        st->n_slot = n_slot;
+    }
+}
+
+int launch_radix_walk(const unsigned long long* hist, int level, const double* q_host, int n_q, int q_is_f32, int reverse,
+                      vu_radix_state* state, cudaStream_t stream) {
+    WalkQ wq;
+    for (int i = 0; i < 32; ++i) wq.q[i] = (q_host && i < n_q) ? q_host[i] : 0.0;
+    radix_walk_kernel<<<1, kWalkThreads, 0, stream>>>(hist, level, wq, n_q, q_is_f32, reverse, state);
+    count_launch("radix_walk");
+    return check_launch("radix_walk");
+}
+
 int launch_radix_hist(const float* values, long long n, const GtView& gt, int level, const unsigned* prefixes, int n_prefix,
-                      unsigned long long* hist, cudaStream_t stream) {
+                      unsigned long long* hist, cudaStream_t stream, const vu_radix_state* state) {
     long long blocks = (n + kRadixThreads - 1) / kRadixThreads;
     const long long cap = (long long)device_sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    radix_hist_kernel<<<(unsigned)blocks, kRadixThreads, 0, stream>>>(values, n, gt, level, prefixes, n_prefix, hist);
+    radix_hist_kernel<<<(unsigned)blocks, kRadixThreads, 0, stream>>>(values, n, gt, level, prefixes, n_prefix, hist, state);
     count_launch("radix_hist");
     return check_launch("radix_hist");
 }

@@ -220,13 +220,14 @@ __device__ __noinline__ double calib2_slow(const StatParams& sp, int k, float x,
     if (!nv) return 0.0;
     unsigned long long* irow = reinterpret_cast<unsigned long long*>(sp.i64 + b * VU_I64_COLS);
     double* frow = sp.f64 + b * VU_F64_COLS;
-    if (x != x) {
+    // (an infinite u with a zero slope gives a NaN confidence as well: (-inf) * 0 in ace.py:329)
+    const float conf = (x != x) ? x : platt_conf(x, sp.calib[k].a2, sp.calib[k].b2, 0);
+    if (conf != conf) {
         atomicAdd(irow + VU_I64_BIN_TOTAL + k * VU_N_BINS + (VU_N_BINS - 1), (unsigned long long)nv);
         if (nc) atomicAdd(irow + VU_I64_BIN_TRUE + k * VU_N_BINS + (VU_N_BINS - 1), (unsigned long long)nc);
         atomicAdd(frow + VU_F64_BIN_SUMS + k * VU_N_BINS + (VU_N_BINS - 1), (double)__int_as_float(0x7fc00000));
         return 0.0;
     }
-    const float conf = platt_conf(x, sp.calib[k].a2, sp.calib[k].b2, 0);
     const unsigned kb = __float_as_uint(fmaf(conf, 20.0f, kRoundMagic));
     const float uu = x * sp.calib[k].sgn;
     const unsigned bb = kb - (uu < lds_f(kb * 4u + ebase) ? 1u : 0u);

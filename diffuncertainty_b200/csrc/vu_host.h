@@ -33,7 +33,9 @@ long long patch_ctas_per_image(long long d0, long long d1, long long d2, int k0,
 int launch_border(const uint8_t* labels, long long B, long long d0, long long d1, long long d2, long long* stats_i64,
                   cudaStream_t stream);
 int launch_radix_hist(const float* values, long long n, const GtView& gt, int level, const unsigned* prefixes, int n_prefix,
-                      unsigned long long* hist, cudaStream_t stream);
+                      unsigned long long* hist, cudaStream_t stream, const vu_radix_state* state = nullptr);
+int launch_radix_walk(const unsigned long long* hist, int level, const double* q_host, int n_q, int q_is_f32, int reverse,
+                      vu_radix_state* state, cudaStream_t stream);
 int launch_binned_calib(const float* map, const uint8_t* labels, long long V, const GtView& gt, const CalibDev& cal, const uint8_t* lut,
                         unsigned long long* counts, double* sums, cudaStream_t stream);
 int launch_member_scores(const vu_member_scores_args* a, const GtView& gt, cudaStream_t stream);

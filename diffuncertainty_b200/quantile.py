@@ -53,6 +53,20 @@ def _gt_struct(gt: Optional[torch.Tensor], ignore_value, n: int):
     return s, g
 
 
+_WS = {}
+
+
+def _workspace(dev):
+    """Per-device workspace of the device-side selection: 64 x 2048 histogram counters, the vu_radix_state and its pinned
+    host mirror (allocated once: a selection is a handful of tiny launches, allocations would dominate it)."""
+    key = (dev.type, dev.index)
+    if key not in _WS:
+        _WS[key] = (torch.empty((64, 2048), dtype=torch.int64, device=dev),
+                    torch.zeros(C.sizeof(_lib.RadixState), dtype=torch.uint8, device=dev),
+                    torch.zeros(C.sizeof(_lib.RadixState), dtype=torch.uint8).pin_memory())
+    return _WS[key]
+
+
 class RadixSelect:
     """Exact rank selection over the multiset formed by all ``values`` tensors (float32, any shape).  With ``refs`` (one
     (R, *S) tensor per values tensor) voxel v counts once per reference that is not ``ignore_value``.  NaN sorts last,
@@ -70,8 +84,55 @@ class RadixSelect:
         self._vals = [_as_device_f32(v) for v in values]
         self._gts = [_gt_struct(None if refs is None else refs[i], ignore_value, self._vals[i].numel())
                      for i in range(len(self._vals))]
-        self._h0 = self._run_pass(0, np.zeros(0, np.uint32))
-        self.total = int(self._h0.sum())
+        self._h0_cache = None
+
+    @property
+    def _h0(self) -> np.ndarray:
+        if self._h0_cache is None:
+            self._h0_cache = self._run_pass(0, np.zeros(0, np.uint32))
+        return self._h0_cache
+
+    @property
+    def total(self) -> int:
+        return int(self._h0.sum())
+
+    def select_quantile_stats(self, qs, q_is_f32: bool = False, reverse: bool = False):
+        """The order statistics np.quantile (method "linear") needs for the fractions ``qs`` (at most 31), selected WITHOUT
+        host round trips between the passes: three histogram passes and three one-warp descents (vu_radix_walk) on the
+        current stream, then ONE read-back.  Returns (total, lo_stats, hi_stats, last) -- float32 order statistics of rank
+        floor((total - 1) q), the next rank, and the largest element (NaN if the data holds a NaN).  ``reverse`` selects the
+        mirrored ranks total - 1 - r instead (a confidence that falls with the uncertainty).  Not for sharded data
+        (``reduce``): there the histograms have to cross ranks between the passes."""
+        if self._reduce is not None:
+            raise ValueError("select_quantile_stats works on one device; use select() with reduce")
+        qs = np.ascontiguousarray(np.asarray(qs, np.float64).reshape(-1))
+        nq = len(qs)
+        if nq > 31:
+            raise ValueError("at most 31 quantile fractions per selection")
+        lib, dev, stream = self._lib, self._dev, _lib.current_stream_ptr()
+        hist, state, state_host = _workspace(dev)
+        qp = qs.ctypes.data_as(C.POINTER(C.c_double))
+        if len(self._vals) == 1:  # one array: the whole selection is one call
+            v, (gs, _keep) = self._vals[0], self._gts[0]
+            _lib.check(lib.vu_quantile_select(v.data_ptr(), v.numel(), C.byref(gs) if gs is not None else None, qp, nq, int(q_is_f32),
+                                              int(reverse), hist.data_ptr(), state.data_ptr(), stream), "vu_quantile_select")
+        else:
+            for level in range(3):
+                hist.zero_()
+                for v, (gs, _keep) in zip(self._vals, self._gts):
+                    _lib.check(lib.vu_radix_hist_state(v.data_ptr(), v.numel(), C.byref(gs) if gs is not None else None, level,
+                                                       state.data_ptr(), hist.data_ptr(), stream), "vu_radix_hist_state")
+                _lib.check(lib.vu_radix_walk(hist.data_ptr(), level, qp, nq, int(q_is_f32), int(reverse), state.data_ptr(), stream),
+                           "vu_radix_walk")
+        state_host.copy_(state, non_blocking=True)  # the one read-back (pinned)
+        torch.cuda.current_stream(dev).synchronize()
+        st = _lib.RadixState.from_buffer_copy(state_host.numpy().tobytes())
+        total = int(st.total)
+        if total == 0:
+            nan = np.full(nq, np.nan, np.float32)
+            return 0, nan, nan.copy(), np.float32(np.nan)
+        keys = _key_to_float(np.array(st.key[:2 * nq + 1], np.uint64))
+        return total, keys[0:2 * nq:2].copy(), keys[1:2 * nq:2].copy(), keys[2 * nq]
 
     def _run_pass(self, level: int, prefixes: np.ndarray) -> np.ndarray:
         n_slots = max(1, len(prefixes))
@@ -145,17 +206,36 @@ def lerp(a: np.ndarray, b: np.ndarray, t: np.ndarray) -> np.ndarray:
     return np.where(t >= 0.5, b - diff * (1 - t), a + diff * t)
 
 
-def quantile(values: Sequence, q, refs: Optional[Sequence] = None, ignore_value=None, dtype=np.float32, reduce=None):
+def quantile(values: Sequence, q, refs: Optional[Sequence] = None, ignore_value=None, dtype=np.float32, reduce=None, index_dtype=None):
     """np.quantile(np.concatenate(values), q) (method "linear") as NumPy 2.x evaluates it for data of ``dtype``: a Python
     scalar ``q`` is cast to ``dtype`` first (so the virtual index of a float32 map is a float32, find_threshold.py:76), an
     array ``q`` keeps its own dtype (float64 for the ``np.linspace`` of ace.py:387).  NaN in the data gives NaN.
+    ``index_dtype=np.float64`` evaluates the virtual index (n - 1) q and the interpolation weight in float64 whatever ``q``
+    is -- what NumPy 1.24 does, the version the reference pins in requirements.txt: with more than 2^24 pooled samples
+    (find_threshold.py:98-105 pools every validation map) a float32 index cannot address every rank and the two NumPy
+    generations select different order statistics.  The default follows the NumPy of this environment (2.x); the golden
+    vectors under tests/golden were recorded with it.  The rank selection itself is exact either way.
     ``reduce=all_reduce_sum``: the maps of this rank are one shard of the data set (find_threshold.py:98-105 over a sharded
     validation split); every rank gets the quantile of the union."""
     scalar = np.ndim(q) == 0
     qs = np.atleast_1d(np.asarray(q, dtype=dtype) if isinstance(q, (int, float)) else np.asarray(q))
+    if index_dtype is not None:
+        qs = qs.astype(index_dtype)
     if qs.size and (np.nanmin(qs) < 0 or np.nanmax(qs) > 1 or np.isnan(qs).any()):
         raise ValueError("Quantiles must be in the range [0, 1]")
     sel = RadixSelect(values, refs, ignore_value, reduce)
+    if reduce is None and 0 < qs.size <= 31 and qs.dtype in (np.float32, np.float64):
+        # one device: three passes and one read-back
+        total, s_lo, s_hi, last = sel.select_quantile_stats(qs.astype(np.float64), q_is_f32=qs.dtype == np.float32)
+        if total == 0:
+            res = np.full(qs.shape, np.nan)
+            return float("nan") if scalar else res
+        _, _, g = quantile_ranks(total, qs)
+        if np.isnan(last):
+            res = np.full(qs.shape, np.nan, np.result_type(dtype, g.dtype))
+        else:
+            res = lerp(s_lo.astype(dtype), s_hi.astype(dtype), g)
+        return res[0] if scalar else res
     total = sel.total
     if total == 0:
         res = np.full(qs.shape, np.nan)

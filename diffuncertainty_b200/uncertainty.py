@@ -65,9 +65,18 @@ class FusedResult:
 
     # -- per-image scores, all computed on the host in float64 from the rows --
     def _rows(self):
+        """Host copies of the two row blocks, read back once (the accessors below all go through here)."""
         if self.stats_f64 is None:
             raise ValueError("this pass was run without statistics (stats=0)")
-        return self.stats_f64.cpu().numpy(), self.stats_i64.cpu().numpy()
+        cached = self.__dict__.get("_host_rows")
+        if cached is None:
+            cached = (self.stats_f64.cpu().numpy(), self.stats_i64.cpu().numpy())
+            self.__dict__["_host_rows"] = cached
+        return cached
+
+    def refresh(self) -> None:
+        """Forget the host copies (the device rows accumulate: call this after another launch added to them)."""
+        self.__dict__.pop("_host_rows", None)
 
     def image_level(self, mean: bool = True) -> np.ndarray:
         """(B, 3) image_level_aggregation scores (aggregate_uncertainties.py:37-39)."""
@@ -159,6 +168,19 @@ def _members_view(members):
     return first
 
 
+@dataclass
+class Groups:
+    """``softmax_pred_groups`` of test_2D.py:1134-1136 handed over as they are: a list of G tensors ``(n_g, B, C, *S)`` -- one
+    stochastic sample per group unless several generative draws share one (test_2D.py:1160) -- that ``fused_pass`` reads in
+    place.  The kernel forms ``torch.stack(groups).mean(dim=1)`` (test_2D.py:1277) itself, in torch's order, optionally after
+    ``_renormalize_probabilities`` (test_2D.py:188-194, the last step of the TTA inversion) and / or the ``--discretize`` one-hot
+    (test_2D.py:1272-1275) of every draw: no stacked copy, no averaged copy, no one-hot copy of the slab exists."""
+    groups: Sequence[torch.Tensor]
+    renormalize: bool = False
+    discretize: bool = False
+    eps: float = 1e-12
+
+
 def group_members(groups: Sequence[torch.Tensor]) -> list:
     """test_2D.py:1277: ``torch.stack(groups).mean(dim=1)`` without the stack -- every group ``(n_g, B, C, *S)`` (one stochastic
     sample per group unless several generative draws share one, test_2D.py:1134-1136, 1160) becomes one member ``(B, C, *S)``
@@ -172,11 +194,47 @@ def group_members(groups: Sequence[torch.Tensor]) -> list:
     return members
 
 
+_PTR_TABLES: Dict[tuple, tuple] = {}
+
+
+def _pointer_table(members, dev):
+    """(host array, device tensor) of the members' base pointers.  Cached by the pointers themselves: a loop that hands the
+    same buffers over again (the usual case: the forward passes write into preallocated outputs) does no host -> device copy
+    and no synchronisation after the first call, which also makes the call capturable in a CUDA graph."""
+    ptrs = tuple(m.data_ptr() for m in members)
+    key = (ptrs, dev.index)
+    hit = _PTR_TABLES.get(key)
+    if hit is None:
+        if len(_PTR_TABLES) > 256:
+            _PTR_TABLES.clear()
+        host = (C.c_void_p * len(ptrs))(*ptrs)
+        staging = torch.tensor(ptrs, dtype=torch.int64).pin_memory()
+        table = torch.empty(len(ptrs), dtype=torch.int64, device=dev)
+        table.copy_(staging, non_blocking=True)
+        hit = (host, table, staging)
+        _PTR_TABLES[key] = hit
+    return hit[0], hit[1]
+
+
 def fill_slab(slab: _lib.Slab, softmax_pred):
     """Describe ``softmax_pred`` -- a (P, B, C, *S) tensor with any strides, or a list of P member tensors (B, C, *S)
     that are then read where they are (no torch.stack, test_2D.py:1277) -- in a vu_slab.  Returns
     (P, B, C, spatial, device, keep-alive objects)."""
     members = None
+    draws, sflags, eps = 1, 0, 1e-12
+    if isinstance(softmax_pred, Groups):
+        grp = softmax_pred
+        if not grp.groups:
+            raise ValueError("softmax_pred: empty group list")
+        g0 = grp.groups[0]
+        for g in grp.groups:
+            _check_slab(g, "softmax_pred group")
+            if g.dim() < 4 or g.shape != g0.shape or g.stride() != g0.stride() or g.device != g0.device:
+                raise ValueError("every group must be (n_g, B, C, *spatial) with one shape / stride pattern (torch.stack needs that too)")
+        draws = int(g0.shape[0])
+        sflags = (_lib.SLAB_RENORMALIZE if grp.renormalize else 0) | (_lib.SLAB_DISCRETIZE if grp.discretize else 0)
+        eps = float(grp.eps)
+        softmax_pred = [g[d] for g in grp.groups for d in range(draws)]  # P * draws views, draw-minor
     if isinstance(softmax_pred, (list, tuple)):
         # P separate member tensors (B, C, *S): read where they are, no torch.stack
         members = [m if m.dtype == torch.float32 else m.float() for m in softmax_pred]
@@ -188,7 +246,7 @@ def fill_slab(slab: _lib.Slab, softmax_pred):
         if _spatial_strides_flat(first, 2) is None:
             members = [m.contiguous() for m in members]
             first = members[0]
-        P, (B, Cn), spatial = len(members), first.shape[:2], tuple(first.shape[2:])
+        P, (B, Cn), spatial = len(members) // draws, first.shape[:2], tuple(first.shape[2:])
         sv, dev = _spatial_strides_flat(first, 2), first.device
         strides = (0, first.stride(0), first.stride(1))
     else:
@@ -211,9 +269,9 @@ def fill_slab(slab: _lib.Slab, softmax_pred):
     slab.P, slab.B, slab.C, slab.V = P, B, Cn, V
     slab.stride_p, slab.stride_b, slab.stride_c = strides
     slab.stride_v = sv
+    slab.draws, slab.flags, slab.renorm_eps, slab.stride_d = draws, sflags, eps, 0
     if members is not None:
-        host_ptrs = (C.c_void_p * P)(*[m.data_ptr() for m in members])
-        dev_ptrs = torch.tensor([m.data_ptr() for m in members], dtype=torch.int64).to(dev, non_blocking=False)
+        host_ptrs, dev_ptrs = _pointer_table(members, dev)
         slab.member_ptrs = dev_ptrs.data_ptr()
         slab.member_ptrs_host = C.cast(host_ptrs, C.c_void_p)
         keep = (host_ptrs, dev_ptrs, members)

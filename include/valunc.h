@@ -106,7 +106,23 @@ typedef struct vu_slab {
      * member_ptrs_host is the same array in HOST memory (used to validate alignment).  Both NULL = `data` form.   */
     const float* const* member_ptrs;
     const float* const* member_ptrs_host;
+    /* The upstream elementwise producers of the slab, folded into the read -- all zero = the slab is
+     * taken as it is.
+     *   draws > 1  every member is a GROUP of `draws` stochastic draws whose mean is the member: the reference's
+     *              torch.stack(softmax_pred_groups).mean(dim=1) (test_2D.py:1277; groups are built at :1134-1136, :1160).
+     *              `data` form: draw d of member p lies at data + p * stride_p + d * stride_d; member_ptrs form: P * draws
+     *              pointers, draw-minor.  The mean is formed in torch's order (cascade sum, true division).
+     *   VU_SLAB_RENORMALIZE  each draw is renormalised over its classes first (_renormalize_probabilities,
+     *              test_2D.py:188-194: p / max(sum_c p, eps) where sum_c p > eps).
+     *   VU_SLAB_DISCRETIZE   each draw is replaced by the one-hot vector of its argmax (--discretize, test_2D.py:1272-1275).
+     * These launches run on the generic kernel (any strides, any class count).                                           */
+    int64_t stride_d;
+    int32_t draws;
+    uint32_t flags;
+    float renorm_eps; /* test_2D.py:189: 1e-12 */
 } vu_slab;
+#define VU_SLAB_RENORMALIZE 0x1u
+#define VU_SLAB_DISCRETIZE 0x2u
 
 /* batch["seg"]: (B, R, V) reference segmentations (test_2D.py:1122-1124).    */
 typedef struct vu_gt {
@@ -326,6 +342,37 @@ VU_API int vu_member_scores(const vu_member_scores_args* args, void* stream);
  * prefixes: DEVICE array of n_prefix <= 64 values (ignored at level 0).                                          */
 VU_API int vu_radix_hist(const float* values, int64_t n, const vu_gt* weights_gt, int32_t level, const uint32_t* prefixes,
                          int32_t n_prefix, uint64_t* hist, void* stream);
+
+/* The same selection without host round trips between the passes.  A vu_radix_state lives in DEVICE memory; vu_radix_walk
+ * descends one level on the device and leaves there what the next histogram pass needs; vu_radix_hist_state is vu_radix_hist
+ * with the prefixes (and their number) taken from the state.  One selection = hist 0, walk 0, hist 1, walk 1, hist 2, walk 2 on
+ * one stream and ONE read-back of the state (total, key[]).
+ *   walk level 0: total = sum of the level-0 histogram; the ranks to select are derived from `n_q` quantile fractions
+ *                 (np.quantile, method "linear": h = (total - 1) q evaluated in float64, or in float32 when q_is_f32;
+ *                 lo = min(floor(h), total - 1), hi = min(lo + 1, total - 1)): rank[2i] = lo_i, rank[2i + 1] = hi_i, and
+ *                 rank[2 n_q] = total - 1 (a NaN anywhere in the data sorts last).  `reverse`: rank r -> total - 1 - r.
+ *                 n_q <= 31.  total == 0 leaves n_rank = 0.
+ *   walk level 1, 2: digit of every rank inside its slot, new prefixes; level 2 writes key[] (order-preserving float keys).
+ * hist: (64, 2048) uint64, zeroed by the caller before every histogram pass.                                               */
+#define VU_RADIX_MAX_RANKS 64
+typedef struct vu_radix_state {
+    int64_t total;
+    int32_t n_rank, n_slot;
+    int64_t rank[VU_RADIX_MAX_RANKS];
+    int64_t residual[VU_RADIX_MAX_RANKS];
+    uint32_t prefix[VU_RADIX_MAX_RANKS];      /* of every rank */
+    int32_t slot[VU_RADIX_MAX_RANKS];         /* histogram slot of every rank (ranks with one prefix share a slot) */
+    uint32_t slot_prefix[VU_RADIX_MAX_RANKS]; /* prefix of every slot */
+    uint32_t key[VU_RADIX_MAX_RANKS];
+} vu_radix_state;
+VU_API int vu_radix_walk(const uint64_t* hist, int32_t level, const double* q_host, int32_t n_q, int32_t q_is_f32, int32_t reverse,
+                         vu_radix_state* state, void* stream);
+VU_API int vu_radix_hist_state(const float* values, int64_t n, const vu_gt* weights_gt, int32_t level, const vu_radix_state* state,
+                               uint64_t* hist, void* stream);
+/* The whole selection over ONE array in one call: clears `hist` (64 x 2048 uint64 of device workspace) before each of the
+ * three passes, runs them and the three descents on `stream`.  The caller reads `state` back afterwards.                  */
+VU_API int vu_quantile_select(const float* values, int64_t n, const vu_gt* weights_gt, const double* q_host, int32_t n_q,
+                              int32_t q_is_f32, int32_t reverse, uint64_t* hist, vu_radix_state* state, void* stream);
 
 /* The three bincounts of calc_eqace (ace.py:392-396) for one map on 19 caller-given thresholds: sample u of voxel v
  * (weight = valid references) falls into bin #{k : u' >= edge_u[k]}, u' = u (mode INC / IDENTITY) or -u with

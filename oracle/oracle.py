@@ -802,3 +802,33 @@ def macro_dice_reference_semantics(label, gt_rater, n_classes, ignore_value=None
         if den > 0:
             vals.append(2.0 * (p & t).sum() / den)
     return float(np.mean(vals)) if vals else float("nan")
+
+
+# ---------------------------------------------------------------------------
+# upstream producers of the slab (uncertainty_modeling/test_2D.py:188-194, :1272-1277)
+# ---------------------------------------------------------------------------
+def renormalize_probabilities(probs: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """AlbumentationsTTABackend._renormalize_probabilities (test_2D.py:188-194), the reference's own torch expression: (B, C, *S) -> same."""
+    normalizer = probs.sum(dim=1, keepdim=True)
+    safe_normalizer = torch.clamp(normalizer, min=eps)
+    renormalized = probs / safe_normalizer
+    return torch.where(normalizer > eps, renormalized, probs)
+
+
+def build_softmax_pred(groups, discretize: bool = False) -> torch.Tensor:
+    """The tail of Tester._build_batch_predictions (test_2D.py:1272-1277): optional one-hot of every draw, then
+    torch.stack(groups).mean(dim=1).  groups: list of (n_g, B, C, H, W) tensors -> (G, B, C, H, W)."""
+    import torch.nn.functional as F
+    if discretize:
+        groups = [F.one_hot(torch.argmax(g, dim=2), num_classes=g.shape[2]).permute(0, 1, 4, 2, 3).float() for g in groups]
+    return torch.stack(list(groups)).mean(dim=1)
+
+
+def renormalize_probabilities_canonical(probs: np.ndarray, eps: float = 1e-12) -> np.ndarray:
+    """The same in NumPy with the summation order spelled out (cascade sum over the class axis, IEEE float32 division):
+    what the kernel implements.  probs: (B, C, *S) float32."""
+    p = np.asarray(probs, np.float32)
+    nrm = cascade_sum_f32(np.moveaxis(p, 1, 0))[:, None]
+    safe = np.maximum(nrm, np.float32(eps))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.where(nrm > np.float32(eps), (p / safe).astype(np.float32), p)

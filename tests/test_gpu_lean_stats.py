@@ -167,3 +167,26 @@ def test_unified_form_vs_oracle_cfg2_like(vu):
             s, t, nn = oracle.calib_histogram(correct, conf, binarize=False)
             assert np.array_equal(bn[b, k], nn) and np.array_equal(bt[b, k], t.astype(np.int64)), name
             np.testing.assert_allclose(bs[b, k], s, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("lean", [True, False])
+def test_zero_slope_platt_bins_like_numpy(vu, lean):
+    """a == 0 (the reference's fallback when the Platt fit fails): the constant confidence puts every sample into ONE bin, the
+    one np.digitize picks -- in both statistics forms."""
+    from diffuncertainty_b200 import _lib, calibration
+    x, gt = make_case(5, 2, (16, 64), 2, None, seed=2)
+    platt = [(0.0, 0.3), (0.0, -2.0), (3.5, -1.25)]
+    _lib.set_option("k1_path", 0 if lean else 1)
+    _lib.set_option("stats_path", 0 if lean else 1)
+    try:
+        res = vu.fused_pass(x, vu.GroundTruth(gt, None), stats=0x1d, calib=[calibration.platt_edges(a, b) for a, b in platt])
+    finally:
+        _lib.set_option("k1_path", 0)
+        _lib.set_option("stats_path", 0)
+    _, _, bn = res.calib_histograms()
+    n = 2 * 16 * 64
+    for k, (a, b) in enumerate(platt[:2]):
+        conf = np.clip(1 / (1 + np.exp(np.float32(0.0) * np.float32(a) + np.float32(b))), 0, 1)
+        want = np.digitize(np.float32(conf), np.linspace(0, 1 + 1e-8, 21)) - 1
+        for img in range(2):
+            assert bn[img, k, want] == n and bn[img, k].sum() == n, (k, want, bn[img, k])

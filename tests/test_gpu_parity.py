@@ -694,3 +694,60 @@ def test_border_and_area_random_shapes(vu):
     _lib.check(lib.vu_border_count(t.data_ptr(), B, *dims, si.data_ptr(), _lib.current_stream_ptr()), "vu_border_count")
     got = si[:, _lib.I64["BORDER"]].cpu().numpy()
     assert np.array_equal(got, [int(oracle.compute_border(l)) for l in labs])
+
+
+# --------------------------------------------------------------------------
+# statistics at one full BASELINE size per config (labels / counts bit-exact, sums 1e-5), one image each
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("name,P,C,spatial,R,ignore,flags", [
+    ("cfg1", 10, 2, (256, 256), 0, None, 0x07),
+    ("cfg2", 5, 2, (64, 64, 64), 4, None, 0x1d),
+    ("cfg3", 10, 19, (1024, 2048), 5, 255, 0x0f),
+    ("cfg4", 32, 2, (128, 128), 4, None, 0x21),
+    ("cfg5", 16, 19, (512, 1024), 1, 255, 0x1f),
+])
+def test_full_size_statistics_vs_oracle(vu, name, P, C, spatial, R, ignore, flags):
+    import os
+    from diffuncertainty_b200 import _lib, calibration, ncc as vncc, synth
+    from oracle import oracle
+    x = synth.synth_slab(P, 1, C, spatial, seed=17, scale=3.0)
+    gt_t = synth.synth_gt(x, max(R, 1), seed=17, flip=0.2, ignore_frac=0.02 if ignore is not None else 0.0,
+                          ignore_value=255 if ignore is None else ignore)
+    platt = [(3.5, -1.25), (6.0, -2.0), (40.0, -0.5)]
+    thr = [0.3, 0.2, 0.02]
+    res = vu.fused_pass(x, vu.GroundTruth(gt_t, ignore) if R else None, stats=flags, thresholds=thr,
+                        calib=[calibration.platt_edges(a, b) for a, b in platt] if flags & _lib.STAT_CALIB else None)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    xc = x[:, 0].cpu()
+    ref = oracle.calculate_uncertainty(xc)
+    label = oracle.argmax_first_nan_max(oracle.mean_members_f32(xc.numpy())).astype(np.uint8)
+    assert np.array_equal(res.labels[0].cpu().numpy(), label)
+    got = {k: res.maps[k][0].cpu().numpy() for k in ("TU", "AU", "EU")}
+    assert_maps_close(got, {k: v.numpy() for k, v in ref.items()}, name)
+    gnp = gt_t[0].cpu().numpy()
+    if flags & _lib.STAT_AREA:
+        assert res.area()[0] == oracle.compute_area(label)
+    if flags & _lib.STAT_DICE:
+        tp, ps, gs = res.dice_counts()
+        otp, ops, ogs = oracle.binary_dice_counts(label, gnp, -12345 if ignore is None else ignore)
+        assert np.array_equal(tp[0], otp) and np.array_equal(ps[0], ops) and np.array_equal(gs[0], ogs)
+    for k, key in enumerate(("TU", "AU", "EU")):
+        m = got[key]
+        if flags & _lib.STAT_IMAGE_SUM:
+            np.testing.assert_allclose(res.image_level()[0, k], oracle.image_level_aggregation(m)["max_score"], rtol=RTOL, atol=1e-9)
+        if flags & _lib.STAT_THRESHOLD:
+            np.testing.assert_allclose(res.threshold_level()[0, k], float(oracle.threshold_aggregation(m, np.float32(thr[k]))["max_score"]), rtol=RTOL)
+            assert int(res.stats_i64[0, _lib.I64["THR_COUNT"] + k]) == int((m >= np.float32(thr[k])).sum())
+        if flags & _lib.STAT_CALIB:
+            bs, bt, bn = res.calib_histograms()
+            correct, conf = oracle.calibration_inputs(gnp, label, m, platt[k][0], platt[k][1], ignore)
+            s, t, n = oracle.calib_histogram(correct, conf, binarize=False)
+            assert np.array_equal(bn[0, k], n) and np.array_equal(bt[0, k], t.astype(np.int64)), key
+            np.testing.assert_allclose(bs[0, k], s, rtol=RTOL, atol=1e-9)
+        if flags & _lib.STAT_NCC:
+            # NCC from the kernel's sums against the reference formula on the kernel's OWN map: 1e-5.  (Against the
+            # reference's map the bound is the map error times the conditioning of the covariance)
+            # NCC is a correlation in [-1, 1] formed from a covariance that cancels (synthetic references: ~3e-4 here), so the
+            # error is bounded absolutely: 1e-5 relative or 1e-7 absolute, whichever is larger.
+            want = oracle.compute_ncc(oracle.rater_variance_map(gnp), m)
+            np.testing.assert_allclose(vncc.ncc_from_result(res, k)[0], want, rtol=RTOL, atol=1e-7)

@@ -105,3 +105,24 @@ def test_group_members_equals_stack_mean():
         pass
     else:
         raise AssertionError("a group without a spatial axis must be rejected")
+
+
+def test_platt_edges_zero_slope_and_hints():
+    """a == 0 is the reference's own fallback when the Platt fit fails (ace.py: a, b = 0.0, 0.0): the confidence is a constant
+    and every sample falls into one bin.  Hints (used by eqACE to shorten the bisection) never change the thresholds."""
+    import numpy as np
+    from diffuncertainty_b200 import calibration as c
+    rng = np.random.default_rng(0)
+    u = np.concatenate([rng.random(500), [0.0, 7.5, -1.0]]).astype(np.float32)
+    for b in (0.0, 0.3, -2.0, 5.0):
+        pe = c.platt_edges(0.0, b)
+        with np.errstate(over="ignore"):
+            conf = np.clip(1 / (1 + np.exp((-u) * np.float32(0.0) + np.float32(b))), 0, 1)
+        assert np.array_equal(pe.bin_of(u), np.digitize(conf, c.bin_edges()) - 1), b
+    for a, b in ((3.5, -1.25), (-40.0, 0.5)):
+        e = np.sort(rng.random(19)) * 0.9 + 0.05
+        want = c.platt_edges(a, b, e).edge_u
+        near = np.stack([np.nextafter(want, np.float32(-np.inf)), np.nextafter(want, np.float32(np.inf))])
+        far = np.stack([np.sort(rng.random(19)).astype(np.float32), np.full(19, np.nan, np.float32)])
+        for hints in (near, far):
+            assert np.array_equal(c.platt_edges(a, b, e, hints=hints).edge_u, want, equal_nan=True)

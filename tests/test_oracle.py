@@ -267,3 +267,21 @@ def test_ged_and_likelihood_match_golden(golden_ged_nll):
                                        float(g[f"{name}/expected_nll"]), rtol=2e-6, atol=1e-7)
     with pytest.raises(ValueError):
         oracle.ged_binary_fast(torch.zeros(3, 3, 4, 4), np.zeros((2, 4, 4), np.int64))
+
+
+def test_renormalize_canonical_order_matches_torch_and_reference():
+    """The class-sum order the kernel uses for _renormalize_probabilities (cascade over the class axis) is torch's, and the
+    oracle's expression is the reference's (test_2D.py:188-194)."""
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(3)
+    for C, S in ((19, (8, 32)), (2, (16, 32)), (40, (4, 32))):
+        p = torch.softmax(3 * torch.randn(2, C, *S, generator=g), dim=1) * (1 + 0.05 * torch.randn(2, 1, *S, generator=g))
+        p[0, :, 0, :3] = 0.0
+        a = oracle.renormalize_probabilities(p).numpy()
+        b = oracle.renormalize_probabilities_canonical(p.numpy())
+        assert same_bits(a, b)
+        if ref_shim.available():
+            ref_shim.load()
+            import importlib
+            backend = importlib.import_module("uncertainty_modeling.test_2D").AlbumentationsTTABackend
+            assert same_bits(backend._renormalize_probabilities(p).numpy(), a)
