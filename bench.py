@@ -510,7 +510,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images-per-step", type=int, default=16)
     ap.add_argument("--e2e-images", type=int, default=16)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config pipelines (configs[0..4]) in the JSON line")
     ap.add_argument("--cpu-images", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")

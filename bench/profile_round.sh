@@ -5,11 +5,11 @@
 tag=${1:-rXX}
 out=gpurun_out
 python bench.py --steps 20 --warmup 3 > $out/${tag}_bench_line.json 2> $out/${tag}_bench.err || exit 1
-short="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+short="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-configs"
 $short > $out/${tag}_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv \
     --log-file $out/${tag}_launches_bench.csv $short > $out/${tag}_ncu_list.log 2>&1
 $short > $out/${tag}_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k1_tma -s 3 -c 1 \
     -o $out/${tag}_k1_tma_bench $short > $out/${tag}_ncu_full.log 2>&1
-python bench/sweep_tma.py --stages 0 --flags 0x0,0x07,0x1f,0x3f > $out/${tag}_sweep_all_configs.txt 2>&1
-python bench/bench_k2k3.py > $out/${tag}_k2_k3_timing.txt 2>&1
+python bench/bench_configs.py > $out/${tag}_configs.jsonl 2>&1
+python bench/bench_k2k3.py > $out/${tag}_k2_k3_k4_timing.txt 2>&1
 tail -c 700 $out/${tag}_bench_line.json
