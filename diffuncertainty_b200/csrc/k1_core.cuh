@@ -184,6 +184,8 @@ struct VoxelAcc {
         cascade_step(p);
     }
 
+    static constexpr float kExactLo = 2.524354896707238e-29f;  // 2^-95
+    static constexpr unsigned kExactLoBits = 0x10000000u;
     // mean (true division, test_2D.py:971), label, TU, AU, EU of the VEC voxels
     __device__ __forceinline__ void finish(float Pf, float (&u)[VU_N_UNC][VEC], int (&label)[VEC]) const {
         const bool fast_div = Pf <= 271.0f;
@@ -209,17 +211,22 @@ struct VoxelAcc {
         }
 #pragma unroll
         for (int k = 0; k < VEC; ++k) asum[k] = -(asum[k] * kLn2);
-        bool exact = fast_div;
+        // in range: a == 0 or 2^-95 <= |a| <= 1e30, no NaN.  min.NaN(|a|, 2^-95) is 0 or 2^-95 (one bit: 0x10000000) exactly
+        // when the lower bound holds (NaN stays NaN), so an OR over the bit patterns tests all values at once; the upper bound is
+        // a test of the largest |a|.
+        unsigned low_bits = 0u;
+        float largest = 0.f;
+        auto in_range = [&](float a) {
+            float b;
+            asm("min.NaN.f32 %0, %1, %2;" : "=f"(b) : "f"(fabsf(a)), "f"(kExactLo));
+            low_bits |= __float_as_uint(b);
+            largest = fmaxf(largest, fabsf(a));
+        };
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const float a = fabsf(sums[e]);
-            exact = exact && ((a > 1e-30f && a < 1e30f) || sums[e] == 0.0f);
-        }
+        for (int e = 0; e < E; ++e) in_range(sums[e]);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            const float a = fabsf(asum[k]);
-            exact = exact && ((a > 1e-30f && a < 1e30f) || asum[k] == 0.0f);
-        }
+        for (int k = 0; k < VEC; ++k) in_range(asum[k]);
+        const bool exact = fast_div && (low_bits & (kExactLoBits - 1u)) == 0u && largest <= 1e30f;
         float qs[C * VEC], au[VEC];
         if (exact) {
 #pragma unroll

@@ -19,6 +19,7 @@
 #include "tma_common.cuh"
 #include <math.h>
 #include <string.h>
+#include <type_traits>
 
 #include "vu_host.h"
 
@@ -35,7 +36,6 @@ struct K1UniParams {
     float* au;
     float* eu;
     uint8_t* lab;
-    uint8_t* mlab;  // per-member labels (P, B, V) or NULL
     long long tiles_per_img, total_tiles;
     int nstages;
     unsigned bar_offset;    // byte offsets inside dynamic shared memory
@@ -83,11 +83,13 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
     stats2_init<kUniRep>(sp, st_smem, tid, CT + 32, kWarps);
     __syncthreads();
 
-    const long long P = prm.P, V = prm.V;
+    const long long V = prm.V;
+    const int P = (int)prm.P;
     const int t0 = (int)(prm.total_tiles * (long long)blockIdx.x / gridDim.x);
     const int t1 = (int)(prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x);
     const int tpi = (int)prm.tiles_per_img;
-    const int fills = (int)((P + G - 1) / G);  // stage fills per tile
+    const int fills = (P + G - 1) / G;  // stage fills per tile
+    const int full_fills = P / G, rem = P - full_fills * G;  // ... of which full ones, and the members in the last one otherwise
 
     if (tid >= CT) {
         // ------------------------------ producer warp ---------------------------------------------------
@@ -145,8 +147,8 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
     unsigned full_bar = full0, empty_bar = empty0;
     unsigned phase = 0;
     const unsigned ring_end = (unsigned)nstages * kStageBytes;
-    const unsigned my_ring = smem_u32(ring) + (unsigned)tid * (VEC * (unsigned)sizeof(float));
-    const bool want_ml = prm.mlab != nullptr;
+    unsigned my_ring = smem_u32(ring) + (unsigned)tid * (VEC * (unsigned)sizeof(float));
+    asm volatile("" : "+r"(my_ring));  // keep it in a register (rematerialised per stage otherwise: S2UR + ULEA + LEA)
     long long img_out = 0;       // b * V: offset of the image in the (B, V) outputs
     const uint8_t* gt_img = nullptr;  // references of the image
     unsigned Wn[RMAX];           // MS: the reference words of the next tile
@@ -185,23 +187,25 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
 
         Acc acc;
         acc.init();
-        for (int fi = 0; fi < fills; ++fi) {
+        // One ring stage = G members.  FULL: all G are there (no per-member test); otherwise the first `rem` (the last stage of a
+        // tile when G does not divide P).
+        auto consume_stage = [&](auto full_tag, const int p0) {
+            constexpr bool FULL = decltype(full_tag)::value;
             mbar_wait(full_bar, phase);  // the bytes of this stage have landed
             const unsigned sbase = my_ring + stage_off;
             // (a partial last tile leaves stale bytes behind the image's end: those threads are inactive and
             //  their arithmetic is discarded)
-            const int p0 = fi * G;
             if constexpr (MS) {
                 // two members per stage: their likelihood values are folded over the lanes together
                 static_assert(!MS || G == 2, "the member-score fold takes the members in pairs");
-                const bool has_b = p0 + 1 < P;
                 f32x2 xa[Acc::NP], xb[Acc::NP], La[Acc::NP], Lb[Acc::NP];
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xa[c * 2]), "=l"(xa[c * 2 + 1]) : "r"(sbase + (unsigned)(c * kRowBytes)));
-                    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xb[c * 2]), "=l"(xb[c * 2 + 1]) : "r"(sbase + (unsigned)((C + c) * kRowBytes)));
+                    if constexpr (FULL)
+                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xb[c * 2]), "=l"(xb[c * 2 + 1]) : "r"(sbase + (unsigned)((C + c) * kRowBytes)));
                 }
-                if (!has_b) {  // odd member count: the second half of the stage holds no member
+                if constexpr (!FULL) {  // odd member count: the second half of the stage holds no member
 #pragma unroll
                     for (int i = 0; i < Acc::NP; ++i) xb[i] = 0ull;
                 }
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
                 acc.add_member_L(xa, p0, false, La);
                 if (ms_ged) mw.member_labels(p0, xa);
                 if (ms_nll) mw.member_values(xa, La, sp.gt.R, prm.ms.log2eps, slow, va);
-                if (has_b) {
+                if constexpr (FULL) {
                     acc.add_member_L(xb, p0 + 1, false, Lb);
                     if (ms_ged) mw.member_labels(p0 + 1, xb);
                     if (ms_nll) mw.member_values(xb, Lb, sp.gt.R, prm.ms.log2eps, slow, vb);
@@ -223,13 +227,12 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
             } else {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    if (G == 1 || p0 + g < P) {
+                    if (FULL || g < rem) {
                         f32x2 xp[Acc::NP];
 #pragma unroll
                         for (int c = 0; c < C; ++c)
                             asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xp[c * 2]), "=l"(xp[c * 2 + 1]) : "r"(sbase + (unsigned)((g * C + c) * kRowBytes)));
-                        acc.add_member(xp, 0.f, p0 + g, want_ml);
-                        if (want_ml && active) VecLoad<VEC>::store_u8(prm.mlab + ((long long)(p0 + g) * prm.B + b) * V + v, acc.bi);
+                        acc.add_member(xp, 0.f, p0 + g, false);
                     }
                 }
             }
@@ -237,7 +240,9 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
             if ((tid & 31) == 0) mbar_arrive(empty_bar);  // this warp is done reading the stage
             stage_off += kStageBytes; full_bar += 8; empty_bar += 8;
             if (stage_off == ring_end) { stage_off = 0u; full_bar = full0; empty_bar = empty0; phase ^= 1; }
-        }
+        };
+        for (int fi = 0; fi < full_fills; ++fi) consume_stage(std::true_type{}, fi * G);
+        if (rem) consume_stage(std::false_type{}, full_fills * G);
 
         float u[VU_N_UNC][VEC];
         int label[VEC];
@@ -332,15 +337,15 @@ int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t str
         if ((a->members.flags & VU_MS_NLL) && (!a->members.nll_sum || !a->members.nll_count || !a->members.nll_bad))
             return set_error(VU_ERR_BAD_ARG, "members: NLL outputs are NULL");
         if ((a->members.flags & VU_MS_GED) && !a->members.ged_counts) return set_error(VU_ERR_BAD_ARG, "members.ged_counts is NULL");
-        if (a->member_labels) return no("member scores in the fused pass and member_labels are not computed by the same kernel");
     }
+    if (a->member_labels) return no("per-member labels are written by the warp-specialised / register-streaming kernels only");
     // bulk copies need 16-byte aligned rows and sizes
     if ((uintptr_t)s.data % 16 || s.V % 4 || (!s.member_ptrs && s.stride_p % 4) || s.stride_b % 4 || s.stride_c % 4) return no("rows are not 16-byte aligned");
     if (s.member_ptrs_host)
         for (int64_t p = 0; p < s.P; ++p)
             if ((uintptr_t)s.member_ptrs_host[p] % 16) return no("rows are not 16-byte aligned");
     auto ok = [&](const void* p, uintptr_t al) { return p == nullptr || ((uintptr_t)p % al) == 0; };
-    if (!ok(a->tu, 16) || !ok(a->au, 16) || !ok(a->eu, 16) || !ok(a->labels, 4) || !ok(a->member_labels, 4)) return no("outputs are not 16-byte aligned");
+    if (!ok(a->tu, 16) || !ok(a->au, 16) || !ok(a->eu, 16) || !ok(a->labels, 4)) return no("outputs are not 16-byte aligned");
     const int need_levels = s.P <= 17 ? 1 : 2;
     const int rmax = (st.flags & heavy) && st.gt.R > 4 ? 8 : 4;
     const UniVariant* pick = nullptr;
@@ -361,7 +366,6 @@ int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     prm.P = s.P; prm.B = s.B; prm.V = s.V;
     prm.sp = s.stride_p; prm.sb = s.stride_b; prm.sc = s.stride_c;
     prm.tu = a->tu; prm.au = a->au; prm.eu = a->eu; prm.lab = a->labels;
-    prm.mlab = a->member_labels;
     prm.st = st;
     memset(&prm.ms, 0, sizeof(prm.ms));
     if (want_ms) {

@@ -10,6 +10,7 @@
 //                     per-image quantile edges pulled back onto the uncertainty axis); float64 sums.
 #include "vu_common.cuh"
 #include "vu_host.h"
+#include <string.h>
 
 namespace vu {
 
@@ -35,11 +36,28 @@ __device__ __forceinline__ int sample_weight(const GtView& gt, long long i) {
 constexpr int kRadixThreads = 256;
 constexpr int kMaxPrefixes = 64;
 
+// Batched form (vu_quantile_select_batch / vu_binned_calib_batch): segment s = m * B + b is image b of map m; every segment
+// has its own histogram block, state, thresholds and outputs, the references are those of image b.  n_maps == 0: one array.
+struct SegBatch {
+    int n_maps, B;
+    const float* maps[4];
+};
+__device__ __forceinline__ void seg_gt(GtView& gt, long long b) {
+    if (gt.data) gt.data = reinterpret_cast<const char*>(gt.data) + b * gt.sb * (gt.dtype == VU_GT_U8 ? 1 : 8);
+}
+
 __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const float* __restrict__ values, long long n, GtView gt, int level,
                                                                   const unsigned* __restrict__ prefixes, int n_prefix,
-                                                                  unsigned long long* hist, const vu_radix_state* state) {
+                                                                  unsigned long long* hist, const vu_radix_state* state, SegBatch seg) {
     __shared__ unsigned h0[2048];
     __shared__ unsigned pre[kMaxPrefixes];
+    if (seg.n_maps) {
+        const int sgm = blockIdx.y, m = sgm / seg.B, b = sgm - m * seg.B;
+        values = seg.maps[m] + (long long)b * n;
+        seg_gt(gt, b);
+        hist += (size_t)sgm * kMaxPrefixes * 2048;
+        state += sgm;
+    }
     if (state && level > 0) {  // prefixes left on the device by vu_radix_walk
         n_prefix = state->n_slot;
         prefixes = state->slot_prefix;
@@ -96,7 +114,12 @@ __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const float* 
 struct WalkQ { double q[32]; };
 constexpr int kWalkThreads = 1024;
 __global__ void __launch_bounds__(kWalkThreads) radix_walk_kernel(const unsigned long long* __restrict__ hist, int level, WalkQ wq, int n_q,
-                                                                   int q_is_f32, int reverse, vu_radix_state* st) {
+                                                                   int q_is_f32, int reverse, vu_radix_state* st, int seg_B) {
+    if (seg_B) {  // batched: one CTA per segment; `reverse` is a bit mask over the maps
+        st += blockIdx.x;
+        hist += (size_t)blockIdx.x * kMaxPrefixes * 2048;
+        reverse = (reverse >> (blockIdx.x / seg_B)) & 1;
+    }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     __shared__ long long s_part[32];
     __shared__ long long s_total;
@@ -211,10 +234,10 @@ __global__ void __launch_bounds__(kWalkThreads) radix_walk_kernel(const unsigned
 }
 
 int launch_radix_walk(const unsigned long long* hist, int level, const double* q_host, int n_q, int q_is_f32, int reverse,
-                      vu_radix_state* state, cudaStream_t stream) {
+                      vu_radix_state* state, cudaStream_t stream, int n_seg, int seg_B) {
     WalkQ wq;
     for (int i = 0; i < 32; ++i) wq.q[i] = (q_host && i < n_q) ? q_host[i] : 0.0;
-    radix_walk_kernel<<<1, kWalkThreads, 0, stream>>>(hist, level, wq, n_q, q_is_f32, reverse, state);
+    radix_walk_kernel<<<n_seg > 0 ? n_seg : 1, kWalkThreads, 0, stream>>>(hist, level, wq, n_q, q_is_f32, reverse, state, n_seg > 0 ? seg_B : 0);
     count_launch("radix_walk");
     return check_launch("radix_walk");
 }
@@ -225,7 +248,27 @@ int launch_radix_hist(const float* values, long long n, const GtView& gt, int le
     const long long cap = (long long)device_sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    radix_hist_kernel<<<(unsigned)blocks, kRadixThreads, 0, stream>>>(values, n, gt, level, prefixes, n_prefix, hist, state);
+    SegBatch seg;
+    memset(&seg, 0, sizeof(seg));
+    radix_hist_kernel<<<(unsigned)blocks, kRadixThreads, 0, stream>>>(values, n, gt, level, prefixes, n_prefix, hist, state, seg);
+    count_launch("radix_hist");
+    return check_launch("radix_hist");
+}
+
+// one histogram pass over every segment of a batch: grid.y = segment, grid.x shares 8 CTAs per SM among the segments
+int launch_radix_hist_batch(const float* const* maps, int n_maps, long long B, long long V, const GtView& gt, int level,
+                            unsigned long long* hist, cudaStream_t stream, const vu_radix_state* states) {
+    SegBatch seg;
+    memset(&seg, 0, sizeof(seg));
+    seg.n_maps = n_maps; seg.B = (int)B;
+    for (int m = 0; m < n_maps; ++m) seg.maps[m] = maps[m];
+    const long long n_seg = (long long)n_maps * B;
+    long long blocks = (V + kRadixThreads - 1) / kRadixThreads;
+    long long cap = (long long)device_sm_count() * 8 / n_seg;
+    if (cap < 1) cap = 1;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    radix_hist_kernel<<<dim3((unsigned)blocks, (unsigned)n_seg), kRadixThreads, 0, stream>>>(nullptr, V, gt, level, nullptr, 0, hist, states, seg);
     count_launch("radix_hist");
     return check_launch("radix_hist");
 }
@@ -240,6 +283,8 @@ struct BinnedParams {
     const uint8_t* lut;
     unsigned long long* counts;  // [2][21]: samples, correct samples
     double* sums;                // [21]
+    SegBatch seg;                // batched: per segment its map, image, thresholds (cals[s]) and output rows
+    const vu_calib* cals;        // DEVICE array, one per segment
 };
 
 constexpr int kBinnedThreads = 256;
@@ -252,7 +297,28 @@ __global__ void __launch_bounds__(kBinnedThreads) binned_calib_kernel(const __gr
     for (int t = threadIdx.x; t < WARPS * VU_N_BINS; t += kBinnedThreads) {
         (&s_sum[0][0])[t] = 0.0; (&s_tot[0][0])[t] = 0; (&s_tru[0][0])[t] = 0;
     }
-    if (threadIdx.x < VU_N_EDGES) thr[threadIdx.x] = prm.cal.edge[threadIdx.x];
+    const float* map = prm.map;
+    const uint8_t* labels = prm.labels;
+    GtView gt = prm.gt;
+    unsigned long long* counts = prm.counts;
+    double* sums = prm.sums;
+    bool increasing = prm.cal.increasing, identity = prm.cal.identity;
+    float ca = prm.cal.a, cb = prm.cal.b;
+    if (prm.seg.n_maps) {
+        const int sgm = blockIdx.y, m = sgm / prm.seg.B, b = sgm - m * prm.seg.B;
+        map = prm.seg.maps[m] + (long long)b * prm.V;
+        if (labels) labels += (long long)b * prm.V;
+        seg_gt(gt, b);
+        counts += (size_t)sgm * 2 * VU_N_BINS;
+        sums += (size_t)sgm * VU_N_BINS;
+        const vu_calib& c = prm.cals[sgm];
+        increasing = c.mode != VU_CALIB_PLATT_DEC;
+        identity = c.mode == VU_CALIB_IDENTITY;
+        ca = c.a; cb = c.b;
+        if (threadIdx.x < VU_N_EDGES) thr[threadIdx.x] = increasing ? c.edge_u[threadIdx.x] : -c.edge_u[threadIdx.x];
+    } else if (threadIdx.x < VU_N_EDGES) {
+        thr[threadIdx.x] = prm.cal.edge[threadIdx.x];
+    }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * kBinnedThreads;
@@ -261,30 +327,30 @@ __global__ void __launch_bounds__(kBinnedThreads) binned_calib_kernel(const __gr
         int bin = -1, nv = 0, nc = 0;
         double w = 0.0;
         if (i < prm.V) {
-            const int label = prm.labels ? (int)__ldg(prm.labels + i) : 0;
+            const int label = labels ? (int)__ldg(labels + i) : 0;
             const long long cmp = prm.lut ? (long long)__ldg(prm.lut + label) : (long long)label;
-            for (int r = 0; r < prm.gt.R; ++r) {
-                const long long off = (long long)r * prm.gt.sr + i * prm.gt.sv;
-                const long long g = prm.gt.dtype == VU_GT_U8 ? (long long)__ldg(reinterpret_cast<const uint8_t*>(prm.gt.data) + off)
-                                                             : __ldg(reinterpret_cast<const long long*>(prm.gt.data) + off);
-                const bool valid = !(prm.gt.has_ignore && g == prm.gt.ignore);
+            for (int r = 0; r < gt.R; ++r) {
+                const long long off = (long long)r * gt.sr + i * gt.sv;
+                const long long g = gt.dtype == VU_GT_U8 ? (long long)__ldg(reinterpret_cast<const uint8_t*>(gt.data) + off)
+                                                         : __ldg(reinterpret_cast<const long long*>(gt.data) + off);
+                const bool valid = !(gt.has_ignore && g == gt.ignore);
                 nv += valid;
                 nc += valid && g == cmp;
             }
             if (nv > 0) {
-                const float u = __ldg(prm.map + i);
+                const float u = __ldg(map + i);
                 if (u != u) {
                     bin = VU_N_BINS - 1;  // NaN: past the last edge
                     w = (double)u;
                 } else {
-                    const float uu = prm.cal.increasing ? u : -u;
+                    const float uu = increasing ? u : -u;
                     bin = 0;
 #pragma unroll
                     for (int k = 0; k < VU_N_EDGES; ++k) bin += (uu >= thr[k]) ? 1 : 0;  // NaN thresholds compare false
                     // ace.py:329 in float32 (the bins do not depend on it, only the float64 sums do)
                     float conf;
-                    if (prm.cal.identity) conf = fminf(fmaxf(u, 0.0f), 1.0f);
-                    else conf = fminf(fmaxf(__fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fadd_rn(__fmul_rn(-u, prm.cal.a), prm.cal.b)))), 0.0f), 1.0f);
+                    if (identity) conf = fminf(fmaxf(u, 0.0f), 1.0f);
+                    else conf = fminf(fmaxf(__fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fadd_rn(__fmul_rn(-u, ca), cb)))), 0.0f), 1.0f);
                     w = (double)conf * (double)nv;
                 }
             }
@@ -308,9 +374,9 @@ __global__ void __launch_bounds__(kBinnedThreads) binned_calib_kernel(const __gr
         double s = 0.0;
         for (int w = 0; w < WARPS; ++w) { tot += s_tot[w][t]; tru += s_tru[w][t]; s += s_sum[w][t]; }
         if (tot) {
-            atomicAdd(prm.counts + t, (unsigned long long)tot);
-            if (tru) atomicAdd(prm.counts + VU_N_BINS + t, (unsigned long long)tru);
-            atomicAdd(prm.sums + t, s);
+            atomicAdd(counts + t, (unsigned long long)tot);
+            if (tru) atomicAdd(counts + VU_N_BINS + t, (unsigned long long)tru);
+            atomicAdd(sums + t, s);
         }
     }
 }
@@ -319,10 +385,29 @@ int launch_binned_calib(const float* map, const uint8_t* labels, long long V, co
                         unsigned long long* counts, double* sums, cudaStream_t stream) {
     BinnedParams prm;
     prm.map = map; prm.labels = labels; prm.V = V; prm.gt = gt; prm.cal = cal; prm.lut = lut; prm.counts = counts; prm.sums = sums;
+    memset(&prm.seg, 0, sizeof(prm.seg));
+    prm.cals = nullptr;
     long long blocks = (V + kBinnedThreads - 1) / kBinnedThreads;
     const long long cap = (long long)device_sm_count() * 8;
     if (blocks > cap) blocks = cap;
     binned_calib_kernel<<<(unsigned)blocks, kBinnedThreads, 0, stream>>>(prm);
+    count_launch("binned_calib");
+    return check_launch("binned_calib");
+}
+
+int launch_binned_calib_batch(const float* const* maps, int n_maps, long long B, long long V, const uint8_t* labels, const GtView& gt,
+                              const vu_calib* cals_dev, const uint8_t* lut, unsigned long long* counts, double* sums, cudaStream_t stream) {
+    BinnedParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.labels = labels; prm.V = V; prm.gt = gt; prm.lut = lut; prm.counts = counts; prm.sums = sums; prm.cals = cals_dev;
+    prm.seg.n_maps = n_maps; prm.seg.B = (int)B;
+    for (int m = 0; m < n_maps; ++m) prm.seg.maps[m] = maps[m];
+    const long long n_seg = (long long)n_maps * B;
+    long long blocks = (V + kBinnedThreads - 1) / kBinnedThreads;
+    long long cap = (long long)device_sm_count() * 8 / n_seg;
+    if (cap < 1) cap = 1;
+    if (blocks > cap) blocks = cap;
+    binned_calib_kernel<<<dim3((unsigned)blocks, (unsigned)n_seg), kBinnedThreads, 0, stream>>>(prm);
     count_launch("binned_calib");
     return check_launch("binned_calib");
 }

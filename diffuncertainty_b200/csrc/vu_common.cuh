@@ -141,7 +141,7 @@ __device__ __forceinline__ void plog2p_parts2(f32x2 P, f32x2& PC, f32x2& L) {
 
 // torch.argmax tie rule (test_2D.py:817,871): first maximal index, NaN is max.
 __device__ __forceinline__ void argmax_step(float v, int c, float& best, int& idx) {
-    const bool take = (v > best) || ((v != v) && (best == best));
+    const bool take = (v > best) | ((v != v) & (best == best));  // (no short-circuit: three compares, no branches)
     best = take ? v : best;
     idx = take ? c : idx;
 }

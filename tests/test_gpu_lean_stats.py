@@ -103,11 +103,16 @@ def test_unified_form_with_nan_and_inf_maps(vu, flags):
     assert nan_slot > 0, "NaN samples belong to slot 20 (np.digitize)"
 
 
-def test_unified_form_accumulates_and_keeps_member_labels(vu):
+def test_unified_form_accumulates_and_member_labels_fall_back(vu):
     x, gt = make_case(5, 2, (16, 128), 2, None, seed=5)
-    once, n = run(vu, x, gt, None, 0x1d, lean=True, want_member_labels=True)
+    # per-member labels are written by the other two forms: the launch must not go to the unified kernel, and agree with it
+    with_labels, n = run(vu, x, gt, None, 0x1d, lean=True, want_member_labels=True)
+    assert n == 0
+    assert torch.equal(with_labels.member_labels, x.argmax(dim=2).to(torch.uint8))
+    once, n = run(vu, x, gt, None, 0x1d, lean=True)
     assert n == 1
-    assert torch.equal(once.member_labels, x.argmax(dim=2).to(torch.uint8))
+    assert torch.equal(with_labels.stats_i64, once.stats_i64)
+    torch.testing.assert_close(with_labels.stats_f64, once.stats_f64, rtol=1e-7, atol=0)  # float32 partial sums per tile, another tile size
     sf, si = torch.zeros_like(once.stats_f64), torch.zeros_like(once.stats_i64)
     for _ in range(3):
         run(vu, x, gt, None, 0x1d, lean=True, stats_out=(sf, si))
