@@ -113,6 +113,10 @@ EXPORTS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "vu_binned_calib": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Gt), C.POINTER(Calib), C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "vu_quantile_select_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int64, C.POINTER(Gt), C.POINTER(C.c_double),
+                                           C.c_int32, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vu_binned_calib_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(Gt), C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vu_synth_slab": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int64,
                                 C.c_float, C.c_void_p]),
     "vu_synth_gt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,

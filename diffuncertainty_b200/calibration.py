@@ -529,3 +529,177 @@ def eqace_from_maps(reference_segs, pred_seg, unc_map, a: float, b: float, ignor
     gs.has_ignore, gs.ignore_index = (0, 0) if ignore_value is None else (1, int(ignore_value))
     counts, sums = _binned(unc, pred, gs, platt_edges(a, b, edges[1:n_bins], hints=np.stack([u_lo[1:n_bins], u_hi[1:n_bins]])).as_struct())
     return _eqace_from_histogram(counts, sums, n_bins)
+
+
+# ---- eqACE of a whole batch of images (every uncertainty type at once) -------------------------------------------------------
+def _platt_edges_many(a32: np.ndarray, b32: np.ndarray, edges: np.ndarray, hints: np.ndarray, increasing: bool) -> np.ndarray:
+    """platt_edges for S rows at once (a32, b32: float32 (S,), all a of one sign and non-zero; edges: float64 (S, 19);
+    hints: float32 (H, S, 19)): the same bisection over float32 bit patterns, every row with its own (a, b) and edges."""
+    S = len(a32)
+    A, Bp = a32.reshape(S, 1).astype(np.float32), b32.reshape(S, 1).astype(np.float32)
+    key_min, key_max = _ord(np.array([-np.inf], np.float32))[0], _ord(np.array([np.inf], np.float32))[0]
+    lo = np.full((S, 19), key_min, np.uint64)
+    hi = np.full((S, 19), key_max, np.uint64)
+
+    def ok(keys):
+        with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+            conf = 1 / (1 + np.exp((-_unord(keys.reshape(-1)).reshape(S, 19)) * A + Bp))  # ace.py:329 in float32
+        return np.clip(conf, 0, 1).astype(np.float64) >= edges
+
+    reach = ok(hi) if increasing else ok(lo)
+    for h in np.asarray(hints, np.float32).reshape(-1, S, 19):
+        fin = ~np.isnan(h)
+        k = np.where(fin, _ord(np.where(fin, h, np.float32(0)).reshape(-1)).reshape(S, 19), key_min).astype(np.uint64)
+        good = ok(k) & fin
+        bad = ~good & fin
+        if increasing:
+            hi = np.where(good, np.minimum(hi, k), hi)
+            lo = np.where(bad, np.maximum(lo, np.minimum(k + 1, hi)), lo)
+        else:
+            lo = np.where(good, np.maximum(lo, k), lo)
+            hi = np.where(bad, np.minimum(hi, np.maximum(k - 1, lo)), hi)
+    for _ in range(34):
+        if np.all(lo >= hi):
+            break
+        if increasing:
+            mid = lo + (hi - lo) // 2
+            good = ok(mid)
+            hi = np.where(good, mid, hi)
+            lo = np.where(good, lo, np.minimum(mid + 1, hi))
+        else:
+            mid = lo + (hi - lo + 1) // 2
+            good = ok(mid)
+            lo = np.where(good, mid, lo)
+            hi = np.where(good, hi, np.maximum(mid - 1, lo))
+    thr = _unord((hi if increasing else lo).reshape(-1)).reshape(S, 19).astype(np.float64)
+    # monotone over the reachable edges of a row (unreachable ones become NaN afterwards and are skipped by the accumulate)
+    filler = -np.inf if increasing else np.inf
+    t = np.where(reach, thr, filler)
+    t = np.maximum.accumulate(t, axis=1) if increasing else np.minimum.accumulate(t, axis=1)
+    return np.where(reach, t, np.nan).astype(np.float32)
+
+
+_EQ_WS = {}
+
+
+def _eq_workspace(dev, n_seg: int):
+    key = (dev.type, dev.index)
+    ws = _EQ_WS.get(key)
+    if ws is None or ws[0].shape[0] < n_seg:
+        nbytes = C.sizeof(_lib.RadixState)
+        ws = (torch.empty((n_seg, 64, 2048), dtype=torch.int64, device=dev),
+              torch.zeros((n_seg, nbytes), dtype=torch.uint8, device=dev),
+              torch.zeros((n_seg, nbytes), dtype=torch.uint8).pin_memory(),
+              torch.zeros((n_seg, C.sizeof(_lib.Calib)), dtype=torch.uint8).pin_memory(),
+              torch.zeros((n_seg, C.sizeof(_lib.Calib)), dtype=torch.uint8, device=dev))
+        _EQ_WS[key] = ws
+    return ws
+
+
+def eqace_from_maps_batch(reference_segs, pred_seg, unc_maps, platt, ignore_value=None, n_bins: int = 20) -> np.ndarray:
+    """calc_eqace (ace.py:378-406) of every image of a batch and every uncertainty type in one go: what the image loop of
+    calibration_error (ace.py:484-515) computes per image and type, without its per-image launches and read-backs.
+        reference_segs (B, R, *S) uint8 / int64, pred_seg (B, *S) uint8, unc_maps: up to four (B, *S) float32 device tensors,
+        platt: one (a, b) per map.  Returns float64 (n_maps, B) -- identical to eqace_from_maps image by image.
+    One rank selection over all segments (vu_quantile_select_batch: 3 histogram passes + 3 descents), ONE read-back, the quantile
+    edges and their inversion through the Platt expression vectorised over the segments on the host, one binning pass
+    (vu_binned_calib_batch), one read-back."""
+    if n_bins != N_BINS:
+        raise NotImplementedError("the GPU path supports the reference's default of 20 bins")
+    _lib.require_device()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    maps = [m.to(dev).float().contiguous() for m in unc_maps]
+    n_maps = len(maps)
+    if not 1 <= n_maps <= 4 or len(platt) != n_maps:
+        raise ValueError("one (a, b) per map, at most four maps")
+    B = maps[0].shape[0]
+    V = maps[0][0].numel() if B else 0
+    if B == 0 or V == 0:
+        return np.full((n_maps, B), np.nan)
+    refs = reference_segs if isinstance(reference_segs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(reference_segs))
+    refs = refs.to(dev)
+    refs = refs.to(torch.uint8 if refs.dtype in (torch.uint8, torch.bool) else torch.int64).contiguous().reshape(B, refs.shape[1], -1)
+    pred = (pred_seg if isinstance(pred_seg, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pred_seg))).to(dev)
+    pred = pred.to(torch.uint8).contiguous().reshape(B, -1)
+    if refs.shape[2] != V or pred.shape[1] != V or any(m.numel() != B * V for m in maps):
+        raise ValueError("references, prediction and maps must cover the same voxels")
+    R = refs.shape[1]
+    n_seg = n_maps * B
+    hist, state, state_host, cal_host, cal_dev = _eq_workspace(dev, n_seg)
+    stream = _lib.current_stream_ptr()
+    gs = _lib.Gt()
+    gs.data, gs.dtype, gs.R = refs.data_ptr(), (_lib.GT_U8 if refs.dtype == torch.uint8 else _lib.GT_I64), R
+    gs.stride_b, gs.stride_r, gs.stride_v = R * V, V, 1
+    gs.has_ignore, gs.ignore_index = (0, 0) if ignore_value is None else (1, int(ignore_value))
+    ptrs = (C.c_void_p * n_maps)(*[m.data_ptr() for m in maps])
+    a32 = np.array([np.float32(a) for a, _ in platt], np.float32)
+    b32 = np.array([np.float32(b) for _, b in platt], np.float32)
+    inc_map = a32 >= 0  # a >= 0: conf rises with u (x = -u, ace.py:329); else the ranks are mirrored
+    rev_mask = int(sum((0 if inc_map[m] else 1) << m for m in range(n_maps)))
+    qs = np.ascontiguousarray(np.linspace(0.0, 1.0, n_bins + 1))
+    _lib.check(lib.vu_quantile_select_batch(ptrs, n_maps, B, V, C.byref(gs), qs.ctypes.data_as(C.POINTER(C.c_double)), n_bins + 1, 0,
+                                            rev_mask, hist.data_ptr(), state.data_ptr(), stream), "vu_quantile_select_batch")
+    state_host[:n_seg].copy_(state[:n_seg], non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    raw = state_host[:n_seg].numpy()
+    RS = _lib.RadixState
+    total = raw[:, RS.total.offset:RS.total.offset + 8].copy().view(np.int64).reshape(n_seg)
+    nk = 2 * (n_bins + 1)
+    keys = raw[:, RS.key.offset:RS.key.offset + 4 * nk].copy().view(np.uint32).reshape(n_seg, nk).astype(np.uint64)
+    bits = np.where(keys & 0x80000000, keys & 0x7FFFFFFF, (~keys) & 0xFFFFFFFF).astype(np.uint32)
+    stats = bits.view(np.float32).reshape(n_seg, nk)
+    u_lo, u_hi = stats[:, 0::2], stats[:, 1::2]                      # (n_seg, 21)
+    A = np.repeat(a32, B).reshape(n_seg, 1)
+    Bp = np.repeat(b32, B).reshape(n_seg, 1)
+    with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+        c_lo = np.clip(1 / (1 + np.exp((-u_lo) * A + Bp)), 0, 1).astype(np.float64)
+        c_hi = np.clip(1 / (1 + np.exp((-u_hi) * A + Bp)), 0, 1).astype(np.float64)
+    # np.quantile's float64 virtual index, per segment (ace.py:387-388)
+    tt = np.maximum(total, 1).reshape(n_seg, 1)
+    h = (tt - 1) * qs.reshape(1, -1)
+    lo_rank = np.minimum(np.floor(h).astype(np.int64), tt - 1)
+    g = h - lo_rank
+    diff = c_hi - c_lo
+    edges = np.where(g >= 0.5, c_hi - diff * (1 - g), c_lo + diff * g)
+    edges[:, 0] = 0.0
+    edges[:, -1] = 1.0 + 1e-8
+    edges = np.maximum.accumulate(edges, axis=1)
+    inner = edges[:, 1:n_bins]
+    thr = np.full((n_seg, 19), np.nan, np.float32)
+    mode = np.zeros(n_seg, np.int32)
+    seg_inc = np.repeat(inc_map, B)
+    seg_zero = np.repeat(a32 == 0, B)
+    hints = np.stack([u_lo[:, 1:n_bins], u_hi[:, 1:n_bins]])
+    for inc in (True, False):
+        rows = np.nonzero((seg_inc == inc) & ~seg_zero & (total > 0))[0]
+        if len(rows):
+            thr[rows] = _platt_edges_many(A[rows, 0], Bp[rows, 0], inner[rows], hints[:, rows], inc)
+            mode[rows] = 1 if inc else 0
+    for s in np.nonzero(seg_zero & (total > 0))[0]:  # the reference's fallback a = 0: a constant confidence
+        pe = platt_edges(float(A[s, 0]), float(Bp[s, 0]), inner[s])
+        thr[s], mode[s] = pe.edge_u, pe.mode
+    CS = _lib.Calib
+    cal = cal_host[:n_seg].numpy()
+    cal[:] = 0
+    cal[:, CS.a.offset:CS.a.offset + 4] = A.astype(np.float32).view(np.uint8).reshape(n_seg, 4)
+    cal[:, CS.b.offset:CS.b.offset + 4] = Bp.astype(np.float32).view(np.uint8).reshape(n_seg, 4)
+    cal[:, CS.edge_u.offset:CS.edge_u.offset + 76] = np.ascontiguousarray(thr).view(np.uint8).reshape(n_seg, 76)
+    cal[:, CS.mode.offset:CS.mode.offset + 4] = np.ascontiguousarray(mode).view(np.uint8).reshape(n_seg, 4)
+    cal_dev[:n_seg].copy_(cal_host[:n_seg], non_blocking=True)
+    counts = torch.zeros((n_seg, 2, 21), dtype=torch.int64, device=dev)
+    sums = torch.zeros((n_seg, 21), dtype=torch.float64, device=dev)
+    _lib.check(lib.vu_binned_calib_batch(ptrs, n_maps, B, V, pred.data_ptr(), C.byref(gs), cal_dev.data_ptr(), None, counts.data_ptr(),
+                                         sums.data_ptr(), stream), "vu_binned_calib_batch")
+    cn, sm = counts.cpu().numpy(), sums.cpu().numpy()
+    # ace.py:392-406 for every segment
+    tot = cn[:, 0, :n_bins].astype(np.float64)
+    tru = cn[:, 1, :n_bins].astype(np.float64)
+    s = sm[:, :n_bins].copy()
+    tot[:, n_bins - 1] += cn[:, 0, n_bins:].sum(1); tru[:, n_bins - 1] += cn[:, 1, n_bins:].sum(1); s[:, n_bins - 1] += sm[:, n_bins:].sum(1)
+    out = np.full(n_seg, np.nan)
+    for i in range(n_seg):  # the reference sums the non-empty bins in bin order (np.sum over the compressed array)
+        nz = tot[i] > 0
+        if nz.any():
+            out[i] = (1.0 / int(nz.sum())) * np.sum(np.abs(tru[i, nz] / tot[i, nz] - s[i, nz] / tot[i, nz]))
+    return out.reshape(n_maps, B)

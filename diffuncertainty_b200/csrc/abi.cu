@@ -396,6 +396,51 @@ int vu_binned_calib(const float* map, const uint8_t* labels, int64_t V, const vu
                                (cudaStream_t)stream);
 }
 
+static int check_seg_batch(const float* const* maps_host, int32_t n_maps, int64_t B, int64_t V) {
+    if (!maps_host || n_maps < 1 || n_maps > 4) return set_error(VU_ERR_BAD_ARG, "1..4 maps per batch");
+    if (B < 1 || V < 1 || B * n_maps > 65535) return set_error(VU_ERR_BAD_ARG, "B, V must be positive, n_maps * B <= 65535");
+    for (int m = 0; m < n_maps; ++m)
+        if (!maps_host[m]) return set_error(VU_ERR_BAD_ARG, "NULL map");
+    return VU_OK;
+}
+
+int vu_quantile_select_batch(const float* const* maps_host, int32_t n_maps, int64_t B, int64_t V, const vu_gt* weights_gt,
+                             const double* q_host, int32_t n_q, int32_t q_is_f32, uint32_t reverse_mask, uint64_t* hist,
+                             vu_radix_state* states, void* stream) {
+    int rc = check_seg_batch(maps_host, n_maps, B, V);
+    if (rc != VU_OK) return rc;
+    if (!hist || !states) return set_error(VU_ERR_BAD_ARG, "NULL pointer");
+    if (n_q < 0 || n_q > 31 || (n_q > 0 && !q_host)) return set_error(VU_ERR_BAD_ARG, "0..31 quantile fractions");
+    for (int i = 0; i < n_q; ++i)
+        if (!(q_host[i] >= 0.0 && q_host[i] <= 1.0)) return set_error(VU_ERR_BAD_ARG, "Quantiles must be in the range [0, 1]");
+    GtView gv;
+    rc = make_gt_view(gv, weights_gt, V);
+    if (rc != VU_OK) return rc;
+    const int n_seg = (int)(n_maps * B);
+    for (int level = 0; level < 3; ++level) {
+        if (cudaMemsetAsync(hist, 0, (size_t)n_seg * VU_RADIX_MAX_RANKS * 2048 * sizeof(uint64_t), (cudaStream_t)stream) != cudaSuccess)
+            return set_cuda_error("cudaMemsetAsync(hist)");
+        rc = launch_radix_hist_batch(maps_host, n_maps, B, V, gv, level, reinterpret_cast<unsigned long long*>(hist), (cudaStream_t)stream, states);
+        if (rc != VU_OK) return rc;
+        rc = launch_radix_walk(reinterpret_cast<const unsigned long long*>(hist), level, q_host, n_q, q_is_f32, (int)reverse_mask, states,
+                               (cudaStream_t)stream, n_seg, (int)B);
+        if (rc != VU_OK) return rc;
+    }
+    return VU_OK;
+}
+
+int vu_binned_calib_batch(const float* const* maps_host, int32_t n_maps, int64_t B, int64_t V, const uint8_t* labels, const vu_gt* gt,
+                          const vu_calib* calibs, const uint8_t* label_lut, int64_t* out_counts, double* out_sums, void* stream) {
+    int rc = check_seg_batch(maps_host, n_maps, B, V);
+    if (rc != VU_OK) return rc;
+    if (!gt || !gt->data || !calibs || !out_counts || !out_sums) return set_error(VU_ERR_BAD_ARG, "NULL pointer");
+    GtView gv;
+    rc = make_gt_view(gv, gt, V);
+    if (rc != VU_OK) return rc;
+    return launch_binned_calib_batch(maps_host, n_maps, B, V, labels, gv, calibs, label_lut, reinterpret_cast<unsigned long long*>(out_counts),
+                                     out_sums, (cudaStream_t)stream);
+}
+
 int64_t vu_ged_cols(int32_t P, int32_t R) {
     if (P < 1 || R < 1) return 0;
     return 2LL * P * R + R + (int64_t)P * P + P + 2LL * R * R + 3;

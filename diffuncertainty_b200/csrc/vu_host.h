@@ -34,8 +34,13 @@ int launch_border(const uint8_t* labels, long long B, long long d0, long long d1
                   cudaStream_t stream);
 int launch_radix_hist(const float* values, long long n, const GtView& gt, int level, const unsigned* prefixes, int n_prefix,
                       unsigned long long* hist, cudaStream_t stream, const vu_radix_state* state = nullptr);
+// n_seg > 0: batched (one CTA per segment, `reverse` is a bit mask over the maps, seg_B images per map)
 int launch_radix_walk(const unsigned long long* hist, int level, const double* q_host, int n_q, int q_is_f32, int reverse,
-                      vu_radix_state* state, cudaStream_t stream);
+                      vu_radix_state* state, cudaStream_t stream, int n_seg = 0, int seg_B = 0);
+int launch_radix_hist_batch(const float* const* maps, int n_maps, long long B, long long V, const GtView& gt, int level,
+                            unsigned long long* hist, cudaStream_t stream, const vu_radix_state* states);
+int launch_binned_calib_batch(const float* const* maps, int n_maps, long long B, long long V, const uint8_t* labels, const GtView& gt,
+                              const vu_calib* cals_dev, const uint8_t* lut, unsigned long long* counts, double* sums, cudaStream_t stream);
 int launch_binned_calib(const float* map, const uint8_t* labels, long long V, const GtView& gt, const CalibDev& cal, const uint8_t* lut,
                         unsigned long long* counts, double* sums, cudaStream_t stream);
 int launch_member_scores(const vu_member_scores_args* a, const GtView& gt, cudaStream_t stream);

@@ -381,6 +381,21 @@ VU_API int vu_quantile_select(const float* values, int64_t n, const vu_gt* weigh
 VU_API int vu_binned_calib(const float* map, const uint8_t* labels, int64_t V, const vu_gt* gt, const vu_calib* calib,
                            const uint8_t* label_lut, int64_t* out_counts, double* out_sums, void* stream);
 
+/* Batched forms for per-image eqACE (ace.py:378-406 inside the image loop of calibration_error, ace.py:484-515): segment
+ * s = m * B + b is image b of map m (n_maps <= 4 uncertainty types, each a contiguous (B, V) device array whose pointer is
+ * given in the HOST array maps_host).  Every segment has its own selection / histogram; the references of image b are
+ * gt + b * stride_b.  One call enqueues the work of all segments: 3 x (memset, histogram pass, descent) resp. one binning pass.
+ *   vu_quantile_select_batch: hist (n_maps * B, 64, 2048) uint64 workspace, states (n_maps * B); reverse_mask bit m: map m
+ *                             selects the mirrored ranks (a confidence that falls with the uncertainty).
+ *   vu_binned_calib_batch:    calibs = DEVICE array of n_maps * B vu_calib (edge_u per segment); out_counts (n_maps * B, 2, 21),
+ *                             out_sums (n_maps * B, 21), accumulated.                                                        */
+VU_API int vu_quantile_select_batch(const float* const* maps_host, int32_t n_maps, int64_t B, int64_t V, const vu_gt* weights_gt,
+                                    const double* q_host, int32_t n_q, int32_t q_is_f32, uint32_t reverse_mask, uint64_t* hist,
+                                    vu_radix_state* states, void* stream);
+VU_API int vu_binned_calib_batch(const float* const* maps_host, int32_t n_maps, int64_t B, int64_t V, const uint8_t* labels,
+                                 const vu_gt* gt, const vu_calib* calibs, const uint8_t* label_lut, int64_t* out_counts,
+                                 double* out_sums, void* stream);
+
 /* Host helper: pull the 19 interior edges of np.linspace(0, 1+1e-8, 21) back
  * through the reference's float32 Platt expression (ace.py:329) by bisection
  * over float32 bit patterns.  Fills calib->edge_u / increasing from a, b.    */

@@ -140,3 +140,33 @@ def test_eqace_matches_golden(g):
         want = oracle.calc_eqace(correct, conf)
         np.testing.assert_allclose(calibration.eqace_from_maps(refs, pred, unc, a, b, 255), want, rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(calibration.calc_eqace(correct, conf), want, rtol=1e-5, atol=1e-9)
+
+
+def test_eqace_batch_equals_per_image_and_oracle():
+    """eqace_from_maps_batch (one selection / binning launch sequence for B images x 3 types) against eqace_from_maps image by
+    image (identical) and against the oracle's calc_eqace (ace.py:378-406) on the per-(rater, pixel) arrays."""
+    import torch
+    from diffuncertainty_b200 import calibration
+    from oracle import oracle
+    rng = np.random.default_rng(21)
+    B, H, W, R = 5, 96, 160, 3
+    pred = rng.integers(0, 4, (B, H, W)).astype(np.uint8)
+    refs = np.stack([np.where(rng.random((B, H, W)) < 0.8, pred, rng.integers(0, 4, (B, H, W))) for _ in range(R)], axis=1).astype(np.uint8)
+    refs[rng.random(refs.shape) < 0.03] = 255
+    refs[3] = 255  # an image without a single valid sample
+    maps = [(rng.random((B, H, W)) ** (k + 1) * 1.3).astype(np.float32) for k in range(3)]
+    maps[1][rng.random((B, H, W)) < 0.5] = 0.0  # heavy ties
+    maps[2][1, :4] = np.nan
+    platt = [(-3.0, 1.0), (2.5, -1.5), (0.0, 0.3)]
+    got = calibration.eqace_from_maps_batch(torch.from_numpy(refs).cuda(), torch.from_numpy(pred).cuda(),
+                                            [torch.from_numpy(m).cuda() for m in maps], platt, 255)
+    assert got.shape == (3, B)
+    for m, (a, b) in enumerate(platt):
+        for i in range(B):
+            one = calibration.eqace_from_maps(refs[i], pred[i], maps[m][i], a, b, 255)
+            assert (np.isnan(one) and np.isnan(got[m, i])) or one == got[m, i], (m, i, one, got[m, i])
+            if i == 3 or (m == 2 and i == 1):
+                continue
+            correct, conf = oracle.calibration_inputs(refs[i], pred[i], maps[m][i], a, b, 255)
+            np.testing.assert_allclose(got[m, i], oracle.calc_eqace(correct, conf), rtol=1e-5, atol=1e-6)
+    assert np.isnan(got[:, 3]).all()

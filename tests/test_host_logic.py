@@ -126,3 +126,23 @@ def test_platt_edges_zero_slope_and_hints():
         far = np.stack([np.sort(rng.random(19)).astype(np.float32), np.full(19, np.nan, np.float32)])
         for hints in (near, far):
             assert np.array_equal(c.platt_edges(a, b, e, hints=hints).edge_u, want, equal_nan=True)
+
+
+def test_platt_edges_many_equals_platt_edges():
+    """the row-vectorised inversion used by eqace_from_maps_batch is the scalar platt_edges, row by row"""
+    from diffuncertainty_b200 import calibration
+    rng = np.random.default_rng(5)
+    for inc in (True, False):
+        S = 7
+        a = (rng.random(S) * 6 + 0.2) * (1 if inc else -1)
+        b = rng.normal(size=S) * 2
+        edges = np.sort(rng.random((S, 19)), axis=1)
+        edges[0, 5:9] = edges[0, 5]  # tied quantile edges
+        edges[1, 15:] = 1.0          # unreachable from below 1
+        hints = (rng.random((2, S, 19)) * 3).astype(np.float32)
+        hints[0, 2, 3] = np.nan
+        thr = calibration._platt_edges_many(a.astype(np.float32), b.astype(np.float32), edges, hints, inc)
+        for s in range(S):
+            one = calibration.platt_edges(float(np.float32(a[s])), float(np.float32(b[s])), edges[s], hints=hints[:, s])
+            np.testing.assert_array_equal(thr[s], one.edge_u)
+            assert one.mode == (1 if inc else 0)
