@@ -450,7 +450,7 @@ def run_ours(args):
         from bench_configs import time_config
         configs = []
         for cid in (1, 2, 3, 4, 5):
-            c = time_config(cid, iters=10, peak=peak)
+            c = time_config(cid, iters=10, peak=peak, logits=True)
             configs.append(c)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -43,7 +43,7 @@ NAMES = {1: "cfg1 toy 2-D TTA: N=10, C=2, 256x256, B=256; maps + labels + image-
          5: "cfg5 sharded sweep: N=16, C=19, 512x1024, R=1 with 2% ignore(255), B=16; maps + labels + image / threshold / area / Dice / ECE-ACE histograms"}
 
 
-def time_config(cid: int, iters: int = 10, peak: float = 6532.2) -> dict:
+def time_config(cid: int, iters: int = 10, peak: float = 6532.2, logits: bool = False) -> dict:
     """The named pipeline of BASELINE config `cid` on resident synthetic inputs, stage by stage with CUDA events."""
     platt = [calibration.platt_edges(a, b) for a, b in ((3.5, -1.25), (6.0, -2.0), (40.0, -0.5))]
     cfg = CONFIGS[cid]
@@ -89,6 +89,16 @@ def time_config(cid: int, iters: int = 10, peak: float = 6532.2) -> dict:
             aggregation.patch_level_batched(maps3.reshape(3 * B, *dims), cfg["patch"])
 
         stages["vu_patch_max_ws (TU, AU, EU in one call)"] = time_call(patch, iters=iters)
+    if logits:
+        # the same launch over a slab of LOGITS (vu_fused_pass_logits: softmax folded into the read); log p are logits whose
+        # softmax is p again, taken in place so that no second slab is resident
+        x.clamp_(min=1e-30).log_()
+
+        def fused_logits():
+            vu.fused_pass(x, gt, stats=flags, thresholds=[0.3, 0.2, 0.02], calib=platt if flags & S.STAT_CALIB else None,
+                          stats_out=(sf, si), maps_out=maps, labels_out=labels, logits=True)
+
+        stages["(vu_fused_pass_logits, same launch over logits)"] = time_call(fused_logits, iters=iters)
     total = sum(v for k, v in stages.items() if not k.startswith("("))
     first = next(iter(stages.values()))
     fused_ms_only = stages.get("(vu_fused_pass alone)", stages.get("vu_fused_pass", first))
@@ -98,6 +108,10 @@ def time_config(cid: int, iters: int = 10, peak: float = 6532.2) -> dict:
             "fused_pass_ms": round(fused_ms_only, 4), "fused_pass_GBps": round(bytes_alg / fused_ms_only / 1e6, 1),
             "fused_pass_frac": round(bytes_alg / fused_ms_only / 1e6 / peak, 3),
             "sample_voxels_per_s": round(P * V * B / total * 1e3, 1), "peak_GBps": peak}
+    lg = stages.get("(vu_fused_pass_logits, same launch over logits)")
+    if lg:
+        line["logits_pass_ms"] = round(lg, 4)
+        line["logits_pass_frac"] = round(bytes_alg / lg / 1e6 / peak, 3)
     del x, gt, maps, maps3, labels
     torch.cuda.empty_cache()
     return line
@@ -107,13 +121,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,2,3,4,5")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--logits", action="store_true", help="also time vu_fused_pass_logits on every config")
     args = ap.parse_args()
     peak = 6532.2
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.isfile(pk):
         peak = float(json.load(open(pk))["hbm_gbs"])
     for cid in [int(c) for c in args.configs.split(",")]:
-        print(json.dumps(time_config(cid, args.iters, peak)), flush=True)
+        print(json.dumps(time_config(cid, args.iters, peak, args.logits)), flush=True)
 
 
 if __name__ == "__main__":

@@ -7,8 +7,8 @@ Python call surface of JakobLC/DiffUncertainty's
 ``evaluation/metrics`` (ECE/ACE, NCC, AURC inputs).  There is no CPU fallback.
 """
 from . import _lib  # noqa: F401
-from .uncertainty import (FusedResult, GroundTruth, Groups, calculate_one_minus_msr, calculate_uncertainty, fused_pass,  # noqa: F401
-                          group_members, map_stats, mean_argmax_labels)
+from .uncertainty import (FusedResult, GroundTruth, Groups, calculate_one_minus_msr, calculate_uncertainty,  # noqa: F401
+                          calculate_uncertainty_from_logits, fused_pass, group_members, map_stats, mean_argmax_labels)
 
 from .members import MemberScoreBuffers, fused_pass_with_member_scores  # noqa: F401,E402
 

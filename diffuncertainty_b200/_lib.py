@@ -20,7 +20,7 @@ GT_U8, GT_I64 = 0, 1
 STAT_IMAGE_SUM, STAT_THRESHOLD, STAT_AREA, STAT_DICE, STAT_CALIB, STAT_NCC, STAT_PLATT_FIT = 1, 2, 4, 8, 16, 32, 64
 STAT_CLASS_COUNTS = 128
 N_PLATT_BINS = 256
-SLAB_RENORMALIZE, SLAB_DISCRETIZE = 1, 2
+SLAB_RENORMALIZE, SLAB_DISCRETIZE, SLAB_LOGITS = 1, 2, 4
 STAT_ALL_NO_GT = STAT_IMAGE_SUM | STAT_THRESHOLD | STAT_AREA
 
 # column layout of the per-image rows (keep in sync with valunc.h; checked in tests/test_abi.py)
@@ -94,6 +94,7 @@ EXPORTS = {
     "vu_device_check": (C.c_int, []),
     "vu_struct_size": (C.c_int, [C.c_int]),
     "vu_fused_pass": (C.c_int, [C.POINTER(FusedArgs), C.c_void_p]),
+    "vu_fused_pass_logits": (C.c_int, [C.POINTER(FusedArgs), C.c_void_p]),
     "vu_fused_members_supported": (C.c_int, [C.POINTER(FusedArgs)]),
     "vu_map_stats": (C.c_int, [C.POINTER(MapStatsArgs), C.c_void_p]),
     "vu_patch_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),

@@ -177,14 +177,31 @@ int vu_struct_size(int which) {
     }
 }
 
+static int fused_pass_checked(const vu_fused_args* a, void* stream);
+
 int vu_fused_pass(const vu_fused_args* a, void* stream) {
     if (!a) return set_error(VU_ERR_BAD_ARG, "args is NULL");
     if (a->struct_size != sizeof(vu_fused_args)) return set_error(VU_ERR_BAD_ARG, "vu_fused_args.struct_size mismatch");
+    if (a->slab.flags & VU_SLAB_LOGITS)
+        return set_error(VU_ERR_BAD_ARG, "slab.flags: logits are opt-in (relaxed label contract) -- call vu_fused_pass_logits");
+    return fused_pass_checked(a, stream);
+}
+
+int vu_fused_pass_logits(const vu_fused_args* a, void* stream) {
+    if (!a) return set_error(VU_ERR_BAD_ARG, "args is NULL");
+    if (a->struct_size != sizeof(vu_fused_args)) return set_error(VU_ERR_BAD_ARG, "vu_fused_args.struct_size mismatch");
+    if (a->members.flags) return set_error(VU_ERR_UNSUPPORTED, "member scores are not available for slabs of logits");
+    vu_fused_args b = *a;
+    b.slab.flags |= VU_SLAB_LOGITS;
+    return fused_pass_checked(&b, stream);
+}
+
+static int fused_pass_checked(const vu_fused_args* a, void* stream) {
     const vu_slab& s = a->slab;
     if (s.P < 1 || s.B < 0 || s.C < 1 || s.V < 0) return set_error(VU_ERR_BAD_ARG, "slab sizes must be positive");
     if (s.C > 256) return set_error(VU_ERR_UNSUPPORTED, "C > 256 (labels are uint8)");
     if (s.B == 0 || s.V == 0) return VU_OK;  // empty batch: nothing to do (its data pointer may be NULL)
-    if (s.draws < 0 || s.draws > 4096 || (s.flags & ~(VU_SLAB_RENORMALIZE | VU_SLAB_DISCRETIZE)))
+    if (s.draws < 0 || s.draws > 4096 || (s.flags & ~(VU_SLAB_RENORMALIZE | VU_SLAB_DISCRETIZE | VU_SLAB_LOGITS)))
         return set_error(VU_ERR_BAD_ARG, "slab.draws / slab.flags");
     if ((s.draws > 1 || s.flags) && a->members.flags)
         return set_error(VU_ERR_UNSUPPORTED, "member scores in the fused pass are not available for grouped / renormalised / discretised slabs");

@@ -184,6 +184,154 @@ struct VoxelAcc {
         cascade_step(p);
     }
 
+    // ---- a member that arrives as LOGITS (VU_SLAB_LOGITS): softmax over its classes in place (xp / xs become the
+    // probabilities), hm / hs receive the member's entropy term sum_c p log2 p of every voxel (see vu_common.cuh for the
+    // arithmetic and the special-value rules).  `reload(i)` returns the ORIGINAL pair i (reload_s(): the leftover value) --
+    // only used on the rare path of a voxel with -inf logits, whose 0 * -inf products have to be taken out of the e z sum.
+    template <class Reload, class ReloadS>
+    __device__ __forceinline__ void softmax_member(f32x2 (&xp)[NP], float& xs, f32x2 (&hm)[NH], float& hs, Reload reload, ReloadS reload_s) {
+        const f32x2 L2E = pk2(kLog2e, kLog2e);
+        if constexpr (VEC >= 2) {
+            float mx[VEC];
+#pragma unroll
+            for (int q = 0; q < NH; ++q) upk2(xp[q], mx[2 * q], mx[2 * q + 1]);
+#pragma unroll
+            for (int c = 1; c + 1 < C; c += 2) {
+#pragma unroll
+                for (int q = 0; q < NH; ++q) {
+                    float a0, a1, b0, b1;
+                    upk2(xp[c * NH + q], a0, a1);
+                    upk2(xp[(c + 1) * NH + q], b0, b1);
+                    mx[2 * q] = max_nan3(mx[2 * q], a0, b0);
+                    mx[2 * q + 1] = max_nan3(mx[2 * q + 1], a1, b1);
+                }
+            }
+            if constexpr ((C & 1) == 0) {
+#pragma unroll
+                for (int q = 0; q < NH; ++q) {
+                    float a0, a1;
+                    upk2(xp[(C - 1) * NH + q], a0, a1);
+                    mx[2 * q] = max_nan(mx[2 * q], a0);
+                    mx[2 * q + 1] = max_nan(mx[2 * q + 1], a1);
+                }
+            }
+            f32x2 NM[NH], S[NH], EZ[NH];
+#pragma unroll
+            for (int q = 0; q < NH; ++q) { NM[q] = pk2(-mx[2 * q], -mx[2 * q + 1]); S[q] = 0ull; EZ[q] = 0ull; }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+                for (int q = 0; q < NH; ++q) {
+                    const f32x2 Z = mul2(add2(xp[c * NH + q], NM[q]), L2E);
+                    float z0, z1;
+                    upk2(Z, z0, z1);
+                    const f32x2 E = pk2(ex2_approx(z0), ex2_approx(z1));
+                    S[q] = add2(S[q], E);
+                    EZ[q] = fma2(E, Z, EZ[q]);
+                    xp[c * NH + q] = E;
+                }
+            }
+            float ez[VEC];
+            bool redo = false;
+#pragma unroll
+            for (int q = 0; q < NH; ++q) {
+                upk2(EZ[q], ez[2 * q], ez[2 * q + 1]);
+                redo |= (ez[2 * q] != ez[2 * q]) | (ez[2 * q + 1] != ez[2 * q + 1]);
+            }
+            if (redo) {  // a 0 * -inf product (or a NaN draw, for which this changes nothing): the e z sums term by term
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) ez[k] = 0.f;
+#pragma unroll  // (a rolled loop would index xp dynamically and put it into local memory)
+                for (int c = 0; c < C; ++c) {
+#pragma unroll
+                    for (int q = 0; q < NH; ++q) {
+                        const f32x2 Z = mul2(add2(reload(c * NH + q), NM[q]), L2E);
+                        float z0, z1, e0, e1;
+                        upk2(Z, z0, z1);
+                        upk2(xp[c * NH + q], e0, e1);
+                        ez[2 * q] = (e0 == 0.0f) ? ez[2 * q] : __fmaf_rn(e0, z0, ez[2 * q]);
+                        ez[2 * q + 1] = (e1 == 0.0f) ? ez[2 * q + 1] : __fmaf_rn(e1, z1, ez[2 * q + 1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NH; ++q) {
+                f32x2 RS;
+                softmax_finish2(S[q], pk2(ez[2 * q], ez[2 * q + 1]), RS, hm[q]);
+#pragma unroll
+                for (int c = 0; c < C; ++c) xp[c * NH + q] = mul2(xp[c * NH + q], RS);
+            }
+        } else {
+            float m;
+            {
+                float a0, a1;
+                upk2(xp[0], a0, a1);
+                m = max_nan(a0, a1);
+#pragma unroll
+                for (int j = 1; j < NP; ++j) {
+                    upk2(xp[j], a0, a1);
+                    m = max_nan3(m, a0, a1);
+                }
+                if constexpr (ODD) m = max_nan(m, xs);
+            }
+            const f32x2 NM = pk2(-m, -m);
+            float S = 0.f, EZ = 0.f;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {  // packed subtraction / scaling, the sums in class order
+                const f32x2 Z = mul2(add2(xp[j], NM), L2E);
+                float z0, z1;
+                upk2(Z, z0, z1);
+                const float e0 = ex2_approx(z0), e1 = ex2_approx(z1);
+                S = __fadd_rn(S, e0);
+                S = __fadd_rn(S, e1);
+                EZ = __fmaf_rn(e0, z0, EZ);
+                EZ = __fmaf_rn(e1, z1, EZ);
+                xp[j] = pk2(e0, e1);
+            }
+            if constexpr (ODD) {
+                const float z = softmax_z(xs, m);
+                const float e = ex2_approx(z);
+                S = __fadd_rn(S, e);
+                EZ = __fmaf_rn(e, z, EZ);
+                xs = e;
+            }
+            if (EZ != EZ) {
+                EZ = 0.f;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    const f32x2 Z = mul2(add2(reload(j), NM), L2E);
+                    float z0, z1, e0, e1;
+                    upk2(Z, z0, z1);
+                    upk2(xp[j], e0, e1);
+                    EZ = (e0 == 0.0f) ? EZ : __fmaf_rn(e0, z0, EZ);
+                    EZ = (e1 == 0.0f) ? EZ : __fmaf_rn(e1, z1, EZ);
+                }
+                if constexpr (ODD) EZ = (xs == 0.0f) ? EZ : __fmaf_rn(xs, softmax_z(reload_s(), m), EZ);
+            }
+            float rS;
+            softmax_finish(S, EZ, rS, hs);
+            const f32x2 RS = pk2(rS, rS);
+#pragma unroll
+            for (int j = 0; j < NP; ++j) xp[j] = mul2(xp[j], RS);
+            if constexpr (ODD) xs = __fmul_rn(xs, rS);
+        }
+    }
+    // add a member whose probabilities and entropy term come from softmax_member; same accumulation order as add_member
+    __device__ __forceinline__ void add_member_pre(const f32x2 (&xp)[NP], float xs, const f32x2 (&hm)[NH], float hs, long long p,
+                                                   bool want_member_label = false) {
+        if (want_member_label) member_argmax<0, C>(xp, xs);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) m0[j] = add2(m0[j], xp[j]);
+        if constexpr (VEC >= 2) {
+#pragma unroll
+            for (int q = 0; q < NH; ++q) a0[q] = add2(a0[q], hm[q]);
+        } else {
+            if constexpr (ODD) m0s = __fadd_rn(m0s, xs);
+            a0s = __fadd_rn(a0s, hs);
+        }
+        cascade_step(p);
+    }
+
     static constexpr float kExactLo = 2.524354896707238e-29f;  // 2^-95
     static constexpr unsigned kExactLoBits = 0x10000000u;
     // mean (true division, test_2D.py:971), label, TU, AU, EU of the VEC voxels

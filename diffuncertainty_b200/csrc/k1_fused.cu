@@ -23,7 +23,7 @@ struct K1Params {
     long long sp, sb, sc, sv;
     long long sd;        // stride between the draws of a member (data form)
     int draws;           // draws per member (>= 1)
-    unsigned sflags;     // VU_SLAB_RENORMALIZE | VU_SLAB_DISCRETIZE
+    unsigned sflags;     // VU_SLAB_RENORMALIZE | VU_SLAB_DISCRETIZE | VU_SLAB_LOGITS
     float renorm_eps;
     float* tu;
     float* au;
@@ -172,6 +172,7 @@ __host__ __device__ inline size_t generic_smem_bytes(long long P, int threads, b
     if (member_labels) n += (size_t)P * threads * (sizeof(float) + 1);
     n = (n + 3) / 4 * 4;
     if (sflags & VU_SLAB_RENORMALIZE) n += (size_t)P * draws * threads * sizeof(float);
+    if (sflags & VU_SLAB_LOGITS) n += 2 * (size_t)P * draws * threads * sizeof(float);
     if (sflags & VU_SLAB_DISCRETIZE) n += (size_t)P * draws * threads;
     return (n + 15) / 16 * 16;
 }
@@ -205,10 +206,14 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
     float* bv_smem = h_smem + (prm.P > 1 ? (size_t)prm.P * THREADS : 0);
     uint8_t* bi_smem = reinterpret_cast<uint8_t*>(bv_smem + (want_ml ? (size_t)prm.P * THREADS : 0));
     const int D = prm.draws;
-    const bool renorm = prm.sflags & VU_SLAB_RENORMALIZE, onehot = prm.sflags & VU_SLAB_DISCRETIZE;
+    const bool renorm = prm.sflags & VU_SLAB_RENORMALIZE, onehot = prm.sflags & VU_SLAB_DISCRETIZE, logits = prm.sflags & VU_SLAB_LOGITS;
+    // logits with nothing else folded in: a member's entropy term comes straight from its softmax (the TMA form does the same)
+    const bool plain_logits = logits && !renorm && !onehot && D == 1;
     const size_t pre_bytes = ((prm.P > 1 ? (size_t)prm.P * THREADS * 4 : 0) + (want_ml ? (size_t)prm.P * THREADS * 5 : 0) + 3) / 4 * 4;
     float* norm_smem = reinterpret_cast<float*>(vu_dyn_smem + pre_bytes);  // class sum of every draw (renormalisation)
-    uint8_t* amax_smem = reinterpret_cast<uint8_t*>(norm_smem + (renorm ? (size_t)prm.P * D * THREADS : 0));  // argmax of every draw
+    float* lmax_smem = norm_smem + (renorm ? (size_t)prm.P * D * THREADS : 0);  // logits: maximum and 1 / sum of every draw's softmax
+    float* lrs_smem = lmax_smem + (logits ? (size_t)prm.P * D * THREADS : 0);
+    uint8_t* amax_smem = reinterpret_cast<uint8_t*>(lrs_smem + (logits ? (size_t)prm.P * D * THREADS : 0));  // argmax of every draw
     void* st_smem = vu_dyn_smem + generic_smem_bytes(prm.P, THREADS, want_ml, D, prm.sflags);
     const bool do_stats = prm.st.flags != 0;
     StatsCursor<THREADS> cursor;
@@ -228,7 +233,11 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
         return prm.mptr ? ld_member_ptr(prm.mptr, p * D + d) : prm.x + p * prm.sp + (long long)d * prm.sd;
     };
     // what the reference's producers make of the raw value x of class c of draw pd at this thread's voxel
+    auto softmaxed = [&](float x, long long pd) {  // F.softmax(logits, dim=1), test_2D.py:1181-1256
+        return __fmul_rn(ex2_approx(softmax_z(x, lmax_smem[pd * THREADS + threadIdx.x])), lrs_smem[pd * THREADS + threadIdx.x]);
+    };
     auto produced = [&](float x, long long pd, int c) {
+        if (logits) x = softmaxed(x, pd);
         if (renorm) {
             const float nrm = norm_smem[pd * THREADS + threadIdx.x];
             x = (nrm > prm.renorm_eps) ? __fdiv_rn(x, fmaxf(nrm, prm.renorm_eps)) : x;  // test_2D.py:190-194
@@ -253,15 +262,29 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
             const long long off0 = (long long)b * prm.sb + v * prm.sv;
             if (P > 1)
                 for (long long p = 0; p < P; ++p) h[p * THREADS] = 0.f;
-            if (renorm | onehot) {
-                // first pass over the draws: the class sum (torch.sum(dim=1): cascade order) and the argmax of the
-                // (renormalised) draw
+            if (renorm | onehot | logits) {
+                // first pass over the draws: the softmax constants of a draw of logits, the class sum (torch.sum(dim=1):
+                // cascade order) and the argmax of the (renormalised) draw
                 for (long long pd = 0; pd < P * D; ++pd) {
                     const float* base = draw_base(pd / D, (int)(pd % D)) + off0;
+                    if (logits) {
+                        float m = ldg_stream(base);
+                        for (int c = 1; c < C; ++c) m = max_nan(m, ldg_stream(base + (long long)c * prm.sc));
+                        float S = 0.f, EZ = 0.f, e, rS, hh;
+                        for (int c = 0; c < C; ++c) softmax_term(ldg_stream(base + (long long)c * prm.sc), m, S, EZ, e);
+                        softmax_finish(S, EZ, rS, hh);
+                        lmax_smem[pd * THREADS + threadIdx.x] = m;
+                        lrs_smem[pd * THREADS + threadIdx.x] = rS;
+                        if (plain_logits && P > 1) h[pd * THREADS] = hh;
+                    }
                     if (renorm) {
                         Cascade cs;
                         cs.reset();
-                        for (int c = 0; c < C; ++c) cs.add(ldg_stream(base + (long long)c * prm.sc), c, nfC, kC);
+                        for (int c = 0; c < C; ++c) {
+                            float x = ldg_stream(base + (long long)c * prm.sc);
+                            if (logits) x = softmaxed(x, pd);
+                            cs.add(x, c, nfC, kC);
+                        }
                         norm_smem[pd * THREADS + threadIdx.x] = cs.total();
                     }
                     if (onehot) {
@@ -270,6 +293,7 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
                         int bi = 0;
                         for (int c = 0; c < C; ++c) {
                             float x = ldg_stream(base + (long long)c * prm.sc);
+                            if (logits) x = softmaxed(x, pd);
                             if (renorm) x = (nrm > prm.renorm_eps) ? __fdiv_rn(x, fmaxf(nrm, prm.renorm_eps)) : x;
                             if (c == 0) { bv = x; bi = 0; } else argmax_step(x, c, bv, bi);
                         }
@@ -284,7 +308,7 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
                 const long long offc = off0 + (long long)c * prm.sc;
                 for (long long p = 0; p < P; ++p) {
                     float x;
-                    if (D == 1 && !(renorm | onehot)) {
+                    if (D == 1 && !(renorm | onehot | logits)) {
                         x = ldg_stream((prm.mptr ? ld_member_ptr(prm.mptr, p) : prm.x + p * prm.sp) + offc);
                     } else {
                         // the member is the mean of its draws (test_2D.py:1277): cascade sum, true division
@@ -297,7 +321,7 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
                         x = D > 1 ? __fdiv_rn(cd.total(), Df) : cd.total();
                     }
                     cas.add(x, p, n_full, level_k);
-                    if (P > 1) h[p * THREADS] = plog2p_acc(h[p * THREADS], x);
+                    if (P > 1 && !plain_logits) h[p * THREADS] = plog2p_acc(h[p * THREADS], x);
                     if (want_ml) {
                         float& bvp = bv_smem[p * THREADS + threadIdx.x];
                         uint8_t& bip = bi_smem[p * THREADS + threadIdx.x];
@@ -420,7 +444,8 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     prm.P = s.P; prm.B = s.B; prm.C = s.C; prm.V = s.V;
     prm.sp = s.stride_p; prm.sb = s.stride_b; prm.sc = s.stride_c; prm.sv = s.stride_v;
     prm.sd = s.stride_d; prm.draws = s.draws > 1 ? s.draws : 1; prm.sflags = s.flags; prm.renorm_eps = s.renorm_eps;
-    const bool produced = prm.draws > 1 || s.flags != 0;  // upstream producers folded into the read: generic kernel
+    const bool lg = (s.flags & VU_SLAB_LOGITS) != 0;  // logits: TMA form or generic kernel
+    const bool produced = prm.draws > 1 || (s.flags & ~VU_SLAB_LOGITS);  // other upstream producers folded into the read: generic kernel
     prm.tu = a->tu; prm.au = a->au; prm.eu = a->eu; prm.lab = a->labels;
     prm.mlab = a->member_labels;
     prm.st = st;
@@ -440,7 +465,7 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     const int need_levels = s.P <= 17 ? 1 : (s.P <= 271 ? 2 : 3);
 
     const FastVariant* pick = nullptr;
-    if (s.stride_v == 1 && s.P >= 2 && need_levels <= 2 && forced != -2 && !produced) {
+    if (s.stride_v == 1 && s.P >= 2 && need_levels <= 2 && forced != -2 && !produced && !lg) {
         if (forced >= 0 && forced < kNumFast) {
             const FastVariant& f = kFast[forced];
             if (f.C == s.C && f.LEVELS >= need_levels && aligned_for(a, f.VEC)) pick = &f;

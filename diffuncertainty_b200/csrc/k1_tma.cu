@@ -99,9 +99,12 @@ __device__ __forceinline__ void stat_warps_loop(const StatParams& st, void* st_s
 // NCH == 1: a stage holds G whole members (G x C rows).  NCH == 2 (G == 1, VEC >= 2): a stage holds half a
 // member's classes ((C+1)/2 rows), for C = 19 where a whole member of a 1024-voxel tile would take 76 KB.
 // ST statistics threads (0: a launch without statistics), SREP histogram replicas per statistics warp.
-template <int C, int VEC, int LEVELS, int CT, int G, int NCH, int ST, int SREP>
+// LG: the slab holds logits (VU_SLAB_LOGITS): every member is softmax'ed over its classes as it is consumed (whole members per
+// stage only: the maximum over all classes comes first).
+template <int C, int VEC, int LEVELS, int CT, int G, int NCH, int ST, int SREP, bool LG = false>
 __global__ void __launch_bounds__(CT + 32 + ST, 1) k1_tma(const __grid_constant__ K1TmaParams prm) {
     constexpr bool STATS = ST > 0;
+    static_assert(!LG || NCH == 1, "logits need whole members per stage");
     constexpr int kStatThreads = ST;
     static_assert(NCH == 1 || (NCH == 2 && G == 1 && VEC >= 2), "class chunks: one member per stage, VEC >= 2");
     constexpr int TV = CT * VEC;  // voxels per tile
@@ -247,7 +250,25 @@ __global__ void __launch_bounds__(CT + 32 + ST, 1) k1_tma(const __grid_constant_
                             for (int j = 0; j < Acc::NP; ++j) xp[j] = pk2(srow[(2 * j) * TV], srow[(2 * j + 1) * TV]);
                             if constexpr (Acc::ODD) xs = srow[(C - 1) * TV];
                         }
-                        acc.add_member(xp, xs, p0 + g, prm.mlab != nullptr);
+                        if constexpr (LG) {
+                            f32x2 hm[Acc::NH];
+                            float hs = 0.f;
+                            auto reload = [&](int i) {
+                                if constexpr (VEC == 4) {
+                                    const float2 w = *reinterpret_cast<const float2*>(srow + (i >> 1) * TV + 2 * (i & 1));
+                                    return pk2(w.x, w.y);
+                                } else if constexpr (VEC == 2) {
+                                    const float2 w = *reinterpret_cast<const float2*>(srow + i * TV);
+                                    return pk2(w.x, w.y);
+                                } else {
+                                    return pk2(srow[(2 * i) * TV], srow[(2 * i + 1) * TV]);
+                                }
+                            };
+                            acc.softmax_member(xp, xs, hm, hs, reload, [&]() { return srow[(C - 1) * TV]; });
+                            acc.add_member_pre(xp, xs, hm, hs, p0 + g, prm.mlab != nullptr);
+                        } else {
+                            acc.add_member(xp, xs, p0 + g, prm.mlab != nullptr);
+                        }
                         if (prm.mlab && active) VecLoad<VEC>::store_u8(prm.mlab + ((long long)(p0 + g) * prm.B + b) * V + v, acc.bi);
                     }
                 }
@@ -319,12 +340,16 @@ typedef void (*K1TmaKernel)(const K1TmaParams);
 struct TmaVariant {
     int C, VEC, LEVELS, CT, G, NCH, ST, SREP;
     int use;  // automatic selection: 0 = any launch, 1 = only launches with reference-based statistics on few-class slabs, -1 = never
+    int logits;  // 1: built for slabs of logits (VU_SLAB_LOGITS)
     K1TmaKernel fn, fn_stats;
 };
-#define VU_TMA_S(C, VEC, LEVELS, CT, G, NCH, ST, SREP, USE)                                              \
-    { C, VEC, LEVELS, CT, G, NCH, ST, SREP, USE, (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, NCH, 0, 32>, \
+#define VU_TMA_S(C, VEC, LEVELS, CT, G, NCH, ST, SREP, USE)                                                 \
+    { C, VEC, LEVELS, CT, G, NCH, ST, SREP, USE, 0, (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, NCH, 0, 32>, \
       (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, NCH, ST, SREP> }
 #define VU_TMA(C, VEC, LEVELS, CT, G, NCH) VU_TMA_S(C, VEC, LEVELS, CT, G, NCH, 96, 32, 0)
+#define VU_TMA_LG(C, VEC, LEVELS, CT, G, USE)                                                                 \
+    { C, VEC, LEVELS, CT, G, 1, 96, 32, USE, 1, (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, 1, 0, 32, true>,   \
+      (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, 1, 96, 32, true> }
 
 static const TmaVariant kTma[] = {
     VU_TMA(2, 4, 1, 512, 2, 1),  VU_TMA(2, 4, 2, 512, 2, 1),   // 0, 1
@@ -336,6 +361,12 @@ static const TmaVariant kTma[] = {
     // few classes with reference-based statistics: the statistics phase outweighs the streaming arithmetic, so the warp
     // split follows the work (consumer warps : statistics warps)
     VU_TMA_S(2, 4, 1, 256, 1, 1, 256, 16, -1), VU_TMA_S(2, 4, 2, 512, 2, 1, 192, 32, -1),  // 12, 13   8 : 8 (16 replicas), 16 : 6
+    // slabs of logits: whole members per stage; C = 19 with one voxel per thread (19 values + 19 sums in registers)
+    VU_TMA_LG(19, 1, 1, 512, 1, 0), VU_TMA_LG(19, 1, 2, 512, 1, 0),  // 14, 15
+    VU_TMA_LG(2, 4, 1, 512, 2, 0),  VU_TMA_LG(2, 4, 2, 512, 2, 0),   // 16, 17
+    VU_TMA_LG(3, 4, 1, 256, 2, 0),  VU_TMA_LG(3, 4, 2, 256, 2, 0),   // 18, 19
+    VU_TMA_LG(4, 4, 1, 256, 2, 0),  VU_TMA_LG(4, 4, 2, 256, 2, 0),   // 20, 21
+    VU_TMA_LG(19, 2, 1, 256, 1, -1), VU_TMA_LG(19, 2, 2, 256, 1, -1),  // 22, 23  (two voxels per thread, 8 consumer warps)
 };
 static const int kNumTma = (int)(sizeof(kTma) / sizeof(kTma[0]));
 
@@ -352,14 +383,16 @@ int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t str
         for (int64_t p = 0; p < s.P; ++p)
             if ((uintptr_t)s.member_ptrs_host[p] % 16) return 1;
     const int need_levels = s.P <= 17 ? 1 : 2;
+    const int lg = (s.flags & VU_SLAB_LOGITS) ? 1 : 0;
+    if (s.draws > 1 || (s.flags & ~VU_SLAB_LOGITS)) return 1;  // grouped draws / renormalise / one-hot: generic kernel
     const TmaVariant* pick = nullptr;
     if (forced >= 0 && forced < kNumTma) {
         const TmaVariant& f = kTma[forced];
-        if (f.C != s.C || f.LEVELS < need_levels) return set_error(VU_ERR_UNSUPPORTED, "k1_tma_variant does not fit this slab");
+        if (f.C != s.C || f.LEVELS < need_levels || f.logits != lg) return set_error(VU_ERR_UNSUPPORTED, "k1_tma_variant does not fit this slab");
         pick = &f;
     } else {
         for (int i = 0; i < kNumTma && !pick; ++i)
-            if (kTma[i].C == s.C && kTma[i].LEVELS == need_levels && kTma[i].use == 0) pick = &kTma[i];
+            if (kTma[i].C == s.C && kTma[i].LEVELS == need_levels && kTma[i].use == 0 && kTma[i].logits == lg) pick = &kTma[i];
     }
     if (!pick) return 1;
     // With few classes the reference-based statistics outweigh the streaming arithmetic; three statistics warps
@@ -367,7 +400,7 @@ int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     // where every warp does both (measured r01: cfg2 / cfg4 with Dice + calibration statistics 1.3-2.2x faster
     // that way; without reference-based statistics the TMA form wins everywhere).
     const unsigned heavy = VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC | VU_STAT_PLATT_FIT | VU_STAT_CLASS_COUNTS;
-    if (forced < 0 && get_option("k1_path", 0) != 2 && (st.flags & heavy) && s.C * s.P < 128) return 1;
+    if (forced < 0 && !lg && get_option("k1_path", 0) != 2 && (st.flags & heavy) && s.C * s.P < 128) return 1;
     const int vec = pick->VEC;
     auto ok = [&](const void* p, uintptr_t al) { return p == nullptr || ((uintptr_t)p % al) == 0; };
     if (!ok(a->tu, 4 * vec) || !ok(a->au, 4 * vec) || !ok(a->eu, 4 * vec) || !ok(a->labels, vec) || !ok(a->member_labels, vec) || s.V % vec) return 1;

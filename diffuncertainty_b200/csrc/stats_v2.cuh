@@ -106,7 +106,6 @@ __device__ __forceinline__ uint2 lds_u2(unsigned addr) {
 __device__ __forceinline__ void sts_u2(unsigned addr, uint2 v) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
-__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ unsigned dp4a_u(unsigned a, unsigned b, unsigned c) {
     unsigned r;

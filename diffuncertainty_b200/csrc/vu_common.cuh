@@ -139,6 +139,86 @@ __device__ __forceinline__ void plog2p_parts2(f32x2 P, f32x2& PC, f32x2& L) {
     PC = pk2(fmaxf(p0, 0.0f), fmaxf(p1, 0.0f));
 }
 
+// ---- softmax of a draw that arrives as logits (VU_SLAB_LOGITS; F.softmax(logits, dim=1), test_2D.py:1181-1256) ----------
+// p_c = e_c / S,  e_c = exp(x_c - max_c x),  S = sum_c e_c (class order, float32), as torch's softmax kernels compute it.  The
+// device evaluates e_c = ex2.approx((x_c - m) * log2 e) (2 ulp; e = 1 exactly at the maximum) and p_c = e_c * RN(1 / S).  A
+// member's entropy term sum_c p_c log2 p_c is formed WITHOUT a logarithm per element:
+//     sum_c p_c (z_c - log2 S) = (sum_c e_c z_c) / S - log2 S,   z_c = (x_c - m) * log2 e,
+// with log2 S from the near-one polynomial above when S - 1 < 1/16 (confident voxels: S = 1 + tiny, and the term is ~ -(S - 1);
+// the reference's own value there is quantised by the float32 rounding of S in exactly the same way).
+// Special values follow torch: the maximum propagates NaN (max.NaN), so a NaN or +inf logit (or a voxel whose logits are all
+// -inf) makes S NaN and with it every probability of the draw; a -inf logit next to finite ones has probability 0.
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float max_nan3(float a, float b, float c) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float z) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z));
+    return e;
+}
+// log2(S) for S >= 1 (a sum of exponentials whose largest term is 1), NaN for NaN
+__device__ __forceinline__ float log2_sum(float S) {
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(S));
+    const float f = __fadd_rn(S, -1.0f);
+    float t = __fmaf_rn(f, kQ3, kQ2);
+    t = __fmaf_rn(t, f, kQ1);
+    t = __fmaf_rn(t, f, kQ0);
+    return (f < kNearOne) ? __fmul_rn(t, f) : lg;  // (NaN: the comparison is false, lg2(NaN) = NaN)
+}
+// 1 / S: MUFU.RCP and one Newton step (the correctly rounded reciprocal in all but a few cases per million; the same
+// operations in the scalar and the packed form, so every kernel form produces the same bits)
+__device__ __forceinline__ float rcp_approx_f(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_newton(float S) {
+    const float r = rcp_approx_f(S);
+    return __fmaf_rn(__fmaf_rn(S, -r, 1.0f), r, r);
+}
+// Scalar reference form of one draw's softmax at one voxel, used where a thread walks the classes one by one (generic kernel)
+// and as the slow path of the vectorised form: pass 1 = softmax_max over the classes, pass 2 = softmax_term per class
+// accumulating S and EZ, then softmax_finish.  -inf logits (and differences that overflow) contribute e = 0 and no e z term.
+__device__ __forceinline__ float softmax_z(float x, float m) { return __fmul_rn(__fadd_rn(x, -m), kLog2e); }
+__device__ __forceinline__ void softmax_term(float x, float m, float& S, float& EZ, float& e) {
+    const float z = softmax_z(x, m);
+    e = ex2_approx(z);
+    S = __fadd_rn(S, e);
+    EZ = (e == 0.0f) ? EZ : __fmaf_rn(e, z, EZ);  // 0 * -inf is not a term; NaN z: e is NaN and stays in
+}
+// rS = 1 / S; h = the draw's sum_c p_c log2 p_c (never positive), 0 when the draw is all NaN (every term skipped,
+// test_utils.py:849-851): fminf returns the operand that is not NaN
+__device__ __forceinline__ void softmax_finish(float S, float EZ, float& rS, float& h) {
+    rS = rcp_newton(S);
+    h = fminf(__fmaf_rn(EZ, rS, -log2_sum(S)), 0.0f);
+}
+// the same for two voxels at once (packed Newton step, polynomial and final fma)
+__device__ __forceinline__ void softmax_finish2(f32x2 S, f32x2 EZ, f32x2& RS, f32x2& H) {
+    float s0, s1;
+    upk2(S, s0, s1);
+    const f32x2 R0 = pk2(rcp_approx_f(s0), rcp_approx_f(s1));
+    const f32x2 ERR = fma2(S, mul2(R0, pk2(-1.0f, -1.0f)), pk2(1.0f, 1.0f));
+    RS = fma2(ERR, R0, R0);
+    float lg0, lg1;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg0) : "f"(s0));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg1) : "f"(s1));
+    const f32x2 F = add2(S, pk2(-1.0f, -1.0f));
+    f32x2 T = fma2(F, pk2(kQ3, kQ3), pk2(kQ2, kQ2));
+    T = fma2(T, F, pk2(kQ1, kQ1));
+    T = fma2(T, F, pk2(kQ0, kQ0));
+    const f32x2 N = mul2(T, F);
+    float f0, f1, n0, n1, t0, t1;
+    upk2(F, f0, f1);
+    upk2(N, n0, n1);
+    const f32x2 NL = pk2((f0 < kNearOne) ? -n0 : -lg0, (f1 < kNearOne) ? -n1 : -lg1);
+    upk2(fma2(EZ, RS, NL), t0, t1);
+    H = pk2(fminf(t0, 0.0f), fminf(t1, 0.0f));
+}
+
 // torch.argmax tie rule (test_2D.py:817,871): first maximal index, NaN is max.
 __device__ __forceinline__ void argmax_step(float v, int c, float& best, int& idx) {
     const bool take = (v > best) | ((v != v) & (best == best));  // (no short-circuit: three compares, no branches)

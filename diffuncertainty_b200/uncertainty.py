@@ -179,6 +179,7 @@ class Groups:
     renormalize: bool = False
     discretize: bool = False
     eps: float = 1e-12
+    logits: bool = False  # the draws are network outputs before F.softmax (test_2D.py:1181-1256); see fused_pass(logits=True)
 
 
 def group_members(groups: Sequence[torch.Tensor]) -> list:
@@ -286,7 +287,7 @@ def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0
                want_maps: bool = True, want_labels: bool = True,
                stats_out: Optional[tuple] = None, maps_out: Optional[Dict[str, torch.Tensor]] = None,
                labels_out: Optional[torch.Tensor] = None, platt_fit=None, want_member_labels: bool = False,
-               members_out=None, class_counts_out: Optional[torch.Tensor] = None) -> FusedResult:
+               members_out=None, class_counts_out: Optional[torch.Tensor] = None, logits: bool = False) -> FusedResult:
     """One launch over ``softmax_pred`` of shape (P, B, C, *S) (test_2D.py:1277) -- or over a list of P member tensors
     (B, C, *S), which are then read where they are (no torch.stack).
 
@@ -301,6 +302,11 @@ def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0
     members_out: a ``members.MemberScoreBuffers``: the member-level scores (GED counts, likelihood sums) are computed in the
                  same pass -- one read of the slab.  Raises NotImplementedError when this launch cannot do that (see
                  ``vu_member_out`` in valunc.h); ``members.fused_pass_with_member_scores`` falls back to a second pass then.
+    logits     : OPT-IN.  ``softmax_pred`` holds the network outputs BEFORE ``F.softmax(output, dim=1)``
+                 (test_2D.py:1181, 1185, 1225, 1241, 1256); the kernel applies the softmax to every member / draw as it reads it
+                 (vu_fused_pass_logits), so the probability slab is never written or re-read.  Relaxed contract: the device's
+                 exponential differs from torch's by a few ulp -- maps keep the 1e-5 tolerance (+1e-6 absolute), labels can
+                 differ where a voxel's two largest mean probabilities agree to ~1e-7 (rates in INTEGRATION.md section 5).
     """
     _lib.require_device()
     lib = _lib.load()
@@ -309,6 +315,9 @@ def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0
     a.stat_flags = int(stats)
     P, B, Cn, spatial, dev, ptr_keep = fill_slab(a.slab, softmax_pred)
     V = int(a.slab.V)
+    logits = bool(logits) or (isinstance(softmax_pred, Groups) and softmax_pred.logits)
+    if logits and members_out is not None:
+        raise NotImplementedError("member-level scores are not available for slabs of logits")
 
     maps: Dict[str, torch.Tensor] = {}
     with torch.cuda.device(dev):
@@ -385,7 +394,10 @@ def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0
             if not lib.vu_fused_members_supported(C.byref(a)):
                 raise NotImplementedError("vu_fused_pass cannot compute the member-level scores in this launch: "
                                           + lib.vu_last_error().decode(errors="replace"))
-        _lib.check(lib.vu_fused_pass(C.byref(a), _lib.current_stream_ptr()), "vu_fused_pass")
+        if logits:
+            _lib.check(lib.vu_fused_pass_logits(C.byref(a), _lib.current_stream_ptr()), "vu_fused_pass_logits")
+        else:
+            _lib.check(lib.vu_fused_pass(C.byref(a), _lib.current_stream_ptr()), "vu_fused_pass")
     del keep, ptr_keep
     return FusedResult(maps=maps, labels=labels, stats_f64=sf, stats_i64=si, n_voxels=V,
                        n_raters=int(a.gt.R) if gt is not None else 0, stat_flags=int(stats), member_labels=member_labels,
@@ -403,6 +415,18 @@ def calculate_uncertainty(softmax_preds: torch.Tensor) -> Dict[str, torch.Tensor
         # members produce: present the member twice through a stride-0 view (no copy)
         softmax_preds = softmax_preds.expand(2, *softmax_preds.shape[1:])
     res = fused_pass(softmax_preds.unsqueeze(1), want_labels=False)
+    return {k: res.maps[k][0] for k in UNC_KEYS}
+
+
+def calculate_uncertainty_from_logits(logits: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """``calculate_uncertainty(F.softmax(logits, dim=1))`` (test_2D.py:1181 -> test_utils.py:833-859) in one pass over the
+    logits (P, C, *S); relaxed contract, see ``fused_pass(logits=True)``."""
+    _check_slab(logits, "logits")
+    if logits.dim() < 2:
+        raise ValueError("logits must be (P, C, *spatial)")
+    if logits.shape[0] == 1:
+        logits = logits.expand(2, *logits.shape[1:])
+    res = fused_pass(logits.unsqueeze(1), want_labels=False, logits=True)
     return {k: res.maps[k][0] for k in UNC_KEYS}
 
 

@@ -115,7 +115,16 @@ typedef struct vu_slab {
      *   VU_SLAB_RENORMALIZE  each draw is renormalised over its classes first (_renormalize_probabilities,
      *              test_2D.py:188-194: p / max(sum_c p, eps) where sum_c p > eps).
      *   VU_SLAB_DISCRETIZE   each draw is replaced by the one-hot vector of its argmax (--discretize, test_2D.py:1272-1275).
-     * These launches run on the generic kernel (any strides, any class count).                                           */
+     *   VU_SLAB_LOGITS       the slab holds LOGITS: each draw is softmax'ed over its classes first (F.softmax(output, dim=1),
+     *              test_2D.py:1181, 1185, 1225, 1241, 1256), before the two producers above.  The probabilities are never
+     *              written anywhere: one full write + read of the slab less than softmax followed by vu_fused_pass.
+     *              RELAXED CONTRACT: the device's exponential is not torch's, so the probabilities differ from the
+     *              reference's by a few ulp; maps stay within the 1e-5 tolerance (plus 1e-6 absolute, the reference's own
+     *              float32 rounding of p next to 1), labels can differ from the reference's where the two largest mean
+     *              probabilities of a voxel agree to ~1e-7 relative (measured rates: INTEGRATION.md section 5).
+     *              Opt-in: vu_fused_pass rejects the flag, vu_fused_pass_logits sets it.
+     * Grouped draws and the two elementwise producers run on the generic kernel (any strides, any class count); plain logits
+     * have TMA forms for C = 2, 3, 4, 19.                                                                               */
     int64_t stride_d;
     int32_t draws;
     uint32_t flags;
@@ -123,6 +132,7 @@ typedef struct vu_slab {
 } vu_slab;
 #define VU_SLAB_RENORMALIZE 0x1u
 #define VU_SLAB_DISCRETIZE 0x2u
+#define VU_SLAB_LOGITS 0x4u
 
 /* batch["seg"]: (B, R, V) reference segmentations (test_2D.py:1122-1124).    */
 typedef struct vu_gt {
@@ -238,6 +248,11 @@ VU_API int vu_struct_size(int which);   /* 0 vu_fused_args, 1 vu_map_stats_args,
  *   NCC sums                 ncc.py:17-27
  * reading the slab exactly once.                                             */
 VU_API int vu_fused_pass(const vu_fused_args* args, void* stream);
+/* The same pass over a slab of LOGITS (args->slab.data / member_ptrs address the network outputs before F.softmax,
+ * test_2D.py:1181-1256): softmax over the classes is applied to every draw while it is read (VU_SLAB_LOGITS is set by this
+ * entry point; see vu_slab for the relaxed label contract).  Everything else -- outputs, statistics, strides, member lists,
+ * grouped draws, renormalise / discretise -- as vu_fused_pass.  Member-level scores (args->members) are not available.  */
+VU_API int vu_fused_pass_logits(const vu_fused_args* args, void* stream);
 /* 1 if vu_fused_pass can compute args->members in the same pass (see vu_member_out), 0 if not (the reason is left in
  * vu_last_error).  Nothing is launched.                                                                                  */
 VU_API int vu_fused_members_supported(const vu_fused_args* args);

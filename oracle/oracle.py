@@ -832,3 +832,11 @@ def renormalize_probabilities_canonical(probs: np.ndarray, eps: float = 1e-12) -
     safe = np.maximum(nrm, np.float32(eps))
     with np.errstate(invalid="ignore", divide="ignore"):
         return np.where(nrm > np.float32(eps), (p / safe).astype(np.float32), p)
+
+
+def softmax_logits(logits: torch.Tensor, dim: int = 1) -> torch.Tensor:
+    """The step that turns network outputs into the probabilities of the slab: ``F.softmax(output, dim=1)``
+    (uncertainty_modeling/test_2D.py:1181, 1185, 1225, 1241, 1256) -- torch's own CPU kernel in float32, which is what the
+    reference runs.  logits: (..., C, *S) with the class axis at ``dim``."""
+    import torch.nn.functional as F
+    return F.softmax(logits.float(), dim=dim)
