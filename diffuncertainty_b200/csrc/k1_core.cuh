@@ -184,12 +184,15 @@ struct VoxelAcc {
         cascade_step(p);
     }
 
-    // ---- a member that arrives as LOGITS (VU_SLAB_LOGITS): softmax over its classes in place (xp / xs become the
-    // probabilities), hm / hs receive the member's entropy term sum_c p log2 p of every voxel (see vu_common.cuh for the
-    // arithmetic and the special-value rules).  `reload(i)` returns the ORIGINAL pair i (reload_s(): the leftover value) --
-    // only used on the rare path of a voxel with -inf logits, whose 0 * -inf products have to be taken out of the e z sum.
+    // ---- a member that arrives as LOGITS (VU_SLAB_LOGITS): softmax over its classes.  xp / xs become the exponentials e_c,
+    // rs receives 1 / sum_c e_c of every voxel (packed like the voxels; VEC == 1: both halves the same) -- the probability
+    // e_c * rs is not materialised: add_member_pre folds the product into the member sum with one fma, in every kernel form --
+    // and hm / hs the member's entropy term sum_c p log2 p (see vu_common.cuh for the arithmetic and the special-value rules).
+    // `reload(i)` returns the ORIGINAL pair i (reload_s(): the leftover value): only used on the rare path of a voxel with -inf
+    // logits, whose 0 * -inf products have to be taken out of the e z sum.
     template <class Reload, class ReloadS>
-    __device__ __forceinline__ void softmax_member(f32x2 (&xp)[NP], float& xs, f32x2 (&hm)[NH], float& hs, Reload reload, ReloadS reload_s) {
+    __device__ __forceinline__ void softmax_member(f32x2 (&xp)[NP], float& xs, f32x2 (&rs)[NH], f32x2 (&hm)[NH], float& hs, Reload reload,
+                                                   ReloadS reload_s) {
         const f32x2 L2E = pk2(kLog2e, kLog2e);
         if constexpr (VEC >= 2) {
             float mx[VEC];
@@ -238,7 +241,8 @@ struct VoxelAcc {
                 upk2(EZ[q], ez[2 * q], ez[2 * q + 1]);
                 redo |= (ez[2 * q] != ez[2 * q]) | (ez[2 * q + 1] != ez[2 * q + 1]);
             }
-            if (redo) {  // a 0 * -inf product (or a NaN draw, for which this changes nothing): the e z sums term by term
+            if (__builtin_expect(redo, 0)) {  // a 0 * -inf product (or a NaN draw, for which this changes nothing): the e z sums term by term
+                asm volatile("");  // (keeps this a branch: if-converted, its fmas would run for every member)
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) ez[k] = 0.f;
 #pragma unroll  // (a rolled loop would index xp dynamically and put it into local memory)
@@ -255,12 +259,7 @@ struct VoxelAcc {
                 }
             }
 #pragma unroll
-            for (int q = 0; q < NH; ++q) {
-                f32x2 RS;
-                softmax_finish2(S[q], pk2(ez[2 * q], ez[2 * q + 1]), RS, hm[q]);
-#pragma unroll
-                for (int c = 0; c < C; ++c) xp[c * NH + q] = mul2(xp[c * NH + q], RS);
-            }
+            for (int q = 0; q < NH; ++q) softmax_finish2(S[q], pk2(ez[2 * q], ez[2 * q + 1]), rs[q], hm[q]);
         } else {
             float m;
             {
@@ -295,7 +294,8 @@ struct VoxelAcc {
                 EZ = __fmaf_rn(e, z, EZ);
                 xs = e;
             }
-            if (EZ != EZ) {
+            if (__builtin_expect(EZ != EZ, 0)) {
+                asm volatile("");
                 EZ = 0.f;
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
@@ -310,23 +310,32 @@ struct VoxelAcc {
             }
             float rS;
             softmax_finish(S, EZ, rS, hs);
-            const f32x2 RS = pk2(rS, rS);
-#pragma unroll
-            for (int j = 0; j < NP; ++j) xp[j] = mul2(xp[j], RS);
-            if constexpr (ODD) xs = __fmul_rn(xs, rS);
+            rs[0] = pk2(rS, rS);
         }
     }
-    // add a member whose probabilities and entropy term come from softmax_member; same accumulation order as add_member
-    __device__ __forceinline__ void add_member_pre(const f32x2 (&xp)[NP], float xs, const f32x2 (&hm)[NH], float hs, long long p,
-                                                   bool want_member_label = false) {
-        if (want_member_label) member_argmax<0, C>(xp, xs);
+    // add a member that comes from softmax_member: member sum += e * rs (one fma per element), entropy sum += hm; per-member
+    // labels are the argmax of the probabilities RN(e * rs), as the reference takes it (test_2D.py:814-818)
+    __device__ __forceinline__ void add_member_pre(const f32x2 (&xp)[NP], float xs, const f32x2 (&rs)[NH], const f32x2 (&hm)[NH], float hs,
+                                                   long long p, bool want_member_label = false) {
+        if (want_member_label) {
+            f32x2 pp[NP];
 #pragma unroll
-        for (int j = 0; j < NP; ++j) m0[j] = add2(m0[j], xp[j]);
+            for (int j = 0; j < NP; ++j) pp[j] = mul2(xp[j], rs[VEC >= 2 ? j % NH : 0]);
+            float r0, r1;
+            upk2(rs[0], r0, r1);
+            member_argmax<0, C>(pp, __fmul_rn(xs, r0));
+        }
+#pragma unroll
+        for (int j = 0; j < NP; ++j) m0[j] = fma2(xp[j], rs[VEC >= 2 ? j % NH : 0], m0[j]);
         if constexpr (VEC >= 2) {
 #pragma unroll
             for (int q = 0; q < NH; ++q) a0[q] = add2(a0[q], hm[q]);
         } else {
-            if constexpr (ODD) m0s = __fadd_rn(m0s, xs);
+            if constexpr (ODD) {
+                float r0, r1;
+                upk2(rs[0], r0, r1);
+                m0s = __fmaf_rn(xs, r0, m0s);
+            }
             a0s = __fadd_rn(a0s, hs);
         }
         cascade_step(p);

@@ -184,6 +184,14 @@ struct Cascade {
     // chunks, k = log2(chunk)
     __device__ __forceinline__ void add(float x, long long i, long long n_full, int k) {
         a[0] += x;
+        fold(i, n_full, k);
+    }
+    // a[0] += e * r in one rounding (a member of a slab of logits: probability = exponential x 1 / sum, VoxelAcc::add_member_pre)
+    __device__ __forceinline__ void add_product(float e, float r, long long i, long long n_full, int k) {
+        a[0] = __fmaf_rn(e, r, a[0]);
+        fold(i, n_full, k);
+    }
+    __device__ __forceinline__ void fold(long long i, long long n_full, int k) {
         const long long done = i + 1;
         const long long mask = (1LL << k) - 1;
         if (i < n_full && (done & mask) == 0) {
@@ -310,6 +318,11 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
                     float x;
                     if (D == 1 && !(renorm | onehot | logits)) {
                         x = ldg_stream((prm.mptr ? ld_member_ptr(prm.mptr, p) : prm.x + p * prm.sp) + offc);
+                    } else if (plain_logits) {
+                        const float e = ex2_approx(softmax_z(ldg_stream(draw_base(p, 0) + offc), lmax_smem[p * THREADS + threadIdx.x]));
+                        const float r = lrs_smem[p * THREADS + threadIdx.x];
+                        cas.add_product(e, r, p, n_full, level_k);
+                        x = __fmul_rn(e, r);  // (per-member labels)
                     } else {
                         // the member is the mean of its draws (test_2D.py:1277): cascade sum, true division
                         Cascade cd;
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
                         }
                         x = D > 1 ? __fdiv_rn(cd.total(), Df) : cd.total();
                     }
-                    cas.add(x, p, n_full, level_k);
+                    if (!plain_logits) cas.add(x, p, n_full, level_k);
                     if (P > 1 && !plain_logits) h[p * THREADS] = plog2p_acc(h[p * THREADS], x);
                     if (want_ml) {
                         float& bvp = bv_smem[p * THREADS + threadIdx.x];

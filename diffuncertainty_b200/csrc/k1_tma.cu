@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(CT + 32 + ST, 1) k1_tma(const __grid_constant_
                             if constexpr (Acc::ODD) xs = srow[(C - 1) * TV];
                         }
                         if constexpr (LG) {
-                            f32x2 hm[Acc::NH];
+                            f32x2 hm[Acc::NH], rs[Acc::NH];
                             float hs = 0.f;
                             auto reload = [&](int i) {
                                 if constexpr (VEC == 4) {
@@ -264,8 +264,8 @@ __global__ void __launch_bounds__(CT + 32 + ST, 1) k1_tma(const __grid_constant_
                                     return pk2(srow[(2 * i) * TV], srow[(2 * i + 1) * TV]);
                                 }
                             };
-                            acc.softmax_member(xp, xs, hm, hs, reload, [&]() { return srow[(C - 1) * TV]; });
-                            acc.add_member_pre(xp, xs, hm, hs, p0 + g, prm.mlab != nullptr);
+                            acc.softmax_member(xp, xs, rs, hm, hs, reload, [&]() { return srow[(C - 1) * TV]; });
+                            acc.add_member_pre(xp, xs, rs, hm, hs, p0 + g, prm.mlab != nullptr);
                         } else {
                             acc.add_member(xp, xs, p0 + g, prm.mlab != nullptr);
                         }

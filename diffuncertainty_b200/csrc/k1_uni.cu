@@ -235,15 +235,15 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
                         for (int c = 0; c < C; ++c)
                             asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xp[c * 2]), "=l"(xp[c * 2 + 1]) : "r"(sbase + (unsigned)((g * C + c) * kRowBytes)));
                         if constexpr (LG) {
-                            f32x2 hm[Acc::NH];
+                            f32x2 hm[Acc::NH], rs[Acc::NH];
                             float xs = 0.f, hs = 0.f;
                             auto reload = [&](int i) {
                                 f32x2 r;
                                 asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(sbase + (unsigned)((g * C + (i >> 1)) * kRowBytes + (i & 1) * 8)));
                                 return r;
                             };
-                            acc.softmax_member(xp, xs, hm, hs, reload, []() { return 0.f; });
-                            acc.add_member_pre(xp, 0.f, hm, hs, p0 + g, false);
+                            acc.softmax_member(xp, xs, rs, hm, hs, reload, []() { return 0.f; });
+                            acc.add_member_pre(xp, 0.f, rs, hm, hs, p0 + g, false);
                         } else {
                             acc.add_member(xp, 0.f, p0 + g, false);
                         }

@@ -319,6 +319,217 @@ __global__ void __launch_bounds__(kP3Threads, KT > 0 ? 3 : 2) patch_box3(const f
     }
 }
 
+// ---- 3-D maps, cubic box of a compile-time edge K <= 10 (patch_size: 10, aggregation_all.yaml:9): plane kernel -------------
+// patch_box3 spends its time in shared memory: per slice a 32 x 32 output window costs (32 + K - 1)^2 float64 stores and two
+// sliding passes that read them back (~100 B of shared-memory traffic per output column and slice, 1.64 x redundant global
+// loads for the halo; ncu r02s: 36 % issue, short-scoreboard and barrier stalls, and 512 CTAs on 444 slots = two waves).
+// Here a CTA of 512 threads owns a 64 x 64 window of input columns (55 x 55 outputs for K = 10: a whole 64^3 LIDC crop per
+// plane, 1.35 x halo instead of 1.64 x) and a chunk of output slices:
+//   z  every thread keeps float64 running sums over the last K slices for 8 consecutive x columns of one row (two 128-bit
+//      loads for the slice entering and the slice leaving, requested one slice ahead);
+//   x  the K-wide sums along x slide over the thread's own 8 columns and the 9 that follow, which the next two lanes hold:
+//      they come through warp shuffles -- no shared memory, no barrier;
+//   y  the x-sums go to shared memory once (XOR-swizzled columns, row stride 65: stores and loads are conflict-free), one
+//      barrier (double-buffered), and every thread slides down 8 outputs of one column (17 loads).
+// ~40 B of shared-memory traffic per column and slice.  MODE and the workspace as in patch_box3: per CTA its own maximum and the
+// maxima of its chunks of kPlChunk output slices; the index pass skips the CTAs that cannot hold a box np.isclose to the
+// image's maximum, starts at the first chunk that holds one and stops after the first slice with a hit.
+constexpr int kPlW = 64, kPlThreads = 512, kPlStride = 65, kPlRows = 65, kPlMaxZ = 4, kPlAhead = 4;
+constexpr int kPlChunk = 4;  // output slices per workspace word (the index pass starts at the first chunk that holds a candidate)
+__host__ __device__ inline long long plane_item_words(long long o0, int nz) { return 1 + ((o0 + nz - 1) / nz + kPlChunk - 1) / kPlChunk; }
+constexpr size_t kPlSmem = 2 * (size_t)kPlRows * kPlStride * sizeof(double);
+
+template <int MODE, int K>
+__global__ void __launch_bounds__(kPlThreads, 2) patch_plane(const float* __restrict__ maps, long long d0, long long d1, long long d2,
+                                                             unsigned long long* max_enc, long long* first, double scale, int tiles_y,
+                                                             int tiles_x, int nz, unsigned long long* item_max) {
+    static_assert(K >= 2 && K <= 10, "the x pass takes its halo from the next two lanes: K - 1 <= 9 columns");
+    constexpr int OUT = kPlW - K + 1;
+    extern __shared__ double smem_d[];
+    const int tid = threadIdx.x;
+    const long long b = blockIdx.y;
+    int item = blockIdx.x;
+    const int txi = item % tiles_x;
+    item /= tiles_x;
+    const int tyi = item % tiles_y, zc = item / tiles_y;
+    const long long o0 = d0 - K + 1, o1 = d1 - K + 1, o2 = d2 - K + 1;
+    const long long per = (o0 + nz - 1) / nz, oz_begin = zc * per, oz_end = oz_begin + per < o0 ? oz_begin + per : o0;
+    unsigned long long* my_max = item_max ? item_max + (b * gridDim.x + blockIdx.x) * plane_item_words(o0, nz) : nullptr;
+    if (oz_begin >= oz_end) {  // (more chunks than output slices)
+        if (MODE == 0 && my_max && tid == 0) *my_max = 0ull;
+        return;
+    }
+    double peak = 0.0, tol = 0.0;
+    long long z_first = oz_begin;  // first input slice this CTA reads
+    if (MODE == 1) {
+        peak = o2d(max_enc[b]);
+        tol = 1e-8 / scale + 1e-5 * fabs(peak);  // np.isclose(v*scale, peak*scale): atol 1e-8, rtol 1e-5
+        if (my_max) {
+            const unsigned long long e = *my_max;
+            if (e == 0ull || !(fabs(o2d(e) - peak) <= tol)) return;  // no candidate in this window / chunk (CTA-uniform)
+            const int nch = (int)((oz_end - oz_begin + kPlChunk - 1) / kPlChunk);
+            int ch = 0;
+            while (ch < nch - 1 && !(my_max[1 + ch] != 0ull && fabs(o2d(my_max[1 + ch]) - peak) <= tol)) ++ch;
+            z_first += (long long)ch * kPlChunk;
+        }
+    }
+    const long long ty0 = (long long)tyi * OUT, tx0 = (long long)txi * OUT;
+    const long long plane = d1 * d2;
+    const float* img = maps + b * d0 * plane;
+
+    // x role: row ry of the window, columns xseg .. xseg + 7
+    const int ry = tid >> 3, l8 = tid & 7, xseg = l8 * 8;
+    const long long gy = ty0 + ry, gx0 = tx0 + xseg;
+    const bool row_in = gy < d1;
+    const float* src = img + (row_in ? gy * d2 : 0) + gx0;  // (only dereferenced where it lies inside the map)
+    const bool fast = row_in && gx0 + 8 <= d2 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (plane & 3) == 0;
+    auto load8 = [&](long long z, float (&v)[8]) {
+        const float* p = src + z * plane;
+        if (fast) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p)), c = __ldg(reinterpret_cast<const float4*>(p) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (row_in && gx0 + i < d2) ? __ldg(p + i) : 0.f;
+        }
+    };
+    // y role: column cx of the window, outputs yseg .. yseg + 7
+    const int cx = tid & 63, yseg = (tid >> 6) * 8;
+    const int cxs = cx ^ ((cx >> 3) & 7);
+    const long long ox = tx0 + cx;
+    const bool col_ok = cx < OUT && ox < o2 && yseg < OUT;
+    int n_valid = 0;  // outputs yseg .. yseg + n_valid - 1 of this thread's column lie inside the window and the map
+    if (col_ok) {
+        long long lim = OUT - yseg < o1 - (ty0 + yseg) ? OUT - yseg : o1 - (ty0 + yseg);
+        n_valid = lim < 0 ? 0 : (lim > 8 ? 8 : (int)lim);
+    }
+
+    double run[8];
+    float nv[8], ov[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { run[i] = 0.0; ov[i] = 0.f; }
+    const long long z_last = oz_end + K - 1;  // input slices [z_first, z_last)
+    load8(z_first, nv);
+    double best = 0.0, chunk_best = -INFINITY;
+    bool have = false, chunk_have = false;
+    long long best_idx = 0x7fffffffffffffffLL;
+    __shared__ unsigned long long wmax[kPlThreads / 32];
+
+    for (long long z = z_first; z < z_last; ++z) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            run[i] += (double)nv[i];
+            run[i] -= (double)ov[i];
+        }
+        if (z + 1 < z_last) {
+            load8(z + 1, nv);
+            if (z + 1 - z_first >= K) load8(z + 1 - K, ov);
+        }
+        // the slice kPlAhead further on goes to L2 now (the leaving slice was read K slices ago and is still there): the register
+        // loads above, issued one slice ahead, then only have L2 latency to hide -- every warp of the CTA waits at the same time
+        if (row_in && z + kPlAhead < z_last && l8 < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (z + kPlAhead) * plane + (l8 ? 32 - xseg : 0)));
+        if (z - z_first < K - 1) continue;  // uniform: the window is not full yet
+        const int buf = (int)(z & 1);
+        {
+            // K-wide sums along x: own columns 0..7, the next lane's 8..15, one more from the lane after it (lanes at the end of
+            // a row pick up another row's values: they only reach outputs beyond the window, which are masked out below)
+            double r[17];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                r[i] = run[i];
+                r[8 + i] = __shfl_down_sync(kFull, run[i], 1);
+            }
+            r[16] = __shfl_down_sync(kFull, run[0], 2);
+            double* xw = smem_d + (size_t)buf * (kPlRows * kPlStride) + ry * kPlStride + xseg;
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) s += r[j];
+            xw[0 ^ l8] = s;
+#pragma unroll
+            for (int i = 1; i < 8; ++i) {
+                s += r[i + K - 1];
+                s -= r[i - 1];
+                xw[i ^ l8] = s;
+            }
+        }
+        __syncthreads();
+        bool hit = false;
+        if (yseg < OUT) {  // (uniform per pair of warps; the last segment holds no valid output)
+            const double* col = smem_d + (size_t)buf * (kPlRows * kPlStride) + yseg * kPlStride + cxs;
+            const long long oz = z - (K - 1);
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) s += col[j * kPlStride];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i > 0) {
+                    s += col[(i + K - 1) * kPlStride];  // (row 64 is never written: it only reaches the masked output 55)
+                    s -= col[(i - 1) * kPlStride];
+                }
+                if (i < n_valid) {
+                    if (MODE == 0) {
+                        chunk_best = fmax(chunk_best, s);  // (one DMNMX; a NaN sum is passed over, as `s > best` did)
+                    } else if (fabs(s - peak) <= tol) {
+                        const long long idx = (oz * o1 + ty0 + yseg + i) * o2 + ox;
+                        if (idx < best_idx) best_idx = idx;
+                        hit = true;
+                    }
+                }
+            }
+            if (MODE == 0 && n_valid > 0) chunk_have = true;
+        }
+        // MODE 1: a hit in this slice ends the search, every later slice only has larger row-major indices.  MODE 0 needs no
+        // second barrier: the next slice writes the other buffer, whose readers passed this slice's barrier already.
+        if (MODE == 1 && __syncthreads_or(hit)) break;
+        if (MODE == 0) {
+            const int done = (int)(z - (K - 1) + 1 - oz_begin);  // output slices of this CTA so far
+            if (done % kPlChunk == 0 || z + 1 == z_last) {      // end of a chunk: fold it into the CTA's maximum, store it
+                if (chunk_have && (!have || chunk_best > best)) { best = chunk_best; have = true; }
+                if (my_max) {
+                    unsigned long long e = chunk_have ? d2o(chunk_best) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        unsigned long long other = __shfl_xor_sync(kFull, e, o);
+                        e = other > e ? other : e;
+                    }
+                    if ((tid & 31) == 0) wmax[tid >> 5] = e;
+                    __syncthreads();
+                    if (tid == 0) {
+                        for (int w = 1; w < kPlThreads / 32; ++w) e = wmax[w] > e ? wmax[w] : e;
+                        my_max[1 + (done - 1) / kPlChunk] = e;
+                    }
+                    // (wmax is rewritten after the next slice's barrier at the earliest)
+                }
+                chunk_have = false;
+                chunk_best = -INFINITY;
+            }
+        }
+    }
+    if (MODE == 0) {
+        unsigned long long e = have ? d2o(best) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(kFull, e, o);
+            e = other > e ? other : e;
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) wmax[tid >> 5] = e;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kPlThreads / 32; ++w) e = wmax[w] > e ? wmax[w] : e;
+            if (my_max) *my_max = e;
+            if (e) atomicMax(max_enc + b, e);
+        }
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            long long other = __shfl_xor_sync(kFull, best_idx, o);
+            best_idx = other < best_idx ? other : best_idx;
+        }
+        if ((tid & 31) == 0 && best_idx != 0x7fffffffffffffffLL) atomicMin(first + b, best_idx);
+    }
+}
+
 // ---- 2-D maps (d0 == 1): one thread per output column, marching down the rows ---------------------------------
 // A CTA owns kTX output columns and a chunk of output rows.  Per input row: the row segment goes to shared memory
 // (double-buffered, one barrier per row), each thread forms its K-tap x-sum in float64 and keeps the last K of
@@ -441,11 +652,36 @@ static bool patch_uses_2d(long long d0, long long d1, int k0, int k1, int k2) {
     return d0 == 1 && k0 == 1 && k1 == k2 && (k1 == 10 || k1 == 4 || k1 == 16) && (d1 - k1 + 1 + kRowsPerCta - 1) / kRowsPerCta <= 65535;
 }
 static bool patch_uses_box3(int k1, int k2) { return (kP3T + k1 - 1) * (kP3T + k2 - 1) <= kP3MaxCols * kP3Threads; }
+static bool patch_uses_plane(long long d0, long long d1, long long d2, int k0, int k1, int k2) {
+    return d0 > 1 && k0 == 10 && k1 == 10 && k2 == 10 && d1 * d2 <= 0x7fffffffLL && get_option("patch_path", 0) != 1;  // option 1: patch_box3 (A/B tests)
+}
+static long long plane_tiles(long long d, int k) { return (d - k + 1 + (kPlW - k + 1) - 1) / (kPlW - k + 1); }
+// chunks of output slices per window: as many as shorten the launch (whole waves of CTAs x slices per CTA, warm-up included)
+static int plane_zchunks(long long B, long long d0, long long d1, long long d2, int k) {
+    const long long o0 = d0 - k + 1, tiles = plane_tiles(d1, k) * plane_tiles(d2, k), slots = 2LL * device_sm_count();
+    int best_nz = 1;
+    long long best_cost = -1;
+    for (int nz = 1; nz <= kPlMaxZ; ++nz) {
+        const long long per = (o0 + nz - 1) / nz;
+        const long long cost = ((B * tiles * nz + slots - 1) / slots) * (per + k - 1);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nz = nz; }
+    }
+    return best_nz;
+}
 
 // CTAs per image of the kernel launch_patch_max picks (one workspace word each)
 long long patch_ctas_per_image(long long d0, long long d1, long long d2, int k0, int k1, int k2) {
     const long long o1 = d1 - k1 + 1, o2 = d2 - k2 + 1;
     if (patch_uses_2d(d0, d1, k0, k1, k2)) return ((o2 + kTX - 1) / kTX) * ((o1 + kRowsPerCta - 1) / kRowsPerCta);
+    if (patch_uses_plane(d0, d1, d2, k0, k1, k2)) {  // (sized for either 3-D kernel: the option can change between the two calls)
+        long long a = 0;
+        for (int nz = 1; nz <= kPlMaxZ; ++nz) {
+            const long long w = plane_tiles(d1, k1) * plane_tiles(d2, k2) * nz * plane_item_words(d0 - k0 + 1, nz);
+            a = w > a ? w : a;
+        }
+        const long long c = ((o1 + kP3T - 1) / kP3T) * ((o2 + kP3T - 1) / kP3T) * (p3_zchunks(d0 - k0 + 1) + 1);
+        return a > c ? a : c;
+    }
     if (patch_uses_box3(k1, k2)) return ((o1 + kP3T - 1) / kP3T) * ((o2 + kP3T - 1) / kP3T) * (p3_zchunks(d0 - k0 + 1) + 1);
     return 0;  // the fallback kernel does not use the workspace
 }
@@ -465,6 +701,17 @@ int launch_patch_max(const float* maps, long long B, long long d0, long long d1,
         else if (k1 == 4) launch_patch2d<4>(maps, B, d1, d2, enc, out_first, scale, tile_max, stream);
         else launch_patch2d<16>(maps, B, d1, d2, enc, out_first, scale, tile_max, stream);
         count_launch("patch_box2d"); count_launch("patch_box2d");
+    } else if (patch_uses_plane(d0, d1, d2, k0, k1, k2)) {
+        const int tiles_y = (int)plane_tiles(d1, k1), tiles_x = (int)plane_tiles(d2, k2);
+        const int nz = plane_zchunks(B, d0, d1, d2, k0);
+        if ((long long)tiles_y * tiles_x * nz > 0x7fffffffLL) return set_error(VU_ERR_UNSUPPORTED, "map too large for one vu_patch_max call");
+        if (cudaFuncSetAttribute(patch_plane<0, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlSmem) != cudaSuccess ||
+            cudaFuncSetAttribute(patch_plane<1, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlSmem) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(patch_plane)");
+        dim3 grid((unsigned)(tiles_y * tiles_x * nz), (unsigned)B);
+        patch_plane<0, 10><<<grid, kPlThreads, kPlSmem, stream>>>(maps, d0, d1, d2, enc, out_first, scale, tiles_y, tiles_x, nz, tile_max);
+        patch_plane<1, 10><<<grid, kPlThreads, kPlSmem, stream>>>(maps, d0, d1, d2, enc, out_first, scale, tiles_y, tiles_x, nz, tile_max);
+        count_launch("patch_plane"); count_launch("patch_plane");
     } else if (patch_uses_box3(k1, k2)) {
         const int tiles_y = (int)((o1 + kP3T - 1) / kP3T), tiles_x = (int)((o2 + kP3T - 1) / kP3T);
         const int in_h = kP3T + k1 - 1, in_w = kP3T + k2 - 1;

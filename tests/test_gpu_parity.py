@@ -274,7 +274,9 @@ def test_golden_aggregations(vu, golden_agg):
 
 @pytest.mark.parametrize("shape,box", [
     ((40, 70, 75), 10),           # 3-D, several 32 x 32 windows per image, ragged edges
-    ((64, 64, 64), 10),           # BASELINE configs[1]
+    ((64, 64, 64), 10),           # BASELINE configs[1]: the plane kernel, one 64 x 64 window per slice
+    ((30, 130, 150), 10),         # plane kernel: 3 x 3 windows, rows that are not 16-byte aligned
+    ((13, 17, 23), 10),           # plane kernel: a map smaller than one window, chunks of one output slice
     ((12, 33, 97), (3, 5, 7)),    # anisotropic box
     ((100, 130), 7),              # 2-D box without a specialised kernel
     ((300, 520), 10),             # 2-D specialised kernel, several CTAs per image
@@ -317,6 +319,27 @@ def test_patch_level_multi_window(vu, shape, box):
     _lib.check(lib.vu_patch_max(t.data_ptr(), len(imgs), *dims, *k3, 0, out_max.data_ptr(), out_first.data_ptr(),
                                 _lib.current_stream_ptr()), "vu_patch_max")
     assert np.array_equal(out_max.cpu().numpy(), batched["max_score"]) and np.array_equal(out_first.cpu().numpy(), batched["first_index"])
+
+
+def test_patch_plane_kernel_equals_sliding_kernel(vu):
+    """The two 3-D kernels behind vu_patch_max_ws (plane kernel: r02; sliding-window kernel: r01, option patch_path = 1) on a
+    batch large enough for one or two chunks of output slices per window: same maxima (float64 sums of float32 values: the
+    order of the additions differs, 1e-12) and the same first-isclose indices."""
+    from diffuncertainty_b200 import _lib, aggregation as agg
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for B, dims in ((130, (64, 64, 64)), (40, (24, 70, 64))):
+        maps = torch.rand((B, *dims), device="cuda", generator=g) ** 3 * 0.69
+        maps[1] = 0.25                      # every box ties
+        maps[2, :, :, :] = 0.0
+        maps[2, 40 % dims[0]:, 5:, 7:] = 0.5  # plateau
+        new = agg.patch_level_batched(maps, (10, 10, 10))
+        _lib.load().vu_set_option(b"patch_path", 1)
+        try:
+            old = agg.patch_level_batched(maps, (10, 10, 10))
+        finally:
+            _lib.load().vu_set_option(b"patch_path", 0)
+        np.testing.assert_allclose(new["max_score"], old["max_score"], rtol=1e-12)
+        assert np.array_equal(new["first_index"], old["first_index"])
 
 
 def test_golden_calibration(vu, golden_calib):
