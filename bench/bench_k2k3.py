@@ -122,8 +122,34 @@ def bench_k4():
         print(f"{name:16s} K4 same ranks, descent on the host (r01)      {t_old:8.3f} ms wall (3 read-backs)", flush=True)
         print(f"{name:16s} K4 quantile(map, 0.9)                          {t_q:8.3f} ms wall", flush=True)
         print(f"{name:16s} K4 eqace_from_maps (R={R}), one image            {t_eq:8.3f} ms wall", flush=True)
+        # the batched form: B images x 3 uncertainty types in one launch sequence, two read-backs for all of them
+        Bb = 16 if V <= (1 << 20) else 4
+        ub = [(torch.rand((Bb,) + shape, device="cuda") ** (k + 2) * 0.69).contiguous() for k in range(3)]
+        predb = (torch.rand((Bb,) + shape, device="cuda") < 0.3).to(torch.uint8)
+        refsb = (torch.rand((Bb, R) + shape, device="cuda") < 0.3).to(torch.uint8)
+        platt3 = [(3.5, -1.25), (6.0, -2.0), (-4.0, 0.5)]
+        t_b = wall(lambda: calibration.eqace_from_maps_batch(refsb, predb, ub, platt3), iters=5)
+        print(f"{name:16s} K4 eqace_from_maps_batch, {Bb} images x 3 types   {t_b:8.3f} ms wall = {t_b / (3 * Bb):6.3f} ms per image and type",
+              flush=True)
+
+
+def bench_generic():
+    """Class counts without a compiled-in fast / TMA form (anything but C = 2, 3, 4, 19), unaligned rows and grouped draws run
+    on the generic kernel (k1_fused.cu: any C <= 256, any strides): its throughput on the fused pass without statistics."""
+    peak = 6532.2
+    for name, P, C, shape, B in (("C=5  N=10 512x512", 10, 5, (512, 512), 8), ("C=7  N=10 512x512", 10, 7, (512, 512), 8),
+                                 ("C=21 N=10 512x512", 10, 21, (512, 512), 4), ("C=19 N=10 511x513 (unaligned rows)", 10, 19, (511, 513), 4)):
+        x = synth.synth_slab(P, B, C, shape, seed=3, scale=3.0)
+        V = x[0, 0, 0].numel()
+        maps = {k: torch.empty((B,) + shape, dtype=torch.float32, device="cuda") for k in ("TU", "AU", "EU")}
+        labels = torch.empty((B,) + shape, dtype=torch.uint8, device="cuda")
+        ms = time_call(lambda: vu.fused_pass(x, maps_out=maps, labels_out=labels), iters=5)
+        nbytes = (4 * P * C + 13) * V * B
+        print(f"generic kernel   {name:36s} {ms:8.3f} ms  {nbytes / ms / 1e6:8.1f} GB/s = {nbytes / ms / 1e6 / peak:5.3f} of the HBM peak", flush=True)
+        del x
 
 
 if __name__ == "__main__":
     main()
     bench_k4()
+    bench_generic()

@@ -10,6 +10,6 @@ $short > $out/${tag}_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --cl
     --log-file $out/${tag}_launches_bench.csv $short > $out/${tag}_ncu_list.log 2>&1
 $short > $out/${tag}_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k1_tma -s 3 -c 1 \
     -o $out/${tag}_k1_tma_bench $short > $out/${tag}_ncu_full.log 2>&1
-python bench/bench_configs.py > $out/${tag}_configs.jsonl 2>&1
+python bench/bench_configs.py --logits > $out/${tag}_configs.jsonl 2>&1
 python bench/bench_k2k3.py > $out/${tag}_k2_k3_k4_timing.txt 2>&1
 tail -c 700 $out/${tag}_bench_line.json

@@ -735,13 +735,11 @@ int launch_patch_max(const float* maps, long long B, long long d0, long long d1,
         const size_t smem = ((size_t)(kT1 + k1 - 1) * kT2 + (size_t)k0 * kT1 * kT2) * sizeof(double) +
                             (size_t)(kT1 + k1 - 1) * (kT2 + k2 - 1) * sizeof(float);
         if (smem > 200 * 1024) return set_error(VU_ERR_UNSUPPORTED, "patch too large for shared memory");
-        static size_t attr = 0;
-        if (smem > attr) {
-            if (cudaFuncSetAttribute(patch_box<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-                cudaFuncSetAttribute(patch_box<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-                return set_cuda_error("cudaFuncSetAttribute(patch_box)");
-            attr = smem;
-        }
+        // (the attribute is per device and this may be the first launch on this one: set it whenever it is needed)
+        if (smem > 48 * 1024 &&
+            (cudaFuncSetAttribute(patch_box<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+             cudaFuncSetAttribute(patch_box<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess))
+            return set_cuda_error("cudaFuncSetAttribute(patch_box)");
         dim3 grid((unsigned)(tiles_y * tiles_x), (unsigned)B);
         patch_box<0><<<grid, kT1 * kT2, smem, stream>>>(maps, d0, d1, d2, k0, k1, k2, enc, out_first, scale, tiles_y, tiles_x);
         patch_box<1><<<grid, kT1 * kT2, smem, stream>>>(maps, d0, d1, d2, k0, k1, k2, enc, out_first, scale, tiles_y, tiles_x);

@@ -81,8 +81,9 @@ class HostResult:
 class HostPipeline:
     def __init__(self, P: int, C: int, spatial: Sequence[int], batch: int, R: int = 0, gt_dtype=torch.uint8,
                  chunk_images: int = 1, n_buffers: int = 3, stats: int = 0, thresholds: Optional[Sequence[float]] = None,
-                 platt=None, ignore_index: Optional[int] = None, device=None):
+                 platt=None, ignore_index: Optional[int] = None, device=None, logits: bool = False):
         _lib.require_device()
+        self.logits = bool(logits)  # the host slab holds network outputs before F.softmax (fused_pass(logits=True): opt-in)
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.P, self.C, self.spatial, self.B, self.R = P, C, tuple(spatial), batch, R
         self.chunk = max(1, min(chunk_images, batch))
@@ -153,7 +154,7 @@ class HostPipeline:
                     fused_pass(self.d_slab[j][:, :n], GroundTruth(self.d_gt[j][:n], self.ignore_index) if self.R else None,
                                stats=self.stats, thresholds=self.thresholds, calib=self.calib,
                                stats_out=(self.rows_f[s:e], self.rows_i[s:e]) if self.stats else None,
-                               maps_out=maps_out, labels_out=self.d_labels[j][:n])
+                               maps_out=maps_out, labels_out=self.d_labels[j][:n], logits=self.logits)
                     ev_run[j].record(self.s_run)
                 with torch.cuda.stream(self.s_out):
                     self.s_out.wait_event(ev_run[j])
