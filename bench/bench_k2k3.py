@@ -134,8 +134,9 @@ def bench_k4():
 
 
 def bench_generic():
-    """Class counts without a compiled-in fast / TMA form (anything but C = 2, 3, 4, 19), unaligned rows and grouped draws run
-    on the generic kernel (k1_fused.cu: any C <= 256, any strides): its throughput on the fused pass without statistics."""
+    """Class counts without a compiled-in fast / TMA form (anything but C = 2, 3, 4, 19) run on the class-outer kernel
+    (k1_classouter: run-time C, P <= 32; r02u: the generic kernel they used to fall to reached 0.5 TB/s), unaligned rows on the
+    one-voxel-per-thread register form: throughput of the fused pass without statistics."""
     peak = 6532.2
     for name, P, C, shape, B in (("C=5  N=10 512x512", 10, 5, (512, 512), 8), ("C=7  N=10 512x512", 10, 7, (512, 512), 8),
                                  ("C=21 N=10 512x512", 10, 21, (512, 512), 4), ("C=19 N=10 511x513 (unaligned rows)", 10, 19, (511, 513), 4)):
@@ -145,7 +146,7 @@ def bench_generic():
         labels = torch.empty((B,) + shape, dtype=torch.uint8, device="cuda")
         ms = time_call(lambda: vu.fused_pass(x, maps_out=maps, labels_out=labels), iters=5)
         nbytes = (4 * P * C + 13) * V * B
-        print(f"generic kernel   {name:36s} {ms:8.3f} ms  {nbytes / ms / 1e6:8.1f} GB/s = {nbytes / ms / 1e6 / peak:5.3f} of the HBM peak", flush=True)
+        print(f"other class counts {name:36s} {ms:8.3f} ms  {nbytes / ms / 1e6:8.1f} GB/s = {nbytes / ms / 1e6 / peak:5.3f} of the HBM peak", flush=True)
         del x
 
 

@@ -206,6 +206,8 @@ struct Cascade {
     __device__ __forceinline__ float total() const { return ((a[0] + a[1]) + a[2]) + a[3]; }
 };
 
+constexpr int kGenAhead = 8;  // members whose loads are in flight per thread
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1Params prm, int level_k) {
     float* h_smem = reinterpret_cast<float*>(vu_dyn_smem);  // [P][THREADS] (P > 1), then the statistics state
@@ -314,25 +316,8 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
                 Cascade cas;
                 cas.reset();
                 const long long offc = off0 + (long long)c * prm.sc;
-                for (long long p = 0; p < P; ++p) {
-                    float x;
-                    if (D == 1 && !(renorm | onehot | logits)) {
-                        x = ldg_stream((prm.mptr ? ld_member_ptr(prm.mptr, p) : prm.x + p * prm.sp) + offc);
-                    } else if (plain_logits) {
-                        const float e = ex2_approx(softmax_z(ldg_stream(draw_base(p, 0) + offc), lmax_smem[p * THREADS + threadIdx.x]));
-                        const float r = lrs_smem[p * THREADS + threadIdx.x];
-                        cas.add_product(e, r, p, n_full, level_k);
-                        x = __fmul_rn(e, r);  // (per-member labels)
-                    } else {
-                        // the member is the mean of its draws (test_2D.py:1277): cascade sum, true division
-                        Cascade cd;
-                        cd.reset();
-                        for (int d = 0; d < D; ++d) {
-                            const float raw = onehot ? 0.f : ldg_stream(draw_base(p, d) + offc);
-                            cd.add(produced(raw, p * D + d, c), d, nfD, kD);
-                        }
-                        x = D > 1 ? __fdiv_rn(cd.total(), Df) : cd.total();
-                    }
+                // what happens to the value x of member p (the mean sum `cas` took it already when the slab holds plain logits)
+                auto consume = [&](long long p, float x) {
                     if (!plain_logits) cas.add(x, p, n_full, level_k);
                     if (P > 1 && !plain_logits) h[p * THREADS] = plog2p_acc(h[p * THREADS], x);
                     if (want_ml) {
@@ -345,6 +330,46 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
                             argmax_step(x, c, bb, ii);
                             bvp = bb; bip = (uint8_t)ii;
                         }
+                    }
+                };
+                if (D == 1 && !(renorm | onehot | logits)) {
+                    // plain probabilities: the loads of kGenAhead members are issued before the first is consumed (one load in
+                    // flight per thread left the kernel latency-bound: 0.5 TB/s; the order of the arithmetic is unchanged)
+                    for (long long p0 = 0; p0 < P; p0 += kGenAhead) {
+                        float xv[kGenAhead];
+#pragma unroll
+                        for (int j = 0; j < kGenAhead; ++j)
+                            if (p0 + j < P) xv[j] = ldg_stream((prm.mptr ? ld_member_ptr(prm.mptr, p0 + j) : prm.x + (p0 + j) * prm.sp) + offc);
+#pragma unroll
+                        for (int j = 0; j < kGenAhead; ++j)
+                            if (p0 + j < P) consume(p0 + j, xv[j]);
+                    }
+                } else if (plain_logits) {
+                    for (long long p0 = 0; p0 < P; p0 += kGenAhead) {
+                        float xv[kGenAhead];
+#pragma unroll
+                        for (int j = 0; j < kGenAhead; ++j)
+                            if (p0 + j < P) xv[j] = ldg_stream(draw_base(p0 + j, 0) + offc);
+#pragma unroll
+                        for (int j = 0; j < kGenAhead; ++j)
+                            if (p0 + j < P) {
+                                const long long p = p0 + j;
+                                const float e = ex2_approx(softmax_z(xv[j], lmax_smem[p * THREADS + threadIdx.x]));
+                                const float r = lrs_smem[p * THREADS + threadIdx.x];
+                                cas.add_product(e, r, p, n_full, level_k);
+                                consume(p, __fmul_rn(e, r));  // (per-member labels)
+                            }
+                    }
+                } else {
+                    for (long long p = 0; p < P; ++p) {
+                        // the member is the mean of its draws (test_2D.py:1277): cascade sum, true division
+                        Cascade cd;
+                        cd.reset();
+                        for (int d = 0; d < D; ++d) {
+                            const float raw = onehot ? 0.f : ldg_stream(draw_base(p, d) + offc);
+                            cd.add(produced(raw, p * D + d, c), d, nfD, kD);
+                        }
+                        consume(p, D > 1 ? __fdiv_rn(cd.total(), Df) : cd.total());
                     }
                 }
                 const float mean = __fdiv_rn(cas.total(), Pf);
@@ -378,6 +403,127 @@ __global__ void __launch_bounds__(THREADS) k1_generic(const __grid_constant__ K1
     }
     if (do_stats && t1 > t0) cursor.finish(prm.st, st_smem, vt, THREADS);
 }
+
+typedef void (*K1Kernel_t)(const K1Params);
+// ---------------------------------------------------------------------------
+// Class-outer kernel: ANY class count at run time, P <= PMAX members (compile time), unit voxel stride.
+// The fast / TMA forms above are compiled for C = 2, 3, 4, 19; every other class count used to fall to the generic kernel
+// (one scalar load in flight per thread, shared-memory read-modify-write per element: 0.5 TB/s, r02u).  Here a thread owns VEC
+// consecutive voxels and walks the classes in the OUTER loop: the P values of one class are P independent loads (8 at a
+// time in flight), their cascade sum is finished in registers (the mean of that class: true division, argmax step, TU term)
+// and the per-member entropy sums live in registers too, indexed at compile time because the member loop is fully unrolled
+// up to PMAX.  Every per-voxel operation and its order are those of k1_core.cuh, so maps and labels are bit-identical with
+// the other forms (tests/test_gpu_parity.py).
+// ---------------------------------------------------------------------------
+template <int VEC, int PMAX, int THREADS, bool MP, bool STATS>
+__global__ void __launch_bounds__(THREADS) k1_classouter(const __grid_constant__ K1Params prm) {
+    static_assert(VEC == 1 || VEC == 2, "one or two voxels per thread");
+    constexpr int CH = 8;       // members whose loads are in flight together
+    constexpr long long kTileVox = (long long)THREADS * VEC;
+    StatsCursor<THREADS> cursor;
+    if (STATS) stats_init<THREADS>(prm.st, vu_dyn_smem);
+    const int P = (int)prm.P, C = (int)prm.C;
+    const long long V = prm.V;
+    const float Pf = (float)P;
+    const bool two = P > 17;  // torch's cascade: chunks of 16 members folded into a second accumulator (k1_core.cuh)
+    const int t0 = (int)(prm.total_tiles * (long long)blockIdx.x / gridDim.x);
+    const int t1 = (int)(prm.total_tiles * (long long)(blockIdx.x + 1) / gridDim.x);
+    const int tpi = (int)prm.tiles_per_img;
+    int b = t0 / tpi, vt = t0 - b * tpi - 1;
+    for (int tile = t0; tile < t1; ++tile) {
+        if (++vt == tpi) { vt = 0; ++b; }
+        const long long v = (long long)vt * kTileVox + (long long)threadIdx.x * VEC;
+        if (STATS) cursor.enter(prm.st, vu_dyn_smem, b, vt, kTileVox);
+        const bool active = v < V;
+        float u[VU_N_UNC][VEC];
+        int label[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { u[0][k] = u[1][k] = u[2][k] = 0.f; label[k] = 0; }
+        if (active) {
+            if (STATS) stats_prefetch_gt<VEC>(prm.st, b, v);
+            const long long off0 = (long long)b * prm.sb + v;
+            // (member bases are formed per load: 2 x PMAX registers of pointers would halve the occupancy)
+            long long sp = prm.sp;
+            auto base = [&](int p) { return (MP ? ld_member_ptr(prm.mptr, p) : prm.x + (long long)p * sp) + off0; };
+            float h[PMAX][VEC];      // per-member entropy sums (log2 units)
+#pragma unroll
+            for (int p = 0; p < PMAX; ++p)
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) h[p][k] = 0.f;
+            float best[VEC], tu2[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { best[k] = 0.f; tu2[k] = 0.f; }
+            for (int c = 0; c < C; ++c) {
+                const long long oc = (long long)c * prm.sc;
+                asm volatile("" : "+l"(sp));  // (keeps the compiler from holding p * stride_p for every p in registers: occupancy)
+                float m0[VEC], m1[VEC];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) { m0[k] = 0.f; m1[k] = 0.f; }
+                // (requesting class c + 1 before class c is consumed was measured: the registers it takes cost more occupancy
+                //  than the loads in flight gain -- 1.3 TB/s against 1.6)
+#pragma unroll
+                for (int p0 = 0; p0 < PMAX; p0 += CH) {
+                    if (p0 < P) {
+                        float x[CH][VEC];
+#pragma unroll
+                        for (int j = 0; j < CH; ++j)
+                            if (p0 + j < PMAX && p0 + j < P) VecLoad<VEC>::load(base(p0 + j) + oc, x[j]);
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            const int p = p0 + j;
+                            if (p < PMAX && p < P) {
+#pragma unroll
+                                for (int k = 0; k < VEC; ++k) {
+                                    m0[k] = __fadd_rn(m0[k], x[j][k]);
+                                    h[p][k] = plog2p_acc(h[p][k], x[j][k]);
+                                }
+                                if ((p & 15) == 15 && two) {
+#pragma unroll
+                                    for (int k = 0; k < VEC; ++k) { m1[k] = __fadd_rn(m1[k], m0[k]); m0[k] = 0.f; }
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    const float sum = two ? __fadd_rn(m0[k], m1[k]) : m0[k];
+                    const float mean = __fdiv_rn(sum, Pf);  // test_2D.py:971
+                    if (c == 0) { best[k] = mean; label[k] = 0; } else argmax_step(mean, c, best[k], label[k]);
+                    tu2[k] = plog2p_acc(tu2[k], mean);
+                }
+            }
+            // AU: the mean over the members of their entropies, in the same cascade order
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int p = 0; p < PMAX; ++p) {
+                    if (p < P) {
+                        a0 = __fadd_rn(a0, h[p][k]);
+                        if ((p & 15) == 15 && two) { a1 = __fadd_rn(a1, a0); a0 = 0.f; }
+                    }
+                }
+                const float asum = two ? __fadd_rn(a0, a1) : a0;
+                const float tu = -(tu2[k] * kLn2);
+                const float au = __fdiv_rn(-(asum * kLn2), Pf);
+                u[0][k] = tu; u[1][k] = au; u[2][k] = tu - au;
+            }
+            const long long o = (long long)b * V + v;
+            if (prm.tu) VecLoad<VEC>::store(prm.tu + o, u[0]);
+            if (prm.au) VecLoad<VEC>::store(prm.au + o, u[1]);
+            if (prm.eu) VecLoad<VEC>::store(prm.eu + o, u[2]);
+            if (prm.lab) VecLoad<VEC>::store_u8(prm.lab + o, label);
+        }
+        if (STATS) stats_tile<VEC, THREADS>(prm.st, vu_dyn_smem, active, b, v, u, label);
+    }
+    if (STATS && t1 > t0) cursor.finish(prm.st, vu_dyn_smem, vt, kTileVox);
+}
+
+struct ClassOuterVariant {
+    int VEC, PMAX;
+    K1Kernel_t fn[2][2];  // [member pointer list][statistics]
+};
 
 // ---------------------------------------------------------------------------
 // host side
@@ -509,6 +655,38 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
         fn<<<(unsigned)grid, pick->THREADS, dyn, stream>>>(prm);
         count_launch("k1_fast");
         return check_launch("k1_fast");
+    }
+
+    // any other class count (and whatever else has no compiled-in form): the class-outer kernel, P <= 32, unit voxel stride
+    if (s.stride_v == 1 && s.P >= 2 && s.P <= 32 && !produced && !lg && forced != -2 && !a->member_labels) {
+        constexpr int T = 256;
+#define VU_CO(VEC, PMAX)                                                                                              \
+    { VEC, PMAX, { { (K1Kernel_t)k1_classouter<VEC, PMAX, T, false, false>, (K1Kernel_t)k1_classouter<VEC, PMAX, T, false, true> },  \
+                   { (K1Kernel_t)k1_classouter<VEC, PMAX, T, true, false>, (K1Kernel_t)k1_classouter<VEC, PMAX, T, true, true> } } }
+        static const ClassOuterVariant kCo[] = {VU_CO(2, 8), VU_CO(2, 16), VU_CO(2, 32), VU_CO(1, 8), VU_CO(1, 16), VU_CO(1, 32)};
+#undef VU_CO
+        const int vec = aligned_for(a, 2) ? 2 : 1;
+        const ClassOuterVariant* co = nullptr;
+        for (const ClassOuterVariant& c : kCo)
+            if (!co && c.VEC == vec && c.PMAX >= s.P) co = &c;
+        const long long tile_vox = (long long)T * vec;
+        prm.tiles_per_img = (s.V + tile_vox - 1) / tile_vox;
+        prm.total_tiles = prm.tiles_per_img * s.B;
+        if (prm.total_tiles >= (1LL << 31)) return set_error(VU_ERR_UNSUPPORTED, "more than 2^31 tiles in one launch; split the batch");
+        K1Kernel_t fn = co->fn[s.member_ptrs ? 1 : 0][st.flags ? 1 : 0];
+        const size_t dyn = stats_smem_bytes(st.flags, st.gt.R, T) + stats_class_bytes(st.flags, st.gt.R, st.ncls);
+        if (dyn <= 200 * 1024) {
+            if (dyn > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+                return set_cuda_error("cudaFuncSetAttribute(k1_classouter)");
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, T, dyn) != cudaSuccess || occ < 1)
+                return set_cuda_error("occupancy query (k1_classouter)");
+            long long grid = (long long)sms * occ;
+            if (grid > prm.total_tiles) grid = prm.total_tiles;
+            fn<<<(unsigned)grid, T, dyn, stream>>>(prm);
+            count_launch("k1_classouter");
+            return check_launch("k1_classouter");
+        }
     }
 
     // generic path

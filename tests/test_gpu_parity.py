@@ -774,3 +774,39 @@ def test_full_size_statistics_vs_oracle(vu, name, P, C, spatial, R, ignore, flag
             # error is bounded absolutely: 1e-5 relative or 1e-7 absolute, whichever is larger.
             want = oracle.compute_ncc(oracle.rater_variance_map(gnp), m)
             np.testing.assert_allclose(vncc.ncc_from_result(res, k)[0], want, rtol=RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("P,B,C,spatial", [(10, 2, 5, (16, 64)), (5, 1, 7, (8, 40)), (16, 1, 21, (8, 32)), (18, 2, 6, (4, 64)),
+                                           (32, 1, 3, (3, 37)), (17, 1, 33, (5, 24)), (2, 3, 255, (2, 16))])
+def test_classouter_kernel_equals_generic_and_oracle(vu, P, B, C, spatial):
+    """Class counts without a compiled-in form (anything but 2, 3, 4, 19) take the class-outer kernel (k1_classouter: run-time
+    C, members unrolled); it must give the bits of the generic kernel -- maps, labels, per-member labels, statistics -- and
+    the oracle's labels."""
+    from diffuncertainty_b200 import _lib
+    from oracle import oracle
+    g = torch.Generator().manual_seed(P * 100 + C)
+    x = torch.softmax(3.0 * torch.randn(P, B, C, *spatial, generator=g), dim=2)
+    x[0, 0, :, 0, :3] = 0.0
+    x[1, 0, 0, 0, 5] = float("nan")
+    gt = torch.randint(0, min(C, 250), (B, 2, *spatial), generator=g, dtype=torch.uint8)
+    flags = _lib.STAT_IMAGE_SUM | _lib.STAT_AREA | _lib.STAT_DICE | _lib.STAT_CLASS_COUNTS
+    before = _lib.get_counter("launches.k1_classouter")
+    co = vu.fused_pass(x.cuda(), vu.GroundTruth(gt.cuda(), None), stats=flags)
+    assert _lib.get_counter("launches.k1_classouter") == before + 1 or C in (2, 3, 4, 19)
+    lst = vu.fused_pass([x[p].cuda() for p in range(P)])  # the member-list form of the same kernel
+    assert torch.equal(lst.labels, co.labels) and torch.equal(lst.maps["EU"], co.maps["EU"])
+    _lib.load().vu_set_option(b"k1_variant", -2)
+    try:
+        gen = vu.fused_pass(x.cuda(), vu.GroundTruth(gt.cuda(), None), stats=flags, want_member_labels=True)
+    finally:
+        _lib.load().vu_set_option(b"k1_variant", -1)
+    assert torch.equal(co.labels, gen.labels)
+    for k in ("TU", "AU", "EU"):
+        assert torch.equal(co.maps[k].view(torch.int32), gen.maps[k].view(torch.int32)), k
+    assert torch.equal(co.stats_i64, gen.stats_i64) and torch.equal(co.class_counts, gen.class_counts)
+    np.testing.assert_allclose(co.stats_f64.cpu().numpy(), gen.stats_f64.cpu().numpy(), rtol=1e-7)
+    torch.set_num_threads(1)
+    for b in range(B):
+        label = oracle.argmax_first_nan_max(oracle.mean_members_f32(x[:, b].numpy())).astype(np.uint8)
+        assert np.array_equal(co.labels[b].cpu().numpy(), label)
+        assert torch.equal(gen.member_labels[:, b].cpu(), x[:, b].argmax(dim=1).to(torch.uint8))
