@@ -215,3 +215,40 @@ def test_logits_label_flip_rate_and_map_error(vu):
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/r02_logits_parity.json", "w") as f:
         json.dump(out, f, indent=1)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_logits_random_combination(vu, seed):
+    """Seeded random shapes (1- to 3-D, aligned or not), member counts across the cascade boundaries, class counts with and
+    without a TMA form, strided views and member lists, masked (-inf) classes: logits=True against torch's CPU softmax + the
+    reference pipeline, under the relaxed contract."""
+    rng = np.random.default_rng(4000 + seed)
+    g = torch.Generator().manual_seed(4000 + seed)
+    ndim = int(rng.integers(1, 4))
+    spatial = tuple(int(s) for s in rng.integers(1, 20, ndim))
+    if rng.random() < 0.6:
+        spatial = spatial[:-1] + (int(rng.choice([4, 8, 16, 32, 64])),)
+    P = int(rng.choice([2, 3, 5, 10, 16, 17, 18, 32, 33]))
+    C = int(rng.choice([2, 2, 3, 4, 5, 19, 19, 21]))
+    B = int(rng.integers(1, 4))
+    scale = float(rng.choice([0.5, 2.0, 6.0, 15.0]))
+    logits = scale * torch.randn(P, B, C, *spatial, generator=g) + 3.0 * torch.randn(P, B, 1, *spatial, generator=g)
+    if rng.random() < 0.3 and C > 2:
+        logits[:, :, 1] = float("-inf")  # a class masked out everywhere: probability exactly 0
+    xd = logits.cuda()
+    layout = rng.choice(["contiguous", "batch_slice", "member_list", "class_padded"])
+    if layout == "batch_slice":
+        big = torch.zeros((P, B + 2, C) + spatial, device="cuda")
+        big[:, 1:B + 1] = xd
+        arg = big[:, 1:B + 1]
+    elif layout == "class_padded":
+        big = torch.zeros((P, B, C + 3) + spatial, device="cuda")
+        big[:, :, :C] = xd
+        arg = big[:, :, :C]
+    elif layout == "member_list":
+        arg = [xd[p].clone() for p in range(P)]
+    else:
+        arg = xd
+    res = vu.fused_pass(arg, logits=True)
+    flips, n = check_against_reference(res, logits, f"seed {seed}: P{P} B{B} C{C} {spatial} {layout}")
+    assert flips <= max(1, n // 1000)
