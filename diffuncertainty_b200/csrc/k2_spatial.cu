@@ -639,6 +639,158 @@ __global__ void __launch_bounds__(kTX) patch_box2d(const float* __restrict__ map
     }
 }
 
+// ---- 2-D maps, square box of a compile-time edge K <= 10: strip kernel (r02) -----------------------------------------------
+// patch_box2d above spends ~50 instructions per output (K shared-memory loads, K conversions and K float64 additions for the
+// x sum of every output, K more for the ring).  Here a WARP is the unit of work: it owns a strip of 128 input columns (116
+// outputs) and a chunk of kStripRows output rows, and needs no barrier at all:
+//   x  a lane holds 4 consecutive columns of the row (one 128-bit load, requested two rows ahead); the K-wide sums slide over
+//      its own values and the 9 that follow, which come from the next three lanes through shuffles (the last three lanes of a
+//      warp produce no output: strips overlap by 12 columns);
+//   y  the box sum of an output is a running sum over the last K x-sums: add the new row's, subtract the one that leaves -- the
+//      x-sums of the last K rows wait in a lane-private ring in shared memory (128-bit stores / loads, conflict-free).
+// ~18 instructions per output.  MODE / workspace as in patch_box2d (one word per warp task).
+constexpr int kStripLanes = 29, kStripCols = kStripLanes * 4 /* 116 outputs per strip */, kStripRows = 32, kStripWarps = 8;
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(kStripWarps * 32) patch_strip2d(const float* __restrict__ maps, long long H, long long W,
+                                                                   unsigned long long* max_enc, long long* first, double scale,
+                                                                   int strips, int chunks, long long tasks, unsigned long long* task_max) {
+    static_assert(K >= 2 && K <= 10, "the halo comes from the next three lanes: K - 1 <= 9 columns after the lane's own four");
+    extern __shared__ double smem_d[];  // [warp][K rows][128 columns]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * kStripWarps + warp;
+    if (task >= tasks) return;
+    const long long b = task / ((long long)strips * chunks);
+    const int rem = (int)(task - b * strips * chunks), chunk = rem / strips, strip = rem - chunk * strips;
+    const long long o1 = H - K + 1, o2 = W - K + 1;
+    const long long x0 = (long long)strip * kStripCols, oy0 = (long long)chunk * kStripRows;
+    const long long oy1 = oy0 + kStripRows < o1 ? oy0 + kStripRows : o1;
+    double peak = 0.0, tol = 0.0;
+    if (MODE == 1) {
+        peak = o2d(max_enc[b]);
+        tol = 1e-8 / scale + 1e-5 * fabs(peak);
+        if (task_max) {
+            const unsigned long long e = task_max[task];
+            if (e == 0ull || !(fabs(o2d(e) - peak) <= tol)) return;  // (warp-uniform)
+        }
+    }
+    const float* img = maps + b * H * W;
+    const long long gx = x0 + 4 * lane;
+    const float* src = img + gx;
+    const bool fast = gx + 4 <= W && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (W & 3) == 0;
+    auto load4 = [&](long long r, float (&v)[4]) {
+        const float* p = src + r * W;
+        if (fast) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = gx + i < W ? __ldg(p + i) : 0.f;
+        }
+    };
+    double* ring = smem_d + ((size_t)warp * K * 128 + 4 * lane);  // row j of the ring: ring + j * 128
+    const int n_out = lane < kStripLanes ? (o2 - gx >= 4 ? 4 : (o2 - gx > 0 ? (int)(o2 - gx) : 0)) : 0;  // valid outputs of this lane
+    double run[4] = {0.0, 0.0, 0.0, 0.0};
+    double best = -INFINITY;
+    long long best_idx = 0x7fffffffffffffffLL;
+    const long long r_end = oy1 + K - 1;  // input rows [oy0, r_end)
+    float va[4], vb[4];
+    load4(oy0, va);
+    if (oy0 + 1 < r_end) load4(oy0 + 1, vb);
+    int slot = 0;  // ring row the current input row goes to (= the row that leaves the window)
+    for (long long r = oy0; r < r_end; ++r) {
+        double d[13];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = (double)va[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { va[i] = vb[i]; }
+        if (r + 2 < r_end) load4(r + 2, vb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            d[4 + i] = __shfl_down_sync(kFull, d[i], 1);
+            d[8 + i] = __shfl_down_sync(kFull, d[i], 2);
+        }
+        d[12] = __shfl_down_sync(kFull, d[0], 3);
+        double xs[4];
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) s += d[j];
+        xs[0] = s;
+#pragma unroll
+        for (int i = 1; i < 4; ++i) {
+            s += d[i + K - 1];
+            s -= d[i - 1];
+            xs[i] = s;
+        }
+        double* rr = ring + slot * 128;
+        if (r - oy0 >= K) {  // (warp-uniform) the x-sums of the row that leaves the window
+            const double2 o01 = *reinterpret_cast<const double2*>(rr), o23 = *reinterpret_cast<const double2*>(rr + 2);
+            run[0] -= o01.x; run[1] -= o01.y; run[2] -= o23.x; run[3] -= o23.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) run[i] += xs[i];
+        *reinterpret_cast<double2*>(rr) = make_double2(xs[0], xs[1]);
+        *reinterpret_cast<double2*>(rr + 2) = make_double2(xs[2], xs[3]);
+        slot = slot + 1 == K ? 0 : slot + 1;
+        const long long oy = r - (K - 1);
+        if (oy >= oy0) {
+            if (MODE == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < n_out) best = fmax(best, run[i]);
+            } else {
+                bool hit = false;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < n_out && fabs(run[i] - peak) <= tol) {
+                        const long long idx = oy * o2 + gx + i;
+                        if (idx < best_idx) best_idx = idx;
+                        hit = true;
+                    }
+                if (__any_sync(kFull, hit)) break;  // every later row only has larger row-major indices
+            }
+        }
+    }
+    if (MODE == 0) {
+        unsigned long long e = (n_out > 0 && oy1 > oy0) ? d2o(best) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(kFull, e, o);
+            e = other > e ? other : e;
+        }
+        if (lane == 0) {
+            if (task_max) task_max[task] = e;
+            if (e) atomicMax(max_enc + b, e);
+        }
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            long long other = __shfl_xor_sync(kFull, best_idx, o);
+            best_idx = other < best_idx ? other : best_idx;
+        }
+        if (lane == 0 && best_idx != 0x7fffffffffffffffLL) atomicMin(first + b, best_idx);
+    }
+}
+static long long strip_tasks_per_image(long long H, long long W, int K) {
+    const long long o1 = H - K + 1, o2 = W - K + 1;
+    return ((o2 + kStripCols - 1) / kStripCols) * ((o1 + kStripRows - 1) / kStripRows);
+}
+template <int K>
+static int launch_strip2d(const float* maps, long long B, long long H, long long W, unsigned long long* enc, long long* first,
+                          double scale, unsigned long long* task_max, cudaStream_t stream) {
+    const long long o1 = H - K + 1, o2 = W - K + 1;
+    const int strips = (int)((o2 + kStripCols - 1) / kStripCols), chunks = (int)((o1 + kStripRows - 1) / kStripRows);
+    const long long tasks = (long long)strips * chunks * B;
+    const size_t smem = (size_t)kStripWarps * K * 128 * sizeof(double);
+    if (cudaFuncSetAttribute(patch_strip2d<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(patch_strip2d<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return set_cuda_error("cudaFuncSetAttribute(patch_strip2d)");
+    const unsigned grid = (unsigned)((tasks + kStripWarps - 1) / kStripWarps);
+    patch_strip2d<K, 0><<<grid, kStripWarps * 32, smem, stream>>>(maps, H, W, enc, first, scale, strips, chunks, tasks, task_max);
+    patch_strip2d<K, 1><<<grid, kStripWarps * 32, smem, stream>>>(maps, H, W, enc, first, scale, strips, chunks, tasks, task_max);
+    return VU_OK;
+}
+
 template <int K>
 static void launch_patch2d(const float* maps, long long B, long long H, long long W, unsigned long long* enc, long long* first,
                            double scale, unsigned long long* tile_max, cudaStream_t stream) {
@@ -672,7 +824,10 @@ static int plane_zchunks(long long B, long long d0, long long d1, long long d2, 
 // CTAs per image of the kernel launch_patch_max picks (one workspace word each)
 long long patch_ctas_per_image(long long d0, long long d1, long long d2, int k0, int k1, int k2) {
     const long long o1 = d1 - k1 + 1, o2 = d2 - k2 + 1;
-    if (patch_uses_2d(d0, d1, k0, k1, k2)) return ((o2 + kTX - 1) / kTX) * ((o1 + kRowsPerCta - 1) / kRowsPerCta);
+    if (patch_uses_2d(d0, d1, k0, k1, k2)) {  // (sized for either 2-D kernel)
+        const long long a = ((o2 + kTX - 1) / kTX) * ((o1 + kRowsPerCta - 1) / kRowsPerCta), c = strip_tasks_per_image(d1, d2, k1);
+        return a > c ? a : c;
+    }
     if (patch_uses_plane(d0, d1, d2, k0, k1, k2)) {  // (sized for either 3-D kernel: the option can change between the two calls)
         long long a = 0;
         for (int nz = 1; nz <= kPlMaxZ; ++nz) {
@@ -697,6 +852,15 @@ int launch_patch_max(const float* maps, long long B, long long d0, long long d1,
     count_launch("patch_init");
     // 2-D maps with a square box of a specialised size: the column-marching kernel
     if (patch_uses_2d(d0, d1, k0, k1, k2)) {
+        if ((k1 == 10 || k1 == 4) && get_option("patch_path", 0) != 1 && strip_tasks_per_image(d1, d2, k1) * B < (1LL << 31)) {
+            const int rc = k1 == 10 ? launch_strip2d<10>(maps, B, d1, d2, enc, out_first, scale, tile_max, stream)
+                                    : launch_strip2d<4>(maps, B, d1, d2, enc, out_first, scale, tile_max, stream);
+            if (rc != VU_OK) return rc;
+            count_launch("patch_strip2d"); count_launch("patch_strip2d");
+            patch_finish<<<ib, 256, 0, stream>>>(enc, B, scale);
+            count_launch("patch_finish");
+            return check_launch("patch_max");
+        }
         if (k1 == 10) launch_patch2d<10>(maps, B, d1, d2, enc, out_first, scale, tile_max, stream);
         else if (k1 == 4) launch_patch2d<4>(maps, B, d1, d2, enc, out_first, scale, tile_max, stream);
         else launch_patch2d<16>(maps, B, d1, d2, enc, out_first, scale, tile_max, stream);
