@@ -416,7 +416,7 @@ typedef void (*K1Kernel_t)(const K1Params);
 // the other forms (tests/test_gpu_parity.py).
 // ---------------------------------------------------------------------------
 template <int VEC, int PMAX, int THREADS, bool MP, bool STATS>
-__global__ void __launch_bounds__(THREADS) k1_classouter(const __grid_constant__ K1Params prm) {
+__global__ void __launch_bounds__(THREADS, (!STATS && PMAX <= 16) ? 4 : 1) k1_classouter(const __grid_constant__ K1Params prm) {
     static_assert(VEC == 1 || VEC == 2, "one or two voxels per thread");
     constexpr int CH = 8;       // members whose loads are in flight together
     constexpr long long kTileVox = (long long)THREADS * VEC;
@@ -446,10 +446,13 @@ __global__ void __launch_bounds__(THREADS) k1_classouter(const __grid_constant__
             long long sp = prm.sp;
             auto base = [&](int p) { return (MP ? ld_member_ptr(prm.mptr, p) : prm.x + (long long)p * sp) + off0; };
             float h[PMAX][VEC];      // per-member entropy sums (log2 units)
+            f32x2 hp[VEC == 2 ? PMAX : 1];  // ... as packed pairs while the classes stream (VEC == 2: FADD2 / FFMA2, as k1_core.cuh)
 #pragma unroll
             for (int p = 0; p < PMAX; ++p)
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) h[p][k] = 0.f;
+#pragma unroll
+            for (int p = 0; p < (VEC == 2 ? PMAX : 1); ++p) hp[p] = 0ull;
             float best[VEC], tu2[VEC];
 #pragma unroll
             for (int k = 0; k < VEC; ++k) { best[k] = 0.f; tu2[k] = 0.f; }
@@ -461,25 +464,51 @@ __global__ void __launch_bounds__(THREADS) k1_classouter(const __grid_constant__
                 for (int k = 0; k < VEC; ++k) { m0[k] = 0.f; m1[k] = 0.f; }
                 // (requesting class c + 1 before class c is consumed was measured: the registers it takes cost more occupancy
                 //  than the loads in flight gain -- 1.3 TB/s against 1.6)
+                if constexpr (VEC == 2) {
+                    f32x2 M0 = 0ull, M1 = 0ull;
 #pragma unroll
-                for (int p0 = 0; p0 < PMAX; p0 += CH) {
-                    if (p0 < P) {
-                        float x[CH][VEC];
+                    for (int p0 = 0; p0 < PMAX; p0 += CH) {
+                        if (p0 < P) {
+                            f32x2 X[CH];
 #pragma unroll
-                        for (int j = 0; j < CH; ++j)
-                            if (p0 + j < PMAX && p0 + j < P) VecLoad<VEC>::load(base(p0 + j) + oc, x[j]);
+                            for (int j = 0; j < CH; ++j)
+                                if (p0 + j < PMAX && p0 + j < P) PairLoad<2>::load(base(p0 + j) + oc, &X[j]);
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) {
-                            const int p = p0 + j;
-                            if (p < PMAX && p < P) {
-#pragma unroll
-                                for (int k = 0; k < VEC; ++k) {
-                                    m0[k] = __fadd_rn(m0[k], x[j][k]);
-                                    h[p][k] = plog2p_acc(h[p][k], x[j][k]);
+                            for (int j = 0; j < CH; ++j) {
+                                const int p = p0 + j;
+                                if (p < PMAX && p < P) {
+                                    M0 = add2(M0, X[j]);
+                                    f32x2 PC, L;
+                                    plog2p_parts2(X[j], PC, L);
+                                    hp[p] = fma2(PC, L, hp[p]);
+                                    if ((p & 15) == 15 && two) { M1 = add2(M1, M0); M0 = 0ull; }
                                 }
-                                if ((p & 15) == 15 && two) {
+                            }
+                        }
+                    }
+                    upk2(M0, m0[0], m0[VEC - 1]);
+                    upk2(M1, m1[0], m1[VEC - 1]);
+                } else {
 #pragma unroll
-                                    for (int k = 0; k < VEC; ++k) { m1[k] = __fadd_rn(m1[k], m0[k]); m0[k] = 0.f; }
+                    for (int p0 = 0; p0 < PMAX; p0 += CH) {
+                        if (p0 < P) {
+                            float x[CH][VEC];
+#pragma unroll
+                            for (int j = 0; j < CH; ++j)
+                                if (p0 + j < PMAX && p0 + j < P) VecLoad<VEC>::load(base(p0 + j) + oc, x[j]);
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) {
+                                const int p = p0 + j;
+                                if (p < PMAX && p < P) {
+#pragma unroll
+                                    for (int k = 0; k < VEC; ++k) {
+                                        m0[k] = __fadd_rn(m0[k], x[j][k]);
+                                        h[p][k] = plog2p_acc(h[p][k], x[j][k]);
+                                    }
+                                    if ((p & 15) == 15 && two) {
+#pragma unroll
+                                        for (int k = 0; k < VEC; ++k) { m1[k] = __fadd_rn(m1[k], m0[k]); m0[k] = 0.f; }
+                                    }
                                 }
                             }
                         }
@@ -492,6 +521,10 @@ __global__ void __launch_bounds__(THREADS) k1_classouter(const __grid_constant__
                     if (c == 0) { best[k] = mean; label[k] = 0; } else argmax_step(mean, c, best[k], label[k]);
                     tu2[k] = plog2p_acc(tu2[k], mean);
                 }
+            }
+            if constexpr (VEC == 2) {
+#pragma unroll
+                for (int p = 0; p < PMAX; ++p) upk2(hp[p], h[p][0], h[p][VEC - 1]);
             }
             // AU: the mean over the members of their entropies, in the same cascade order
 #pragma unroll
