@@ -135,8 +135,8 @@ def bench_k4():
 
 def bench_generic():
     """Class counts without a compiled-in fast / TMA form (anything but C = 2, 3, 4, 19) run on the class-outer kernel
-    (k1_classouter: run-time C, P <= 32; r02u: the generic kernel they used to fall to reached 0.5 TB/s), unaligned rows on the
-    one-voxel-per-thread register form: throughput of the fused pass without statistics."""
+    (k1_co_tma / k1_classouter: run-time C, P <= 32; r02u: the generic kernel they used to fall to reached 0.5 TB/s), unaligned
+    rows on the one-voxel-per-thread register form: throughput of the fused pass without statistics."""
     peak = 6532.2
     for name, P, C, shape, B in (("C=5  N=10 512x512", 10, 5, (512, 512), 8), ("C=7  N=10 512x512", 10, 7, (512, 512), 8),
                                  ("C=21 N=10 512x512", 10, 21, (512, 512), 4), ("C=19 N=10 511x513 (unaligned rows)", 10, 19, (511, 513), 4)):

@@ -19,7 +19,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libvalunc.so")
-SOURCES = ["abi.cu", "k1_fused.cu", "k1_tma.cu", "k1_uni.cu", "k2_spatial.cu", "k3_map_stats.cu", "k4_quantile.cu", "k5_members.cu", "synth.cu"]
+SOURCES = ["abi.cu", "k1_fused.cu", "k1_tma.cu", "k1_uni.cu", "k1_co_tma.cu", "k2_spatial.cu", "k3_map_stats.cu", "k4_quantile.cu", "k5_members.cu", "synth.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",

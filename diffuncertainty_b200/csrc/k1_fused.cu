@@ -690,7 +690,12 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
         return check_launch("k1_fast");
     }
 
-    // any other class count (and whatever else has no compiled-in form): the class-outer kernel, P <= 32, unit voxel stride
+    // any other class count (and whatever else has no compiled-in form): the class-outer kernels, P <= 32, unit voxel stride --
+    // rows through the TMA ring when they are 16-byte aligned and no statistics are asked for (k1_co_tma.cu), else direct loads
+    if (forced == -1 && !produced && !lg && s.C != 2 && s.C != 3 && s.C != 4 && s.C != 19) {
+        const int rc = launch_k1_co_tma(a, st, stream);
+        if (rc <= 0) return rc;
+    }
     if (s.stride_v == 1 && s.P >= 2 && s.P <= 32 && !produced && !lg && forced != -2 && !a->member_labels) {
         constexpr int T = 256;
 #define VU_CO(VEC, PMAX)                                                                                              \

@@ -23,6 +23,7 @@ int device_sm_count();
 int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream);
 int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t stream);  // 1 = not eligible
 int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t stream, bool dry_run = false);  // 1 = not eligible
+int launch_k1_co_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t stream);  // class-outer TMA form; 1 = not eligible
 int num_tma_variants();
 int num_fast_variants();
 int describe_fast_variant(int i, int* out7);

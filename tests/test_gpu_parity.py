@@ -796,8 +796,17 @@ def test_classouter_kernel_equals_generic_and_oracle(vu, P, B, C, spatial):
     before = _lib.get_counter("launches.k1_classouter")
     co = vu.fused_pass(x.cuda(), vu.GroundTruth(gt.cuda(), None), stats=flags)
     assert _lib.get_counter("launches.k1_classouter") == before + 1 or C in (2, 3, 4, 19)
-    lst = vu.fused_pass([x[p].cuda() for p in range(P)])  # the member-list form of the same kernel
-    assert torch.equal(lst.labels, co.labels) and torch.equal(lst.maps["EU"], co.maps["EU"])
+    # without statistics and with 16-byte aligned rows the rows go through the TMA ring (k1_co_tma): same bits, also from a
+    # member list
+    before_tma = _lib.get_counter("launches.k1_co_tma")
+    plain = vu.fused_pass(x.cuda())
+    lst = vu.fused_pass([x[p].cuda() for p in range(P)])
+    if int(np.prod(spatial)) % 4 == 0 and C not in (2, 3, 4, 19):
+        assert _lib.get_counter("launches.k1_co_tma") == before_tma + 2
+    for r in (plain, lst):
+        assert torch.equal(r.labels, co.labels)
+        for k in ("TU", "AU", "EU"):
+            assert torch.equal(r.maps[k].view(torch.int32), co.maps[k].view(torch.int32)), k
     _lib.load().vu_set_option(b"k1_variant", -2)
     try:
         gen = vu.fused_pass(x.cuda(), vu.GroundTruth(gt.cuda(), None), stats=flags, want_member_labels=True)
