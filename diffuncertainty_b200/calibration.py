@@ -625,6 +625,12 @@ def eqace_from_maps_batch(reference_segs, pred_seg, unc_maps, platt, ignore_valu
     if refs.shape[2] != V or pred.shape[1] != V or any(m.numel() != B * V for m in maps):
         raise ValueError("references, prediction and maps must cover the same voxels")
     R = refs.shape[1]
+    max_seg = 96  # 1 MB of histogram workspace per segment: larger batches go through in slices
+    if n_maps * B > max_seg:
+        step = max(1, max_seg // n_maps)
+        parts = [eqace_from_maps_batch(refs[s:s + step], pred[s:s + step], [m[s:s + step] for m in maps], platt, ignore_value, n_bins)
+                 for s in range(0, B, step)]
+        return np.concatenate(parts, axis=1)
     n_seg = n_maps * B
     hist, state, state_host, cal_host, cal_dev = _eq_workspace(dev, n_seg)
     stream = _lib.current_stream_ptr()

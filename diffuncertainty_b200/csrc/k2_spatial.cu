@@ -427,7 +427,8 @@ __global__ void __launch_bounds__(kPlThreads, 2) patch_plane(const float* __rest
         }
         // the slice kPlAhead further on goes to L2 now (the leaving slice was read K slices ago and is still there): the register
         // loads above, issued one slice ahead, then only have L2 latency to hide -- every warp of the CTA waits at the same time
-        if (row_in && z + kPlAhead < z_last && l8 < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (z + kPlAhead) * plane + (l8 ? 32 - xseg : 0)));
+        if (row_in && z + kPlAhead < z_last && l8 < 2 && tx0 + 32 * l8 < d2)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (z + kPlAhead) * plane + (l8 ? 32 - xseg : 0)));
         if (z - z_first < K - 1) continue;  // uniform: the window is not full yet
         const int buf = (int)(z & 1);
         {

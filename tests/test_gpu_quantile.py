@@ -170,3 +170,21 @@ def test_eqace_batch_equals_per_image_and_oracle():
             correct, conf = oracle.calibration_inputs(refs[i], pred[i], maps[m][i], a, b, 255)
             np.testing.assert_allclose(got[m, i], oracle.calc_eqace(correct, conf), rtol=1e-5, atol=1e-6)
     assert np.isnan(got[:, 3]).all()
+
+
+def test_eqace_batch_slices_large_batches():
+    """more than 96 segments: the batch goes through in slices (1 MB of histogram workspace per segment), same values"""
+    import torch
+    from diffuncertainty_b200 import calibration
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, shape, R = 40, (16, 32), 2
+    pred = (torch.rand((B,) + shape, device="cuda", generator=g) < 0.4).to(torch.uint8)
+    refs = (torch.rand((B, R) + shape, device="cuda", generator=g) < 0.4).to(torch.uint8)
+    maps = [torch.rand((B,) + shape, device="cuda", generator=g) ** (k + 1) for k in range(3)]
+    platt = [(3.5, -1.25), (-2.0, 0.5), (6.0, -2.0)]
+    got = calibration.eqace_from_maps_batch(refs, pred, maps, platt)
+    assert got.shape == (3, B)
+    for m in range(3):
+        for i in (0, 31, 32, 39):
+            one = calibration.eqace_from_maps(refs[i], pred[i], maps[m][i], *platt[m])
+            assert one == got[m, i], (m, i, one, got[m, i])
