@@ -200,10 +200,11 @@ def test_logits_label_flip_rate_and_map_error(vu):
     """The measured numbers of the relaxed contract on BASELINE-shaped inputs (cfg 5: N = 16, C = 19; cfg 1: N = 10, C = 2;
     peaked variant): label flips against the reference's labels and the largest map error relative to max(|TU|, |AU|)."""
     stats = []
-    for name, P, C, spatial, scale in (("cfg5-shaped", 16, 19, (128, 256), 3.0), ("cfg5 peaked", 16, 19, (128, 256), 8.0),
-                                       ("cfg1-shaped", 10, 2, (256, 256), 2.0), ("cfg4-shaped", 32, 2, (128, 128), 4.0)):
+    for name, P, C, spatial, scale, B in (("cfg5-shaped", 16, 19, (128, 256), 3.0, 2), ("cfg5 peaked", 16, 19, (128, 256), 8.0, 2),
+                                          ("cfg1-shaped", 10, 2, (256, 256), 2.0, 2), ("cfg4-shaped", 32, 2, (128, 128), 4.0, 2),
+                                          ("cfg5 full size (one 512x1024 image)", 16, 19, (512, 1024), 4.0, 1)):
         g = torch.Generator().manual_seed(len(name))
-        logits = scale * torch.randn(P, 2, C, *spatial, generator=g)
+        logits = scale * torch.randn(P, B, C, *spatial, generator=g)
         res = vu.fused_pass(logits.cuda(), logits=True)
         check_against_reference(res, logits, name, stats)
     total = sum(s["voxels"] for s in stats)
