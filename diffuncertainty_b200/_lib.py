@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(PKG, "lib", "libvalunc.so")
 
 VU_OK = 0
 VU_ERR_BAD_ARG, VU_ERR_UNSUPPORTED, VU_ERR_CUDA, VU_ERR_NO_DEVICE = -1, -2, -3, -4
-VU_ABI_VERSION = 3
+VU_ABI_VERSION = 4
 N_UNC, N_BINS, N_EDGES, MAX_RATERS = 3, 21, 19, 8
 GT_U8, GT_I64 = 0, 1
 STAT_IMAGE_SUM, STAT_THRESHOLD, STAT_AREA, STAT_DICE, STAT_CALIB, STAT_NCC, STAT_PLATT_FIT = 1, 2, 4, 8, 16, 32, 64

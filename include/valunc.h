@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VU_ABI_VERSION 3
+#define VU_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define VU_API __attribute__((visibility("default")))
