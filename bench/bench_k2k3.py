@@ -147,6 +147,17 @@ def bench_generic():
         ms = time_call(lambda: vu.fused_pass(x, maps_out=maps, labels_out=labels), iters=5)
         nbytes = (4 * P * C + 13) * V * B
         print(f"other class counts {name:36s} {ms:8.3f} ms  {nbytes / ms / 1e6:8.1f} GB/s = {nbytes / ms / 1e6 / peak:5.3f} of the HBM peak", flush=True)
+        if C == 21:  # ... and with reference-based statistics in the same pass (general statistics form)
+            gt = vu.GroundTruth(synth.synth_gt(x, 1, seed=3, flip=0.2, ignore_frac=0.02, ignore_value=255), 255)
+            sf = torch.zeros((B, 80), dtype=torch.float64, device="cuda")
+            si = torch.zeros((B, 156), dtype=torch.int64, device="cuda")
+            platt = [calibration.platt_edges(a, b) for a, b in ((3.5, -1.25), (6.0, -2.0), (40.0, -0.5))]
+            for fl in (0x0f, 0x1f):
+                ms = time_call(lambda: vu.fused_pass(x, gt, stats=fl, thresholds=[0.3, 0.2, 0.02], calib=platt if fl & 0x10 else None,
+                                                     stats_out=(sf, si), maps_out=maps, labels_out=labels), iters=5)
+                nb2 = (4 * P * C + 14) * V * B
+                print(f"other class counts {name + f' + statistics {fl:#x}':36s} {ms:8.3f} ms  {nb2 / ms / 1e6:8.1f} GB/s = {nb2 / ms / 1e6 / peak:5.3f} of the HBM peak",
+                      flush=True)
         del x
 
 

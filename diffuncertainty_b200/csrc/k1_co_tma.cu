@@ -8,8 +8,9 @@
 // of that class (TV voxels each, one cp.async.bulk per row) into a ring stage; the consumer threads own VEC = 2 voxels each and
 // do exactly what k1_classouter does -- class mean finished in registers, per-member entropy sums in registers (member loop
 // unrolled to PMAX), same operations in the same order as every other form (bit-identical maps and labels).
-// The (tile, class) pairs of a CTA form one flat sequence, so the ring never drains between tiles.  No statistics phase
-// (launches with statistics keep the direct-load form).
+// The (tile, class) pairs of a CTA form one flat sequence, so the ring never drains between tiles.  With statistics the
+// consumer threads run the general statistics phase (vu_common.cuh) on their two voxels after the last class of a tile, on a
+// named barrier of their own (the producer warp takes no part), as the register-streaming kernel does.
 //
 // Reference semantics: see k1_fused.cu / k1_core.cuh.
 #include "k1_core.cuh"
@@ -31,10 +32,11 @@ struct K1CoParams {
     uint8_t* lab;
     long long tiles_per_img, total_tiles;
     int nstages;
-    unsigned bar_offset;
+    unsigned bar_offset, stats_offset;
+    StatParams st;
 };
 
-template <int PMAX, int CT>
+template <int PMAX, int CT, bool STATS>
 __global__ void __launch_bounds__(CT + 32, 1) k1_co_tma(const __grid_constant__ K1CoParams prm) {
     constexpr int VEC = 2, TV = CT * VEC;
     constexpr unsigned kRowBytes = TV * sizeof(float);
@@ -92,10 +94,17 @@ __global__ void __launch_bounds__(CT + 32, 1) k1_co_tma(const __grid_constant__ 
     int stage = 0;
     unsigned phase = 0;
     const unsigned my_ring = smem_u32(vu_co_smem) + (unsigned)tid * (VEC * (unsigned)sizeof(float));
+    void* st_smem = vu_co_smem + prm.stats_offset;
+    StatsCursor<CT> cursor;
+    if (STATS) stats_init<CT, 1, 0, 16>(prm.st, st_smem);
     for (int tile = t0; tile < t1; ++tile) {
         if (++vt == tpi) { vt = 0; ++b; }
         const long long v = (long long)vt * TV + (long long)tid * VEC;
         const bool active = v < V;
+        if (STATS) {
+            cursor.template enter<1, 0, 16>(prm.st, st_smem, b, vt, TV);
+            if (active) stats_prefetch_gt<VEC>(prm.st, b, v);
+        }
         f32x2 hp[PMAX];  // per-member entropy sums of the two voxels (log2 units)
 #pragma unroll
         for (int p = 0; p < PMAX; ++p) hp[p] = 0ull;
@@ -132,8 +141,8 @@ __global__ void __launch_bounds__(CT + 32, 1) k1_co_tma(const __grid_constant__ 
                 tu2[k] = plog2p_acc(tu2[k], mean);
             }
         }
+        float u[VU_N_UNC][VEC] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
         if (active) {
-            float u[VU_N_UNC][VEC];
             float h[PMAX][VEC];
 #pragma unroll
             for (int p = 0; p < PMAX; ++p) upk2(hp[p], h[p][0], h[p][1]);
@@ -158,15 +167,19 @@ __global__ void __launch_bounds__(CT + 32, 1) k1_co_tma(const __grid_constant__ 
             if (prm.au) VecLoad<VEC>::store(prm.au + o, u[1]);
             if (prm.eu) VecLoad<VEC>::store(prm.eu + o, u[2]);
             if (prm.lab) VecLoad<VEC>::store_u8(prm.lab + o, label);
+        } else {
+            label[0] = label[1] = 0;
         }
+        if (STATS) stats_tile<VEC, CT, 0, 16>(prm.st, st_smem, active, b, v, u, label);
     }
+    if (STATS && t1 > t0) cursor.template finish<1, 0, 16>(prm.st, st_smem, vt, TV);
 }
 
 // Returns VU_OK after launching, 1 if this launch is not one for this form (caller goes on), or a negative vu_status.
 int launch_k1_co_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t stream) {
     const vu_slab& s = a->slab;
     if (get_option("k1_path", 0) == 1 || get_option("k1_variant", -1) != -1) return 1;
-    if (st.flags || a->member_labels || s.draws > 1 || s.flags) return 1;
+    if (a->member_labels || s.draws > 1 || s.flags) return 1;
     if (s.stride_v != 1 || s.P < 2 || s.P > 32) return 1;
     // bulk copies need 16-byte aligned rows and sizes
     if ((uintptr_t)s.data % 16 || s.V % 4 || (!s.member_ptrs && s.stride_p % 4) || s.stride_b % 4 || s.stride_c % 4) return 1;
@@ -177,10 +190,14 @@ int launch_k1_co_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t 
     if (!ok(a->tu, 8) || !ok(a->au, 8) || !ok(a->eu, 8) || !ok(a->labels, 2)) return 1;
 
     typedef void (*Fn)(const K1CoParams);
-    // 512 consumer threads (4 KB rows) while the registers allow it, 256 (2 KB rows) for up to 32 members
-    const int ct = s.P <= 16 ? 512 : 256;
-    Fn fn = s.P <= 8 ? (Fn)k1_co_tma<8, 512> : (s.P <= 16 ? (Fn)k1_co_tma<16, 512> : (Fn)k1_co_tma<32, 256>);
+    // 512 consumer threads (4 KB rows) while the registers allow it, 256 (2 KB rows) for up to 32 members and with statistics
+    // (whose per-thread columns and per-warp histograms share the shared memory with the ring)
+    const bool stats = st.flags != 0;
+    const int ct = (s.P <= 16 && !stats) ? 512 : 256;
+    Fn fn = stats ? (s.P <= 8 ? (Fn)k1_co_tma<8, 256, true> : (s.P <= 16 ? (Fn)k1_co_tma<16, 256, true> : (Fn)k1_co_tma<32, 256, true>))
+                  : (s.P <= 8 ? (Fn)k1_co_tma<8, 512, false> : (s.P <= 16 ? (Fn)k1_co_tma<16, 512, false> : (Fn)k1_co_tma<32, 256, false>));
     K1CoParams prm;
+    prm.st = st;
     prm.x = s.data; prm.mptr = s.member_ptrs;
     prm.P = s.P; prm.B = s.B; prm.C = s.C; prm.V = s.V;
     prm.sp = s.stride_p; prm.sb = s.stride_b; prm.sc = s.stride_c;
@@ -190,13 +207,16 @@ int launch_k1_co_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t 
     prm.total_tiles = prm.tiles_per_img * s.B;
     if (prm.total_tiles >= (1LL << 31)) return set_error(VU_ERR_UNSUPPORTED, "more than 2^31 tiles in one launch; split the batch");
     const size_t stage_bytes = (size_t)s.P * tile_vox * sizeof(float);
+    const size_t stats_bytes = stats ? (stats_smem_bytes(st.flags, st.gt.R, ct) + stats_class_bytes(st.flags, st.gt.R, st.ncls) + 127) / 128 * 128 : 0;
     const size_t budget = 225 * 1024 - 512;
-    long long nstages = (long long)(budget / stage_bytes);
+    if (stats_bytes + 2 * stage_bytes > budget) return 1;
+    long long nstages = (long long)((budget - stats_bytes) / stage_bytes);
     if (nstages > 8) nstages = 8;
     if (nstages < 2) return 1;
     prm.nstages = (int)nstages;
     prm.bar_offset = (unsigned)(nstages * stage_bytes);
-    const size_t dyn = nstages * stage_bytes + 256;
+    prm.stats_offset = (unsigned)(nstages * stage_bytes + 256);
+    const size_t dyn = nstages * stage_bytes + 256 + stats_bytes;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
         return set_cuda_error("cudaFuncSetAttribute(k1_co_tma)");
     long long grid = device_sm_count();

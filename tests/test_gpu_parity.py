@@ -793,20 +793,29 @@ def test_classouter_kernel_equals_generic_and_oracle(vu, P, B, C, spatial):
     x[1, 0, 0, 0, 5] = float("nan")
     gt = torch.randint(0, min(C, 250), (B, 2, *spatial), generator=g, dtype=torch.uint8)
     flags = _lib.STAT_IMAGE_SUM | _lib.STAT_AREA | _lib.STAT_DICE | _lib.STAT_CLASS_COUNTS
+    aligned = int(np.prod(spatial)) % 4 == 0 and C not in (2, 3, 4, 19)
+    # the direct-load form (option k1_path = 1 keeps the TMA forms out)
     before = _lib.get_counter("launches.k1_classouter")
-    co = vu.fused_pass(x.cuda(), vu.GroundTruth(gt.cuda(), None), stats=flags)
+    _lib.load().vu_set_option(b"k1_path", 1)
+    try:
+        co = vu.fused_pass(x.cuda(), vu.GroundTruth(gt.cuda(), None), stats=flags)
+    finally:
+        _lib.load().vu_set_option(b"k1_path", 0)
     assert _lib.get_counter("launches.k1_classouter") == before + 1 or C in (2, 3, 4, 19)
-    # without statistics and with 16-byte aligned rows the rows go through the TMA ring (k1_co_tma): same bits, also from a
-    # member list
+    # with 16-byte aligned rows the rows go through the TMA ring (k1_co_tma) -- with statistics, without, and from a member
+    # list: same bits
     before_tma = _lib.get_counter("launches.k1_co_tma")
+    tma = vu.fused_pass(x.cuda(), vu.GroundTruth(gt.cuda(), None), stats=flags)
     plain = vu.fused_pass(x.cuda())
     lst = vu.fused_pass([x[p].cuda() for p in range(P)])
-    if int(np.prod(spatial)) % 4 == 0 and C not in (2, 3, 4, 19):
-        assert _lib.get_counter("launches.k1_co_tma") == before_tma + 2
-    for r in (plain, lst):
+    if aligned:
+        assert _lib.get_counter("launches.k1_co_tma") == before_tma + 3
+    for r in (tma, plain, lst):
         assert torch.equal(r.labels, co.labels)
         for k in ("TU", "AU", "EU"):
             assert torch.equal(r.maps[k].view(torch.int32), co.maps[k].view(torch.int32)), k
+    assert torch.equal(tma.stats_i64, co.stats_i64) and torch.equal(tma.class_counts, co.class_counts)
+    np.testing.assert_allclose(tma.stats_f64.cpu().numpy(), co.stats_f64.cpu().numpy(), rtol=1e-7)
     _lib.load().vu_set_option(b"k1_variant", -2)
     try:
         gen = vu.fused_pass(x.cuda(), vu.GroundTruth(gt.cuda(), None), stats=flags, want_member_labels=True)
