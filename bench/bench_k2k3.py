@@ -161,7 +161,26 @@ def bench_generic():
         del x
 
 
+def bench_half():
+    """A cfg5-shaped slab in bfloat16 (autocast output) read as it is (vu_slab.dtype, class-outer TMA form) against what the
+    wrapper did before: upcast copy + the float32 pass."""
+    peak = 6532.2
+    P, C, shape, B = 16, 19, (512, 1024), 8
+    x32 = synth.synth_slab(P, B, C, shape, seed=5, scale=3.0)
+    x16 = x32.to(torch.bfloat16)
+    V = shape[0] * shape[1]
+    maps = {k: torch.empty((B,) + shape, dtype=torch.float32, device="cuda") for k in ("TU", "AU", "EU")}
+    labels = torch.empty((B,) + shape, dtype=torch.uint8, device="cuda")
+    ms16 = time_call(lambda: vu.fused_pass(x16, maps_out=maps, labels_out=labels), iters=5)
+    ms32 = time_call(lambda: vu.fused_pass(x32, maps_out=maps, labels_out=labels), iters=5)
+    msup = time_call(lambda: vu.fused_pass(x16.float(), maps_out=maps, labels_out=labels), iters=5)
+    nb16, nb32 = (2 * P * C + 13) * V * B, (4 * P * C + 13) * V * B
+    print(f"bf16 slab N=16 C=19 512x1024 B={B}: read as it is {ms16:7.3f} ms ({nb16 / ms16 / 1e6:7.1f} GB/s = {nb16 / ms16 / 1e6 / peak:5.3f} of the HBM peak, "
+          f"{P * V * B / ms16 / 1e6:6.1f} G sample-voxels/s); upcast copy + float32 pass {msup:7.3f} ms; float32 slab {ms32:7.3f} ms", flush=True)
+
+
 if __name__ == "__main__":
     main()
     bench_k4()
     bench_generic()
+    bench_half()

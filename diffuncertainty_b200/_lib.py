@@ -21,6 +21,7 @@ STAT_IMAGE_SUM, STAT_THRESHOLD, STAT_AREA, STAT_DICE, STAT_CALIB, STAT_NCC, STAT
 STAT_CLASS_COUNTS = 128
 N_PLATT_BINS = 256
 SLAB_RENORMALIZE, SLAB_DISCRETIZE, SLAB_LOGITS = 1, 2, 4
+SLAB_F32, SLAB_BF16, SLAB_F16 = 0, 1, 2
 STAT_ALL_NO_GT = STAT_IMAGE_SUM | STAT_THRESHOLD | STAT_AREA
 
 # column layout of the per-image rows (keep in sync with valunc.h; checked in tests/test_abi.py)
@@ -33,7 +34,7 @@ class Slab(C.Structure):
     _fields_ = [("data", C.c_void_p), ("P", C.c_int64), ("B", C.c_int64), ("C", C.c_int64), ("V", C.c_int64),
                 ("stride_p", C.c_int64), ("stride_b", C.c_int64), ("stride_c", C.c_int64), ("stride_v", C.c_int64),
                 ("member_ptrs", C.c_void_p), ("member_ptrs_host", C.c_void_p),
-                ("stride_d", C.c_int64), ("draws", C.c_int32), ("flags", C.c_uint32), ("renorm_eps", C.c_float)]
+                ("stride_d", C.c_int64), ("draws", C.c_int32), ("flags", C.c_uint32), ("renorm_eps", C.c_float), ("dtype", C.c_int32)]
 
 
 class Gt(C.Structure):

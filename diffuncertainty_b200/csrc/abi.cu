@@ -203,6 +203,11 @@ static int fused_pass_checked(const vu_fused_args* a, void* stream) {
     if (s.B == 0 || s.V == 0) return VU_OK;  // empty batch: nothing to do (its data pointer may be NULL)
     if (s.draws < 0 || s.draws > 4096 || (s.flags & ~(VU_SLAB_RENORMALIZE | VU_SLAB_DISCRETIZE | VU_SLAB_LOGITS)))
         return set_error(VU_ERR_BAD_ARG, "slab.draws / slab.flags");
+    if (s.dtype != VU_SLAB_F32) {
+        if (s.dtype != VU_SLAB_BF16 && s.dtype != VU_SLAB_F16) return set_error(VU_ERR_BAD_ARG, "slab.dtype");
+        if (s.draws > 1 || s.flags || a->members.flags || a->member_labels)
+            return set_error(VU_ERR_UNSUPPORTED, "16-bit slabs: plain slabs only (no draws / producer flags / member labels / member scores); upcast");
+    }
     if ((s.draws > 1 || s.flags) && a->members.flags)
         return set_error(VU_ERR_UNSUPPORTED, "member scores in the fused pass are not available for grouped / renormalised / discretised slabs");
     const int64_t n_ptrs = s.P * (s.draws > 1 ? s.draws : 1);
@@ -224,6 +229,10 @@ static int fused_pass_checked(const vu_fused_args* a, void* stream) {
         if (a->stat_flags == 0) return set_error(VU_ERR_UNSUPPORTED, "member scores in the fused pass need a statistics mask (e.g. VU_STAT_IMAGE_SUM)");
         rc = launch_k1_uni(a, st, (cudaStream_t)stream);
         return rc == 1 ? set_error(VU_ERR_UNSUPPORTED, "member scores in the fused pass: launch not eligible") : rc;
+    }
+    if (s.dtype != VU_SLAB_F32) {  // 16-bit slabs: the class-outer TMA form reads them (k1_co_tma.cu)
+        rc = launch_k1_co_tma(a, st, (cudaStream_t)stream);
+        return rc == 1 ? set_error(VU_ERR_UNSUPPORTED, "16-bit slab not eligible (2..32 members, unit voxel stride, 16-byte aligned rows); upcast") : rc;
     }
     return launch_k1(a, st, (cudaStream_t)stream);
 }
@@ -472,7 +481,8 @@ int vu_member_scores(const vu_member_scores_args* a, void* stream) {
     if (!(a->flags & (VU_MS_NLL | VU_MS_GED)) || (a->flags & ~(VU_MS_NLL | VU_MS_GED))) return set_error(VU_ERR_BAD_ARG, "flags");
     if ((a->flags & VU_MS_GED) && s.C != 2) return set_error(VU_ERR_BAD_ARG, "GED counts need C == 2 (ged_fast.py:33)");
     if ((a->flags & VU_MS_GED) && s.P > 32) return set_error(VU_ERR_UNSUPPORTED, "GED counts need P <= 32");
-    if (s.draws > 1 || s.flags) return set_error(VU_ERR_UNSUPPORTED, "member scores take the members as they are (no draws / producer flags)");
+    if (s.draws > 1 || s.flags || s.dtype != VU_SLAB_F32)
+        return set_error(VU_ERR_UNSUPPORTED, "member scores take float32 members as they are (no draws / producer flags / 16-bit slabs)");
     if (s.B == 0 || s.V == 0) return VU_OK;
     if (s.member_ptrs || s.member_ptrs_host) {
         if (!s.member_ptrs || !s.member_ptrs_host)

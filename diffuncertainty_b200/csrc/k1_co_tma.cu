@@ -12,17 +12,23 @@
 // consumer threads run the general statistics phase (vu_common.cuh) on their two voxels after the last class of a tile, on a
 // named barrier of their own (the producer warp takes no part), as the register-streaming kernel does.
 //
+// ET: element type of the slab -- 0 float32, 1 bfloat16, 2 float16 (vu_slab.dtype).  16-bit rows are copied as they are (half
+// the bytes) and widened to float32 by the consumers as they read the stage: exact, so the results are those of the upcast slab
+// bit for bit.  This form is the one that reads 16-bit slabs, for every class count.  (Two CTAs per SM were measured for
+// P <= 16: +5 % for C = 5 / 7, -4 % for C = 21, nothing for 16-bit slabs -- one CTA per SM it stays.)
+//
 // Reference semantics: see k1_fused.cu / k1_core.cuh.
 #include "k1_core.cuh"
 #include "tma_common.cuh"
 #include "vu_host.h"
+#include <type_traits>
 
 namespace vu {
 
 extern __shared__ __align__(128) unsigned char vu_co_smem[];
 
 struct K1CoParams {
-    const float* x;
+    const float* x;  // (16-bit elements when ET != 0; strides are in elements)
     const float* const* mptr;
     long long P, B, C, V;
     long long sp, sb, sc;
@@ -36,10 +42,20 @@ struct K1CoParams {
     StatParams st;
 };
 
-template <int PMAX, int CT, bool STATS>
+// two voxels of a 16-bit row -> packed float32 pair
+template <int ET>
+__device__ __forceinline__ f32x2 widen2(unsigned w) {
+    if (ET == 1) return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));  // bfloat16: the upper half of a float32
+    float lo, hi;
+    asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(lo), "=f"(hi) : "r"(w));
+    return pk2(lo, hi);
+}
+
+template <int PMAX, int CT, bool STATS, int ET>
 __global__ void __launch_bounds__(CT + 32, 1) k1_co_tma(const __grid_constant__ K1CoParams prm) {
     constexpr int VEC = 2, TV = CT * VEC;
-    constexpr unsigned kRowBytes = TV * sizeof(float);
+    constexpr unsigned kEs = ET == 0 ? 4u : 2u;  // bytes per element
+    constexpr unsigned kRowBytes = TV * kEs;
     const int P = (int)prm.P, C = (int)prm.C;
     const long long V = prm.V;
     const unsigned stage_bytes = (unsigned)P * kRowBytes;
@@ -70,7 +86,7 @@ __global__ void __launch_bounds__(CT + 32, 1) k1_co_tma(const __grid_constant__ 
         for (int tile = t0; tile < t1; ++tile) {
             if (++vt == tpi) { vt = 0; ++b; }
             const long long v0 = (long long)vt * TV, left = V - v0;
-            const unsigned row_bytes = left >= TV ? kRowBytes : (unsigned)(left * sizeof(float));
+            const unsigned row_bytes = left >= TV ? kRowBytes : (unsigned)(left * kEs);
             const long long off0 = (long long)b * prm.sb + v0;
             for (int c = 0; c < C; ++c) {
                 mbar_wait_hint(empty0 + 8 * stage, phase ^ 1, 2000u);
@@ -78,8 +94,10 @@ __global__ void __launch_bounds__(CT + 32, 1) k1_co_tma(const __grid_constant__ 
                 __syncwarp();
                 const unsigned dst0 = smem_u32(vu_co_smem) + (unsigned)stage * stage_bytes;
                 for (int p = lane; p < P; p += 32) {
-                    const float* mem = prm.mptr ? ld_member_ptr(prm.mptr, p) : prm.x + (long long)p * prm.sp;
-                    bulk_g2s(dst0 + (unsigned)p * kRowBytes, mem + off0 + (long long)c * prm.sc, row_bytes, full0 + 8 * stage, policy);
+                    // (byte arithmetic: the elements are 2 or 4 bytes wide)
+                    const char* mem = prm.mptr ? reinterpret_cast<const char*>(ld_member_ptr(prm.mptr, p))
+                                               : reinterpret_cast<const char*>(prm.x) + (long long)p * prm.sp * kEs;
+                    bulk_g2s(dst0 + (unsigned)p * kRowBytes, mem + (off0 + (long long)c * prm.sc) * kEs, row_bytes, full0 + 8 * stage, policy);
                 }
                 if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
@@ -93,7 +111,7 @@ __global__ void __launch_bounds__(CT + 32, 1) k1_co_tma(const __grid_constant__ 
     int b = t0 / tpi, vt = t0 - b * tpi - 1;
     int stage = 0;
     unsigned phase = 0;
-    const unsigned my_ring = smem_u32(vu_co_smem) + (unsigned)tid * (VEC * (unsigned)sizeof(float));
+    const unsigned my_ring = smem_u32(vu_co_smem) + (unsigned)tid * (VEC * kEs);
     void* st_smem = vu_co_smem + prm.stats_offset;
     StatsCursor<CT> cursor;
     if (STATS) stats_init<CT, 1, 0, 16>(prm.st, st_smem);
@@ -119,7 +137,13 @@ __global__ void __launch_bounds__(CT + 32, 1) k1_co_tma(const __grid_constant__ 
             for (int p = 0; p < PMAX; ++p) {
                 if (p < P) {
                     f32x2 X;
-                    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(X) : "r"(src + (unsigned)p * kRowBytes));
+                    if constexpr (ET == 0) {
+                        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(X) : "r"(src + (unsigned)p * kRowBytes));
+                    } else {
+                        unsigned w;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(src + (unsigned)p * kRowBytes));
+                        X = widen2<ET>(w);
+                    }
                     M0 = add2(M0, X);
                     f32x2 PC, L;
                     plog2p_parts2(X, PC, L);
@@ -181,8 +205,10 @@ int launch_k1_co_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t 
     if (get_option("k1_path", 0) == 1 || get_option("k1_variant", -1) != -1) return 1;
     if (a->member_labels || s.draws > 1 || s.flags) return 1;
     if (s.stride_v != 1 || s.P < 2 || s.P > 32) return 1;
+    const int et = s.dtype;  // 0 float32, 1 bfloat16, 2 float16
+    const int es = et == VU_SLAB_F32 ? 4 : 2, per16 = 16 / es;
     // bulk copies need 16-byte aligned rows and sizes
-    if ((uintptr_t)s.data % 16 || s.V % 4 || (!s.member_ptrs && s.stride_p % 4) || s.stride_b % 4 || s.stride_c % 4) return 1;
+    if ((uintptr_t)s.data % 16 || s.V % per16 || (!s.member_ptrs && s.stride_p % per16) || s.stride_b % per16 || s.stride_c % per16) return 1;
     if (s.member_ptrs_host)
         for (int64_t p = 0; p < s.P; ++p)
             if ((uintptr_t)s.member_ptrs_host[p] % 16) return 1;
@@ -194,8 +220,12 @@ int launch_k1_co_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t 
     // (whose per-thread columns and per-warp histograms share the shared memory with the ring)
     const bool stats = st.flags != 0;
     const int ct = (s.P <= 16 && !stats) ? 512 : 256;
-    Fn fn = stats ? (s.P <= 8 ? (Fn)k1_co_tma<8, 256, true> : (s.P <= 16 ? (Fn)k1_co_tma<16, 256, true> : (Fn)k1_co_tma<32, 256, true>))
-                  : (s.P <= 8 ? (Fn)k1_co_tma<8, 512, false> : (s.P <= 16 ? (Fn)k1_co_tma<16, 512, false> : (Fn)k1_co_tma<32, 256, false>));
+    auto pick = [&](auto et_tag) -> Fn {
+        constexpr int ET = decltype(et_tag)::value;
+        return stats ? (s.P <= 8 ? (Fn)k1_co_tma<8, 256, true, ET> : (s.P <= 16 ? (Fn)k1_co_tma<16, 256, true, ET> : (Fn)k1_co_tma<32, 256, true, ET>))
+                     : (s.P <= 8 ? (Fn)k1_co_tma<8, 512, false, ET> : (s.P <= 16 ? (Fn)k1_co_tma<16, 512, false, ET> : (Fn)k1_co_tma<32, 256, false, ET>));
+    };
+    Fn fn = et == VU_SLAB_F32 ? pick(std::integral_constant<int, 0>()) : (et == VU_SLAB_BF16 ? pick(std::integral_constant<int, 1>()) : pick(std::integral_constant<int, 2>()));
     K1CoParams prm;
     prm.st = st;
     prm.x = s.data; prm.mptr = s.member_ptrs;
@@ -206,7 +236,7 @@ int launch_k1_co_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t 
     prm.tiles_per_img = (s.V + tile_vox - 1) / tile_vox;
     prm.total_tiles = prm.tiles_per_img * s.B;
     if (prm.total_tiles >= (1LL << 31)) return set_error(VU_ERR_UNSUPPORTED, "more than 2^31 tiles in one launch; split the batch");
-    const size_t stage_bytes = (size_t)s.P * tile_vox * sizeof(float);
+    const size_t stage_bytes = (size_t)s.P * tile_vox * es;
     const size_t stats_bytes = stats ? (stats_smem_bytes(st.flags, st.gt.R, ct) + stats_class_bytes(st.flags, st.gt.R, st.ncls) + 127) / 128 * 128 : 0;
     const size_t budget = 225 * 1024 - 512;
     if (stats_bytes + 2 * stage_bytes > budget) return 1;

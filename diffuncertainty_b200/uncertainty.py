@@ -217,12 +217,18 @@ def _pointer_table(members, dev):
     return hit[0], hit[1]
 
 
-def fill_slab(slab: _lib.Slab, softmax_pred):
+_HALF = {torch.bfloat16: _lib.SLAB_BF16, torch.float16: _lib.SLAB_F16}
+
+
+def fill_slab(slab: _lib.Slab, softmax_pred, allow_half: bool = False):
     """Describe ``softmax_pred`` -- a (P, B, C, *S) tensor with any strides, or a list of P member tensors (B, C, *S)
     that are then read where they are (no torch.stack, test_2D.py:1277) -- in a vu_slab.  Returns
-    (P, B, C, spatial, device, keep-alive objects)."""
+    (P, B, C, spatial, device, keep-alive objects).
+    ``allow_half``: bfloat16 / float16 tensors are handed over as they are (vu_slab.dtype; the kernel widens the values as it
+    reads them) instead of being upcast to float32 first."""
     members = None
     draws, sflags, eps = 1, 0, 1e-12
+    sdtype = _lib.SLAB_F32
     if isinstance(softmax_pred, Groups):
         grp = softmax_pred
         if not grp.groups:
@@ -238,9 +244,13 @@ def fill_slab(slab: _lib.Slab, softmax_pred):
         softmax_pred = [g[d] for g in grp.groups for d in range(draws)]  # P * draws views, draw-minor
     if isinstance(softmax_pred, (list, tuple)):
         # P separate member tensors (B, C, *S): read where they are, no torch.stack
-        members = [m if m.dtype == torch.float32 else m.float() for m in softmax_pred]
-        if not members:
+        if not softmax_pred:
             raise ValueError("softmax_pred: empty member list")
+        d0 = softmax_pred[0].dtype
+        if allow_half and draws == 1 and d0 in _HALF and all(m.dtype == d0 for m in softmax_pred):
+            members, sdtype = list(softmax_pred), _HALF[d0]
+        else:
+            members = [m if m.dtype == torch.float32 else m.float() for m in softmax_pred]
         first = _members_view(members)
         if first.dim() < 3:
             raise ValueError(f"every member must be (B, C, *spatial), got shape {tuple(first.shape)}")
@@ -254,9 +264,11 @@ def fill_slab(slab: _lib.Slab, softmax_pred):
         _check_slab(softmax_pred, "softmax_pred")
         if softmax_pred.dim() < 4:
             raise ValueError(f"softmax_pred must be (P, B, C, *spatial), got shape {tuple(softmax_pred.shape)}")
-        if softmax_pred.dtype != torch.float32:
+        if allow_half and softmax_pred.dtype in _HALF:
+            sdtype = _HALF[softmax_pred.dtype]  # read as it is: half the HBM traffic, no upcast copy
+        elif softmax_pred.dtype != torch.float32:
             # the reference computes fp32 maps whatever the input dtype (test_utils.py:836);
-            # the kernels read fp32 only, so other dtypes are upcast once here
+            # the kernels compute in fp32, so other dtypes are upcast once here
             softmax_pred = softmax_pred.float()
         P, B, Cn = softmax_pred.shape[:3]
         spatial = tuple(softmax_pred.shape[3:])
@@ -271,6 +283,7 @@ def fill_slab(slab: _lib.Slab, softmax_pred):
     slab.stride_p, slab.stride_b, slab.stride_c = strides
     slab.stride_v = sv
     slab.draws, slab.flags, slab.renorm_eps, slab.stride_d = draws, sflags, eps, 0
+    slab.dtype = sdtype
     if members is not None:
         host_ptrs, dev_ptrs = _pointer_table(members, dev)
         slab.member_ptrs = dev_ptrs.data_ptr()
@@ -313,9 +326,11 @@ def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0
     a = _lib.FusedArgs()
     a.struct_size = C.sizeof(_lib.FusedArgs)
     a.stat_flags = int(stats)
-    P, B, Cn, spatial, dev, ptr_keep = fill_slab(a.slab, softmax_pred)
-    V = int(a.slab.V)
     logits = bool(logits) or (isinstance(softmax_pred, Groups) and softmax_pred.logits)
+    # bfloat16 / float16 slabs (autocast) are read as they are where the library can (plain slabs, 2..32 members, aligned rows)
+    half_ok = not logits and members_out is None and not want_member_labels and not isinstance(softmax_pred, Groups)
+    P, B, Cn, spatial, dev, ptr_keep = fill_slab(a.slab, softmax_pred, allow_half=half_ok)
+    V = int(a.slab.V)
     if logits and members_out is not None:
         raise NotImplementedError("member-level scores are not available for slabs of logits")
 
@@ -397,7 +412,12 @@ def fused_pass(softmax_pred, gt: Optional[GroundTruth] = None, *, stats: int = 0
         if logits:
             _lib.check(lib.vu_fused_pass_logits(C.byref(a), _lib.current_stream_ptr()), "vu_fused_pass_logits")
         else:
-            _lib.check(lib.vu_fused_pass(C.byref(a), _lib.current_stream_ptr()), "vu_fused_pass")
+            rc = lib.vu_fused_pass(C.byref(a), _lib.current_stream_ptr())
+            if rc == -2 and a.slab.dtype != _lib.SLAB_F32:
+                # this 16-bit slab has no native form (unaligned rows, P > 32, ...): upcast it once, as for any other dtype
+                P, B, Cn, spatial, dev, ptr_keep = fill_slab(a.slab, softmax_pred, allow_half=False)
+                rc = lib.vu_fused_pass(C.byref(a), _lib.current_stream_ptr())
+            _lib.check(rc, "vu_fused_pass")
     del keep, ptr_keep
     return FusedResult(maps=maps, labels=labels, stats_f64=sf, stats_i64=si, n_voxels=V,
                        n_raters=int(a.gt.R) if gt is not None else 0, stat_flags=int(stats), member_labels=member_labels,

@@ -129,7 +129,19 @@ typedef struct vu_slab {
     int32_t draws;
     uint32_t flags;
     float renorm_eps; /* test_2D.py:189: 1e-12 */
+    /* Element type of the slab.  VU_SLAB_F32 (0, the default): float32 as declared.  VU_SLAB_BF16 / VU_SLAB_F16: `data` (and
+     * every member pointer) addresses 16-bit elements -- what a network under autocast returns; strides stay in ELEMENTS.
+     * The kernel widens every value to float32 as it reads it (exact) and computes as for a float32 slab, so the results are
+     * those of the upcast slab bit for bit, at half the HBM traffic and without the upcast copy (the reference computes float32
+     * maps whatever the input dtype, test_utils.py:836; its own half-precision intermediate arithmetic is not reproduced).
+     * Available for plain slabs (no draws / producer flags / per-member labels / member scores) of 2..32 members with unit voxel
+     * stride and 16-byte aligned rows (V, strides multiples of 8); vu_fused_pass returns VU_ERR_UNSUPPORTED otherwise and the
+     * caller upcasts. */
+    int32_t dtype;
 } vu_slab;
+#define VU_SLAB_F32 0
+#define VU_SLAB_BF16 1
+#define VU_SLAB_F16 2
 #define VU_SLAB_RENORMALIZE 0x1u
 #define VU_SLAB_DISCRETIZE 0x2u
 #define VU_SLAB_LOGITS 0x4u
