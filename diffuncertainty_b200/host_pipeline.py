@@ -81,8 +81,11 @@ class HostResult:
 class HostPipeline:
     def __init__(self, P: int, C: int, spatial: Sequence[int], batch: int, R: int = 0, gt_dtype=torch.uint8,
                  chunk_images: int = 1, n_buffers: int = 3, stats: int = 0, thresholds: Optional[Sequence[float]] = None,
-                 platt=None, ignore_index: Optional[int] = None, device=None, logits: bool = False):
+                 platt=None, ignore_index: Optional[int] = None, device=None, logits: bool = False, dtype=torch.float32):
         _lib.require_device()
+        if dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            raise ValueError("dtype must be float32, bfloat16 or float16")
+        self.dtype = dtype  # element type of the host slab: 16-bit slabs cross PCIe and HBM at half the bytes (vu_slab.dtype)
         self.logits = bool(logits)  # the host slab holds network outputs before F.softmax (fused_pass(logits=True): opt-in)
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.P, self.C, self.spatial, self.B, self.R = P, C, tuple(spatial), batch, R
@@ -95,7 +98,7 @@ class HostPipeline:
         self.map_keys = UNC_KEYS if P > 1 else ("pred_entropy",)
         self._lib = _lib.load()
         with torch.cuda.device(self.dev):
-            self.d_slab = [torch.empty((P, self.chunk, C) + S, dtype=torch.float32, device=self.dev) for _ in range(n_buffers)]
+            self.d_slab = [torch.empty((P, self.chunk, C) + S, dtype=dtype, device=self.dev) for _ in range(n_buffers)]
             self.d_gt = [torch.empty((self.chunk, R) + S, dtype=gt_dtype, device=self.dev) for _ in range(n_buffers)] if R else None
             self.d_maps = [{k: torch.empty((self.chunk,) + S, dtype=torch.float32, device=self.dev) for k in self.map_keys}
                            for _ in range(n_buffers)]
@@ -109,14 +112,14 @@ class HostPipeline:
         self.h_rows_i = torch.empty((batch, I64["COLS"]), dtype=torch.int64).pin_memory()
 
     def run(self, x_host: torch.Tensor, gt_host: Optional[torch.Tensor] = None) -> HostResult:
-        """x_host: (P, B, C, *S) float32 host tensor (pinned for full speed); gt_host: (B, R, *S)."""
+        """x_host: (P, B, C, *S) host tensor of the pipeline's dtype (pinned for full speed); gt_host: (B, R, *S)."""
         P, B, nb, ch = self.P, self.B, self.nb, self.chunk
-        if tuple(x_host.shape) != (P, B, self.C) + self.spatial or x_host.dtype != torch.float32 or x_host.is_cuda:
-            raise ValueError("x_host must be a float32 host tensor of shape (P, B, C, *spatial)")
+        if tuple(x_host.shape) != (P, B, self.C) + self.spatial or x_host.dtype != self.dtype or x_host.is_cuda:
+            raise ValueError(f"x_host must be a {self.dtype} host tensor of shape (P, B, C, *spatial)")
         if self.R and (gt_host is None or tuple(gt_host.shape) != (B, self.R) + self.spatial):
             raise ValueError("gt_host must have shape (B, R, *spatial)")
         h2d = d2h = 0
-        img_bytes = self.C * int(np.prod(self.spatial)) * 4
+        img_bytes = self.C * int(np.prod(self.spatial)) * x_host.element_size()
         ev_in = [torch.cuda.Event() for _ in range(nb)]
         ev_run = [torch.cuda.Event() for _ in range(nb)]
         ev_out = [None] * nb

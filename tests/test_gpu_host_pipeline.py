@@ -51,3 +51,18 @@ def test_host_pipeline_equals_device_pass(vu, P, B, C, spatial, R, chunk, logits
         np.testing.assert_allclose(res.stats_f64, ref.stats_f64.cpu().numpy(), rtol=1e-9, atol=1e-12)
     assert res.h2d_bytes == x.numel() * 4 + (gt.numel() if R else 0)
     assert res.d2h_bytes >= B * int(np.prod(spatial)) * (4 * len(ref.maps) + 1)
+
+
+def test_host_pipeline_half_slab(vu):
+    """a bfloat16 host slab crosses PCIe and HBM at half the bytes and gives the maps of the upcast slab bit for bit"""
+    from diffuncertainty_b200.host_pipeline import HostPipeline
+    g = torch.Generator().manual_seed(11)
+    P, B, C, spatial = 8, 5, 19, (16, 64)
+    x = torch.softmax(3.0 * torch.randn(P, B, C, *spatial, generator=g), dim=2).to(torch.bfloat16).contiguous().pin_memory()
+    res = HostPipeline(P, C, spatial, B, chunk_images=2, dtype=torch.bfloat16).run(x)
+    ref = vu.fused_pass(x.cuda().float())
+    torch.cuda.synchronize()
+    for k in ref.maps:
+        assert torch.equal(res.maps[k].view(torch.int32), ref.maps[k].cpu().view(torch.int32)), k
+    assert torch.equal(res.labels, ref.labels.cpu())
+    assert res.h2d_bytes == x.numel() * 2
