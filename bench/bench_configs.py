@@ -90,6 +90,15 @@ def time_config(cid: int, iters: int = 10, peak: float = 6532.2, logits: bool = 
 
         stages["vu_patch_max_ws (TU, AU, EU in one call)"] = time_call(patch, iters=iters)
     if logits:
+        # the same launch with every member replaced by its one-hot argmax (--discretize, test_2D.py:1272-1275), read in place
+        grp = vu.Groups([x[p:p + 1] for p in range(P)], discretize=True)
+
+        def fused_onehot():
+            vu.fused_pass(grp, gt, stats=flags, thresholds=[0.3, 0.2, 0.02], calib=platt if flags & S.STAT_CALIB else None,
+                          stats_out=(sf, si), maps_out=maps, labels_out=labels)
+
+        stages["(vu_fused_pass, members discretised in the read)"] = time_call(fused_onehot, iters=iters)
+        del grp
         # the same launch over a slab of LOGITS (vu_fused_pass_logits: softmax folded into the read); log p are logits whose
         # softmax is p again, taken in place so that no second slab is resident
         x.clamp_(min=1e-30).log_()
@@ -108,6 +117,10 @@ def time_config(cid: int, iters: int = 10, peak: float = 6532.2, logits: bool = 
             "fused_pass_ms": round(fused_ms_only, 4), "fused_pass_GBps": round(bytes_alg / fused_ms_only / 1e6, 1),
             "fused_pass_frac": round(bytes_alg / fused_ms_only / 1e6 / peak, 3),
             "sample_voxels_per_s": round(P * V * B / total * 1e3, 1), "peak_GBps": peak}
+    oh = stages.get("(vu_fused_pass, members discretised in the read)")
+    if oh:
+        line["discretize_pass_ms"] = round(oh, 4)
+        line["discretize_pass_frac"] = round(bytes_alg / oh / 1e6 / peak, 3)
     lg = stages.get("(vu_fused_pass_logits, same launch over logits)")
     if lg:
         line["logits_pass_ms"] = round(lg, 4)

@@ -341,6 +341,25 @@ struct VoxelAcc {
         cascade_step(p);
     }
 
+    // a member that is replaced by the one-hot vector of its argmax (--discretize, test_2D.py:1272-1275: F.one_hot(argmax)): the
+    // member sum takes 1.0 at the label (first maximum, NaN is maximal: torch.argmax) and 0.0 elsewhere; its entropy term is 0
+    // (1 log 1, and the skipped 0 log 0 terms), so the entropy sums are not touched.  bi holds the member's label afterwards.
+    __device__ __forceinline__ void add_member_onehot(const f32x2 (&xp)[NP], float xs, long long p) {
+        member_argmax<0, C>(xp, xs);
+        if constexpr (VEC >= 2) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int q = 0; q < NH; ++q)
+                    m0[c * NH + q] = add2(m0[c * NH + q], pk2(bi[2 * q] == c ? 1.0f : 0.0f, bi[2 * q + 1] == c ? 1.0f : 0.0f));
+        } else {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) m0[j] = add2(m0[j], pk2(bi[0] == 2 * j ? 1.0f : 0.0f, bi[0] == 2 * j + 1 ? 1.0f : 0.0f));
+            if constexpr (ODD) m0s = __fadd_rn(m0s, bi[0] == C - 1 ? 1.0f : 0.0f);
+        }
+        cascade_step(p);
+    }
+
     static constexpr float kExactLo = 2.524354896707238e-29f;  // 2^-95
     static constexpr unsigned kExactLoBits = 0x10000000u;
     // mean (true division, test_2D.py:971), label, TU, AU, EU of the VEC voxels

@@ -636,8 +636,10 @@ int launch_k1(const vu_fused_args* a, const StatParams& st, cudaStream_t stream)
     prm.P = s.P; prm.B = s.B; prm.C = s.C; prm.V = s.V;
     prm.sp = s.stride_p; prm.sb = s.stride_b; prm.sc = s.stride_c; prm.sv = s.stride_v;
     prm.sd = s.stride_d; prm.draws = s.draws > 1 ? s.draws : 1; prm.sflags = s.flags; prm.renorm_eps = s.renorm_eps;
-    const bool lg = (s.flags & VU_SLAB_LOGITS) != 0;  // logits: TMA form or generic kernel
-    const bool produced = prm.draws > 1 || (s.flags & ~VU_SLAB_LOGITS);  // other upstream producers folded into the read: generic kernel
+    // plain logits or plain one-hot members (--discretize): TMA form or generic kernel; every other combination of the upstream
+    // producers (grouped draws, renormalisation): generic kernel
+    const bool lg = prm.draws <= 1 && (s.flags == VU_SLAB_LOGITS || s.flags == VU_SLAB_DISCRETIZE);
+    const bool produced = !lg && (prm.draws > 1 || s.flags != 0);
     prm.tu = a->tu; prm.au = a->au; prm.eu = a->eu; prm.lab = a->labels;
     prm.mlab = a->member_labels;
     prm.st = st;

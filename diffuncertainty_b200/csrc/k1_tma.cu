@@ -101,10 +101,12 @@ __device__ __forceinline__ void stat_warps_loop(const StatParams& st, void* st_s
 // ST statistics threads (0: a launch without statistics), SREP histogram replicas per statistics warp.
 // LG: the slab holds logits (VU_SLAB_LOGITS): every member is softmax'ed over its classes as it is consumed (whole members per
 // stage only: the maximum over all classes comes first).
-template <int C, int VEC, int LEVELS, int CT, int G, int NCH, int ST, int SREP, bool LG = false>
+// OH: every member is replaced by the one-hot vector of its argmax as it is consumed (VU_SLAB_DISCRETIZE, --discretize).
+template <int C, int VEC, int LEVELS, int CT, int G, int NCH, int ST, int SREP, bool LG = false, bool OH = false>
 __global__ void __launch_bounds__(CT + 32 + ST, 1) k1_tma(const __grid_constant__ K1TmaParams prm) {
     constexpr bool STATS = ST > 0;
-    static_assert(!LG || NCH == 1, "logits need whole members per stage");
+    static_assert(!(LG || OH) || NCH == 1, "logits / one-hot members need whole members per stage");
+    static_assert(!(LG && OH), "one producer per kernel");
     constexpr int kStatThreads = ST;
     static_assert(NCH == 1 || (NCH == 2 && G == 1 && VEC >= 2), "class chunks: one member per stage, VEC >= 2");
     constexpr int TV = CT * VEC;  // voxels per tile
@@ -250,7 +252,9 @@ __global__ void __launch_bounds__(CT + 32 + ST, 1) k1_tma(const __grid_constant_
                             for (int j = 0; j < Acc::NP; ++j) xp[j] = pk2(srow[(2 * j) * TV], srow[(2 * j + 1) * TV]);
                             if constexpr (Acc::ODD) xs = srow[(C - 1) * TV];
                         }
-                        if constexpr (LG) {
+                        if constexpr (OH) {
+                            acc.add_member_onehot(xp, xs, p0 + g);
+                        } else if constexpr (LG) {
                             f32x2 hm[Acc::NH], rs[Acc::NH];
                             float hs = 0.f;
                             auto reload = [&](int i) {
@@ -340,13 +344,16 @@ typedef void (*K1TmaKernel)(const K1TmaParams);
 struct TmaVariant {
     int C, VEC, LEVELS, CT, G, NCH, ST, SREP;
     int use;  // automatic selection: 0 = any launch, 1 = only launches with reference-based statistics on few-class slabs, -1 = never
-    int logits;  // 1: built for slabs of logits (VU_SLAB_LOGITS)
+    int logits;  // 1: built for slabs of logits (VU_SLAB_LOGITS), 2: for members replaced by their one-hot argmax (VU_SLAB_DISCRETIZE)
     K1TmaKernel fn, fn_stats;
 };
 #define VU_TMA_S(C, VEC, LEVELS, CT, G, NCH, ST, SREP, USE)                                                 \
     { C, VEC, LEVELS, CT, G, NCH, ST, SREP, USE, 0, (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, NCH, 0, 32>, \
       (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, NCH, ST, SREP> }
 #define VU_TMA(C, VEC, LEVELS, CT, G, NCH) VU_TMA_S(C, VEC, LEVELS, CT, G, NCH, 96, 32, 0)
+#define VU_TMA_OH(C, VEC, LEVELS, CT, G)                                                                            \
+    { C, VEC, LEVELS, CT, G, 1, 96, 32, 0, 2, (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, 1, 0, 32, false, true>,    \
+      (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, 1, 96, 32, false, true> }
 #define VU_TMA_LG(C, VEC, LEVELS, CT, G, USE)                                                                 \
     { C, VEC, LEVELS, CT, G, 1, 96, 32, USE, 1, (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, 1, 0, 32, true>,   \
       (K1TmaKernel)k1_tma<C, VEC, LEVELS, CT, G, 1, 96, 32, true> }
@@ -367,6 +374,11 @@ static const TmaVariant kTma[] = {
     VU_TMA_LG(3, 4, 1, 256, 2, 0),  VU_TMA_LG(3, 4, 2, 256, 2, 0),   // 18, 19
     VU_TMA_LG(4, 4, 1, 256, 2, 0),  VU_TMA_LG(4, 4, 2, 256, 2, 0),   // 20, 21
     VU_TMA_LG(19, 2, 1, 256, 1, -1), VU_TMA_LG(19, 2, 2, 256, 1, -1),  // 22, 23  (two voxels per thread, 8 consumer warps)
+    // members replaced by their one-hot argmax (--discretize): same stage shapes
+    VU_TMA_OH(19, 1, 1, 512, 1), VU_TMA_OH(19, 1, 2, 512, 1),  // 24, 25
+    VU_TMA_OH(2, 4, 1, 512, 2),  VU_TMA_OH(2, 4, 2, 512, 2),   // 26, 27
+    VU_TMA_OH(3, 4, 1, 256, 2),  VU_TMA_OH(3, 4, 2, 256, 2),   // 28, 29
+    VU_TMA_OH(4, 4, 1, 256, 2),  VU_TMA_OH(4, 4, 2, 256, 2),   // 30, 31
 };
 static const int kNumTma = (int)(sizeof(kTma) / sizeof(kTma[0]));
 
@@ -383,8 +395,9 @@ int launch_k1_tma(const vu_fused_args* a, const StatParams& st, cudaStream_t str
         for (int64_t p = 0; p < s.P; ++p)
             if ((uintptr_t)s.member_ptrs_host[p] % 16) return 1;
     const int need_levels = s.P <= 17 ? 1 : 2;
-    const int lg = (s.flags & VU_SLAB_LOGITS) ? 1 : 0;
-    if (s.draws > 1 || (s.flags & ~VU_SLAB_LOGITS)) return 1;  // grouped draws / renormalise / one-hot: generic kernel
+    // 0: probabilities as they are, 1: logits, 2: one-hot members; grouped draws, renormalisation and combinations: generic kernel
+    const int lg = s.flags == VU_SLAB_LOGITS ? 1 : (s.flags == VU_SLAB_DISCRETIZE ? 2 : 0);
+    if (s.draws > 1 || (s.flags && !lg)) return 1;
     const TmaVariant* pick = nullptr;
     if (forced >= 0 && forced < kNumTma) {
         const TmaVariant& f = kTma[forced];

@@ -53,10 +53,11 @@ constexpr int kUniRep = 16;  // histogram replicas per warp (two lanes share one
 // MSS >= 0: the member-level scores (GED counts, likelihood sums; members_fold.cuh) are computed in the same pass, with MSS
 // shuffle steps per member pair before the partial sums go to shared memory (MsGeom); MSS < 0: no member scores.
 // LG: the slab holds logits (VU_SLAB_LOGITS): every member is softmax'ed over its two classes as it is consumed.
-template <int LEVELS, int CT, int G, unsigned FL, int RMAX, int MINB, int MSS, bool LG = false>
+// OH: every member is replaced by the one-hot vector of its argmax (VU_SLAB_DISCRETIZE, --discretize).
+template <int LEVELS, int CT, int G, unsigned FL, int RMAX, int MINB, int MSS, bool LG = false, bool OH = false>
 __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ K1UniParams prm) {
     constexpr bool MS = MSS >= 0;
-    static_assert(!(MS && LG), "member scores are not available for slabs of logits");
+    static_assert(!(MS && (LG || OH)) && !(LG && OH), "member scores take the members as they are; one producer per kernel");
     constexpr int kMsS = MS ? MSS : 3;
     static_assert(!MS || RMAX == kMsR, "the member-score fold is built for up to four raters");
     constexpr int C = 2, VEC = 4;
@@ -234,7 +235,9 @@ __global__ void __launch_bounds__(CT + 32, MINB) k1_uni(const __grid_constant__ 
 #pragma unroll
                         for (int c = 0; c < C; ++c)
                             asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xp[c * 2]), "=l"(xp[c * 2 + 1]) : "r"(sbase + (unsigned)((g * C + c) * kRowBytes)));
-                        if constexpr (LG) {
+                        if constexpr (OH) {
+                            acc.add_member_onehot(xp, 0.f, p0 + g);
+                        } else if constexpr (LG) {
                             f32x2 hm[Acc::NH], rs[Acc::NH];
                             float xs = 0.f, hs = 0.f;
                             auto reload = [&](int i) {
@@ -300,13 +303,14 @@ struct UniVariant {
     int mss;  // ... with this many shuffle steps per member pair (MsGeom)
     K1UniKernel fn;
     K1UniKernel fn_logits;  // the same launch over a slab of logits (NULL: not built)
+    K1UniKernel fn_onehot;  // ... with the members replaced by their one-hot argmax (NULL: not built)
 };
 #define VU_UNI(LEVELS, CT, G, FL, RMAX, MINB, USE) \
-    { LEVELS, CT, G, FL, RMAX, MINB, USE, 0, -1, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX, MINB, -1>, nullptr }
+    { LEVELS, CT, G, FL, RMAX, MINB, USE, 0, -1, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX, MINB, -1>, nullptr, nullptr }
 #define VU_UNI_L(LEVELS, CT, G, FL, RMAX, MINB, USE)                                                    \
     { LEVELS, CT, G, FL, RMAX, MINB, USE, 0, -1, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX, MINB, -1>, \
-      (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX, MINB, -1, true> }
-#define VU_UNI_MS(LEVELS, CT, FL, MSS, USE) { LEVELS, CT, 2, FL, 4, 1, USE, 1, MSS, (K1UniKernel)k1_uni<LEVELS, CT, 2, FL, 4, 1, MSS>, nullptr }
+      (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX, MINB, -1, true>, (K1UniKernel)k1_uni<LEVELS, CT, G, FL, RMAX, MINB, -1, false, true> }
+#define VU_UNI_MS(LEVELS, CT, FL, MSS, USE) { LEVELS, CT, 2, FL, 4, 1, USE, 1, MSS, (K1UniKernel)k1_uni<LEVELS, CT, 2, FL, 4, 1, MSS>, nullptr, nullptr }
 // Registers are allocated per SM sub-partition: 16 consumer warps + the producer put 5 warps on one of them (96 registers per
 // thread), 15 + 1 leave 4 on each (128).  The masks with calibration histograms need the 128 (they spill 260-720 bytes at
 // 96); the others do not, and keep the power-of-two tile.
@@ -343,9 +347,9 @@ int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     const long long path = get_option("k1_path", 0);
     if (path == 1 || path == 2) return no("k1_path option excludes the unified kernel");  // 1 = register-streaming kernels only, 2 = warp-specialised TMA kernels only
     if (get_option("k1_tma_variant", -1) >= 0 || get_option("stats_path", 0) == 1) return no("tuning options exclude the unified kernel");
-    const bool lg = (s.flags & VU_SLAB_LOGITS) != 0;
-    if ((s.flags & ~VU_SLAB_LOGITS) || s.draws > 1) return no("the unified kernel takes the members as they are (no draws / producer flags)");
-    if (lg && want_ms) return no("member scores are not available for slabs of logits");
+    const bool lg = s.flags == VU_SLAB_LOGITS, oh = s.flags == VU_SLAB_DISCRETIZE;
+    if ((s.flags && !lg && !oh) || s.draws > 1) return no("the unified kernel takes plain members, logits or one-hot members (no draws / renormalisation)");
+    if ((lg || oh) && want_ms) return no("member scores take the members as they are");
     if (s.C != 2 || s.stride_v != 1 || s.P < 2 || s.P > 271 || !st.flags) return no("member scores in the fused pass need C == 2, unit voxel stride, a statistics mask");
     const unsigned heavy = VU_STAT_DICE | VU_STAT_CALIB | VU_STAT_NCC;
     if (!want_ms && !(st.flags & heavy) && path != 3) return 1;  // sums / thresholds / area only: the warp-specialised form is at the HBM roofline
@@ -373,7 +377,7 @@ int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     const long long shape = get_option("k1_uni_shape", 0);
     for (int i = 0; i < kNumUni && !pick; ++i) {
         const UniVariant& u = kUni[i];
-        if (u.LEVELS != need_levels || u.FL != st.flags || u.RMAX < rmax || (u.ms != 0) != want_ms || (lg && !u.fn_logits)) continue;
+        if (u.LEVELS != need_levels || u.FL != st.flags || u.RMAX < rmax || (u.ms != 0) != want_ms || (lg && !u.fn_logits) || (oh && !u.fn_onehot)) continue;
         const long long ushape = u.ms ? u.CT * 100 + u.G * 10 + u.mss : u.CT * 100 + u.G * 10 + u.MINB;
         if (shape ? ushape == shape : u.use == 1) pick = &u;
     }
@@ -422,7 +426,7 @@ int launch_k1_uni(const vu_fused_args* a, const StatParams& st, cudaStream_t str
     prm.ms_offset = (unsigned)(off + (stats2_smem_bytes(st.flags, pick->CT, kUniRep) + 15) / 16 * 16);
     const size_t dyn = off + stats_bytes;
 
-    const K1UniKernel fn = lg ? pick->fn_logits : pick->fn;
+    const K1UniKernel fn = lg ? pick->fn_logits : (oh ? pick->fn_onehot : pick->fn);
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
         return set_cuda_error("cudaFuncSetAttribute(k1_uni)");
     long long grid = (long long)device_sm_count() * pick->MINB;

@@ -80,3 +80,48 @@ def test_groups_contract(vu):
         vu.fused_pass(vu.Groups(x))     # torch.stack would refuse groups of different sizes as well
     with pytest.raises(ValueError):
         vu.fused_pass(vu.Groups([]))
+
+
+@pytest.mark.parametrize("P,B,C,spatial", [(10, 2, 19, (16, 64)), (32, 2, 2, (32, 32)), (5, 1, 3, (8, 64)), (18, 1, 4, (8, 32)),
+                                           (6, 1, 7, (8, 32)), (4, 1, 19, (5, 7))])
+def test_discretize_tma_form_equals_generic_and_oracle(vu, P, B, C, spatial):
+    """--discretize on plain members (one draw per group, the usual case): C = 2, 3, 4, 19 with aligned rows take the one-hot TMA
+    variants of k1_tma, everything else the generic kernel; same bits, and the reference's labels / maps."""
+    from diffuncertainty_b200 import _lib
+    from oracle import oracle
+    g = torch.Generator().manual_seed(P * 100 + C)
+    x = torch.softmax(3.0 * torch.randn(P, B, C, *spatial, generator=g), dim=2)
+    x[0, 0, 0, 0, :4] = x[0, 0, 1, 0, :4]          # ties: first maximum
+    x[1, 0, C - 1, 0, 4] = float("nan")            # NaN is maximal
+    groups = [x[p:p + 1].cuda() for p in range(P)]
+    before = _lib.get_counter("launches.k1_tma")
+    res = vu.fused_pass(vu.Groups(groups, discretize=True), want_member_labels=True)
+    fast = C in (2, 3, 4, 19) and int(np.prod(spatial)) % 4 == 0
+    assert _lib.get_counter("launches.k1_tma") == before + (1 if fast else 0)
+    _lib.load().vu_set_option(b"k1_variant", -2)
+    try:
+        gen = vu.fused_pass(vu.Groups(groups, discretize=True), want_member_labels=True)
+    finally:
+        _lib.load().vu_set_option(b"k1_variant", -1)
+    assert torch.equal(res.labels, gen.labels) and torch.equal(res.member_labels, gen.member_labels)
+    for k in ("TU", "AU", "EU"):
+        assert torch.equal(res.maps[k], gen.maps[k]), k   # (value equality: AU is -0.0 / +0.0)
+    torch.set_num_threads(1)
+    want = oracle.build_softmax_pred([x[p:p + 1] for p in range(P)], True)
+    for b in range(B):
+        ref = oracle.calculate_uncertainty(want[:, b])
+        assert torch.equal(res.labels[b].cpu(), want[:, b].mean(dim=0).argmax(dim=0).to(torch.uint8))
+        assert torch.equal(res.member_labels[:, b].cpu(), want[:, b].argmax(dim=1).to(torch.uint8))
+        for k in ("TU", "AU", "EU"):
+            np.testing.assert_allclose(res.maps[k][b].cpu().numpy(), ref[k].numpy(), rtol=1e-5, atol=1e-7)
+    # with statistics (Dice counts see the labels of the one-hot mean)
+    gt = torch.randint(0, C, (B, 2, *spatial), generator=g, dtype=torch.uint8).cuda()
+    fl = _lib.STAT_IMAGE_SUM | _lib.STAT_AREA | _lib.STAT_DICE
+    a = vu.fused_pass(vu.Groups(groups, discretize=True), vu.GroundTruth(gt, None), stats=fl)
+    _lib.load().vu_set_option(b"k1_variant", -2)
+    try:
+        c = vu.fused_pass(vu.Groups(groups, discretize=True), vu.GroundTruth(gt, None), stats=fl)
+    finally:
+        _lib.load().vu_set_option(b"k1_variant", -1)
+    assert torch.equal(a.stats_i64, c.stats_i64) and torch.equal(a.labels, c.labels)
+    np.testing.assert_allclose(a.stats_f64.cpu().numpy(), c.stats_f64.cpu().numpy(), rtol=1e-7, atol=1e-12)
